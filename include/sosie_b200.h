@@ -1,0 +1,160 @@
+/* sosie_b200.h -- C ABI of the B200-native replacement for SOSIE's horizontal-interpolation hot path.
+ *
+ * This is the drop-in boundary: exactly what the ISO_C_BINDING shim modules in
+ * sosie_b200/fortran/ (mod_bilin_2d, mod_akima_2d, mod_bdrown, mod_drown) bind to.  Each entry
+ * cites the reference interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions (same as the reference):
+ *   - every array is Fortran column-major, extents passed explicitly as int32;
+ *   - coordinates REAL(8), fields REAL(4), masks INTEGER(4) (INTEGER(1) for mod_drown);
+ *   - k_ew = -1: no east-west periodicity, >= 0: periodic with k_ew overlap points;
+ *   - longitudes in [0,360), NaN already replaced by -9999;
+ *   - return value: 0 = ok, non-zero = the condition on which the reference would PRINT+STOP
+ *     (sosie_last_error() gives the text; the Fortran shim prints it and STOPs);
+ *   - pointers are HOST pointers unless the entry name ends in _dev (device pointers, used by
+ *     callers that keep slabs resident in HBM; all _dev work is enqueued on the context stream);
+ *   - one host thread per context at a time (the reference is not re-entrant either).
+ *
+ * There is no CPU fallback: every entry fails with SOSIE_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SOSIE_B200_H
+#define SOSIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sosie_ctx sosie_ctx;
+
+enum {
+  SOSIE_OK = 0,
+  SOSIE_ERR_CUDA = 1,      /* CUDA runtime / no device                                            */
+  SOSIE_ERR_ARG = 2,       /* bad argument (shape mismatch: the reference's "do not agree" STOPs)  */
+  SOSIE_ERR_STATE = 3,     /* call order (apply before map/load)                                   */
+  SOSIE_ERR_REF_STOP = 4   /* a data condition on which the reference STOPs (see last_error)       */
+};
+
+/* ---- context ------------------------------------------------------------------------------ */
+int sosie_create(sosie_ctx** ctx, int device);
+int sosie_destroy(sosie_ctx* ctx);
+const char* sosie_last_error(const sosie_ctx* ctx);
+/* run everything on the caller's CUDA stream (a cudaStream_t passed as void*); NULL = own stream */
+int sosie_set_stream(sosie_ctx* ctx, void* cuda_stream);
+int sosie_sync(sosie_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t sosie_launch_count(const sosie_ctx* ctx);
+const char* sosie_version(void);
+
+/* ---- bilinear: grids -> mapping -> apply -------------------------------------------------------
+ * Replaces BILIN_2D / MAPPING_BL / INTERP_BL, src/mod_bilin_2d.f90:44-361,366-691, and the search
+ * FIND_NEAREST_POINT/_EASY/_TWISTED, src/mod_manip.f90:834-1440.
+ *
+ * sosie_bilin_set_grids: the coordinate part of BILIN_2D's prologue (:97-171): 1-D axes are kept
+ *   1-D on device (src_1d/trg_1d != 0 -> X is (nx), Y is (ny)), else (nx,ny) arrays; when
+ *   l_reg_src and the grid reaches the pole the two extra rows of EXT_NORTH_TO_90_REGG
+ *   (src/mod_manip.f90:1751-1839) are added.  mask_domain_trg may be NULL (all 1).
+ *   l_reg_src and i_orca_trg are the mod_conf globals the reference reads implicitly.            */
+int sosie_bilin_set_grids(sosie_ctx* ctx, int32_t k_ew_per,
+                          int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
+                          int32_t l_reg_src,
+                          int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d,
+                          const int32_t* mask_domain_trg, int32_t i_orca_trg);
+/* same with device-resident coordinates (borrowed until the next set_grids / destroy) */
+int sosie_bilin_set_grids_dev(sosie_ctx* ctx, int32_t k_ew_per,
+                              int32_t nx1, int32_t ny1, const double* dX10, const double* dY10, int32_t src_1d,
+                              int32_t l_reg_src,
+                              int32_t nx2, int32_t ny2, const double* dX20, const double* dY20, int32_t trg_1d,
+                              const int32_t* dmask_domain_trg, int32_t i_orca_trg);
+
+/* MAPPING_BL (:366-691): builds, on device, metrics(nx2,ny2,3)=(iP,jP,iqdrn), alphabeta(nx2,ny2,2),
+ * ID_problem(nx2,ny2) and distance_to_np(nx2,ny2), and keeps them cached in the context.          */
+int sosie_bilin_map(sosie_ctx* ctx);
+/* copy the cached mapping to host arrays (what P2D_MAPPING_AB, src/io_ezcdf.f90:2195, writes).
+ * Any pointer may be NULL.  mask_out receives mask_domain_trg as modified by the search (-1/-2). */
+int sosie_bilin_get_map(sosie_ctx* ctx, int32_t* metrics, double* alphabeta, int16_t* id_problem,
+                        float* dist_np, int32_t* mask_out);
+/* load a mapping read by RD_MAPPING_AB (src/io_ezcdf.f90:2280) instead of building it; may be called
+ * before or after sosie_bilin_set_grids (a set_grids with the same target extents keeps it).        */
+int sosie_bilin_load_map(sosie_ctx* ctx, int32_t nx2, int32_t ny2, const int32_t* metrics,
+                         const double* alphabeta, const int16_t* id_problem);
+/* search diagnostics: info[0..7] = j_strt_t, j_stop_t, jlat_icr, l_is_reg_s, l_is_reg_t,
+ * algorithm (0 EASY, 1 TWISTED), TWISTED chain iterations, l_add_extra_j                          */
+int sosie_bilin_map_info(sosie_ctx* ctx, int32_t* info);
+
+/* the apply loop of BILIN_2D (:209-263) for nslab source slabs Z1(nx1,ny1,nslab) ->
+ * Z2(nx2,ny2,nslab): identical-point copy, INTERP_BL with its error codes, pole rows of
+ * EXT_NORTH_TO_90_REGG recomputed per slab, ORCA last-row patch.  first_call: value of
+ * l_first_call_interp_routine for the first slab (evaluates l_last_y_row_missing, :241-247).      */
+int sosie_bilin_apply(sosie_ctx* ctx, int32_t nslab, const float* Z1, float* Z2, int32_t first_call);
+int sosie_bilin_apply_dev(sosie_ctx* ctx, int32_t nslab, const float* dZ1, float* dZ2, int32_t first_call);
+
+/* apply with the cheap per-record post-ops of INTERP_2D fused (src/mod_interp.f90:97-98,133-137):
+ * clamp to [vmin,vmax] when use_clamp, then rmiss_val where mask_trg == 0 when dmask_trg != NULL.  */
+int sosie_bilin_apply_ex_dev(sosie_ctx* ctx, int32_t nslab, const float* dZ1, float* dZ2, int32_t first_call,
+                             int32_t use_clamp, float vmin, float vmax, const int32_t* dmask_trg, float rmiss_val);
+
+/* apply to a (U,V) pair and rotate on the target grid in the same kernel (corr_vect,
+ * src/corr_vect.f90:622-624,630,632): Uo = REAL(cos*U2 + sin*V2,4), Vo = REAL(cos*V2 - sin*U2,4)
+ * with U2,V2 the interpolated slabs; xcos/xsin REAL(8)(nx2,ny2).                                   */
+int sosie_bilin_apply_uv_dev(sosie_ctx* ctx, int32_t nslab, const float* dU1, const float* dV1, float* dUo,
+                             float* dVo, const double* dxcos, const double* dxsin);
+
+/* one-call mirror of BILIN_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2, cnpat, mask_domain_trg)
+ * (src/mod_bilin_2d.f90:44): on *l_first_call != 0 sets the grids and builds the mapping (or uses the
+ * one given through sosie_bilin_load_map when have_mapping != 0), applies it, and clears
+ * *l_first_call exactly as :267 does.  Host pointers.                                              */
+int sosie_bilin_2d(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t ny1, const double* X10,
+                   const double* Y10, int32_t src_1d, const float* Z1, int32_t nx2, int32_t ny2,
+                   const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
+                   const int32_t* mask_domain_trg, int32_t l_reg_src, int32_t i_orca_trg,
+                   int32_t* l_first_call, int32_t have_mapping, int32_t nslab);
+
+/* scalar INTERP_BL(k_ew_per, jiP, jjP, iqd, xa, xb, Z_in) for n trajectory points
+ * (src/mod_bilin_2d.f90:275; callers src/interp_to_ground_track.f90:750): host pointers.           */
+int sosie_interp_bl(sosie_ctx* ctx, int32_t k_ew_per, int32_t nxi, int32_t nyi, const float* Z_in, int32_t n,
+                    const int32_t* jiP, const int32_t* jjP, const int32_t* iqd, const double* xa,
+                    const double* xb, float* out);
+
+/* ---- Akima 2D ------------------------------------------------------------------------------------
+ * Replaces AKIMA_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2, icall), src/mod_akima_2d.f90:59-239
+ * (FILL_EXTRA_BANDS src/mod_manip.f90:69, SLOPES_AKIMA :483, build_pol :249, pol_val :445,
+ * find_nearest_akima :670).  i_orca_src is the mod_conf global read at :168.                       */
+int sosie_akima_set_grids(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t ny1, const double* X10,
+                          const double* Y10, int32_t src_1d, int32_t i_orca_src, int32_t nx2, int32_t ny2,
+                          const double* X20, const double* Y20, int32_t trg_1d);
+int sosie_akima_apply(sosie_ctx* ctx, int32_t nslab, const float* Z1, float* Z2);
+int sosie_akima_apply_dev(sosie_ctx* ctx, int32_t nslab, const float* dZ1, float* dZ2);
+/* the SAVE'd ixy_pos(nx2,ny2,2) table (src/mod_akima_2d.f90:41) */
+int sosie_akima_get_ixy(sosie_ctx* ctx, int32_t* ixy_pos);
+
+/* ---- BDROWN / SMOOTHER (src/mod_bdrown.f90:18-439, 444-608) --------------------------------------
+ * X(ni,nj,nslab) in place; mask(ni,nj) shared by all slabs, or (ni,nj,nslab) when mask_per_slab.
+ * nsweeps (nullable) receives the number of incursion sweeps actually executed per slab
+ * (the device-side "any land left" flag replacing ANY(maskv==0), :125).                           */
+int sosie_bdrown(sosie_ctx* ctx, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X,
+                 const int32_t* mask, int32_t mask_per_slab, int32_t nb_inc, int32_t nb_smooth, float pmin,
+                 float pmax, float pval_land, int32_t* nsweeps);
+int sosie_bdrown_dev(sosie_ctx* ctx, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* dX,
+                     const int32_t* dmask, int32_t mask_per_slab, int32_t nb_inc, int32_t nb_smooth,
+                     float pmin, float pmax, float pval_land, int32_t* nsweeps_host);
+/* SMOOTHER(k_ew, X, nb_smooth, msk, l_exclude_mask_points): msk may be NULL; l_emp mirrors
+ * PRESENT(l_exclude_mask_points) (presence, not value: :496).                                      */
+int sosie_smoother(sosie_ctx* ctx, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X,
+                   int32_t nb_smooth, const int32_t* msk, int32_t l_emp);
+
+/* ---- DROWN (Gaussian), src/mod_drown.f90:18-198: mask is INTEGER(1) ------------------------------ */
+int sosie_drown(sosie_ctx* ctx, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X,
+                const int8_t* mask, int32_t nb_inc, int32_t* nsweeps);
+
+/* ---- vector rotation alone, src/corr_vect.f90:622-624 (inverse != 0: :963,970) ------------------- */
+int sosie_rotate_uv(sosie_ctx* ctx, int64_t n, int32_t nslab, const float* U, const float* V,
+                    const double* xcos, const double* xsin, float* Uo, float* Vo, int32_t inverse);
+int sosie_rotate_uv_dev(sosie_ctx* ctx, int64_t n, int32_t nslab, const float* dU, const float* dV,
+                        const double* dxcos, const double* dxsin, float* dUo, float* dVo, int32_t inverse);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOSIE_B200_H */

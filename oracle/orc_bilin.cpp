@@ -903,9 +903,11 @@ int orc_bilin_2d(int k_ew_per, int nx1, int ny1, const double* X10, const double
     }
     A2<float> Z2a(Z2s, nx2, ny2);
     for (int64_t k = 0; k < n2; k++) Z2s[k] = (float)rmv;
-    // IMETRICS(:,:,1:2) = MAX(IMETRICS(:,:,1:2), 1)   (:217) -- modifies the SAVE'd array
-    for (int64_t k = 0; k < 2 * n2; k++) metrics[k] = std::max(metrics[k], 1);
-    A3<int32_t> IM(metrics, nx2, ny2, 3);
+    // IMETRICS(:,:,1:2) = MAX(IMETRICS(:,:,1:2), 1)   (:217) -- the reference clamps its SAVE'd copy (read back
+    // from the mapping file); the caller's `metrics` keeps what MAPPING_BL wrote to the file.
+    std::vector<int32_t> imv(metrics, metrics + 3 * n2);
+    for (int64_t k = 0; k < 2 * n2; k++) imv[k] = std::max(imv[k], 1);
+    A3<int32_t> IM(imv.data(), nx2, ny2, 3);
     A3<double> RAB(alphabeta, nx2, ny2, 2);
     A2<const float> Z1wc(Z1wv.data(), nx1, ny1w);
     for (int jj = 1; jj <= ny2; jj++)

@@ -1,0 +1,314 @@
+"""sosie_b200 -- B200-native (sm_100a) replacement for SOSIE's horizontal-interpolation hot path.
+
+The product is the C-ABI shared library ``libsosie_b200.so`` (include/sosie_b200.h): hand-written CUDA
+kernels behind the entry points the reference's Fortran modules would bind through ISO_C_BINDING
+(sosie_b200/fortran/).  This Python package is only a thin ctypes mirror of that ABI, used by the
+tests and by bench.py; names and argument meaning follow the reference routines:
+
+    BILIN_2D / MAPPING_BL / INTERP_BL   src/mod_bilin_2d.f90:44,366,275
+    AKIMA_2D                            src/mod_akima_2d.f90:59
+    BDROWN / SMOOTHER                   src/mod_bdrown.f90:18,444
+    DROWN                               src/mod_drown.f90:18
+    vector rotation                     src/corr_vect.f90:622-624
+
+There is NO CPU fallback: if the library is missing or no CUDA device is usable, every call raises.
+Array convention: Fortran (ni,nj) column-major == numpy shape (nj,ni) C-contiguous.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+__all__ = ["Sosie", "SosieError", "lib_path", "load_library", "EXPORTS"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "_build", "libsosie_b200.so")
+
+
+# every symbol include/sosie_b200.h declares (tests check the library exports all of them)
+EXPORTS = [
+    "sosie_create", "sosie_destroy", "sosie_last_error", "sosie_set_stream", "sosie_sync", "sosie_launch_count",
+    "sosie_version", "sosie_bilin_set_grids", "sosie_bilin_set_grids_dev", "sosie_bilin_map", "sosie_bilin_get_map",
+    "sosie_bilin_load_map", "sosie_bilin_map_info", "sosie_bilin_apply", "sosie_bilin_apply_dev", "sosie_bilin_apply_ex_dev",
+    "sosie_bilin_apply_uv_dev", "sosie_bilin_2d", "sosie_interp_bl", "sosie_akima_set_grids", "sosie_akima_apply",
+    "sosie_akima_apply_dev", "sosie_akima_get_ixy", "sosie_bdrown", "sosie_bdrown_dev", "sosie_smoother", "sosie_drown",
+    "sosie_rotate_uv", "sosie_rotate_uv_dev",
+]
+
+_lib = None
+
+
+class SosieError(RuntimeError):
+    pass
+
+
+def load_library():
+    """dlopen libsosie_b200.so.  Raises if it has not been built (python -m sosie_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not os.path.exists(p):
+        raise SosieError(f"{p} is missing: build it with `python -m sosie_b200.build` (nvcc, sm_100a). "
+                         "There is no CPU fallback.")
+    lib = C.CDLL(p)
+    lib.sosie_last_error.restype = C.c_char_p
+    lib.sosie_version.restype = C.c_char_p
+    lib.sosie_launch_count.restype = C.c_int64
+    lib.sosie_launch_count.argtypes = [C.c_void_p]
+    lib.sosie_last_error.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _dp(t):
+    """raw device pointer of a torch CUDA tensor (or an int already)"""
+    if t is None:
+        return None
+    if isinstance(t, int):
+        return C.c_void_p(t)
+    return C.c_void_p(t.data_ptr())
+
+
+class Sosie:
+    """One GPU context (opaque ``sosie_ctx``): owns the device copies of the grids, the cached mapping
+    (the reference's SAVE'd RAB/IMETRICS/IPB, src/mod_bilin_2d.f90:22-24) and the work buffers."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.sosie_create(C.byref(h), int(device))
+        if rc != 0:
+            raise SosieError(f"sosie_create(device={device}) failed with code {rc}: no usable CUDA device "
+                             "(this library has no CPU fallback)")
+        self._h = h
+        self.device = device
+        self.l_first_call_interp_routine = True   # the mod_conf global (src/mod_conf.f90:13)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.sosie_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            msg = self._lib.sosie_last_error(self._h)
+            raise SosieError(f"sosie_b200 error {rc}: {msg.decode() if msg else ''}")
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self._lib.sosie_set_stream(self._h, C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None))
+
+    def sync(self):
+        self._ck(self._lib.sosie_sync(self._h))
+
+    @property
+    def launches(self) -> int:
+        return int(self._lib.sosie_launch_count(self._h))
+
+    # ---------------------------------------------------------------- bilinear
+    def bilin_set_grids(self, k_ew_per, X10, Y10, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0):
+        X10, Y10, X20, Y20 = _f64(X10), _f64(Y10), _f64(X20), _f64(Y20)
+        src_1d, trg_1d = X10.ndim == 1, X20.ndim == 1
+        nx1, ny1 = (X10.size, Y10.size) if src_1d else (X10.shape[1], X10.shape[0])
+        nx2, ny2 = (X20.size, Y20.size) if trg_1d else (X20.shape[1], X20.shape[0])
+        m = None if mask_domain_trg is None else _i32(mask_domain_trg)
+        self._shape = (nx1, ny1, nx2, ny2)
+        self._ck(self._lib.sosie_bilin_set_grids(self._h, int(k_ew_per), nx1, ny1, _p(X10), _p(Y10), int(src_1d), int(l_reg_src),
+                                                 nx2, ny2, _p(X20), _p(Y20), int(trg_1d), _p(m), int(i_orca_trg)))
+
+    def bilin_set_grids_dev(self, k_ew_per, nx1, ny1, dX10, dY10, src_1d, nx2, ny2, dX20, dY20, trg_1d, dmask=None,
+                            l_reg_src=False, i_orca_trg=0):
+        self._shape = (nx1, ny1, nx2, ny2)
+        self._keep = (dX10, dY10, dX20, dY20, dmask)   # borrowed by the library: keep alive
+        self._ck(self._lib.sosie_bilin_set_grids_dev(self._h, int(k_ew_per), nx1, ny1, _dp(dX10), _dp(dY10), int(src_1d),
+                                                     int(l_reg_src), nx2, ny2, _dp(dX20), _dp(dY20), int(trg_1d), _dp(dmask),
+                                                     int(i_orca_trg)))
+
+    def bilin_map(self):
+        """MAPPING_BL on device."""
+        self._ck(self._lib.sosie_bilin_map(self._h))
+
+    def bilin_get_map(self):
+        nx1, ny1, nx2, ny2 = self._shape
+        met = np.empty((3, ny2, nx2), np.int32)
+        ab = np.empty((2, ny2, nx2), np.float64)
+        ipb = np.empty((ny2, nx2), np.int16)
+        dnp = np.empty((ny2, nx2), np.float32)
+        msk = np.empty((ny2, nx2), np.int32)
+        self._ck(self._lib.sosie_bilin_get_map(self._h, _p(met), _p(ab), _p(ipb), _p(dnp), _p(msk)))
+        info = np.zeros(8, np.int32)
+        self._ck(self._lib.sosie_bilin_map_info(self._h, _p(info)))
+        return dict(metrics=met, alphabeta=ab, ipb=ipb, dist_np=dnp, mask=msk, info=info)
+
+    def bilin_load_map(self, metrics, alphabeta, ipb=None):
+        met, ab = _i32(metrics), _f64(alphabeta)
+        ny2, nx2 = met.shape[1], met.shape[2]
+        ip = None if ipb is None else np.ascontiguousarray(ipb, np.int16)
+        self._ck(self._lib.sosie_bilin_load_map(self._h, nx2, ny2, _p(met), _p(ab), _p(ip)))
+
+    def bilin_apply(self, Z1, first_call=False):
+        Z1 = _f32(Z1)
+        if Z1.ndim == 2:
+            Z1 = Z1[None]
+        nx1, ny1, nx2, ny2 = self._shape
+        assert Z1.shape[1:] == (ny1, nx1), (Z1.shape, self._shape)
+        Z2 = np.empty((Z1.shape[0], ny2, nx2), np.float32)
+        self._ck(self._lib.sosie_bilin_apply(self._h, Z1.shape[0], _p(Z1), _p(Z2), int(first_call)))
+        return Z2
+
+    def bilin_apply_dev(self, nslab, dZ1, dZ2, first_call=False):
+        self._ck(self._lib.sosie_bilin_apply_dev(self._h, int(nslab), _dp(dZ1), _dp(dZ2), int(first_call)))
+
+    def bilin_apply_ex_dev(self, nslab, dZ1, dZ2, first_call=False, clamp=None, dmask_trg=None, rmiss_val=-9999.0):
+        use = clamp is not None
+        vmin, vmax = clamp if use else (0.0, 0.0)
+        self._ck(self._lib.sosie_bilin_apply_ex_dev(self._h, int(nslab), _dp(dZ1), _dp(dZ2), int(first_call), int(use),
+                                                    C.c_float(vmin), C.c_float(vmax), _dp(dmask_trg), C.c_float(rmiss_val)))
+
+    def bilin_apply_uv_dev(self, nslab, dU1, dV1, dUo, dVo, dcos, dsin):
+        self._ck(self._lib.sosie_bilin_apply_uv_dev(self._h, int(nslab), _dp(dU1), _dp(dV1), _dp(dUo), _dp(dVo), _dp(dcos), _dp(dsin)))
+
+    def bilin_2d(self, k_ew_per, X10, Y10, Z1, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0, have_mapping=False):
+        """BILIN_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2, cnpat, mask_domain_trg): builds the mapping on the
+        first call (l_first_call_interp_routine), applies it to every slab of Z1."""
+        X10, Y10, X20, Y20 = _f64(X10), _f64(Y10), _f64(X20), _f64(Y20)
+        Z1 = _f32(Z1)
+        if Z1.ndim == 2:
+            Z1 = Z1[None]
+        src_1d, trg_1d = X10.ndim == 1, X20.ndim == 1
+        nx1, ny1 = (X10.size, Y10.size) if src_1d else (X10.shape[1], X10.shape[0])
+        nx2, ny2 = (X20.size, Y20.size) if trg_1d else (X20.shape[1], X20.shape[0])
+        self._shape = (nx1, ny1, nx2, ny2)
+        m = None if mask_domain_trg is None else _i32(mask_domain_trg)
+        Z2 = np.empty((Z1.shape[0], ny2, nx2), np.float32)
+        first = C.c_int32(1 if self.l_first_call_interp_routine else 0)
+        self._ck(self._lib.sosie_bilin_2d(self._h, int(k_ew_per), nx1, ny1, _p(X10), _p(Y10), int(src_1d), _p(Z1), nx2, ny2,
+                                          _p(X20), _p(Y20), int(trg_1d), _p(Z2), _p(m), int(l_reg_src), int(i_orca_trg),
+                                          C.byref(first), int(have_mapping), Z1.shape[0]))
+        self.l_first_call_interp_routine = bool(first.value)
+        return Z2
+
+    def interp_bl(self, k_ew_per, jiP, jjP, iqd, xa, xb, Z_in):
+        Z = _f32(Z_in)
+        ji, jj, iq = _i32(np.atleast_1d(jiP)), _i32(np.atleast_1d(jjP)), _i32(np.atleast_1d(iqd))
+        a, b = _f64(np.atleast_1d(xa)), _f64(np.atleast_1d(xb))
+        out = np.empty(ji.size, np.float32)
+        self._ck(self._lib.sosie_interp_bl(self._h, int(k_ew_per), Z.shape[1], Z.shape[0], _p(Z), ji.size, _p(ji), _p(jj), _p(iq),
+                                           _p(a), _p(b), _p(out)))
+        return out
+
+    # ---------------------------------------------------------------- akima
+    def akima_set_grids(self, k_ew_per, X10, Y10, X20, Y20, i_orca_src=0):
+        X10, Y10, X20, Y20 = _f64(X10), _f64(Y10), _f64(X20), _f64(Y20)
+        src_1d, trg_1d = X10.ndim == 1, X20.ndim == 1
+        nx1, ny1 = (X10.size, Y10.size) if src_1d else (X10.shape[1], X10.shape[0])
+        nx2, ny2 = (X20.size, Y20.size) if trg_1d else (X20.shape[1], X20.shape[0])
+        self._ashape = (nx1, ny1, nx2, ny2)
+        self._ck(self._lib.sosie_akima_set_grids(self._h, int(k_ew_per), nx1, ny1, _p(X10), _p(Y10), int(src_1d), int(i_orca_src),
+                                                 nx2, ny2, _p(X20), _p(Y20), int(trg_1d)))
+
+    def akima_apply(self, Z1):
+        Z1 = _f32(Z1)
+        if Z1.ndim == 2:
+            Z1 = Z1[None]
+        nx1, ny1, nx2, ny2 = self._ashape
+        assert Z1.shape[1:] == (ny1, nx1)
+        Z2 = np.empty((Z1.shape[0], ny2, nx2), np.float32)
+        self._ck(self._lib.sosie_akima_apply(self._h, Z1.shape[0], _p(Z1), _p(Z2)))
+        return Z2
+
+    def akima_apply_dev(self, nslab, dZ1, dZ2):
+        self._ck(self._lib.sosie_akima_apply_dev(self._h, int(nslab), _dp(dZ1), _dp(dZ2)))
+
+    def akima_get_ixy(self):
+        nx1, ny1, nx2, ny2 = self._ashape
+        ixy = np.empty((2, ny2, nx2), np.int32)
+        self._ck(self._lib.sosie_akima_get_ixy(self._h, _p(ixy)))
+        return ixy
+
+    def akima_2d(self, k_ew_per, X10, Y10, Z1, X20, Y20, i_orca_src=0):
+        """AKIMA_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2)"""
+        self.akima_set_grids(k_ew_per, X10, Y10, X20, Y20, i_orca_src)
+        return self.akima_apply(Z1)
+
+    # ---------------------------------------------------------------- drown / smoother / rotation
+    def bdrown(self, k_ew, X, mask, nb_inc=200, nb_smooth=0, pmin=-1.0e24, pmax=1.0e24, pval_land=0.0):
+        """BDROWN(k_ew, X, mask, nb_inc, nb_smooth, pmin, pmax, pval_land); returns (X_drowned, nsweeps)."""
+        X = _f32(X).copy()
+        sq = X.ndim == 2
+        if sq:
+            X = X[None]
+        nslab, nj, ni = X.shape
+        mask = _i32(mask)
+        per = mask.ndim == 3
+        nsw = np.zeros(nslab, np.int32)
+        self._ck(self._lib.sosie_bdrown(self._h, int(k_ew), ni, nj, nslab, _p(X), _p(mask), int(per), int(nb_inc), int(nb_smooth),
+                                        C.c_float(pmin), C.c_float(pmax), C.c_float(pval_land), _p(nsw)))
+        return (X[0] if sq else X), nsw
+
+    def bdrown_dev(self, k_ew, ni, nj, nslab, dX, dmask, mask_per_slab, nb_inc, nb_smooth, pmin, pmax, pval_land, want_nsweeps=False):
+        nsw = np.zeros(nslab, np.int32) if want_nsweeps else None
+        self._ck(self._lib.sosie_bdrown_dev(self._h, int(k_ew), ni, nj, nslab, _dp(dX), _dp(dmask), int(mask_per_slab), int(nb_inc),
+                                            int(nb_smooth), C.c_float(pmin), C.c_float(pmax), C.c_float(pval_land), _p(nsw)))
+        return nsw
+
+    def smoother(self, k_ew, X, nb_smooth=10, msk=None, l_exclude_mask_points=False):
+        X = _f32(X).copy()
+        sq = X.ndim == 2
+        if sq:
+            X = X[None]
+        nslab, nj, ni = X.shape
+        m = None if msk is None else _i32(msk)
+        self._ck(self._lib.sosie_smoother(self._h, int(k_ew), ni, nj, nslab, _p(X), int(nb_smooth), _p(m), int(l_exclude_mask_points)))
+        return X[0] if sq else X
+
+    def drown(self, k_ew, X, mask, nb_inc=200):
+        X = _f32(X).copy()
+        sq = X.ndim == 2
+        if sq:
+            X = X[None]
+        nslab, nj, ni = X.shape
+        mask = np.ascontiguousarray(mask, np.int8)
+        nsw = np.zeros(nslab, np.int32)
+        self._ck(self._lib.sosie_drown(self._h, int(k_ew), ni, nj, nslab, _p(X), _p(mask), int(nb_inc), _p(nsw)))
+        return (X[0] if sq else X), nsw
+
+    def rotate_uv(self, U, V, xcos, xsin, inverse=False):
+        U, V = _f32(U), _f32(V)
+        xcos, xsin = _f64(xcos), _f64(xsin)
+        n = xcos.size
+        nslab = U.size // n
+        Uo, Vo = np.empty_like(U), np.empty_like(V)
+        self._ck(self._lib.sosie_rotate_uv(self._h, C.c_int64(n), nslab, _p(U), _p(V), _p(xcos), _p(xsin), _p(Uo), _p(Vo), int(inverse)))
+        return Uo, Vo
+
+    def rotate_uv_dev(self, n, nslab, dU, dV, dcos, dsin, dUo, dVo, inverse=False):
+        self._ck(self._lib.sosie_rotate_uv_dev(self._h, C.c_int64(n), int(nslab), _dp(dU), _dp(dV), _dp(dcos), _dp(dsin), _dp(dUo),
+                                               _dp(dVo), int(inverse)))

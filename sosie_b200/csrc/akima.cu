@@ -1,0 +1,540 @@
+// akima.cu -- Akima 2-D bicubic interpolation on device.
+//
+// GPU counterpart of AKIMA_2D (src/mod_akima_2d.f90:59-239): FILL_EXTRA_BANDS (src/mod_manip.f90:69-305),
+// SLOPES_AKIMA (:483-664), build_pol (:249-441), pol_val (:445-480), find_nearest_akima (:670-745).
+// All arithmetic is REAL(8) in the reference's order (FMA contraction off) -> bit-identical output.
+//
+// Data flow per batch of slabs (everything stays in HBM/L2, slabs batched in grid.y):
+//   Z1 (f32) --frame--> zF (nx+4,ny+4) --frame--> ZF8 (nx+8,ny+8) --slopes--> sx,sy,sxy (nx+4,ny+4)
+//   target: cell index (cached ixy_pos) -> 16 coefficients recomputed in registers from the 4
+//   corner values/slopes (the reference materialises 128 B/cell; here 0 B) -> Horner -> f32.
+// Coordinate frames, the target->cell table and the source range are built once per grid pair.
+#include "geom.cuh"
+
+#define A2D(P, n1, i, j) (P)[(size_t)((i)-1) + (size_t)((j)-1) * (size_t)(n1)]
+
+__device__ __forceinline__ void d_extra_2_east(double x1, double x2, double x3, double x4, double x5, double y1, double y2,
+                                               double y3, double& y4, double& y5) {
+  double A = x2 - x1, B = x3 - x2, C = x4 - x3, D = x5 - x4;
+  double ALF = y2 - y1, BET = y3 - y2;
+  if ((A == 0.) || (B == 0.) || (C == 0.)) { y4 = y3; y5 = y3; }
+  else {
+    y4 = C * (2 * BET / B - ALF / A) + y3;
+    y5 = y4 + y4 * D / C + BET * D / B - ALF * D / A - y3 * D / C;
+  }
+}
+__device__ __forceinline__ void d_extra_2_west(double x5, double x4, double x3, double x2, double x1, double y5, double y4,
+                                               double y3, double& y2, double& y1) {
+  double A = x4 - x5, B = x3 - x4, C = x2 - x3, D = x1 - x2;
+  double ALF = y4 - y5, BET = y3 - y4;
+  if ((A == 0.) || (B == 0.) || (C == 0.)) { y2 = y3; y1 = y3; }
+  else {
+    y2 = C * (2 * BET / B - ALF / A) + y3;
+    y1 = y2 + y2 * D / C + BET * D / B - ALF * D / A - y3 * D / C;
+  }
+}
+
+// ---- FILL_EXTRA_BANDS, statement by statement (each kernel = one block of statements) ---------------
+// centre + zero init; src is f64 (nx,ny) or f32 (nx,ny) per slab (grid.y = slab)
+template <class TS>
+__global__ void k_feb_center(const TS* __restrict__ src, int nx, int ny, double* P, size_t src_stride, size_t dst_stride) {
+  const int nxp4 = nx + 4, nyp4 = ny + 4;
+  const TS* s = src + blockIdx.y * src_stride;
+  double* d = P + blockIdx.y * dst_stride;
+  size_t n = (size_t)nxp4 * nyp4;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(k / nxp4) + 1, i = (int)(k % nxp4) + 1;
+    double v = 0.0;
+    if (i >= 3 && i <= nxp4 - 2 && j >= 3 && j <= nyp4 - 2) v = (double)s[(size_t)(i - 3) + (size_t)(j - 3) * nx];
+    d[k] = v;
+  }
+}
+// X array: east-west columns on rows 3..nyp4-2 (:148-165)
+__global__ void k_feb_x_ew(double* XP4, int nx, int ny, int k_ew) {
+  const int nxp4 = nx + 4;
+  for (int jj = blockIdx.x * blockDim.x + threadIdx.x + 1; jj <= ny; jj += gridDim.x * blockDim.x) {
+    int r = jj + 2;
+#define XXc(i) A2D(XP4, nxp4, (i) + 2, r)
+    if (k_ew > -1) {
+      A2D(XP4, nxp4, 1, r) = XXc(nx - 1 - k_ew) - 360.;
+      A2D(XP4, nxp4, 2, r) = XXc(nx - k_ew) - 360.;
+      A2D(XP4, nxp4, nxp4, r) = XXc(2 + k_ew) + 360.;
+      A2D(XP4, nxp4, nxp4 - 1, r) = XXc(1 + k_ew) + 360.;
+    } else {
+      A2D(XP4, nxp4, 2, r) = XXc(2) - (XXc(3) - XXc(1));
+      A2D(XP4, nxp4, 1, r) = XXc(1) - (XXc(3) - XXc(1));
+      A2D(XP4, nxp4, nxp4 - 1, r) = XXc(nx - 1) + XXc(nx) - XXc(nx - 2);
+      A2D(XP4, nxp4, nxp4, r) = XXc(nx) + XXc(nx) - XXc(nx - 2);
+    }
+#undef XXc
+  }
+}
+// X array: southern rows (:172-173) and default northern rows (:192-193), all columns
+__global__ void k_feb_x_ns(double* XP4, int nxp4, int nyp4, int do_north) {
+  for (int ji = blockIdx.x * blockDim.x + threadIdx.x + 1; ji <= nxp4; ji += gridDim.x * blockDim.x) {
+    double a2 = A2D(XP4, nxp4, ji, 4) - (A2D(XP4, nxp4, ji, 5) - A2D(XP4, nxp4, ji, 3));
+    double a1 = A2D(XP4, nxp4, ji, 3) - (A2D(XP4, nxp4, ji, 5) - A2D(XP4, nxp4, ji, 3));
+    A2D(XP4, nxp4, ji, 2) = a2;
+    A2D(XP4, nxp4, ji, 1) = a1;
+    if (do_north) {
+      double b1 = A2D(XP4, nxp4, ji, nyp4 - 3) + A2D(XP4, nxp4, ji, nyp4 - 2) - A2D(XP4, nxp4, ji, nyp4 - 4);
+      double b2 = A2D(XP4, nxp4, ji, nyp4 - 2) + A2D(XP4, nxp4, ji, nyp4 - 2) - A2D(XP4, nxp4, ji, nyp4 - 4);
+      A2D(XP4, nxp4, ji, nyp4 - 1) = b1;
+      A2D(XP4, nxp4, ji, nyp4) = b2;
+    }
+  }
+}
+// Y array: default top (:215-216) and bottom (:221-222) on the centre columns
+__global__ void k_feb_y_tb(double* YP4, int nx, int ny, int do_top) {
+  const int nxp4 = nx + 4, nyp4 = ny + 4;
+  for (int ji = blockIdx.x * blockDim.x + threadIdx.x + 1; ji <= nx; ji += gridDim.x * blockDim.x) {
+    int c = ji + 2;
+#define YYc(j) A2D(YP4, nxp4, c, (j) + 2)
+    if (do_top) {
+      A2D(YP4, nxp4, c, nyp4 - 1) = YYc(ny - 1) + YYc(ny) - YYc(ny - 2);
+      A2D(YP4, nxp4, c, nyp4) = YYc(ny) + YYc(ny) - YYc(ny - 2);
+    }
+    A2D(YP4, nxp4, c, 2) = YYc(2) - (YYc(3) - YYc(1));
+    A2D(YP4, nxp4, c, 1) = YYc(1) - (YYc(3) - YYc(1));
+#undef YYc
+  }
+}
+// Y array: east-west columns, all rows (:224-239)
+__global__ void k_feb_y_ew(double* YP4, int nx, int ny, int k_ew) {
+  const int nxp4 = nx + 4, nyp4 = ny + 4;
+  for (int jj = blockIdx.x * blockDim.x + threadIdx.x + 1; jj <= nyp4; jj += gridDim.x * blockDim.x) {
+    if (k_ew > -1) {
+      double v1 = A2D(YP4, nxp4, nx - 1 - k_ew + 2, jj), v2 = A2D(YP4, nxp4, nx - k_ew + 2, jj);
+      double v3 = A2D(YP4, nxp4, 2 + k_ew + 2, jj), v4 = A2D(YP4, nxp4, 1 + k_ew + 2, jj);
+      A2D(YP4, nxp4, 1, jj) = v1;
+      A2D(YP4, nxp4, 2, jj) = v2;
+      A2D(YP4, nxp4, nxp4, jj) = v3;
+      A2D(YP4, nxp4, nxp4 - 1, jj) = v4;
+    } else {
+      A2D(YP4, nxp4, 2, jj) = A2D(YP4, nxp4, 4, jj) - (A2D(YP4, nxp4, 5, jj) - A2D(YP4, nxp4, 3, jj));
+      A2D(YP4, nxp4, 1, jj) = A2D(YP4, nxp4, 3, jj) - (A2D(YP4, nxp4, 5, jj) - A2D(YP4, nxp4, 3, jj));
+      A2D(YP4, nxp4, nxp4 - 1, jj) = A2D(YP4, nxp4, nxp4 - 3, jj) + A2D(YP4, nxp4, nxp4 - 2, jj) - A2D(YP4, nxp4, nxp4 - 4, jj);
+      A2D(YP4, nxp4, nxp4, jj) = A2D(YP4, nxp4, nxp4 - 2, jj) + A2D(YP4, nxp4, nxp4 - 2, jj) - A2D(YP4, nxp4, nxp4 - 4, jj);
+    }
+  }
+}
+// Data array: east-west columns on rows 3..nyp4-2 (:245-270); grid.y = slab
+__global__ void k_feb_f_ew(const double* __restrict__ XP4, double* FP4, int nx, int ny, int k_ew, size_t stride) {
+  const int nxp4 = nx + 4;
+  double* F = FP4 + blockIdx.y * stride;
+  for (int jj = blockIdx.x * blockDim.x + threadIdx.x + 3; jj <= ny + 2; jj += gridDim.x * blockDim.x) {
+    if (k_ew > -1) {
+      A2D(F, nxp4, 1, jj) = A2D(F, nxp4, nx - 1 - k_ew + 2, jj);
+      A2D(F, nxp4, 2, jj) = A2D(F, nxp4, nx - k_ew + 2, jj);
+      A2D(F, nxp4, nxp4, jj) = A2D(F, nxp4, 2 + k_ew + 2, jj);
+      A2D(F, nxp4, nxp4 - 1, jj) = A2D(F, nxp4, 1 + k_ew + 2, jj);
+    } else {
+      double y4, y5;
+      d_extra_2_east(A2D(XP4, nxp4, nxp4 - 4, jj), A2D(XP4, nxp4, nxp4 - 3, jj), A2D(XP4, nxp4, nxp4 - 2, jj),
+                     A2D(XP4, nxp4, nxp4 - 1, jj), A2D(XP4, nxp4, nxp4, jj), A2D(F, nxp4, nxp4 - 4, jj),
+                     A2D(F, nxp4, nxp4 - 3, jj), A2D(F, nxp4, nxp4 - 2, jj), y4, y5);
+      A2D(F, nxp4, nxp4 - 1, jj) = y4;
+      A2D(F, nxp4, nxp4, jj) = y5;
+      double y2, y1;
+      d_extra_2_west(A2D(XP4, nxp4, 5, jj), A2D(XP4, nxp4, 4, jj), A2D(XP4, nxp4, 3, jj), A2D(XP4, nxp4, 2, jj),
+                     A2D(XP4, nxp4, 1, jj), A2D(F, nxp4, 5, jj), A2D(F, nxp4, 4, jj), A2D(F, nxp4, 3, jj), y2, y1);
+      A2D(F, nxp4, 2, jj) = y2;
+      A2D(F, nxp4, 1, jj) = y1;
+    }
+  }
+}
+// Data array: default top (:288-294) and bottom (:297-303) per column; grid.y = slab
+__global__ void k_feb_f_tb(const double* __restrict__ YP4, double* FP4, int nxp4, int nyp4, int do_top, size_t stride) {
+  double* F = FP4 + blockIdx.y * stride;
+  for (int ji = blockIdx.x * blockDim.x + threadIdx.x + 1; ji <= nxp4; ji += gridDim.x * blockDim.x) {
+    if (do_top) {
+      double y4, y5;
+      d_extra_2_east(A2D(YP4, nxp4, ji, nyp4 - 4), A2D(YP4, nxp4, ji, nyp4 - 3), A2D(YP4, nxp4, ji, nyp4 - 2),
+                     A2D(YP4, nxp4, ji, nyp4 - 1), A2D(YP4, nxp4, ji, nyp4), A2D(F, nxp4, ji, nyp4 - 4),
+                     A2D(F, nxp4, ji, nyp4 - 3), A2D(F, nxp4, ji, nyp4 - 2), y4, y5);
+      A2D(F, nxp4, ji, nyp4 - 1) = y4;
+      A2D(F, nxp4, ji, nyp4) = y5;
+    }
+    double y2, y1;
+    d_extra_2_west(A2D(YP4, nxp4, ji, 5), A2D(YP4, nxp4, ji, 4), A2D(YP4, nxp4, ji, 3), A2D(YP4, nxp4, ji, 2),
+                   A2D(YP4, nxp4, ji, 1), A2D(F, nxp4, ji, 5), A2D(F, nxp4, ji, 4), A2D(F, nxp4, ji, 3), y2, y1);
+    A2D(F, nxp4, ji, 2) = y2;
+    A2D(F, nxp4, ji, 1) = y1;
+  }
+}
+// ORCA north-fold section copies (:181-190 etc.): P(l0+k*ls, jl) = P(r0+k*rs, jr); RHS staged first
+__global__ void k_sectd_read(const double* P, int n1, int n, int r0, int rs, int jr, double* tmp, size_t stride, int ntmp) {
+  const double* Q = P + blockIdx.y * stride;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    int ir = r0 + k * rs;
+    tmp[(size_t)blockIdx.y * ntmp + k] = (ir >= 1 && ir <= n1) ? A2D(Q, n1, ir, jr) : 0.0;
+  }
+}
+__global__ void k_sectd_write(double* P, int n1, int n, int l0, int ls, int jl, const double* tmp, size_t stride, int ntmp) {
+  double* Q = P + blockIdx.y * stride;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    A2D(Q, n1, l0 + k * ls, jl) = tmp[(size_t)blockIdx.y * ntmp + k];
+}
+
+// ---- SLOPES_AKIMA on the twice-extended arrays (:528-653); grid.y = slab -----------------------------
+__device__ __forceinline__ double d_guard(double rx) { return d_sign(1.0, rx) * fmax(fabs(rx), G_REPS); }
+
+__global__ void __launch_bounds__(128)
+k_slopes(const double* __restrict__ ZX, const double* __restrict__ ZY, const double* __restrict__ ZFb, int nx, int ny,
+         double* dFdX, double* dFdY, double* d2F, size_t zf_stride, size_t out_stride) {
+  const int n8 = nx + 4;  // leading dimension of the extended arrays (nx is already the frame-extended extent)
+  const double* ZF = ZFb + blockIdx.y * zf_stride;
+  double* ox = dFdX + blockIdx.y * out_stride;
+  double* oy = dFdY + blockIdx.y * out_stride;
+  double* oxy = d2F + blockIdx.y * out_stride;
+  size_t n = (size_t)nx * ny;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int jj = (int)(k / nx) + 1, ji = (int)(k % nx) + 1;
+    int ip1 = ji + 1, ip2 = ji + 2, jp1 = jj + 1, jp2 = jj + 2;
+    double m1, m2, m3, m4, Wx2 = 0., Wx3 = 0., Wy2 = 0., Wy3 = 0.;
+    m1 = (A2D(ZF, n8, ip1, jp2) - A2D(ZF, n8, ji, jp2)) / d_guard(A2D(ZX, n8, ip1, jp2) - A2D(ZX, n8, ji, jp2));
+    m2 = (A2D(ZF, n8, ip2, jp2) - A2D(ZF, n8, ip1, jp2)) / d_guard(A2D(ZX, n8, ip2, jp2) - A2D(ZX, n8, ip1, jp2));
+    m3 = (A2D(ZF, n8, ji + 3, jp2) - A2D(ZF, n8, ip2, jp2)) / d_guard(A2D(ZX, n8, ji + 3, jp2) - A2D(ZX, n8, ip2, jp2));
+    m4 = (A2D(ZF, n8, ji + 4, jp2) - A2D(ZF, n8, ji + 3, jp2)) / d_guard(A2D(ZX, n8, ji + 4, jp2) - A2D(ZX, n8, ji + 3, jp2));
+    double rx;
+    if ((m1 == m2) && (m3 == m4)) rx = 0.5 * (m2 + m3);
+    else {
+      Wx2 = fabs(m4 - m3);
+      Wx3 = fabs(m2 - m1);
+      rx = (Wx2 * m2 + Wx3 * m3) / (Wx2 + Wx3);
+    }
+    ox[k] = rx;
+    m1 = (A2D(ZF, n8, ip2, jp1) - A2D(ZF, n8, ip2, jj)) / d_guard(A2D(ZY, n8, ip2, jp1) - A2D(ZY, n8, ip2, jj));
+    m2 = (A2D(ZF, n8, ip2, jp2) - A2D(ZF, n8, ip2, jp1)) / d_guard(A2D(ZY, n8, ip2, jp2) - A2D(ZY, n8, ip2, jp1));
+    m3 = (A2D(ZF, n8, ip2, jj + 3) - A2D(ZF, n8, ip2, jp2)) / d_guard(A2D(ZY, n8, ip2, jj + 3) - A2D(ZY, n8, ip2, jp2));
+    m4 = (A2D(ZF, n8, ip2, jj + 4) - A2D(ZF, n8, ip2, jj + 3)) / d_guard(A2D(ZY, n8, ip2, jj + 4) - A2D(ZY, n8, ip2, jj + 3));
+    double ry;
+    if ((m1 == m2) && (m3 == m4)) ry = 0.5 * (m2 + m3);
+    else {
+      Wy2 = fabs(m4 - m3);
+      Wy3 = fabs(m2 - m1);
+      ry = (Wy2 * m2 + Wy3 * m3) / (Wy2 + Wy3);
+    }
+    oy[k] = ry;
+    double d22 = (A2D(ZF, n8, ip1, jp2) - A2D(ZF, n8, ip1, jp1)) / d_guard(A2D(ZY, n8, ip1, jp2) - A2D(ZY, n8, ip1, jp1));
+    double d23 = (A2D(ZF, n8, ip1, jj + 3) - A2D(ZF, n8, ip1, jp2)) / d_guard(A2D(ZY, n8, ip1, jj + 3) - A2D(ZY, n8, ip1, jp2));
+    double d42 = (A2D(ZF, n8, ji + 3, jp2) - A2D(ZF, n8, ji + 3, jp1)) / d_guard(A2D(ZY, n8, ji + 3, jp2) - A2D(ZY, n8, ji + 3, jp1));
+    double d43 = (A2D(ZF, n8, ji + 3, jj + 3) - A2D(ZF, n8, ji + 3, jp2)) / d_guard(A2D(ZY, n8, ji + 3, jj + 3) - A2D(ZY, n8, ji + 3, jp2));
+    double e22 = (m2 - d22) / d_guard(A2D(ZX, n8, ip2, jp1) - A2D(ZX, n8, ip1, jp1));
+    double e23 = (m3 - d23) / d_guard(A2D(ZX, n8, ip2, jp2) - A2D(ZX, n8, ip1, jp2));
+    double e32 = (d42 - m2) / d_guard(A2D(ZX, n8, ji + 3, jp2) - A2D(ZX, n8, ip2, jp2));
+    double e33 = (d43 - m3) / d_guard(A2D(ZX, n8, ji + 3, jp2) - A2D(ZX, n8, ip2, jp2));
+    if (((Wx2 == 0) && (Wx3 == 0)) || ((Wy2 == 0) && (Wy3 == 0))) {
+      if ((Wx2 == 0) && (Wx3 == 0)) { Wx2 = 1.; Wx3 = 1.; }
+      if ((Wy2 == 0) && (Wy3 == 0)) { Wy2 = 1.; Wy3 = 1.; }
+    }
+    oxy[k] = (Wx2 * (Wy2 * e22 + Wy3 * e23) + Wx3 * (Wy2 * e32 + Wy3 * e33)) / ((Wx2 + Wx3) * (Wy2 + Wy3));
+  }
+}
+
+// ---- find_nearest_akima (:670-745): literal state machine, one thread per target ---------------------
+__global__ void k_find_nearest_akima(const double* __restrict__ plon, const double* __restrict__ plat, int nxs, int nys,
+                                     double x0, double x1, double y0, double y1, const double* __restrict__ X2,
+                                     const double* __restrict__ Y2, size_t nt, int sorted, int32_t* ixy) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    double pxt = X2[k], pyt = Y2[k];
+    int jis = 0, jjs = 0;  // ixy_pos initialised to 0 (:196)
+    if (((pxt >= x0) && (pxt <= x1)) && ((pyt >= y0) && (pyt <= y1))) {
+      if (sorted) {
+        // separable, strictly increasing axes: "first jis with lon(jis) <= x < lon(jis+1), else nxs-1"
+        int lo = 0, hi = nxs;  // upper_bound on row 1
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (plon[mid] <= pxt) lo = mid + 1; else hi = mid; }
+        jis = lo;  // number of elements <= pxt (1-based index of the last one)
+        if (jis < 1 || jis >= nxs) jis = nxs - 1;
+        lo = 0; hi = nys;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (plat[(size_t)mid * nxs] <= pyt) lo = mid + 1; else hi = mid; }
+        jjs = lo;
+        if (jjs < 1 || jjs >= nys) jjs = nys - 1;
+      } else {
+        jis = 1; jjs = 1;
+        bool lx = false, ly = false;
+        while (!(lx && ly)) {
+          lx = false;
+          while (!lx) {
+            if (jis < nxs) {
+              if ((A2D(plon, nxs, jis, jjs) <= pxt) && (A2D(plon, nxs, jis + 1, jjs) > pxt)) lx = true;
+              else jis = jis + 1;
+            } else { jis = jis - 1; lx = true; }
+          }
+          ly = false;
+          while (!ly) {
+            if (jjs < nys) {
+              if ((A2D(plat, nxs, jis, jjs) <= pyt) && (A2D(plat, nxs, jis, jjs + 1) > pyt)) ly = true;
+              else { jjs = jjs + 1; lx = false; ly = true; }
+            } else { jjs = nys - 1; ly = true; }
+          }
+        }
+      }
+    }
+    ixy[k] = jis;
+    ixy[k + nt] = jjs;
+  }
+}
+// separable + strictly increasing check of the frame-extended coordinates
+__global__ void k_check_axes(const double* __restrict__ X, const double* __restrict__ Y, int nx, int ny, int* bad) {
+  size_t n = (size_t)nx * ny;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(k / nx), i = (int)(k % nx);
+    if (X[k] != X[i]) atomicOr(bad, 1);
+    if (Y[k] != Y[(size_t)j * nx]) atomicOr(bad, 1);
+    if (j == 0 && i > 0 && !(X[i] > X[i - 1])) atomicOr(bad, 1);
+    if (i == 0 && j > 0 && !(Y[k] > Y[k - nx])) atomicOr(bad, 1);
+  }
+}
+
+// ---- evaluation: build_pol (one cell, in registers) + pol_val; grid.y = slab ----------------------------
+__global__ void __launch_bounds__(128)
+k_akima_eval(const double* __restrict__ zX, const double* __restrict__ zY, const double* __restrict__ zFb,
+             const double* __restrict__ sxb, const double* __restrict__ syb, const double* __restrict__ sxyb, int ni1, int nj1,
+             const double* __restrict__ X2, const double* __restrict__ Y2, const int32_t* __restrict__ ixy, size_t nt, double x0,
+             double x1, double y0, double y1, float* Z2, size_t wstride) {
+  const double* ZF = zFb + blockIdx.y * wstride;
+  const double* sx = sxb + blockIdx.y * wstride;
+  const double* sy = syb + blockIdx.y * wstride;
+  const double* sxy = sxyb + blockIdx.y * wstride;
+  float* out = Z2 + blockIdx.y * nt;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    double px2 = X2[k], py2 = Y2[k];
+    float r = 0.f;
+    if (((px2 >= x0) && (px2 <= x1)) && ((py2 >= y0) && (py2 <= y1))) {
+      int ji = ixy[k], jj = ixy[k + nt];
+      px2 = px2 - A2D(zX, ni1, ji, jj);
+      py2 = py2 - A2D(zY, ni1, ji, jj);
+      double x = A2D(zX, ni1, ji + 1, jj) - A2D(zX, ni1, ji, jj);
+      double y = A2D(zY, ni1, ji, jj + 1) - A2D(zY, ni1, ji, jj);
+      double x2 = x * x, x3 = x2 * x, y2 = y * y, y3 = y2 * y, xy = x * y;
+      double b1 = A2D(ZF, ni1, ji, jj), b2 = A2D(ZF, ni1, ji + 1, jj), b3 = A2D(ZF, ni1, ji + 1, jj + 1), b4 = A2D(ZF, ni1, ji, jj + 1);
+      double b5 = A2D(sx, ni1, ji, jj), b6 = A2D(sx, ni1, ji + 1, jj), b7 = A2D(sx, ni1, ji + 1, jj + 1), b8 = A2D(sx, ni1, ji, jj + 1);
+      double b9 = A2D(sy, ni1, ji, jj), b10 = A2D(sy, ni1, ji + 1, jj), b11 = A2D(sy, ni1, ji + 1, jj + 1), b12 = A2D(sy, ni1, ji, jj + 1);
+      double b13 = A2D(sxy, ni1, ji, jj), b14 = A2D(sxy, ni1, ji + 1, jj), b15 = A2D(sxy, ni1, ji + 1, jj + 1), b16 = A2D(sxy, ni1, ji, jj + 1);
+      double V11 = b13, V12 = b5, V15 = b9, V16 = b1;
+      b5 = x * b5; b6 = x * b6; b7 = x * b7; b8 = x * b8;
+      b9 = y * b9; b10 = y * b10; b11 = y * b11; b12 = y * b12;
+      b13 = xy * b13; b14 = xy * b14; b15 = xy * b15; b16 = xy * b16;
+      double c1 = b1 - b2, c2 = b3 - b4, c3 = b5 + b6, c4 = b7 + b8, c5 = b9 - b10, c6 = b11 - b12;
+      double c7 = b13 + b14, c8 = b15 + b16, c9 = 2 * b5 + b6, c10 = b7 + 2 * b8, c11 = 2 * b13 + b14;
+      double c12 = b15 + 2 * b16, c13 = b5 - b8, c14 = b1 - b4, c15 = b13 + b16, c16 = 2 * b13 + b16;
+      double c17 = b9 + b12, c18 = 2 * b9 + b12;
+      double d1 = c1 + c2, d2 = c3 - c4, d3 = c5 - c6, d4 = c7 + c8, d5 = c9 - c10, d6 = 2 * c5 - c6;
+      double d7 = 2 * c7 + c8, d8 = c11 + c12, d9 = 2 * c11 + c12;
+      double f1 = 2 * d1 + d2, f2 = 2 * d3 + d4, f3 = 2 * d6 + d7, f4 = 3 * d1 + d5, f5 = 3 * d3 + d8, f6 = 3 * d6 + d9;
+      double V1 = 2 * f1 + f2, V2 = -(3 * f1 + f3), V3 = 2 * c5 + c7, V4 = 2 * c1 + c3, V5 = -(2 * f4 + f5), V6 = 3 * f4 + f6;
+      double V7 = -(3 * c5 + c11), V8 = -(3 * c1 + c9), V9 = 2 * c13 + c15, V10 = -(3 * c13 + c16), V13 = 2 * c14 + c17;
+      double V14 = -(3 * c14 + c18);
+      V1 = V1 / (x3 * y3); V2 = V2 / (x3 * y2); V3 = V3 / (x3 * y); V4 = V4 / x3;
+      V5 = V5 / (x2 * y3); V6 = V6 / (x2 * y2); V7 = V7 / (x2 * y); V8 = V8 / x2;
+      V9 = V9 / (x * y3); V10 = V10 / (x * y2); V13 = V13 / y3; V14 = V14 / y2;
+      double p1 = ((V1 * py2 + V2) * py2 + V3) * py2 + V4;
+      double p2 = ((V5 * py2 + V6) * py2 + V7) * py2 + V8;
+      double p3 = ((V9 * py2 + V10) * py2 + V11) * py2 + V12;
+      double p4 = ((V13 * py2 + V14) * py2 + V15) * py2 + V16;
+      r = (float)(((p1 * px2 + p2) * px2 + p3) * px2 + p4);
+    }
+    __stcs(out + k, r);
+  }
+}
+
+__global__ void k_expand_axes(const double* __restrict__ X1d, const double* __restrict__ Y1d, int nx, int ny, double* X, double* Y) {
+  size_t n = (size_t)nx * ny;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    X[k] = X1d[k % nx];
+    Y[k] = Y1d[k / nx];
+  }
+}
+__global__ void k_minmax_d(const double* __restrict__ a, size_t n, unsigned long long* omin, unsigned long long* omax);  // (bilin_map.cu twin below)
+
+__device__ __forceinline__ unsigned long long a_enc_d(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+__global__ void k_minmax_d(const double* __restrict__ a, size_t n, unsigned long long* omin, unsigned long long* omax) {
+  unsigned long long lmin = ~0ULL, lmax = 0ULL;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long e = a_enc_d(a[k]);
+    lmin = min(lmin, e);
+    lmax = max(lmax, e);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(omin, lmin); atomicMax(omax, lmax); }
+}
+static inline double a_dec_d(unsigned long long u) {
+  unsigned long long v = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
+  double x;
+  memcpy(&x, &v, 8);
+  return x;
+}
+
+// ===================================================================================================
+// coordinates of one FILL_EXTRA_BANDS level: (XX,YY)(nx,ny) -> (XP4,YP4)(nx+4,ny+4)
+static int feb_coords(sosie_ctx* ctx, int k_ew, const double* XX, const double* YY, int nx, int ny, double* XP4, double* YP4,
+                      int iorca, DBuf<double>& tmp) {
+  cudaStream_t st = ctx->stream;
+  const int nxp4 = nx + 4, nyp4 = ny + 4;
+  size_t ne = (size_t)nxp4 * nyp4;
+  k_feb_center<double><<<dim3(grid_for(ctx, ne, 256), 1), 256, 0, st>>>(XX, nx, ny, XP4, 0, 0); KLAUNCH_CHECK();
+  k_feb_center<double><<<dim3(grid_for(ctx, ne, 256), 1), 256, 0, st>>>(YY, nx, ny, YP4, 0, 0); KLAUNCH_CHECK();
+  const bool fold = (iorca == 4 || iorca == 6);
+  CK(tmp.alloc(nxp4 + 8));
+  auto sect = [&](double* P, int l0, int ls, int n, int jl, int r0, int rs, int jr) -> int {
+    if (n <= 0) return 0;
+    k_sectd_read<<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(P, nxp4, n, r0, rs, jr, tmp.p, 0, 0); KLAUNCH_CHECK();
+    k_sectd_write<<<dim3(cdiv(n, 256), 1), 256, 0, st>>>(P, nxp4, n, l0, ls, jl, tmp.p, 0, 0); KLAUNCH_CHECK();
+    return 0;
+  };
+  auto fold_top = [&](double* P) -> int {
+    int rc = 0;
+    if (iorca == 4) {
+      int nA = nxp4 / 2 - 1, nB = nxp4 / 2 + 3;
+      rc |= sect(P, 2, 1, nA, nyp4 - 1, nxp4, -1, nyp4 - 5);
+      rc |= sect(P, nxp4, -1, nB, nyp4 - 1, 2, 1, nyp4 - 5);
+      rc |= sect(P, 2, 1, nA, nyp4, nxp4, -1, nyp4 - 6);
+      rc |= sect(P, nxp4, -1, nB, nyp4, 2, 1, nyp4 - 6);
+    } else {
+      int nA = nxp4 / 2 - 1;
+      rc |= sect(P, 2, 1, nA, nyp4 - 1, nxp4 - 1, -1, nyp4 - 4);
+      rc |= sect(P, nxp4 - 1, -1, nA, nyp4 - 1, 2, 1, nyp4 - 4);
+      rc |= sect(P, 2, 1, nA, nyp4, nxp4 - 1, -1, nyp4 - 5);
+      rc |= sect(P, nxp4 - 1, -1, nA, nyp4, 2, 1, nyp4 - 5);
+    }
+    return rc;
+  };
+  k_feb_x_ew<<<cdiv(ny, 128), 128, 0, st>>>(XP4, nx, ny, k_ew); KLAUNCH_CHECK();
+  k_feb_x_ns<<<cdiv(nxp4, 128), 128, 0, st>>>(XP4, nxp4, nyp4, fold ? 0 : 1); KLAUNCH_CHECK();
+  if (fold) { if (int rc = fold_top(XP4)) return rc; }
+  if (fold) {
+    if (int rc = fold_top(YP4)) return rc;
+    k_feb_y_tb<<<cdiv(nx, 128), 128, 0, st>>>(YP4, nx, ny, 0); KLAUNCH_CHECK();
+  } else {
+    k_feb_y_tb<<<cdiv(nx, 128), 128, 0, st>>>(YP4, nx, ny, 1); KLAUNCH_CHECK();
+  }
+  k_feb_y_ew<<<cdiv(nyp4, 128), 128, 0, st>>>(YP4, nx, ny, k_ew); KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
+
+// field part of one FILL_EXTRA_BANDS level for `ns` slabs: F already holds zero + centre
+static int feb_field(sosie_ctx* ctx, int k_ew, const double* XP4, const double* YP4, double* FP4, int nx, int ny, int iorca, int ns,
+                     DBuf<double>& tmp) {
+  cudaStream_t st = ctx->stream;
+  const int nxp4 = nx + 4, nyp4 = ny + 4;
+  size_t stride = (size_t)nxp4 * nyp4;
+  k_feb_f_ew<<<dim3(cdiv(ny, 128), ns), 128, 0, st>>>(XP4, FP4, nx, ny, k_ew, stride); KLAUNCH_CHECK();
+  const bool fold = (iorca == 4 || iorca == 6);
+  if (fold) {
+    int ntmp = nxp4 + 8;
+    CK(tmp.alloc((size_t)ntmp * ns));
+    auto sect = [&](int l0, int ls, int n, int jl, int r0, int rs, int jr) -> int {
+      if (n <= 0) return 0;
+      k_sectd_read<<<dim3(cdiv(n, 256), ns), 256, 0, st>>>(FP4, nxp4, n, r0, rs, jr, tmp.p, stride, ntmp); KLAUNCH_CHECK();
+      k_sectd_write<<<dim3(cdiv(n, 256), ns), 256, 0, st>>>(FP4, nxp4, n, l0, ls, jl, tmp.p, stride, ntmp); KLAUNCH_CHECK();
+      return 0;
+    };
+    int rc = 0;
+    if (iorca == 4) {
+      int nA = nxp4 / 2 - 1, nB = nxp4 / 2 + 3;
+      rc |= sect(2, 1, nA, nyp4 - 1, nxp4, -1, nyp4 - 5);
+      rc |= sect(nxp4, -1, nB, nyp4 - 1, 2, 1, nyp4 - 5);
+      rc |= sect(2, 1, nA, nyp4, nxp4, -1, nyp4 - 6);
+      rc |= sect(nxp4, -1, nB, nyp4, 2, 1, nyp4 - 6);
+    } else {
+      int nA = nxp4 / 2 - 1;
+      rc |= sect(2, 1, nA, nyp4 - 1, nxp4 - 1, -1, nyp4 - 4);
+      rc |= sect(nxp4 - 1, -1, nA, nyp4 - 1, 2, 1, nyp4 - 4);
+      rc |= sect(2, 1, nA, nyp4, nxp4 - 1, -1, nyp4 - 5);
+      rc |= sect(nxp4 - 1, -1, nA, nyp4, 2, 1, nyp4 - 5);
+    }
+    if (rc) return rc;
+  }
+  k_feb_f_tb<<<dim3(cdiv(nxp4, 128), ns), 128, 0, st>>>(YP4, FP4, nxp4, nyp4, fold ? 0 : 1, stride); KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
+
+int akima_prepare_impl(sosie_ctx* ctx) {
+  cudaStream_t st = ctx->stream;
+  const int nx1 = ctx->ak_nx1, ny1 = ctx->ak_ny1, nx2 = ctx->ak_nx2, ny2 = ctx->ak_ny2;
+  const int ni1 = nx1 + 4, nj1 = ny1 + 4;
+  const size_t n1 = (size_t)nx1 * ny1, ne = (size_t)ni1 * nj1, ne8 = (size_t)(ni1 + 4) * (nj1 + 4), nt = (size_t)nx2 * ny2;
+  // ctx->ak_zX / ak_zY currently hold the 2-D source coordinates (nx1,ny1) in ak_ZX8/ak_ZY8 scratch: see capi
+  DBuf<double> tmp;
+  DBuf<double> X1, Y1;
+  X1.borrow(ctx->ak_ZX8.p, n1); Y1.borrow(ctx->ak_ZY8.p, n1);  // staged there by the C API
+  CK(ctx->ak_zX.alloc(ne)); CK(ctx->ak_zY.alloc(ne));
+  if (int rc = feb_coords(ctx, ctx->ak_kew, X1.p, Y1.p, nx1, ny1, ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_iorca, tmp)) return rc;
+  CK(cudaStreamSynchronize(st));
+  DBuf<double> X8, Y8; CK(X8.alloc(ne8)); CK(Y8.alloc(ne8));
+  int kewp = -1;
+  if (ctx->ak_kew > -1) kewp = ctx->ak_kew + 4;
+  if (int rc = feb_coords(ctx, kewp, ctx->ak_zX.p, ctx->ak_zY.p, ni1, nj1, X8.p, Y8.p, 0, tmp)) return rc;
+  CK(cudaStreamSynchronize(st));
+  // hand the twice-extended coordinates over to the context
+  ctx->ak_ZX8.release(); ctx->ak_ZY8.release();
+  ctx->ak_ZX8.p = X8.p; ctx->ak_ZX8.n = X8.n; ctx->ak_ZX8.own = true; X8.own = false;
+  ctx->ak_ZY8.p = Y8.p; ctx->ak_ZY8.n = Y8.n; ctx->ak_ZY8.own = true; Y8.own = false;
+  // source range (:186-188)
+  DBuf<unsigned long long> mm; CK(mm.alloc(4));
+  unsigned long long init[4] = {~0ULL, 0ULL, ~0ULL, 0ULL};
+  CK(cudaMemcpyAsync(mm.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+  k_minmax_d<<<grid_for(ctx, ne, 256), 256, 0, st>>>(ctx->ak_zX.p, ne, mm.p, mm.p + 1); KLAUNCH_CHECK();
+  k_minmax_d<<<grid_for(ctx, ne, 256), 256, 0, st>>>(ctx->ak_zY.p, ne, mm.p + 2, mm.p + 3); KLAUNCH_CHECK();
+  DBuf<int> bad; CK(bad.alloc(1));
+  CK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+  k_check_axes<<<grid_for(ctx, ne, 256), 256, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ni1, nj1, bad.p); KLAUNCH_CHECK();
+  unsigned long long hmm[4];
+  int hbad = 0;
+  CK(cudaMemcpyAsync(hmm, mm.p, sizeof(hmm), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < 4; k++) ctx->ak_range[k] = a_dec_d(hmm[k]);
+  CK(ctx->ak_ixy.alloc(2 * nt));
+  k_find_nearest_akima<<<grid_for(ctx, nt, 128), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ni1, nj1, ctx->ak_range[0], ctx->ak_range[1],
+                                                               ctx->ak_range[2], ctx->ak_range[3], ctx->ak_X2.p, ctx->ak_Y2.p, nt,
+                                                               hbad ? 0 : 1, ctx->ak_ixy.p); KLAUNCH_CHECK();
+  CK(cudaStreamSynchronize(st));
+  ctx->ak_set = true;
+  return SOSIE_OK;
+}
+
+int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
+  if (!ctx->ak_set) { ctx->err = "sosie_akima_apply: grids not set"; return SOSIE_ERR_STATE; }
+  cudaStream_t st = ctx->stream;
+  const int nx1 = ctx->ak_nx1, ny1 = ctx->ak_ny1;
+  const int ni1 = nx1 + 4, nj1 = ny1 + 4;
+  const size_t n1 = (size_t)nx1 * ny1, ne = (size_t)ni1 * nj1, ne8 = (size_t)(ni1 + 4) * (nj1 + 4);
+  const size_t nt = (size_t)ctx->ak_nx2 * ctx->ak_ny2;
+  // slabs per batch: bound the f64 workspace (4*ne + ne8 doubles per slab) to ~4 GB
+  size_t per = (4 * ne + ne8) * sizeof(double);
+  int nb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nslab, (size_t)4e9 / per));
+  if (nb > 32768) nb = 32768;
+  CK(ctx->ak_zF.alloc(ne * nb)); CK(ctx->ak_ZF8.alloc(ne8 * nb));
+  CK(ctx->ak_sx.alloc(ne * nb)); CK(ctx->ak_sy.alloc(ne * nb)); CK(ctx->ak_sxy.alloc(ne * nb));
+  DBuf<double> tmp;
+  int kewp = -1;
+  if (ctx->ak_kew > -1) kewp = ctx->ak_kew + 4;
+  for (int s0 = 0; s0 < nslab; s0 += nb) {
+    int ns = std::min(nb, nslab - s0);
+    k_feb_center<float><<<dim3(grid_for(ctx, ne, 256), ns), 256, 0, st>>>(dZ1 + (size_t)s0 * n1, nx1, ny1, ctx->ak_zF.p, n1, ne); KLAUNCH_CHECK();
+    if (int rc = feb_field(ctx, ctx->ak_kew, ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, nx1, ny1, ctx->ak_iorca, ns, tmp)) return rc;
+    k_feb_center<double><<<dim3(grid_for(ctx, ne8, 256), ns), 256, 0, st>>>(ctx->ak_zF.p, ni1, nj1, ctx->ak_ZF8.p, ne, ne8); KLAUNCH_CHECK();
+    if (int rc = feb_field(ctx, kewp, ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, 0, ns, tmp)) return rc;
+    k_slopes<<<dim3(grid_for(ctx, ne, 128), ns), 128, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
+                                                                ctx->ak_sxy.p, ne8, ne); KLAUNCH_CHECK();
+    k_akima_eval<<<dim3(grid_for(ctx, nt, 128), ns), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, ctx->ak_sx.p, ctx->ak_sy.p, ctx->ak_sxy.p,
+                                                                    ni1, nj1, ctx->ak_X2.p, ctx->ak_Y2.p, ctx->ak_ixy.p, nt, ctx->ak_range[0],
+                                                                    ctx->ak_range[1], ctx->ak_range[2], ctx->ak_range[3], dZ2 + (size_t)s0 * nt, ne); KLAUNCH_CHECK();
+  }
+  return SOSIE_OK;
+}
+
+// helper used by the C API to expand 1-D axes on device
+int akima_expand_axes(sosie_ctx* ctx, const double* dX1d, const double* dY1d, int nx, int ny, double* dX, double* dY) {
+  k_expand_axes<<<grid_for(ctx, (size_t)nx * ny, 256), 256, 0, ctx->stream>>>(dX1d, dY1d, nx, ny, dX, dY);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}

@@ -1,0 +1,345 @@
+// bilin_apply.cu -- per-slab application of the cached bilinear mapping.
+//
+// GPU counterpart of the apply loop of BILIN_2D (src/mod_bilin_2d.f90:209-263) and of INTERP_BL
+// (:275-361).  HBM-bound gather-FMA:
+//   * a one-off "pack" kernel turns (iP,jP,iqdrn,alpha,beta) into one 32-byte record per target:
+//     int4 = the four corner offsets in the working source slab (column-major, pole rows
+//     included), float4 = the four REAL(4) weights exactly as INTERP_BL rounds them (:334-337).
+//     Identical-point copies (:227-230) and the error codes -9998..-9994 (:347-356) are encoded
+//     in the record, so the hot kernel has no coordinate reads and no index arithmetic;
+//   * the apply kernel keeps a target's record in registers and loops over the slabs of its
+//     chunk (records x levels batched in ONE launch), issuing the 4 gathers of several slabs
+//     before consuming them.  Neighbouring targets hit neighbouring source cells, so a slab's
+//     gathers are served by L1/L2 and each source element leaves HBM once;
+//   * the two virtual pole rows of EXT_NORTH_TO_90_REGG (src/mod_manip.f90:1821-1832) are
+//     evaluated on the fly from the slab instead of materialising Z1w per record;
+//   * optional fused post-ops of INTERP_2D (clamp :97-98, target mask :133-137) and the
+//     corr_vect rotation (src/corr_vect.f90:622-632).
+// Arithmetic is REAL(4) in the reference's order with FMA contraction off -> bit-identical fields.
+#include "geom.cuh"
+
+#define REC_COPY (-1)   // idx.x: copy Z1w(idx.y)
+#define REC_CONST (-2)  // idx.x: constant w.x
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ MT, const double* __restrict__ AB, int4* pidx,
+       float4* pw) {
+  const size_t nt = (size_t)tg.nx * tg.ny;
+  const int nxi = sg.nx, nyi = sg.nyw;
+  const double eps5 = (double)1.E-5f;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    int jj = (int)(k / tg.nx) + 1, ji = (int)(k % tg.nx) + 1;
+    int iP = max(MT[k], 1), jP = max(MT[k + nt], 1);  // IMETRICS(:,:,1:2) = MAX(IMETRICS(:,:,1:2), 1)  (:217)
+    int iqd = MT[k + 2 * nt];
+    double xa = AB[k], xb = AB[k + nt];
+    int4 id;
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    // a stale mapping could hold iP/jP beyond the source: the reference would read out of bounds
+    int iPc = min(iP, nxi), jPc = min(jP, nyi);
+    bool same = (fabs(d_degE_to_degWE(src_lon(sg, iPc, jPc)) - d_degE_to_degWE(trg_lon(tg, ji, jj))) < eps5) &&
+                (fabs(src_lat(sg, iPc, jPc) - trg_lat(tg, ji, jj)) < eps5);
+    if (same) {
+      id = make_int4(REC_COPY, (iPc - 1) + (jPc - 1) * nxi, 0, 0);
+    } else {
+      int jiPm1 = iP - 1, jiPp1 = iP + 1;
+      if ((jiPm1 == 0) && (k_ew >= 0)) jiPm1 = nxi - k_ew;
+      if ((jiPp1 == nxi + 1) && (k_ew >= 0)) jiPp1 = 1 + k_ew;
+      int i1 = 0, j1 = 0, i2 = 0, j2 = 0, i3 = 0, j3 = 0, i4 = 0, j4 = 0;  // Q19 (iqd outside 1..4 cannot occur after the fix-ups)
+      switch (iqd) {
+        case 1: i1 = iP; j1 = jP; i2 = jiPp1; j2 = jP; i3 = jiPp1; j3 = jP + 1; i4 = iP; j4 = jP + 1; break;
+        case 2: i1 = iP; j1 = jP; i2 = iP; j2 = jP - 1; i3 = jiPp1; j3 = jP - 1; i4 = jiPp1; j4 = jP; break;
+        case 3: i1 = iP; j1 = jP; i2 = jiPm1; j2 = jP; i3 = jiPm1; j3 = jP - 1; i4 = iP; j4 = jP - 1; break;
+        case 4: i1 = iP; j1 = jP; i2 = iP; j2 = jP + 1; i3 = jiPm1; j3 = jP + 1; i4 = jiPm1; j4 = jP; break;
+        default: break;
+      }
+      float w1 = (float)((1.0 - xa) * (1.0 - xb));
+      float w2 = (float)(xa * (1.0 - xb));
+      float w3 = (float)(xa * xb);
+      float w4 = (float)((1.0 - xa) * xb);
+      float wup = w1 + w2 + w3 + w4;
+      float cst = 0.f;
+      bool isc = true;
+      if (wup == 0.f) cst = -9998.f;
+      else if ((i1 < 1) || (i2 < 1) || (i3 < 1) || (i4 < 1)) cst = -9997.f;
+      else if ((j1 < 1) || (j2 < 1) || (j3 < 1) || (j4 < 1)) cst = -9996.f;
+      else if ((j1 > nyi) || (j2 > nyi) || (j3 > nyi) || (j4 > nyi)) cst = -9995.f;
+      else if ((i1 > nxi) || (i2 > nxi) || (i3 > nxi) || (i4 > nxi)) cst = -9994.f;
+      else isc = false;
+      if (isc) { id = make_int4(REC_CONST, 0, 0, 0); w.x = cst; }
+      else {
+        id = make_int4((i1 - 1) + (j1 - 1) * nxi, (i2 - 1) + (j2 - 1) * nxi, (i3 - 1) + (j3 - 1) * nxi, (i4 - 1) + (j4 - 1) * nxi);
+        w = make_float4(w1, w2, w3, w4);
+      }
+    }
+    pidx[k] = id;
+    pw[k] = w;
+  }
+}
+
+// value of the working slab Z1w at linear offset `lin` (pole rows virtual)
+struct SlabView {
+  int nx, ny;            // physical slab extents
+  int nreal;             // nx*ny
+  const int32_t* im;     // ji_m table (1-based), only when pole rows exist
+};
+__device__ __forceinline__ float zget(const float* __restrict__ Z, const SlabView& v, int lin) {
+  if (lin < v.nreal) return __ldg(Z + lin);
+  int r = lin - v.nreal;
+  if (r < v.nx) {  // row ny+1 : 0.5*(XF(ji,ny) + XF(ji_m,ny))
+    int i = r, m = v.im[i] - 1;
+    const float* row = Z + (size_t)(v.ny - 1) * v.nx;
+    return 0.5f * (__ldg(row + i) + __ldg(row + m));
+  }
+  int i = r - v.nx, m = v.im[i] - 1;  // row ny+2 : XF(ji_m,ny-1)
+  return __ldg(Z + (size_t)(v.ny - 2) * v.nx + m);
+}
+
+__device__ __forceinline__ float interp_one(const float* __restrict__ Z, const SlabView& v, const int4& id, const float4& w,
+                                            float wup) {
+  if (id.x >= 0) {
+    float z1 = zget(Z, v, id.x), z2 = zget(Z, v, id.y), z3 = zget(Z, v, id.z), z4 = zget(Z, v, id.w);
+    // ( Z_in(i1,j1)*w1 + Z_in(i2,j2)*w2 + Z_in(i3,j3)*w3 + Z_in(i4,j4)*w4 )/wup   (:358)
+    return __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z1, w.x), __fmul_rn(z2, w.y)), __fmul_rn(z3, w.z)), __fmul_rn(z4, w.w)), wup);
+  }
+  if (id.x == REC_COPY) return zget(Z, v, id.y);
+  return w.x;
+}
+
+struct PostOps {
+  int use_clamp;
+  float vmin, vmax;
+  const int32_t* mask_trg;
+  float rmiss;
+};
+
+#define SLAB_UNROLL 4
+// grid: x = target tiles, y = slab chunks.  Each thread: one target, all slabs of its chunk.
+__global__ void __launch_bounds__(256)
+k_apply(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ Z1,
+        float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po) {
+  const size_t src_stride = (size_t)v.nreal;
+  const int s0 = blockIdx.y * slabs_per_chunk;
+  const int s1 = min(s0 + slabs_per_chunk, nslab);
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    const int4 id = pidx[k];
+    const float4 w = pw[k];
+    const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
+    const bool masked = po.mask_trg ? (po.mask_trg[k] == 0) : false;
+    int s = s0;
+    if (id.x >= 0 && id.w < v.nreal && id.x < v.nreal && id.y < v.nreal && id.z < v.nreal) {
+      // fast path: four plain gathers per slab, SLAB_UNROLL slabs in flight
+      for (; s + SLAB_UNROLL <= s1; s += SLAB_UNROLL) {
+        float z[SLAB_UNROLL][4];
+#pragma unroll
+        for (int u = 0; u < SLAB_UNROLL; u++) {
+          const float* Z = Z1 + (size_t)(s + u) * src_stride;
+          z[u][0] = __ldg(Z + id.x); z[u][1] = __ldg(Z + id.y); z[u][2] = __ldg(Z + id.z); z[u][3] = __ldg(Z + id.w);
+        }
+#pragma unroll
+        for (int u = 0; u < SLAB_UNROLL; u++) {
+          float r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z[u][0], w.x), __fmul_rn(z[u][1], w.y)), __fmul_rn(z[u][2], w.z)), __fmul_rn(z[u][3], w.w)), wup);
+          if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+          if (masked) r = po.rmiss;
+          __stcs(Z2 + (size_t)(s + u) * nt + k, r);
+        }
+      }
+    }
+    for (; s < s1; s++) {
+      float r = interp_one(Z1 + (size_t)s * src_stride, v, id, w, wup);
+      if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+      if (masked) r = po.rmiss;
+      __stcs(Z2 + (size_t)s * nt + k, r);
+    }
+  }
+}
+
+// (U,V) pair + rotation on the target grid (src/corr_vect.f90:622-624,630,632)
+__global__ void __launch_bounds__(256)
+k_apply_uv(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ U1,
+           const float* __restrict__ V1, float* __restrict__ Uo, float* __restrict__ Vo, const double* __restrict__ xcos,
+           const double* __restrict__ xsin, int nslab, int slabs_per_chunk) {
+  const size_t src_stride = (size_t)v.nreal;
+  const int s0 = blockIdx.y * slabs_per_chunk;
+  const int s1 = min(s0 + slabs_per_chunk, nslab);
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    const int4 id = pidx[k];
+    const float4 w = pw[k];
+    const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
+    const double c = xcos[k], sn = xsin[k];
+    for (int s = s0; s < s1; s++) {
+      double zU = (double)interp_one(U1 + (size_t)s * src_stride, v, id, w, wup);
+      double zV = (double)interp_one(V1 + (size_t)s * src_stride, v, id, w, wup);
+      float uo = (float)__dadd_rn(__dmul_rn(c, zU), __dmul_rn(sn, zV));
+      float vo = (float)__dsub_rn(__dmul_rn(c, zV), __dmul_rn(sn, zU));
+      __stcs(Uo + (size_t)s * nt + k, uo);
+      __stcs(Vo + (size_t)s * nt + k, vo);
+    }
+  }
+}
+
+// rmeanv = SUM(Z2(:,ny2))/nx2 sequentially (:244)
+__global__ void k_lastrow_mean(const float* __restrict__ Z2, int nx2, int ny2, float* out) {
+  float s = 0.f;
+  const float* row = Z2 + (size_t)(ny2 - 1) * nx2;
+  for (int i = 0; i < nx2; i++) s = __fadd_rn(s, row[i]);
+  *out = __fdiv_rn(s, (float)nx2);
+}
+// section copy dst(l0+k*ls, jl) = src(r0+k*rs, jr) (1-based), RHS read before any store (two kernels)
+__global__ void k_sect_read(const float* Z, int nx, int n, int r0, int rs, int jr, float* tmp) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    int ir = r0 + k * rs;
+    tmp[k] = (ir >= 1 && ir <= nx) ? Z[(size_t)(ir - 1) + (size_t)(jr - 1) * nx] : 0.f;
+  }
+}
+__global__ void k_sect_write(float* Z, int nx, int n, int l0, int ls, int jl, const float* tmp) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    Z[(size_t)(l0 + k * ls - 1) + (size_t)(jl - 1) * nx] = tmp[k];
+}
+
+// ---------------------------------------------------------------------------------------------------
+int bilin_pack_impl(sosie_ctx* ctx) {
+  if (!ctx->map_ready) { ctx->err = "bilinear mapping neither built nor loaded"; return SOSIE_ERR_STATE; }
+  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
+  if ((size_t)ctx->sg.nx * ctx->sg.nyw > 2147483647ULL) { ctx->err = "source slab too large for 32-bit offsets"; return SOSIE_ERR_ARG; }
+  CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt));
+  k_pack<<<grid_for(ctx, nt, 256), 256, 0, ctx->stream>>>(ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p, ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p);
+  KLAUNCH_CHECK();
+  ctx->pack_ready = true;
+  return SOSIE_OK;
+}
+
+static void apply_grid(const sosie_ctx* ctx, size_t nt, int nslab, dim3& grid, int& spc) {
+  // x covers the targets once (<= 2^31 blocks); y splits the slabs so that the whole grid is a
+  // few waves of 148 SMs x 8 resident CTAs.
+  int gx = (int)((nt + 255) / 256);
+  int waves_target = ctx->num_sms * 8 * 4;
+  int chunks = 1;
+  if (gx < waves_target) chunks = (waves_target + gx - 1) / gx;
+  if (chunks > nslab) chunks = nslab;
+  if (chunks < 1) chunks = 1;
+  spc = (nslab + chunks - 1) / chunks;
+  // keep SLAB_UNROLL granularity when possible
+  if (spc > SLAB_UNROLL) spc = ((spc + SLAB_UNROLL - 1) / SLAB_UNROLL) * SLAB_UNROLL;
+  chunks = (nslab + spc - 1) / spc;
+  grid = dim3(gx, chunks, 1);
+}
+
+static int orca_lastrow_patch(sosie_ctx* ctx, float* dZ2s) {
+  const int nx2 = ctx->tg.nx, ny2 = ctx->tg.ny, io = ctx->i_orca_trg;
+  cudaStream_t st = ctx->stream;
+  auto sect = [&](int l0, int ls, int n, int jl, int r0, int rs, int jr) -> int {
+    if (n <= 0) return 0;
+    CK(ctx->d_stage2.alloc((size_t)n > ctx->d_stage2.n ? (size_t)n : ctx->d_stage2.n));
+    k_sect_read<<<cdiv(n, 256), 256, 0, st>>>(dZ2s, nx2, n, r0, rs, jr, ctx->d_stage2.p); KLAUNCH_CHECK();
+    k_sect_write<<<cdiv(n, 256), 256, 0, st>>>(dZ2s, nx2, n, l0, ls, jl, ctx->d_stage2.p); KLAUNCH_CHECK();
+    return 0;
+  };
+  if (io == 4) {  // non-conforming sections: left-hand extent governs
+    int nA = nx2 / 2 - 1, nB = nx2 / 2 + 3;
+    if (int rc = sect(2, 1, nA, ny2, nx2, -1, ny2 - 2)) return rc;
+    if (int rc = sect(nx2, -1, nB, ny2, 2, 1, ny2 - 2)) return rc;
+  }
+  if (io == 6) {
+    int nA = nx2 / 2 - 1;
+    if (int rc = sect(2, 1, nA, ny2, nx2 - 1, -1, ny2 - 1)) return rc;
+    if (int rc = sect(nx2 - 1, -1, nA, ny2, 2, 1, ny2 - 1)) return rc;
+  }
+  return 0;
+}
+
+int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, int first_call, int use_clamp, float vmin,
+                     float vmax, const int32_t* dmask_trg, float rmiss) {
+  if (!ctx->pack_ready) { if (int rc = bilin_pack_impl(ctx)) return rc; }
+  if (nslab <= 0) return SOSIE_OK;
+  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
+  SlabView v;
+  v.nx = ctx->sg.nx; v.ny = ctx->sg.ny; v.nreal = ctx->sg.nx * ctx->sg.ny; v.im = ctx->d_im.p;
+  PostOps po;
+  po.use_clamp = use_clamp; po.vmin = vmin; po.vmax = vmax; po.mask_trg = dmask_trg; po.rmiss = rmiss;
+  dim3 grid;
+  int spc;
+  apply_grid(ctx, nt, nslab, grid, spc);
+  k_apply<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po);
+  KLAUNCH_CHECK();
+  // l_last_y_row_missing (:241-247) is evaluated on the first call only, the patch (:254-263) on every call
+  if (first_call) {
+    ctx->l_last_y_row_missing = 0;
+    if (ctx->i_orca_trg >= 4) {
+      DBuf<float> dm; CK(dm.alloc(1));
+      k_lastrow_mean<<<1, 1, 0, ctx->stream>>>(dZ2, ctx->tg.nx, ctx->tg.ny, dm.p); KLAUNCH_CHECK();
+      float hm;
+      CK(cudaMemcpyAsync(&hm, dm.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+      CK(cudaStreamSynchronize(ctx->stream));
+      double rmeanv = (double)hm;
+      ctx->l_last_y_row_missing = ((rmeanv < G_RMV + (double)0.1f) && (rmeanv > G_RMV - (double)0.1f)) ? 1 : 0;
+    }
+  }
+  if (ctx->l_last_y_row_missing && !use_clamp && !dmask_trg) {
+    for (int s = 0; s < nslab; s++)
+      if (int rc = orca_lastrow_patch(ctx, dZ2 + (size_t)s * nt)) return rc;
+  }
+  return SOSIE_OK;
+}
+
+int bilin_apply_uv_impl(sosie_ctx* ctx, int nslab, const float* dU1, const float* dV1, float* dUo, float* dVo,
+                        const double* dcos, const double* dsin) {
+  if (!ctx->pack_ready) { if (int rc = bilin_pack_impl(ctx)) return rc; }
+  if (nslab <= 0) return SOSIE_OK;
+  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
+  SlabView v;
+  v.nx = ctx->sg.nx; v.ny = ctx->sg.ny; v.nreal = ctx->sg.nx * ctx->sg.ny; v.im = ctx->d_im.p;
+  dim3 grid;
+  int spc;
+  apply_grid(ctx, nt, nslab, grid, spc);
+  k_apply_uv<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dU1, dV1, dUo, dVo, dcos, dsin, nslab, spc);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// scalar INTERP_BL for trajectory points (src/mod_bilin_2d.f90:275-361)
+__global__ void k_interp_bl(int k_ew, int nxi, int nyi, const float* __restrict__ Z, int n, const int32_t* __restrict__ jiP,
+                            const int32_t* __restrict__ jjP, const int32_t* __restrict__ iqdv, const double* __restrict__ xav,
+                            const double* __restrict__ xbv, float* out) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    int iP = jiP[k], jP = jjP[k], iqd = iqdv[k];
+    double xa = xav[k], xb = xbv[k];
+    int jiPm1 = iP - 1, jiPp1 = iP + 1;
+    if ((jiPm1 == 0) && (k_ew >= 0)) jiPm1 = nxi - k_ew;
+    if ((jiPp1 == nxi + 1) && (k_ew >= 0)) jiPp1 = 1 + k_ew;
+    int i1 = 0, j1 = 0, i2 = 0, j2 = 0, i3 = 0, j3 = 0, i4 = 0, j4 = 0;
+    switch (iqd) {
+      case 1: i1 = iP; j1 = jP; i2 = jiPp1; j2 = jP; i3 = jiPp1; j3 = jP + 1; i4 = iP; j4 = jP + 1; break;
+      case 2: i1 = iP; j1 = jP; i2 = iP; j2 = jP - 1; i3 = jiPp1; j3 = jP - 1; i4 = jiPp1; j4 = jP; break;
+      case 3: i1 = iP; j1 = jP; i2 = jiPm1; j2 = jP; i3 = jiPm1; j3 = jP - 1; i4 = iP; j4 = jP - 1; break;
+      case 4: i1 = iP; j1 = jP; i2 = iP; j2 = jP + 1; i3 = jiPm1; j3 = jP + 1; i4 = jiPm1; j4 = jP; break;
+      default: break;
+    }
+    float w1 = (float)((1.0 - xa) * (1.0 - xb));
+    float w2 = (float)(xa * (1.0 - xb));
+    float w3 = (float)(xa * xb);
+    float w4 = (float)((1.0 - xa) * xb);
+    float wup = __fadd_rn(__fadd_rn(__fadd_rn(w1, w2), w3), w4);
+    float r;
+    if (wup == 0.f) r = -9998.f;
+    else if ((i1 < 1) || (i2 < 1) || (i3 < 1) || (i4 < 1)) r = -9997.f;
+    else if ((j1 < 1) || (j2 < 1) || (j3 < 1) || (j4 < 1)) r = -9996.f;
+    else if ((j1 > nyi) || (j2 > nyi) || (j3 > nyi) || (j4 > nyi)) r = -9995.f;
+    else if ((i1 > nxi) || (i2 > nxi) || (i3 > nxi) || (i4 > nxi)) r = -9994.f;
+    else {
+      float z1 = Z[(size_t)(i1 - 1) + (size_t)(j1 - 1) * nxi], z2 = Z[(size_t)(i2 - 1) + (size_t)(j2 - 1) * nxi];
+      float z3 = Z[(size_t)(i3 - 1) + (size_t)(j3 - 1) * nxi], z4 = Z[(size_t)(i4 - 1) + (size_t)(j4 - 1) * nxi];
+      r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z1, w1), __fmul_rn(z2, w2)), __fmul_rn(z3, w3)), __fmul_rn(z4, w4)), wup);
+    }
+    out[k] = r;
+  }
+}
+
+int interp_bl_impl(sosie_ctx* ctx, int k_ew, int nxi, int nyi, const float* dZ, int n, const int32_t* ji, const int32_t* jj,
+                   const int32_t* iq, const double* xa, const double* xb, float* out) {
+  if (n <= 0) return SOSIE_OK;
+  k_interp_bl<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(k_ew, nxi, nyi, dZ, n, ji, jj, iq, xa, xb, out);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}

@@ -1,0 +1,848 @@
+// bilin_map.cu -- device construction of the bilinear mapping.
+//
+// GPU counterpart of MAPPING_BL (src/mod_bilin_2d.f90:366-691) and of the nearest-point search
+// FIND_NEAREST_POINT / _EASY / _TWISTED (src/mod_manip.f90:834-1440).  Results are bit-identical to
+// the reference algorithm evaluated with the pmath libm (see pmath.h): every decision is taken
+// by the same IEEE operations in the same order; only the *schedule* is different:
+//   * EASY (regular source): one thread per target, search + quadrant + Newton fused in one kernel;
+//     the separable 1-D MINLOCs are bracket searches with the reference's first-index tie-break;
+//     the per-target 1.E12 fill of the whole source array (:1038) is a dead store and is skipped.
+//   * TWISTED (curvilinear source): the chain-independent latitude-band result is computed for all
+//     targets in parallel (one warp per target), then the sequential "luck window" chain
+//     s(t) = f_t(s(t-1)) (:1342-1349) is solved by parallel fixed-point iteration -- the fixed point
+//     of a chain recurrence is unique, so the converged state IS the sequential result.
+//   * acos is only evaluated for candidates whose dot product is within 1e-13 of the running best
+//     (a margin 100x larger than any rounding wiggle of acos): identical argmin, ~10x fewer acos.
+#include <cub/cub.cuh>
+
+#include "geom.cuh"
+
+// ---------------------------------------------------------------------------------------------------
+// order-preserving encoding of doubles for atomicMin/atomicMax
+__device__ __forceinline__ unsigned long long enc_d(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
+static inline double dec_d_host(unsigned long long u) {
+  unsigned long long v = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
+  double x;
+  memcpy(&x, &v, 8);
+  return x;
+}
+
+struct Prelude {            // scalars produced on device, read back once
+  unsigned long long ymin_s, ymax_s, ymin_t, ymax_t, rmin_dlat;  // encoded doubles
+  int irreg_s, irreg_t;     // != 0 : L_IS_GRID_REGULAR false
+  int j_strt, j_stop;       // MINVAL / MAXVAL over columns
+  int err;
+  double rtmp;              // SUM(ztmp_t(:,ny_t/2))
+  unsigned long long ymaxabs_dummy;
+};
+
+__global__ void k_prelude_init(Prelude* p) {
+  p->ymin_s = ~0ULL; p->ymax_s = 0ULL; p->ymin_t = ~0ULL; p->ymax_t = 0ULL; p->rmin_dlat = ~0ULL;
+  p->irreg_s = 0; p->irreg_t = 0; p->j_strt = 2147483647; p->j_stop = 0; p->err = 0; p->rtmp = 0.0;
+}
+
+__global__ void k_minmax(const double* __restrict__ a, size_t n, unsigned long long* omin, unsigned long long* omax) {
+  unsigned long long lmin = ~0ULL, lmax = 0ULL;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long e = enc_d(a[k]);
+    lmin = min(lmin, e);
+    lmax = max(lmax, e);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+    lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(omin, lmin); atomicMax(omax, lmax); }
+}
+
+// L_IS_GRID_REGULAR (src/mod_manip.f90:1632-1663), both tests, on a 2-D (nx,ny) pair
+__global__ void k_is_regular(const double* __restrict__ X, const double* __restrict__ Y, int nx, int ny, int* irreg) {
+  const double tol = (double)1.E-12f;
+  __shared__ double sh[32];
+  // a/ one block per row jj>=2 : SUM(ABS(Xlon(:,jj)-Xlon(:,1)))
+  for (int jj = 2 + blockIdx.x; jj <= ny; jj += gridDim.x) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) s += fabs(X[(size_t)i + (size_t)(jj - 1) * nx] - X[i]);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < (blockDim.x >> 5); w++) t += sh[w];
+      if (t > tol) atomicOr(irreg, 1);
+    }
+    __syncthreads();
+  }
+  // b/ one thread per column ji : SUM(ABS(Xlat(ji,:)-Xlat(1,:))), sequential in j as the reference
+  for (int ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nx; ji += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int jj = 0; jj < ny; jj++) s += fabs(Y[(size_t)ji + (size_t)jj * nx] - Y[(size_t)jj * nx]);
+    if (s > tol) atomicOr(irreg, 2);
+  }
+}
+
+// rtmp = SUM(Ytrg(:,jm) - Ytrg(:,jm-1)) sequentially (only its sign is used, :921-922)
+__global__ void k_rtmp(TrgGeom tg, Prelude* p) {
+  int jm = tg.ny / 2;
+  double r = 0.0;
+  if (jm >= 2)
+    for (int i = 1; i <= tg.nx; i++) r += (trg_lat(tg, i, jm) - trg_lat(tg, i, jm - 1));
+  p->rtmp = r;
+}
+
+__global__ void k_min_dlat(TrgGeom tg, Prelude* p) {
+  double sg = d_sign(1.0, p->rtmp);
+  unsigned long long lmin = ~0ULL;
+  size_t n = (size_t)tg.nx * tg.ny;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(k / tg.nx) + 1, i = (int)(k % tg.nx) + 1;
+    if (j < 2) continue;
+    double v = sg * (trg_lat(tg, i, j) - trg_lat(tg, i, j - 1));
+    lmin = min(lmin, enc_d(v));
+  }
+  for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+  if ((threadIdx.x & 31) == 0) atomicMin(&p->rmin_dlat, lmin);
+}
+
+// i1dum = MINLOC(Ytrg, mask=(Ytrg>=y_min_s), dim=2) ; MAXLOC(Ytrg, mask=(Ytrg<=y_max_s), dim=2)  (:939-941)
+__global__ void k_jrange(TrgGeom tg, Prelude* p, double y_min_s, double y_max_s) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i <= tg.nx; i += gridDim.x * blockDim.x) {
+    int jn = 0, jx = 0;
+    double vmin = 0, vmax = 0;
+    for (int j = 1; j <= tg.ny; j++) {
+      double v = trg_lat(tg, i, j);
+      if (v >= y_min_s) { if (jn == 0 || v < vmin) { vmin = v; jn = j; } }
+      if (v <= y_max_s) { if (jx == 0 || v > vmax) { vmax = v; jx = j; } }
+    }
+    if (jn > 0) atomicMin(&p->j_strt, jn);
+    atomicMax(&p->j_stop, jx);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// source preparation
+__global__ void k_trig_table(const double* __restrict__ deg, int n, double* c, double* s) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    double sv, cv;
+    pm_sincos(deg[k] * G_ZCONV, &sv, &cv);
+    c[k] = cv;
+    s[k] = sv;
+  }
+}
+// 2-D working arrays (nx,nyw): copy + the two rows of EXT_NORTH_TO_90_REGG (:1813-1819), unit vectors
+__global__ void k_build_src2d(const double* __restrict__ Xin, const double* __restrict__ Yin, int nx, int ny, int nyw,
+                              int in_1d, double dyp, double* X, double* Y, double* vx, double* vy, double* vz) {
+  size_t n = (size_t)nx * nyw;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(k / nx), i = (int)(k % nx);
+    double lo, la;
+    if (j < ny) {
+      lo = in_1d ? Xin[i] : Xin[(size_t)i + (size_t)j * nx];
+      la = in_1d ? Yin[j] : Yin[(size_t)i + (size_t)j * nx];
+    } else {
+      lo = in_1d ? Xin[i] : Xin[(size_t)i + (size_t)(ny - 1) * nx];
+      la = (j == ny) ? 90.0 : 90.0 + dyp;
+    }
+    X[k] = lo;
+    Y[k] = la;
+    double ux, uy, uz;
+    unit_vec(lo, la, ux, uy, uz);
+    vx[k] = ux; vy[k] = uy; vz[k] = uz;
+  }
+}
+__global__ void k_lat_table(const double* __restrict__ Yin, int ny, int nyw, double dyp, double* lat) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nyw; j += gridDim.x * blockDim.x)
+    lat[j] = (j < ny) ? Yin[j] : ((j == ny) ? 90.0 : 90.0 + dyp);
+}
+// ji_m = MINLOC(ABS(XX(:,ny)-MOD(zlon+180.,360.)))  (src/mod_manip.f90:1821-1826)
+__global__ void k_jim_table(const double* __restrict__ lonrow, int nx, int32_t* im) {
+  for (int ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nx; ji += gridDim.x * blockDim.x) {
+    double zlon_m = fmod(lonrow[ji] + 180.0, 360.0);
+    int best = 0;
+    double bv = fabs(lonrow[0] - zlon_m);
+    for (int i = 1; i < nx; i++) {
+      double v = fabs(lonrow[i] - zlon_m);
+      if (v < bv) { bv = v; best = i; }
+    }
+    im[ji] = best + 1;
+  }
+}
+__global__ void k_gather_axes(SrcGeom sg, double* vlon, double* vlat) {  // vlon = Xsrc(:,3), vlat = Ysrc(3,:)
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < sg.nx + sg.nyw; k += gridDim.x * blockDim.x) {
+    if (k < sg.nx) vlon[k] = src_lon(sg, k + 1, 3);
+    else vlat[k - sg.nx] = src_lat(sg, 3, k - sg.nx + 1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// MINLOC(ABS(v(:)-r)) : first minimum, 1-based
+__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r) {
+  int lo = 0, hi = n;  // lower_bound: first index with v[idx] >= r
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (v[mid] < r) lo = mid + 1; else hi = mid;
+  }
+  int best;
+  if (lo == 0) best = 0;
+  else if (lo == n) best = n - 1;
+  else best = (fabs(v[lo - 1] - r) <= fabs(v[lo] - r)) ? lo - 1 : lo;
+  double bv = fabs(v[best] - r);
+  while (best > 0 && fabs(v[best - 1] - r) == bv) best--;
+  return best + 1;
+}
+__device__ __forceinline__ int minloc_abs_linear(const double* __restrict__ v, int n, double r) {
+  int best = 0;
+  double bv = fabs(v[0] - r);
+  for (int i = 1; i < n; i++) {
+    double x = fabs(v[i] - r);
+    if (x < bv) { bv = x; best = i; }
+  }
+  return best + 1;
+}
+
+// first-minimum scan of zr*ACOS(MIN(pds,1)) over the window (i1:i2, j1:j2), column-major order
+struct Best {
+  double d, pds;
+  int i, j;
+};
+#define PDS_MARGIN 1.0e-13
+__device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
+                                            int j2, Best& b) {
+  b.d = 0.0; b.pds = -4.0; b.i = 0; b.j = 0;
+  for (int jj = j1; jj <= j2; jj++) {
+    for (int ji = i1; ji <= i2; ji++) {
+      double vx, vy, vz;
+      src_vec(sg, ji, jj, vx, vy, vz);
+      double zpds = ux * vx + uy * vy + uz * vz;
+      if (b.i != 0 && zpds < b.pds - PDS_MARGIN) continue;
+      double d = G_ZR * pm_acos(fmin(zpds, 1.0));
+      if (b.i == 0 || d < b.d) { b.d = d; b.pds = zpds; b.i = ji; b.j = jj; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct MapOut {
+  int iq;
+  double a, b;
+  int ipb;
+  float dnp;
+};
+
+// body of the target loop of MAPPING_BL, src/mod_bilin_2d.f90:459-634
+__device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP, double yP, int iP, int jP, MapOut& o,
+                                         int* err) {
+  o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
+  const int nxi = sg.nx, nyi = sg.nyw;
+  if (!((iP != (int)G_RMV) && (jP != (int)G_RMV) && (jP < nyi))) return;
+  int iPm1 = iP - 1, iPp1 = iP + 1, jPm1 = jP - 1, jPp1 = jP + 1;
+  if (iPm1 == 0) { if (k_ew >= 0) iPm1 = nxi - k_ew; }
+  if (iPp1 == nxi + 1) { if (k_ew >= 0) iPp1 = 1 + k_ew; }
+  if ((iPm1 < 1) || (jPm1 < 1) || (iPp1 > nxi)) return;
+  double lonP = fmod(src_lon(sg, iP, jP), 360.0), latP = src_lat(sg, iP, jP);
+  double lonN = fmod(src_lon(sg, iP, jPp1), 360.0), latN = src_lat(sg, iP, jPp1);
+  double lonE = fmod(src_lon(sg, iPp1, jP), 360.0), latE = src_lat(sg, iPp1, jP);
+  double lonS = fmod(src_lon(sg, iP, jPm1), 360.0), latS = src_lat(sg, iP, jPm1);
+  double lonW = fmod(src_lon(sg, iPm1, jP), 360.0), latW = src_lat(sg, iPm1, jP);
+  xP = fmod(xP, 360.0);
+  double ya = d_merc(latP);
+  double hP = d_heading_y(lonP, xP, ya, d_merc(yP));
+  double hN = d_heading_y(lonP, lonN, ya, d_merc(latN));
+  double hE = d_heading_y(lonP, lonE, ya, d_merc(latE));
+  double hS = d_heading_y(lonP, lonS, ya, d_merc(latS));
+  double hW = d_heading_y(lonP, lonW, ya, d_merc(latW));
+  int iqdrn = 4;
+  double hPp = d_degE_to_degWE(hP);
+  if (hN > hE) hN = hN - 360.0;
+  if (hPp > hN && hPp <= hE) iqdrn = 1;
+  if (hP > hE && hP <= hS) iqdrn = 2;
+  if (hP > hS && hP <= hW) iqdrn = 3;
+  if (hP > hW && hPp <= hN) iqdrn = 4;
+  double loni[5], lati[5];
+  loni[0] = xP; lati[0] = yP;
+  loni[1] = lonP; lati[1] = latP;
+  o.dnp = (float)d_distance(xP, lonP, yP, latP);
+  int icpt = 0;
+  bool lagain = true;
+  const int iqdrn0 = 0;  // Q2
+  while (lagain) {
+    switch (iqdrn) {
+      case 1:
+        loni[2] = lonE; lati[2] = latE;
+        loni[3] = fmod(src_lon(sg, iPp1, jPp1), 360.0); lati[3] = src_lat(sg, iPp1, jPp1);
+        loni[4] = lonN; lati[4] = latN;
+        break;
+      case 2:
+        loni[2] = lonS; lati[2] = latS;
+        loni[3] = fmod(src_lon(sg, iPp1, jPm1), 360.0); lati[3] = src_lat(sg, iPp1, jPm1);
+        loni[4] = lonE; lati[4] = latE;
+        break;
+      case 3:
+        loni[2] = lonW; lati[2] = latW;
+        loni[3] = fmod(src_lon(sg, iPm1, jPm1), 360.0); lati[3] = src_lat(sg, iPm1, jPm1);
+        loni[4] = lonS; lati[4] = latS;
+        break;
+      case 4:
+        loni[2] = lonN; lati[2] = latN;
+        loni[3] = fmod(src_lon(sg, iPm1, jPp1), 360.0); lati[3] = src_lat(sg, iPm1, jPp1);
+        loni[4] = lonW; lati[4] = latW;
+        break;
+      default: break;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) if (loni[k] <= 0.0) loni[k] = loni[k] + 360.0;
+    int ok = d_l_inpoly(&loni[1], &lati[1], xP, yP);  // Q8: the un-moved xP
+    if (ok < 0) { atomicOr(err, 1); ok = 0; }
+    if ((!ok) && (yP < 88.0)) { icpt = icpt + 1; iqdrn = icpt; }
+    else lagain = false;
+    if (icpt == 5) { lagain = false; iqdrn = iqdrn0; }
+  }
+  d_local_coord(loni, lati, o.a, o.b, o.ipb);
+  o.iq = iqdrn;
+}
+
+// whole-array fix-ups of MAPPING_BL, :642-683, per element, in the reference's order (Q25)
+__device__ __forceinline__ void map_store(const MapOut& o, int iP, int jP, int m, size_t k, size_t nt, int32_t* MT,
+                                          double* AB, int16_t* IDP, float* DNP) {
+  double a = o.a, b = o.b;
+  int iq = o.iq;
+  int id = o.ipb;
+  if ((iP == (int)G_RMV) || (jP == (int)G_RMV)) { a = G_RMV; b = G_RMV; }
+  if ((a < 0.0) && (a > -G_REPS)) a = 0.0;
+  if ((b < 0.0) && (b > -G_REPS)) b = 0.0;
+  if ((a > G_RMV) && (a < 0.0)) { a = 0.5; id = 4; }
+  if (a > 1.0) { a = 0.5; id = 5; }
+  if ((b > G_RMV) && (b < 0.0)) { b = 0.5; id = 6; }
+  if (b > 1.0) { b = 0.5; id = 7; }
+  if (iq < 1) { iq = 1; id = 1; }
+  if (m <= -1) id = -1;
+  if (m == 0) id = -2;
+  if (m < -2) id = -3;
+  MT[k] = iP; MT[k + nt] = jP; MT[k + 2 * nt] = iq;
+  AB[k] = a; AB[k + nt] = b;
+  IDP[k] = (int16_t)id;
+  DNP[k] = o.dnp;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// EASY search (src/mod_manip.f90:967-1069) fused with the MAPPING_BL body: one thread per target.
+__global__ void __launch_bounds__(128)
+k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
+           const double* __restrict__ vlat, int sorted_lon, int sorted_lat, int jlo, int jhi, int32_t* MT, double* AB,
+           int16_t* IDP, float* DNP, int* err) {
+  const size_t nt = (size_t)tg.nx * tg.ny;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    int jj_t = (int)(k / tg.nx) + 1, ji_t = (int)(k % tg.nx) + 1;
+    int m = mask ? mask[k] : 1;
+    int iP = -1, jP = -1;
+    double rlon = trg_lon(tg, ji_t, jj_t), rlat = trg_lat(tg, ji_t, jj_t);
+    if (m == 1 && jj_t >= jlo && jj_t <= jhi) {
+      int ip = sorted_lon ? minloc_abs_sorted(vlon, sg.nx, rlon) : minloc_abs_linear(vlon, sg.nx, rlon);
+      int jp = sorted_lat ? minloc_abs_sorted(vlat, sg.nyw, rlat) : minloc_abs_linear(vlat, sg.nyw, rlat);
+      int i1s = max(ip - 4, 1), i2s = min(ip + 4, sg.nx);
+      int j1s = max(jp - 4, 1), j2s = min(jp + 4, sg.nyw);
+      double ux, uy, uz;
+      unit_vec(rlon, rlat, ux, uy, uz);
+      Best b;
+      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b);
+      iP = b.i; jP = b.j;
+      if (iP == 0 || jP == 0) atomicOr(err, 2);
+    }
+    MapOut o;
+    o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
+    if (m == 1) map_body(sg, k_ew, rlon, rlat, iP, jP, o, err);
+    map_store(o, iP, jP, m, k, nt, MT, AB, IDP, DNP);
+  }
+}
+
+// body only (after TWISTED): JI/JJ given
+__global__ void __launch_bounds__(128)
+k_map_body(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const int32_t* __restrict__ JI,
+           const int32_t* __restrict__ JJ, int32_t* MT, double* AB, int16_t* IDP, float* DNP, int* err) {
+  const size_t nt = (size_t)tg.nx * tg.ny;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    int jj_t = (int)(k / tg.nx) + 1, ji_t = (int)(k % tg.nx) + 1;
+    int m = mask[k];
+    int iP = JI[k], jP = JJ[k];
+    MapOut o;
+    o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
+    if (m == 1) map_body(sg, k_ew, trg_lon(tg, ji_t, jj_t), trg_lat(tg, ji_t, jj_t), iP, jP, o, err);
+    map_store(o, iP, jP, m, k, nt, MT, AB, IDP, DNP);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// TWISTED pieces
+// e1_s/e2_s (src/mod_manip.f90:1152-1164)
+__global__ void k_src_metrics(SrcGeom sg, double* e1, double* e2) {
+  size_t n = (size_t)sg.nx * sg.nyw;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int j = (int)(k / sg.nx) + 1, i = (int)(k % sg.nx) + 1;
+    double a = (double)40000.f, b = (double)40000.f;
+    int ie = (i <= sg.nx - 1) ? i : sg.nx - 1;  // e1_s(nx_s,:) = e1_s(nx_s-1,:)
+    int je = (j <= sg.nyw - 1) ? j : sg.nyw - 1;
+    if (sg.nx > 1) a = d_distance(src_lon(sg, ie, j), src_lon(sg, ie + 1, j), src_lat(sg, ie, j), src_lat(sg, ie + 1, j)) * 1000.0;
+    if (sg.nyw > 1) b = d_distance(src_lon(sg, i, je), src_lon(sg, i, je + 1), src_lat(sg, i, je), src_lat(sg, i, je + 1)) * 1000.0;
+    e1[k] = a;
+    e2[k] = b;
+  }
+}
+
+// argmin |Y - 90| with first-index tie-break (IS_POLAR_PROJ, src/mod_manip.f90:1862)
+__global__ void k_argmin_np(const double* __restrict__ Y, size_t n, int is1d, int nx, MinIdx* partial) {
+  MinIdx m;
+  m.v = 0; m.k = -1;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    double y = is1d ? Y[k / nx] : Y[k];
+    MinIdx c;
+    c.v = fabs(y - 90.0); c.k = (long long)k;
+    m = minidx_better(m, c);
+  }
+  m = warp_minidx(m);
+  __shared__ MinIdx sh[32];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    MinIdx r = sh[0];
+    for (int w = 1; w < (blockDim.x >> 5); w++) r = minidx_better(r, sh[w]);
+    partial[blockIdx.x] = r;
+  }
+}
+
+// J_VLAT_S (src/mod_manip.f90:1263-1286): thread per (column, bin)
+__global__ void k_jvlat(SrcGeom sg, int nsplit, const double* __restrict__ VB, int* jmaxb, int* jminb) {
+  int total = sg.nx * nsplit;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int b = t / sg.nx, i = t % sg.nx + 1;
+    double r1 = VB[b], r2 = VB[b + 1];
+    int jx = 0, jn = 0;
+    double vmax = 0, vmin = 0;
+    for (int j = 1; j <= sg.nyw; j++) {
+      double v = src_lat(sg, i, j);
+      if (v <= r2) { if (jx == 0 || v > vmax) { vmax = v; jx = j; } }
+      if (v > r1)  { if (jn == 0 || v < vmin) { vmin = v; jn = j; } }
+    }
+    atomicMax(&jmaxb[b], jx);
+    if (jn > 0) atomicMin(&jminb[b], jn);
+  }
+}
+
+// flags of targets to search, in processing order p = (row_k, i); order[] = compacted target indices
+__global__ void k_twisted_flags(TrgGeom tg, const int32_t* __restrict__ mask, int j_strt, int icr, int nrows, uint8_t* flags,
+                                int64_t* lin) {
+  size_t n = (size_t)nrows * tg.nx;
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+    int rk = (int)(p / tg.nx), i = (int)(p % tg.nx);
+    int jj = j_strt + rk * icr;
+    size_t k = (size_t)i + (size_t)(jj - 1) * tg.nx;
+    flags[p] = (mask[k] == 1) ? 1 : 0;
+    lin[p] = (int64_t)k;
+  }
+}
+
+struct TwParams {
+  int lStupido, nsplit;
+  const double* VB;   // [nsplit+1]
+  const int* JV;      // [2*nsplit] column-major (nsplit,2)
+  const double* e1;
+  const double* e2;
+  double frac_emax, sqrt2f;
+};
+
+// chain-independent band search (niter = 0,1,...), one warp per target (:1350-1426)
+__global__ void __launch_bounds__(256)
+k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ order, int T, int2* band_pos,
+               int8_t* band_found, int* err) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int q = warp; q < T; q += nwarps) {
+    size_t k = (size_t)order[q];
+    int jj_t = (int)(k / tg.nx) + 1, ji_t = (int)(k % tg.nx) + 1;
+    double rlon = trg_lon(tg, ji_t, jj_t), rlat = trg_lat(tg, ji_t, jj_t);
+    double ux, uy, uz;
+    unit_vec(rlon, rlat, ux, uy, uz);
+    int jlat = 0;
+    if (!tp.lStupido) {
+      for (jlat = 1; jlat <= tp.nsplit; jlat++) {
+        if (rlat == tp.VB[jlat - 1]) break;
+        if ((rlat > tp.VB[jlat - 1]) && (rlat <= tp.VB[jlat])) break;
+      }
+    }
+    int niter = 0, found = 0, bi = 0, bj = 0;
+    while (true) {
+      int j1s, j2s;
+      if (tp.lStupido) { j1s = 1; j2s = sg.nyw; }
+      else {
+        int a1 = max(jlat - niter, 1), a2 = min(jlat + niter, tp.nsplit);
+        j1s = tp.JV[(a1 - 1)];                    // (a1,1); a1 == nsplit+1 aliases (1,2)  (Q4)
+        j2s = tp.JV[(a2 - 1) + tp.nsplit];        // (a2,2)
+      }
+      long long ncand = (j2s >= j1s) ? (long long)sg.nx * (j2s - j1s + 1) : 0;
+      double bd = 0.0, bp = -4.0;
+      long long bk = -1;
+      for (long long c = lane; c < ncand; c += 32) {
+        int ji = (int)(c % sg.nx) + 1, jj = (int)(c / sg.nx) + j1s;
+        double vx, vy, vz;
+        src_vec(sg, ji, jj, vx, vy, vz);
+        double zpds = ux * vx + uy * vy + uz * vz;
+        if (bk >= 0 && zpds < bp - PDS_MARGIN) continue;
+        double d = G_ZR * pm_acos(fmin(zpds, 1.0));
+        if (bk < 0 || d < bd) { bd = d; bp = zpds; bk = c; }
+      }
+      MinIdx m;
+      m.v = bd; m.k = bk;
+      m = warp_minidx(m);
+      if (m.k < 0) { if (lane == 0) atomicOr(err, 4); break; }
+      bi = (int)(m.k % sg.nx) + 1;
+      bj = (int)(m.k / sg.nx) + j1s;
+      size_t ks = (size_t)(bi - 1) + (size_t)(bj - 1) * sg.nx;
+      double emax = fmax(tp.e1[ks], tp.e2[ks]) / 1000.0 * tp.sqrt2f;
+      if (m.v <= tp.frac_emax * emax) { found = 1; break; }
+      if (niter == 0) {
+        double lo1 = fmax(rlon - 0.5, 0.0), hi1 = fmin(rlon + 0.5, 360.0);
+        double lo2 = fmax(rlat - 0.5, -90.0), hi2 = fmin(rlat + 0.5, 90.0);
+        int any = 0;
+        size_t ns = (size_t)sg.nx * sg.nyw;
+        for (size_t c = lane; c < ns && !any; c += 32) {
+          int ji = (int)(c % sg.nx) + 1, jj = (int)(c / sg.nx) + 1;
+          double xs = src_lon(sg, ji, jj), ys = src_lat(sg, ji, jj);
+          if ((xs > lo1) && (xs < hi1) && (ys > lo2) && (ys < hi2)) any = 1;
+        }
+        any = __any_sync(0xffffffffu, any);
+        if (!any) break;
+      }
+      if (niter > tp.nsplit / 3) break;
+      niter++;
+    }
+    if (lane == 0) { band_pos[q] = make_int2(bi, bj); band_found[q] = (int8_t)found; }
+  }
+}
+
+// one pass of the chain: S_new[q] = f_q(S_old[q-1])   (:1336-1349, 1385-1391)
+__global__ void __launch_bounds__(128)
+k_twisted_chain(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ order, int T,
+                const int2* __restrict__ band_pos, const int8_t* __restrict__ band_found,
+                const int2* __restrict__ S_old, int2* S_new, int8_t* found, int* changed) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < T; q += gridDim.x * blockDim.x) {
+    size_t k = (size_t)order[q];
+    int jj_t = (int)(k / tg.nx) + 1, ji_t = (int)(k % tg.nx) + 1;
+    double rlat = trg_lat(tg, ji_t, jj_t);
+    int2 res = band_pos[q];
+    int fnd = band_found[q];
+    if (!(rlat > 60.0)) {
+      int2 pr = (q == 0) ? make_int2(0, 0) : S_old[q - 1];  // Q3: (0,0) before the first target
+      double rlon = trg_lon(tg, ji_t, jj_t);
+      double ux, uy, uz;
+      unit_vec(rlon, rlat, ux, uy, uz);
+      int i1s = max(pr.x - 5, 1), i2s = min(pr.x + 5, sg.nx);
+      int j1s = max(pr.y - 5, 1), j2s = min(pr.y + 5, sg.nyw);
+      Best b;
+      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b);
+      if (b.i != 0) {
+        size_t ks = (size_t)(b.i - 1) + (size_t)(b.j - 1) * sg.nx;
+        double emax = fmax(tp.e1[ks], tp.e2[ks]) / 1000.0 * tp.sqrt2f;
+        if (b.d <= tp.frac_emax * emax) { res = make_int2(b.i, b.j); fnd = 1; }
+      }
+    }
+    int2 old = S_old[q];
+    if (old.x != res.x || old.y != res.y) *changed = 1;
+    S_new[q] = res;
+    found[q] = (int8_t)fnd;
+  }
+}
+
+__global__ void k_twisted_scatter(const int64_t* __restrict__ order, int T, const int2* __restrict__ S,
+                                  const int8_t* __restrict__ found, int32_t* JI, int32_t* JJ) {
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < T; q += gridDim.x * blockDim.x) {
+    if (found[q]) { size_t k = (size_t)order[q]; JI[k] = S[q].x; JJ[k] = S[q].y; }
+  }
+}
+__global__ void k_fill_i32(int32_t* a, size_t n, int32_t v) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) a[k] = v;
+}
+// WHERE(JIpos==-1) mask_t=-1 ; WHERE(JJpos==-1) mask_t=-2   (:1434-1435)
+__global__ void k_twisted_mask(const int32_t* __restrict__ JI, const int32_t* __restrict__ JJ, int32_t* mask, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    if (JI[k] == -1) mask[k] = -1;
+    if (JJ[k] == -1) mask[k] = -2;
+  }
+}
+
+// ===================================================================================================
+// host orchestration
+static int fetch_d(sosie_ctx* ctx, const double* dptr, double* out) {
+  CK(cudaMemcpyAsync(out, dptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// coordinate part of BILIN_2D's prologue (:97-148): decide l_add_extra_j, build the working source
+int bilin_prepare_src(sosie_ctx* ctx) {
+  SrcGeom& sg = ctx->sg;
+  const int nx = sg.nx, ny = sg.ny;
+  const double* Xin = ctx->s_in_X.p;
+  const double* Yin = ctx->s_in_Y.p;
+  const int in_1d = sg.separable;  // at this point: "input given as 1-D axes"
+  cudaStream_t st = ctx->stream;
+  ctx->l_add_extra_j = 0;
+  double dyp = 0.0;
+  if (ctx->l_reg_src && (ny > 20) && (nx > 20)) {
+    double ymx, ym1;
+    int ih = nx / 2;  // Y1(nx1/2, ny1)
+    if (in_1d) { if (fetch_d(ctx, Yin + (ny - 1), &ymx)) return SOSIE_ERR_CUDA; if (fetch_d(ctx, Yin + (ny - 2), &ym1)) return SOSIE_ERR_CUDA; }
+    else {
+      if (fetch_d(ctx, Yin + (size_t)(ih - 1) + (size_t)(ny - 1) * nx, &ymx)) return SOSIE_ERR_CUDA;
+      if (fetch_d(ctx, Yin + (size_t)(ih - 1) + (size_t)(ny - 2) * nx, &ym1)) return SOSIE_ERR_CUDA;
+    }
+    if ((ymx < 90.0) && (2.0 * ymx - ym1 >= 90.0)) {
+      ctx->l_add_extra_j = 1;
+      dyp = ymx - ym1;  // YY(nx/2,ny) - YY(nx/2,ny-1)
+      if (!in_1d) {     // EXT_NORTH_TO_90_REGG sanity STOPs (:1803-1811) on the last row
+        std::vector<double> row(nx);
+        CK(cudaMemcpyAsync(row.data(), Yin + (size_t)(ny - 1) * nx, sizeof(double) * nx, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        double s = 0.0;
+        for (int i = 0; i < nx; i++) { double d = row[i] - ymx; s += d * d; }
+        if (s > (double)1.E-12f) { ctx->err = "EXT_NORTH_TO_90_REGG: grid doesnt seem to be regular"; return SOSIE_ERR_REF_STOP; }
+      }
+    }
+  }
+  sg.nyw = ny + (ctx->l_add_extra_j ? 2 : 0);
+  const int nyw = sg.nyw;
+  if (in_1d) {
+    CK(ctx->s_lat1.alloc(nyw));
+    CK(ctx->s_clon.alloc(nx)); CK(ctx->s_slon.alloc(nx)); CK(ctx->s_clat.alloc(nyw)); CK(ctx->s_slat.alloc(nyw));
+    k_lat_table<<<cdiv(nyw, 256), 256, 0, st>>>(Yin, ny, nyw, dyp, ctx->s_lat1.p); KLAUNCH_CHECK();
+    k_trig_table<<<cdiv(nx, 256), 256, 0, st>>>(Xin, nx, ctx->s_clon.p, ctx->s_slon.p); KLAUNCH_CHECK();
+    k_trig_table<<<cdiv(nyw, 256), 256, 0, st>>>(ctx->s_lat1.p, nyw, ctx->s_clat.p, ctx->s_slat.p); KLAUNCH_CHECK();
+    sg.separable = 1;
+    sg.lon1 = Xin; sg.lat1 = ctx->s_lat1.p;
+    sg.clon = ctx->s_clon.p; sg.slon = ctx->s_slon.p; sg.clat = ctx->s_clat.p; sg.slat = ctx->s_slat.p;
+  } else {
+    size_t n = (size_t)nx * nyw;
+    CK(ctx->s_X.alloc(n)); CK(ctx->s_Y.alloc(n)); CK(ctx->s_vx.alloc(n)); CK(ctx->s_vy.alloc(n)); CK(ctx->s_vz.alloc(n));
+    k_build_src2d<<<grid_for(ctx, n, 256), 256, 0, st>>>(Xin, Yin, nx, ny, nyw, 0, dyp, ctx->s_X.p, ctx->s_Y.p, ctx->s_vx.p,
+                                                          ctx->s_vy.p, ctx->s_vz.p); KLAUNCH_CHECK();
+    sg.separable = 0;
+    sg.X = ctx->s_X.p; sg.Y = ctx->s_Y.p; sg.vx = ctx->s_vx.p; sg.vy = ctx->s_vy.p; sg.vz = ctx->s_vz.p;
+  }
+  if (ctx->l_add_extra_j) {
+    CK(ctx->d_im.alloc(nx));
+    const double* lonrow = in_1d ? Xin : Xin + (size_t)(ny - 1) * nx;
+    k_jim_table<<<cdiv(nx, 128), 128, 0, st>>>(lonrow, nx, ctx->d_im.p); KLAUNCH_CHECK();
+  }
+  return SOSIE_OK;
+}
+
+static int is_sorted_host(const std::vector<double>& v, int off, int n) {
+  for (int i = 1; i < n; i++) if (v[off + i] < v[off + i - 1]) return 0;
+  return 1;
+}
+
+int bilin_map_impl(sosie_ctx* ctx) {
+  if (!ctx->grids_set) { ctx->err = "sosie_bilin_map: grids not set"; return SOSIE_ERR_STATE; }
+  SrcGeom& sg = ctx->sg;
+  TrgGeom& tg = ctx->tg;
+  cudaStream_t st = ctx->stream;
+  const size_t nt = (size_t)tg.nx * tg.ny;
+  const size_t nsrc = (size_t)sg.nx * sg.nyw;
+  CK(ctx->d_metrics.alloc(3 * nt)); CK(ctx->d_ab.alloc(2 * nt)); CK(ctx->d_ipb.alloc(nt)); CK(ctx->d_dnp.alloc(nt));
+  DBuf<Prelude> dpre; CK(dpre.alloc(1));
+  DBuf<int> derr; CK(derr.alloc(1));
+  CK(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+  k_prelude_init<<<1, 1, 0, st>>>(dpre.p); KLAUNCH_CHECK();
+
+  // ---- FIND_NEAREST_POINT prelude (:888-947)
+  // y_min_s / y_max_s : MINVAL/MAXVAL(Ysrc) over the working array (pole rows included)
+  if (sg.separable) { k_minmax<<<grid_for(ctx, sg.nyw, 256), 256, 0, st>>>(sg.lat1, sg.nyw, &dpre.p->ymin_s, &dpre.p->ymax_s); KLAUNCH_CHECK(); }
+  else { k_minmax<<<grid_for(ctx, nsrc, 256), 256, 0, st>>>(sg.Y, nsrc, &dpre.p->ymin_s, &dpre.p->ymax_s); KLAUNCH_CHECK(); }
+  { size_t nty = tg.is_1d ? (size_t)tg.ny : nt;
+    k_minmax<<<grid_for(ctx, nty, 256), 256, 0, st>>>(tg.Y, nty, &dpre.p->ymin_t, &dpre.p->ymax_t); KLAUNCH_CHECK(); }
+  if (!sg.separable) { k_is_regular<<<grid_for(ctx, (size_t)sg.nyw * 32, 256), 256, 0, st>>>(sg.X, sg.Y, sg.nx, sg.nyw, &dpre.p->irreg_s); KLAUNCH_CHECK(); }
+  if (!tg.is_1d) { k_is_regular<<<grid_for(ctx, (size_t)tg.ny * 32, 256), 256, 0, st>>>(tg.X, tg.Y, tg.nx, tg.ny, &dpre.p->irreg_t); KLAUNCH_CHECK(); }
+  if (tg.nx > 2) {
+    k_rtmp<<<1, 1, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
+    k_min_dlat<<<grid_for(ctx, nt, 256), 256, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
+  }
+  Prelude hp;
+  CK(cudaMemcpyAsync(&hp, dpre.p, sizeof(Prelude), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const double y_min_s = dec_d_host(hp.ymin_s), y_max_s = dec_d_host(hp.ymax_s);
+  const double y_min_t = dec_d_host(hp.ymin_t), y_max_t = dec_d_host(hp.ymax_t);
+  const bool l_is_reg_s = (hp.irreg_s == 0), l_is_reg_t = (hp.irreg_t == 0);
+  double rmin_dlat_dj = (double)-100.f;
+  if (tg.nx > 2 && tg.ny >= 2) rmin_dlat_dj = dec_d_host(hp.rmin_dlat);
+  int j_strt_t = 1, j_stop_t = tg.ny, jlat_icr = 1;
+  if ((rmin_dlat_dj > (double)-1.E-12f) || l_is_reg_t) {
+    k_jrange<<<grid_for(ctx, tg.nx, 128), 128, 0, st>>>(tg, dpre.p, y_min_s, y_max_s); KLAUNCH_CHECK();
+    CK(cudaMemcpyAsync(&hp, dpre.p, sizeof(Prelude), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    j_strt_t = hp.j_strt; j_stop_t = hp.j_stop;
+    if (j_strt_t > j_stop_t) jlat_icr = -1;
+    if (j_strt_t < 1 || j_strt_t > tg.ny || j_stop_t < 1 || j_stop_t > tg.ny) {
+      ctx->err = "FIND_NEAREST_POINT: target latitudes not covered by the source (the reference loops out of bounds)";
+      return SOSIE_ERR_REF_STOP;
+    }
+  }
+  ctx->map_info[0] = j_strt_t; ctx->map_info[1] = j_stop_t; ctx->map_info[2] = jlat_icr;
+  ctx->map_info[3] = l_is_reg_s; ctx->map_info[4] = l_is_reg_t; ctx->map_info[6] = 0; ctx->map_info[7] = ctx->l_add_extra_j;
+
+  int32_t* MT = ctx->d_metrics.p;
+  double* AB = ctx->d_ab.p;
+  int16_t* IDP = ctx->d_ipb.p;
+  float* DNP = ctx->d_dnp.p;
+
+  if (l_is_reg_s) {
+    // ---- FIND_NEAREST_EASY + body, fused
+    ctx->map_info[5] = 0;
+    DBuf<double> vax; CK(vax.alloc(sg.nx + sg.nyw));
+    k_gather_axes<<<cdiv(sg.nx + sg.nyw, 256), 256, 0, st>>>(sg, vax.p, vax.p + sg.nx); KLAUNCH_CHECK();
+    std::vector<double> hax(sg.nx + sg.nyw);
+    CK(cudaMemcpyAsync(hax.data(), vax.p, sizeof(double) * hax.size(), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int sorted_lon = is_sorted_host(hax, 0, sg.nx), sorted_lat = is_sorted_host(hax, sg.nx, sg.nyw);
+    int jlo = j_strt_t < j_stop_t ? j_strt_t : j_stop_t, jhi = j_strt_t < j_stop_t ? j_stop_t : j_strt_t;
+    k_map_easy<<<grid_for(ctx, nt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
+                                                           sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p); KLAUNCH_CHECK();
+    CK(cudaStreamSynchronize(st));  // vax lifetime
+  } else {
+    // ---- FIND_NEAREST_TWISTED
+    ctx->map_info[5] = 1;
+    if ((y_min_t >= y_max_s) || (y_max_t <= y_min_s)) { ctx->err = "FIND_NEAREST_TWISTED: Target and source latitudes do not overlap!"; return SOSIE_ERR_REF_STOP; }
+    if (sg.separable) { ctx->err = "internal: TWISTED with separable source"; return SOSIE_ERR_ARG; }
+    DBuf<double> e1, e2; CK(e1.alloc(nsrc)); CK(e2.alloc(nsrc));
+    k_src_metrics<<<grid_for(ctx, nsrc, 128), 128, 0, st>>>(sg, e1.p, e2.p); KLAUNCH_CHECK();
+    // IS_POLAR_PROJ on source and target (:1171,1181)
+    auto polar = [&](const double* X, const double* Y, int nx, int ny, int is1d, double ymax, bool* lpp) -> int {
+      *lpp = false;
+      if (!(ymax > 88.0)) return 0;
+      const int nb = 64;
+      DBuf<MinIdx> part; CK(part.alloc(nb));
+      size_t n = (size_t)nx * ny;
+      k_argmin_np<<<nb, 256, 0, st>>>(Y, n, is1d, nx, part.p); KLAUNCH_CHECK();
+      MinIdx hpart[nb];
+      CK(cudaMemcpyAsync(hpart, part.p, sizeof(hpart), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      MinIdx r = hpart[0];
+      for (int b = 1; b < nb; b++) {
+        MinIdx c = hpart[b];
+        if (c.k < 0) continue;
+        if (r.k < 0 || c.v < r.v || (c.v == r.v && c.k < r.k)) r = c;
+      }
+      int iNP = (int)(r.k % nx) + 1, jNP = (int)(r.k / nx) + 1;
+      if (jNP - 3 < 1 || jNP + 3 > ny) return 0;  // Q5: out-of-range probe DEFINED as "not polar"
+      auto getY = [&](int i, int j, double* v) -> int { return fetch_d(ctx, is1d ? Y + (j - 1) : Y + (size_t)(i - 1) + (size_t)(j - 1) * nx, v); };
+      auto getX = [&](int i, int j, double* v) -> int { return fetch_d(ctx, is1d ? X + (i - 1) : X + (size_t)(i - 1) + (size_t)(j - 1) * nx, v); };
+      double ym, y0, yp, xm, xp;
+      if (getY(iNP, jNP - 3, &ym) || getY(iNP, jNP, &y0) || getY(iNP, jNP + 3, &yp)) return SOSIE_ERR_CUDA;
+      bool lipp = (ym < y0) && (yp < y0);
+      if (lipp) {
+        if (getX(iNP, jNP - 3, &xm) || getX(iNP, jNP + 3, &xp)) return SOSIE_ERR_CUDA;
+        double d = fabs(xm - xp);
+        lipp = (d > 100.0) && (d < 220.0);
+      }
+      *lpp = lipp;
+      return 0;
+    };
+    bool lNPs, lNPt;
+    if (int rc = polar(sg.X, sg.Y, sg.nx, sg.nyw, 0, y_max_s, &lNPs)) return rc;
+    if (int rc = polar(tg.X, tg.Y, tg.nx, tg.ny, tg.is_1d, y_max_t, &lNPt)) return rc;
+    const bool lStupido = lNPs || lNPt;
+    int nsplit = 0;  // undefined in the reference when lStupido; DEFINED 0 (see oracle)
+    DBuf<double> dVB; DBuf<int> dJV;
+    if (!lStupido) {
+      double y_max_bnd = std::min(y_max_t, y_max_s), y_max_bnd0 = y_max_bnd;
+      double y_min_bnd = std::max(y_min_t, y_min_s), y_min_bnd0 = y_min_bnd;
+      y_max_bnd = std::min((double)(int)(y_max_bnd + 2.0), 90.0);
+      y_min_bnd = std::max((double)(int)(y_min_bnd - 2.0), -90.0);
+      y_max_bnd = std::min((double)lround(y_max_bnd / 0.5) * 0.5, 90.0);
+      y_min_bnd = std::max((double)lround(y_min_bnd / 0.5) * 0.5, -90.0);
+      y_max_bnd = std::max(y_max_bnd, y_max_bnd0);
+      y_min_bnd = std::min(y_min_bnd, y_min_bnd0);
+      nsplit = std::max((int)(((double)40.0f * (y_max_bnd - y_min_bnd)) / 180.0), 1);
+      std::vector<double> VB(nsplit + 1);
+      double dy = (y_max_bnd - y_min_bnd) / (double)(float)nsplit;
+      for (int jl = 1; jl <= nsplit + 1; jl++) VB[jl - 1] = y_min_bnd + (double)(float)(jl - 1) * dy;
+      if ((y_min_bnd > y_min_bnd0) || (y_max_bnd < y_max_bnd0)) { ctx->err = "FIND_NEAREST_POINT: Bounds for latitude for VLAT_SPLIT_BOUNDS are bad!"; return SOSIE_ERR_REF_STOP; }
+      CK(dVB.alloc(nsplit + 1)); CK(dJV.alloc(2 * nsplit));
+      CK(cudaMemcpyAsync(dVB.p, VB.data(), sizeof(double) * (nsplit + 1), cudaMemcpyHostToDevice, st));
+      DBuf<int> jmx, jmn; CK(jmx.alloc(nsplit)); CK(jmn.alloc(nsplit));
+      CK(cudaMemsetAsync(jmx.p, 0, sizeof(int) * nsplit, st));
+      k_fill_i32<<<1, 64, 0, st>>>(jmn.p, nsplit, 2147483647); KLAUNCH_CHECK();
+      k_jvlat<<<grid_for(ctx, (size_t)sg.nx * nsplit, 128), 128, 0, st>>>(sg, nsplit, dVB.p, jmx.p, jmn.p); KLAUNCH_CHECK();
+      std::vector<int> hmx(nsplit), hmn(nsplit), JV(2 * nsplit);
+      CK(cudaMemcpyAsync(hmx.data(), jmx.p, sizeof(int) * nsplit, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(hmn.data(), jmn.p, sizeof(int) * nsplit, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      for (int b = 0; b < nsplit; b++) {
+        JV[b] = std::max(hmn[b] - 1, 1);
+        JV[b + nsplit] = std::min(hmx[b] + 1, sg.nyw);
+        if (JV[b + nsplit] <= JV[b]) { ctx->err = "FIND_NEAREST_TWISTED: ERROR: jj_stop > jj_start !"; return SOSIE_ERR_REF_STOP; }
+      }
+      CK(cudaMemcpyAsync(dJV.p, JV.data(), sizeof(int) * 2 * nsplit, cudaMemcpyHostToDevice, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    TwParams tp;
+    tp.lStupido = lStupido ? 1 : 0; tp.nsplit = nsplit; tp.VB = dVB.p; tp.JV = dJV.p; tp.e1 = e1.p; tp.e2 = e2.p;
+    tp.frac_emax = (double)0.51f; tp.sqrt2f = (double)sqrtf(2.0f);
+    // processing order of the searched targets
+    long ntrip = ((long)j_stop_t - (long)j_strt_t + jlat_icr) / jlat_icr;
+    if (ntrip < 0) ntrip = 0;
+    size_t np = (size_t)ntrip * tg.nx;
+    DBuf<int32_t> JI, JJ; CK(JI.alloc(nt)); CK(JJ.alloc(nt));
+    k_fill_i32<<<grid_for(ctx, nt, 256), 256, 0, st>>>(JI.p, nt, -1); KLAUNCH_CHECK();
+    k_fill_i32<<<grid_for(ctx, nt, 256), 256, 0, st>>>(JJ.p, nt, -1); KLAUNCH_CHECK();
+    int T = 0;
+    DBuf<int64_t> order;
+    if (np > 0) {
+      DBuf<uint8_t> flags; DBuf<int64_t> lin; DBuf<int> dnum;
+      CK(flags.alloc(np)); CK(lin.alloc(np)); CK(order.alloc(np)); CK(dnum.alloc(1));
+      k_twisted_flags<<<grid_for(ctx, np, 256), 256, 0, st>>>(tg, ctx->t_mask.p, j_strt_t, jlat_icr, (int)ntrip, flags.p, lin.p); KLAUNCH_CHECK();
+      size_t tmpb = 0;
+      cub::DeviceSelect::Flagged(nullptr, tmpb, lin.p, flags.p, order.p, dnum.p, (int)np, st);
+      DBuf<uint8_t> tmp; CK(tmp.alloc(tmpb + 16));
+      CK(cub::DeviceSelect::Flagged(tmp.p, tmpb, lin.p, flags.p, order.p, dnum.p, (int)np, st));
+      ctx->launches += 2;
+      CK(cudaMemcpyAsync(&T, dnum.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+    }
+    if (T > 0) {
+      DBuf<int2> bpos, S0, S1; DBuf<int8_t> bfound, found; DBuf<int> dchg;
+      CK(bpos.alloc(T)); CK(S0.alloc(T)); CK(S1.alloc(T)); CK(bfound.alloc(T)); CK(found.alloc(T)); CK(dchg.alloc(1));
+      k_twisted_band<<<grid_for(ctx, (size_t)T * 32, 256), 256, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, derr.p); KLAUNCH_CHECK();
+      CK(cudaMemcpyAsync(S0.p, bpos.p, sizeof(int2) * T, cudaMemcpyDeviceToDevice, st));
+      int2* Sa = S0.p;
+      int2* Sb = S1.p;
+      int iters = 0;
+      while (true) {
+        CK(cudaMemsetAsync(dchg.p, 0, sizeof(int), st));
+        k_twisted_chain<<<grid_for(ctx, T, 128), 128, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, Sa, Sb, found.p, dchg.p); KLAUNCH_CHECK();
+        int chg = 0;
+        CK(cudaMemcpyAsync(&chg, dchg.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        iters++;
+        std::swap(Sa, Sb);
+        if (!chg) break;
+        if (iters > T + 2) { ctx->err = "internal: TWISTED chain did not converge"; return SOSIE_ERR_CUDA; }
+      }
+      ctx->map_info[6] = iters;
+      k_twisted_scatter<<<grid_for(ctx, T, 256), 256, 0, st>>>(order.p, T, Sa, found.p, JI.p, JJ.p); KLAUNCH_CHECK();
+    }
+    k_twisted_mask<<<grid_for(ctx, nt, 256), 256, 0, st>>>(JI.p, JJ.p, ctx->t_mask.p, nt); KLAUNCH_CHECK();
+    k_map_body<<<grid_for(ctx, nt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, JI.p, JJ.p, MT, AB, IDP, DNP, derr.p); KLAUNCH_CHECK();
+    CK(cudaStreamSynchronize(st));
+  }
+  int herr = 0;
+  CK(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (herr & 1) { ctx->err = "ERROR (L_InPoly of mod_poly.f90): we only expect positive longitudes!"; return SOSIE_ERR_REF_STOP; }
+  if (herr & 6) { ctx->err = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)"; return SOSIE_ERR_REF_STOP; }
+  ctx->map_ready = true;
+  ctx->map_nt = nt;
+  ctx->pack_ready = false;
+  return SOSIE_OK;
+}

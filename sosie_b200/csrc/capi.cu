@@ -1,0 +1,410 @@
+// capi.cu -- extern "C" entry points declared in include/sosie_b200.h.
+// Host pointers are staged through device buffers owned by the context; _dev entries work on the
+// caller's device pointers.  No CPU compute path exists: without a CUDA device every call fails.
+#include <algorithm>
+
+#include "geom.cuh"
+
+int akima_expand_axes(sosie_ctx* ctx, const double* dX1d, const double* dY1d, int nx, int ny, double* dX, double* dY);
+
+#define NEED(ctx_)                                   \
+  if (!(ctx_)) return SOSIE_ERR_ARG;                 \
+  sosie_ctx* ctx = (ctx_);                           \
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return SOSIE_ERR_CUDA; }
+
+extern "C" {
+
+const char* sosie_version(void) { return "sosie_b200 0.1 (sm_100a)"; }
+
+int sosie_create(sosie_ctx** out, int device) {
+  if (!out) return SOSIE_ERR_ARG;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return SOSIE_ERR_CUDA;
+  if (device < 0 || device >= ndev) return SOSIE_ERR_ARG;
+  if (cudaSetDevice(device) != cudaSuccess) return SOSIE_ERR_CUDA;
+  sosie_ctx* c = new sosie_ctx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SOSIE_ERR_CUDA; }
+  c->own_stream = true;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->num_sms = sms;
+  *out = c;
+  return SOSIE_OK;
+}
+
+int sosie_destroy(sosie_ctx* c) {
+  if (!c) return SOSIE_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SOSIE_OK;
+}
+
+const char* sosie_last_error(const sosie_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int sosie_set_stream(sosie_ctx* c, void* s) {
+  NEED(c);
+  cudaStreamSynchronize(ctx->stream);
+  if (s) {
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)s;
+    ctx->own_stream = false;
+  } else if (!ctx->own_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return SOSIE_OK;
+}
+
+int sosie_sync(sosie_ctx* c) {
+  NEED(c);
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SOSIE_OK;
+}
+
+int64_t sosie_launch_count(const sosie_ctx* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------
+static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_1d, int l_reg_src, int nx2, int ny2, int trg_1d,
+                            const int32_t* dmask, bool mask_on_device, int i_orca_trg) {
+  if (nx1 < 3 || ny1 < 3 || nx2 < 1 || ny2 < 1) { ctx->err = "sosie_bilin_set_grids: bad extents"; return SOSIE_ERR_ARG; }
+  ctx->k_ew = k_ew; ctx->l_reg_src = l_reg_src; ctx->i_orca_trg = i_orca_trg;
+  ctx->sg = SrcGeom();
+  ctx->sg.nx = nx1; ctx->sg.ny = ny1; ctx->sg.separable = src_1d ? 1 : 0;
+  const bool keep_map = ctx->map_ready && ctx->map_nt == (size_t)nx2 * ny2 && ctx->tg.nx == nx2 && ctx->tg.ny == ny2 &&
+                        ctx->map_info[5] == -1;  // -1: mapping came from sosie_bilin_load_map
+  ctx->tg = TrgGeom();
+  ctx->tg.nx = nx2; ctx->tg.ny = ny2; ctx->tg.is_1d = trg_1d ? 1 : 0;
+  ctx->tg.X = ctx->t_X.p; ctx->tg.Y = ctx->t_Y.p;
+  const size_t nt = (size_t)nx2 * ny2;
+  CK(ctx->t_mask.alloc(nt));
+  if (dmask) {
+    CK(cudaMemcpyAsync(ctx->t_mask.p, dmask, nt * sizeof(int32_t), mask_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    std::vector<int32_t> ones(nt, 1);
+    CK(cudaMemcpyAsync(ctx->t_mask.p, ones.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  if (int rc = bilin_prepare_src(ctx)) return rc;
+  ctx->grids_set = true;
+  ctx->pack_ready = false;
+  if (!keep_map) ctx->map_ready = false;
+  return SOSIE_OK;
+}
+
+int sosie_bilin_set_grids(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
+                          int32_t l_reg_src, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d,
+                          const int32_t* mask, int32_t i_orca_trg) {
+  NEED(c);
+  if (!X10 || !Y10 || !X20 || !Y20) { ctx->err = "sosie_bilin_set_grids: null coordinate pointer"; return SOSIE_ERR_ARG; }
+  size_t nsx = src_1d ? (size_t)nx1 : (size_t)nx1 * ny1, nsy = src_1d ? (size_t)ny1 : (size_t)nx1 * ny1;
+  size_t ntx = trg_1d ? (size_t)nx2 : (size_t)nx2 * ny2, nty = trg_1d ? (size_t)ny2 : (size_t)nx2 * ny2;
+  ctx->s_in_X.release(); ctx->s_in_Y.release(); ctx->t_X.release(); ctx->t_Y.release();
+  CK(ctx->s_in_X.alloc(nsx)); CK(ctx->s_in_Y.alloc(nsy)); CK(ctx->t_X.alloc(ntx)); CK(ctx->t_Y.alloc(nty));
+  CK(cudaMemcpyAsync(ctx->s_in_X.p, X10, nsx * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->s_in_Y.p, Y10, nsy * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->t_X.p, X20, ntx * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->t_Y.p, Y20, nty * 8, cudaMemcpyHostToDevice, ctx->stream));
+  return set_grids_common(ctx, k_ew, nx1, ny1, src_1d, l_reg_src, nx2, ny2, trg_1d, mask, false, i_orca_trg);
+}
+
+int sosie_bilin_set_grids_dev(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* dX10, const double* dY10,
+                              int32_t src_1d, int32_t l_reg_src, int32_t nx2, int32_t ny2, const double* dX20, const double* dY20,
+                              int32_t trg_1d, const int32_t* dmask, int32_t i_orca_trg) {
+  NEED(c);
+  if (!dX10 || !dY10 || !dX20 || !dY20) { ctx->err = "sosie_bilin_set_grids_dev: null coordinate pointer"; return SOSIE_ERR_ARG; }
+  size_t nsx = src_1d ? (size_t)nx1 : (size_t)nx1 * ny1, nsy = src_1d ? (size_t)ny1 : (size_t)nx1 * ny1;
+  size_t ntx = trg_1d ? (size_t)nx2 : (size_t)nx2 * ny2, nty = trg_1d ? (size_t)ny2 : (size_t)nx2 * ny2;
+  ctx->s_in_X.borrow(dX10, nsx); ctx->s_in_Y.borrow(dY10, nsy); ctx->t_X.borrow(dX20, ntx); ctx->t_Y.borrow(dY20, nty);
+  return set_grids_common(ctx, k_ew, nx1, ny1, src_1d, l_reg_src, nx2, ny2, trg_1d, dmask, true, i_orca_trg);
+}
+
+int sosie_bilin_map(sosie_ctx* c) {
+  NEED(c);
+  return bilin_map_impl(ctx);
+}
+
+int sosie_bilin_map_info(sosie_ctx* c, int32_t* info) {
+  NEED(c);
+  if (!info) return SOSIE_ERR_ARG;
+  for (int k = 0; k < 8; k++) info[k] = ctx->map_info[k];
+  return SOSIE_OK;
+}
+
+int sosie_bilin_get_map(sosie_ctx* c, int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np, int32_t* mask_out) {
+  NEED(c);
+  if (!ctx->map_ready) { ctx->err = "sosie_bilin_get_map: no mapping"; return SOSIE_ERR_STATE; }
+  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
+  cudaStream_t st = ctx->stream;
+  if (metrics) CK(cudaMemcpyAsync(metrics, ctx->d_metrics.p, 3 * nt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (alphabeta) CK(cudaMemcpyAsync(alphabeta, ctx->d_ab.p, 2 * nt * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (id_problem) CK(cudaMemcpyAsync(id_problem, ctx->d_ipb.p, nt * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  if (dist_np && ctx->d_dnp.p) CK(cudaMemcpyAsync(dist_np, ctx->d_dnp.p, nt * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (mask_out && ctx->t_mask.p) CK(cudaMemcpyAsync(mask_out, ctx->t_mask.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_bilin_load_map(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32_t* metrics, const double* alphabeta,
+                         const int16_t* id_problem) {
+  NEED(c);
+  if (!metrics || !alphabeta || nx2 < 1 || ny2 < 1) { ctx->err = "sosie_bilin_load_map: bad arguments"; return SOSIE_ERR_ARG; }
+  if (ctx->grids_set && (ctx->tg.nx != nx2 || ctx->tg.ny != ny2)) ctx->grids_set = false;  // a new grid pair follows
+  const size_t nt = (size_t)nx2 * ny2;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->d_metrics.alloc(3 * nt)); CK(ctx->d_ab.alloc(2 * nt)); CK(ctx->d_ipb.alloc(nt)); CK(ctx->d_dnp.alloc(nt));
+  ctx->map_nt = nt;
+  CK(cudaMemcpyAsync(ctx->d_metrics.p, metrics, 3 * nt * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_ab.p, alphabeta, 2 * nt * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (id_problem) CK(cudaMemcpyAsync(ctx->d_ipb.p, id_problem, nt * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  else CK(cudaMemsetAsync(ctx->d_ipb.p, 0, nt * sizeof(int16_t), st));
+  CK(cudaMemsetAsync(ctx->d_dnp.p, 0, nt * sizeof(float), st));
+  CK(cudaStreamSynchronize(st));
+  if (!ctx->grids_set) { ctx->tg.nx = nx2; ctx->tg.ny = ny2; }
+  ctx->map_ready = true;
+  ctx->pack_ready = false;
+  for (int k = 0; k < 8; k++) ctx->map_info[k] = 0;
+  ctx->map_info[5] = -1;
+  return SOSIE_OK;
+}
+
+// host-pointer apply: slabs are streamed through device staging buffers in chunks
+static int apply_host(sosie_ctx* ctx, int nslab, const float* Z1, float* Z2, int first_call) {
+  if (!ctx->grids_set) { ctx->err = "sosie_bilin_apply: grids not set"; return SOSIE_ERR_STATE; }
+  const size_t n1 = (size_t)ctx->sg.nx * ctx->sg.ny, n2 = (size_t)ctx->tg.nx * ctx->tg.ny;
+  const size_t budget = (size_t)6 << 30;  // bytes of staging per chunk
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nslab, budget / ((n1 + n2) * sizeof(float))));
+  CK(ctx->d_stage1.alloc(n1 * chunk));
+  DBuf<float> out; CK(out.alloc(n2 * chunk));
+  cudaStream_t st = ctx->stream;
+  for (int s0 = 0; s0 < nslab; s0 += chunk) {
+    int ns = std::min(chunk, nslab - s0);
+    CK(cudaMemcpyAsync(ctx->d_stage1.p, Z1 + (size_t)s0 * n1, n1 * ns * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = bilin_apply_impl(ctx, ns, ctx->d_stage1.p, out.p, first_call && s0 == 0, 0, 0.f, 0.f, nullptr, 0.f)) return rc;
+    CK(cudaMemcpyAsync(Z2 + (size_t)s0 * n2, out.p, n2 * ns * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_bilin_apply(sosie_ctx* c, int32_t nslab, const float* Z1, float* Z2, int32_t first_call) {
+  NEED(c);
+  if (!Z1 || !Z2 || nslab < 0) { ctx->err = "sosie_bilin_apply: bad arguments"; return SOSIE_ERR_ARG; }
+  return apply_host(ctx, nslab, Z1, Z2, first_call);
+}
+
+int sosie_bilin_apply_dev(sosie_ctx* c, int32_t nslab, const float* dZ1, float* dZ2, int32_t first_call) {
+  NEED(c);
+  if (!ctx->grids_set) { ctx->err = "sosie_bilin_apply_dev: grids not set"; return SOSIE_ERR_STATE; }
+  return bilin_apply_impl(ctx, nslab, dZ1, dZ2, first_call, 0, 0.f, 0.f, nullptr, 0.f);
+}
+
+int sosie_bilin_apply_ex_dev(sosie_ctx* c, int32_t nslab, const float* dZ1, float* dZ2, int32_t first_call, int32_t use_clamp,
+                             float vmin, float vmax, const int32_t* dmask_trg, float rmiss_val) {
+  NEED(c);
+  if (!ctx->grids_set) { ctx->err = "sosie_bilin_apply_ex_dev: grids not set"; return SOSIE_ERR_STATE; }
+  return bilin_apply_impl(ctx, nslab, dZ1, dZ2, first_call, use_clamp, vmin, vmax, dmask_trg, rmiss_val);
+}
+
+int sosie_bilin_apply_uv_dev(sosie_ctx* c, int32_t nslab, const float* dU1, const float* dV1, float* dUo, float* dVo,
+                             const double* dxcos, const double* dxsin) {
+  NEED(c);
+  if (!ctx->grids_set) { ctx->err = "sosie_bilin_apply_uv_dev: grids not set"; return SOSIE_ERR_STATE; }
+  return bilin_apply_uv_impl(ctx, nslab, dU1, dV1, dUo, dVo, dxcos, dxsin);
+}
+
+int sosie_bilin_2d(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
+                   const float* Z1, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
+                   const int32_t* mask, int32_t l_reg_src, int32_t i_orca_trg, int32_t* l_first_call, int32_t have_mapping,
+                   int32_t nslab) {
+  NEED(c);
+  if (!l_first_call) return SOSIE_ERR_ARG;
+  int first = *l_first_call;
+  if (first) {
+    if (int rc = sosie_bilin_set_grids(ctx, k_ew, nx1, ny1, X10, Y10, src_1d, l_reg_src, nx2, ny2, X20, Y20, trg_1d, mask, i_orca_trg)) return rc;
+    if (!have_mapping) { if (int rc = bilin_map_impl(ctx)) return rc; }
+    else if (!ctx->map_ready) { ctx->err = "sosie_bilin_2d: have_mapping set but no mapping loaded"; return SOSIE_ERR_STATE; }
+  } else {
+    if (!ctx->grids_set || ctx->sg.nx != nx1 || ctx->sg.ny != ny1 || ctx->tg.nx != nx2 || ctx->tg.ny != ny2) {
+      ctx->err = "sosie_bilin_2d: extents differ from the first call"; return SOSIE_ERR_ARG;
+    }
+  }
+  if (int rc = apply_host(ctx, nslab, Z1, Z2, first)) return rc;
+  *l_first_call = 0;  // l_first_call_interp_routine = .FALSE. (:267)
+  return SOSIE_OK;
+}
+
+int sosie_interp_bl(sosie_ctx* c, int32_t k_ew, int32_t nxi, int32_t nyi, const float* Z_in, int32_t n, const int32_t* jiP,
+                    const int32_t* jjP, const int32_t* iqd, const double* xa, const double* xb, float* out) {
+  NEED(c);
+  if (n <= 0) return SOSIE_OK;
+  cudaStream_t st = ctx->stream;
+  DBuf<float> dZ, dout; DBuf<int32_t> di, dj, dq; DBuf<double> da, db;
+  size_t nz = (size_t)nxi * nyi;
+  CK(dZ.alloc(nz)); CK(dout.alloc(n)); CK(di.alloc(n)); CK(dj.alloc(n)); CK(dq.alloc(n)); CK(da.alloc(n)); CK(db.alloc(n));
+  CK(cudaMemcpyAsync(dZ.p, Z_in, nz * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(di.p, jiP, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dj.p, jjP, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dq.p, iqd, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(da.p, xa, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(db.p, xb, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if (int rc = interp_bl_impl(ctx, k_ew, nxi, nyi, dZ.p, n, di.p, dj.p, dq.p, da.p, db.p, dout.p)) return rc;
+  CK(cudaMemcpyAsync(out, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int sosie_akima_set_grids(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
+                          int32_t i_orca_src, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d) {
+  NEED(c);
+  if (nx1 < 3 || ny1 < 3 || nx2 < 1 || ny2 < 1 || !X10 || !Y10 || !X20 || !Y20) { ctx->err = "sosie_akima_set_grids: bad arguments"; return SOSIE_ERR_ARG; }
+  cudaStream_t st = ctx->stream;
+  ctx->ak_set = false;
+  ctx->ak_kew = k_ew; ctx->ak_nx1 = nx1; ctx->ak_ny1 = ny1; ctx->ak_nx2 = nx2; ctx->ak_ny2 = ny2; ctx->ak_iorca = i_orca_src;
+  const size_t n1 = (size_t)nx1 * ny1, nt = (size_t)nx2 * ny2;
+  // stage the 2-D source coordinates in ak_ZX8/ak_ZY8 (akima_prepare_impl consumes them)
+  ctx->ak_ZX8.release(); ctx->ak_ZY8.release();
+  CK(ctx->ak_ZX8.alloc(n1)); CK(ctx->ak_ZY8.alloc(n1));
+  if (src_1d) {
+    DBuf<double> ax, ay; CK(ax.alloc(nx1)); CK(ay.alloc(ny1));
+    CK(cudaMemcpyAsync(ax.p, X10, (size_t)nx1 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ay.p, Y10, (size_t)ny1 * 8, cudaMemcpyHostToDevice, st));
+    if (int rc = akima_expand_axes(ctx, ax.p, ay.p, nx1, ny1, ctx->ak_ZX8.p, ctx->ak_ZY8.p)) return rc;
+    CK(cudaStreamSynchronize(st));
+  } else {
+    CK(cudaMemcpyAsync(ctx->ak_ZX8.p, X10, n1 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->ak_ZY8.p, Y10, n1 * 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(ctx->ak_X2.alloc(nt)); CK(ctx->ak_Y2.alloc(nt));
+  if (trg_1d) {
+    DBuf<double> ax, ay; CK(ax.alloc(nx2)); CK(ay.alloc(ny2));
+    CK(cudaMemcpyAsync(ax.p, X20, (size_t)nx2 * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ay.p, Y20, (size_t)ny2 * 8, cudaMemcpyHostToDevice, st));
+    if (int rc = akima_expand_axes(ctx, ax.p, ay.p, nx2, ny2, ctx->ak_X2.p, ctx->ak_Y2.p)) return rc;
+    CK(cudaStreamSynchronize(st));
+  } else {
+    CK(cudaMemcpyAsync(ctx->ak_X2.p, X20, nt * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->ak_Y2.p, Y20, nt * 8, cudaMemcpyHostToDevice, st));
+  }
+  return akima_prepare_impl(ctx);
+}
+
+int sosie_akima_apply_dev(sosie_ctx* c, int32_t nslab, const float* dZ1, float* dZ2) {
+  NEED(c);
+  return akima_apply_impl(ctx, nslab, dZ1, dZ2);
+}
+
+int sosie_akima_apply(sosie_ctx* c, int32_t nslab, const float* Z1, float* Z2) {
+  NEED(c);
+  if (!ctx->ak_set) { ctx->err = "sosie_akima_apply: grids not set"; return SOSIE_ERR_STATE; }
+  if (!Z1 || !Z2 || nslab < 0) return SOSIE_ERR_ARG;
+  const size_t n1 = (size_t)ctx->ak_nx1 * ctx->ak_ny1, n2 = (size_t)ctx->ak_nx2 * ctx->ak_ny2;
+  const size_t budget = (size_t)2 << 30;
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nslab, budget / ((n1 + n2) * sizeof(float))));
+  CK(ctx->ak_stage1.alloc(n1 * chunk)); CK(ctx->ak_stage2.alloc(n2 * chunk));
+  cudaStream_t st = ctx->stream;
+  for (int s0 = 0; s0 < nslab; s0 += chunk) {
+    int ns = std::min(chunk, nslab - s0);
+    CK(cudaMemcpyAsync(ctx->ak_stage1.p, Z1 + (size_t)s0 * n1, n1 * ns * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (int rc = akima_apply_impl(ctx, ns, ctx->ak_stage1.p, ctx->ak_stage2.p)) return rc;
+    CK(cudaMemcpyAsync(Z2 + (size_t)s0 * n2, ctx->ak_stage2.p, n2 * ns * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_akima_get_ixy(sosie_ctx* c, int32_t* ixy) {
+  NEED(c);
+  if (!ctx->ak_set || !ixy) return SOSIE_ERR_STATE;
+  const size_t nt = (size_t)ctx->ak_nx2 * ctx->ak_ny2;
+  CK(cudaMemcpyAsync(ixy, ctx->ak_ixy.p, 2 * nt * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SOSIE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+int sosie_bdrown_dev(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* dX, const int32_t* dmask,
+                     int32_t mask_per_slab, int32_t nb_inc, int32_t nb_smooth, float pmin, float pmax, float pval_land,
+                     int32_t* nsweeps_host) {
+  NEED(c);
+  if (ni < 3 || nj < 3 || nslab < 1 || !dX || !dmask) { ctx->err = "sosie_bdrown: bad arguments"; return SOSIE_ERR_ARG; }
+  return bdrown_impl(ctx, k_ew, ni, nj, nslab, dX, dmask, mask_per_slab, nb_inc, nb_smooth, pmin, pmax, pval_land, nsweeps_host);
+}
+
+int sosie_bdrown(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X, const int32_t* mask,
+                 int32_t mask_per_slab, int32_t nb_inc, int32_t nb_smooth, float pmin, float pmax, float pval_land, int32_t* nsweeps) {
+  NEED(c);
+  if (ni < 3 || nj < 3 || nslab < 1 || !X || !mask) { ctx->err = "sosie_bdrown: bad arguments"; return SOSIE_ERR_ARG; }
+  const size_t n = (size_t)ni * nj;
+  cudaStream_t st = ctx->stream;
+  DBuf<float> dX; DBuf<int32_t> dM;
+  CK(dX.alloc(n * nslab)); CK(dM.alloc(n * (mask_per_slab ? nslab : 1)));
+  CK(cudaMemcpyAsync(dX.p, X, n * nslab * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dM.p, mask, n * (mask_per_slab ? nslab : 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (int rc = bdrown_impl(ctx, k_ew, ni, nj, nslab, dX.p, dM.p, mask_per_slab, nb_inc, nb_smooth, pmin, pmax, pval_land, nsweeps)) return rc;
+  CK(cudaMemcpyAsync(X, dX.p, n * nslab * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_smoother(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X, int32_t nb_smooth, const int32_t* msk,
+                   int32_t l_emp) {
+  NEED(c);
+  if (ni < 3 || nj < 3 || nslab < 1 || !X) { ctx->err = "sosie_smoother: bad arguments"; return SOSIE_ERR_ARG; }
+  const size_t n = (size_t)ni * nj;
+  cudaStream_t st = ctx->stream;
+  DBuf<float> dX; DBuf<int32_t> dM;
+  CK(dX.alloc(n * nslab));
+  CK(cudaMemcpyAsync(dX.p, X, n * nslab * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (msk) { CK(dM.alloc(n)); CK(cudaMemcpyAsync(dM.p, msk, n * sizeof(int32_t), cudaMemcpyHostToDevice, st)); }
+  if (int rc = smoother_impl(ctx, k_ew, ni, nj, nslab, dX.p, nb_smooth, msk ? dM.p : nullptr, l_emp)) return rc;
+  CK(cudaMemcpyAsync(X, dX.p, n * nslab * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_drown(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X, const int8_t* mask, int32_t nb_inc,
+                int32_t* nsweeps) {
+  NEED(c);
+  if (ni < 3 || nj < 3 || nslab < 1 || !X || !mask) { ctx->err = "sosie_drown: bad arguments"; return SOSIE_ERR_ARG; }
+  const size_t n = (size_t)ni * nj;
+  cudaStream_t st = ctx->stream;
+  DBuf<float> dX; DBuf<int8_t> dM;
+  CK(dX.alloc(n * nslab)); CK(dM.alloc(n));
+  CK(cudaMemcpyAsync(dX.p, X, n * nslab * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dM.p, mask, n, cudaMemcpyHostToDevice, st));
+  if (int rc = drown_impl(ctx, k_ew, ni, nj, nslab, dX.p, dM.p, nb_inc, nsweeps)) return rc;
+  CK(cudaMemcpyAsync(X, dX.p, n * nslab * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_rotate_uv_dev(sosie_ctx* c, int64_t n, int32_t nslab, const float* dU, const float* dV, const double* dxcos,
+                        const double* dxsin, float* dUo, float* dVo, int32_t inverse) {
+  NEED(c);
+  return rotate_impl(ctx, n, nslab, dU, dV, dxcos, dxsin, dUo, dVo, inverse);
+}
+
+int sosie_rotate_uv(sosie_ctx* c, int64_t n, int32_t nslab, const float* U, const float* V, const double* xcos, const double* xsin,
+                    float* Uo, float* Vo, int32_t inverse) {
+  NEED(c);
+  if (n <= 0 || nslab <= 0) return SOSIE_OK;
+  cudaStream_t st = ctx->stream;
+  size_t tot = (size_t)n * nslab;
+  DBuf<float> dU, dV, dUo, dVo; DBuf<double> dc, ds;
+  CK(dU.alloc(tot)); CK(dV.alloc(tot)); CK(dUo.alloc(tot)); CK(dVo.alloc(tot)); CK(dc.alloc(n)); CK(ds.alloc(n));
+  CK(cudaMemcpyAsync(dU.p, U, tot * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dV.p, V, tot * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dc.p, xcos, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ds.p, xsin, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+  if (int rc = rotate_impl(ctx, n, nslab, dU.p, dV.p, dc.p, ds.p, dUo.p, dVo.p, inverse)) return rc;
+  CK(cudaMemcpyAsync(Uo, dUo.p, tot * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(Vo, dVo.p, tot * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+}  // extern "C"

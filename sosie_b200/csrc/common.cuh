@@ -1,0 +1,167 @@
+// common.cuh -- context, device buffers and launch helpers shared by all translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sosie_b200.h"
+#include "pmath.h"
+
+#define SOSIE_NUM_SMS_B200 148
+
+template <class T>
+struct DBuf {  // owning device buffer (or borrowed pointer when own == false)
+  T* p = nullptr;
+  size_t n = 0;
+  bool own = true;
+  cudaError_t alloc(size_t count) {
+    if (own && p && n >= count && count > 0) return cudaSuccess;
+    release();
+    own = true;
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc((void**)&p, count * sizeof(T));
+  }
+  void borrow(const T* q, size_t count) {
+    release();
+    p = const_cast<T*>(q);
+    n = count;
+    own = false;
+  }
+  void release() {
+    if (own && p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+    own = true;
+  }
+  ~DBuf() { release(); }
+};
+
+// Source grid geometry as the kernels see it (1-based accessors below).
+struct SrcGeom {
+  int nx = 0, ny = 0;      // original extents
+  int nyw = 0;             // working extent in j (ny + 2 when the pole rows are added)
+  int separable = 0;       // 1: 1-D axes + trig tables; 0: full 2-D arrays (nx,nyw)
+  const double* lon1 = nullptr;  // [nx]      (separable)
+  const double* lat1 = nullptr;  // [nyw]
+  const double* clon = nullptr;  // cos/sin of lon*zconv  [nx]
+  const double* slon = nullptr;
+  const double* clat = nullptr;  // cos/sin of lat*zconv  [nyw]
+  const double* slat = nullptr;
+  const double* X = nullptr;     // [nx*nyw]  (non separable)
+  const double* Y = nullptr;
+  const double* vx = nullptr;    // unit vectors [nx*nyw]
+  const double* vy = nullptr;
+  const double* vz = nullptr;
+};
+
+struct TrgGeom {
+  int nx = 0, ny = 0;
+  int is_1d = 0;
+  const double* X = nullptr;  // [nx] or [nx*ny]
+  const double* Y = nullptr;  // [ny] or [nx*ny]
+};
+
+struct sosie_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  std::string err;
+  int64_t launches = 0;
+  int num_sms = SOSIE_NUM_SMS_B200;
+
+  // ---- bilinear state
+  int k_ew = -1, l_reg_src = 0, i_orca_trg = 0, l_add_extra_j = 0;
+  bool grids_set = false, map_ready = false, pack_ready = false;
+  size_t map_nt = 0;             // target count the cached mapping was built/loaded for
+  SrcGeom sg;
+  TrgGeom tg;
+  DBuf<double> s_lon1, s_lat1, s_clon, s_slon, s_clat, s_slat, s_X, s_Y, s_vx, s_vy, s_vz;
+  DBuf<double> s_in_X, s_in_Y;   // uploaded (or borrowed) raw source coordinates
+  DBuf<double> t_X, t_Y;
+  DBuf<int32_t> t_mask;          // mask_domain_trg as modified by the search
+  DBuf<int32_t> d_metrics;       // (nx2,ny2,3)
+  DBuf<double> d_ab;             // (nx2,ny2,2)
+  DBuf<int16_t> d_ipb;
+  DBuf<float> d_dnp;
+  DBuf<int32_t> d_im;            // ji_m table of EXT_NORTH_TO_90_REGG [nx1]
+  DBuf<int4> d_pidx;             // packed apply records
+  DBuf<float4> d_pw;
+  DBuf<float> d_stage1, d_stage2;  // staging for host-pointer apply
+  DBuf<double> d_scratch;        // reductions
+  DBuf<int32_t> d_iscratch;
+  int32_t map_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int l_last_y_row_missing = 0;
+
+  // ---- akima state
+  bool ak_set = false;
+  int ak_kew = -1, ak_nx1 = 0, ak_ny1 = 0, ak_nx2 = 0, ak_ny2 = 0, ak_iorca = 0, ak_trg_1d = 0;
+  DBuf<double> ak_zX, ak_zY;         // frame-extended coordinates (nx1+4, ny1+4)
+  DBuf<double> ak_ZX8, ak_ZY8;       // twice-extended coordinates (nx1+8, ny1+8)
+  DBuf<double> ak_X2, ak_Y2;         // target coordinates (2-D)
+  DBuf<int32_t> ak_ixy;              // (nx2,ny2,2)
+  DBuf<double> ak_zF, ak_ZF8, ak_sx, ak_sy, ak_sxy;  // per-slab work arrays
+  DBuf<float> ak_stage1, ak_stage2;
+  double ak_range[4] = {0, 0, 0, 0};
+
+  // ---- drown work buffers
+  DBuf<int8_t> dr_m0, dr_m1;
+  DBuf<float> dr_x, dr_x2;
+  DBuf<int32_t> dr_cnt, dr_mask32;
+};
+
+#define CK(call)                                                                      \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                 \
+      return SOSIE_ERR_CUDA;                                                          \
+    }                                                                                 \
+  } while (0)
+
+#define KLAUNCH_CHECK()                                                               \
+  do {                                                                                \
+    ctx->launches++;                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess) {                                                         \
+      ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e__);            \
+      return SOSIE_ERR_CUDA;                                                          \
+    }                                                                                 \
+  } while (0)
+
+static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// grid size for grid-stride kernels: a multiple of the SM count (148 on B200)
+static inline int grid_for(const sosie_ctx* ctx, int64_t work_items, int block, int max_blocks_per_sm = 8) {
+  int64_t need = (work_items + block - 1) / block;
+  int64_t cap = (int64_t)ctx->num_sms * max_blocks_per_sm;
+  if (need < 1) need = 1;
+  if (need > cap) need = cap;
+  return (int)need;
+}
+
+// entry points implemented in the other translation units
+int bilin_map_impl(sosie_ctx* ctx);
+int bilin_pack_impl(sosie_ctx* ctx);
+int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, int first_call, int use_clamp,
+                     float vmin, float vmax, const int32_t* dmask_trg, float rmiss);
+int bilin_apply_uv_impl(sosie_ctx* ctx, int nslab, const float* dU1, const float* dV1, float* dUo, float* dVo,
+                        const double* dcos, const double* dsin);
+int bilin_prepare_src(sosie_ctx* ctx);
+int interp_bl_impl(sosie_ctx* ctx, int k_ew, int nxi, int nyi, const float* dZ, int n, const int32_t* ji,
+                   const int32_t* jj, const int32_t* iq, const double* xa, const double* xb, float* out);
+int akima_prepare_impl(sosie_ctx* ctx);
+int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2);
+int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, const int32_t* dmask,
+                int mask_per_slab, int nb_inc, int nb_smooth, float pmin, float pmax, float pval_land,
+                int32_t* nsweeps_host);
+int smoother_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, int nb_smooth,
+                  const int32_t* dmsk, int l_emp);
+int drown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, const int8_t* dmask, int nb_inc,
+               int32_t* nsweeps_host);
+int rotate_impl(sosie_ctx* ctx, int64_t n, int nslab, const float* dU, const float* dV, const double* dcos,
+                const double* dsin, float* dUo, float* dVo, int inverse);

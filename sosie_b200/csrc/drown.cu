@@ -1,0 +1,551 @@
+// drown.cu -- land-mask extrapolation (BDROWN, SMOOTHER, DROWN) and the corr_vect rotation on device.
+//
+// GPU counterparts of src/mod_bdrown.f90:18-439 (BDROWN), :444-608 (SMOOTHER), src/mod_drown.f90:18-198
+// (DROWN) and src/corr_vect.f90:622-624.  REAL(4) arithmetic in the reference's order, FMA off.
+//
+// BDROWN schedule (all slabs = records x levels batched in every launch, grid.y = slab):
+//   * prefill: one thread per (row, slab) does the sequential zonal sum (:109-120);
+//   * one kernel per coastline sweep: each land cell derives its coastline flag from the 1-byte
+//     running mask of the previous sweep, and a coastline cell is the weighted mean of its sea
+//     neighbours.  The update is done IN PLACE: a coastline cell only reads cells whose running mask
+//     is 1, and those are never written in the same sweep, so the reference's `dold` copy (:130) is
+//     not needed; the mask is ping-ponged (1 B/cell).  A per-slab land counter written by sweep k is
+//     the device-side convergence flag read by sweep k+1 (replaces ANY(maskv==0), :125): finished
+//     slabs cost one predicated exit per block, no host round trip;
+//   * the per-sweep whole-array clamp (:414-415) is folded into the reads of sweeps >= 2 plus one
+//     final clamp pass (identical results, no extra traffic per sweep).
+#include "geom.cuh"
+
+#define RIS2F 0.70710677f  // REAL( 1./SQRT(2.) , 4 )
+
+struct BdGeom {
+  int ni, nj, k_ew;
+  int jimW, jipW, jimE, jipE;  // periodic neighbours of column 1 (W) and column ni (E): vim_per/vip_per (:98-101)
+};
+
+static BdGeom make_bdgeom(int ni, int nj, int k_ew) {
+  BdGeom g;
+  g.ni = ni; g.nj = nj; g.k_ew = k_ew;
+  g.jimW = ni - k_ew; g.jipW = 2; g.jimE = ni - 1; g.jipE = 1 + k_ew;
+  return g;
+}
+
+// ---- BDROWN --------------------------------------------------------------------------------------------
+__global__ void k_bd_init(const int32_t* __restrict__ mask, size_t n, int nmask, int8_t* m0, int32_t* cnt) {
+  // m0 = mask (1 byte), cnt[0][ms] = number of land cells
+  int ms = blockIdx.y;
+  const int32_t* mk = mask + (size_t)ms * n;
+  int8_t* m = m0 + (size_t)ms * n;
+  int local = 0;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int v = mk[k];
+    m[k] = (int8_t)v;
+    local += (v == 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt[ms], local);
+}
+
+// zonal-mean prefill (:109-120): thread per (row, slab), sequential REAL(4) sum
+__global__ void k_bd_prefill(float* X, const int32_t* __restrict__ mask, int ni, int nj, int nslab, int mask_per_slab) {
+  size_t n = (size_t)ni * nj;
+  int total = nj * nslab;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int s = t / nj, jj = t % nj;
+    float* row = X + (size_t)s * n + (size_t)jj * ni;
+    const int32_t* mrow = mask + (mask_per_slab ? (size_t)s * n : 0) + (size_t)jj * ni;
+    int nbp = 0;
+    for (int i = 0; i < ni; i++) nbp += mrow[i];
+    if (nbp > 0) {
+      float sum = 0.f;
+      for (int i = 0; i < ni; i++) sum = __fadd_rn(sum, __fmul_rn(row[i], (float)mrow[i]));
+      float zmv = __fdiv_rn(sum, (float)nbp);
+      for (int i = 0; i < ni; i++) if (mrow[i] == 0) row[i] = zmv;
+    }
+  }
+}
+
+// one coastline sweep (:130-415)
+__global__ void __launch_bounds__(256)
+k_bd_sweep(BdGeom g, float* Xb, const int8_t* __restrict__ mcb, int8_t* mnb, int mask_per_slab, const int32_t* cnt_in,
+           int32_t* cnt_out, int32_t* nsw, int first_sweep, float zmin, float zmax) {
+  const int s = blockIdx.y;
+  const int ms = mask_per_slab ? s : 0;
+  if (cnt_in[ms] == 0) return;  // no land left: this slab has left the loop (:125-128)
+  const int ni = g.ni, nj = g.nj;
+  const size_t n = (size_t)ni * nj;
+  float* X = Xb + (size_t)s * n;
+  const int8_t* mc = mcb + (size_t)ms * n;
+  int8_t* mn = mnb + (size_t)ms * n;
+  const bool writer = mask_per_slab || s == 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) nsw[s] += 1;
+  int left = 0;
+#define MV(i, j) ((int)mc[(size_t)((i)-1) + (size_t)((j)-1) * ni])
+  auto DV = [&](int i, int j) -> float {
+    float d = X[(size_t)(i - 1) + (size_t)(j - 1) * ni];
+    if (!first_sweep) { d = fmaxf(d, zmin); d = fminf(d, zmax); }
+    return d;
+  };
+  // term helpers: maskv*dold and ris2*maskv*dold with maskv in {0,1}
+  auto T = [&](int i, int j) -> float { return MV(i, j) ? DV(i, j) : 0.f; };
+  auto TD = [&](int i, int j) -> float { return MV(i, j) ? __fmul_rn(RIS2F, DV(i, j)) : 0.f; };
+  auto MD = [&](int i, int j) -> float { return MV(i, j) ? RIS2F : 0.f; };
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int m = mc[k];
+    if (m != 0) { if (writer) mn[k] = (int8_t)m; continue; }
+    const int jj = (int)(k / ni) + 1, ji = (int)(k % ni) + 1;
+    int coast;
+    float val = 0.f;
+    const bool per = g.k_ew >= 0;
+    if (jj >= 2 && jj <= nj - 1) {
+      if (ji >= 2 && ji <= ni - 1) {
+        coast = (MV(ji + 1, jj) + MV(ji, jj + 1) + MV(ji - 1, jj) + MV(ji, jj - 1)) > 0;
+        if (coast) {
+          float den = __fadd_rn((float)(MV(ji + 1, jj) + MV(ji, jj + 1) + MV(ji - 1, jj) + MV(ji, jj - 1)),
+                                __fmul_rn(RIS2F, (float)(MV(ji + 1, jj + 1) + MV(ji - 1, jj + 1) + MV(ji - 1, jj - 1) + MV(ji + 1, jj - 1))));
+          float num = T(ji + 1, jj);
+          num = __fadd_rn(num, T(ji, jj + 1)); num = __fadd_rn(num, T(ji - 1, jj)); num = __fadd_rn(num, T(ji, jj - 1));
+          num = __fadd_rn(num, TD(ji + 1, jj + 1)); num = __fadd_rn(num, TD(ji - 1, jj + 1));
+          num = __fadd_rn(num, TD(ji - 1, jj - 1)); num = __fadd_rn(num, TD(ji + 1, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else if (per) {
+        int jim = (ji == 1) ? g.jimW : g.jimE, jip = (ji == 1) ? g.jipW : g.jipE;
+        coast = (MV(jip, jj) + MV(ji, jj + 1) + MV(jim, jj) + MV(ji, jj - 1)) > 0;
+        if (coast) {
+          float den = __fadd_rn((float)(MV(jip, jj) + MV(ji, jj + 1) + MV(jim, jj) + MV(ji, jj - 1)),
+                                __fmul_rn(RIS2F, (float)(MV(jip, jj + 1) + MV(jim, jj + 1) + MV(jim, jj - 1) + MV(jip, jj - 1))));
+          float num = T(jip, jj);
+          num = __fadd_rn(num, T(ji, jj + 1)); num = __fadd_rn(num, T(jim, jj)); num = __fadd_rn(num, T(ji, jj - 1));
+          num = __fadd_rn(num, TD(jip, jj + 1)); num = __fadd_rn(num, TD(jim, jj + 1));
+          num = __fadd_rn(num, TD(jim, jj - 1)); num = __fadd_rn(num, TD(jip, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else if (ji == 1) {
+        coast = (MV(2, jj) + MV(1, jj + 1) + MV(1, jj - 1)) > 0;
+        if (coast) {
+          float den = __fadd_rn(__fadd_rn((float)(MV(2, jj) + MV(ji, jj + 1) + MV(ji, jj - 1)), MD(2, jj + 1)), MD(2, jj - 1));
+          float num = T(2, jj);
+          num = __fadd_rn(num, T(ji, jj + 1)); num = __fadd_rn(num, T(ji, jj - 1));
+          num = __fadd_rn(num, TD(2, jj + 1)); num = __fadd_rn(num, TD(2, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else {  // ji == ni, not periodic
+        coast = (MV(ni, jj + 1) + MV(ni - 1, jj) + MV(ni, jj - 1)) > 0;
+        if (coast) {
+          float den = __fadd_rn(__fadd_rn((float)(MV(ji, jj + 1) + MV(ni - 1, jj) + MV(ji, jj - 1)), MD(ni - 1, jj + 1)), MD(ni - 1, jj - 1));
+          float num = T(ji, jj + 1);
+          num = __fadd_rn(num, T(ni - 1, jj)); num = __fadd_rn(num, T(ji, jj - 1));
+          num = __fadd_rn(num, TD(ni - 1, jj + 1)); num = __fadd_rn(num, TD(ni - 1, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      }
+    } else if (jj == nj) {
+      if (ji >= 2 && ji <= ni - 1) {
+        coast = (MV(ji + 1, nj) + MV(ji - 1, nj) + MV(ji, nj - 1)) > 0;
+        if (coast) {
+          float den = __fadd_rn(__fadd_rn((float)(MV(ji + 1, jj) + MV(ji - 1, jj) + MV(ji, jj - 1)), MD(ji - 1, jj - 1)), MD(ji + 1, jj - 1));
+          float num = T(ji + 1, jj);
+          num = __fadd_rn(num, T(ji - 1, jj)); num = __fadd_rn(num, T(ji, jj - 1));
+          num = __fadd_rn(num, TD(ji - 1, jj - 1)); num = __fadd_rn(num, TD(ji + 1, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else if (per) {
+        int jim = (ji == 1) ? g.jimW : g.jimE, jip = (ji == 1) ? g.jipW : g.jipE;
+        if (ji == 1) coast = (MV(2, nj) + MV(ni - g.k_ew, nj) + MV(1, nj - 1)) > 0;
+        else coast = (MV(g.k_ew + 1, nj) + MV(ni - 1, nj) + MV(ni - 1, nj - 1)) > 0;  // Q15: the diagonal
+        if (coast) {
+          float den = __fadd_rn(__fadd_rn((float)(MV(jip, jj) + MV(jim, jj) + MV(ji, jj - 1)), MD(jim, jj - 1)), MD(jip, jj - 1));
+          float num = T(jip, jj);
+          num = __fadd_rn(num, T(jim, jj)); num = __fadd_rn(num, T(ji, jj - 1));
+          num = __fadd_rn(num, TD(jim, jj - 1)); num = __fadd_rn(num, TD(jip, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else if (ji == 1) {
+        coast = (MV(2, nj) + MV(1, nj - 1)) > 0;
+        if (coast) {
+          float den = __fadd_rn((float)(MV(2, jj) + MV(ji, jj - 1)), MD(2, jj - 1));
+          float num = T(2, jj);
+          num = __fadd_rn(num, T(ji, jj - 1)); num = __fadd_rn(num, TD(2, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else {
+        coast = (MV(ni - 1, nj) + MV(ni - 1, nj - 1)) > 0;  // Q15
+        if (coast) {
+          float den = __fadd_rn((float)(MV(ni - 1, jj) + MV(ji, jj - 1)), MD(ni - 1, jj - 1));
+          float num = T(ni - 1, jj);
+          num = __fadd_rn(num, T(ji, jj - 1)); num = __fadd_rn(num, TD(ni - 1, jj - 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      }
+    } else {  // jj == 1
+      if (ji >= 2 && ji <= ni - 1) {
+        coast = (MV(ji + 1, 1) + MV(ji, 2) + MV(ji - 1, 1)) > 0;
+        if (coast) {
+          float den = __fadd_rn(__fadd_rn((float)(MV(ji + 1, jj) + MV(ji, jj + 1) + MV(ji - 1, jj)), MD(ji + 1, jj + 1)), MD(ji - 1, jj + 1));
+          float num = T(ji + 1, jj);
+          num = __fadd_rn(num, T(ji, jj + 1)); num = __fadd_rn(num, T(ji - 1, jj));
+          num = __fadd_rn(num, TD(ji + 1, jj + 1)); num = __fadd_rn(num, TD(ji - 1, jj + 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else if (per) {
+        int jim = (ji == 1) ? g.jimW : g.jimE, jip = (ji == 1) ? g.jipW : g.jipE;
+        if (ji == 1) coast = (MV(2, 1) + MV(1, 2) + MV(ni - g.k_ew, 1)) > 0;
+        else coast = (MV(1 + g.k_ew, 1) + MV(ni, 2) + MV(ni, 1)) > 0;  // Q15: uses itself (0 here)
+        if (coast) {
+          float den = __fadd_rn(__fadd_rn((float)(MV(jip, jj) + MV(ji, jj + 1) + MV(jim, jj)), MD(jip, jj + 1)), MD(jim, jj + 1));
+          float num = T(jip, jj);
+          num = __fadd_rn(num, T(ji, jj + 1)); num = __fadd_rn(num, T(jim, jj));
+          num = __fadd_rn(num, TD(jip, jj + 1)); num = __fadd_rn(num, TD(jim, jj + 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else if (ji == 1) {
+        coast = (MV(2, 1) + MV(1, 2)) > 0;
+        if (coast) {
+          float den = __fadd_rn((float)(MV(2, jj) + MV(ji, jj + 1)), MD(2, jj + 1));
+          float num = T(2, jj);
+          num = __fadd_rn(num, T(ji, jj + 1)); num = __fadd_rn(num, TD(2, jj + 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      } else {
+        coast = (MV(ni, 2) + MV(ni, 1)) > 0;  // Q15
+        if (coast) {
+          float den = __fadd_rn((float)(MV(ji, jj + 1) + MV(ni - 1, jj)), MD(ni - 1, jj + 1));
+          float num = T(ji, jj + 1);
+          num = __fadd_rn(num, T(ni - 1, jj)); num = __fadd_rn(num, TD(ni - 1, jj + 1));
+          val = __fmul_rn(__fdiv_rn(1.f, den), num);
+        }
+      }
+    }
+    if (coast) {
+      val = fmaxf(val, zmin);
+      val = fminf(val, zmax);
+      X[k] = val;
+      if (writer) mn[k] = 1;
+    } else {
+      if (writer) mn[k] = 0;
+      left++;
+    }
+  }
+#undef MV
+  if (writer) {
+    for (int o = 16; o > 0; o >>= 1) left += __shfl_xor_sync(0xffffffffu, left, o);
+    if ((threadIdx.x & 31) == 0 && left) atomicAdd(&cnt_out[ms], left);
+  }
+}
+
+// after the loop: whole-array clamp if at least one sweep ran; then (separately) pval_land fill (:431-433)
+__global__ void k_bd_clamp(float* Xb, size_t n, const int32_t* nsw, float zmin, float zmax) {
+  const int s = blockIdx.y;
+  if (nsw[s] == 0) return;
+  float* X = Xb + (size_t)s * n;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    float v = X[k];
+    float c = fminf(fmaxf(v, zmin), zmax);
+    if (c != v) X[k] = c;
+  }
+}
+__global__ void k_bd_pval(float* Xb, size_t n, const int8_t* __restrict__ mfin, int mask_per_slab, float zval,
+                          const int32_t* __restrict__ cnt_final) {
+  const int s = blockIdx.y;
+  // land left after the last sweep?  (slabs that left the loop early never wrote cnt_final: 0)
+  if (cnt_final[mask_per_slab ? s : 0] == 0) return;
+  float* X = Xb + (size_t)s * n;
+  const int8_t* m = mfin + (mask_per_slab ? (size_t)s * n : 0);
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x)
+    if (m[k] == 0) X[k] = zval;
+}
+__global__ void k_land_msk(const int32_t* __restrict__ mask, size_t n, int32_t* out) {  // mtmp = 1 - mask (:423)
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) out[k] = 1 - mask[k];
+}
+
+// ---- SMOOTHER: one Jacobi pass (:529-602); grid.y = slab ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_smooth_pass(BdGeom g, const float* __restrict__ xinb, float* xoutb, const float* __restrict__ xorigb,
+              const int32_t* __restrict__ mskb, int msk_per_slab, int l_emp) {
+  const int ni = g.ni, nj = g.nj;
+  const size_t n = (size_t)ni * nj;
+  const int s = blockIdx.y;
+  const float* xin = xinb + (size_t)s * n;
+  float* xout = xoutb + (size_t)s * n;
+  const float* xorig = xorigb ? xorigb + (size_t)s * n : nullptr;
+  const int32_t* msk = mskb ? mskb + (msk_per_slab ? (size_t)s * n : 0) : nullptr;
+  const float w0 = 0.35f;
+  const float omw = 1.f - w0;
+  const float c4 = 4.f * (1.f + RIS2F);
+#define XI(i, j) xin[(size_t)((i)-1) + (size_t)((j)-1) * ni]
+#define MK(i, j) msk[(size_t)((i)-1) + (size_t)((j)-1) * ni]
+  auto XT = [&](int i, int j) -> float {  // xtmp = X [* REAL(msk,4) when l_emp]  (:531-533)
+    float v = XI(i, j);
+    if (l_emp) v = __fmul_rn(v, (float)MK(i, j));
+    return v;
+  };
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const int jj = (int)(k / ni) + 1, ji = (int)(k % ni) + 1;
+    float v = xin[k];
+    if (jj >= 2 && jj <= nj - 1) {
+      int jim = ji - 1, jip = ji + 1;
+      bool doit = true;
+      if (ji == 1) { if (g.k_ew >= 0) { jim = g.jimW; jip = g.jipW; } else doit = false; }
+      else if (ji == ni) { if (g.k_ew >= 0) { jim = g.jimE; jip = g.jipE; } else doit = false; }
+      if (doit) {
+        float s4 = __fadd_rn(__fadd_rn(__fadd_rn(XT(jip, jj), XT(ji, jj + 1)), XT(jim, jj)), XT(ji, jj - 1));
+        float sd = __fadd_rn(__fadd_rn(__fadd_rn(XT(jip, jj + 1), XT(jip, jj - 1)), XT(jim, jj - 1)), XT(jim, jj + 1));
+        float body = __fmul_rn(omw, __fadd_rn(s4, __fmul_rn(RIS2F, sd)));
+        if (l_emp) {
+          int i4 = MK(jip, jj) + MK(ji, jj + 1) + MK(jim, jj) + MK(ji, jj - 1);
+          int id = MK(jip, jj + 1) + MK(jip, jj - 1) + MK(jim, jj - 1) + MK(jim, jj + 1);
+          float rd = __fdiv_rn(1.f, fmaxf(__fadd_rn((float)i4, __fmul_rn(RIS2F, (float)id)), 0.01f));
+          v = __fadd_rn(__fmul_rn(w0, XT(ji, jj)), __fmul_rn(body, rd));
+          if (i4 + id == 0) v = xorig[k];
+        } else {
+          v = __fadd_rn(__fmul_rn(w0, XT(ji, jj)), __fdiv_rn(body, c4));
+        }
+      }
+      if (msk) {  // X(:,2:nj-1) = msk*X - (msk-1)*xorig  (:600)
+        int m = msk[k];
+        v = __fsub_rn(__fmul_rn((float)m, v), __fmul_rn((float)(m - 1), xorig[k]));
+      }
+    }
+    xout[k] = v;
+  }
+#undef XI
+#undef MK
+}
+
+// ---- DROWN (src/mod_drown.f90) ----------------------------------------------------------------------------------
+__global__ void k_dr_init(float* Xb, const int8_t* __restrict__ mask, size_t n, int8_t* mvb, int32_t* cnt) {
+  const int s = blockIdx.y;
+  float* X = Xb + (size_t)s * n;
+  int8_t* mv = mvb + (size_t)s * n;
+  int local = 0;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int8_t m = mask[k];
+    X[k] = __fmul_rn(X[k], (float)m);  // X = X * mask (:70)
+    mv[k] = m;
+    local += (m == 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt[s], local);
+}
+__global__ void k_dr_wtab(float* wtab, int nr2, int jinc) {  // EXP(-1.*(jjm**2+jim**2)/jinc**2) per r2
+  for (int r2 = blockIdx.x * blockDim.x + threadIdx.x; r2 < nr2; r2 += gridDim.x * blockDim.x) {
+    float arg = -(__fdiv_rn(__fmul_rn(1.f, (float)r2), (float)(jinc * jinc)));
+    wtab[r2] = pm_expf(arg);
+  }
+}
+__device__ __forceinline__ int dr_fold(int j, int ni, int k_ew) {
+  if (j > ni - k_ew) j = j - ni + 2 * k_ew;
+  if (j < 1 + k_ew) j = j + ni - 2 * k_ew;
+  return j;
+}
+// coastline mask (:98-127)
+__global__ void k_dr_coast(const int8_t* __restrict__ mvb, int8_t* mcb, int ni, int nj, int k_ew, const int32_t* cnt_in, int32_t* nsw) {
+  const int s = blockIdx.y;
+  if (cnt_in[s] == 0) return;
+  size_t n = (size_t)ni * nj;
+  const int8_t* mv = mvb + (size_t)s * n;
+  int8_t* mc = mcb + (size_t)s * n;
+  if (blockIdx.x == 0 && threadIdx.x == 0) nsw[s] += 1;
+#define MV(i, j) ((int)mv[(size_t)((i)-1) + (size_t)((j)-1) * ni])
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int jj = (int)(k / ni) + 1, ji = (int)(k % ni) + 1;
+    int jjp1 = jj + 1, jjm1 = jj - 1;
+    if (jjp1 > nj) jjp1 = nj;
+    if (jjm1 < 1) jjm1 = 1;
+    int ji0 = ji, jip1 = ji + 1, jim1 = ji - 1;
+    if (k_ew >= 0) { ji0 = dr_fold(ji0, ni, k_ew); jip1 = dr_fold(jip1, ni, k_ew); jim1 = dr_fold(jim1, ni, k_ew); }
+    else { if (jip1 > ni) jip1 = ni; if (jim1 < 1) jim1 = 1; }
+    int sum = MV(jim1, jj) + MV(jip1, jj) + MV(ji0, jjm1) + MV(ji0, jjp1);
+    mc[k] = (int8_t)(min(sum, 1) * (1 - MV(ji0, jj)));
+  }
+#undef MV
+}
+// Gaussian box mean on the coastline (:137-178); writes the next field and the next running mask
+__global__ void __launch_bounds__(128)
+k_dr_update(const float* __restrict__ xinb, float* xoutb, const int8_t* __restrict__ mvb, int8_t* mvnb, const int8_t* __restrict__ mcb,
+            const float* __restrict__ wtab, int ni, int nj, int k_ew, int ns, const int32_t* cnt_in, int32_t* cnt_out) {
+  const int s = blockIdx.y;
+  if (cnt_in[s] == 0) return;
+  size_t n = (size_t)ni * nj;
+  const float* xin = xinb + (size_t)s * n;
+  float* xout = xoutb + (size_t)s * n;
+  const int8_t* mv = mvb + (size_t)s * n;
+  int8_t* mvn = mvnb + (size_t)s * n;
+  const int8_t* mc = mcb + (size_t)s * n;
+  int left = 0;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    int jj = (int)(k / ni) + 1, ji = (int)(k % ni) + 1;
+    float v = xin[k];
+    int c = mc[k];
+    if (c == 1) {
+      float summsk = 0.f, datmsk = 0.f;
+      for (int jjm = -ns; jjm <= ns; jjm++) {
+        int jjc = jj + jjm;
+        if (jjc < 1 || jjc > nj) continue;
+        for (int jim = -ns; jim <= ns; jim++) {
+          int jic = ji + jim;
+          if (k_ew >= 0) {
+            if (jic > ni - k_ew) jic = jic - ni + 2 * k_ew;
+            if (jic < 1 + k_ew) jic = jic + ni - 2 * k_ew;
+          }
+          if (jic >= 1 && jic <= ni) {
+            size_t kc = (size_t)(jic - 1) + (size_t)(jjc - 1) * ni;
+            float zweight = __fmul_rn(wtab[jjm * jjm + jim * jim], (float)mv[kc]);
+            summsk = __fadd_rn(summsk, zweight);
+            datmsk = __fadd_rn(datmsk, __fmul_rn(zweight, xin[kc]));
+          }
+        }
+      }
+      v = __fdiv_rn(datmsk, summsk);
+    }
+    xout[k] = v;
+    int8_t mnew = (int8_t)(mv[k] + c);
+    mvn[k] = mnew;
+    left += (mnew == 0);
+  }
+  for (int o = 16; o > 0; o >>= 1) left += __shfl_xor_sync(0xffffffffu, left, o);
+  if ((threadIdx.x & 31) == 0 && left) atomicAdd(&cnt_out[s], left);
+}
+
+// ---- rotation (src/corr_vect.f90:622-624,630,632 ; inverse :963,970) -----------------------------------------------
+__global__ void k_rotate(size_t n, const float* __restrict__ U, const float* __restrict__ V, const double* __restrict__ xcos,
+                         const double* __restrict__ xsin, float* Uo, float* Vo, int inverse) {
+  const size_t off = (size_t)blockIdx.y * n;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    double zU = (double)U[off + k], zV = (double)V[off + k];
+    double c = xcos[k], sn = xsin[k];
+    float uo, vo;
+    if (!inverse) {
+      uo = (float)__dadd_rn(__dmul_rn(c, zU), __dmul_rn(sn, zV));
+      vo = (float)__dsub_rn(__dmul_rn(c, zV), __dmul_rn(sn, zU));
+    } else {
+      uo = (float)__dsub_rn(__dmul_rn(c, zU), __dmul_rn(sn, zV));
+      vo = (float)__dadd_rn(__dmul_rn(c, zV), __dmul_rn(sn, zU));
+    }
+    __stcs(Uo + off + k, uo);
+    __stcs(Vo + off + k, vo);
+  }
+}
+
+// ===================================================================================================
+static int smoother_dev(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, int nsmooth, const int32_t* dmsk, int msk_per_slab,
+                        int l_emp) {
+  if (nsmooth <= 0) return SOSIE_OK;
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)g.ni * g.nj, tot = n * nslab;
+  if (l_emp && !dmsk) { ctx->err = "PROBLEM in SMOOTH (mod_bdrown.f90): you need to provide a \"msk\""; return SOSIE_ERR_REF_STOP; }
+  CK(ctx->dr_x2.alloc(tot));
+  const float* xorig = nullptr;
+  if (dmsk) {
+    CK(ctx->dr_x.alloc(tot));
+    CK(cudaMemcpyAsync(ctx->dr_x.p, dX, tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    xorig = ctx->dr_x.p;
+  }
+  float* a = dX;
+  float* b = ctx->dr_x2.p;
+  dim3 grid(grid_for(ctx, n, 256, 4), nslab);
+  for (int js = 0; js < nsmooth; js++) {
+    k_smooth_pass<<<grid, 256, 0, st>>>(g, a, b, xorig, dmsk, msk_per_slab, l_emp); KLAUNCH_CHECK();
+    std::swap(a, b);
+  }
+  if (a != dX) CK(cudaMemcpyAsync(dX, a, tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SOSIE_OK;
+}
+
+int smoother_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, int nb_smooth, const int32_t* dmsk, int l_emp) {
+  BdGeom g = make_bdgeom(ni, nj, k_ew);
+  return smoother_dev(ctx, g, nslab, dX, nb_smooth, dmsk, 0, l_emp);
+}
+
+int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, const int32_t* dmask, int mask_per_slab,
+                int nb_inc, int nb_smooth, float pmin, float pmax, float pval_land, int32_t* nsweeps_host) {
+  cudaStream_t st = ctx->stream;
+  BdGeom g = make_bdgeom(ni, nj, k_ew);
+  const size_t n = (size_t)ni * nj;
+  const int nmask = mask_per_slab ? nslab : 1;
+  if (nb_inc < 0) nb_inc = 0;
+  CK(ctx->dr_m0.alloc(n * nmask)); CK(ctx->dr_m1.alloc(n * nmask));
+  CK(ctx->dr_cnt.alloc((size_t)(nb_inc + 1) * nmask + nslab));
+  CK(cudaMemsetAsync(ctx->dr_cnt.p, 0, sizeof(int32_t) * ((size_t)(nb_inc + 1) * nmask + nslab), st));
+  int32_t* cnt = ctx->dr_cnt.p;
+  int32_t* nsw = cnt + (size_t)(nb_inc + 1) * nmask;
+  k_bd_init<<<dim3(grid_for(ctx, n, 256, 4), nmask), 256, 0, st>>>(dmask, n, nmask, ctx->dr_m0.p, cnt); KLAUNCH_CHECK();
+  k_bd_prefill<<<grid_for(ctx, (size_t)nj * nslab, 128), 128, 0, st>>>(dX, dmask, ni, nj, nslab, mask_per_slab); KLAUNCH_CHECK();
+  int8_t* mc = ctx->dr_m0.p;
+  int8_t* mn = ctx->dr_m1.p;
+  dim3 grid(grid_for(ctx, n, 256, 4), nslab);
+  for (int jinc = 1; jinc <= nb_inc; jinc++) {
+    k_bd_sweep<<<grid, 256, 0, st>>>(g, dX, mc, mn, mask_per_slab, cnt + (size_t)(jinc - 1) * nmask, cnt + (size_t)jinc * nmask, nsw,
+                                     jinc == 1 ? 1 : 0, pmin, pmax); KLAUNCH_CHECK();
+    std::swap(mc, mn);
+  }
+  // NOTE: a slab that left the loop early stops writing its mask; its final mask may live in either
+  // buffer.  Exited slabs have no land left, so the pval_land fill cannot touch them; slabs that ran
+  // all nb_inc sweeps have their final mask in `mc`.
+  k_bd_clamp<<<grid, 256, 0, st>>>(dX, n, nsw, pmin, pmax); KLAUNCH_CHECK();
+  if (nb_smooth > 0) {
+    CK(ctx->dr_mask32.alloc(n * nmask));
+    k_land_msk<<<grid_for(ctx, n * nmask, 256), 256, 0, st>>>(dmask, n * nmask, ctx->dr_mask32.p); KLAUNCH_CHECK();
+    if (int rc = smoother_dev(ctx, g, nslab, dX, nb_smooth, ctx->dr_mask32.p, mask_per_slab, 0)) return rc;
+  }
+  if (fabsf(pval_land) > 1.e-12f) {
+    if (nb_inc == 0) { /* maskv == mask */ }
+    // cells still 0 in the final running mask of slabs that never emptied
+    k_bd_pval<<<grid, 256, 0, st>>>(dX, n, mc, mask_per_slab, pval_land, cnt + (size_t)nb_inc * nmask); KLAUNCH_CHECK();
+  }
+  if (nsweeps_host) {
+    CK(cudaMemcpyAsync(nsweeps_host, nsw, sizeof(int32_t) * nslab, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return SOSIE_OK;
+}
+
+int drown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, const int8_t* dmask, int nb_inc, int32_t* nsweeps_host) {
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)ni * nj, tot = n * nslab;
+  if (nb_inc < 0) nb_inc = 0;
+  DBuf<int8_t> mc; CK(mc.alloc(tot));
+  CK(ctx->dr_m0.alloc(tot)); CK(ctx->dr_m1.alloc(tot)); CK(ctx->dr_x2.alloc(tot));
+  CK(ctx->dr_cnt.alloc((size_t)(nb_inc + 2) * nslab));
+  CK(cudaMemsetAsync(ctx->dr_cnt.p, 0, sizeof(int32_t) * (size_t)(nb_inc + 2) * nslab, st));
+  int32_t* cnt = ctx->dr_cnt.p;
+  int32_t* nsw = cnt + (size_t)(nb_inc + 1) * nslab;
+  DBuf<float> wtab; CK(wtab.alloc(2 * 50 * 50 + 1));
+  dim3 grid(grid_for(ctx, n, 128, 8), nslab);
+  k_dr_init<<<grid, 128, 0, st>>>(dX, dmask, n, ctx->dr_m0.p, cnt); KLAUNCH_CHECK();
+  float* a = dX;
+  float* b = ctx->dr_x2.p;
+  int8_t* mv = ctx->dr_m0.p;
+  int8_t* mvn = ctx->dr_m1.p;
+  // per-slab early exit leaves the slab's data in whichever buffer it was last written: keep both
+  // buffers identical for exited slabs by copying before the loop
+  CK(cudaMemcpyAsync(b, a, tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(mvn, mv, tot, cudaMemcpyDeviceToDevice, st));
+  for (int jinc = 1; jinc <= nb_inc; jinc++) {
+    int ns = jinc < 50 ? jinc : 50;
+    k_dr_wtab<<<cdiv(2 * ns * ns + 1, 128), 128, 0, st>>>(wtab.p, 2 * ns * ns + 1, jinc); KLAUNCH_CHECK();
+    k_dr_coast<<<grid, 128, 0, st>>>(mv, mc.p, ni, nj, k_ew, cnt + (size_t)(jinc - 1) * nslab, nsw); KLAUNCH_CHECK();
+    k_dr_update<<<grid, 128, 0, st>>>(a, b, mv, mvn, mc.p, wtab.p, ni, nj, k_ew, ns, cnt + (size_t)(jinc - 1) * nslab,
+                                      cnt + (size_t)jinc * nslab); KLAUNCH_CHECK();
+    std::swap(a, b);
+    std::swap(mv, mvn);
+  }
+  // gather: a slab that ran an odd number of sweeps has its result in the scratch buffer
+  std::vector<int32_t> hns(nslab);
+  CK(cudaMemcpyAsync(hns.data(), nsw, sizeof(int32_t) * nslab, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  for (int s = 0; s < nslab; s++)
+    if (hns[s] & 1) CK(cudaMemcpyAsync(dX + (size_t)s * n, ctx->dr_x2.p + (size_t)s * n, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (nsweeps_host) memcpy(nsweeps_host, hns.data(), sizeof(int32_t) * nslab);
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int rotate_impl(sosie_ctx* ctx, int64_t n, int nslab, const float* dU, const float* dV, const double* dcos, const double* dsin,
+                float* dUo, float* dVo, int inverse) {
+  if (n <= 0 || nslab <= 0) return SOSIE_OK;
+  k_rotate<<<dim3(grid_for(ctx, (size_t)n, 256), nslab), 256, 0, ctx->stream>>>((size_t)n, dU, dV, dcos, dsin, dUo, dVo, inverse);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
