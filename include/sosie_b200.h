@@ -46,6 +46,17 @@ int sosie_sync(sosie_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t sosie_launch_count(const sosie_ctx* ctx);
 const char* sosie_version(void);
+/* per-kernel device timing: when enabled, CUDA events bracket the dominant kernels on the context
+ * stream; sosie_get_timing returns the duration (ms) of the LAST bracket of that id (syncs on it). */
+enum { SOSIE_T_MAP = 0, SOSIE_T_PACK = 1, SOSIE_T_APPLY = 2, SOSIE_T_BDROWN = 3, SOSIE_T_SMOOTH = 4,
+       SOSIE_T_AKIMA_PREP = 5, SOSIE_T_AKIMA_EVAL = 6, SOSIE_T_DROWN = 7 };
+int sosie_profile(sosie_ctx* ctx, int32_t enable);
+int sosie_get_timing(sosie_ctx* ctx, int32_t id, float* ms);
+/* multi-GPU sharding of the bilinear path by target rows: this context maps / packs /
+ * applies only target rows j0..j1 (1-based, inclusive; 0,0 = all rows).  The search prelude
+ * (row range, regularity tests) still sees the whole target grid, so results equal the unsharded ones.
+ * Only the regular-source (EASY) search shards; the curvilinear-source chain is not split.           */
+int sosie_bilin_set_shard(sosie_ctx* ctx, int32_t j0, int32_t j1);
 
 /* ---- bilinear: grids -> mapping -> apply -------------------------------------------------------
  * Replaces BILIN_2D / MAPPING_BL / INTERP_BL, src/mod_bilin_2d.f90:44-361,366-691, and the search

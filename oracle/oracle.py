@@ -163,7 +163,7 @@ def interp_bl(k_ew, iP, jP, iqd, xa, xb, Z_in):
 
 
 def bilin_2d(k_ew, X10, Y10, Z1, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0, mapping=None,
-             elide_fill=True, nthreads=1):
+             elide_fill=True, nthreads=1, virtual_src=False):
     """BILIN_2D over nslab source slabs Z1 (nslab, ny1, nx1).  X10/Y10 (and X20/Y20) are either 1-D axes or
     2-D (nj,ni) arrays.  Returns (Z2 (nslab, ny2, nx2), mapping dict)."""
     Z1 = _f32(Z1)
@@ -192,7 +192,7 @@ def bilin_2d(k_ew, X10, Y10, Z1, X20, Y20, mask_domain_trg=None, l_reg_src=False
                             _p(Z1, C.c_float), nx2, ny2, _p(X20, C.c_double), _p(Y20, C.c_double), int(trg_1d),
                             _p(Z2, C.c_float), _p(m, C.c_int32), int(l_reg_src), int(i_orca_trg), 1, int(have),
                             _p(met, C.c_int32), _p(ab, C.c_double), _p(ipb, C.c_int16), _p(dnp, C.c_float), C.byref(lrow),
-                            int(elide_fill), int(nthreads), _p(info, C.c_int32))
+                            int(elide_fill), int(nthreads), _p(info, C.c_int32), int(virtual_src))
     if rc:
         raise RuntimeError(f"oracle BILIN_2D: reference would STOP (code {rc})")
     return Z2, dict(metrics=met, alphabeta=ab, ipb=ipb, dist_np=dnp, l_last_y_row_missing=lrow.value, info=info)

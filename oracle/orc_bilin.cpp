@@ -87,6 +87,7 @@ static void minloc_block(const A2<double>& X, int i1, int i2, int j1, int j2, in
 // src/mod_manip.f90:1632-1663
 bool l_is_grid_regular(const A2<const double>& Xlon, const A2<const double>& Xlat) {
   int nx = (int)Xlon.ni, ny = (int)Xlon.nj;
+  if (Xlon.sj == 0 && Xlat.si == 0) return true;  // virtual expansion of 1-D axes: all the sums are exactly 0
   const double tol = (double)1.E-12f;
   bool reg = true;
   for (int jj = 2; jj <= ny; jj++) {
@@ -110,8 +111,9 @@ void is_polar_proj(const A2<const double>& XX, const A2<const double>& YY, bool*
   int nx = (int)YY.ni, ny = (int)YY.nj;
   *jjNP = -1;
   bool lipp = false;
-  for (int64_t k = 0; k < (int64_t)nx * ny; k++)
-    if (YY.p[k] > 88.0) { lipp = true; break; }
+  for (int jj = 1; jj <= ny && !lipp; jj++)
+    for (int ji = 1; ji <= nx; ji++)
+      if (YY(ji, jj) > 88.0) { lipp = true; break; }
   int jNP = 0;
   if (lipp) {
     double best = 0.0;
@@ -196,7 +198,7 @@ static void find_nearest_easy(const A2<const double>& Xtrg, const A2<const doubl
           // same arithmetic on a window-sized scratch: shift the view so (i1s,j1s) is element (1,1)
           int wi = i2s - i1s + 1, wj = j2s - j1s + 1;
           A2<double> W(xd_store.data(), wi, wj);
-          A2<const double> Xs(&Xsrc(i1s, j1s), Xsrc.ni, Xsrc.nj), Ys(&Ysrc(i1s, j1s), Ysrc.ni, Ysrc.nj);
+          A2<const double> Xs(&Xsrc(i1s, j1s), Xsrc.ni, Xsrc.nj, Xsrc.si, Xsrc.sj), Ys(&Ysrc(i1s, j1s), Ysrc.ni, Ysrc.nj, Ysrc.si, Ysrc.sj);
           // distance_2d_block indexes (ji,jj) on both; emulate with explicit loops
           const double zconv = kPi / 180.0;
           const double zr = earth_radius_km();
@@ -240,10 +242,10 @@ static void find_nearest_twisted(const A2<const double>& Xtrg, const A2<const do
   std::vector<double> xd_store(ns);
   A2<double> Xdist(xd_store.data(), nx_s, ny_s);
 
-  double y_min_s = Ysrc.p[0], y_max_s = Ysrc.p[0];
-  for (int64_t k = 1; k < ns; k++) { y_min_s = std::min(y_min_s, Ysrc.p[k]); y_max_s = std::max(y_max_s, Ysrc.p[k]); }
-  double y_min_t = Ytrg.p[0], y_max_t = Ytrg.p[0];
-  for (int64_t k = 1; k < nt; k++) { y_min_t = std::min(y_min_t, Ytrg.p[k]); y_max_t = std::max(y_max_t, Ytrg.p[k]); }
+  double y_min_s = Ysrc(1, 1), y_max_s = Ysrc(1, 1);
+  for (int jj = 1; jj <= ny_s; jj++) for (int ji = 1; ji <= nx_s; ji++) { y_min_s = std::min(y_min_s, Ysrc(ji, jj)); y_max_s = std::max(y_max_s, Ysrc(ji, jj)); }
+  double y_min_t = Ytrg(1, 1), y_max_t = Ytrg(1, 1);
+  for (int jj = 1; jj <= ny_t; jj++) for (int ji = 1; ji <= nx_t; ji++) { y_min_t = std::min(y_min_t, Ytrg(ji, jj)); y_max_t = std::max(y_max_t, Ytrg(ji, jj)); }
   if ((y_min_t >= y_max_s) || (y_max_t <= y_min_s)) { g_error = 2; return; }
 
   for (int64_t k = 0; k < nt; k++) { JIpos.p[k] = -1; JJpos.p[k] = -1; }
@@ -362,10 +364,11 @@ static void find_nearest_twisted(const A2<const double>& Xtrg, const A2<const do
             double lo1 = std::max(rlon - 0.5, 0.0), hi1 = std::min(rlon + 0.5, 360.0);
             double lo2 = std::max(rlat - 0.5, -90.0), hi2 = std::min(rlat + 0.5, 90.0);
             bool any = false;
-            for (int64_t k = 0; k < ns; k++) {
-              double xs = Xsrc.p[k], ys = Ysrc.p[k];
-              if ((xs > lo1) && (xs < hi1) && (ys > lo2) && (ys < hi2)) { any = true; break; }
-            }
+            for (int jj = 1; jj <= ny_s && !any; jj++)
+              for (int ji = 1; ji <= nx_s; ji++) {
+                double xs = Xsrc(ji, jj), ys = Ysrc(ji, jj);
+                if ((xs > lo1) && (xs < hi1) && (ys > lo2) && (ys < hi2)) { any = true; break; }
+              }
             if (!any) lagain = false;
           }
           if (niter > nsplit / 3) lagain = false;
@@ -392,9 +395,12 @@ int find_nearest_point(const A2<const double>& Xtrg, const A2<const double>& Ytr
   std::vector<int32_t> mstore(mask_domain_trg.p, mask_domain_trg.p + (int64_t)nx_t * ny_t);
   A2<int32_t> mask_ignore_t(mstore.data(), nx_t, ny_t);
 
-  int64_t ns = (int64_t)nx_s * ny_s;
-  double y_min_s = Ysrc.p[0], y_max_s = Ysrc.p[0];
-  for (int64_t k = 1; k < ns; k++) { y_min_s = std::min(y_min_s, Ysrc.p[k]); y_max_s = std::max(y_max_s, Ysrc.p[k]); }
+  double y_min_s = Ysrc(1, 1), y_max_s = Ysrc(1, 1);
+  if (Ysrc.si == 0) {  // virtual expansion of a 1-D axis: every column holds the same values
+    for (int jj = 1; jj <= ny_s; jj++) { y_min_s = std::min(y_min_s, Ysrc(1, jj)); y_max_s = std::max(y_max_s, Ysrc(1, jj)); }
+  } else {
+    for (int jj = 1; jj <= ny_s; jj++) for (int ji = 1; ji <= nx_s; ji++) { y_min_s = std::min(y_min_s, Ysrc(ji, jj)); y_max_s = std::max(y_max_s, Ysrc(ji, jj)); }
+  }
 
   int j_strt_t = 1, j_stop_t = ny_t, jlat_icr = 1;
   double rmin_dlat_dj = (double)-100.f;
@@ -843,29 +849,54 @@ int orc_bilin_2d(int k_ew_per, int nx1, int ny1, const double* X10, const double
                  const float* Z1, int nx2, int ny2, const double* X20, const double* Y20, int trg_1d, float* Z2,
                  const int32_t* mask_domain_trg, int l_reg_src, int i_orca_trg, int first_call, int have_mapping,
                  int32_t* metrics, double* alphabeta, int16_t* ipb, float* dist_np, int* l_last_y_row_missing,
-                 int elide_fill, int nthreads, int* info) {
+                 int elide_fill, int nthreads, int* info, int virtual_src) {
+  // virtual_src != 0 (1-D source axes only): the 2-D expansions X1/Y1/X1w/Y1w of :100-148 are strided VIEWS of
+  // the axes instead of copies (identical values; needed to run the 21600x10800 shape on a sample of targets
+  // without 8 GB of coordinate copies per call).
   const double rmv = kRmv;
+  const bool virt = (src_1d != 0) && (virtual_src != 0);
   int64_t n1 = (int64_t)nx1 * ny1, n2 = (int64_t)nx2 * ny2;
-  std::vector<double> X1v(n1), Y1v(n1);
-  A2<double> X1(X1v.data(), nx1, ny1), Y1(Y1v.data(), nx1, ny1);
-  if (src_1d) {
-    for (int jj = 1; jj <= ny1; jj++) for (int ji = 1; ji <= nx1; ji++) { X1(ji, jj) = X10[ji - 1]; Y1(ji, jj) = Y10[jj - 1]; }
+  std::vector<double> X1v, Y1v;
+  A2<const double> X1c, Y1c;
+  if (virt) {
+    X1c = A2<const double>(X10, nx1, ny1, 1, 0);
+    Y1c = A2<const double>(Y10, nx1, ny1, 0, 1);
   } else {
-    std::memcpy(X1v.data(), X10, sizeof(double) * n1);
-    std::memcpy(Y1v.data(), Y10, sizeof(double) * n1);
+    X1v.resize(n1); Y1v.resize(n1);
+    A2<double> X1(X1v.data(), nx1, ny1), Y1(Y1v.data(), nx1, ny1);
+    if (src_1d) {
+      for (int jj = 1; jj <= ny1; jj++) for (int ji = 1; ji <= nx1; ji++) { X1(ji, jj) = X10[ji - 1]; Y1(ji, jj) = Y10[jj - 1]; }
+    } else {
+      std::memcpy(X1v.data(), X10, sizeof(double) * n1);
+      std::memcpy(Y1v.data(), Y10, sizeof(double) * n1);
+    }
+    X1c = A2<const double>(X1v.data(), nx1, ny1);
+    Y1c = A2<const double>(Y1v.data(), nx1, ny1);
   }
   bool l_add_extra_j = false;
   int ny1w = ny1;
   if (l_reg_src && (ny1 > 20) && (nx1 > 20)) {
-    double ymx = Y1(nx1 / 2, ny1);
-    if ((ymx < 90.0) && (2.0 * ymx - Y1(nx1 / 2, ny1 - 1) >= 90.0)) { ny1w = ny1 + 2; l_add_extra_j = true; }
+    double ymx = Y1c(nx1 / 2, ny1);
+    if ((ymx < 90.0) && (2.0 * ymx - Y1c(nx1 / 2, ny1 - 1) >= 90.0)) { ny1w = ny1 + 2; l_add_extra_j = true; }
   }
   int64_t n1w = (int64_t)nx1 * ny1w;
-  std::vector<double> X1wv(n1w), Y1wv(n1w);
+  std::vector<double> X1wv, Y1wv, latw;
   std::vector<float> Z1wv(n1w);
-  A2<double> X1w(X1wv.data(), nx1, ny1w), Y1w(Y1wv.data(), nx1, ny1w);
   A2<float> Z1w(Z1wv.data(), nx1, ny1w);
-  A2<const double> X1c(X1v.data(), nx1, ny1), Y1c(Y1v.data(), nx1, ny1);
+  A2<double> X1w, Y1w;          // physical working arrays (dense mode)
+  A2<const double> X1wc, Y1wc;  // what the rest of the routine reads
+  if (virt) {
+    latw.assign(Y10, Y10 + ny1);
+    if (l_add_extra_j) { latw.push_back(90.0); latw.push_back(90.0 + (Y1c(nx1 / 2, ny1) - Y1c(nx1 / 2, ny1 - 1))); }
+    X1wc = A2<const double>(X10, nx1, ny1w, 1, 0);
+    Y1wc = A2<const double>(latw.data(), nx1, ny1w, 0, 1);
+  } else {
+    X1wv.resize(n1w); Y1wv.resize(n1w);
+    X1w = A2<double>(X1wv.data(), nx1, ny1w);
+    Y1w = A2<double>(Y1wv.data(), nx1, ny1w);
+    X1wc = A2<const double>(X1wv.data(), nx1, ny1w);
+    Y1wc = A2<const double>(Y1wv.data(), nx1, ny1w);
+  }
 
   std::vector<double> X2v(n2), Y2v(n2);
   A2<double> X2(X2v.data(), nx2, ny2), Y2(Y2v.data(), nx2, ny2);
@@ -885,17 +916,19 @@ int orc_bilin_2d(int k_ew_per, int nx1, int ny1, const double* X10, const double
     float* Z2s = Z2 + (int64_t)s * n2;
     A2<const float> Z1c(Z1s, nx1, ny1);
     // the reference redoes the extension (coords + field) on every call (:142-148)
-    if (l_add_extra_j) ext_north_to_90_regg(X1c, Y1c, Z1c, X1w, Y1w, Z1w, 1, 1);
+    if (l_add_extra_j) ext_north_to_90_regg(X1c, Y1c, Z1c, X1w, Y1w, Z1w, virt ? 0 : 1, 1);
     else {
-      std::memcpy(X1wv.data(), X1v.data(), sizeof(double) * n1);
-      std::memcpy(Y1wv.data(), Y1v.data(), sizeof(double) * n1);
+      if (!virt) {
+        std::memcpy(X1wv.data(), X1v.data(), sizeof(double) * n1);
+        std::memcpy(Y1wv.data(), Y1v.data(), sizeof(double) * n1);
+      }
       std::memcpy(Z1wv.data(), Z1s, sizeof(float) * n1);
     }
     bool l_first = (first_call != 0) && (s == 0);
     if (l_first) {
       *l_last_y_row_missing = 0;
       if (!have_mapping) {
-        mapping_bl(k_ew_per, A2<const double>(X1wv.data(), nx1, ny1w), A2<const double>(Y1wv.data(), nx1, ny1w),
+        mapping_bl(k_ew_per, X1wc, Y1wc,
                    A2<const double>(X2v.data(), nx2, ny2), A2<const double>(Y2v.data(), nx2, ny2), mask_ignore.data(),
                    metrics, alphabeta, ipb, dist_np, elide_fill, nthreads, info);
         if (g_error) return g_error;
@@ -914,8 +947,8 @@ int orc_bilin_2d(int k_ew_per, int nx1, int ny1, const double* X10, const double
       for (int ji = 1; ji <= nx2; ji++) {
         int iP = IM(ji, jj, 1), jP = IM(ji, jj, 2), iqdrn = IM(ji, jj, 3);
         double alpha = RAB(ji, jj, 1), beta = RAB(ji, jj, 2);
-        if ((std::fabs(degE_to_degWE(X1w(iP, jP)) - degE_to_degWE(X2(ji, jj))) < eps5) &&
-            (std::fabs(Y1w(iP, jP) - Y2(ji, jj)) < eps5))
+        if ((std::fabs(degE_to_degWE(X1wc(iP, jP)) - degE_to_degWE(X2(ji, jj))) < eps5) &&
+            (std::fabs(Y1wc(iP, jP) - Y2(ji, jj)) < eps5))
           Z2a(ji, jj) = Z1w(iP, jP);
         else
           Z2a(ji, jj) = interp_bl(st, k_ew_per, iP, jP, iqdrn, alpha, beta, Z1wc);

@@ -29,14 +29,18 @@ inline double m_log(double x) { return g_libm ? pm_log(x) : std::log(x); }
 inline double m_atan2(double y, double x) { return g_libm ? pm_atan2(y, x) : std::atan2(y, x); }
 inline float m_expf(float x) { return g_libm ? pm_expf(x) : ::expf(x); }
 
-// Fortran (ni,nj) column-major, 1-based
+// Fortran (ni,nj) column-major, 1-based.  Strides (si,sj) default to (1,ni); a 1-D axis can be viewed as
+// its 2-D expansion without materialising it (si=1,sj=0 for lon(i); si=0,sj=1 for lat(j)): same values
+// as the reference's X1(:,jj)=X10(:,1) copies (src/mod_bilin_2d.f90:103-112), none of the memory.
 template <class T>
 struct A2 {
   T* p;
-  int64_t ni, nj;
-  A2() : p(nullptr), ni(0), nj(0) {}
-  A2(T* p_, int64_t ni_, int64_t nj_) : p(p_), ni(ni_), nj(nj_) {}
-  inline T& operator()(int64_t i, int64_t j) const { return p[(i - 1) + (j - 1) * ni]; }
+  int64_t ni, nj, si, sj;
+  A2() : p(nullptr), ni(0), nj(0), si(1), sj(0) {}
+  A2(T* p_, int64_t ni_, int64_t nj_) : p(p_), ni(ni_), nj(nj_), si(1), sj(ni_) {}
+  A2(T* p_, int64_t ni_, int64_t nj_, int64_t si_, int64_t sj_) : p(p_), ni(ni_), nj(nj_), si(si_), sj(sj_) {}
+  inline T& operator()(int64_t i, int64_t j) const { return p[(i - 1) * si + (j - 1) * sj]; }
+  inline bool dense() const { return si == 1 && sj == ni; }
 };
 template <class T>
 struct A3 {

@@ -33,7 +33,7 @@ def lib_path() -> str:
 # every symbol include/sosie_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
     "sosie_create", "sosie_destroy", "sosie_last_error", "sosie_set_stream", "sosie_sync", "sosie_launch_count",
-    "sosie_version", "sosie_bilin_set_grids", "sosie_bilin_set_grids_dev", "sosie_bilin_map", "sosie_bilin_get_map",
+    "sosie_version", "sosie_profile", "sosie_get_timing", "sosie_bilin_set_shard", "sosie_bilin_set_grids", "sosie_bilin_set_grids_dev", "sosie_bilin_map", "sosie_bilin_get_map",
     "sosie_bilin_load_map", "sosie_bilin_map_info", "sosie_bilin_apply", "sosie_bilin_apply_dev", "sosie_bilin_apply_ex_dev",
     "sosie_bilin_apply_uv_dev", "sosie_bilin_2d", "sosie_interp_bl", "sosie_akima_set_grids", "sosie_akima_apply",
     "sosie_akima_apply_dev", "sosie_akima_get_ixy", "sosie_bdrown", "sosie_bdrown_dev", "sosie_smoother", "sosie_drown",
@@ -123,6 +123,10 @@ class Sosie:
             raise SosieError(f"sosie_b200 error {rc}: {msg.decode() if msg else ''}")
 
     def set_stream(self, cuda_stream_handle):
+        """run on the caller's stream (e.g. torch.cuda.Stream().cuda_stream); None = the context's own stream.
+        The legacy default stream (handle 0) cannot be named through the ABI: use a real stream."""
+        if cuda_stream_handle is not None and int(cuda_stream_handle) == 0:
+            raise SosieError("set_stream: handle 0 is the legacy default stream; pass a non-default stream or None")
         self._ck(self._lib.sosie_set_stream(self._h, C.c_void_p(cuda_stream_handle) if cuda_stream_handle else None))
 
     def sync(self):
@@ -131,6 +135,21 @@ class Sosie:
     @property
     def launches(self) -> int:
         return int(self._lib.sosie_launch_count(self._h))
+
+    T_MAP, T_PACK, T_APPLY, T_BDROWN, T_SMOOTH, T_AKIMA_PREP, T_AKIMA_EVAL, T_DROWN = range(8)
+
+    def profile(self, enable=True):
+        """bracket the dominant kernels with CUDA events on the context stream"""
+        self._ck(self._lib.sosie_profile(self._h, int(enable)))
+
+    def timing_ms(self, which: int) -> float:
+        ms = C.c_float(-1.0)
+        self._ck(self._lib.sosie_get_timing(self._h, int(which), C.byref(ms)))
+        return float(ms.value)
+
+    def bilin_set_shard(self, j0: int, j1: int):
+        """this context handles target rows j0..j1 (1-based inclusive); (0,0) = all"""
+        self._ck(self._lib.sosie_bilin_set_shard(self._h, int(j0), int(j1)))
 
     # ---------------------------------------------------------------- bilinear
     def bilin_set_grids(self, k_ew_per, X10, Y10, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0):

@@ -519,15 +519,19 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
   if (ctx->ak_kew > -1) kewp = ctx->ak_kew + 4;
   for (int s0 = 0; s0 < nslab; s0 += nb) {
     int ns = std::min(nb, nslab - s0);
+    prof_begin(ctx, SOSIE_T_AKIMA_PREP);
     k_feb_center<float><<<dim3(grid_for(ctx, ne, 256), ns), 256, 0, st>>>(dZ1 + (size_t)s0 * n1, nx1, ny1, ctx->ak_zF.p, n1, ne); KLAUNCH_CHECK();
     if (int rc = feb_field(ctx, ctx->ak_kew, ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, nx1, ny1, ctx->ak_iorca, ns, tmp)) return rc;
     k_feb_center<double><<<dim3(grid_for(ctx, ne8, 256), ns), 256, 0, st>>>(ctx->ak_zF.p, ni1, nj1, ctx->ak_ZF8.p, ne, ne8); KLAUNCH_CHECK();
     if (int rc = feb_field(ctx, kewp, ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, 0, ns, tmp)) return rc;
     k_slopes<<<dim3(grid_for(ctx, ne, 128), ns), 128, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
                                                                 ctx->ak_sxy.p, ne8, ne); KLAUNCH_CHECK();
+    prof_end(ctx, SOSIE_T_AKIMA_PREP);
+    prof_begin(ctx, SOSIE_T_AKIMA_EVAL);
     k_akima_eval<<<dim3(grid_for(ctx, nt, 128), ns), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, ctx->ak_sx.p, ctx->ak_sy.p, ctx->ak_sxy.p,
                                                                     ni1, nj1, ctx->ak_X2.p, ctx->ak_Y2.p, ctx->ak_ixy.p, nt, ctx->ak_range[0],
                                                                     ctx->ak_range[1], ctx->ak_range[2], ctx->ak_range[3], dZ2 + (size_t)s0 * nt, ne); KLAUNCH_CHECK();
+    prof_end(ctx, SOSIE_T_AKIMA_EVAL);
   }
   return SOSIE_OK;
 }

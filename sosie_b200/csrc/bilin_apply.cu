@@ -24,11 +24,12 @@
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_pack(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ MT, const double* __restrict__ AB, int4* pidx,
-       float4* pw) {
+       float4* pw, size_t k0, size_t kcnt) {
   const size_t nt = (size_t)tg.nx * tg.ny;
   const int nxi = sg.nx, nyi = sg.nyw;
   const double eps5 = (double)1.E-5f;
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+  for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < kcnt; kk += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = k0 + kk;
     int jj = (int)(k / tg.nx) + 1, ji = (int)(k % tg.nx) + 1;
     int iP = max(MT[k], 1), jP = max(MT[k + nt], 1);  // IMETRICS(:,:,1:2) = MAX(IMETRICS(:,:,1:2), 1)  (:217)
     int iqd = MT[k + 2 * nt];
@@ -106,6 +107,10 @@ __device__ __forceinline__ float interp_one(const float* __restrict__ Z, const S
   return w.x;
 }
 
+struct TileGeom {  // 32x8 target tiles over rows j0..j1 (0-based, inclusive) of an (nx, ny) target grid
+  int nx, j0, j1, tiles_x, ntiles;
+};
+
 struct PostOps {
   int use_clamp;
   float vmin, vmax;
@@ -114,14 +119,21 @@ struct PostOps {
 };
 
 #define SLAB_UNROLL 4
+#define APPLY_SLABS_PER_CHUNK 8
 // grid: x = target tiles, y = slab chunks.  Each thread: one target, all slabs of its chunk.
 __global__ void __launch_bounds__(256)
 k_apply(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ Z1,
-        float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po) {
+        float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm) {
   const size_t src_stride = (size_t)v.nreal;
   const int s0 = blockIdx.y * slabs_per_chunk;
   const int s1 = min(s0 + slabs_per_chunk, nslab);
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+  // 32 x 8 target tile per block: a compact source footprint (L1/L2 reuse of the gathers) for any smooth mapping,
+  // and still one full 128-byte store per warp
+  for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
+    const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
+    const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);  // 0-based
+    if (i >= tgm.nx || j > tgm.j1) continue;
+    const size_t k = (size_t)i + (size_t)j * tgm.nx;
     const int4 id = pidx[k];
     const float4 w = pw[k];
     const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
@@ -158,11 +170,15 @@ k_apply(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt,
 __global__ void __launch_bounds__(256)
 k_apply_uv(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ U1,
            const float* __restrict__ V1, float* __restrict__ Uo, float* __restrict__ Vo, const double* __restrict__ xcos,
-           const double* __restrict__ xsin, int nslab, int slabs_per_chunk) {
+           const double* __restrict__ xsin, int nslab, int slabs_per_chunk, TileGeom tgm) {
   const size_t src_stride = (size_t)v.nreal;
   const int s0 = blockIdx.y * slabs_per_chunk;
   const int s1 = min(s0 + slabs_per_chunk, nslab);
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+  for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
+    const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
+    const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);
+    if (i >= tgm.nx || j > tgm.j1) continue;
+    const size_t k = (size_t)i + (size_t)j * tgm.nx;
     const int4 id = pidx[k];
     const float4 w = pw[k];
     const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
@@ -203,25 +219,31 @@ int bilin_pack_impl(sosie_ctx* ctx) {
   const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
   if ((size_t)ctx->sg.nx * ctx->sg.nyw > 2147483647ULL) { ctx->err = "source slab too large for 32-bit offsets"; return SOSIE_ERR_ARG; }
   CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt));
-  k_pack<<<grid_for(ctx, nt, 256), 256, 0, ctx->stream>>>(ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p, ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p);
+  size_t k0, kcnt;
+  shard_range(ctx, &k0, &kcnt);
+  prof_begin(ctx, SOSIE_T_PACK);
+  k_pack<<<grid_for(ctx, kcnt, 256), 256, 0, ctx->stream>>>(ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p, ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p, k0, kcnt);
   KLAUNCH_CHECK();
+  prof_end(ctx, SOSIE_T_PACK);
   ctx->pack_ready = true;
   return SOSIE_OK;
 }
 
-static void apply_grid(const sosie_ctx* ctx, size_t nt, int nslab, dim3& grid, int& spc) {
-  // x covers the targets once (<= 2^31 blocks); y splits the slabs so that the whole grid is a
-  // few waves of 148 SMs x 8 resident CTAs.
-  int gx = (int)((nt + 255) / 256);
-  int waves_target = ctx->num_sms * 8 * 4;
-  int chunks = 1;
-  if (gx < waves_target) chunks = (waves_target + gx - 1) / gx;
-  if (chunks > nslab) chunks = nslab;
-  if (chunks < 1) chunks = 1;
-  spc = (nslab + chunks - 1) / chunks;
-  // keep SLAB_UNROLL granularity when possible
-  if (spc > SLAB_UNROLL) spc = ((spc + SLAB_UNROLL - 1) / SLAB_UNROLL) * SLAB_UNROLL;
-  chunks = (nslab + spc - 1) / spc;
+static void apply_grid(const sosie_ctx* ctx, int nslab, dim3& grid, int& spc, TileGeom& tgm) {
+  size_t k0, kcnt;
+  shard_range(ctx, &k0, &kcnt);
+  tgm.nx = ctx->tg.nx;
+  tgm.j0 = (int)(k0 / (size_t)ctx->tg.nx);
+  tgm.j1 = tgm.j0 + (int)(kcnt / (size_t)ctx->tg.nx) - 1;
+  tgm.tiles_x = (tgm.nx + 31) / 32;
+  int tiles_y = (tgm.j1 - tgm.j0 + 1 + 7) / 8;
+  tgm.ntiles = tgm.tiles_x * tiles_y;
+  // x covers the tiles once (fastest-varying in the block schedule), y the slab chunks: blocks that run together
+  // work on neighbouring tiles of the SAME few slabs, so HBM is streamed slab by slab in whole DRAM pages instead
+  // of 1460 concurrent 13 MB-strided trickles; the 32 B/target records are re-read per chunk from L2, not HBM.
+  int gx = tgm.ntiles;
+  spc = nslab < APPLY_SLABS_PER_CHUNK ? nslab : APPLY_SLABS_PER_CHUNK;
+  int chunks = (nslab + spc - 1) / spc;
   grid = dim3(gx, chunks, 1);
 }
 
@@ -259,9 +281,12 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
   po.use_clamp = use_clamp; po.vmin = vmin; po.vmax = vmax; po.mask_trg = dmask_trg; po.rmiss = rmiss;
   dim3 grid;
   int spc;
-  apply_grid(ctx, nt, nslab, grid, spc);
-  k_apply<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po);
+  TileGeom tgm;
+  apply_grid(ctx, nslab, grid, spc, tgm);
+  prof_begin(ctx, SOSIE_T_APPLY);
+  k_apply<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po, tgm);
   KLAUNCH_CHECK();
+  prof_end(ctx, SOSIE_T_APPLY);
   // l_last_y_row_missing (:241-247) is evaluated on the first call only, the patch (:254-263) on every call
   if (first_call) {
     ctx->l_last_y_row_missing = 0;
@@ -275,7 +300,12 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
       ctx->l_last_y_row_missing = ((rmeanv < G_RMV + (double)0.1f) && (rmeanv > G_RMV - (double)0.1f)) ? 1 : 0;
     }
   }
-  if (ctx->l_last_y_row_missing && !use_clamp && !dmask_trg) {
+  if (ctx->l_last_y_row_missing && (use_clamp || dmask_trg)) {
+    // the reference patches the row inside BILIN_2D, BEFORE INTERP_2D's clamp/mask: not fusable
+    ctx->err = "bilin_apply_ex: fused post-ops cannot be combined with the ORCA last-row patch (l_last_y_row_missing)";
+    return SOSIE_ERR_STATE;
+  }
+  if (ctx->l_last_y_row_missing) {
     for (int s = 0; s < nslab; s++)
       if (int rc = orca_lastrow_patch(ctx, dZ2 + (size_t)s * nt)) return rc;
   }
@@ -291,9 +321,12 @@ int bilin_apply_uv_impl(sosie_ctx* ctx, int nslab, const float* dU1, const float
   v.nx = ctx->sg.nx; v.ny = ctx->sg.ny; v.nreal = ctx->sg.nx * ctx->sg.ny; v.im = ctx->d_im.p;
   dim3 grid;
   int spc;
-  apply_grid(ctx, nt, nslab, grid, spc);
-  k_apply_uv<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dU1, dV1, dUo, dVo, dcos, dsin, nslab, spc);
+  TileGeom tgm;
+  apply_grid(ctx, nslab, grid, spc, tgm);
+  prof_begin(ctx, SOSIE_T_APPLY);
+  k_apply_uv<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dU1, dV1, dUo, dVo, dcos, dsin, nslab, spc, tgm);
   KLAUNCH_CHECK();
+  prof_end(ctx, SOSIE_T_APPLY);
   return SOSIE_OK;
 }
 

@@ -62,8 +62,13 @@ __global__ void k_minmax(const double* __restrict__ a, size_t n, unsigned long l
 __global__ void k_is_regular(const double* __restrict__ X, const double* __restrict__ Y, int nx, int ny, int* irreg) {
   const double tol = (double)1.E-12f;
   __shared__ double sh[32];
+  __shared__ int stop;
   // a/ one block per row jj>=2 : SUM(ABS(Xlon(:,jj)-Xlon(:,1)))
   for (int jj = 2 + blockIdx.x; jj <= ny; jj += gridDim.x) {
+    // the reference EXITs at the first irregular row (:1651): stop early, block-uniformly
+    if (threadIdx.x == 0) stop = *(volatile int*)irreg;
+    __syncthreads();
+    if (stop) return;
     double s = 0.0;
     for (int i = threadIdx.x; i < nx; i += blockDim.x) s += fabs(X[(size_t)i + (size_t)(jj - 1) * nx] - X[i]);
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -77,6 +82,8 @@ __global__ void k_is_regular(const double* __restrict__ X, const double* __restr
     __syncthreads();
   }
   // b/ one thread per column ji : SUM(ABS(Xlat(ji,:)-Xlat(1,:))), sequential in j as the reference
+  //    (only evaluated when a/ passed, :1655)
+  if (*(volatile int*)irreg) return;
   for (int ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nx; ji += gridDim.x * blockDim.x) {
     double s = 0.0;
     for (int jj = 0; jj < ny; jj++) s += fabs(Y[(size_t)ji + (size_t)jj * nx] - Y[(size_t)jj * nx]);
@@ -86,11 +93,22 @@ __global__ void k_is_regular(const double* __restrict__ X, const double* __restr
 
 // rtmp = SUM(Ytrg(:,jm) - Ytrg(:,jm-1)) sequentially (only its sign is used, :921-922)
 __global__ void k_rtmp(TrgGeom tg, Prelude* p) {
+  __shared__ double sh[1024];
   int jm = tg.ny / 2;
-  double r = 0.0;
-  if (jm >= 2)
-    for (int i = 1; i <= tg.nx; i++) r += (trg_lat(tg, i, jm) - trg_lat(tg, i, jm - 1));
-  p->rtmp = r;
+  double r = 0.0;  // carried by thread 0 only
+  if (jm >= 2) {
+    for (int i0 = 1; i0 <= tg.nx; i0 += 1024) {
+      int i = i0 + threadIdx.x;
+      if (i <= tg.nx) sh[threadIdx.x] = trg_lat(tg, i, jm) - trg_lat(tg, i, jm - 1);
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        int n = min(1024, tg.nx - i0 + 1);
+        for (int k = 0; k < n; k++) r += sh[k];  // sequential, in index order, as SUM() does
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) p->rtmp = r;
 }
 
 __global__ void k_min_dlat(TrgGeom tg, Prelude* p) {
@@ -152,6 +170,9 @@ __global__ void k_build_src2d(const double* __restrict__ Xin, const double* __re
     unit_vec(lo, la, ux, uy, uz);
     vx[k] = ux; vy[k] = uy; vz[k] = uz;
   }
+}
+__global__ void k_merc_table(const double* __restrict__ lat, size_t n, double* merc) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) merc[k] = d_merc(lat[k]);
 }
 __global__ void k_lat_table(const double* __restrict__ Yin, int ny, int nyw, double dyp, double* lat) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nyw; j += gridDim.x * blockDim.x)
@@ -242,18 +263,18 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
   if (iPm1 == 0) { if (k_ew >= 0) iPm1 = nxi - k_ew; }
   if (iPp1 == nxi + 1) { if (k_ew >= 0) iPp1 = 1 + k_ew; }
   if ((iPm1 < 1) || (jPm1 < 1) || (iPp1 > nxi)) return;
-  double lonP = fmod(src_lon(sg, iP, jP), 360.0), latP = src_lat(sg, iP, jP);
-  double lonN = fmod(src_lon(sg, iP, jPp1), 360.0), latN = src_lat(sg, iP, jPp1);
-  double lonE = fmod(src_lon(sg, iPp1, jP), 360.0), latE = src_lat(sg, iPp1, jP);
-  double lonS = fmod(src_lon(sg, iP, jPm1), 360.0), latS = src_lat(sg, iP, jPm1);
-  double lonW = fmod(src_lon(sg, iPm1, jP), 360.0), latW = src_lat(sg, iPm1, jP);
-  xP = fmod(xP, 360.0);
-  double ya = d_merc(latP);
+  double lonP = d_mod(src_lon(sg, iP, jP), 360.0), latP = src_lat(sg, iP, jP);
+  double lonN = d_mod(src_lon(sg, iP, jPp1), 360.0), latN = src_lat(sg, iP, jPp1);
+  double lonE = d_mod(src_lon(sg, iPp1, jP), 360.0), latE = src_lat(sg, iPp1, jP);
+  double lonS = d_mod(src_lon(sg, iP, jPm1), 360.0), latS = src_lat(sg, iP, jPm1);
+  double lonW = d_mod(src_lon(sg, iPm1, jP), 360.0), latW = src_lat(sg, iPm1, jP);
+  xP = d_mod(xP, 360.0);
+  double ya = src_merc(sg, iP, jP);
   double hP = d_heading_y(lonP, xP, ya, d_merc(yP));
-  double hN = d_heading_y(lonP, lonN, ya, d_merc(latN));
-  double hE = d_heading_y(lonP, lonE, ya, d_merc(latE));
-  double hS = d_heading_y(lonP, lonS, ya, d_merc(latS));
-  double hW = d_heading_y(lonP, lonW, ya, d_merc(latW));
+  double hN = d_heading_y(lonP, lonN, ya, src_merc(sg, iP, jPp1));
+  double hE = d_heading_y(lonP, lonE, ya, src_merc(sg, iPp1, jP));
+  double hS = d_heading_y(lonP, lonS, ya, src_merc(sg, iP, jPm1));
+  double hW = d_heading_y(lonP, lonW, ya, src_merc(sg, iPm1, jP));
   int iqdrn = 4;
   double hPp = d_degE_to_degWE(hP);
   if (hN > hE) hN = hN - 360.0;
@@ -272,22 +293,22 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
     switch (iqdrn) {
       case 1:
         loni[2] = lonE; lati[2] = latE;
-        loni[3] = fmod(src_lon(sg, iPp1, jPp1), 360.0); lati[3] = src_lat(sg, iPp1, jPp1);
+        loni[3] = d_mod(src_lon(sg, iPp1, jPp1), 360.0); lati[3] = src_lat(sg, iPp1, jPp1);
         loni[4] = lonN; lati[4] = latN;
         break;
       case 2:
         loni[2] = lonS; lati[2] = latS;
-        loni[3] = fmod(src_lon(sg, iPp1, jPm1), 360.0); lati[3] = src_lat(sg, iPp1, jPm1);
+        loni[3] = d_mod(src_lon(sg, iPp1, jPm1), 360.0); lati[3] = src_lat(sg, iPp1, jPm1);
         loni[4] = lonE; lati[4] = latE;
         break;
       case 3:
         loni[2] = lonW; lati[2] = latW;
-        loni[3] = fmod(src_lon(sg, iPm1, jPm1), 360.0); lati[3] = src_lat(sg, iPm1, jPm1);
+        loni[3] = d_mod(src_lon(sg, iPm1, jPm1), 360.0); lati[3] = src_lat(sg, iPm1, jPm1);
         loni[4] = lonS; lati[4] = latS;
         break;
       case 4:
         loni[2] = lonN; lati[2] = latN;
-        loni[3] = fmod(src_lon(sg, iPm1, jPp1), 360.0); lati[3] = src_lat(sg, iPm1, jPp1);
+        loni[3] = d_mod(src_lon(sg, iPm1, jPp1), 360.0); lati[3] = src_lat(sg, iPm1, jPp1);
         loni[4] = lonW; lati[4] = latW;
         break;
       default: break;
@@ -332,9 +353,10 @@ __device__ __forceinline__ void map_store(const MapOut& o, int iP, int jP, int m
 __global__ void __launch_bounds__(128)
 k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
            const double* __restrict__ vlat, int sorted_lon, int sorted_lat, int jlo, int jhi, int32_t* MT, double* AB,
-           int16_t* IDP, float* DNP, int* err) {
+           int16_t* IDP, float* DNP, int* err, size_t k0, size_t kcnt) {
   const size_t nt = (size_t)tg.nx * tg.ny;
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+  for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < kcnt; kk += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = k0 + kk;
     int jj_t = (int)(k / tg.nx) + 1, ji_t = (int)(k % tg.nx) + 1;
     int m = mask ? mask[k] : 1;
     int iP = -1, jP = -1;
@@ -564,6 +586,11 @@ __global__ void k_twisted_scatter(const int64_t* __restrict__ order, int T, cons
 __global__ void k_fill_i32(int32_t* a, size_t n, int32_t v) {
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) a[k] = v;
 }
+int fill_i32_dev(sosie_ctx* ctx, int32_t* p, size_t n, int32_t v) {
+  k_fill_i32<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, v);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
 // WHERE(JIpos==-1) mask_t=-1 ; WHERE(JJpos==-1) mask_t=-2   (:1434-1435)
 __global__ void k_twisted_mask(const int32_t* __restrict__ JI, const int32_t* __restrict__ JJ, int32_t* mask, size_t n) {
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
@@ -619,6 +646,9 @@ int bilin_prepare_src(sosie_ctx* ctx) {
     k_lat_table<<<cdiv(nyw, 256), 256, 0, st>>>(Yin, ny, nyw, dyp, ctx->s_lat1.p); KLAUNCH_CHECK();
     k_trig_table<<<cdiv(nx, 256), 256, 0, st>>>(Xin, nx, ctx->s_clon.p, ctx->s_slon.p); KLAUNCH_CHECK();
     k_trig_table<<<cdiv(nyw, 256), 256, 0, st>>>(ctx->s_lat1.p, nyw, ctx->s_clat.p, ctx->s_slat.p); KLAUNCH_CHECK();
+    CK(ctx->s_merc.alloc(nyw));
+    k_merc_table<<<cdiv(nyw, 256), 256, 0, st>>>(ctx->s_lat1.p, nyw, ctx->s_merc.p); KLAUNCH_CHECK();
+    sg.merc = ctx->s_merc.p;
     sg.separable = 1;
     sg.lon1 = Xin; sg.lat1 = ctx->s_lat1.p;
     sg.clon = ctx->s_clon.p; sg.slon = ctx->s_slon.p; sg.clat = ctx->s_clat.p; sg.slat = ctx->s_slat.p;
@@ -627,6 +657,9 @@ int bilin_prepare_src(sosie_ctx* ctx) {
     CK(ctx->s_X.alloc(n)); CK(ctx->s_Y.alloc(n)); CK(ctx->s_vx.alloc(n)); CK(ctx->s_vy.alloc(n)); CK(ctx->s_vz.alloc(n));
     k_build_src2d<<<grid_for(ctx, n, 256), 256, 0, st>>>(Xin, Yin, nx, ny, nyw, 0, dyp, ctx->s_X.p, ctx->s_Y.p, ctx->s_vx.p,
                                                           ctx->s_vy.p, ctx->s_vz.p); KLAUNCH_CHECK();
+    CK(ctx->s_merc.alloc(n));
+    k_merc_table<<<grid_for(ctx, n, 256), 256, 0, st>>>(ctx->s_Y.p, n, ctx->s_merc.p); KLAUNCH_CHECK();
+    sg.merc = ctx->s_merc.p;
     sg.separable = 0;
     sg.X = ctx->s_X.p; sg.Y = ctx->s_Y.p; sg.vx = ctx->s_vx.p; sg.vy = ctx->s_vy.p; sg.vz = ctx->s_vz.p;
   }
@@ -651,8 +684,10 @@ int bilin_map_impl(sosie_ctx* ctx) {
   const size_t nt = (size_t)tg.nx * tg.ny;
   const size_t nsrc = (size_t)sg.nx * sg.nyw;
   CK(ctx->d_metrics.alloc(3 * nt)); CK(ctx->d_ab.alloc(2 * nt)); CK(ctx->d_ipb.alloc(nt)); CK(ctx->d_dnp.alloc(nt));
-  DBuf<Prelude> dpre; CK(dpre.alloc(1));
-  DBuf<int> derr; CK(derr.alloc(1));
+  CK(ctx->d_scratch.alloc(64)); CK(ctx->d_iscratch.alloc(4));
+  struct { Prelude* p; } dpre = {reinterpret_cast<Prelude*>(ctx->d_scratch.p)};
+  struct { int* p; } derr = {reinterpret_cast<int*>(ctx->d_iscratch.p)};
+  static_assert(sizeof(Prelude) <= 64 * sizeof(double), "Prelude does not fit the scratch buffer");
   CK(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
   k_prelude_init<<<1, 1, 0, st>>>(dpre.p); KLAUNCH_CHECK();
 
@@ -665,7 +700,7 @@ int bilin_map_impl(sosie_ctx* ctx) {
   if (!sg.separable) { k_is_regular<<<grid_for(ctx, (size_t)sg.nyw * 32, 256), 256, 0, st>>>(sg.X, sg.Y, sg.nx, sg.nyw, &dpre.p->irreg_s); KLAUNCH_CHECK(); }
   if (!tg.is_1d) { k_is_regular<<<grid_for(ctx, (size_t)tg.ny * 32, 256), 256, 0, st>>>(tg.X, tg.Y, tg.nx, tg.ny, &dpre.p->irreg_t); KLAUNCH_CHECK(); }
   if (tg.nx > 2) {
-    k_rtmp<<<1, 1, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
+    k_rtmp<<<1, 1024, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
     k_min_dlat<<<grid_for(ctx, nt, 256), 256, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
   }
   Prelude hp;
@@ -699,16 +734,20 @@ int bilin_map_impl(sosie_ctx* ctx) {
   if (l_is_reg_s) {
     // ---- FIND_NEAREST_EASY + body, fused
     ctx->map_info[5] = 0;
-    DBuf<double> vax; CK(vax.alloc(sg.nx + sg.nyw));
+    CK(ctx->d_vax.alloc(sg.nx + sg.nyw));
+    struct { double* p; } vax = {ctx->d_vax.p};
     k_gather_axes<<<cdiv(sg.nx + sg.nyw, 256), 256, 0, st>>>(sg, vax.p, vax.p + sg.nx); KLAUNCH_CHECK();
     std::vector<double> hax(sg.nx + sg.nyw);
     CK(cudaMemcpyAsync(hax.data(), vax.p, sizeof(double) * hax.size(), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     int sorted_lon = is_sorted_host(hax, 0, sg.nx), sorted_lat = is_sorted_host(hax, sg.nx, sg.nyw);
     int jlo = j_strt_t < j_stop_t ? j_strt_t : j_stop_t, jhi = j_strt_t < j_stop_t ? j_stop_t : j_strt_t;
-    k_map_easy<<<grid_for(ctx, nt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
-                                                           sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p); KLAUNCH_CHECK();
-    CK(cudaStreamSynchronize(st));  // vax lifetime
+    size_t k0, kcnt;
+    shard_range(ctx, &k0, &kcnt);
+    prof_begin(ctx, SOSIE_T_MAP);
+    k_map_easy<<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
+                                                             sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p, k0, kcnt); KLAUNCH_CHECK();
+    prof_end(ctx, SOSIE_T_MAP);
   } else {
     // ---- FIND_NEAREST_TWISTED
     ctx->map_info[5] = 1;
@@ -813,7 +852,9 @@ int bilin_map_impl(sosie_ctx* ctx) {
     if (T > 0) {
       DBuf<int2> bpos, S0, S1; DBuf<int8_t> bfound, found; DBuf<int> dchg;
       CK(bpos.alloc(T)); CK(S0.alloc(T)); CK(S1.alloc(T)); CK(bfound.alloc(T)); CK(found.alloc(T)); CK(dchg.alloc(1));
+      prof_begin(ctx, SOSIE_T_MAP);
       k_twisted_band<<<grid_for(ctx, (size_t)T * 32, 256), 256, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, derr.p); KLAUNCH_CHECK();
+      prof_end(ctx, SOSIE_T_MAP);
       CK(cudaMemcpyAsync(S0.p, bpos.p, sizeof(int2) * T, cudaMemcpyDeviceToDevice, st));
       int2* Sa = S0.p;
       int2* Sb = S1.p;

@@ -6,6 +6,7 @@
 #include "geom.cuh"
 
 int akima_expand_axes(sosie_ctx* ctx, const double* dX1d, const double* dY1d, int nx, int ny, double* dX, double* dY);
+int fill_i32_dev(sosie_ctx* ctx, int32_t* p, size_t n, int32_t v);
 
 #define NEED(ctx_)                                   \
   if (!(ctx_)) return SOSIE_ERR_ARG;                 \
@@ -66,6 +67,27 @@ int sosie_sync(sosie_ctx* c) {
 
 int64_t sosie_launch_count(const sosie_ctx* c) { return c ? c->launches : 0; }
 
+int sosie_profile(sosie_ctx* c, int32_t enable) {
+  NEED(c);
+  ctx->prof = enable != 0;
+  return SOSIE_OK;
+}
+int sosie_get_timing(sosie_ctx* c, int32_t id, float* ms) {
+  NEED(c);
+  if (id < 0 || id >= SOSIE_T_COUNT || !ms) return SOSIE_ERR_ARG;
+  if (!ctx->ev_used[id]) { *ms = -1.f; return SOSIE_OK; }
+  CK(cudaEventSynchronize(ctx->ev1[id]));
+  CK(cudaEventElapsedTime(ms, ctx->ev0[id], ctx->ev1[id]));
+  return SOSIE_OK;
+}
+int sosie_bilin_set_shard(sosie_ctx* c, int32_t j0, int32_t j1) {
+  NEED(c);
+  if (j0 < 0 || j1 < j0) { ctx->err = "sosie_bilin_set_shard: bad row range"; return SOSIE_ERR_ARG; }
+  ctx->shard_j0 = j0; ctx->shard_j1 = j1;
+  ctx->pack_ready = false;
+  return SOSIE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_1d, int l_reg_src, int nx2, int ny2, int trg_1d,
                             const int32_t* dmask, bool mask_on_device, int i_orca_trg) {
@@ -83,9 +105,7 @@ static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_
   if (dmask) {
     CK(cudaMemcpyAsync(ctx->t_mask.p, dmask, nt * sizeof(int32_t), mask_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   } else {
-    std::vector<int32_t> ones(nt, 1);
-    CK(cudaMemcpyAsync(ctx->t_mask.p, ones.data(), nt * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (int rc = fill_i32_dev(ctx, ctx->t_mask.p, nt, 1)) return rc;
   }
   if (int rc = bilin_prepare_src(ctx)) return rc;
   ctx->grids_set = true;
@@ -101,7 +121,6 @@ int sosie_bilin_set_grids(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, 
   if (!X10 || !Y10 || !X20 || !Y20) { ctx->err = "sosie_bilin_set_grids: null coordinate pointer"; return SOSIE_ERR_ARG; }
   size_t nsx = src_1d ? (size_t)nx1 : (size_t)nx1 * ny1, nsy = src_1d ? (size_t)ny1 : (size_t)nx1 * ny1;
   size_t ntx = trg_1d ? (size_t)nx2 : (size_t)nx2 * ny2, nty = trg_1d ? (size_t)ny2 : (size_t)nx2 * ny2;
-  ctx->s_in_X.release(); ctx->s_in_Y.release(); ctx->t_X.release(); ctx->t_Y.release();
   CK(ctx->s_in_X.alloc(nsx)); CK(ctx->s_in_Y.alloc(nsy)); CK(ctx->t_X.alloc(ntx)); CK(ctx->t_Y.alloc(nty));
   CK(cudaMemcpyAsync(ctx->s_in_X.p, X10, nsx * 8, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(ctx->s_in_Y.p, Y10, nsy * 8, cudaMemcpyHostToDevice, ctx->stream));

@@ -12,6 +12,7 @@
 #include "pmath.h"
 
 #define SOSIE_NUM_SMS_B200 148
+#define SOSIE_T_COUNT 8
 
 template <class T>
 struct DBuf {  // owning device buffer (or borrowed pointer when own == false)
@@ -57,6 +58,7 @@ struct SrcGeom {
   const double* vx = nullptr;    // unit vectors [nx*nyw]
   const double* vy = nullptr;
   const double* vz = nullptr;
+  const double* merc = nullptr;  // Mercator ordinate of heading() per source latitude: [nyw] (separable) or [nx*nyw]
 };
 
 struct TrgGeom {
@@ -78,9 +80,14 @@ struct sosie_ctx {
   int k_ew = -1, l_reg_src = 0, i_orca_trg = 0, l_add_extra_j = 0;
   bool grids_set = false, map_ready = false, pack_ready = false;
   size_t map_nt = 0;             // target count the cached mapping was built/loaded for
+  int shard_j0 = 0, shard_j1 = 0; // 1-based inclusive target rows handled by this context (0,0 = all)
+  // ---- per-kernel CUDA-event timing (sosie_profile / sosie_get_timing)
+  bool prof = false;
+  cudaEvent_t ev0[SOSIE_T_COUNT] = {}, ev1[SOSIE_T_COUNT] = {};
+  bool ev_used[SOSIE_T_COUNT] = {};
   SrcGeom sg;
   TrgGeom tg;
-  DBuf<double> s_lon1, s_lat1, s_clon, s_slon, s_clat, s_slat, s_X, s_Y, s_vx, s_vy, s_vz;
+  DBuf<double> s_lon1, s_lat1, s_clon, s_slon, s_clat, s_slat, s_X, s_Y, s_vx, s_vy, s_vz, s_merc;
   DBuf<double> s_in_X, s_in_Y;   // uploaded (or borrowed) raw source coordinates
   DBuf<double> t_X, t_Y;
   DBuf<int32_t> t_mask;          // mask_domain_trg as modified by the search
@@ -92,8 +99,9 @@ struct sosie_ctx {
   DBuf<int4> d_pidx;             // packed apply records
   DBuf<float4> d_pw;
   DBuf<float> d_stage1, d_stage2;  // staging for host-pointer apply
-  DBuf<double> d_scratch;        // reductions
-  DBuf<int32_t> d_iscratch;
+  DBuf<double> d_scratch;        // Prelude + misc scalars of the search
+  DBuf<int32_t> d_iscratch;      // error flag
+  DBuf<double> d_vax;            // vlon/vlat axes of the EASY search
   int32_t map_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int l_last_y_row_missing = 0;
 
@@ -134,6 +142,26 @@ struct sosie_ctx {
   } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// event brackets around the dominant kernels (ids: SOSIE_T_* in sosie_b200.h)
+static inline void prof_begin(sosie_ctx* ctx, int id) {
+  if (!ctx->prof) return;
+  if (!ctx->ev0[id]) { cudaEventCreate(&ctx->ev0[id]); cudaEventCreate(&ctx->ev1[id]); }
+  cudaEventRecord(ctx->ev0[id], ctx->stream);
+}
+static inline void prof_end(sosie_ctx* ctx, int id) {
+  if (!ctx->prof) return;
+  cudaEventRecord(ctx->ev1[id], ctx->stream);
+  ctx->ev_used[id] = true;
+}
+// target index range [k0, k0+cnt) of this context's shard
+static inline void shard_range(const sosie_ctx* ctx, size_t* k0, size_t* cnt) {
+  size_t nx = (size_t)ctx->tg.nx, ny = (size_t)ctx->tg.ny;
+  if (ctx->shard_j0 >= 1 && ctx->shard_j1 >= ctx->shard_j0 && (size_t)ctx->shard_j1 <= ny) {
+    *k0 = (size_t)(ctx->shard_j0 - 1) * nx;
+    *cnt = (size_t)(ctx->shard_j1 - ctx->shard_j0 + 1) * nx;
+  } else { *k0 = 0; *cnt = nx * ny; }
+}
 
 // grid size for grid-stride kernels: a multiple of the SM count (148 on B200)
 static inline int grid_for(const sosie_ctx* ctx, int64_t work_items, int block, int max_blocks_per_sm = 8) {

@@ -445,10 +445,12 @@ static int smoother_dev(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, i
   float* a = dX;
   float* b = ctx->dr_x2.p;
   dim3 grid(grid_for(ctx, n, 256, 4), nslab);
+  prof_begin(ctx, SOSIE_T_SMOOTH);
   for (int js = 0; js < nsmooth; js++) {
     k_smooth_pass<<<grid, 256, 0, st>>>(g, a, b, xorig, dmsk, msk_per_slab, l_emp); KLAUNCH_CHECK();
     std::swap(a, b);
   }
+  prof_end(ctx, SOSIE_T_SMOOTH);
   if (a != dX) CK(cudaMemcpyAsync(dX, a, tot * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return SOSIE_OK;
 }
@@ -475,6 +477,7 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
   int8_t* mc = ctx->dr_m0.p;
   int8_t* mn = ctx->dr_m1.p;
   dim3 grid(grid_for(ctx, n, 256, 4), nslab);
+  prof_begin(ctx, SOSIE_T_BDROWN);
   for (int jinc = 1; jinc <= nb_inc; jinc++) {
     k_bd_sweep<<<grid, 256, 0, st>>>(g, dX, mc, mn, mask_per_slab, cnt + (size_t)(jinc - 1) * nmask, cnt + (size_t)jinc * nmask, nsw,
                                      jinc == 1 ? 1 : 0, pmin, pmax); KLAUNCH_CHECK();
@@ -483,6 +486,7 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
   // NOTE: a slab that left the loop early stops writing its mask; its final mask may live in either
   // buffer.  Exited slabs have no land left, so the pval_land fill cannot touch them; slabs that ran
   // all nb_inc sweeps have their final mask in `mc`.
+  prof_end(ctx, SOSIE_T_BDROWN);
   k_bd_clamp<<<grid, 256, 0, st>>>(dX, n, nsw, pmin, pmax); KLAUNCH_CHECK();
   if (nb_smooth > 0) {
     CK(ctx->dr_mask32.alloc(n * nmask));

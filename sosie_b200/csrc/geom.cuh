@@ -74,11 +74,21 @@ __device__ __forceinline__ double d_merc(double plat) {
   return -pm_log(rr);
 }
 
+// the same ordinate for a source point, from the table built once per grid (identical bits: pure function)
+__device__ __forceinline__ double src_merc(const SrcGeom& g, int i, int j) {
+  return g.separable ? g.merc[j - 1] : g.merc[(size_t)(i - 1) + (size_t)(j - 1) * g.nx];
+}
+// MOD(a, p) for reals; exact shortcut when |a| < p (the common case: longitudes already in [0,360))
+__device__ __forceinline__ double d_mod(double a, double p) {
+  if (fabs(a) < p) return a;
+  return fmod(a, p);
+}
+
 // heading, src/mod_bilin_2d.f90:818-870 (ya passed in: it is shared by the five calls at :511-515)
 __device__ __forceinline__ double d_heading_y(double plona, double plonb, double ya, double yb) {
   double xa = plona * G_ZCONV;
   double xb = plonb * G_ZCONV;
-  double xb_xa = fmod((xb - xa), 2 * G_PI);
+  double xb_xa = d_mod((xb - xa), 2 * G_PI);
   if (xb_xa >= G_PI) xb_xa = xb_xa - 2 * G_PI;
   if (xb_xa <= -G_PI) xb_xa = xb_xa + 2 * G_PI;
   double angled = pm_atan2(xb_xa, yb - ya);
