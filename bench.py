@@ -332,8 +332,8 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     # shard target rows over the ranks
-    r0 = (ny2 * rank) // world + 1
-    r1 = (ny2 * (rank + 1)) // world
+    from sosie_b200.shard import row_shard
+    r0, r1 = row_shard(ny2, rank, world)
     if world > 1:
         ctx.bilin_set_shard(r0, r1)
     my_targets = (r1 - r0 + 1) * nx2

@@ -120,6 +120,7 @@ struct PostOps {
 
 #define SLAB_UNROLL 4
 #define APPLY_SLABS_PER_CHUNK 8
+#define APPLY_SLABS_PER_CHUNK_STAGED 32
 // grid: x = target tiles, y = slab chunks.  Each thread: one target, all slabs of its chunk.
 __global__ void __launch_bounds__(256)
 k_apply(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ Z1,
@@ -163,6 +164,143 @@ k_apply(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt,
       if (masked) r = po.rmiss;
       __stcs(Z2 + (size_t)s * nt + k, r);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Staged variant for batched slabs.  The gathers of a 32x8 target tile fall in a small box of the source
+// slab (a few hundred cells), but on a target whose rows cut across source rows (polar stereographic: the
+// lanes of a warp step through ~10 source rows) every warp-level gather touches ~12 sectors and L1TEX
+// saturates at ~30 % of HBM speed (profiles/ r01).  Here the box is computed once per tile at pack time,
+// each slab's box is streamed into shared memory with cp.async (row segments, NSTAGE slabs in flight), and
+// the four gathers become shared-memory reads: one pass over HBM, L1TEX traffic cut ~5x.
+#define BOXMAX 512
+#define NSTAGE 8
+#define BOX_PER_THREAD (BOXMAX / 256)
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// one block per tile: bounding box (0-based i0, j0, w, h) of the tile's source cells; w == 0 -> not stageable
+__global__ void __launch_bounds__(256)
+k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes) {
+  __shared__ int sh[4][8];
+  __shared__ int shbad[8];
+  for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
+    const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
+    const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);
+    int imin = 2147483647, imax = -1, jmin = 2147483647, jmax = -1, bad = 0;
+    if (i < tgm.nx && j <= tgm.j1) {
+      const int4 id = pidx[(size_t)i + (size_t)j * tgm.nx];
+      if (id.x < 0) bad = 1;
+      else {
+        int c[4] = {id.x, id.y, id.z, id.w};
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (c[q] >= v.nreal) { bad = 1; continue; }
+          int ii = c[q] % v.nx, jj = c[q] / v.nx;
+          imin = min(imin, ii); imax = max(imax, ii); jmin = min(jmin, jj); jmax = max(jmax, jj);
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      imin = min(imin, __shfl_xor_sync(0xffffffffu, imin, o)); imax = max(imax, __shfl_xor_sync(0xffffffffu, imax, o));
+      jmin = min(jmin, __shfl_xor_sync(0xffffffffu, jmin, o)); jmax = max(jmax, __shfl_xor_sync(0xffffffffu, jmax, o));
+      bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    }
+    const int wq = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[0][wq] = imin; sh[1][wq] = imax; sh[2][wq] = jmin; sh[3][wq] = jmax; shbad[wq] = bad; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int q = 1; q < 8; q++) {
+        sh[0][0] = min(sh[0][0], sh[0][q]); sh[1][0] = max(sh[1][0], sh[1][q]);
+        sh[2][0] = min(sh[2][0], sh[2][q]); sh[3][0] = max(sh[3][0], sh[3][q]);
+        shbad[0] |= shbad[q];
+      }
+      int w = sh[1][0] - sh[0][0] + 1, h = sh[3][0] - sh[2][0] + 1;
+      int4 b = make_int4(0, 0, 0, 0);
+      if (!shbad[0] && sh[1][0] >= 0 && (long long)w * h <= BOXMAX) b = make_int4(sh[0][0], sh[2][0], w, h);
+      boxes[tile] = b;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+k_apply_staged(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ Z1,
+               float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm, const int4* __restrict__ boxes) {
+  __shared__ float buf[NSTAGE][BOXMAX];
+  const size_t src_stride = (size_t)v.nreal;
+  const int s0 = blockIdx.y * slabs_per_chunk;
+  const int s1 = min(s0 + slabs_per_chunk, nslab);
+  const int nsl = s1 - s0;
+  for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
+    const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
+    const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);
+    const bool valid = (i < tgm.nx && j <= tgm.j1);
+    const size_t k = valid ? (size_t)i + (size_t)j * tgm.nx : 0;
+    int4 id = make_int4(REC_CONST, 0, 0, 0);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) { id = pidx[k]; w = pw[k]; }
+    const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
+    const bool masked = (valid && po.mask_trg) ? (po.mask_trg[k] == 0) : false;
+    const int4 box = boxes[tile];
+    if (box.z == 0) {  // not stageable (special records, pole rows, E-W wrap, huge footprint): direct gathers
+      if (valid)
+        for (int s = s0; s < s1; s++) {
+          float r = interp_one(Z1 + (size_t)s * src_stride, v, id, w, wup);
+          if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+          if (masked) r = po.rmiss;
+          __stcs(Z2 + (size_t)s * nt + k, r);
+        }
+      continue;  // block-uniform
+    }
+    const int bw = box.z, nelem = box.z * box.w;
+    int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+    if (valid) {
+      o1 = (id.x / v.nx - box.y) * bw + (id.x % v.nx - box.x);
+      o2 = (id.y / v.nx - box.y) * bw + (id.y % v.nx - box.x);
+      o3 = (id.z / v.nx - box.y) * bw + (id.z % v.nx - box.x);
+      o4 = (id.w / v.nx - box.y) * bw + (id.w % v.nx - box.x);
+    }
+    int goff[BOX_PER_THREAD];
+#pragma unroll
+    for (int m = 0; m < BOX_PER_THREAD; m++) {
+      int e = threadIdx.x + 256 * m;
+      goff[m] = (e < nelem) ? (box.y + e / bw) * v.nx + box.x + e % bw : -1;
+    }
+    auto issue = [&](int q) {
+      const float* Z = Z1 + (size_t)(s0 + q) * src_stride;
+      float* b = buf[q % NSTAGE];
+#pragma unroll
+      for (int m = 0; m < BOX_PER_THREAD; m++)
+        if (goff[m] >= 0) cp_async4(b + threadIdx.x + 256 * m, Z + goff[m]);
+    };
+#pragma unroll
+    for (int q = 0; q < NSTAGE - 1; q++) {
+      if (q < nsl) issue(q);
+      cp_async_commit();
+    }
+    for (int q = 0; q < nsl; q++) {
+      cp_async_wait<NSTAGE - 2>();  // this thread's copies of slab q have landed
+      __syncthreads();              // ... everybody's have, and everybody is done reading slab q-1's buffer
+      if (q + NSTAGE - 1 < nsl) issue(q + NSTAGE - 1);  // refills the buffer slab q-1 used
+      cp_async_commit();
+      if (valid) {
+        const float* b = buf[q % NSTAGE];
+        float r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b[o1], w.x), __fmul_rn(b[o2], w.y)), __fmul_rn(b[o3], w.z)), __fmul_rn(b[o4], w.w)), wup);
+        if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+        if (masked) r = po.rmiss;
+        __stcs(Z2 + (size_t)(s0 + q) * nt + k, r);
+      }
+    }
+    __syncthreads();  // the next tile's prologue overwrites the buffers
+    cp_async_wait<0>();
   }
 }
 
@@ -226,6 +364,7 @@ int bilin_pack_impl(sosie_ctx* ctx) {
   KLAUNCH_CHECK();
   prof_end(ctx, SOSIE_T_PACK);
   ctx->pack_ready = true;
+  ctx->boxes_ready = false;
   return SOSIE_OK;
 }
 
@@ -283,10 +422,26 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
   int spc;
   TileGeom tgm;
   apply_grid(ctx, nslab, grid, spc, tgm);
-  prof_begin(ctx, SOSIE_T_APPLY);
-  k_apply<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po, tgm);
-  KLAUNCH_CHECK();
-  prof_end(ctx, SOSIE_T_APPLY);
+  if (nslab >= 2) {
+    // batched slabs: shared-memory staged gathers; the per-tile source boxes are cached with the packed records
+    if (!ctx->boxes_ready) {
+      CK(ctx->d_boxes.alloc(tgm.ntiles));
+      k_tilebox<<<grid_for(ctx, (size_t)tgm.ntiles * 256, 256), 256, 0, ctx->stream>>>(ctx->d_pidx.p, v, tgm, ctx->d_boxes.p);
+      KLAUNCH_CHECK();
+      ctx->boxes_ready = true;
+    }
+    spc = nslab < APPLY_SLABS_PER_CHUNK_STAGED ? nslab : APPLY_SLABS_PER_CHUNK_STAGED;
+    grid = dim3(tgm.ntiles, (nslab + spc - 1) / spc, 1);
+    prof_begin(ctx, SOSIE_T_APPLY);
+    k_apply_staged<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po, tgm, ctx->d_boxes.p);
+    KLAUNCH_CHECK();
+    prof_end(ctx, SOSIE_T_APPLY);
+  } else {
+    prof_begin(ctx, SOSIE_T_APPLY);
+    k_apply<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po, tgm);
+    KLAUNCH_CHECK();
+    prof_end(ctx, SOSIE_T_APPLY);
+  }
   // l_last_y_row_missing (:241-247) is evaluated on the first call only, the patch (:254-263) on every call
   if (first_call) {
     ctx->l_last_y_row_missing = 0;

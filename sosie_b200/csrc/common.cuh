@@ -98,6 +98,8 @@ struct sosie_ctx {
   DBuf<int32_t> d_im;            // ji_m table of EXT_NORTH_TO_90_REGG [nx1]
   DBuf<int4> d_pidx;             // packed apply records
   DBuf<float4> d_pw;
+  DBuf<int4> d_boxes;            // per-tile source bounding boxes of the staged apply
+  bool boxes_ready = false;
   DBuf<float> d_stage1, d_stage2;  // staging for host-pointer apply
   DBuf<double> d_scratch;        // Prelude + misc scalars of the search
   DBuf<int32_t> d_iscratch;      // error flag

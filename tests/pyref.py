@@ -1,0 +1,459 @@
+"""TEST INFRASTRUCTURE -- an independent, slow numpy/Python transliteration of parts of the reference, used only to
+pin the C++ oracle ("two independent transcriptions must agree bit-for-bit").  Array-syntax
+statements of the Fortran source are written as numpy slicing (a different route from the C++ scalar loops).
+
+Arrays here are Fortran-shaped (ni, nj) numpy arrays indexed [i, j] 0-based; helpers convert from the (nj, ni)
+C-order convention of the rest of the repo.
+"""
+import math
+
+import numpy as np
+
+F32 = np.float32
+RIS2 = F32(1.0) / np.sqrt(F32(2.0))
+
+
+def to_f(a):        # (nj, ni) C-order -> (ni, nj) view
+    return np.ascontiguousarray(a).T
+
+
+def from_f(a):
+    return np.ascontiguousarray(a.T)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# scalar geometry (src/mod_manip.f90:1443-1504, src/mod_bilin_2d.f90:697-870, src/mod_poly.f90:54-266), glibc libm
+ZR = float((F32(6378.137) + F32(6356.7523)) / F32(2.0))
+REPS = float(F32(1.0e-9))
+
+
+def distance(lona, lonb, lata, latb):
+    zconv = math.acos(-1.0) / 180.0
+    ux = math.cos(lona * zconv) * math.cos(lata * zconv)
+    uy = math.sin(lona * zconv) * math.cos(lata * zconv)
+    uz = math.sin(lata * zconv)
+    vx = math.cos(lonb * zconv) * math.cos(latb * zconv)
+    vy = math.sin(lonb * zconv) * math.cos(latb * zconv)
+    vz = math.sin(latb * zconv)
+    pds = ux * vx + uy * vy + uz * vz
+    return 0.0 if pds >= 1.0 else ZR * math.acos(pds)
+
+
+def degE_to_degWE(x):
+    return math.copysign(1.0, 180.0 - x) * min(x, abs(x - 360.0))
+
+
+def heading(plona, plonb, plata, platb):
+    zpi = math.acos(-1.0)
+    zconv = zpi / 180.0
+    xa, xb = plona * zconv, plonb * zconv
+    ya = -math.log(max(abs(math.tan(zpi / 4.0 - zconv * plata / 2.0)), REPS))
+    yb = -math.log(max(abs(math.tan(zpi / 4.0 - zconv * platb / 2.0)), REPS))
+    d = math.fmod(xb - xa, 2 * zpi)
+    if d >= zpi:
+        d -= 2 * zpi
+    if d <= -zpi:
+        d += 2 * zpi
+    h = math.atan2(d, yb - ya) * 180.0 / zpi
+    return h + 360.0 if h < 0 else h
+
+
+def l_inpoly(vplon, vplat, px, py):
+    vplon = [float(v) for v in vplon]
+    vplat = [float(v) for v in vplat]
+    rmaxx, rminx = F32(max(vplon)), F32(min(vplon))
+    rmaxy, rminy = F32(max(vplat)), F32(min(vplat))
+    if rminx < 0 or px < 0:
+        raise ValueError("negative longitude")
+    if rminx < F32(10.0) and rmaxx > F32(350.0):
+        zx = math.copysign(1.0, 180.0 - px) * min(px, abs(px - 360.0))
+        vx = [F32(math.copysign(1.0, 180.0 - v) * min(v, abs(v - 360.0))) for v in vplon]
+        rmaxx, rminx = max(vx), min(vx)
+    else:
+        zx = px
+        vx = [F32(v) for v in vplon]
+    zy = py
+    vy = [F32(v) for v in vplat]
+    vx.append(vx[0])
+    vy.append(vy[0])
+    for k in range(5):
+        if vx[k] - F32(int(vx[k])) == 0:
+            vx[k] = F32(vx[k] + F32(0.001))
+        if vy[k] - F32(int(vy[k])) == 0:
+            vy[k] = F32(vy[k] + F32(0.001))
+    if not (zx <= float(rmaxx) and zx >= float(rminx) and zy <= float(rmaxy) and zy >= float(rminy)):
+        return False
+    icross = 0
+    for ji in range(4):
+        jn = 0 if ji == 3 else ji + 1
+        xa, xb, ya, yb = float(vx[ji]), float(vx[jn]), float(vy[ji]), float(vy[jn])
+        rise, run = yb - ya, xb - xa
+        slope = 9999.0 if run == 0 else rise / run
+        if abs(slope) <= float(F32(0.001)):
+            slope = 0.0
+        if slope == 0.0:
+            continue
+        if slope == 9999.0:
+            if zx >= xa and ((zy <= ya and zy > yb) or (zy >= ya and zy < yb)):
+                icross += 1
+        else:
+            rc = slope * xa - ya
+            zxpt = (rc + zy) / slope
+            if ((zxpt <= xa and zxpt > xb) or (zxpt >= xa and zxpt < xb)) and zx >= zxpt:
+                icross += 1
+    return icross % 2 == 1
+
+
+def local_coord(xlam, xphi):
+    zx = [float(v) for v in xlam]
+    xp = [float(v) for v in xphi]
+    if abs(zx[1] - zx[4]) >= 180.0 or abs(zx[1] - zx[2]) >= 180.0 or abs(zx[1] - zx[3]) >= 180.0:
+        zx = [degE_to_degWE(v) for v in zx]
+    zres, dlam, dphi, a, b, n = 1000.0, 0.5, 0.5, 0.0, 0.0, 0
+    zresmax = float(F32(0.1))
+    while zres > zresmax and n < 200:
+        z1, z2, z3 = zx[2] - zx[1], zx[1] - zx[4], zx[3] - zx[2]
+        a11 = z1 + (z2 + z3) * b
+        a12 = -z2 + (z2 + z3) * a
+        a21 = xp[2] - xp[1] + (xp[1] - xp[4] + xp[3] - xp[2]) * b
+        a22 = xp[4] - xp[1] + (xp[1] - xp[4] + xp[3] - xp[2]) * a
+        det = a11 * a22 - a12 * a21
+        det = math.copysign(1.0, det) * max(abs(det), REPS)
+        da = (dlam * a22 - a12 * dphi) / det
+        db = (a11 * dphi - dlam * a21) / det
+        zres = math.sqrt(da * da + db * db)
+        a, b = a + da, b + db
+        dlam = zx[0] - ((1.0 - a) * (1 - b) * zx[1] + a * (1 - b) * zx[2] + a * b * zx[3] + (1 - a) * b * zx[4])
+        dphi = xp[0] - ((1.0 - a) * (1 - b) * xp[1] + a * (1 - b) * xp[2] + a * b * xp[3] + (1 - a) * b * xp[4])
+        n += 1
+    ipb = 0
+    if n >= 200:
+        a, b, ipb = 0.5, 0.5, 11
+    if xp[1] == xp[2] == xp[3] == xp[4]:
+        a, b, ipb = 0.5, 0.5, 12
+    return a, b, ipb
+
+
+def find_nearest_easy_point(rlon, rlat, lon1d, lat1d):
+    """EASY search for one target on a regular source given by its 1-D axes (src/mod_manip.f90:1028-1042); 1-based result."""
+    ip = int(np.argmin(np.abs(lon1d - rlon))) + 1
+    jp = int(np.argmin(np.abs(lat1d - rlat))) + 1
+    i1, i2 = max(ip - 4, 1), min(ip + 4, lon1d.size)
+    j1, j2 = max(jp - 4, 1), min(jp + 4, lat1d.size)
+    best, bi, bj = None, 0, 0
+    zconv = math.acos(-1.0) / 180.0
+    ux = math.cos(rlon * zconv) * math.cos(rlat * zconv)
+    uy = math.sin(rlon * zconv) * math.cos(rlat * zconv)
+    uz = math.sin(rlat * zconv)
+    for jj in range(j1, j2 + 1):
+        for ji in range(i1, i2 + 1):
+            lo, la = lon1d[ji - 1] * zconv, lat1d[jj - 1] * zconv
+            pds = ux * (math.cos(lo) * math.cos(la)) + uy * (math.sin(lo) * math.cos(la)) + uz * math.sin(la)
+            d = ZR * math.acos(min(pds, 1.0))
+            if best is None or d < best:
+                best, bi, bj = d, ji, jj
+    return bi, bj
+
+
+def mapping_point_regular(k_ew, lon1d, lat1d, xP, yP, iP, jP):
+    """One target of MAPPING_BL (src/mod_bilin_2d.f90:459-634) on a regular source; returns (iqdrn, alpha, beta, ipb) or None if skipped."""
+    nxi, nyi = lon1d.size, lat1d.size
+    if not (jP < nyi):
+        return None
+    iPm1, iPp1, jPm1, jPp1 = iP - 1, iP + 1, jP - 1, jP + 1
+    if iPm1 == 0 and k_ew >= 0:
+        iPm1 = nxi - k_ew
+    if iPp1 == nxi + 1 and k_ew >= 0:
+        iPp1 = 1 + k_ew
+    if iPm1 < 1 or jPm1 < 1 or iPp1 > nxi:
+        return None
+    X = lambda i: math.fmod(lon1d[i - 1], 360.0)  # noqa: E731
+    Y = lambda j: float(lat1d[j - 1])             # noqa: E731
+    lonP, latP = X(iP), Y(jP)
+    lonN, latN, lonE, latE = X(iP), Y(jPp1), X(iPp1), Y(jP)
+    lonS, latS, lonW, latW = X(iP), Y(jPm1), X(iPm1), Y(jP)
+    xP = math.fmod(xP, 360.0)
+    hP = heading(lonP, xP, latP, yP)
+    hN, hE = heading(lonP, lonN, latP, latN), heading(lonP, lonE, latP, latE)
+    hS, hW = heading(lonP, lonS, latP, latS), heading(lonP, lonW, latP, latW)
+    iq = 4
+    hPp = degE_to_degWE(hP)
+    if hN > hE:
+        hN -= 360.0
+    if hPp > hN and hPp <= hE:
+        iq = 1
+    if hP > hE and hP <= hS:
+        iq = 2
+    if hP > hS and hP <= hW:
+        iq = 3
+    if hP > hW and hPp <= hN:
+        iq = 4
+    icpt = 0
+    while True:
+        if iq == 1:
+            quad = [(lonE, latE), (X(iPp1), Y(jPp1)), (lonN, latN)]
+        elif iq == 2:
+            quad = [(lonS, latS), (X(iPp1), Y(jPm1)), (lonE, latE)]
+        elif iq == 3:
+            quad = [(lonW, latW), (X(iPm1), Y(jPm1)), (lonS, latS)]
+        elif iq == 4:
+            quad = [(lonN, latN), (X(iPm1), Y(jPp1)), (lonW, latW)]
+        loni = [xP, lonP] + [q[0] for q in quad]
+        lati = [yP, latP] + [q[1] for q in quad]
+        loni = [v + 360.0 if v <= 0.0 else v for v in loni]
+        ok = l_inpoly(loni[1:], lati[1:], xP, yP)
+        if (not ok) and yP < 88.0:
+            icpt += 1
+            iq = icpt
+        else:
+            break
+        if icpt == 5:
+            iq = 0
+            break
+    a, b, ipb = local_coord(loni, lati)
+    return iq, a, b, ipb
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BDROWN / SMOOTHER in array syntax (src/mod_bdrown.f90), X and mask are (ni, nj) [i, j]
+def smoother(k_ew, X, nsmooth, msk=None, l_emp=False):
+    X = X.astype(F32).copy()
+    ni, nj = X.shape
+    w0 = F32(0.35)
+    omw = F32(1.0) - w0
+    c4 = F32(4.0) * (F32(1.0) + RIS2)
+    xorig = X.copy() if msk is not None else None
+    if l_emp:
+        nbp = np.zeros((ni, nj), np.int32)
+        rdnm = np.full((ni, nj), F32(0.25))
+    I = slice(1, ni - 1)   # 2:ni-1
+    J = slice(1, nj - 1)
+    Ip, Im = slice(2, ni), slice(0, ni - 2)
+    Jp, Jm = slice(2, nj), slice(0, nj - 2)
+    if k_ew >= 0:
+        vim = [ni - k_ew - 1, ni - 2]   # 0-based of (ni-k_ew, ni-1)
+        vip = [1, k_ew]                 # 0-based of (2, 1+k_ew)
+        ivi = [0, ni - 1]
+    for _ in range(nsmooth):
+        xt = X.copy()
+        if l_emp:
+            xt = (xt * msk.astype(F32)).astype(F32)
+        s4 = ((xt[Ip, J] + xt[I, Jp]) + xt[Im, J]) + xt[I, Jm]
+        sd = ((xt[Ip, Jp] + xt[Ip, Jm]) + xt[Im, Jm]) + xt[Im, Jp]
+        if l_emp:
+            m = msk
+            nbp[I, J] = m[Ip, J] + m[I, Jp] + m[Im, J] + m[I, Jm] + m[Ip, Jp] + m[Ip, Jm] + m[Im, Jm] + m[Im, Jp]
+            i4 = (m[Ip, J] + m[I, Jp] + m[Im, J] + m[I, Jm]).astype(F32)
+            idg = (m[Ip, Jp] + m[Ip, Jm] + m[Im, Jm] + m[Im, Jp]).astype(F32)
+            rdnm[I, J] = F32(1.0) / np.maximum((i4 + RIS2 * idg).astype(F32), F32(0.01))
+            X[I, J] = w0 * xt[I, J] + (omw * (s4 + RIS2 * sd)) * rdnm[I, J]
+            X[I, J] = np.where(nbp[I, J] == 0, xorig[I, J], X[I, J])
+        else:
+            X[I, J] = w0 * xt[I, J] + (omw * (s4 + RIS2 * sd)) / c4
+        if k_ew >= 0:
+            for c in range(2):
+                ji, jim, jip = ivi[c], vim[c], vip[c]
+                s4 = ((xt[jip, J] + xt[ji, Jp]) + xt[jim, J]) + xt[ji, Jm]
+                sd = ((xt[jip, Jp] + xt[jip, Jm]) + xt[jim, Jm]) + xt[jim, Jp]
+                if l_emp:
+                    m = msk
+                    nbp[ji, J] = m[jip, J] + m[ji, Jp] + m[jim, J] + m[ji, Jm] + m[jip, Jp] + m[jip, Jm] + m[jim, Jm] + m[jim, Jp]
+                    i4 = (m[jip, J] + m[ji, Jp] + m[jim, J] + m[ji, Jm]).astype(F32)
+                    idg = (m[jip, Jp] + m[jip, Jm] + m[jim, Jm] + m[jim, Jp]).astype(F32)
+                    rdnm[ji, J] = F32(1.0) / np.maximum((i4 + RIS2 * idg).astype(F32), F32(0.01))
+                    X[ji, J] = w0 * xt[ji, J] + (omw * (s4 + RIS2 * sd)) * rdnm[ji, J]
+                    X[ji, J] = np.where(nbp[ji, J] == 0, xorig[ji, J], X[ji, J])
+                else:
+                    X[ji, J] = w0 * xt[ji, J] + (omw * (s4 + RIS2 * sd)) / c4
+        if msk is not None:
+            mf = msk[:, J].astype(F32)
+            X[:, J] = mf * X[:, J] - (msk[:, J] - 1).astype(F32) * xorig[:, J]
+    return X
+
+
+def bdrown(k_ew, X, mask, ninc_max, nsmooth, zmin, zmax, zval_land):
+    X = X.astype(F32).copy()
+    ni, nj = X.shape
+    zmin, zmax = F32(zmin), F32(zmax)
+    maskv = mask.astype(np.int32).copy()
+    for jj in range(nj):
+        nbp = int(mask[:, jj].sum())
+        if nbp > 0:
+            s = F32(0.0)
+            for v, m in zip(X[:, jj], mask[:, jj]):      # sequential REAL(4) SUM
+                s = F32(s + F32(v * F32(m)))
+            zmv = F32(s / F32(nbp))
+            X[mask[:, jj] == 0, jj] = zmv
+    if k_ew >= 0:
+        vim, vip, ivi = [ni - k_ew - 1, ni - 2], [1, k_ew], [0, ni - 1]
+    nsw = 0
+    E = lambda a: a   # noqa: E731
+    for _ in range(ninc_max):
+        if not (maskv == 0).any():
+            break
+        nsw += 1
+        d = X.copy()
+        mv = maskv
+        mc = np.zeros((ni, nj), np.int32)
+        I, J = slice(1, ni - 1), slice(1, nj - 1)
+        Ip, Im, Jp, Jm = slice(2, ni), slice(0, ni - 2), slice(2, nj), slice(0, nj - 2)
+        mc[I, J] = (mv[Ip, J] + mv[I, Jp] + mv[Im, J] + mv[I, Jm]) * (-(mv[I, J] - 1))
+        if k_ew >= 0:
+            for c in range(2):
+                ji, jim, jip = ivi[c], vim[c], vip[c]
+                mc[ji, J] = (mv[jip, J] + mv[ji, Jp] + mv[jim, J] + mv[ji, Jm]) * (-(mv[ji, J] - 1))
+        else:
+            mc[0, J] = (mv[1, J] + mv[0, Jp] + mv[0, Jm]) * (-(mv[0, J] - 1))
+            mc[ni - 1, J] = (mv[ni - 1, Jp] + mv[ni - 2, J] + mv[ni - 1, Jm]) * (-(mv[ni - 1, J] - 1))
+        mc[I, 0] = (mv[Ip, 0] + mv[I, 1] + mv[Im, 0]) * (-(mv[I, 0] - 1))
+        if k_ew >= 0:
+            mc[0, 0] = (mv[1, 0] + mv[0, 1] + mv[ni - k_ew - 1, 0]) * (-(mv[0, 0] - 1))
+            mc[ni - 1, 0] = (mv[k_ew, 0] + mv[ni - 1, 1] + mv[ni - 1, 0]) * (-(mv[ni - 1, 0] - 1))
+        else:
+            mc[0, 0] = (mv[1, 0] + mv[0, 1]) * (-(mv[0, 0] - 1))
+            mc[ni - 1, 0] = (mv[ni - 1, 1] + mv[ni - 1, 0]) * (-(mv[ni - 1, 0] - 1))
+        mc[I, nj - 1] = (mv[Ip, nj - 1] + mv[Im, nj - 1] + mv[I, nj - 2]) * (-(mv[I, nj - 1] - 1))
+        if k_ew >= 0:
+            mc[0, nj - 1] = (mv[1, nj - 1] + mv[ni - k_ew - 1, nj - 1] + mv[0, nj - 2]) * (-(mv[0, nj - 1] - 1))
+            mc[ni - 1, nj - 1] = (mv[k_ew, nj - 1] + mv[ni - 2, nj - 1] + mv[ni - 2, nj - 2]) * (-(mv[ni - 1, nj - 1] - 1))
+        else:
+            mc[0, nj - 1] = (mv[1, nj - 1] + mv[0, nj - 2]) * (-(mv[0, nj - 1] - 1))
+            mc[ni - 1, nj - 1] = (mv[ni - 2, nj - 1] + mv[ni - 2, nj - 2]) * (-(mv[ni - 1, nj - 1] - 1))
+        mc = (mc > 0).astype(np.int32)
+
+        def T(i, j):
+            return F32(F32(mv[i, j]) * d[i, j])
+
+        def TD(i, j):
+            return F32(F32(RIS2 * F32(mv[i, j])) * d[i, j])
+
+        def MD(i, j):
+            return F32(RIS2 * F32(mv[i, j]))
+
+        def upd(directs, diags, grouped):
+            den = F32(sum(int(mv[i, j]) for i, j in directs))
+            if grouped:
+                den = F32(den + F32(RIS2 * F32(sum(int(mv[i, j]) for i, j in diags))))
+            else:
+                for i, j in diags:
+                    den = F32(den + MD(i, j))
+            num = None
+            for i, j in directs:
+                t = T(i, j)
+                num = t if num is None else F32(num + t)
+            for i, j in diags:
+                num = F32(num + TD(i, j))
+            return F32(F32(F32(1.0) / den) * num)
+
+        for ji, jj in zip(*np.nonzero(mc)):
+            per = k_ew >= 0
+            if 1 <= jj <= nj - 2:
+                if 1 <= ji <= ni - 2:
+                    v = upd([(ji + 1, jj), (ji, jj + 1), (ji - 1, jj), (ji, jj - 1)],
+                            [(ji + 1, jj + 1), (ji - 1, jj + 1), (ji - 1, jj - 1), (ji + 1, jj - 1)], True)
+                elif per:
+                    c = 0 if ji == 0 else 1
+                    jim, jip = vim[c], vip[c]
+                    v = upd([(jip, jj), (ji, jj + 1), (jim, jj), (ji, jj - 1)],
+                            [(jip, jj + 1), (jim, jj + 1), (jim, jj - 1), (jip, jj - 1)], True)
+                elif ji == 0:
+                    v = upd([(1, jj), (0, jj + 1), (0, jj - 1)], [(1, jj + 1), (1, jj - 1)], False)
+                else:
+                    v = upd([(ji, jj + 1), (ni - 2, jj), (ji, jj - 1)], [(ni - 2, jj + 1), (ni - 2, jj - 1)], False)
+            elif jj == nj - 1:
+                if 1 <= ji <= ni - 2:
+                    v = upd([(ji + 1, jj), (ji - 1, jj), (ji, jj - 1)], [(ji - 1, jj - 1), (ji + 1, jj - 1)], False)
+                elif per:
+                    c = 0 if ji == 0 else 1
+                    jim, jip = vim[c], vip[c]
+                    v = upd([(jip, jj), (jim, jj), (ji, jj - 1)], [(jim, jj - 1), (jip, jj - 1)], False)
+                elif ji == 0:
+                    v = upd([(1, jj), (0, jj - 1)], [(1, jj - 1)], False)
+                else:
+                    v = upd([(ni - 2, jj), (ji, jj - 1)], [(ni - 2, jj - 1)], False)
+            else:
+                if 1 <= ji <= ni - 2:
+                    v = upd([(ji + 1, jj), (ji, jj + 1), (ji - 1, jj)], [(ji + 1, jj + 1), (ji - 1, jj + 1)], False)
+                elif per:
+                    c = 0 if ji == 0 else 1
+                    jim, jip = vim[c], vip[c]
+                    v = upd([(jip, jj), (ji, jj + 1), (jim, jj)], [(jip, jj + 1), (jim, jj + 1)], False)
+                elif ji == 0:
+                    v = upd([(1, jj), (0, jj + 1)], [(1, jj + 1)], False)
+                else:
+                    v = upd([(ji, jj + 1), (ni - 2, jj)], [(ni - 2, jj + 1)], False)
+            X[ji, jj] = v
+        maskv = maskv + mc
+        X = np.minimum(np.maximum(X, zmin), zmax)
+    if nsmooth > 0:
+        X = smoother(k_ew, X, nsmooth, msk=(1 - mask).astype(np.int32))
+    if abs(F32(zval_land)) > F32(1.0e-12):
+        X[maskv == 0] = F32(zval_land)
+    return X, nsw
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FILL_EXTRA_BANDS in array syntax (src/mod_manip.f90:69-305), iorca = 0 only; arrays (ni, nj)
+def _extra_2_east(x1, x2, x3, x4, x5, y1, y2, y3):
+    A, B, C, D = x2 - x1, x3 - x2, x4 - x3, x5 - x4
+    ALF, BET = y2 - y1, y3 - y2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        y4 = C * (2 * BET / B - ALF / A) + y3
+        y5 = y4 + y4 * D / C + BET * D / B - ALF * D / A - y3 * D / C
+    deg = (A == 0.0) | (B == 0.0) | (C == 0.0)
+    return np.where(deg, y3, y4), np.where(deg, y3, y5)
+
+
+def fill_extra_bands(k_ew, XX, YY, XF):
+    nx, ny = XX.shape
+    nxp4, nyp4 = nx + 4, ny + 4
+    XP4 = np.zeros((nxp4, nyp4)); YP4 = np.zeros((nxp4, nyp4)); FP4 = np.zeros((nxp4, nyp4))
+    C = (slice(2, nxp4 - 2), slice(2, nyp4 - 2))
+    XP4[C], YP4[C], FP4[C] = XX, YY, XF
+    R = slice(2, nyp4 - 2)
+    if k_ew > -1:
+        XP4[0, R] = XX[nx - 2 - k_ew, :] - 360.0
+        XP4[1, R] = XX[nx - 1 - k_ew, :] - 360.0
+        XP4[nxp4 - 1, R] = XX[1 + k_ew, :] + 360.0
+        XP4[nxp4 - 2, R] = XX[k_ew, :] + 360.0
+    else:
+        XP4[1, R] = XX[1, :] - (XX[2, :] - XX[0, :])
+        XP4[0, R] = XX[0, :] - (XX[2, :] - XX[0, :])
+        XP4[nxp4 - 2, R] = XX[nx - 2, :] + XX[nx - 1, :] - XX[nx - 3, :]
+        XP4[nxp4 - 1, R] = XX[nx - 1, :] + XX[nx - 1, :] - XX[nx - 3, :]
+    XP4[:, 1] = XP4[:, 3] - (XP4[:, 4] - XP4[:, 2])
+    XP4[:, 0] = XP4[:, 2] - (XP4[:, 4] - XP4[:, 2])
+    XP4[:, nyp4 - 2] = XP4[:, nyp4 - 4] + XP4[:, nyp4 - 3] - XP4[:, nyp4 - 5]
+    XP4[:, nyp4 - 1] = XP4[:, nyp4 - 3] + XP4[:, nyp4 - 3] - XP4[:, nyp4 - 5]
+    Cc = slice(2, nxp4 - 2)
+    YP4[Cc, nyp4 - 2] = YY[:, ny - 2] + YY[:, ny - 1] - YY[:, ny - 3]
+    YP4[Cc, nyp4 - 1] = YY[:, ny - 1] + YY[:, ny - 1] - YY[:, ny - 3]
+    YP4[Cc, 1] = YY[:, 1] - (YY[:, 2] - YY[:, 0])
+    YP4[Cc, 0] = YY[:, 0] - (YY[:, 2] - YY[:, 0])
+    if k_ew > -1:
+        YP4[0, :] = YP4[nx - 2 - k_ew + 2, :]
+        YP4[1, :] = YP4[nx - 1 - k_ew + 2, :]
+        YP4[nxp4 - 1, :] = YP4[1 + k_ew + 2, :]
+        YP4[nxp4 - 2, :] = YP4[k_ew + 2, :]
+    else:
+        YP4[1, :] = YP4[3, :] - (YP4[4, :] - YP4[2, :])
+        YP4[0, :] = YP4[2, :] - (YP4[4, :] - YP4[2, :])
+        YP4[nxp4 - 2, :] = YP4[nxp4 - 4, :] + YP4[nxp4 - 3, :] - YP4[nxp4 - 5, :]
+        YP4[nxp4 - 1, :] = YP4[nxp4 - 3, :] + YP4[nxp4 - 3, :] - YP4[nxp4 - 5, :]
+    if k_ew > -1:
+        FP4[0, R] = XF[nx - 2 - k_ew, :]
+        FP4[1, R] = XF[nx - 1 - k_ew, :]
+        FP4[nxp4 - 1, R] = XF[1 + k_ew, :]
+        FP4[nxp4 - 2, R] = XF[k_ew, :]
+    else:
+        y4, y5 = _extra_2_east(XP4[nxp4 - 5, R], XP4[nxp4 - 4, R], XP4[nxp4 - 3, R], XP4[nxp4 - 2, R], XP4[nxp4 - 1, R],
+                               FP4[nxp4 - 5, R], FP4[nxp4 - 4, R], FP4[nxp4 - 3, R])
+        FP4[nxp4 - 2, R], FP4[nxp4 - 1, R] = y4, y5
+        y2, y1 = _extra_2_east(XP4[4, R], XP4[3, R], XP4[2, R], XP4[1, R], XP4[0, R], FP4[4, R], FP4[3, R], FP4[2, R])
+        FP4[1, R], FP4[0, R] = y2, y1
+    y4, y5 = _extra_2_east(YP4[:, nyp4 - 5], YP4[:, nyp4 - 4], YP4[:, nyp4 - 3], YP4[:, nyp4 - 2], YP4[:, nyp4 - 1],
+                           FP4[:, nyp4 - 5], FP4[:, nyp4 - 4], FP4[:, nyp4 - 3])
+    FP4[:, nyp4 - 2], FP4[:, nyp4 - 1] = y4, y5
+    y2, y1 = _extra_2_east(YP4[:, 4], YP4[:, 3], YP4[:, 2], YP4[:, 1], YP4[:, 0], FP4[:, 4], FP4[:, 3], FP4[:, 2])
+    FP4[:, 1], FP4[:, 0] = y2, y1
+    return XP4, YP4, FP4

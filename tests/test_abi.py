@@ -1,0 +1,67 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol include/sosie_b200.h declares,
+and refuses to work (no CPU fallback) when there is no CUDA device."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import sosie_b200
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "sosie_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sosie_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(sosie_b200.lib_path()):
+        from sosie_b200 import build
+        build.build()
+    return ctypes.CDLL(sosie_b200.lib_path())
+
+
+def test_header_symbols_exported(lib):
+    names = _declared()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sosie_b200.h but not exported"
+    assert sorted(sosie_b200.EXPORTS) == names
+
+
+def test_version_string(lib):
+    lib.sosie_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.sosie_version()
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the refusal path cannot be exercised")
+    with pytest.raises(sosie_b200.SosieError):
+        sosie_b200.Sosie(0)
+
+
+def test_product_does_not_touch_the_oracle():
+    """the product package must not import / link the test oracle"""
+    for dp, _, files in os.walk(os.path.join(ROOT, "sosie_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".f90")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "from oracle" not in txt and "import oracle" not in txt and "orc_" not in txt, os.path.join(dp, f)
+    out = os.popen(f"ldd {sosie_b200.lib_path()}").read()
+    assert "oracle" not in out
+
+
+def test_sass_is_sm100a():
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("no cuobjdump")
+    out = subprocess.run([cuobjdump, "-lelf", sosie_b200.lib_path()], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

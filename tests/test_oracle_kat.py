@@ -1,0 +1,259 @@
+"""Known-answer / property tests of the CPU oracle and cross-checks against the independent numpy transliteration
+(tests/pyref.py).  The reference has no tests of this path, so these are the pins."""
+import math
+
+import numpy as np
+import pytest
+
+from sosie_b200 import grids as G
+from tests import pyref as P
+
+
+@pytest.fixture(autouse=True)
+def _glibc(orc):
+    orc.set_libm(orc.GLIBC)
+    yield
+    orc.set_libm(orc.PMATH)
+
+
+def test_literal_kinds(orc):
+    # Appendix A, Q1: REAL(4) literals widened to REAL(8)
+    assert orc.earth_radius() == 6367.44482421875
+    assert P.ZR == 6367.44482421875
+    assert float(np.float32(0.1)) == 0.10000000149011612 and float(np.float32(1e-9)) == 9.999999717180685e-10
+    assert float(np.float32(0.51)) == 0.5099999904632568 and float(np.sqrt(np.float32(2.0))) == 1.4142135381698608
+
+
+def test_heading_and_distance_kat(orc):
+    assert orc.heading(10, 11, 20, 20) == 90.0          # due east
+    assert orc.heading(10, 10, 20, 21) == 0.0           # due north
+    assert orc.heading(10, 10, 20, 19) == 180.0
+    assert orc.heading(10, 9, 20, 20) == 270.0
+    assert orc.heading(359.5, 0.5, 0, 0) == 90.0        # across Greenwich
+    assert orc.distance(10, 10, 20, 20) == 0.0          # zpds >= 1 branch
+    d = orc.distance(0, 90, 0, 0)
+    assert abs(d - orc.earth_radius() * math.pi / 2) < 1e-9
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        a = rng.uniform(0, 360, 2); b = rng.uniform(-89, 89, 2)
+        assert orc.distance(a[0], a[1], b[0], b[1]) == P.distance(a[0], a[1], b[0], b[1])
+        assert orc.heading(a[0], a[1], b[0], b[1]) == P.heading(a[0], a[1], b[0], b[1])
+
+
+def test_l_inpoly_nudge_and_frames(orc):
+    sq = ([10, 11, 11, 10], [20, 20, 21, 21])           # integer vertices: +0.001 nudge (Q9)
+    assert orc.l_inpoly(*sq, 10.5, 20.5)
+    assert not orc.l_inpoly(*sq, 10.5, 20.0005)         # inside the nudged strip -> rejected
+    assert not orc.l_inpoly(*sq, 12.0, 20.5)
+    hs = ([10.5, 11.5, 11.5, 10.5], [20.5, 20.5, 21.5, 21.5])   # half-integer vertices: clean
+    assert orc.l_inpoly(*hs, 10.6, 20.5004)
+    gw = ([359.5, 0.5, 0.5, 359.5], [10.5, 10.5, 11.5, 11.5])   # spans Greenwich -> -180..180 frame
+    assert orc.l_inpoly(*gw, 0.2, 11.0) and orc.l_inpoly(*gw, 359.8, 11.0) and not orc.l_inpoly(*gw, 1.0, 11.0)
+    rng = np.random.default_rng(1)
+    for _ in range(3000):
+        x0, y0 = rng.uniform(1, 358), rng.uniform(-80, 80)
+        if rng.random() < 0.3:
+            x0, y0 = float(int(x0)), float(int(y0))
+        dx, dy = rng.uniform(0.05, 1.5, 2)
+        sk = rng.uniform(-0.3, 0.3, 4)
+        vx = [x0, x0 + dx, x0 + dx + sk[0], x0 + sk[1]]
+        vy = [y0, y0 + sk[2], y0 + dy, y0 + dy + sk[3]]
+        px, py = x0 + rng.uniform(-0.2, 1.2) * dx, y0 + rng.uniform(-0.2, 1.2) * dy
+        if min(vx) < 0 or px < 0:
+            continue
+        assert orc.l_inpoly(vx, vy, px, py) == P.l_inpoly(vx, vy, px, py), (vx, vy, px, py)
+
+
+def test_local_coord_rectangle_and_transliteration(orc):
+    # rectangular cell: alpha, beta are the exact fractions to ~1e-12 (A.1), three iterations
+    lam = [10.3, 10.0, 11.0, 11.0, 10.0]; phi = [20.6, 20.0, 20.0, 21.0, 21.0]
+    a, b, ipb = orc.local_coord(lam, phi)
+    assert ipb == 0 and abs(a - 0.3) < 1e-12 and abs(b - 0.6) < 1e-12
+    a, b, ipb = orc.local_coord([10.3, 10, 11, 11, 10], [20.0, 20, 20, 20, 20])     # all latitudes equal -> 12
+    assert (a, b, ipb) == (0.5, 0.5, 12)
+    rng = np.random.default_rng(2)
+    for _ in range(500):
+        x0, y0 = rng.uniform(0.5, 359), rng.uniform(-80, 80)
+        sk = rng.uniform(-0.2, 0.2, 6)
+        lam = [x0 + rng.uniform(0, 1), x0, x0 + 1 + sk[0], x0 + 1 + sk[1], x0 + sk[2]]
+        phi = [y0 + rng.uniform(0, 1), y0, y0 + sk[3], y0 + 1 + sk[4], y0 + 1 + sk[5]]
+        assert orc.local_coord(lam, phi) == P.local_coord(lam, phi)
+
+
+def test_interp_bl_error_codes_and_weights(orc):
+    Z = np.arange(30, dtype=np.float32).reshape(5, 6)          # (nj=5, ni=6)
+    assert orc.interp_bl(-1, 3, 3, 1, 0.0, 0.0, Z) == Z[2, 2]
+    assert orc.interp_bl(-1, 3, 3, 1, 1.0, 1.0, Z) == Z[3, 3]
+    assert orc.interp_bl(-1, 1, 3, 3, 0.5, 0.5, Z) == -9997.0  # i-1 = 0, not periodic
+    assert orc.interp_bl(-1, 3, 1, 2, 0.5, 0.5, Z) == -9996.0  # j-1 = 0
+    assert orc.interp_bl(-1, 3, 5, 1, 0.5, 0.5, Z) == -9995.0  # j+1 > nj
+    assert orc.interp_bl(-1, 6, 3, 1, 0.5, 0.5, Z) == -9994.0  # i+1 > ni
+    assert orc.interp_bl(2, 1, 3, 3, 0.5, 0.5, Z) != -9997.0   # periodic wrap i-1 -> ni-k_ew
+    # affine fields are reproduced exactly inside a cell (bilinear property)
+    f = lambda i, j: 2.0 * i - 3.0 * j + 1.0   # noqa: E731
+    Zf = np.array([[f(i, j) for i in range(1, 7)] for j in range(1, 6)], np.float32)
+    assert abs(orc.interp_bl(-1, 2, 2, 1, 0.25, 0.75, Zf) - f(2.25, 2.75)) < 1e-5
+
+
+def test_easy_search_and_mapping_vs_transliteration(orc):
+    """EASY search + MAPPING_BL body: C++ oracle vs the numpy/Python transliteration, bit for bit."""
+    lon, lat = G.regular_latlon(90, 45)
+    rng = np.random.default_rng(3)
+    nt = 300
+    tx = rng.uniform(0.0, 359.9, nt); ty = rng.uniform(-84, 84, nt)
+    tx[:40] = lon[rng.integers(0, 90, 40)]            # exact alignments / ties
+    ty[40:80] = lat[rng.integers(3, 42, 40)]
+    Xt, Yt = tx.reshape(3, 100), ty.reshape(3, 100)
+    Xs, Ys = G.expand_2d(lon, lat)
+    m = orc.mapping_bl(0, Xs, Ys, Xt, Yt)
+    met, ab, ipb = m["metrics"], m["alphabeta"], m["ipb"]
+    ndiff = 0
+    for j in range(3):
+        for i in range(100):
+            iP, jP = P.find_nearest_easy_point(Xt[j, i], Yt[j, i], lon, lat)
+            assert (met[0, j, i], met[1, j, i]) == (iP, jP)
+            r = P.mapping_point_regular(0, lon, lat, Xt[j, i], Yt[j, i], iP, jP)
+            if r is None:
+                assert met[2, j, i] == 1 and ipb[j, i] == 1 and ab[0, j, i] == 0.0
+                continue
+            iq, a, b, ip = r
+            # whole-array fix-ups (src/mod_bilin_2d.f90:654-679)
+            eps = float(np.float32(1e-9))
+            if a < 0 and a > -eps: a = 0.0
+            if b < 0 and b > -eps: b = 0.0
+            if a < 0: a, ip = 0.5, 4
+            if a > 1: a, ip = 0.5, 5
+            if b < 0: b, ip = 0.5, 6
+            if b > 1: b, ip = 0.5, 7
+            if iq < 1: iq, ip = 1, 1
+            assert (met[2, j, i], ab[0, j, i], ab[1, j, i], ipb[j, i]) == (iq, a, b, ip), (i, j)
+            ndiff += 1
+    assert ndiff > 250
+
+
+def test_mapping_invariants_all_configs(orc):
+    for name, scale in (("A", 0.2), ("B", 0.2), ("C", 0.25), ("D", 0.05), ("E", 0.01)):
+        cfg = G.config(name, scale)
+        Xs, Ys = G.src_2d(cfg); Z1 = G.field_slabs(Xs, Ys, 1)
+        Z2, m = orc.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"],
+                             l_reg_src=cfg["l_reg_src"], i_orca_trg=cfg["i_orca_trg"])
+        met, ab, ipb = m["metrics"], m["alphabeta"], m["ipb"]
+        found = met[0] >= 1
+        assert ((met[0][found] <= cfg["nxs"]) & (met[1][found] >= 1)).all()
+        assert set(np.unique(met[2])) <= {1, 2, 3, 4}
+        assert (ab >= 0).all() and (ab <= 1).all()                 # after the fix-ups
+        assert set(np.unique(ipb)) <= {-2, -1, 0, 1, 4, 5, 6, 7, 11, 12}
+        ok = (ipb == 0)
+        assert ok.mean() > 0.6
+        # a well-mapped target is interpolated within the range of the source field
+        assert Z2[0][ok].min() >= Z1.min() - 1e-3 and Z2[0][ok].max() <= Z1.max() + 1e-3
+
+
+def test_bdrown_vs_transliteration_and_invariants(orc):
+    rng = np.random.default_rng(4)
+    for ni, nj, kew in ((24, 17, -1), (26, 15, 2), (20, 20, 0)):
+        X = (rng.random((nj, ni)) * 30).astype(np.float32)
+        mask = (rng.random((nj, ni)) > 0.45).astype(np.int32)
+        mask[3:9, 5:13] = 0                       # a continent wider than nb_inc
+        mask[:, 0] = rng.integers(0, 2, nj); mask[0, :] = rng.integers(0, 2, ni); mask[-1, :] = rng.integers(0, 2, ni)
+        if kew > 0:
+            mask[:, -kew:] = mask[:, :kew]; X[:, -kew:] = X[:, :kew]
+        X[mask == 0] = -9999.0
+        for ninc, nsm, pval, lo, hi in ((3, 2, -5.0, -1e3, 1e3), (50, 4, 0.0, 5.0, 25.0)):
+            Xo, nsw = orc.bdrown(kew, X, mask, ninc, nsm, lo, hi, pval)
+            Xp, nswp = P.bdrown(kew, P.to_f(X), P.to_f(mask), ninc, nsm, lo, hi, pval)
+            assert nsw[0] == nswp
+            assert np.array_equal(Xo, P.from_f(Xp)), (ni, nj, kew, ninc)
+            sea = mask == 1
+            if nsw[0] > 0:
+                assert np.array_equal(Xo[sea], np.clip(X[sea], lo, hi))     # mask==1 untouched (mod_bdrown.f90:22-24)
+    # no land at all: nothing happens, not even the clamp (the loop exits before :414)
+    X = (rng.random((9, 11)) * 30).astype(np.float32)
+    Xo, nsw = orc.bdrown(-1, X, np.ones((9, 11), np.int32), 10, 0, 5.0, 10.0, 0.0)
+    assert nsw[0] == 0 and np.array_equal(Xo, X)
+
+
+def test_smoother_vs_transliteration(orc):
+    rng = np.random.default_rng(5)
+    for ni, nj, kew in ((19, 14, -1), (22, 13, 2)):
+        X = (rng.random((nj, ni)) * 10).astype(np.float32)
+        msk = (rng.random((nj, ni)) > 0.4).astype(np.int32)
+        a = orc.smoother(kew, X, 3)
+        assert np.array_equal(a, P.from_f(P.smoother(kew, P.to_f(X), 3)))
+        a = orc.smoother(kew, X, 3, msk=msk)
+        assert np.array_equal(a, P.from_f(P.smoother(kew, P.to_f(X), 3, msk=P.to_f(msk))))
+        assert np.array_equal(a[msk == 0], X[msk == 0])             # msk==0 preserved
+        a = orc.smoother(kew, X, 3, msk=msk, l_exclude_mask_points=True)
+        assert np.array_equal(a, P.from_f(P.smoother(kew, P.to_f(X), 3, msk=P.to_f(msk), l_emp=True)))
+    c = np.full((12, 15), 7.25, np.float32)                         # constants are preserved to rounding
+    assert np.allclose(orc.smoother(-1, c, 5), c, rtol=1e-6)
+    assert np.array_equal(orc.smoother(-1, c, 5)[0], c[0])          # rows 1 and nj never touched
+
+
+def test_drown_gaussian_invariants(orc):
+    rng = np.random.default_rng(6)
+    X = (rng.random((20, 30)) * 10 + 1).astype(np.float32)
+    mask = (rng.random((20, 30)) > 0.3).astype(np.int8)
+    Xo, nsw = orc.drown(-1, X, mask, 30)
+    assert np.array_equal(Xo[mask == 1], X[mask == 1])
+    assert nsw[0] >= 1 and np.isfinite(Xo).all() and Xo[mask == 0].min() >= X[mask == 1].min() - 1e-4
+    assert Xo[mask == 0].max() <= X[mask == 1].max() + 1e-4       # weighted means of sea values
+
+
+def test_fill_extra_bands_vs_transliteration(orc):
+    rng = np.random.default_rng(7)
+    lon, lat = G.regular_latlon(30, 16)
+    XX, YY = G.expand_2d(lon, lat)
+    F = rng.random(XX.shape)
+    for kew in (0, 2, -1):
+        a = orc.fill_extra_bands(kew, XX, YY, F)
+        b = P.fill_extra_bands(kew, P.to_f(XX), P.to_f(YY), P.to_f(F))
+        for u, v in zip(a, b):
+            assert np.array_equal(u, P.from_f(v)), kew
+
+
+def test_akima_reproduces_linear_and_quadratic(orc):
+    lon = 10.0 + 0.5 * np.arange(40); lat = -10.0 + 0.5 * np.arange(30)
+    X, Y = G.expand_2d(lon, lat)
+    tl = 12.03 + 0.37 * np.arange(40); tt = -8.02 + 0.29 * np.arange(40)
+    TX, TY = G.expand_2d(tl, tt)
+    for f, tol in ((lambda x, y: 2 * x - 3 * y + 1, 2e-5), (lambda x, y: 0.01 * x * x - 0.02 * y * y + 0.03 * x * y, 2e-5)):
+        Z2, _ = orc.akima_2d(-1, lon, lat, f(X, Y).astype(np.float32), tl, tt)
+        ref = f(TX, TY)
+        assert np.max(np.abs(Z2[0] - ref) / np.maximum(1.0, np.abs(ref))) < tol
+    # outside the (frame-extended) source domain -> 0.0 (src/mod_akima_2d.f90:222-224)
+    Z2, _ = orc.akima_2d(-1, lon, lat, np.ones(X.shape, np.float32), np.array([0.0, 200.0]), np.array([50.0, 60.0]))
+    assert (Z2 == 0).all()
+
+
+def test_ext_north_to_90_regg(orc):
+    lon, lat = G.regular_latlon(24, 22)
+    X, Y = G.expand_2d(lon, lat)
+    F = np.random.default_rng(8).random(X.shape).astype(np.float32)
+    XP, YP, FP = orc.ext_north_to_90_regg(X, Y, F)
+    assert YP.shape == (24, 24) and (YP[22] == 90.0).all() and np.allclose(YP[23], 90.0 + (lat[-1] - lat[-2]))
+    im = (np.arange(24) + 12) % 24                       # the column across the pole
+    assert np.array_equal(FP[22], np.float32(0.5) * (F[21] + F[21][im]))
+    assert np.array_equal(FP[23], F[20][im])
+
+
+def test_rotation_roundtrip(orc):
+    rng = np.random.default_rng(9)
+    U = rng.standard_normal((2, 500)).astype(np.float32); V = rng.standard_normal((2, 500)).astype(np.float32)
+    ang = rng.random(500) * 2 * np.pi
+    uo, vo = orc.rotate_uv(U, V, np.cos(ang), np.sin(ang))
+    ub, vb = orc.rotate_uv(uo, vo, np.cos(ang), np.sin(ang), inverse=True)
+    assert np.allclose(ub, U, atol=2e-6) and np.allclose(vb, V, atol=2e-6)
+    assert np.allclose(uo ** 2 + vo ** 2, U ** 2 + V ** 2, rtol=1e-5)
+
+
+def test_faithful_fill_equals_elided(orc):
+    """the per-target Xdist = 1.E12 whole-array store (src/mod_manip.f90:1038,1368) is dead: results are identical"""
+    for name, scale in (("D", 0.04), ("B", 0.15)):
+        cfg = G.config(name, scale)
+        Xs, Ys = G.src_2d(cfg); Z1 = G.field_slabs(Xs, Ys, 1)
+        a, ma = orc.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"],
+                             l_reg_src=cfg["l_reg_src"], elide_fill=False)
+        b, mb = orc.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"],
+                             l_reg_src=cfg["l_reg_src"], elide_fill=True, nthreads=2)
+        assert np.array_equal(a, b) and all(np.array_equal(ma[k], mb[k]) for k in ("metrics", "alphabeta", "ipb"))
