@@ -1,0 +1,125 @@
+MODULE MOD_BILIN_2D
+   !! Drop-in replacement of SOSIE's src/mod_bilin_2d.f90: same module name, same PUBLIC procedures and
+   !! argument lists (BILIN_2D :44, MAPPING_BL :366, INTERP_BL :275), bodies are calls into libsosie_b200.
+   !! sosie.f90, mod_interp, mod_conf, mod_init, mod_grids and io_ezcdf are untouched.
+   !! NOT COMPILED IN THIS ENVIRONMENT (no Fortran compiler); shipped as source.
+   USE, INTRINSIC :: ISO_C_BINDING
+   USE mod_conf          !: l_reg_src, i_orca_trg, l_first_call_interp_routine, rmissval  (implicit inputs, SURVEY 8b)
+   USE io_ezcdf, ONLY : RD_MAPPING_AB, P2D_MAPPING_AB, TEST_XYZ
+   USE sosie_gpu_c
+   IMPLICIT NONE
+   PRIVATE
+   PUBLIC :: BILIN_2D, MAPPING_BL, INTERP_BL
+
+CONTAINS
+
+   SUBROUTINE BILIN_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2, cnpat,  mask_domain_trg)
+      INTEGER,                 INTENT(in)  :: k_ew_per
+      REAL(8), DIMENSION(:,:), INTENT(in)  :: X10, Y10
+      REAL(4), DIMENSION(:,:), INTENT(in)  :: Z1
+      REAL(8), DIMENSION(:,:), INTENT(in)  :: X20, Y20
+      REAL(4), DIMENSION(:,:), INTENT(out) :: Z2
+      CHARACTER(len=*),        INTENT(in)  :: cnpat
+      INTEGER, OPTIONAL, DIMENSION(:,:), INTENT(in), TARGET :: mask_domain_trg
+      !!
+      INTEGER :: nx1, ny1, nx2, ny2, is1d, it1d
+      LOGICAL :: lefw
+      CHARACTER(len=400) :: cf_wght
+      REAL(8),    DIMENSION(:,:),   ALLOCATABLE :: xs, ys, xt, yt     ! contiguous copies (assumed-shape actuals may be sections)
+      REAL(4),    DIMENSION(:,:),   ALLOCATABLE :: z1c, z2c
+      INTEGER(4), DIMENSION(:,:),   ALLOCATABLE, TARGET :: mskc
+      INTEGER(4), DIMENSION(:,:,:), ALLOCATABLE :: imetrics
+      REAL(8),    DIMENSION(:,:,:), ALLOCATABLE :: rab
+      INTEGER(2), DIMENSION(:,:),   ALLOCATABLE :: ipb
+      REAL(4),    DIMENSION(:,:),   ALLOCATABLE :: d2np
+      TYPE(C_PTR) :: pmask
+      !!
+      CALL GPU_INIT()
+      nx1 = SIZE(Z1,1) ; ny1 = SIZE(Z1,2) ; nx2 = SIZE(Z2,1) ; ny2 = SIZE(Z2,2)
+      is1d = 0 ; IF ( TEST_XYZ(X10,Y10,Z1) == '1d' ) is1d = 1
+      it1d = 0 ; IF ( TEST_XYZ(X20,Y20,Z2) == '1d' ) it1d = 1
+      ALLOCATE ( z1c(nx1,ny1), z2c(nx2,ny2) ) ; z1c = Z1
+
+      IF ( l_first_call_interp_routine ) THEN
+         ALLOCATE ( xs(SIZE(X10,1),SIZE(X10,2)), ys(SIZE(Y10,1),SIZE(Y10,2)), xt(SIZE(X20,1),SIZE(X20,2)), yt(SIZE(Y20,1),SIZE(Y20,2)) )
+         xs = X10 ; ys = Y10 ; xt = X20 ; yt = Y20
+         pmask = C_NULL_PTR
+         IF ( PRESENT(mask_domain_trg) ) THEN
+            ALLOCATE ( mskc(nx2,ny2) ) ; mskc = mask_domain_trg ; pmask = C_LOC(mskc)
+         END IF
+         CALL GPU_CHECK( sosie_bilin_set_grids(gpu_ctx, k_ew_per, nx1, ny1, xs, ys, is1d, MERGE(1,0,l_reg_src), &
+            &                                  nx2, ny2, xt, yt, it1d, pmask, i_orca_trg), 'BILIN_2D/set_grids' )
+         ALLOCATE ( imetrics(nx2,ny2,3), rab(nx2,ny2,2), ipb(nx2,ny2), d2np(nx2,ny2) )
+         WRITE(cf_wght,'("sosie_mapping_",a,".nc")') TRIM(cnpat)
+         INQUIRE(FILE=cf_wght, EXIST=lefw )
+         IF ( lefw ) THEN
+            !! same cache file as stock SOSIE: a CPU-built mapping is reused as is
+            CALL RD_MAPPING_AB(cf_wght, imetrics, rab, ipb)
+            CALL GPU_CHECK( sosie_bilin_load_map(gpu_ctx, nx2, ny2, imetrics, rab, ipb), 'BILIN_2D/load_map' )
+         ELSE
+            CALL GPU_CHECK( sosie_bilin_map(gpu_ctx), 'MAPPING_BL' )
+            CALL GPU_CHECK( sosie_bilin_get_map(gpu_ctx, imetrics, rab, ipb, d2np, C_NULL_PTR), 'BILIN_2D/get_map' )
+            IF ( it1d == 1 ) THEN
+               CALL P2D_MAPPING_AB(cf_wght, SPREAD(xt(:,1),2,ny2), SPREAD(yt(:,1),1,nx2), imetrics, rab, REAL(rmissval,8), ipb, d2np=d2np)
+            ELSE
+               CALL P2D_MAPPING_AB(cf_wght, xt, yt, imetrics, rab, REAL(rmissval,8), ipb, d2np=d2np)
+            END IF
+         END IF
+         DEALLOCATE ( imetrics, rab, ipb, d2np, xs, ys, xt, yt )
+      END IF
+
+      CALL GPU_CHECK( sosie_bilin_apply(gpu_ctx, 1, z1c, z2c, MERGE(1,0,l_first_call_interp_routine)), 'BILIN_2D/apply' )
+      Z2 = z2c
+      DEALLOCATE ( z1c, z2c )
+      l_first_call_interp_routine = .FALSE.
+   END SUBROUTINE BILIN_2D
+
+
+   SUBROUTINE MAPPING_BL(k_ew_per, X1, Y1, lon_trg, lat_trg, cf_w,  mask_domain_trg)
+      !! stand-alone use (interp_to_ground_track.f90:627, interp_to_hydro_section.f90:464): X1,Y1 are full 2-D arrays
+      INTEGER,                 INTENT(in) :: k_ew_per
+      REAL(8), DIMENSION(:,:), INTENT(in) :: X1, Y1
+      REAL(8), DIMENSION(:,:), INTENT(in) :: lon_trg, lat_trg
+      CHARACTER(len=*)       , INTENT(in) :: cf_w
+      INTEGER, OPTIONAL ,DIMENSION(:,:), INTENT(in) :: mask_domain_trg
+      INTEGER :: nxi, nyi, nxo, nyo
+      REAL(8),    DIMENSION(:,:),   ALLOCATABLE :: xs, ys, xt, yt
+      INTEGER(4), DIMENSION(:,:),   ALLOCATABLE, TARGET :: mskc
+      INTEGER(4), DIMENSION(:,:,:), ALLOCATABLE :: imetrics
+      REAL(8),    DIMENSION(:,:,:), ALLOCATABLE :: rab
+      INTEGER(2), DIMENSION(:,:),   ALLOCATABLE :: ipb
+      REAL(4),    DIMENSION(:,:),   ALLOCATABLE :: d2np
+      TYPE(C_PTR) :: pmask
+      CALL GPU_INIT()
+      nxi = SIZE(X1,1) ; nyi = SIZE(X1,2) ; nxo = SIZE(lon_trg,1) ; nyo = SIZE(lon_trg,2)
+      ALLOCATE ( xs(nxi,nyi), ys(nxi,nyi), xt(nxo,nyo), yt(nxo,nyo), imetrics(nxo,nyo,3), rab(nxo,nyo,2), ipb(nxo,nyo), d2np(nxo,nyo) )
+      xs = X1 ; ys = Y1 ; xt = lon_trg ; yt = lat_trg
+      pmask = C_NULL_PTR
+      IF ( PRESENT(mask_domain_trg) ) THEN
+         ALLOCATE ( mskc(nxo,nyo) ) ; mskc = mask_domain_trg ; pmask = C_LOC(mskc)
+      END IF
+      !! l_reg_src = 0: the caller already extended the arrays (or does not want the pole rows)
+      CALL GPU_CHECK( sosie_bilin_set_grids(gpu_ctx, k_ew_per, nxi, nyi, xs, ys, 0, 0, nxo, nyo, xt, yt, 0, pmask, 0), 'MAPPING_BL/set_grids' )
+      CALL GPU_CHECK( sosie_bilin_map(gpu_ctx), 'MAPPING_BL' )
+      CALL GPU_CHECK( sosie_bilin_get_map(gpu_ctx, imetrics, rab, ipb, d2np, C_NULL_PTR), 'MAPPING_BL/get_map' )
+      CALL P2D_MAPPING_AB(cf_w, lon_trg, lat_trg, imetrics, rab, REAL(rmissval,8), ipb, d2np=d2np)
+      DEALLOCATE ( xs, ys, xt, yt, imetrics, rab, ipb, d2np )
+   END SUBROUTINE MAPPING_BL
+
+
+   FUNCTION INTERP_BL(k_ew_per, jiP, jjP, iqd, xa, xb, Z_in)
+      INTEGER,                 INTENT(in) :: k_ew_per
+      INTEGER,                 INTENT(in) :: jiP, jjP, iqd
+      REAL(8),                 INTENT(in) :: xa, xb
+      REAL(4), DIMENSION(:,:), INTENT(in) :: Z_in
+      REAL(4) :: INTERP_BL
+      REAL(4), DIMENSION(:,:), ALLOCATABLE :: zc
+      REAL(4) :: zout(1)
+      CALL GPU_INIT()
+      ALLOCATE ( zc(SIZE(Z_in,1),SIZE(Z_in,2)) ) ; zc = Z_in
+      CALL GPU_CHECK( sosie_interp_bl(gpu_ctx, k_ew_per, SIZE(Z_in,1), SIZE(Z_in,2), zc, 1, (/jiP/), (/jjP/), (/iqd/), (/xa/), (/xb/), zout), 'INTERP_BL' )
+      INTERP_BL = zout(1)
+      DEALLOCATE ( zc )
+   END FUNCTION INTERP_BL
+
+END MODULE MOD_BILIN_2D

@@ -1,0 +1,142 @@
+MODULE SOSIE_GPU_C
+   !! ISO_C_BINDING view of include/sosie_b200.h -- the only thing the drop-in modules below need.
+   !! NOT COMPILED IN THIS ENVIRONMENT (no Fortran compiler in the image); the C ABI itself is exercised
+   !! from Python (ctypes) by tests/.  Link:  ... -L<repo>/sosie_b200/_build -lsosie_b200 -lcudart
+   USE, INTRINSIC :: ISO_C_BINDING
+   IMPLICIT NONE
+   TYPE(C_PTR), SAVE :: gpu_ctx = C_NULL_PTR   !: one context per process (the reference is single-threaded)
+
+   INTERFACE
+      INTEGER(C_INT) FUNCTION sosie_create(ctx, device) BIND(C, name='sosie_create')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), INTENT(out) :: ctx
+         INTEGER(C_INT), VALUE    :: device
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_destroy(ctx) BIND(C, name='sosie_destroy')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: ctx
+      END FUNCTION
+      TYPE(C_PTR) FUNCTION sosie_last_error(ctx) BIND(C, name='sosie_last_error')
+         IMPORT :: C_PTR
+         TYPE(C_PTR), VALUE :: ctx
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_set_grids(ctx, k_ew, nx1, ny1, X10, Y10, src_1d, l_reg_src, &
+         &                                          nx2, ny2, X20, Y20, trg_1d, mask, i_orca_trg) BIND(C, name='sosie_bilin_set_grids')
+         IMPORT :: C_PTR, C_INT, C_DOUBLE
+         TYPE(C_PTR), VALUE    :: ctx, mask            ! mask: C_NULL_PTR or c_loc(INTEGER(4) array)
+         INTEGER(C_INT), VALUE :: k_ew, nx1, ny1, src_1d, l_reg_src, nx2, ny2, trg_1d, i_orca_trg
+         REAL(C_DOUBLE), INTENT(in) :: X10(*), Y10(*), X20(*), Y20(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_map(ctx) BIND(C, name='sosie_bilin_map')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: ctx
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_get_map(ctx, metrics, alphabeta, id_problem, dist_np, mask_out) BIND(C, name='sosie_bilin_get_map')
+         IMPORT :: C_PTR, C_INT, C_DOUBLE, C_SHORT, C_FLOAT
+         TYPE(C_PTR), VALUE :: ctx, mask_out
+         INTEGER(C_INT)   :: metrics(*)
+         REAL(C_DOUBLE)   :: alphabeta(*)
+         INTEGER(C_SHORT) :: id_problem(*)
+         REAL(C_FLOAT)    :: dist_np(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_load_map(ctx, nx2, ny2, metrics, alphabeta, id_problem) BIND(C, name='sosie_bilin_load_map')
+         IMPORT :: C_PTR, C_INT, C_DOUBLE, C_SHORT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: nx2, ny2
+         INTEGER(C_INT), INTENT(in)   :: metrics(*)
+         REAL(C_DOUBLE), INTENT(in)   :: alphabeta(*)
+         INTEGER(C_SHORT), INTENT(in) :: id_problem(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_apply(ctx, nslab, Z1, Z2, first_call) BIND(C, name='sosie_bilin_apply')
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: nslab, first_call
+         REAL(C_FLOAT), INTENT(in)  :: Z1(*)
+         REAL(C_FLOAT), INTENT(out) :: Z2(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_interp_bl(ctx, k_ew, nxi, nyi, Z_in, n, jiP, jjP, iqd, xa, xb, zout) BIND(C, name='sosie_interp_bl')
+         IMPORT :: C_PTR, C_INT, C_FLOAT, C_DOUBLE
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: k_ew, nxi, nyi, n
+         REAL(C_FLOAT), INTENT(in)  :: Z_in(*)
+         INTEGER(C_INT), INTENT(in) :: jiP(*), jjP(*), iqd(*)
+         REAL(C_DOUBLE), INTENT(in) :: xa(*), xb(*)
+         REAL(C_FLOAT), INTENT(out) :: zout(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_akima_set_grids(ctx, k_ew, nx1, ny1, X10, Y10, src_1d, i_orca_src, &
+         &                                          nx2, ny2, X20, Y20, trg_1d) BIND(C, name='sosie_akima_set_grids')
+         IMPORT :: C_PTR, C_INT, C_DOUBLE
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: k_ew, nx1, ny1, src_1d, i_orca_src, nx2, ny2, trg_1d
+         REAL(C_DOUBLE), INTENT(in) :: X10(*), Y10(*), X20(*), Y20(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_akima_apply(ctx, nslab, Z1, Z2) BIND(C, name='sosie_akima_apply')
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: nslab
+         REAL(C_FLOAT), INTENT(in)  :: Z1(*)
+         REAL(C_FLOAT), INTENT(out) :: Z2(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bdrown(ctx, k_ew, ni, nj, nslab, X, mask, mask_per_slab, nb_inc, nb_smooth, &
+         &                                 pmin, pmax, pval_land, nsweeps) BIND(C, name='sosie_bdrown')
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx, nsweeps
+         INTEGER(C_INT), VALUE :: k_ew, ni, nj, nslab, mask_per_slab, nb_inc, nb_smooth
+         REAL(C_FLOAT)         :: X(*)
+         INTEGER(C_INT), INTENT(in) :: mask(*)
+         REAL(C_FLOAT), VALUE  :: pmin, pmax, pval_land
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_smoother(ctx, k_ew, ni, nj, nslab, X, nb_smooth, msk, l_emp) BIND(C, name='sosie_smoother')
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx, msk
+         INTEGER(C_INT), VALUE :: k_ew, ni, nj, nslab, nb_smooth, l_emp
+         REAL(C_FLOAT)         :: X(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_drown(ctx, k_ew, ni, nj, nslab, X, mask, nb_inc, nsweeps) BIND(C, name='sosie_drown')
+         IMPORT :: C_PTR, C_INT, C_FLOAT, C_SIGNED_CHAR
+         TYPE(C_PTR), VALUE    :: ctx, nsweeps
+         INTEGER(C_INT), VALUE :: k_ew, ni, nj, nslab, nb_inc
+         REAL(C_FLOAT)         :: X(*)
+         INTEGER(C_SIGNED_CHAR), INTENT(in) :: mask(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_rotate_uv(ctx, n, nslab, U, V, xcos, xsin, Uo, Vo, inverse) BIND(C, name='sosie_rotate_uv')
+         IMPORT :: C_PTR, C_INT, C_FLOAT, C_DOUBLE, C_INT64_T
+         TYPE(C_PTR), VALUE        :: ctx
+         INTEGER(C_INT64_T), VALUE :: n
+         INTEGER(C_INT), VALUE     :: nslab, inverse
+         REAL(C_FLOAT), INTENT(in)  :: U(*), V(*)
+         REAL(C_DOUBLE), INTENT(in) :: xcos(*), xsin(*)
+         REAL(C_FLOAT), INTENT(out) :: Uo(*), Vo(*)
+      END FUNCTION
+   END INTERFACE
+
+CONTAINS
+
+   SUBROUTINE GPU_INIT()
+      INTEGER(C_INT) :: ierr
+      IF ( .NOT. C_ASSOCIATED(gpu_ctx) ) THEN
+         ierr = sosie_create(gpu_ctx, 0_C_INT)
+         IF ( ierr /= 0 ) THEN
+            PRINT *, 'ERROR (sosie_gpu_c): no usable CUDA device -- this build has no CPU fallback'; STOP
+         END IF
+      END IF
+   END SUBROUTINE GPU_INIT
+
+   SUBROUTINE GPU_CHECK(ierr, cwhere)
+      !! the C ABI returns codes where the reference PRINTs and STOPs: keep that behaviour
+      INTEGER(C_INT),   INTENT(in) :: ierr
+      CHARACTER(len=*), INTENT(in) :: cwhere
+      CHARACTER(kind=C_CHAR), POINTER :: cmsg(:)
+      INTEGER :: k
+      IF ( ierr /= 0 ) THEN
+         CALL C_F_POINTER(sosie_last_error(gpu_ctx), cmsg, (/ 512 /))
+         k = 1
+         DO WHILE ( (k < 512) .AND. (cmsg(k) /= C_NULL_CHAR) )
+            k = k + 1
+         END DO
+         PRINT *, 'ERROR in ', TRIM(cwhere), ' (sosie_b200, code', ierr, '): ', cmsg(1:k-1)
+         STOP
+      END IF
+   END SUBROUTINE GPU_CHECK
+
+END MODULE SOSIE_GPU_C
