@@ -36,7 +36,7 @@ EXPORTS = [
     "sosie_version", "sosie_profile", "sosie_get_timing", "sosie_bilin_set_shard", "sosie_bilin_set_grids", "sosie_bilin_set_grids_dev", "sosie_bilin_map", "sosie_bilin_get_map",
     "sosie_bilin_load_map", "sosie_bilin_map_info", "sosie_bilin_apply", "sosie_bilin_apply_dev", "sosie_bilin_apply_ex_dev",
     "sosie_bilin_apply_uv_dev", "sosie_bilin_2d", "sosie_interp_bl", "sosie_akima_set_grids", "sosie_akima_apply",
-    "sosie_akima_apply_dev", "sosie_akima_get_ixy", "sosie_bdrown", "sosie_bdrown_dev", "sosie_smoother", "sosie_drown",
+    "sosie_akima_apply_dev", "sosie_akima_get_ixy", "sosie_bdrown", "sosie_bdrown_dev", "sosie_bdrown_force_general", "sosie_smoother", "sosie_drown",
     "sosie_rotate_uv", "sosie_rotate_uv_dev",
 ]
 
@@ -291,6 +291,10 @@ class Sosie:
         self._ck(self._lib.sosie_bdrown(self._h, int(k_ew), ni, nj, nslab, _p(X), _p(mask), int(per), int(nb_inc), int(nb_smooth),
                                         C.c_float(pmin), C.c_float(pmax), C.c_float(pval_land), _p(nsw)))
         return (X[0] if sq else X), nsw
+
+    def bdrown_force_general(self, on=True):
+        """test hook: use the multi-launch global-memory BDROWN path even for slabs that fit one SM's shared memory"""
+        self._ck(self._lib.sosie_bdrown_force_general(self._h, int(on)))
 
     def bdrown_dev(self, k_ew, ni, nj, nslab, dX, dmask, mask_per_slab, nb_inc, nb_smooth, pmin, pmax, pval_land, want_nsweeps=False):
         nsw = np.zeros(nslab, np.int32) if want_nsweeps else None

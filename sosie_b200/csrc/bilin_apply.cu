@@ -268,35 +268,49 @@ k_apply_staged(const int4* __restrict__ pidx, const float4* __restrict__ pw, siz
       o3 = (id.z / v.nx - box.y) * bw + (id.z % v.nx - box.x);
       o4 = (id.w / v.nx - box.y) * bw + (id.w % v.nx - box.x);
     }
-    int goff[BOX_PER_THREAD];
+    // per-thread running pointers: source cells this thread stages (advance by one slab per issue), output cell
+    const float* gsrc[BOX_PER_THREAD];
+    bool gok[BOX_PER_THREAD];
 #pragma unroll
     for (int m = 0; m < BOX_PER_THREAD; m++) {
       int e = threadIdx.x + 256 * m;
-      goff[m] = (e < nelem) ? (box.y + e / bw) * v.nx + box.x + e % bw : -1;
+      gok[m] = e < nelem;
+      gsrc[m] = Z1 + (size_t)s0 * src_stride + (gok[m] ? (size_t)(box.y + e / bw) * v.nx + box.x + e % bw : 0);
     }
-    auto issue = [&](int q) {
-      const float* Z = Z1 + (size_t)(s0 + q) * src_stride;
-      float* b = buf[q % NSTAGE];
+    float* outp = Z2 + (size_t)s0 * nt + k;
+    float* const sbase = &buf[0][0] + threadIdx.x;
+    auto issue = [&](int stage) {
 #pragma unroll
-      for (int m = 0; m < BOX_PER_THREAD; m++)
-        if (goff[m] >= 0) cp_async4(b + threadIdx.x + 256 * m, Z + goff[m]);
+      for (int m = 0; m < BOX_PER_THREAD; m++) {
+        if (gok[m]) cp_async4(sbase + stage * BOXMAX + 256 * m, gsrc[m]);
+        gsrc[m] += src_stride;
+      }
     };
 #pragma unroll
     for (int q = 0; q < NSTAGE - 1; q++) {
       if (q < nsl) issue(q);
       cp_async_commit();
     }
-    for (int q = 0; q < nsl; q++) {
-      cp_async_wait<NSTAGE - 2>();  // this thread's copies of slab q have landed
-      __syncthreads();              // ... everybody's have, and everybody is done reading slab q-1's buffer
-      if (q + NSTAGE - 1 < nsl) issue(q + NSTAGE - 1);  // refills the buffer slab q-1 used
-      cp_async_commit();
-      if (valid) {
-        const float* b = buf[q % NSTAGE];
-        float r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b[o1], w.x), __fmul_rn(b[o2], w.y)), __fmul_rn(b[o3], w.z)), __fmul_rn(b[o4], w.w)), wup);
-        if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
-        if (masked) r = po.rmiss;
-        __stcs(Z2 + (size_t)(s0 + q) * nt + k, r);
+    int nissued = NSTAGE - 1;
+    for (int q0 = 0; q0 < nsl; q0 += NSTAGE) {
+#pragma unroll
+      for (int u = 0; u < NSTAGE; u++) {  // stage index == u: compile-time shared-memory offsets
+        const int q = q0 + u;
+        if (q < nsl) {
+          cp_async_wait<NSTAGE - 2>();  // this thread's copies of slab q have landed
+          __syncthreads();              // ... everybody's have, and everybody is done reading slab q-1's buffer
+          if (nissued < nsl) issue((u + NSTAGE - 1) % NSTAGE);  // refills the buffer slab q-1 used
+          nissued++;
+          cp_async_commit();
+          if (valid) {
+            const float* b = &buf[u][0];
+            float r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(b[o1], w.x), __fmul_rn(b[o2], w.y)), __fmul_rn(b[o3], w.z)), __fmul_rn(b[o4], w.w)), wup);
+            if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+            if (masked) r = po.rmiss;
+            __stcs(outp, r);
+            outp += nt;
+          }
+        }
       }
     }
     __syncthreads();  // the next tile's prologue overwrites the buffers

@@ -369,6 +369,12 @@ int sosie_bdrown(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nsl
   return SOSIE_OK;
 }
 
+int sosie_bdrown_force_general(sosie_ctx* c, int32_t on) {
+  NEED(c);
+  ctx->force_general_bdrown = on != 0;
+  return SOSIE_OK;
+}
+
 int sosie_smoother(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X, int32_t nb_smooth, const int32_t* msk,
                    int32_t l_emp) {
   NEED(c);

@@ -122,6 +122,7 @@ struct sosie_ctx {
   DBuf<int8_t> dr_m0, dr_m1;
   DBuf<float> dr_x, dr_x2;
   DBuf<int32_t> dr_cnt, dr_mask32;
+  bool force_general_bdrown = false;  // tests: exercise the multi-launch global-memory path on small slabs too
 };
 
 #define CK(call)                                                                      \

@@ -110,12 +110,17 @@ def test_bdrown_vs_oracle(gpu, orc, scale, kew, per_slab):
         mask = base
     X = np.where(np.broadcast_to(mask, X.shape) == 0, np.float32(-9999.0), X).astype(np.float32)
     for nb_inc, nb_smooth, pval in ((20, 5, 0.0), (3, 0, -5.0), (200, 50, 0.0)):
-        Xg, ng = gpu.bdrown(kew, X, mask, nb_inc, nb_smooth, -1.0e3, 1.0e3, pval)
         Xo, no = orc.bdrown(kew, X, mask, nb_inc, nb_smooth, -1.0e3, 1.0e3, pval)
-        assert np.array_equal(ng, no), (ng, no)
-        assert np.array_equal(Xg, Xo), f"bdrown differs at {(Xg != Xo).sum()} points, max {np.nanmax(np.abs(Xg - Xo))}"
-        sea = np.broadcast_to(mask, X.shape) == 1
-        assert np.array_equal(Xg[sea], np.clip(X[sea], -1.0e3, 1.0e3))    # mask==1 untouched (mod_bdrown.f90:22-24)
+        for general in (False, True):      # on-chip one-CTA-per-slab kernel, and the general multi-launch path
+            gpu.bdrown_force_general(general)
+            try:
+                Xg, ng = gpu.bdrown(kew, X, mask, nb_inc, nb_smooth, -1.0e3, 1.0e3, pval)
+            finally:
+                gpu.bdrown_force_general(False)
+            assert np.array_equal(ng, no), (general, ng, no)
+            assert np.array_equal(Xg, Xo), f"bdrown(general={general}) differs at {(Xg != Xo).sum()} points, max {np.nanmax(np.abs(Xg - Xo))}"
+            sea = np.broadcast_to(mask, X.shape) == 1
+            assert np.array_equal(Xg[sea], np.clip(X[sea], -1.0e3, 1.0e3))    # mask==1 untouched (mod_bdrown.f90:22-24)
 
 
 def test_bdrown_clamp_active(gpu, orc):
