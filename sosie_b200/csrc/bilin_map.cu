@@ -230,6 +230,9 @@ struct Best {
   int i, j;
 };
 #define PDS_MARGIN 1.0e-13
+#ifndef MAP_MIN_BLOCKS
+#define MAP_MIN_BLOCKS 6
+#endif
 __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
                                             int j2, Best& b) {
   b.d = 0.0; b.pds = -4.0; b.i = 0; b.j = 0;
@@ -255,7 +258,7 @@ struct MapOut {
 
 // body of the target loop of MAPPING_BL, src/mod_bilin_2d.f90:459-634
 __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP, double yP, int iP, int jP, MapOut& o,
-                                         int* err) {
+                                         int* err, bool have_u = false, double ux0 = 0.0, double uy0 = 0.0, double uz0 = 0.0) {
   o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
   const int nxi = sg.nx, nyi = sg.nyw;
   if (!((iP != (int)G_RMV) && (jP != (int)G_RMV) && (jP < nyi))) return;
@@ -285,7 +288,15 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
   double loni[5], lati[5];
   loni[0] = xP; lati[0] = yP;
   loni[1] = lonP; lati[1] = latP;
-  o.dnp = (float)d_distance(xP, lonP, yP, latP);
+  {
+    // DISTANCE(xP, lonP, yP, latP) (:549).  The unit vectors are pure functions of (lon, lat): reuse the target's
+    // (computed by the search for the same xP) and the source table entry when MOD() left the longitudes unchanged.
+    double ux, uy, uz, vx, vy, vz;
+    if (have_u) { ux = ux0; uy = uy0; uz = uz0; } else unit_vec(xP, yP, ux, uy, uz);
+    if (lonP == src_lon(sg, iP, jP)) src_vec(sg, iP, jP, vx, vy, vz); else unit_vec(lonP, latP, vx, vy, vz);
+    double zpds = ux * vx + uy * vy + uz * vz;
+    o.dnp = (zpds >= 1.0) ? 0.f : (float)(G_ZR * pm_acos(zpds));
+  }
   int icpt = 0;
   bool lagain = true;
   const int iqdrn0 = 0;  // Q2
@@ -350,7 +361,7 @@ __device__ __forceinline__ void map_store(const MapOut& o, int iP, int jP, int m
 
 // ---------------------------------------------------------------------------------------------------
 // EASY search (src/mod_manip.f90:967-1069) fused with the MAPPING_BL body: one thread per target.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MAP_MIN_BLOCKS)
 k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
            const double* __restrict__ vlat, int sorted_lon, int sorted_lat, int jlo, int jhi, int32_t* MT, double* AB,
            int16_t* IDP, float* DNP, int* err, size_t k0, size_t kcnt) {
@@ -361,13 +372,15 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
     int m = mask ? mask[k] : 1;
     int iP = -1, jP = -1;
     double rlon = trg_lon(tg, ji_t, jj_t), rlat = trg_lat(tg, ji_t, jj_t);
+    double ux = 0.0, uy = 0.0, uz = 0.0;
+    bool have_u = false;
     if (m == 1 && jj_t >= jlo && jj_t <= jhi) {
       int ip = sorted_lon ? minloc_abs_sorted(vlon, sg.nx, rlon) : minloc_abs_linear(vlon, sg.nx, rlon);
       int jp = sorted_lat ? minloc_abs_sorted(vlat, sg.nyw, rlat) : minloc_abs_linear(vlat, sg.nyw, rlat);
       int i1s = max(ip - 4, 1), i2s = min(ip + 4, sg.nx);
       int j1s = max(jp - 4, 1), j2s = min(jp + 4, sg.nyw);
-      double ux, uy, uz;
       unit_vec(rlon, rlat, ux, uy, uz);
+      have_u = (fabs(rlon) < 360.0);   // MOD(xP,360) == xP: the body's DISTANCE sees the same longitude
       Best b;
       scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b);
       iP = b.i; jP = b.j;
@@ -375,7 +388,7 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
     }
     MapOut o;
     o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
-    if (m == 1) map_body(sg, k_ew, rlon, rlat, iP, jP, o, err);
+    if (m == 1) map_body(sg, k_ew, rlon, rlat, iP, jP, o, err, have_u, ux, uy, uz);
     map_store(o, iP, jP, m, k, nt, MT, AB, IDP, DNP);
   }
 }
