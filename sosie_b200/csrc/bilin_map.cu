@@ -234,16 +234,30 @@ struct Best {
 #define MAP_MIN_BLOCKS 6
 #endif
 __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
-                                            int j2, Best& b) {
+                                            int j2, Best& b, int ic, int jc) {
+  // MINLOC = lexicographic minimum of (distance, column-major position).  The window centre (ic,jc) -- the
+  // index-nearest point, almost always the winner or next to it -- is evaluated first, so that nearly every other
+  // candidate is rejected by the dot-product margin without an acos; ties are still resolved by position, which
+  // makes the result independent of the evaluation order.
   b.d = 0.0; b.pds = -4.0; b.i = 0; b.j = 0;
+  ic = min(max(ic, i1), i2);
+  jc = min(max(jc, j1), j2);
+  {
+    double vx, vy, vz;
+    src_vec(sg, ic, jc, vx, vy, vz);
+    double zpds = ux * vx + uy * vy + uz * vz;
+    b.d = G_ZR * pm_acos(fmin(zpds, 1.0));
+    b.pds = zpds; b.i = ic; b.j = jc;
+  }
   for (int jj = j1; jj <= j2; jj++) {
     for (int ji = i1; ji <= i2; ji++) {
       double vx, vy, vz;
       src_vec(sg, ji, jj, vx, vy, vz);
       double zpds = ux * vx + uy * vy + uz * vz;
-      if (b.i != 0 && zpds < b.pds - PDS_MARGIN) continue;
+      if (zpds < b.pds - PDS_MARGIN) continue;   // => strictly farther than the current best
       double d = G_ZR * pm_acos(fmin(zpds, 1.0));
-      if (b.i == 0 || d < b.d) { b.d = d; b.pds = zpds; b.i = ji; b.j = jj; }
+      bool earlier = (jj < b.j) || (jj == b.j && ji < b.i);
+      if (d < b.d || (d == b.d && earlier)) { b.d = d; b.pds = zpds; b.i = ji; b.j = jj; }
     }
   }
 }
@@ -382,7 +396,7 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
       unit_vec(rlon, rlat, ux, uy, uz);
       have_u = (fabs(rlon) < 360.0);   // MOD(xP,360) == xP: the body's DISTANCE sees the same longitude
       Best b;
-      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b);
+      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, ip, jp);
       iP = b.i; jP = b.j;
       if (iP == 0 || jP == 0) atomicOr(err, 2);
     }
@@ -576,7 +590,7 @@ k_twisted_chain(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__
       int i1s = max(pr.x - 5, 1), i2s = min(pr.x + 5, sg.nx);
       int j1s = max(pr.y - 5, 1), j2s = min(pr.y + 5, sg.nyw);
       Best b;
-      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b);
+      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, pr.x, pr.y);
       if (b.i != 0) {
         size_t ks = (size_t)(b.i - 1) + (size_t)(b.j - 1) * sg.nx;
         double emax = fmax(tp.e1[ks], tp.e2[ks]) / 1000.0 * tp.sqrt2f;

@@ -260,13 +260,15 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
               float zmin, float zmax, float zval, int32_t* nsw_out) {
   extern __shared__ __align__(16) unsigned char smraw[];
   const int ni = g.ni, nj = g.nj, n = ni * nj;
+  // layout: X[n] f32 | mw[n] u8 | list[n] u16 | 2 int counters      (7n + 16 bytes)
+  //   mw: 0 = land (not reached yet), 1 = sea, j+1 = land drowned by sweep j
   float* X = reinterpret_cast<float*>(smraw);
-  int8_t* morig = reinterpret_cast<int8_t*>(X + n);   // 1 sea, 0 land; after the sweeps: 2 = land never reached
-  int8_t* m0 = morig + n;                             // running mask, ping
-  int8_t* m1 = m0 + n;                                // pong; after the sweeps m0|m1 (2n bytes) hold the land list
+  uint8_t* mw = reinterpret_cast<uint8_t*>(X + n);
+  const int list_off = ((5 * n + 1) / 2) * 2;
+  unsigned short* list = reinterpret_cast<unsigned short*>(smraw + list_off);
+  const int smem_cnt_off = ((list_off + 2 * n + 7) / 8) * 8;
+  int* cnt = reinterpret_cast<int*>(smraw + smem_cnt_off);
   const int tid = threadIdx.x;
-  // layout: X[n] f32 | morig[n] | m0[n] | m1[n] | pad | 2 int counters
-  const int smem_cnt_off = ((7 * n + 7) / 8) * 8;
   const float w0 = 0.35f, omw = 1.f - w0, c4 = 4.f * (1.f + RIS2F);
   for (int s = blockIdx.x; s < nslab; s += gridDim.x) {
     float* Xg = Xb + (size_t)s * n;
@@ -274,15 +276,13 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
     __syncthreads();
     for (int k = tid; k < n; k += BDS_THREADS) {
       X[k] = Xg[k];
-      int8_t m = (int8_t)mg[k];
-      m0[k] = m;
-      morig[k] = m;
+      mw[k] = (uint8_t)mg[k];
     }
     __syncthreads();
     // zonal-mean prefill (:109-120): one thread per row, sequential REAL(4) sum
     for (int jj = tid; jj < nj; jj += BDS_THREADS) {
       float* row = X + jj * ni;
-      const int8_t* mrow = morig + jj * ni;
+      const uint8_t* mrow = mw + jj * ni;
       int nbp = 0;
       for (int i = 0; i < ni; i++) nbp += mrow[i];
       if (nbp > 0) {
@@ -293,7 +293,6 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
       }
     }
     __syncthreads();
-    uint8_t* mw = reinterpret_cast<uint8_t*>(m0);   // 0 land, 1 sea, j+1 = drowned by sweep j
     int nsw = 0;
     // strip mapping: thread -> fixed column ji, rows jj0+1, jj0+1+rpp, ... (no integer division in the loops,
     // consecutive lanes on consecutive cells: conflict-free shared-memory access)
@@ -305,13 +304,11 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
       for (int jj = my_j0 + 1; jj <= nj; jj += rpp) land |= (mw[(jj - 1) * ni + my_i - 1] == 0);
     int any_land = __syncthreads_or(land);
     // Each sweep in two dense phases (a warp whose lanes mix sea / inland / coastline cells would otherwise execute
-    // the long coastline path for every row it walks): (1) cheap coastline test, coastline cells appended to a 16-bit
-    // list in the spare mask buffer; (2) the list is processed with all lanes busy.
-    unsigned short* clist = reinterpret_cast<unsigned short*>(m1);   // <= n/2 coastline cells (they need a sea neighbour)
-    int* ccnt = reinterpret_cast<int*>(smraw + smem_cnt_off);
+    // the long coastline path for every row it walks): (1) cheap coastline test, coastline cells appended to the
+    // 16-bit list; (2) the list is processed with all lanes busy.
     for (int jinc = 1; jinc <= nb_inc && any_land; jinc++) {   // IF(.NOT. ANY(maskv == 0)) EXIT (:125)
       nsw++;
-      if (tid == 0) ccnt[0] = 0;
+      if (tid == 0) cnt[0] = 0;
       __syncthreads();
       land = 0;
       if (strip_active)
@@ -319,13 +316,13 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
           const int k = (jj - 1) * ni + my_i - 1;
           if (mw[k] != 0) continue;
           float dummy;
-          if (bd_cell<false>(g, mw, X, my_i, jj, 0, zmin, zmax, dummy, jinc)) clist[atomicAdd(&ccnt[0], 1)] = (unsigned short)k;
+          if (bd_cell<false>(g, mw, X, my_i, jj, 0, zmin, zmax, dummy, jinc)) list[atomicAdd(&cnt[0], 1)] = (unsigned short)k;
           else land = 1;
         }
       any_land = __syncthreads_or(land);
-      const int nc = ccnt[0];
+      const int nc = cnt[0];
       for (int q = tid; q < nc; q += BDS_THREADS) {
-        const int k = clist[q];
+        const int k = list[q];
         const int jj = k / ni + 1, ji = k % ni + 1;
         float val;
         bd_cell<true>(g, mw, X, ji, jj, jinc == 1, zmin, zmax, val, jinc);
@@ -336,29 +333,18 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
       }
       __syncthreads();
     }
-    // normalise the running mask to 0/1 for what follows
-    for (int k = tid; k < n; k += BDS_THREADS) m0[k] = (m0[k] != 0) ? 1 : 0;
-    int8_t* mc = m0;
-    __syncthreads();
     if (nsw >= 1) {  // the per-sweep whole-array clamp (:414-415), once
       for (int k = tid; k < n; k += BDS_THREADS) { float v = X[k]; X[k] = fminf(fmaxf(v, zmin), zmax); }
     }
     __syncthreads();
-    // SMOOTHER(msk = 1 - mask) (:419-425).  Only land cells of rows 2..nj-1 change; they are compacted once into a
-    // 16-bit index list (kept in the mask buffer the sweeps no longer need + the spare tail of the allocation):
-    // interior cells first (fixed neighbour offsets), periodic edge-column cells after them.
-    if (fabsf(zval) > 1.e-12f)   // remember the cells no sweep reached: the running masks are recycled below
-      for (int k = tid; k < n; k += BDS_THREADS) if (mc[k] == 0) morig[k] = 2;
-    __syncthreads();
+    // SMOOTHER(msk = 1 - mask) (:419-425).  Only land cells (mw != 1) of rows 2..nj-1 change; they are compacted once
+    // into the 16-bit list: interior cells first (fixed neighbour offsets), periodic edge-column cells after them.
     if (nb_smooth > 0) {
-      unsigned short* list = reinterpret_cast<unsigned short*>(m0);   // m0|m1: 2n bytes
-      int* cnt = reinterpret_cast<int*>(smraw + smem_cnt_off);
       if (tid < 2) cnt[tid] = 0;
       __syncthreads();
       const bool per = g.k_ew >= 0;
-      // pass 1: count / reserve (block-wide atomics; order inside the list is irrelevant)
       for (int k = tid; k < n; k += BDS_THREADS) {
-        if (morig[k] == 1) continue;
+        if (mw[k] == 1) continue;
         const int jj = k / ni + 1, ji = k % ni + 1;
         if (jj < 2 || jj > nj - 1) continue;
         if (ji >= 2 && ji <= ni - 1) { int p = atomicAdd(&cnt[0], 1); list[p] = (unsigned short)k; }
@@ -367,7 +353,7 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
       const int n_int = cnt[0];
       if (per)
         for (int k = tid; k < n; k += BDS_THREADS) {
-          if (morig[k] == 1) continue;
+          if (mw[k] == 1) continue;
           const int jj = k / ni + 1, ji = k % ni + 1;
           if (jj < 2 || jj > nj - 1) continue;
           if (ji == 1 || ji == ni) { int p = atomicAdd(&cnt[1], 1); list[n_int + p] = (unsigned short)k; }
@@ -406,7 +392,7 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
       }
     }
     if (fabsf(zval) > 1.e-12f) {
-      for (int k = tid; k < n; k += BDS_THREADS) if (morig[k] == 2) X[k] = zval;  // (:431-433)
+      for (int k = tid; k < n; k += BDS_THREADS) if (mw[k] == 0) X[k] = zval;  // (:431-433)
     }
     __syncthreads();
     for (int k = tid; k < n; k += BDS_THREADS) Xg[k] = X[k];
@@ -647,7 +633,7 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
   const size_t n = (size_t)ni * nj;
   const int nmask = mask_per_slab ? nslab : 1;
   if (nb_inc < 0) nb_inc = 0;
-  const size_t smem_need = ((7 * n + 7) / 8) * 8 + 16;  // X | morig | m0 | m1 | 2 counters
+  const size_t smem_need = ((((5 * n + 1) / 2) * 2 + 2 * n + 7) / 8) * 8 + 16;  // X | mw | list | 2 counters
   if (smem_need <= (size_t)227 * 1024 && (n + BDS_THREADS - 1) / BDS_THREADS <= BDS_MAXCPT && ni <= BDS_THREADS && n < 65536 && nb_inc <= 250 && !ctx->force_general_bdrown) {
     // the whole slab fits one SM's shared memory: one CTA per slab, every sweep on chip
     CK(ctx->dr_cnt.alloc(nslab));
