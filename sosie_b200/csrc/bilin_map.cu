@@ -126,18 +126,52 @@ __global__ void k_min_dlat(TrgGeom tg, Prelude* p) {
 }
 
 // i1dum = MINLOC(Ytrg, mask=(Ytrg>=y_min_s), dim=2) ; MAXLOC(Ytrg, mask=(Ytrg<=y_max_s), dim=2)  (:939-941)
-__global__ void k_jrange(TrgGeom tg, Prelude* p, double y_min_s, double y_max_s) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i <= tg.nx; i += gridDim.x * blockDim.x) {
-    int jn = 0, jx = 0;
-    double vmin = 0, vmax = 0;
-    for (int j = 1; j <= tg.ny; j++) {
+// Two exact parallel passes per column: (1) the extreme VALUE (atomicMin/Max on order-preserving encodings),
+// (2) the FIRST row attaining it (atomicMin on the row index) -- MINLOC/MAXLOC return the first occurrence.
+__global__ void k_fill_i32(int32_t* a, size_t n, int32_t v);
+#define JR_ROWS 64
+__global__ void k_jrange_val(TrgGeom tg, double y_min_s, double y_max_s, unsigned long long* cmin, unsigned long long* cmax) {
+  int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
+  size_t total = (size_t)tg.nx * nchunk;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int i = (int)(t % tg.nx) + 1, c = (int)(t / tg.nx);
+    unsigned long long lmin = ~0ULL, lmax = 0ULL;
+    int j1 = min(tg.ny, (c + 1) * JR_ROWS);
+    for (int j = c * JR_ROWS + 1; j <= j1; j++) {
       double v = trg_lat(tg, i, j);
-      if (v >= y_min_s) { if (jn == 0 || v < vmin) { vmin = v; jn = j; } }
-      if (v <= y_max_s) { if (jx == 0 || v > vmax) { vmax = v; jx = j; } }
+      if (v >= y_min_s) lmin = min(lmin, enc_d(v));
+      if (v <= y_max_s) lmax = max(lmax, enc_d(v));
     }
-    if (jn > 0) atomicMin(&p->j_strt, jn);
-    atomicMax(&p->j_stop, jx);
+    if (lmin != ~0ULL) atomicMin(&cmin[i - 1], lmin);
+    if (lmax != 0ULL) atomicMax(&cmax[i - 1], lmax);
   }
+}
+__global__ void k_jrange_idx(TrgGeom tg, const unsigned long long* __restrict__ cmin, const unsigned long long* __restrict__ cmax,
+                             int* jn, int* jx) {
+  int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
+  size_t total = (size_t)tg.nx * nchunk;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    int i = (int)(t % tg.nx) + 1, c = (int)(t / tg.nx);
+    unsigned long long vmin = cmin[i - 1], vmax = cmax[i - 1];
+    int j1 = min(tg.ny, (c + 1) * JR_ROWS);
+    int fn = 2147483647, fx = 2147483647;
+    for (int j = c * JR_ROWS + 1; j <= j1; j++) {
+      unsigned long long e = enc_d(trg_lat(tg, i, j));
+      if (e == vmin && fn == 2147483647) fn = j;
+      if (e == vmax && fx == 2147483647) fx = j;
+    }
+    if (vmin != ~0ULL && fn != 2147483647) atomicMin(&jn[i - 1], fn);
+    if (vmax != 0ULL && fx != 2147483647) atomicMin(&jx[i - 1], fx);
+  }
+}
+__global__ void k_jrange_fin(int nx, const int* __restrict__ jn, const int* __restrict__ jx, Prelude* p) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    if (jn[i] != 2147483647) atomicMin(&p->j_strt, jn[i]);            // MINVAL(i1dum, mask=(i1dum>0))
+    atomicMax(&p->j_stop, jx[i] != 2147483647 ? jx[i] : 0);           // MAXVAL(MAXLOC(...)) (0 where the mask is empty)
+  }
+}
+__global__ void k_fill_u64(unsigned long long* a, size_t n, unsigned long long v) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) a[k] = v;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -179,9 +213,11 @@ __global__ void k_lat_table(const double* __restrict__ Yin, int ny, int nyw, dou
     lat[j] = (j < ny) ? Yin[j] : ((j == ny) ? 90.0 : 90.0 + dyp);
 }
 // ji_m = MINLOC(ABS(XX(:,ny)-MOD(zlon+180.,360.)))  (src/mod_manip.f90:1821-1826)
-__global__ void k_jim_table(const double* __restrict__ lonrow, int nx, int32_t* im) {
+__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r);
+__global__ void k_jim_table(const double* __restrict__ lonrow, int nx, int sorted, int32_t* im) {
   for (int ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nx; ji += gridDim.x * blockDim.x) {
     double zlon_m = fmod(lonrow[ji] + 180.0, 360.0);
+    if (sorted) { im[ji] = minloc_abs_sorted(lonrow, nx, zlon_m); continue; }
     int best = 0;
     double bv = fabs(lonrow[0] - zlon_m);
     for (int i = 1; i < nx; i++) {
@@ -190,6 +226,10 @@ __global__ void k_jim_table(const double* __restrict__ lonrow, int nx, int32_t* 
     }
     im[ji] = best + 1;
   }
+}
+__global__ void k_check_sorted(const double* __restrict__ v, int n, int* unsorted) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x)
+    if (v[i] < v[i - 1]) atomicOr(unsorted, 1);
 }
 __global__ void k_gather_axes(SrcGeom sg, double* vlon, double* vlat) {  // vlon = Xsrc(:,3), vlat = Ysrc(3,:)
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < sg.nx + sg.nyw; k += gridDim.x * blockDim.x) {
@@ -693,7 +733,13 @@ int bilin_prepare_src(sosie_ctx* ctx) {
   if (ctx->l_add_extra_j) {
     CK(ctx->d_im.alloc(nx));
     const double* lonrow = in_1d ? Xin : Xin + (size_t)(ny - 1) * nx;
-    k_jim_table<<<cdiv(nx, 128), 128, 0, st>>>(lonrow, nx, ctx->d_im.p); KLAUNCH_CHECK();
+    CK(ctx->d_iscratch.alloc(4));
+    CK(cudaMemsetAsync(ctx->d_iscratch.p + 1, 0, sizeof(int), st));
+    k_check_sorted<<<cdiv(nx, 256), 256, 0, st>>>(lonrow, nx, ctx->d_iscratch.p + 1); KLAUNCH_CHECK();
+    int unsorted = 0;
+    CK(cudaMemcpyAsync(&unsorted, ctx->d_iscratch.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    k_jim_table<<<cdiv(nx, 128), 128, 0, st>>>(lonrow, nx, unsorted ? 0 : 1, ctx->d_im.p); KLAUNCH_CHECK();
   }
   return SOSIE_OK;
 }
@@ -711,6 +757,7 @@ int bilin_map_impl(sosie_ctx* ctx) {
   const size_t nt = (size_t)tg.nx * tg.ny;
   const size_t nsrc = (size_t)sg.nx * sg.nyw;
   CK(ctx->d_metrics.alloc(3 * nt)); CK(ctx->d_ab.alloc(2 * nt)); CK(ctx->d_ipb.alloc(nt)); CK(ctx->d_dnp.alloc(nt));
+  ctx->ws_cursor = 0;
   CK(ctx->d_scratch.alloc(64)); CK(ctx->d_iscratch.alloc(4));
   struct { Prelude* p; } dpre = {reinterpret_cast<Prelude*>(ctx->d_scratch.p)};
   struct { int* p; } derr = {reinterpret_cast<int*>(ctx->d_iscratch.p)};
@@ -740,7 +787,17 @@ int bilin_map_impl(sosie_ctx* ctx) {
   if (tg.nx > 2 && tg.ny >= 2) rmin_dlat_dj = dec_d_host(hp.rmin_dlat);
   int j_strt_t = 1, j_stop_t = tg.ny, jlat_icr = 1;
   if ((rmin_dlat_dj > (double)-1.E-12f) || l_is_reg_t) {
-    k_jrange<<<grid_for(ctx, tg.nx, 128), 128, 0, st>>>(tg, dpre.p, y_min_s, y_max_s); KLAUNCH_CHECK();
+    {
+      WS(unsigned long long, cmin, tg.nx); WS(unsigned long long, cmax, tg.nx); WS(int, jn, tg.nx); WS(int, jx, tg.nx);
+      k_fill_u64<<<cdiv(tg.nx, 256), 256, 0, st>>>(cmin.p, tg.nx, ~0ULL); KLAUNCH_CHECK();
+      CK(cudaMemsetAsync(cmax.p, 0, sizeof(unsigned long long) * tg.nx, st));
+      k_fill_i32<<<cdiv(tg.nx, 256), 256, 0, st>>>(jn.p, tg.nx, 2147483647); KLAUNCH_CHECK();
+      k_fill_i32<<<cdiv(tg.nx, 256), 256, 0, st>>>(jx.p, tg.nx, 2147483647); KLAUNCH_CHECK();
+      size_t tot = (size_t)tg.nx * ((tg.ny + JR_ROWS - 1) / JR_ROWS);
+      k_jrange_val<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, y_min_s, y_max_s, cmin.p, cmax.p); KLAUNCH_CHECK();
+      k_jrange_idx<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, cmin.p, cmax.p, jn.p, jx.p); KLAUNCH_CHECK();
+      k_jrange_fin<<<cdiv(tg.nx, 256), 256, 0, st>>>(tg.nx, jn.p, jx.p, dpre.p); KLAUNCH_CHECK();
+    }
     CK(cudaMemcpyAsync(&hp, dpre.p, sizeof(Prelude), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     j_strt_t = hp.j_strt; j_stop_t = hp.j_stop;
@@ -780,14 +837,14 @@ int bilin_map_impl(sosie_ctx* ctx) {
     ctx->map_info[5] = 1;
     if ((y_min_t >= y_max_s) || (y_max_t <= y_min_s)) { ctx->err = "FIND_NEAREST_TWISTED: Target and source latitudes do not overlap!"; return SOSIE_ERR_REF_STOP; }
     if (sg.separable) { ctx->err = "internal: TWISTED with separable source"; return SOSIE_ERR_ARG; }
-    DBuf<double> e1, e2; CK(e1.alloc(nsrc)); CK(e2.alloc(nsrc));
+    WS(double, e1, nsrc); WS(double, e2, nsrc);
     k_src_metrics<<<grid_for(ctx, nsrc, 128), 128, 0, st>>>(sg, e1.p, e2.p); KLAUNCH_CHECK();
     // IS_POLAR_PROJ on source and target (:1171,1181)
     auto polar = [&](const double* X, const double* Y, int nx, int ny, int is1d, double ymax, bool* lpp) -> int {
       *lpp = false;
       if (!(ymax > 88.0)) return 0;
       const int nb = 64;
-      DBuf<MinIdx> part; CK(part.alloc(nb));
+      WS(MinIdx, part, nb);
       size_t n = (size_t)nx * ny;
       k_argmin_np<<<nb, 256, 0, st>>>(Y, n, is1d, nx, part.p); KLAUNCH_CHECK();
       MinIdx hpart[nb];
@@ -834,9 +891,9 @@ int bilin_map_impl(sosie_ctx* ctx) {
       double dy = (y_max_bnd - y_min_bnd) / (double)(float)nsplit;
       for (int jl = 1; jl <= nsplit + 1; jl++) VB[jl - 1] = y_min_bnd + (double)(float)(jl - 1) * dy;
       if ((y_min_bnd > y_min_bnd0) || (y_max_bnd < y_max_bnd0)) { ctx->err = "FIND_NEAREST_POINT: Bounds for latitude for VLAT_SPLIT_BOUNDS are bad!"; return SOSIE_ERR_REF_STOP; }
-      CK(dVB.alloc(nsplit + 1)); CK(dJV.alloc(2 * nsplit));
+      { WS(double, tvb, nsplit + 1); WS(int, tjv, 2 * nsplit); dVB.borrow(tvb.p, nsplit + 1); dJV.borrow(tjv.p, 2 * nsplit); }
       CK(cudaMemcpyAsync(dVB.p, VB.data(), sizeof(double) * (nsplit + 1), cudaMemcpyHostToDevice, st));
-      DBuf<int> jmx, jmn; CK(jmx.alloc(nsplit)); CK(jmn.alloc(nsplit));
+      WS(int, jmx, nsplit); WS(int, jmn, nsplit);
       CK(cudaMemsetAsync(jmx.p, 0, sizeof(int) * nsplit, st));
       k_fill_i32<<<1, 64, 0, st>>>(jmn.p, nsplit, 2147483647); KLAUNCH_CHECK();
       k_jvlat<<<grid_for(ctx, (size_t)sg.nx * nsplit, 128), 128, 0, st>>>(sg, nsplit, dVB.p, jmx.p, jmn.p); KLAUNCH_CHECK();
@@ -859,26 +916,24 @@ int bilin_map_impl(sosie_ctx* ctx) {
     long ntrip = ((long)j_stop_t - (long)j_strt_t + jlat_icr) / jlat_icr;
     if (ntrip < 0) ntrip = 0;
     size_t np = (size_t)ntrip * tg.nx;
-    DBuf<int32_t> JI, JJ; CK(JI.alloc(nt)); CK(JJ.alloc(nt));
+    WS(int32_t, JI, nt); WS(int32_t, JJ, nt);
     k_fill_i32<<<grid_for(ctx, nt, 256), 256, 0, st>>>(JI.p, nt, -1); KLAUNCH_CHECK();
     k_fill_i32<<<grid_for(ctx, nt, 256), 256, 0, st>>>(JJ.p, nt, -1); KLAUNCH_CHECK();
     int T = 0;
-    DBuf<int64_t> order;
+    WS(int64_t, order, np + 1);
     if (np > 0) {
-      DBuf<uint8_t> flags; DBuf<int64_t> lin; DBuf<int> dnum;
-      CK(flags.alloc(np)); CK(lin.alloc(np)); CK(order.alloc(np)); CK(dnum.alloc(1));
+      WS(uint8_t, flags, np); WS(int64_t, lin, np); WS(int, dnum, 1);
       k_twisted_flags<<<grid_for(ctx, np, 256), 256, 0, st>>>(tg, ctx->t_mask.p, j_strt_t, jlat_icr, (int)ntrip, flags.p, lin.p); KLAUNCH_CHECK();
       size_t tmpb = 0;
       cub::DeviceSelect::Flagged(nullptr, tmpb, lin.p, flags.p, order.p, dnum.p, (int)np, st);
-      DBuf<uint8_t> tmp; CK(tmp.alloc(tmpb + 16));
+      WS(uint8_t, tmp, tmpb + 16);
       CK(cub::DeviceSelect::Flagged(tmp.p, tmpb, lin.p, flags.p, order.p, dnum.p, (int)np, st));
       ctx->launches += 2;
       CK(cudaMemcpyAsync(&T, dnum.p, sizeof(int), cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
     }
     if (T > 0) {
-      DBuf<int2> bpos, S0, S1; DBuf<int8_t> bfound, found; DBuf<int> dchg;
-      CK(bpos.alloc(T)); CK(S0.alloc(T)); CK(S1.alloc(T)); CK(bfound.alloc(T)); CK(found.alloc(T)); CK(dchg.alloc(1));
+      WS(int2, bpos, T); WS(int2, S0, T); WS(int2, S1, T); WS(int8_t, bfound, T); WS(int8_t, found, T); WS(int, dchg, 1);
       prof_begin(ctx, SOSIE_T_MAP);
       k_twisted_band<<<grid_for(ctx, (size_t)T * 32, 256), 256, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, derr.p); KLAUNCH_CHECK();
       prof_end(ctx, SOSIE_T_MAP);

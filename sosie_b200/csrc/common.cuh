@@ -104,6 +104,11 @@ struct sosie_ctx {
   DBuf<double> d_scratch;        // Prelude + misc scalars of the search
   DBuf<int32_t> d_iscratch;      // error flag
   DBuf<double> d_vax;            // vlon/vlat axes of the EASY search
+  // persistent scratch slots handed out in call order (cudaMalloc/cudaFree cost ~0.1-1 ms each and cudaFree
+  // synchronises: the mapping would otherwise spend more time allocating than computing on small grids)
+  std::vector<DBuf<unsigned char>*> ws_slots;
+  size_t ws_cursor = 0;
+  ~sosie_ctx() { for (auto* p : ws_slots) delete p; }
   int32_t map_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int l_last_y_row_missing = 0;
 
@@ -145,6 +150,20 @@ struct sosie_ctx {
   } while (0)
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// scratch slot #cursor of the context, grown to hold `count` T's (nullptr on allocation failure)
+template <class T>
+static inline T* ws_get(sosie_ctx* ctx, size_t count) {
+  if (ctx->ws_cursor >= ctx->ws_slots.size()) ctx->ws_slots.push_back(new DBuf<unsigned char>());
+  DBuf<unsigned char>* b = ctx->ws_slots[ctx->ws_cursor++];
+  size_t bytes = count * sizeof(T) + 16;
+  if (b->alloc(bytes) != cudaSuccess) return nullptr;
+  return reinterpret_cast<T*>(b->p);
+}
+#define WS(T, name, count)                                                              \
+  T* name##_p = ws_get<T>(ctx, (count));                                                \
+  if (!name##_p) { ctx->err = "out of device memory (scratch)"; return SOSIE_ERR_CUDA; } \
+  struct { T* p; } name = {name##_p}
 
 // event brackets around the dominant kernels (ids: SOSIE_T_* in sosie_b200.h)
 static inline void prof_begin(sosie_ctx* ctx, int id) {
