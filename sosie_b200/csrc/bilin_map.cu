@@ -289,6 +289,33 @@ __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double
     b.d = G_ZR * pm_acos(fmin(zpds, 1.0));
     b.pds = zpds; b.i = ic; b.j = jc;
   }
+  if (sg.separable && (i2 - i1) < 9) {
+    // Regular source: u.v = clat_j*(ux*clon_i + uy*slon_i) + uz*slat_j up to ~4e-16 of rounding.  That cheap form
+    // (2 flops per candidate) is only used to REJECT (with the margin widened by 1e-14, 20x its error); survivors are
+    // re-evaluated in the reference's own operation order before any comparison that decides the result.
+    double a[9];
+#pragma unroll
+    for (int q = 0; q < 9; q++) {
+      int ji = min(i1 + q, i2);
+      a[q] = ux * sg.clon[ji - 1] + uy * sg.slon[ji - 1];
+    }
+    for (int jj = j1; jj <= j2; jj++) {
+      const double cl = sg.clat[jj - 1], sl = sg.slat[jj - 1];
+      const double c0 = uz * sl;
+#pragma unroll
+      for (int q = 0; q < 9; q++) {
+        const int ji = i1 + q;
+        if (ji > i2) break;
+        if (cl * a[q] + c0 < b.pds - (PDS_MARGIN + 1.0e-14)) continue;
+        double zpds = ux * (sg.clon[ji - 1] * cl) + uy * (sg.slon[ji - 1] * cl) + uz * sl;
+        if (zpds < b.pds - PDS_MARGIN) continue;
+        double d = G_ZR * pm_acos(fmin(zpds, 1.0));
+        bool earlier = (jj < b.j) || (jj == b.j && ji < b.i);
+        if (d < b.d || (d == b.d && earlier)) { b.d = d; b.pds = zpds; b.i = ji; b.j = jj; }
+      }
+    }
+    return;
+  }
   for (int jj = j1; jj <= j2; jj++) {
     for (int ji = i1; ji <= i2; ji++) {
       double vx, vy, vz;
