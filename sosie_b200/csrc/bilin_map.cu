@@ -208,16 +208,40 @@ __global__ void k_build_src2d(const double* __restrict__ Xin, const double* __re
 __global__ void k_merc_table(const double* __restrict__ lat, size_t n, double* merc) {
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) merc[k] = d_merc(lat[k]);
 }
+// hE/hW per column and hN/hS per row of a separable source (see map_body): the arguments are exactly those the
+// body would form -- lonN = lonS = lonP (same column), yb = ya for the E/W neighbours (same row)
+__global__ void k_heading_tables(SrcGeom sg, int k_ew, double* hE, double* hW, double* hN, double* hS) {
+  const int nx = sg.nx, nyw = sg.nyw;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nx + nyw; k += gridDim.x * blockDim.x) {
+    if (k < nx) {
+      const int iP = k + 1;
+      int iPm1 = iP - 1, iPp1 = iP + 1;
+      if (iPm1 == 0) { if (k_ew >= 0) iPm1 = nx - k_ew; }
+      if (iPp1 == nx + 1) { if (k_ew >= 0) iPp1 = 1 + k_ew; }
+      const double lonP = d_mod(sg.lon1[iP - 1], 360.0);
+      double e = 0.0, w = 0.0;
+      if (iPp1 >= 1 && iPp1 <= nx) e = d_heading_y(lonP, d_mod(sg.lon1[iPp1 - 1], 360.0), 0.0, 0.0);
+      if (iPm1 >= 1 && iPm1 <= nx) w = d_heading_y(lonP, d_mod(sg.lon1[iPm1 - 1], 360.0), 0.0, 0.0);
+      hE[k] = e; hW[k] = w;
+    } else {
+      const int j = k - nx;  // 0-based row jP-1
+      double n = 0.0, s_ = 0.0;
+      if (j + 1 < nyw) n = d_heading_y(0.0, 0.0, sg.merc[j], sg.merc[j + 1]);
+      if (j >= 1) s_ = d_heading_y(0.0, 0.0, sg.merc[j], sg.merc[j - 1]);
+      hN[j] = n; hS[j] = s_;
+    }
+  }
+}
 __global__ void k_lat_table(const double* __restrict__ Yin, int ny, int nyw, double dyp, double* lat) {
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nyw; j += gridDim.x * blockDim.x)
     lat[j] = (j < ny) ? Yin[j] : ((j == ny) ? 90.0 : 90.0 + dyp);
 }
 // ji_m = MINLOC(ABS(XX(:,ny)-MOD(zlon+180.,360.)))  (src/mod_manip.f90:1821-1826)
-__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r);
+__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r, double v0, double inv_d);
 __global__ void k_jim_table(const double* __restrict__ lonrow, int nx, int sorted, int32_t* im) {
   for (int ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nx; ji += gridDim.x * blockDim.x) {
     double zlon_m = fmod(lonrow[ji] + 180.0, 360.0);
-    if (sorted) { im[ji] = minloc_abs_sorted(lonrow, nx, zlon_m); continue; }
+    if (sorted) { im[ji] = minloc_abs_sorted(lonrow, nx, zlon_m, 0.0, 0.0); continue; }
     int best = 0;
     double bv = fabs(lonrow[0] - zlon_m);
     for (int i = 1; i < nx; i++) {
@@ -240,12 +264,32 @@ __global__ void k_gather_axes(SrcGeom sg, double* vlon, double* vlat) {  // vlon
 
 // ---------------------------------------------------------------------------------------------------
 // MINLOC(ABS(v(:)-r)) : first minimum, 1-based
-__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r) {
-  int lo = 0, hi = n;  // lower_bound: first index with v[idx] >= r
+// lower_bound (first index with v[idx] >= r) of a sorted axis.  On a uniform axis the index is guessed from
+// (r - v0) * inv_d and VERIFIED against the two neighbouring entries (the definition of lower_bound), so the result
+// is the bracket search's in 2-3 loads instead of log2(n) dependent ones; any miss falls back to the bisection.
+__device__ __forceinline__ int lower_bound_axis(const double* __restrict__ v, int n, double r, double v0, double inv_d) {
+  if (inv_d > 0.0) {
+    const double t = (r - v0) * inv_d;
+    if (t > -2.0 && t < (double)n + 2.0) {  // (false for NaN)
+      const int g = (int)ceil(t);
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        const int lo = g + (d == 0 ? 0 : (d == 1 ? -1 : 1));
+        if (lo < 0 || lo > n) continue;
+        if ((lo == 0 || v[lo - 1] < r) && (lo == n || v[lo] >= r)) return lo;
+      }
+    }
+  }
+  int lo = 0, hi = n;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
     if (v[mid] < r) lo = mid + 1; else hi = mid;
   }
+  return lo;
+}
+__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r, double v0 = 0.0,
+                                                 double inv_d = 0.0) {
+  const int lo = lower_bound_axis(v, n, r, v0, inv_d);
   int best;
   if (lo == 0) best = 0;
   else if (lo == n) best = n - 1;
@@ -254,7 +298,7 @@ __device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, i
   while (best > 0 && fabs(v[best - 1] - r) == bv) best--;
   return best + 1;
 }
-__device__ __forceinline__ int minloc_abs_linear(const double* __restrict__ v, int n, double r) {
+static __device__ __noinline__ int minloc_abs_linear(const double* __restrict__ v, int n, double r) {
   int best = 0;
   double bv = fabs(v[0] - r);
   for (int i = 1; i < n; i++) {
@@ -273,40 +317,50 @@ struct Best {
 #ifndef MAP_MIN_BLOCKS
 #define MAP_MIN_BLOCKS 6
 #endif
+template <bool SEP>
 __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
                                             int j2, Best& b, int ic, int jc) {
   // MINLOC = lexicographic minimum of (distance, column-major position).  The window centre (ic,jc) -- the
   // index-nearest point, almost always the winner or next to it -- is evaluated first, so that nearly every other
   // candidate is rejected by the dot-product margin without an acos; ties are still resolved by position, which
   // makes the result independent of the evaluation order.
-  b.d = 0.0; b.pds = -4.0; b.i = 0; b.j = 0;
   ic = min(max(ic, i1), i2);
   jc = min(max(jc, j1), j2);
-  {
-    double vx, vy, vz;
-    src_vec(sg, ic, jc, vx, vy, vz);
-    double zpds = ux * vx + uy * vy + uz * vz;
-    b.d = G_ZR * pm_acos(fmin(zpds, 1.0));
-    b.pds = zpds; b.i = ic; b.j = jc;
-  }
-  if (sg.separable && (i2 - i1) < 9) {
+  if (SEP) {  // callers guarantee i2 - i1 <= 8 (the EASY 9x9 window)
     // Regular source: u.v = clat_j*(ux*clon_i + uy*slon_i) + uz*slat_j up to ~4e-16 of rounding.  That cheap form
     // (2 flops per candidate) is only used to REJECT (with the margin widened by 1e-14, 20x its error); survivors are
     // re-evaluated in the reference's own operation order before any comparison that decides the result.
+    // A whole row is rejected at once through the largest cheap form it can hold (rounding is monotone, so
+    // cl*amax + c0 -- or cl*amin + c0 on the virtual row beyond the pole where cl < 0 -- IS that maximum).
+    // Pass 0 is the centre alone (it seeds the running best); passes 1.. are the rows j1..j2.  One code copy of
+    // the exact evaluation (acos) serves both: the kernel is instruction-cache bound.
     double a[9];
+    double amax = -4.0, amin = 4.0;
 #pragma unroll
     for (int q = 0; q < 9; q++) {
       int ji = min(i1 + q, i2);
       a[q] = ux * sg.clon[ji - 1] + uy * sg.slon[ji - 1];
+      amax = fmax(amax, a[q]); amin = fmin(amin, a[q]);
     }
-    for (int jj = j1; jj <= j2; jj++) {
+    b.d = 1.0e300; b.pds = -4.0; b.i = 0; b.j = 0;
+    const int nq = i2 - i1 + 1;
+    for (int pass = 0; pass <= j2 - j1 + 1; pass++) {
+      const int jj = (pass == 0) ? jc : j1 + pass - 1;
       const double cl = sg.clat[jj - 1], sl = sg.slat[jj - 1];
       const double c0 = uz * sl;
+      const double thr = b.pds - (PDS_MARGIN + 1.0e-14);
+      unsigned surv = 0;
+      if (pass == 0) surv = 1u << (ic - i1);
+      else if (!(((cl >= 0.0) ? cl * amax : cl * amin) + c0 < thr)) {
 #pragma unroll
-      for (int q = 0; q < 9; q++) {
+        for (int q = 0; q < 9; q++)
+          if (q < nq && !(cl * a[q] + c0 < thr)) surv |= 1u << q;
+        if (jj == jc) surv &= ~(1u << (ic - i1));  // the centre is already in the running best
+      }
+      while (surv) {
+        const int q = __ffs(surv) - 1;
+        surv &= surv - 1;
         const int ji = i1 + q;
-        if (ji > i2) break;
-        if (cl * a[q] + c0 < b.pds - (PDS_MARGIN + 1.0e-14)) continue;
         double zpds = ux * (sg.clon[ji - 1] * cl) + uy * (sg.slon[ji - 1] * cl) + uz * sl;
         if (zpds < b.pds - PDS_MARGIN) continue;
         double d = G_ZR * pm_acos(fmin(zpds, 1.0));
@@ -315,6 +369,14 @@ __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double
       }
     }
     return;
+  }
+  b.d = 0.0; b.pds = -4.0; b.i = 0; b.j = 0;
+  {
+    double vx, vy, vz;
+    src_vec(sg, ic, jc, vx, vy, vz);
+    double zpds = ux * vx + uy * vy + uz * vz;
+    b.d = G_ZR * pm_acos(fmin(zpds, 1.0));
+    b.pds = zpds; b.i = ic; b.j = jc;
   }
   for (int jj = j1; jj <= j2; jj++) {
     for (int ji = i1; ji <= i2; ji++) {
@@ -338,8 +400,22 @@ struct MapOut {
 };
 
 // body of the target loop of MAPPING_BL, src/mod_bilin_2d.f90:459-634
+// DISTANCE(xP, lonP, yP, latP) (:549), general form, kept out of line (code size: the kernel is instruction-cache bound).
+// The unit vectors are pure functions of (lon, lat): the target's is reused when the search computed it for the same xP,
+// the source table entry when MOD() left the longitude unchanged.
+static __device__ __noinline__ float dnp_noinline(const SrcGeom& sg, double xP, double yP, double lonP, double latP, int iP, int jP,
+                                           bool have_u, double ux0, double uy0, double uz0) {
+  double ux, uy, uz, vx, vy, vz;
+  if (have_u) { ux = ux0; uy = uy0; uz = uz0; } else unit_vec(xP, yP, ux, uy, uz);
+  if (lonP == src_lon(sg, iP, jP)) src_vec(sg, iP, jP, vx, vy, vz); else unit_vec(lonP, latP, vx, vy, vz);
+  double zpds = ux * vx + uy * vy + uz * vz;
+  return (zpds >= 1.0) ? 0.f : (float)(G_ZR * pm_acos(zpds));
+}
+
+template <bool SEP>
 __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP, double yP, int iP, int jP, MapOut& o,
-                                         int* err, bool have_u = false, double ux0 = 0.0, double uy0 = 0.0, double uz0 = 0.0) {
+                                         int* err, bool have_u = false, double ux0 = 0.0, double uy0 = 0.0, double uz0 = 0.0,
+                                         double best_pds = 0.0, double best_d = 0.0) {
   o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
   const int nxi = sg.nx, nyi = sg.nyw;
   if (!((iP != (int)G_RMV) && (jP != (int)G_RMV) && (jP < nyi))) return;
@@ -355,10 +431,17 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
   xP = d_mod(xP, 360.0);
   double ya = src_merc(sg, iP, jP);
   double hP = d_heading_y(lonP, xP, ya, d_merc(yP));
-  double hN = d_heading_y(lonP, lonN, ya, src_merc(sg, iP, jPp1));
-  double hE = d_heading_y(lonP, lonE, ya, src_merc(sg, iPp1, jP));
-  double hS = d_heading_y(lonP, lonS, ya, src_merc(sg, iP, jPm1));
-  double hW = d_heading_y(lonP, lonW, ya, src_merc(sg, iPm1, jP));
+  double hN, hE, hS, hW;
+  if (SEP) {
+    // regular source: lonN == lonS == lonP and the E/W neighbours share the row's ordinate, so these four are
+    // functions of jP (N, S) or iP (E, W) alone -- read from the tables k_heading_tables built with this very function
+    hN = sg.hN[jP - 1]; hE = sg.hE[iP - 1]; hS = sg.hS[jP - 1]; hW = sg.hW[iP - 1];
+  } else {
+    hN = d_heading_y(lonP, lonN, ya, src_merc(sg, iP, jPp1));
+    hE = d_heading_y(lonP, lonE, ya, src_merc(sg, iPp1, jP));
+    hS = d_heading_y(lonP, lonS, ya, src_merc(sg, iP, jPm1));
+    hW = d_heading_y(lonP, lonW, ya, src_merc(sg, iPm1, jP));
+  }
   int iqdrn = 4;
   double hPp = d_degE_to_degWE(hP);
   if (hN > hE) hN = hN - 360.0;
@@ -372,11 +455,13 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
   {
     // DISTANCE(xP, lonP, yP, latP) (:549).  The unit vectors are pure functions of (lon, lat): reuse the target's
     // (computed by the search for the same xP) and the source table entry when MOD() left the longitudes unchanged.
-    double ux, uy, uz, vx, vy, vz;
-    if (have_u) { ux = ux0; uy = uy0; uz = uz0; } else unit_vec(xP, yP, ux, uy, uz);
-    if (lonP == src_lon(sg, iP, jP)) src_vec(sg, iP, jP, vx, vy, vz); else unit_vec(lonP, latP, vx, vy, vz);
-    double zpds = ux * vx + uy * vy + uz * vz;
-    o.dnp = (zpds >= 1.0) ? 0.f : (float)(G_ZR * pm_acos(zpds));
+    if (SEP && have_u && (lonP == src_lon(sg, iP, jP))) {
+      // the search's winning dot product was formed from these very unit vectors in this very order, and its
+      // distance is zr*ACOS(MIN(pds,1)): DISTANCE differs only by returning 0 when pds >= 1
+      o.dnp = (best_pds >= 1.0) ? 0.f : (float)best_d;
+    } else {
+      o.dnp = dnp_noinline(sg, xP, yP, lonP, latP, iP, jP, have_u, ux0, uy0, uz0);
+    }
   }
   int icpt = 0;
   bool lagain = true;
@@ -442,6 +527,7 @@ __device__ __forceinline__ void map_store(const MapOut& o, int iP, int jP, int m
 
 // ---------------------------------------------------------------------------------------------------
 // EASY search (src/mod_manip.f90:967-1069) fused with the MAPPING_BL body: one thread per target.
+template <bool SEP>
 __global__ void __launch_bounds__(128, MAP_MIN_BLOCKS)
 k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
            const double* __restrict__ vlat, int sorted_lon, int sorted_lat, int jlo, int jhi, int32_t* MT, double* AB,
@@ -453,23 +539,23 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
     int m = mask ? mask[k] : 1;
     int iP = -1, jP = -1;
     double rlon = trg_lon(tg, ji_t, jj_t), rlat = trg_lat(tg, ji_t, jj_t);
-    double ux = 0.0, uy = 0.0, uz = 0.0;
+    double ux = 0.0, uy = 0.0, uz = 0.0, bpds = 0.0, bd = 0.0;
     bool have_u = false;
     if (m == 1 && jj_t >= jlo && jj_t <= jhi) {
-      int ip = sorted_lon ? minloc_abs_sorted(vlon, sg.nx, rlon) : minloc_abs_linear(vlon, sg.nx, rlon);
-      int jp = sorted_lat ? minloc_abs_sorted(vlat, sg.nyw, rlat) : minloc_abs_linear(vlat, sg.nyw, rlat);
+      int ip = sorted_lon ? minloc_abs_sorted(vlon, sg.nx, rlon, sg.lon0, sg.inv_dlon) : minloc_abs_linear(vlon, sg.nx, rlon);
+      int jp = sorted_lat ? minloc_abs_sorted(vlat, sg.nyw, rlat, sg.lat0, sg.inv_dlat) : minloc_abs_linear(vlat, sg.nyw, rlat);
       int i1s = max(ip - 4, 1), i2s = min(ip + 4, sg.nx);
       int j1s = max(jp - 4, 1), j2s = min(jp + 4, sg.nyw);
       unit_vec(rlon, rlat, ux, uy, uz);
       have_u = (fabs(rlon) < 360.0);   // MOD(xP,360) == xP: the body's DISTANCE sees the same longitude
       Best b;
-      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, ip, jp);
-      iP = b.i; jP = b.j;
+      scan_window<SEP>(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, ip, jp);
+      iP = b.i; jP = b.j; bpds = b.pds; bd = b.d;
       if (iP == 0 || jP == 0) atomicOr(err, 2);
     }
     MapOut o;
     o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
-    if (m == 1) map_body(sg, k_ew, rlon, rlat, iP, jP, o, err, have_u, ux, uy, uz);
+    if (m == 1) map_body<SEP>(sg, k_ew, rlon, rlat, iP, jP, o, err, have_u, ux, uy, uz, bpds, bd);
     map_store(o, iP, jP, m, k, nt, MT, AB, IDP, DNP);
   }
 }
@@ -485,7 +571,7 @@ k_map_body(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
     int iP = JI[k], jP = JJ[k];
     MapOut o;
     o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
-    if (m == 1) map_body(sg, k_ew, trg_lon(tg, ji_t, jj_t), trg_lat(tg, ji_t, jj_t), iP, jP, o, err);
+    if (m == 1) map_body<false>(sg, k_ew, trg_lon(tg, ji_t, jj_t), trg_lat(tg, ji_t, jj_t), iP, jP, o, err);
     map_store(o, iP, jP, m, k, nt, MT, AB, IDP, DNP);
   }
 }
@@ -657,7 +743,7 @@ k_twisted_chain(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__
       int i1s = max(pr.x - 5, 1), i2s = min(pr.x + 5, sg.nx);
       int j1s = max(pr.y - 5, 1), j2s = min(pr.y + 5, sg.nyw);
       Best b;
-      scan_window(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, pr.x, pr.y);
+      scan_window<false>(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, pr.x, pr.y);
       if (b.i != 0) {
         size_t ks = (size_t)(b.i - 1) + (size_t)(b.j - 1) * sg.nx;
         double emax = fmax(tp.e1[ks], tp.e2[ks]) / 1000.0 * tp.sqrt2f;
@@ -746,6 +832,10 @@ int bilin_prepare_src(sosie_ctx* ctx) {
     sg.separable = 1;
     sg.lon1 = Xin; sg.lat1 = ctx->s_lat1.p;
     sg.clon = ctx->s_clon.p; sg.slon = ctx->s_slon.p; sg.clat = ctx->s_clat.p; sg.slat = ctx->s_slat.p;
+    CK(ctx->s_head.alloc(2 * (size_t)nx + 2 * (size_t)nyw));
+    double* hd = ctx->s_head.p;
+    k_heading_tables<<<cdiv(nx + nyw, 128), 128, 0, st>>>(sg, ctx->k_ew, hd, hd + nx, hd + 2 * nx, hd + 2 * nx + nyw); KLAUNCH_CHECK();
+    sg.hE = hd; sg.hW = hd + nx; sg.hN = hd + 2 * nx; sg.hS = hd + 2 * nx + nyw;
   } else {
     size_t n = (size_t)nx * nyw;
     CK(ctx->s_X.alloc(n)); CK(ctx->s_Y.alloc(n)); CK(ctx->s_vx.alloc(n)); CK(ctx->s_vy.alloc(n)); CK(ctx->s_vz.alloc(n));
@@ -855,9 +945,19 @@ int bilin_map_impl(sosie_ctx* ctx) {
     int jlo = j_strt_t < j_stop_t ? j_strt_t : j_stop_t, jhi = j_strt_t < j_stop_t ? j_stop_t : j_strt_t;
     size_t k0, kcnt;
     shard_range(ctx, &k0, &kcnt);
+    sg.lon0 = sg.inv_dlon = sg.lat0 = sg.inv_dlat = 0.0;
+    if (sorted_lon && hax[sg.nx - 1] > hax[0]) { sg.lon0 = hax[0]; sg.inv_dlon = (double)(sg.nx - 1) / (hax[sg.nx - 1] - hax[0]); }
+    if (sorted_lat && hax[sg.nx + sg.nyw - 1] > hax[sg.nx]) {
+      sg.lat0 = hax[sg.nx]; sg.inv_dlat = (double)(sg.nyw - 1) / (hax[sg.nx + sg.nyw - 1] - hax[sg.nx]);
+    }
     prof_begin(ctx, SOSIE_T_MAP);
-    k_map_easy<<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
-                                                             sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p, k0, kcnt); KLAUNCH_CHECK();
+    if (sg.separable)
+      k_map_easy<true><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
+                                                                   sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p, k0, kcnt);
+    else
+      k_map_easy<false><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
+                                                                    sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p, k0, kcnt);
+    KLAUNCH_CHECK();
     prof_end(ctx, SOSIE_T_MAP);
   } else {
     // ---- FIND_NEAREST_TWISTED

@@ -59,6 +59,14 @@ struct SrcGeom {
   const double* vy = nullptr;
   const double* vz = nullptr;
   const double* merc = nullptr;  // Mercator ordinate of heading() per source latitude: [nyw] (separable) or [nx*nyw]
+  // separable only: the four neighbour headings of MAPPING_BL (:512-515) depend on the column (E, W) or the row
+  // (N, S) of the nearest point alone; tabulated once per grid with the same device function (identical bits)
+  const double* hE = nullptr;    // [nx]
+  const double* hW = nullptr;    // [nx]
+  const double* hN = nullptr;    // [nyw]
+  const double* hS = nullptr;    // [nyw]
+  // uniform-axis hints of the EASY bracket search (0 = none): index guess = (r - v0) * inv_d, verified exactly
+  double lon0 = 0.0, inv_dlon = 0.0, lat0 = 0.0, inv_dlat = 0.0;
 };
 
 struct TrgGeom {
@@ -87,7 +95,7 @@ struct sosie_ctx {
   bool ev_used[SOSIE_T_COUNT] = {};
   SrcGeom sg;
   TrgGeom tg;
-  DBuf<double> s_lon1, s_lat1, s_clon, s_slon, s_clat, s_slat, s_X, s_Y, s_vx, s_vy, s_vz, s_merc;
+  DBuf<double> s_lon1, s_lat1, s_clon, s_slon, s_clat, s_slat, s_X, s_Y, s_vx, s_vy, s_vz, s_merc, s_head;
   DBuf<double> s_in_X, s_in_Y;   // uploaded (or borrowed) raw source coordinates
   DBuf<double> t_X, t_Y;
   DBuf<int32_t> t_mask;          // mask_domain_trg as modified by the search

@@ -79,9 +79,10 @@ __device__ __forceinline__ double src_merc(const SrcGeom& g, int i, int j) {
   return g.separable ? g.merc[j - 1] : g.merc[(size_t)(i - 1) + (size_t)(j - 1) * g.nx];
 }
 // MOD(a, p) for reals; exact shortcut when |a| < p (the common case: longitudes already in [0,360))
+static __device__ __noinline__ double d_fmod_slow(double a, double p) { return fmod(a, p); }  // out of line: code size
 __device__ __forceinline__ double d_mod(double a, double p) {
   if (fabs(a) < p) return a;
-  return fmod(a, p);
+  return d_fmod_slow(a, p);
 }
 
 // heading, src/mod_bilin_2d.f90:818-870 (ya passed in: it is shared by the five calls at :511-515)
