@@ -396,12 +396,10 @@ def run_ours(args):
         return C.c_void_p(t.data_ptr())
 
     def step_host():
-        first.value = 1
-        rc = lib.sosie_bilin_2d(ctx._h, int(cfg["ewper_src"]), nx1, ny1, vp(lon_s), vp(lat_s), 1, vp(Z1_host), nx2, ny2, vp(Xt), vp(Yt), 0,
-                                vp(Z2_host), None, 1, 0, C.byref(first), 0, 1)
-        ctx._ck(rc)
-        rc = lib.sosie_bilin_get_map(ctx._h, vp(map_host["metrics"]), vp(map_host["alphabeta"]), vp(map_host["ipb"]),
-                                     vp(map_host["dist_np"]), None)
+        # what the reference's first BILIN_2D call does end to end: MAPPING_BL -> (mapping for P2D_MAPPING_AB) -> apply
+        rc = lib.sosie_bilin_2d_first(ctx._h, int(cfg["ewper_src"]), nx1, ny1, vp(lon_s), vp(lat_s), 1, vp(Z1_host), nx2, ny2, vp(Xt), vp(Yt), 0,
+                                      vp(Z2_host), None, 1, 0, 1, vp(map_host["metrics"]), vp(map_host["alphabeta"]),
+                                      vp(map_host["ipb"]), vp(map_host["dist_np"]))
         ctx._ck(rc)
 
     e2e_steps = max(1, min(args.steps, 5))
@@ -416,10 +414,18 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    h2d = 8 * (nx1 + ny1) + 2 * 8 * nt + 4 * nx1 * ny1
-    d2h = 4 * nt + (3 * 4 + 2 * 8 + 2 + 4) * nt
+    info = ctx.bilin_get_map_info()
+    src_rows = ctx.src_rows()
+    nrow_src = max(0, src_rows[1] - src_rows[0] + 1)
+    # bytes actually copied by the pipelined first call on this rank (csrc/bilin_pipeline.cu): both coordinate arrays
+    # of the rank's target rows + the whole latitude array (search prelude) + the source rows its mapping reads
+    h2d = 8 * (nx1 + ny1) + 8 * my_targets + 8 * nt + 4 * nx1 * nrow_src
+    d2h = 4 * my_targets + (3 * 4 + 2 * 8 + 2 + 4) * my_targets
     e2e = {"value": nt / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-           "note": "per rank: full coordinates + source slab in, result + full mapping (for P2D_MAPPING_AB) out"}
+           "source_rows_uploaded": [int(src_rows[0]) + 1, int(src_rows[1]) + 1, ny1],
+           "note": "sosie_bilin_2d_first from pinned host arrays, per rank: target coordinates + the source rows the mapping "
+                   "reads in; interpolated field + mapping (metrics, alpha/beta, iproblem, dist_np: what P2D_MAPPING_AB "
+                   "writes) out; H2D | kernels | D2H pipelined over blocks of target rows"}
 
     # sanity: the timed device path and the host path produce the same field on this rank's rows
     d_chk = d_Z2[r0 - 1:r1].cpu()

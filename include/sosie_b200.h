@@ -20,6 +20,7 @@
 #ifndef SOSIE_B200_H
 #define SOSIE_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -83,7 +84,8 @@ int sosie_bilin_set_grids_dev(sosie_ctx* ctx, int32_t k_ew_per,
  * ID_problem(nx2,ny2) and distance_to_np(nx2,ny2), and keeps them cached in the context.          */
 int sosie_bilin_map(sosie_ctx* ctx);
 /* copy the cached mapping to host arrays (what P2D_MAPPING_AB, src/io_ezcdf.f90:2195, writes).
- * Any pointer may be NULL.  mask_out receives mask_domain_trg as modified by the search (-1/-2). */
+ * Any pointer may be NULL.  mask_out receives mask_domain_trg as modified by the search (-1/-2).
+ * A sharded context (sosie_bilin_set_shard) copies only its own target rows; the others are left untouched. */
 int sosie_bilin_get_map(sosie_ctx* ctx, int32_t* metrics, double* alphabeta, int16_t* id_problem,
                         float* dist_np, int32_t* mask_out);
 /* load a mapping read by RD_MAPPING_AB (src/io_ezcdf.f90:2280) instead of building it; may be called
@@ -121,6 +123,29 @@ int sosie_bilin_2d(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t ny1, c
                    const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
                    const int32_t* mask_domain_trg, int32_t l_reg_src, int32_t i_orca_trg,
                    int32_t* l_first_call, int32_t have_mapping, int32_t nslab);
+
+/* the FIRST call of BILIN_2D with MAPPING_BL's products handed back in the same call -- what the reference's first
+ * call does end to end: MAPPING_BL (:196) -> P2D_MAPPING_AB writes metrics / alphabeta / iproblem / dist_np
+ * (src/mod_bilin_2d.f90:686, src/io_ezcdf.f90:2195) -> apply loop (:209).  metrics(nx2,ny2,3), alphabeta(nx2,ny2,2),
+ * id_problem(nx2,ny2), dist_np(nx2,ny2): any may be NULL.  With a regular source given as 1-D axes and a 2-D target
+ * the call is a three-stream pipeline (coordinate upload | search+weights per block of target rows | mapping download,
+ * then only the source rows the mapping reads are uploaded and applied): see csrc/bilin_pipeline.cu.  Host arrays
+ * should be page-locked (sosie_host_register) for the copies to overlap.  Equivalent to
+ * sosie_bilin_2d(first call) + sosie_bilin_get_map; a sharded context fills only its target rows.                 */
+int sosie_bilin_2d_first(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t ny1, const double* X10,
+                         const double* Y10, int32_t src_1d, const float* Z1, int32_t nx2, int32_t ny2,
+                         const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
+                         const int32_t* mask_domain_trg, int32_t l_reg_src, int32_t i_orca_trg, int32_t nslab,
+                         int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np);
+/* rows[0..1] = first / last physical source row (0-based) read by this context's packed mapping records: the
+ * host-pointer apply paths upload only those rows of every slab (a regional target touches part of a global slab) */
+int sosie_bilin_src_rows(sosie_ctx* ctx, int32_t* rows);
+/* first calls with fewer targets than n take the sequential path (default 2^20; tests set 0 to force the pipeline) */
+int sosie_set_pipeline_min_targets(sosie_ctx* ctx, int64_t n);
+/* page-lock / release a caller-owned host array (cudaHostRegister): the Fortran shim pins the arrays it passes
+ * repeatedly (coordinates, record buffers) so that the library's copies run asynchronously at full PCIe speed   */
+int sosie_host_register(void* p, size_t bytes);
+int sosie_host_unregister(void* p);
 
 /* scalar INTERP_BL(k_ew_per, jiP, jjP, iqd, xa, xb, Z_in) for n trajectory points
  * (src/mod_bilin_2d.f90:275; callers src/interp_to_ground_track.f90:750): host pointers.           */

@@ -37,7 +37,8 @@ EXPORTS = [
     "sosie_bilin_load_map", "sosie_bilin_map_info", "sosie_bilin_apply", "sosie_bilin_apply_dev", "sosie_bilin_apply_ex_dev",
     "sosie_bilin_apply_uv_dev", "sosie_bilin_2d", "sosie_interp_bl", "sosie_akima_set_grids", "sosie_akima_apply",
     "sosie_akima_apply_dev", "sosie_akima_get_ixy", "sosie_bdrown", "sosie_bdrown_dev", "sosie_bdrown_force_general", "sosie_smoother", "sosie_drown",
-    "sosie_rotate_uv", "sosie_rotate_uv_dev",
+    "sosie_rotate_uv", "sosie_rotate_uv_dev", "sosie_bilin_2d_first", "sosie_set_pipeline_min_targets",
+    "sosie_host_register", "sosie_host_unregister", "sosie_bilin_src_rows",
 ]
 
 _lib = None
@@ -186,6 +187,17 @@ class Sosie:
         self._ck(self._lib.sosie_bilin_map_info(self._h, _p(info)))
         return dict(metrics=met, alphabeta=ab, ipb=ipb, dist_np=dnp, mask=msk, info=info)
 
+    def bilin_get_map_info(self):
+        info = np.zeros(8, np.int32)
+        self._ck(self._lib.sosie_bilin_map_info(self._h, _p(info)))
+        return info
+
+    def src_rows(self):
+        """(lo, hi), 0-based inclusive: physical source rows the packed mapping records of this shard read"""
+        r = np.zeros(2, np.int32)
+        self._ck(self._lib.sosie_bilin_src_rows(self._h, _p(r)))
+        return int(r[0]), int(r[1])
+
     def bilin_load_map(self, metrics, alphabeta, ipb=None):
         met, ab = _i32(metrics), _f64(alphabeta)
         ny2, nx2 = met.shape[1], met.shape[2]
@@ -233,6 +245,35 @@ class Sosie:
                                           C.byref(first), int(have_mapping), Z1.shape[0]))
         self.l_first_call_interp_routine = bool(first.value)
         return Z2
+
+    def bilin_2d_first(self, k_ew_per, X10, Y10, Z1, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0):
+        """first call of BILIN_2D with MAPPING_BL's products returned in the same call (pipelined for a regular
+        1-D source and a 2-D target): returns (Z2, mapping dict).  Rows outside this context's shard are zero."""
+        X10, Y10, X20, Y20 = _f64(X10), _f64(Y10), _f64(X20), _f64(Y20)
+        Z1 = _f32(Z1)
+        if Z1.ndim == 2:
+            Z1 = Z1[None]
+        src_1d, trg_1d = X10.ndim == 1, X20.ndim == 1
+        nx1, ny1 = (X10.size, Y10.size) if src_1d else (X10.shape[1], X10.shape[0])
+        nx2, ny2 = (X20.size, Y20.size) if trg_1d else (X20.shape[1], X20.shape[0])
+        self._shape = (nx1, ny1, nx2, ny2)
+        m = None if mask_domain_trg is None else _i32(mask_domain_trg)
+        Z2 = np.zeros((Z1.shape[0], ny2, nx2), np.float32)
+        met = np.zeros((3, ny2, nx2), np.int32)
+        ab = np.zeros((2, ny2, nx2), np.float64)
+        ipb = np.zeros((ny2, nx2), np.int16)
+        dnp = np.zeros((ny2, nx2), np.float32)
+        self._ck(self._lib.sosie_bilin_2d_first(self._h, int(k_ew_per), nx1, ny1, _p(X10), _p(Y10), int(src_1d), _p(Z1), nx2, ny2,
+                                                _p(X20), _p(Y20), int(trg_1d), _p(Z2), _p(m), int(l_reg_src), int(i_orca_trg),
+                                                Z1.shape[0], _p(met), _p(ab), _p(ipb), _p(dnp)))
+        self.l_first_call_interp_routine = False
+        info = np.zeros(8, np.int32)
+        self._ck(self._lib.sosie_bilin_map_info(self._h, _p(info)))
+        return Z2, dict(metrics=met, alphabeta=ab, ipb=ipb, dist_np=dnp, info=info)
+
+    def set_pipeline_min_targets(self, n: int):
+        """first calls with fewer targets take the sequential path (tests pass 0 to force the pipeline)"""
+        self._ck(self._lib.sosie_set_pipeline_min_targets(self._h, C.c_int64(int(n))))
 
     def interp_bl(self, k_ew_per, jiP, jjP, iqd, xa, xb, Z_in):
         Z = _f32(Z_in)

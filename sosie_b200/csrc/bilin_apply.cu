@@ -366,19 +366,68 @@ __global__ void k_sect_write(float* Z, int nx, int n, int l0, int ls, int jl, co
 }
 
 // ---------------------------------------------------------------------------------------------------
-int bilin_pack_impl(sosie_ctx* ctx) {
-  if (!ctx->map_ready) { ctx->err = "bilinear mapping neither built nor loaded"; return SOSIE_ERR_STATE; }
+int bilin_pack_range(sosie_ctx* ctx, size_t k0, size_t kcnt) {
   const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
   if ((size_t)ctx->sg.nx * ctx->sg.nyw > 2147483647ULL) { ctx->err = "source slab too large for 32-bit offsets"; return SOSIE_ERR_ARG; }
   CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt));
+  if (kcnt == 0) return SOSIE_OK;
+  k_pack<<<grid_for(ctx, kcnt, 256), 256, 0, ctx->stream>>>(ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p, ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p, k0, kcnt);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
+
+int bilin_pack_impl(sosie_ctx* ctx) {
+  if (!ctx->map_ready) { ctx->err = "bilinear mapping neither built nor loaded"; return SOSIE_ERR_STATE; }
   size_t k0, kcnt;
   shard_range(ctx, &k0, &kcnt);
   prof_begin(ctx, SOSIE_T_PACK);
-  k_pack<<<grid_for(ctx, kcnt, 256), 256, 0, ctx->stream>>>(ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p, ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p, k0, kcnt);
-  KLAUNCH_CHECK();
+  if (int rc = bilin_pack_range(ctx, k0, kcnt)) return rc;
   prof_end(ctx, SOSIE_T_PACK);
   ctx->pack_ready = true;
+  ctx->pack_gen++;
   ctx->boxes_ready = false;
+  return SOSIE_OK;
+}
+
+// rows (0-based, physical) of the source slab that the packed records [k0, k0+kcnt) read: the host-pointer paths
+// upload only those (a regional target touches a fraction of a global slab).  The virtual pole rows read rows
+// ny-2 and ny-1 (zget).  row_lo > row_hi: nothing is read (all records constant).
+__global__ void k_src_rowrange(const int4* __restrict__ pidx, size_t k0, size_t kcnt, int nx, int ny, int* out) {
+  int lo = 2147483647, hi = -1;
+  const int nreal = nx * ny;
+  for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < kcnt; kk += (size_t)gridDim.x * blockDim.x) {
+    const int4 id = pidx[k0 + kk];
+    int c[4] = {id.x, id.y, id.z, id.w};
+    int n = 4;
+    if (id.x == REC_COPY) { c[0] = id.y; n = 1; }
+    else if (id.x < 0) n = 0;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (q >= n) break;
+      if (c[q] >= nreal) { lo = min(lo, ny - 2); hi = max(hi, ny - 1); }
+      else { int r = c[q] / nx; lo = min(lo, r); hi = max(hi, r); }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMin(&out[0], lo); atomicMax(&out[1], hi); }
+}
+
+__global__ void k_rowrange_init(int* out) { out[0] = 2147483647; out[1] = -1; }
+
+int bilin_src_rowrange(sosie_ctx* ctx, size_t k0, size_t kcnt, int* row_lo, int* row_hi) {
+  CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
+  int* d = ctx->d_iscratch.p + 2;
+  k_rowrange_init<<<1, 1, 0, ctx->stream>>>(d); KLAUNCH_CHECK();
+  if (kcnt > 0) {
+    k_src_rowrange<<<grid_for(ctx, kcnt, 256), 256, 0, ctx->stream>>>(ctx->d_pidx.p, k0, kcnt, ctx->sg.nx, ctx->sg.ny, d);
+    KLAUNCH_CHECK();
+  }
+  int h[2];
+  if (int rc = fetch_small(ctx, d, h, sizeof(h))) return rc;
+  *row_lo = h[0]; *row_hi = h[1];
   return SOSIE_OK;
 }
 
@@ -463,8 +512,7 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
       DBuf<float> dm; CK(dm.alloc(1));
       k_lastrow_mean<<<1, 1, 0, ctx->stream>>>(dZ2, ctx->tg.nx, ctx->tg.ny, dm.p); KLAUNCH_CHECK();
       float hm;
-      CK(cudaMemcpyAsync(&hm, dm.p, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-      CK(cudaStreamSynchronize(ctx->stream));
+      if (int rc = fetch_small(ctx, dm.p, &hm, sizeof(float))) return rc;
       double rmeanv = (double)hm;
       ctx->l_last_y_row_missing = ((rmeanv < G_RMV + (double)0.1f) && (rmeanv > G_RMV - (double)0.1f)) ? 1 : 0;
     }

@@ -59,12 +59,13 @@ __global__ void k_minmax(const double* __restrict__ a, size_t n, unsigned long l
 }
 
 // L_IS_GRID_REGULAR (src/mod_manip.f90:1632-1663), both tests, on a 2-D (nx,ny) pair
-__global__ void k_is_regular(const double* __restrict__ X, const double* __restrict__ Y, int nx, int ny, int* irreg) {
+__global__ void k_is_regular(const double* __restrict__ X, const double* __restrict__ Y, int nx, int ny, int ja, int jb,
+                             int* irreg) {
   const double tol = (double)1.E-12f;
   __shared__ double sh[32];
   __shared__ int stop;
   // a/ one block per row jj>=2 : SUM(ABS(Xlon(:,jj)-Xlon(:,1)))
-  for (int jj = 2 + blockIdx.x; jj <= ny; jj += gridDim.x) {
+  for (int jj = ja + blockIdx.x; jj <= jb; jj += gridDim.x) {   // all rows: ja = 2, jb = ny
     // the reference EXITs at the first irregular row (:1651): stop early, block-uniformly
     if (threadIdx.x == 0) stop = *(volatile int*)irreg;
     __syncthreads();
@@ -781,11 +782,26 @@ __global__ void k_twisted_mask(const int32_t* __restrict__ JI, const int32_t* __
 
 // ===================================================================================================
 // host orchestration
-static int fetch_d(sosie_ctx* ctx, const double* dptr, double* out) {
-  CK(cudaMemcpyAsync(out, dptr, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
-  return 0;
+__global__ void k_to_mailbox(const unsigned char* __restrict__ src, unsigned char* dst, size_t n) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) dst[k] = src[k];
 }
+int fetch_small(sosie_ctx* ctx, const void* dsrc, void* hdst, size_t bytes) {
+  if (bytes == 0) return SOSIE_OK;
+  if (bytes > SOSIE_MAILBOX_BYTES) {
+    CK(cudaMemcpyAsync(hdst, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return SOSIE_OK;
+  }
+  if (!ctx->mailbox) CK(cudaHostAlloc((void**)&ctx->mailbox, SOSIE_MAILBOX_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
+  unsigned char* dmb = nullptr;
+  CK(cudaHostGetDevicePointer((void**)&dmb, ctx->mailbox, 0));
+  k_to_mailbox<<<bytes > 4096 ? 32 : 1, 256, 0, ctx->stream>>>((const unsigned char*)dsrc, dmb, bytes);
+  KLAUNCH_CHECK();
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(hdst, ctx->mailbox, bytes);
+  return SOSIE_OK;
+}
+static int fetch_d(sosie_ctx* ctx, const double* dptr, double* out) { return fetch_small(ctx, dptr, out, sizeof(double)); }
 
 // coordinate part of BILIN_2D's prologue (:97-148): decide l_add_extra_j, build the working source
 int bilin_prepare_src(sosie_ctx* ctx) {
@@ -850,12 +866,11 @@ int bilin_prepare_src(sosie_ctx* ctx) {
   if (ctx->l_add_extra_j) {
     CK(ctx->d_im.alloc(nx));
     const double* lonrow = in_1d ? Xin : Xin + (size_t)(ny - 1) * nx;
-    CK(ctx->d_iscratch.alloc(4));
+    CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
     CK(cudaMemsetAsync(ctx->d_iscratch.p + 1, 0, sizeof(int), st));
     k_check_sorted<<<cdiv(nx, 256), 256, 0, st>>>(lonrow, nx, ctx->d_iscratch.p + 1); KLAUNCH_CHECK();
     int unsorted = 0;
-    CK(cudaMemcpyAsync(&unsorted, ctx->d_iscratch.p + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (int rc = fetch_small(ctx, ctx->d_iscratch.p + 1, &unsorted, sizeof(int))) return rc;
     k_jim_table<<<cdiv(nx, 128), 128, 0, st>>>(lonrow, nx, unsorted ? 0 : 1, ctx->d_im.p); KLAUNCH_CHECK();
   }
   return SOSIE_OK;
@@ -866,37 +881,42 @@ static int is_sorted_host(const std::vector<double>& v, int off, int n) {
   return 1;
 }
 
-int bilin_map_impl(sosie_ctx* ctx) {
-  if (!ctx->grids_set) { ctx->err = "sosie_bilin_map: grids not set"; return SOSIE_ERR_STATE; }
+// ---- FIND_NEAREST_POINT prelude (:888-947): regularity tests, latitude ranges, target row range.
+// xrow_a..xrow_b (1-based, inclusive; 0,0 = all): rows of the target longitude array that are resident -- the
+// pipelined first call (bilin_pipeline.cu) uploads only row 1 and its shard's rows.  L_IS_GRID_REGULAR is then
+// evaluated on those rows; an irregular row settles it (any one does), otherwise *need_full_x is set and the
+// caller must complete the array and call again.
+int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool* need_full_x) {
   SrcGeom& sg = ctx->sg;
   TrgGeom& tg = ctx->tg;
   cudaStream_t st = ctx->stream;
   const size_t nt = (size_t)tg.nx * tg.ny;
   const size_t nsrc = (size_t)sg.nx * sg.nyw;
-  CK(ctx->d_metrics.alloc(3 * nt)); CK(ctx->d_ab.alloc(2 * nt)); CK(ctx->d_ipb.alloc(nt)); CK(ctx->d_dnp.alloc(nt));
+  if (need_full_x) *need_full_x = false;
   ctx->ws_cursor = 0;
-  CK(ctx->d_scratch.alloc(64)); CK(ctx->d_iscratch.alloc(4));
+  CK(ctx->d_scratch.alloc(64)); CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
   struct { Prelude* p; } dpre = {reinterpret_cast<Prelude*>(ctx->d_scratch.p)};
-  struct { int* p; } derr = {reinterpret_cast<int*>(ctx->d_iscratch.p)};
   static_assert(sizeof(Prelude) <= 64 * sizeof(double), "Prelude does not fit the scratch buffer");
-  CK(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
   k_prelude_init<<<1, 1, 0, st>>>(dpre.p); KLAUNCH_CHECK();
 
-  // ---- FIND_NEAREST_POINT prelude (:888-947)
   // y_min_s / y_max_s : MINVAL/MAXVAL(Ysrc) over the working array (pole rows included)
   if (sg.separable) { k_minmax<<<grid_for(ctx, sg.nyw, 256), 256, 0, st>>>(sg.lat1, sg.nyw, &dpre.p->ymin_s, &dpre.p->ymax_s); KLAUNCH_CHECK(); }
   else { k_minmax<<<grid_for(ctx, nsrc, 256), 256, 0, st>>>(sg.Y, nsrc, &dpre.p->ymin_s, &dpre.p->ymax_s); KLAUNCH_CHECK(); }
   { size_t nty = tg.is_1d ? (size_t)tg.ny : nt;
     k_minmax<<<grid_for(ctx, nty, 256), 256, 0, st>>>(tg.Y, nty, &dpre.p->ymin_t, &dpre.p->ymax_t); KLAUNCH_CHECK(); }
-  if (!sg.separable) { k_is_regular<<<grid_for(ctx, (size_t)sg.nyw * 32, 256), 256, 0, st>>>(sg.X, sg.Y, sg.nx, sg.nyw, &dpre.p->irreg_s); KLAUNCH_CHECK(); }
-  if (!tg.is_1d) { k_is_regular<<<grid_for(ctx, (size_t)tg.ny * 32, 256), 256, 0, st>>>(tg.X, tg.Y, tg.nx, tg.ny, &dpre.p->irreg_t); KLAUNCH_CHECK(); }
+  if (!sg.separable) { k_is_regular<<<grid_for(ctx, (size_t)sg.nyw * 32, 256), 256, 0, st>>>(sg.X, sg.Y, sg.nx, sg.nyw, 2, sg.nyw, &dpre.p->irreg_s); KLAUNCH_CHECK(); }
+  const bool partial_x = !tg.is_1d && xrow_a >= 1 && !(xrow_a <= 2 && xrow_b >= tg.ny);
+  if (!tg.is_1d) {
+    int ja = partial_x ? std::max(2, xrow_a) : 2, jb = partial_x ? xrow_b : tg.ny;
+    k_is_regular<<<grid_for(ctx, (size_t)tg.ny * 32, 256), 256, 0, st>>>(tg.X, tg.Y, tg.nx, tg.ny, ja, jb, &dpre.p->irreg_t); KLAUNCH_CHECK();
+  }
   if (tg.nx > 2) {
     k_rtmp<<<1, 1024, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
     k_min_dlat<<<grid_for(ctx, nt, 256), 256, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
   }
   Prelude hp;
-  CK(cudaMemcpyAsync(&hp, dpre.p, sizeof(Prelude), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (int rc = fetch_small(ctx, dpre.p, &hp, sizeof(Prelude))) return rc;
+  if (partial_x && hp.irreg_t == 0) { if (need_full_x) *need_full_x = true; return SOSIE_OK; }
   const double y_min_s = dec_d_host(hp.ymin_s), y_max_s = dec_d_host(hp.ymax_s);
   const double y_min_t = dec_d_host(hp.ymin_t), y_max_t = dec_d_host(hp.ymax_t);
   const bool l_is_reg_s = (hp.irreg_s == 0), l_is_reg_t = (hp.irreg_t == 0);
@@ -915,8 +935,7 @@ int bilin_map_impl(sosie_ctx* ctx) {
       k_jrange_idx<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, cmin.p, cmax.p, jn.p, jx.p); KLAUNCH_CHECK();
       k_jrange_fin<<<cdiv(tg.nx, 256), 256, 0, st>>>(tg.nx, jn.p, jx.p, dpre.p); KLAUNCH_CHECK();
     }
-    CK(cudaMemcpyAsync(&hp, dpre.p, sizeof(Prelude), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (int rc = fetch_small(ctx, dpre.p, &hp, sizeof(Prelude))) return rc;
     j_strt_t = hp.j_strt; j_stop_t = hp.j_stop;
     if (j_strt_t > j_stop_t) jlat_icr = -1;
     if (j_strt_t < 1 || j_strt_t > tg.ny || j_stop_t < 1 || j_stop_t > tg.ny) {
@@ -926,6 +945,72 @@ int bilin_map_impl(sosie_ctx* ctx) {
   }
   ctx->map_info[0] = j_strt_t; ctx->map_info[1] = j_stop_t; ctx->map_info[2] = jlat_icr;
   ctx->map_info[3] = l_is_reg_s; ctx->map_info[4] = l_is_reg_t; ctx->map_info[6] = 0; ctx->map_info[7] = ctx->l_add_extra_j;
+  pl->j_strt = j_strt_t; pl->j_stop = j_stop_t; pl->icr = jlat_icr;
+  pl->jlo = j_strt_t < j_stop_t ? j_strt_t : j_stop_t; pl->jhi = j_strt_t < j_stop_t ? j_stop_t : j_strt_t;
+  pl->reg_s = l_is_reg_s; pl->reg_t = l_is_reg_t;
+  pl->y_min_s = y_min_s; pl->y_max_s = y_max_s; pl->y_min_t = y_min_t; pl->y_max_t = y_max_t;
+  return SOSIE_OK;
+}
+
+// EASY search, source-only preparation: Xsrc(:,3) / Ysrc(3,:) axes, their sortedness, uniform-axis hints
+int bilin_easy_prepare(sosie_ctx* ctx) {
+  SrcGeom& sg = ctx->sg;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->d_vax.alloc(sg.nx + sg.nyw));
+  double* vax = ctx->d_vax.p;
+  k_gather_axes<<<cdiv(sg.nx + sg.nyw, 256), 256, 0, st>>>(sg, vax, vax + sg.nx); KLAUNCH_CHECK();
+  std::vector<double> hax(sg.nx + sg.nyw);
+  if (int rc = fetch_small(ctx, vax, hax.data(), sizeof(double) * hax.size())) return rc;
+  ctx->easy_sorted_lon = is_sorted_host(hax, 0, sg.nx);
+  ctx->easy_sorted_lat = is_sorted_host(hax, sg.nx, sg.nyw);
+  sg.lon0 = sg.inv_dlon = sg.lat0 = sg.inv_dlat = 0.0;
+  if (ctx->easy_sorted_lon && hax[sg.nx - 1] > hax[0]) { sg.lon0 = hax[0]; sg.inv_dlon = (double)(sg.nx - 1) / (hax[sg.nx - 1] - hax[0]); }
+  if (ctx->easy_sorted_lat && hax[sg.nx + sg.nyw - 1] > hax[sg.nx]) {
+    sg.lat0 = hax[sg.nx]; sg.inv_dlat = (double)(sg.nyw - 1) / (hax[sg.nx + sg.nyw - 1] - hax[sg.nx]);
+  }
+  return SOSIE_OK;
+}
+
+// FIND_NEAREST_EASY + MAPPING_BL body for the targets [k0, k0+kcnt), searched rows jlo..jhi; errors OR'ed into *derr
+int bilin_easy_rows(sosie_ctx* ctx, int jlo, int jhi, size_t k0, size_t kcnt, int* derr) {
+  SrcGeom& sg = ctx->sg;
+  TrgGeom& tg = ctx->tg;
+  cudaStream_t st = ctx->stream;
+  if (kcnt == 0) return SOSIE_OK;
+  const double* vax = ctx->d_vax.p;
+  if (sg.separable)
+    k_map_easy<true><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
+                                                                 ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
+                                                                 ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt);
+  else
+    k_map_easy<false><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
+                                                                  ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
+                                                                  ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
+
+int bilin_map_alloc(sosie_ctx* ctx) {
+  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
+  CK(ctx->d_metrics.alloc(3 * nt)); CK(ctx->d_ab.alloc(2 * nt)); CK(ctx->d_ipb.alloc(nt)); CK(ctx->d_dnp.alloc(nt));
+  return SOSIE_OK;
+}
+
+int bilin_map_impl(sosie_ctx* ctx) {
+  if (!ctx->grids_set) { ctx->err = "sosie_bilin_map: grids not set"; return SOSIE_ERR_STATE; }
+  SrcGeom& sg = ctx->sg;
+  TrgGeom& tg = ctx->tg;
+  cudaStream_t st = ctx->stream;
+  const size_t nt = (size_t)tg.nx * tg.ny;
+  const size_t nsrc = (size_t)sg.nx * sg.nyw;
+  if (int rc = bilin_map_alloc(ctx)) return rc;
+  MapPlan pl;
+  if (int rc = bilin_map_prelude(ctx, &pl, 0, 0, nullptr)) return rc;
+  struct { int* p; } derr = {reinterpret_cast<int*>(ctx->d_iscratch.p)};
+  CK(cudaMemsetAsync(derr.p, 0, sizeof(int), st));
+  const double y_min_s = pl.y_min_s, y_max_s = pl.y_max_s, y_min_t = pl.y_min_t, y_max_t = pl.y_max_t;
+  const bool l_is_reg_s = pl.reg_s;
+  const int j_strt_t = pl.j_strt, j_stop_t = pl.j_stop, jlat_icr = pl.icr;
 
   int32_t* MT = ctx->d_metrics.p;
   double* AB = ctx->d_ab.p;
@@ -935,29 +1020,11 @@ int bilin_map_impl(sosie_ctx* ctx) {
   if (l_is_reg_s) {
     // ---- FIND_NEAREST_EASY + body, fused
     ctx->map_info[5] = 0;
-    CK(ctx->d_vax.alloc(sg.nx + sg.nyw));
-    struct { double* p; } vax = {ctx->d_vax.p};
-    k_gather_axes<<<cdiv(sg.nx + sg.nyw, 256), 256, 0, st>>>(sg, vax.p, vax.p + sg.nx); KLAUNCH_CHECK();
-    std::vector<double> hax(sg.nx + sg.nyw);
-    CK(cudaMemcpyAsync(hax.data(), vax.p, sizeof(double) * hax.size(), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    int sorted_lon = is_sorted_host(hax, 0, sg.nx), sorted_lat = is_sorted_host(hax, sg.nx, sg.nyw);
-    int jlo = j_strt_t < j_stop_t ? j_strt_t : j_stop_t, jhi = j_strt_t < j_stop_t ? j_stop_t : j_strt_t;
+    if (int rc = bilin_easy_prepare(ctx)) return rc;
     size_t k0, kcnt;
     shard_range(ctx, &k0, &kcnt);
-    sg.lon0 = sg.inv_dlon = sg.lat0 = sg.inv_dlat = 0.0;
-    if (sorted_lon && hax[sg.nx - 1] > hax[0]) { sg.lon0 = hax[0]; sg.inv_dlon = (double)(sg.nx - 1) / (hax[sg.nx - 1] - hax[0]); }
-    if (sorted_lat && hax[sg.nx + sg.nyw - 1] > hax[sg.nx]) {
-      sg.lat0 = hax[sg.nx]; sg.inv_dlat = (double)(sg.nyw - 1) / (hax[sg.nx + sg.nyw - 1] - hax[sg.nx]);
-    }
     prof_begin(ctx, SOSIE_T_MAP);
-    if (sg.separable)
-      k_map_easy<true><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
-                                                                   sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p, k0, kcnt);
-    else
-      k_map_easy<false><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax.p, vax.p + sg.nx, sorted_lon,
-                                                                    sorted_lat, jlo, jhi, MT, AB, IDP, DNP, derr.p, k0, kcnt);
-    KLAUNCH_CHECK();
+    if (int rc = bilin_easy_rows(ctx, pl.jlo, pl.jhi, k0, kcnt, derr.p)) return rc;
     prof_end(ctx, SOSIE_T_MAP);
   } else {
     // ---- FIND_NEAREST_TWISTED
@@ -1072,8 +1139,7 @@ int bilin_map_impl(sosie_ctx* ctx) {
         CK(cudaMemsetAsync(dchg.p, 0, sizeof(int), st));
         k_twisted_chain<<<grid_for(ctx, T, 128), 128, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, Sa, Sb, found.p, dchg.p); KLAUNCH_CHECK();
         int chg = 0;
-        CK(cudaMemcpyAsync(&chg, dchg.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if (int rc = fetch_small(ctx, dchg.p, &chg, sizeof(int))) return rc;
         iters++;
         std::swap(Sa, Sb);
         if (!chg) break;
@@ -1087,8 +1153,7 @@ int bilin_map_impl(sosie_ctx* ctx) {
     CK(cudaStreamSynchronize(st));
   }
   int herr = 0;
-  CK(cudaMemcpyAsync(&herr, derr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  if (int rc = fetch_small(ctx, derr.p, &herr, sizeof(int))) return rc;
   if (herr & 1) { ctx->err = "ERROR (L_InPoly of mod_poly.f90): we only expect positive longitudes!"; return SOSIE_ERR_REF_STOP; }
   if (herr & 6) { ctx->err = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)"; return SOSIE_ERR_REF_STOP; }
   ctx->map_ready = true;

@@ -155,14 +155,11 @@ int sosie_bilin_map_info(sosie_ctx* c, int32_t* info) {
 int sosie_bilin_get_map(sosie_ctx* c, int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np, int32_t* mask_out) {
   NEED(c);
   if (!ctx->map_ready) { ctx->err = "sosie_bilin_get_map: no mapping"; return SOSIE_ERR_STATE; }
-  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
-  cudaStream_t st = ctx->stream;
-  if (metrics) CK(cudaMemcpyAsync(metrics, ctx->d_metrics.p, 3 * nt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (alphabeta) CK(cudaMemcpyAsync(alphabeta, ctx->d_ab.p, 2 * nt * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (id_problem) CK(cudaMemcpyAsync(id_problem, ctx->d_ipb.p, nt * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-  if (dist_np && ctx->d_dnp.p) CK(cudaMemcpyAsync(dist_np, ctx->d_dnp.p, nt * sizeof(float), cudaMemcpyDeviceToHost, st));
-  if (mask_out && ctx->t_mask.p) CK(cudaMemcpyAsync(mask_out, ctx->t_mask.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  size_t k0, kcnt;
+  shard_range(ctx, &k0, &kcnt);  // a sharded context only owns (and only copies) its rows
+  const int j0 = (int)(k0 / (size_t)ctx->tg.nx), j1 = j0 + (int)(kcnt / (size_t)ctx->tg.nx) - 1;
+  if (int rc = bilin_map_rows_d2h(ctx, ctx->stream, j0, j1, metrics, alphabeta, id_problem, dist_np, mask_out)) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
   return SOSIE_OK;
 }
 
@@ -189,23 +186,81 @@ int sosie_bilin_load_map(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32_t* 
   return SOSIE_OK;
 }
 
-// host-pointer apply: slabs are streamed through device staging buffers in chunks
+// host-pointer apply: slab chunks flow through two staging buffer pairs on three streams (H2D | kernels | D2H run
+// concurrently: PCIe is full duplex); only the source rows the packed records read are uploaded, only this
+// shard's target rows come back.
+namespace {
+struct ApplyPipe {
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t e_in[2] = {}, e_ap[2] = {}, e_out[2] = {};
+  ~ApplyPipe() {
+    for (int b = 0; b < 2; b++) { if (e_in[b]) cudaEventDestroy(e_in[b]); if (e_ap[b]) cudaEventDestroy(e_ap[b]); if (e_out[b]) cudaEventDestroy(e_out[b]); }
+    if (h2d) cudaStreamDestroy(h2d);
+    if (d2h) cudaStreamDestroy(d2h);
+  }
+};
+}  // namespace
+
+static int apply_host_run(sosie_ctx* ctx, ApplyPipe& P, int nslab, const float* Z1, float* Z2, int first_call) {
+  const size_t n1 = (size_t)ctx->sg.nx * ctx->sg.ny, n2 = (size_t)ctx->tg.nx * ctx->tg.ny;
+  cudaStream_t sc = ctx->stream;
+  if (!ctx->pack_ready) { if (int rc = bilin_pack_impl(ctx)) return rc; }
+  size_t k0, kcnt;
+  shard_range(ctx, &k0, &kcnt);
+  if (ctx->rows_gen != ctx->pack_gen) {
+    if (int rc = bilin_src_rowrange(ctx, k0, kcnt, &ctx->src_row_lo, &ctx->src_row_hi)) return rc;
+    ctx->rows_gen = ctx->pack_gen;
+  }
+  const int rlo = ctx->src_row_lo, rhi = ctx->src_row_hi;
+  const size_t soff = rhi >= rlo ? (size_t)rlo * ctx->sg.nx : 0, scnt = rhi >= rlo ? (size_t)(rhi - rlo + 1) * ctx->sg.nx : 0;
+  const bool whole_src = (scnt == n1), whole_trg = (kcnt == n2);
+  const size_t budget = (size_t)1 << 30;  // bytes of staging per buffer pair
+  const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nslab, budget / ((n1 + n2) * sizeof(float))));
+  const int nbuf = (nslab > chunk) ? 2 : 1;
+  CK(ctx->d_stage1.alloc(n1 * chunk * nbuf));
+  CK(ctx->d_out.alloc(n2 * chunk * nbuf));
+  CK(cudaStreamSynchronize(sc));
+  CK(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    CK(cudaEventCreateWithFlags(&P.e_in[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&P.e_ap[b], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&P.e_out[b], cudaEventDisableTiming));
+  }
+  int it = 0;
+  for (int s0 = 0; s0 < nslab; s0 += chunk, it++) {
+    const int ns = std::min(chunk, nslab - s0), b = it % nbuf;
+    float* din = ctx->d_stage1.p + (size_t)b * chunk * n1;
+    float* dout = ctx->d_out.p + (size_t)b * chunk * n2;
+    if (it >= nbuf) CK(cudaStreamWaitEvent(P.h2d, P.e_ap[b], 0));  // the kernels of chunk it-2 are done with this input buffer
+    if (whole_src) CK(cudaMemcpyAsync(din, Z1 + (size_t)s0 * n1, n1 * ns * sizeof(float), cudaMemcpyHostToDevice, P.h2d));
+    else
+      for (int s = 0; s < ns && scnt; s++)
+        CK(cudaMemcpyAsync(din + (size_t)s * n1 + soff, Z1 + (size_t)(s0 + s) * n1 + soff, scnt * sizeof(float), cudaMemcpyHostToDevice, P.h2d));
+    CK(cudaEventRecord(P.e_in[b], P.h2d));
+    CK(cudaStreamWaitEvent(sc, P.e_in[b], 0));
+    if (it >= nbuf) CK(cudaStreamWaitEvent(sc, P.e_out[b], 0));    // chunk it-2's results have left this output buffer
+    if (int rc = bilin_apply_impl(ctx, ns, din, dout, first_call && s0 == 0, 0, 0.f, 0.f, nullptr, 0.f)) return rc;
+    CK(cudaEventRecord(P.e_ap[b], sc));
+    CK(cudaStreamWaitEvent(P.d2h, P.e_ap[b], 0));
+    if (whole_trg) CK(cudaMemcpyAsync(Z2 + (size_t)s0 * n2, dout, n2 * ns * sizeof(float), cudaMemcpyDeviceToHost, P.d2h));
+    else
+      for (int s = 0; s < ns; s++)
+        CK(cudaMemcpyAsync(Z2 + (size_t)(s0 + s) * n2 + k0, dout + (size_t)s * n2 + k0, kcnt * sizeof(float), cudaMemcpyDeviceToHost, P.d2h));
+    CK(cudaEventRecord(P.e_out[b], P.d2h));
+  }
+  return SOSIE_OK;
+}
+
 static int apply_host(sosie_ctx* ctx, int nslab, const float* Z1, float* Z2, int first_call) {
   if (!ctx->grids_set) { ctx->err = "sosie_bilin_apply: grids not set"; return SOSIE_ERR_STATE; }
-  const size_t n1 = (size_t)ctx->sg.nx * ctx->sg.ny, n2 = (size_t)ctx->tg.nx * ctx->tg.ny;
-  const size_t budget = (size_t)6 << 30;  // bytes of staging per chunk
-  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nslab, budget / ((n1 + n2) * sizeof(float))));
-  CK(ctx->d_stage1.alloc(n1 * chunk));
-  DBuf<float> out; CK(out.alloc(n2 * chunk));
-  cudaStream_t st = ctx->stream;
-  for (int s0 = 0; s0 < nslab; s0 += chunk) {
-    int ns = std::min(chunk, nslab - s0);
-    CK(cudaMemcpyAsync(ctx->d_stage1.p, Z1 + (size_t)s0 * n1, n1 * ns * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (int rc = bilin_apply_impl(ctx, ns, ctx->d_stage1.p, out.p, first_call && s0 == 0, 0, 0.f, 0.f, nullptr, 0.f)) return rc;
-    CK(cudaMemcpyAsync(Z2 + (size_t)s0 * n2, out.p, n2 * ns * sizeof(float), cudaMemcpyDeviceToHost, st));
-  }
-  CK(cudaStreamSynchronize(st));
-  return SOSIE_OK;
+  if (nslab <= 0) return SOSIE_OK;
+  ApplyPipe P;
+  int rc = apply_host_run(ctx, P, nslab, Z1, Z2, first_call);
+  if (P.h2d) cudaStreamSynchronize(P.h2d);
+  if (P.d2h) cudaStreamSynchronize(P.d2h);
+  cudaStreamSynchronize(ctx->stream);
+  return rc;
 }
 
 int sosie_bilin_apply(sosie_ctx* c, int32_t nslab, const float* Z1, float* Z2, int32_t first_call) {
@@ -234,17 +289,26 @@ int sosie_bilin_apply_uv_dev(sosie_ctx* c, int32_t nslab, const float* dU1, cons
   return bilin_apply_uv_impl(ctx, nslab, dU1, dV1, dUo, dVo, dxcos, dxsin);
 }
 
-int sosie_bilin_2d(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
-                   const float* Z1, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
-                   const int32_t* mask, int32_t l_reg_src, int32_t i_orca_trg, int32_t* l_first_call, int32_t have_mapping,
-                   int32_t nslab) {
-  NEED(c);
+static int bilin_2d_common(sosie_ctx* ctx, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
+                           const float* Z1, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
+                           const int32_t* mask, int32_t l_reg_src, int32_t i_orca_trg, int32_t* l_first_call, int32_t have_mapping,
+                           int32_t nslab, int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np) {
   if (!l_first_call) return SOSIE_ERR_ARG;
+  if (!X10 || !Y10 || !X20 || !Y20 || !Z1 || !Z2 || nslab < 0) { ctx->err = "sosie_bilin_2d: null pointer / bad nslab"; return SOSIE_ERR_ARG; }
   int first = *l_first_call;
   if (first) {
+    bool handled = false;
+    if (!have_mapping && src_1d && !trg_1d) {
+      if (int rc = bilin_first_pipelined(ctx, k_ew, nx1, ny1, X10, Y10, Z1, nx2, ny2, X20, Y20, Z2, mask, l_reg_src, i_orca_trg, nslab,
+                                         metrics, alphabeta, id_problem, dist_np, &handled)) return rc;
+    }
+    if (handled) { *l_first_call = 0; return SOSIE_OK; }
     if (int rc = sosie_bilin_set_grids(ctx, k_ew, nx1, ny1, X10, Y10, src_1d, l_reg_src, nx2, ny2, X20, Y20, trg_1d, mask, i_orca_trg)) return rc;
     if (!have_mapping) { if (int rc = bilin_map_impl(ctx)) return rc; }
     else if (!ctx->map_ready) { ctx->err = "sosie_bilin_2d: have_mapping set but no mapping loaded"; return SOSIE_ERR_STATE; }
+    if (metrics || alphabeta || id_problem || dist_np) {
+      if (int rc = sosie_bilin_get_map(ctx, metrics, alphabeta, id_problem, dist_np, nullptr)) return rc;
+    }
   } else {
     if (!ctx->grids_set || ctx->sg.nx != nx1 || ctx->sg.ny != ny1 || ctx->tg.nx != nx2 || ctx->tg.ny != ny2) {
       ctx->err = "sosie_bilin_2d: extents differ from the first call"; return SOSIE_ERR_ARG;
@@ -253,6 +317,55 @@ int sosie_bilin_2d(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const d
   if (int rc = apply_host(ctx, nslab, Z1, Z2, first)) return rc;
   *l_first_call = 0;  // l_first_call_interp_routine = .FALSE. (:267)
   return SOSIE_OK;
+}
+
+int sosie_bilin_2d(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
+                   const float* Z1, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
+                   const int32_t* mask, int32_t l_reg_src, int32_t i_orca_trg, int32_t* l_first_call, int32_t have_mapping,
+                   int32_t nslab) {
+  NEED(c);
+  return bilin_2d_common(ctx, k_ew, nx1, ny1, X10, Y10, src_1d, Z1, nx2, ny2, X20, Y20, trg_1d, Z2, mask, l_reg_src, i_orca_trg,
+                         l_first_call, have_mapping, nslab, nullptr, nullptr, nullptr, nullptr);
+}
+
+int sosie_bilin_2d_first(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
+                         const float* Z1, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
+                         const int32_t* mask, int32_t l_reg_src, int32_t i_orca_trg, int32_t nslab, int32_t* metrics,
+                         double* alphabeta, int16_t* id_problem, float* dist_np) {
+  NEED(c);
+  int32_t first = 1;
+  return bilin_2d_common(ctx, k_ew, nx1, ny1, X10, Y10, src_1d, Z1, nx2, ny2, X20, Y20, trg_1d, Z2, mask, l_reg_src, i_orca_trg,
+                         &first, 0, nslab, metrics, alphabeta, id_problem, dist_np);
+}
+
+int sosie_bilin_src_rows(sosie_ctx* c, int32_t* rows) {
+  NEED(c);
+  if (!rows) return SOSIE_ERR_ARG;
+  if (!ctx->map_ready) { ctx->err = "sosie_bilin_src_rows: no mapping"; return SOSIE_ERR_STATE; }
+  if (!ctx->pack_ready) { if (int rc = bilin_pack_impl(ctx)) return rc; }
+  if (ctx->rows_gen != ctx->pack_gen) {
+    size_t k0, kcnt;
+    shard_range(ctx, &k0, &kcnt);
+    if (int rc = bilin_src_rowrange(ctx, k0, kcnt, &ctx->src_row_lo, &ctx->src_row_hi)) return rc;
+    ctx->rows_gen = ctx->pack_gen;
+  }
+  rows[0] = ctx->src_row_lo; rows[1] = ctx->src_row_hi;
+  return SOSIE_OK;
+}
+
+int sosie_set_pipeline_min_targets(sosie_ctx* c, int64_t n) {
+  NEED(c);
+  ctx->pipeline_min_targets = n < 0 ? 0 : (size_t)n;
+  return SOSIE_OK;
+}
+
+int sosie_host_register(void* p, size_t bytes) {
+  if (!p || !bytes) return SOSIE_ERR_ARG;
+  return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? SOSIE_OK : SOSIE_ERR_CUDA;
+}
+int sosie_host_unregister(void* p) {
+  if (!p) return SOSIE_ERR_ARG;
+  return cudaHostUnregister(p) == cudaSuccess ? SOSIE_OK : SOSIE_ERR_CUDA;
 }
 
 int sosie_interp_bl(sosie_ctx* c, int32_t k_ew, int32_t nxi, int32_t nyi, const float* Z_in, int32_t n, const int32_t* jiP,

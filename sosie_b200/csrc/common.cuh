@@ -13,6 +13,7 @@
 
 #define SOSIE_NUM_SMS_B200 148
 #define SOSIE_T_COUNT 8
+#define SOSIE_ISCRATCH 256   // ints: [0] error flags, [1] sortedness probe, [2..3] source row range, [8..] per-chunk error flags
 
 template <class T>
 struct DBuf {  // owning device buffer (or borrowed pointer when own == false)
@@ -109,6 +110,10 @@ struct sosie_ctx {
   DBuf<int4> d_boxes;            // per-tile source bounding boxes of the staged apply
   bool boxes_ready = false;
   DBuf<float> d_stage1, d_stage2;  // staging for host-pointer apply
+  DBuf<float> d_out;               // result staging of the host-pointer paths
+  size_t pipeline_min_targets = (size_t)1 << 20;  // first calls smaller than this take the sequential path
+  uint64_t pack_gen = 0, rows_gen = ~0ULL;        // generation of the packed records / of the cached source row range
+  int src_row_lo = 0, src_row_hi = -1;            // physical source rows (0-based) the packed records of this shard read
   DBuf<double> d_scratch;        // Prelude + misc scalars of the search
   DBuf<int32_t> d_iscratch;      // error flag
   DBuf<double> d_vax;            // vlon/vlat axes of the EASY search
@@ -116,8 +121,16 @@ struct sosie_ctx {
   // synchronises: the mapping would otherwise spend more time allocating than computing on small grids)
   std::vector<DBuf<unsigned char>*> ws_slots;
   size_t ws_cursor = 0;
-  ~sosie_ctx() { for (auto* p : ws_slots) delete p; }
+  // page-locked, device-mapped "mailbox": small results (scalars, flags, axis tables) are written to it BY A KERNEL
+  // and read by the host after a stream sync.  A cudaMemcpy D2H would queue behind the bulk downloads that the
+  // pipelined paths keep on the copy engine (measured: a 72-byte read-back waited 16 ms for 1.2 GB of mapping).
+  unsigned char* mailbox = nullptr;
+  ~sosie_ctx() {
+    for (auto* p : ws_slots) delete p;
+    if (mailbox) cudaFreeHost(mailbox);
+  }
   int32_t map_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int easy_sorted_lon = 0, easy_sorted_lat = 0;
   int l_last_y_row_missing = 0;
 
   // ---- akima state
@@ -202,8 +215,31 @@ static inline int grid_for(const sosie_ctx* ctx, int64_t work_items, int block, 
   return (int)need;
 }
 
+// result of the FIND_NEAREST_POINT prelude
+struct MapPlan {
+  int j_strt = 1, j_stop = 0, icr = 1, jlo = 1, jhi = 0;
+  bool reg_s = true, reg_t = true;
+  double y_min_s = 0, y_max_s = 0, y_min_t = 0, y_max_t = 0;
+};
+
+#define SOSIE_MAILBOX_BYTES (512 * 1024)
+// device -> host read-back of a small object through the mailbox (synchronises the context stream)
+int fetch_small(sosie_ctx* ctx, const void* dsrc, void* hdst, size_t bytes);
+
 // entry points implemented in the other translation units
 int bilin_map_impl(sosie_ctx* ctx);
+int bilin_map_alloc(sosie_ctx* ctx);
+int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool* need_full_x);
+int bilin_easy_prepare(sosie_ctx* ctx);
+int bilin_easy_rows(sosie_ctx* ctx, int jlo, int jhi, size_t k0, size_t kcnt, int* derr);
+int bilin_pack_range(sosie_ctx* ctx, size_t k0, size_t kcnt);
+int bilin_src_rowrange(sosie_ctx* ctx, size_t k0, size_t kcnt, int* row_lo, int* row_hi);
+int bilin_map_rows_d2h(sosie_ctx* ctx, cudaStream_t st, int j0, int j1, int32_t* metrics, double* alphabeta,
+                       int16_t* id_problem, float* dist_np, int32_t* mask_out);
+int bilin_first_pipelined(sosie_ctx* ctx, int k_ew, int nx1, int ny1, const double* X10, const double* Y10, const float* Z1,
+                          int nx2, int ny2, const double* X20, const double* Y20, float* Z2, const int32_t* mask,
+                          int l_reg_src, int i_orca_trg, int nslab, int32_t* metrics, double* alphabeta, int16_t* id_problem,
+                          float* dist_np, bool* handled);
 int bilin_pack_impl(sosie_ctx* ctx);
 int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, int first_call, int use_clamp,
                      float vmin, float vmax, const int32_t* dmask_trg, float rmiss);

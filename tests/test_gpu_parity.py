@@ -195,3 +195,78 @@ def test_rotate_uv(gpu, orc):
     ug, vg = gpu.rotate_uv(U, V, c, s)
     ub, vb = gpu.rotate_uv(ug, vg, c, s, inverse=True)
     assert np.allclose(ub, U, atol=2e-6) and np.allclose(vb, V, atol=2e-6)
+
+
+# ---------------------------------------------------------------------------------------------------
+# pipelined first call (csrc/bilin_pipeline.cu): same results as the oracle's sequential BILIN_2D
+def _first_vs_oracle(gpu, orc, kew, lon_s, lat_s, Z1, Xt, Yt, mask=None, shard=None, tag=""):
+    gpu.set_pipeline_min_targets(0)
+    try:
+        if shard:
+            gpu.bilin_set_shard(*shard)
+        Z2g, mg = gpu.bilin_2d_first(kew, lon_s, lat_s, Z1, Xt, Yt, mask_domain_trg=mask, l_reg_src=True)
+    finally:
+        gpu.bilin_set_shard(0, 0)
+        gpu.set_pipeline_min_targets(1 << 20)
+    Z2o, mo = orc.bilin_2d(kew, lon_s, lat_s, Z1, Xt, Yt, mask_domain_trg=mask, l_reg_src=True)
+    rows = slice(None) if not shard else slice(shard[0] - 1, shard[1])
+    for k in ("metrics", "alphabeta"):
+        assert np.array_equal(mg[k][:, rows], mo[k][:, rows]), f"{tag}: {k} differs"
+    for k in ("ipb", "dist_np"):
+        assert np.array_equal(mg[k][rows], mo[k][rows]), f"{tag}: {k} differs"
+    assert np.array_equal(Z2g[:, rows], Z2o[:, rows]), f"{tag}: fields differ at {(Z2g[:, rows] != Z2o[:, rows]).sum()} points"
+    assert tuple(mg["info"][:3]) == tuple(mo["info"][:3]), (tag, mg["info"], mo["info"])
+    return mg, mo
+
+
+@pytest.mark.parametrize("name,scale,nslab", [("E", 0.012, 1), ("E", 0.03, 2), ("D", 0.06, 3)])
+def test_pipelined_first_call_vs_oracle(gpu, orc, name, scale, nslab):
+    cfg = G.config(name, scale)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, nslab, seed=5)
+    Xt, Yt = G.trg_2d(cfg)
+    _first_vs_oracle(gpu, orc, cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt, tag=name)
+    # the cached state serves the following (non-first) calls: cropped, double-buffered host apply
+    Z1b = G.field_slabs(Xs, Ys, 5, seed=6)
+    Z2g = gpu.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1b, Xt, Yt, l_reg_src=True)
+    Z2o, _ = orc.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1b, Xt, Yt, l_reg_src=True)
+    assert np.array_equal(Z2g, Z2o)
+
+
+def test_pipelined_first_call_mask_and_shard(gpu, orc):
+    cfg = G.config("E", 0.02)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, 2, seed=9)
+    Xt, Yt = G.trg_2d(cfg)
+    mask = np.ones(Xt.shape, np.int32)
+    mask[::7, ::3] = 0
+    _first_vs_oracle(gpu, orc, 0, cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt, mask=mask, tag="mask")
+    ny = Xt.shape[0]
+    _first_vs_oracle(gpu, orc, 0, cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt, mask=mask, shard=(ny // 3, 2 * ny // 3), tag="shard")
+    _first_vs_oracle(gpu, orc, -1, cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt, shard=(1, ny // 4), tag="shard-first-rows")
+
+
+def test_pipelined_speculation_is_corrected(gpu, orc):
+    """A regional regular source narrower in latitude than the target: the prelude (src/mod_manip.f90:914-947)
+    restricts the searched target rows AFTER the pipeline has mapped them speculatively -> chunks are redone."""
+    lon_s = (np.arange(720) + 0.5) * 0.5
+    lat_s = 24.0 + np.arange(70) * 0.5          # 24N .. 58.5N, no pole extension
+    cfg = G.config("E", 0.012)                   # target spans about 6N .. 72N
+    Xt, Yt = G.trg_2d(cfg)
+    Xs, Ys = G.expand_2d(lon_s, lat_s)
+    Z1 = G.field_slabs(Xs, Ys, 1, seed=4)
+    mg, mo = _first_vs_oracle(gpu, orc, 0, lon_s, lat_s, Z1, Xt, Yt, tag="restricted")
+    assert mg["info"][0] > 1 and mg["info"][1] < Xt.shape[0], mg["info"]   # the row range was indeed cut on both sides
+
+
+def test_pipelined_regular_2d_target_sharded(gpu, orc):
+    """A regular target passed as 2-D arrays: every resident longitude row equals row 1, so the sharded pipeline
+    must fetch the remaining rows before L_IS_GRID_REGULAR can answer (need_full_x path)."""
+    cfg = G.config("D", 0.06)
+    lon_t = (np.arange(90) + 0.5) * 4.0
+    lat_t = -80.0 + np.arange(60) * 2.5
+    Xt, Yt = G.expand_2d(lon_t, lat_t)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, 2, seed=8)
+    mg, mo = _first_vs_oracle(gpu, orc, 0, cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt, shard=(20, 41), tag="reg2d")
+    assert mg["info"][4] == 1   # l_is_reg_t
