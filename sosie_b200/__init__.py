@@ -27,7 +27,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "_build", "libsosie_b200.so")
+    # SOSIE_B200_LIB: an alternative build of the same library (kernel tuning experiments)
+    return os.environ.get("SOSIE_B200_LIB") or os.path.join(_HERE, "_build", "libsosie_b200.so")
 
 
 # every symbol include/sosie_b200.h declares (tests check the library exports all of them)

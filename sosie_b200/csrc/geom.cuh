@@ -104,7 +104,10 @@ __device__ __forceinline__ void d_point_slope(double& pslup, float xa, float xb,
   double zvertxa = xa, zvertxb = xb, zvertya = ya, zvertyb = yb;
   double zrise = zvertyb - zvertya;
   double zrun = zvertxb - zvertxa;
+  // zrise == 0 (every horizontal edge of a regular grid's cells): the quotient is +-0 and the next statement makes it
+  // +0 -- skip the division (CUDA's fp64 divide takes its ~70-instruction slow path on a zero numerator)
   if (zrun == 0) pslup = 9999;
+  else if (zrise == 0) pslup = 0.0;
   else pslup = zrise / zrun;
   if (fabs(pslup) <= (double)0.001f) pslup = 0.0;
   if (pslup == 0) { pax = pslup; pcnstnt = zvertya; }
@@ -168,6 +171,11 @@ __device__ __forceinline__ int d_l_inpoly(const double* vplon, const double* vpl
   return (icross & 1);
 }
 
+// x / y for a finite non-zero y: identical to the IEEE quotient, without the divide's slow path when x == 0
+__device__ __forceinline__ double d_div_nz(double x, double y) {
+  if (x == 0.0) return (signbit(x) != signbit(y)) ? -0.0 : 0.0;
+  return x / y;
+}
 __device__ __forceinline__ double d_det(double p1, double p2, double p3, double p4) { return p1 * p4 - p2 * p3; }
 
 // LOCAL_COORD, src/mod_bilin_2d.f90:697-799
@@ -198,8 +206,8 @@ __device__ __forceinline__ void d_local_coord(const double* xlam, const double* 
     double za22 = p41 + pc * zalpha;
     double zdeta = d_det(za11, za12, za21, za22);
     zdeta = (d_sign(1.0, zdeta) * fmax(fabs(zdeta), G_REPS));
-    double zdalp = d_det(zdlam, za12, zdphi, za22) / zdeta;
-    double zdbet = d_det(za11, zdlam, za21, zdphi) / zdeta;
+    double zdalp = d_div_nz(d_det(zdlam, za12, zdphi, za22), zdeta);  // |zdeta| >= repsilon: finite, non-zero
+    double zdbet = d_div_nz(d_det(za11, zdlam, za21, zdphi), zdeta);
     zres = sqrt(zdalp * zdalp + zdbet * zdbet);
     zalpha = zalpha + zdalp;
     zbeta = zbeta + zdbet;

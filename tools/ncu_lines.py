@@ -45,7 +45,7 @@ def main():
         break
     if recs is None:
         sys.exit("kernel not found in " + lib)
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern], capture_output=True, text=True).stdout
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + os.environ.get("NCU_KERNEL", kern)], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hi = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
     hdr = rows[hi]
