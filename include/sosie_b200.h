@@ -177,8 +177,9 @@ int sosie_bdrown_dev(sosie_ctx* ctx, int32_t k_ew, int32_t ni, int32_t nj, int32
                      float pmin, float pmax, float pval_land, int32_t* nsweeps_host);
 /* SMOOTHER(k_ew, X, nb_smooth, msk, l_exclude_mask_points): msk may be NULL; l_emp mirrors
  * PRESENT(l_exclude_mask_points) (presence, not value: :496).                                      */
-/* test hook: force the general (global-memory, one launch per sweep) BDROWN path even when a slab fits the
- * shared memory of one SM (the default picks the on-chip kernel for such slabs; results are identical). */
+/* test hook: which BDROWN implementation runs (results are identical): 0 = automatic (one-CTA-per-slab on-chip kernel
+ * when a slab fits the shared memory of one SM, level lists otherwise), 1 = level-list general path for every size,
+ * 2 = legacy dense path (one whole-array kernel per sweep).                                                        */
 int sosie_bdrown_force_general(sosie_ctx* ctx, int32_t on);
 int sosie_smoother(sosie_ctx* ctx, int32_t k_ew, int32_t ni, int32_t nj, int32_t nslab, float* X,
                    int32_t nb_smooth, const int32_t* msk, int32_t l_emp);

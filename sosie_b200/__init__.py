@@ -335,7 +335,7 @@ class Sosie:
         return (X[0] if sq else X), nsw
 
     def bdrown_force_general(self, on=True):
-        """test hook: use the multi-launch global-memory BDROWN path even for slabs that fit one SM's shared memory"""
+        """test hook: 0/False automatic, 1/True level-list general path for every slab size, 2 legacy dense path"""
         self._ck(self._lib.sosie_bdrown_force_general(self._h, int(on)))
 
     def bdrown_dev(self, k_ew, ni, nj, nslab, dX, dmask, mask_per_slab, nb_inc, nb_smooth, pmin, pmax, pval_land, want_nsweeps=False):

@@ -484,7 +484,7 @@ int sosie_bdrown(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nsl
 
 int sosie_bdrown_force_general(sosie_ctx* c, int32_t on) {
   NEED(c);
-  ctx->force_general_bdrown = on != 0;
+  ctx->force_general_bdrown = on;
   return SOSIE_OK;
 }
 

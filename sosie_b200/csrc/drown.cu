@@ -14,6 +14,8 @@
 //     slabs cost one predicated exit per block, no host round trip;
 //   * the per-sweep whole-array clamp (:414-415) is folded into the reads of sweeps >= 2 plus one
 //     final clamp pass (identical results, no extra traffic per sweep).
+#include <cub/cub.cuh>
+
 #include "geom.cuh"
 
 #define RIS2F 0.70710677f  // REAL( 1./SQRT(2.) , 4 )
@@ -46,21 +48,38 @@ __global__ void k_bd_init(const int32_t* __restrict__ mask, size_t n, int nmask,
   if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt[ms], local);
 }
 
-// zonal-mean prefill (:109-120): thread per (row, slab), sequential REAL(4) sum
-__global__ void k_bd_prefill(float* X, const int32_t* __restrict__ mask, int ni, int nj, int nslab, int mask_per_slab) {
-  size_t n = (size_t)ni * nj;
-  int total = nj * nslab;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
-    int s = t / nj, jj = t % nj;
+// zonal-mean prefill (:109-120): one WARP per (row, slab).  The REAL(4) sum is sequential in i as in the reference
+// (every lane replays it through shuffles: 2 instructions per element), but the loads and stores are coalesced --
+// a thread-per-row walk cost 3.8 ms on 64 slabs of 2560x1280, 0.45 ms this way.
+__global__ void __launch_bounds__(256)
+k_bd_prefill(float* X, const int32_t* __restrict__ mask, int ni, int nj, int nslab, int mask_per_slab) {
+  const size_t n = (size_t)ni * nj;
+  const int total = nj * nslab;
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < total; t += gridDim.x * wpb) {
+    const int s = t / nj, jj = t % nj;
     float* row = X + (size_t)s * n + (size_t)jj * ni;
     const int32_t* mrow = mask + (mask_per_slab ? (size_t)s * n : 0) + (size_t)jj * ni;
     int nbp = 0;
-    for (int i = 0; i < ni; i++) nbp += mrow[i];
+    float sum = 0.f;
+    for (int i0 = 0; i0 < ni; i0 += 32) {
+      const int i = i0 + lane;
+      const int m = (i < ni) ? mrow[i] : 0;
+      const float p = (i < ni) ? __fmul_rn(row[i], (float)m) : 0.f;
+      nbp += m;
+      const int c = min(32, ni - i0);
+      if (c == 32) {
+#pragma unroll
+        for (int q = 0; q < 32; q++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, p, q));
+      } else {
+        for (int q = 0; q < c; q++) sum = __fadd_rn(sum, __shfl_sync(0xffffffffu, p, q));
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) nbp += __shfl_xor_sync(0xffffffffu, nbp, o);
     if (nbp > 0) {
-      float sum = 0.f;
-      for (int i = 0; i < ni; i++) sum = __fadd_rn(sum, __fmul_rn(row[i], (float)mrow[i]));
-      float zmv = __fdiv_rn(sum, (float)nbp);
-      for (int i = 0; i < ni; i++) if (mrow[i] == 0) row[i] = zmv;
+      const float zmv = __fdiv_rn(sum, (float)nbp);
+      for (int i = lane; i < ni; i += 32) if (mrow[i] == 0) row[i] = zmv;
     }
   }
 }
@@ -229,7 +248,7 @@ k_bd_sweep(BdGeom g, float* Xb, const int8_t* __restrict__ mcb, int8_t* mnb, int
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
     int m = mc[k];
     if (m != 0) { if (writer) mn[k] = (int8_t)m; continue; }
-    const int jj = (int)(k / ni) + 1, ji = (int)(k % ni) + 1;
+    const int jj = (int)((unsigned int)k / (unsigned int)ni) + 1, ji = (int)((unsigned int)k % (unsigned int)ni) + 1;  // n < 2^31
     float val;
     const int coast = bd_cell<true>(g, reinterpret_cast<const uint8_t*>(mc), X, ji, jj, first_sweep, zmin, zmax, val, 255);
     if (coast) {
@@ -245,6 +264,193 @@ k_bd_sweep(BdGeom g, float* Xb, const int8_t* __restrict__ mcb, int8_t* mnb, int
   if (writer) {
     for (int o = 16; o > 0; o >>= 1) left += __shfl_xor_sync(0xffffffffu, left, o);
     if ((threadIdx.x & 31) == 0 && left) atomicAdd(&cnt_out[ms], left);
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Level-list BDROWN for slabs that do not fit one SM (the general path).
+//
+// The coastline sequence of BDROWN depends on the MASK alone: a land cell is drowned at sweep j when, after sweep
+// j-1, one of its 4 neighbours is sea (with the reference's asymmetric border/corner rules, bd_cell<false>), and
+// its value is the weighted mean of the 8 neighbours that are sea after sweep j-1.  So
+//   phase A (once per mask, 1-byte traffic): walk the list of still-land cells sweep by sweep; a cell that turns
+//           coastline at sweep j gets mw = j+1 and is appended to the level-j segment of the level list, the others
+//           go to the next remaining-land list.  mw doubles as the running mask of every sweep: "sea after sweep
+//           j-1" == 1 <= mw <= j, so a cell drowned during sweep j (mw = j+1) is still land for its neighbours;
+//   phase B (per level, all slabs of the mask in one launch): the cells of level j are computed IN PLACE from
+//           neighbours of lower levels -- each land cell of each slab is read-modified exactly once.
+// HBM traffic: O(land cells x slabs) in total instead of O(all cells x slabs) PER SWEEP; the arithmetic, its order
+// and the clamps are those of the sweep kernel (same bd_cell), so the result is bit-identical.
+struct IsLandByte {
+  const int8_t* m;
+  __device__ __forceinline__ bool operator()(const unsigned int& g) const { return m[g] == 0; }
+};
+
+struct BdlCounters {   // device-resident, zeroed per call
+  // [0 .. NB]            rtot[j]   entries of the remaining-land list after sweep j (j = 0: all land cells)
+  // [NB+1 .. 2NB+1]      lvcount[j] cells drowned by sweep j
+  unsigned int* base;
+  int nb;
+  __device__ __host__ unsigned int* rtot() const { return base; }
+  __device__ __host__ unsigned int* lvcount() const { return base + nb + 1; }
+};
+
+__global__ void k_bdl_rtot0(const unsigned int* __restrict__ nsel, unsigned int* rtot0) { *rtot0 = *nsel; }
+
+__global__ void __launch_bounds__(256)
+k_bdl_sweep(BdGeom g, uint8_t* mwb, const unsigned int* __restrict__ Rin, unsigned int* Rout, unsigned int* Lv, BdlCounters C,
+            int32_t* rem_out, int j) {
+  const unsigned int n = (unsigned int)g.ni * (unsigned int)g.nj;
+  const unsigned int cnt = C.rtot()[j - 1];
+  if (cnt == 0) return;
+  const unsigned int lbase = C.rtot()[0] - cnt;   // cells drowned before this sweep = all land - land left after sweep j-1
+  for (unsigned int q0 = blockIdx.x * blockDim.x; q0 < cnt; q0 += gridDim.x * blockDim.x) {
+    const unsigned int q = q0 + threadIdx.x;
+    int coast = 0, valid = q < cnt;
+    unsigned int gid = 0, ms = 0;
+    if (valid) {
+      gid = Rin[q];
+      ms = gid / n;
+      const unsigned int k = gid - ms * n;
+      const int jj = (int)(k / (unsigned int)g.ni) + 1, ji = (int)(k % (unsigned int)g.ni) + 1;
+      float dummy;
+      coast = bd_cell<false>(g, mwb + (size_t)ms * n, nullptr, ji, jj, 0, 0.f, 0.f, dummy, j);
+    }
+    // block-aggregated appends: one global atomic per list per block iteration (same-address atomics serialise in
+    // L2; per-thread ones made a sweep cost 0.25 ms); order inside a block is kept, so neighbouring cells stay
+    // neighbours in the lists
+    const unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int mc = __ballot_sync(0xffffffffu, valid && coast), mr = __ballot_sync(0xffffffffu, valid && !coast);
+    __shared__ unsigned int wc[8], wr[8], bc, br;
+    if (lane == 0) { wc[wid] = __popc(mc); wr[wid] = __popc(mr); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int tc = 0, tr = 0;
+      for (int w = 0; w < 8; w++) { unsigned int a = wc[w], b = wr[w]; wc[w] = tc; wr[w] = tr; tc += a; tr += b; }
+      bc = tc ? atomicAdd(&C.lvcount()[j], tc) : 0u;
+      br = tr ? atomicAdd(&C.rtot()[j], tr) : 0u;
+    }
+    __syncthreads();
+    const unsigned int below = (1u << lane) - 1u;
+    if (valid && coast) {
+      mwb[gid] = (uint8_t)(j + 1);   // invisible to this sweep's tests (lim = j)
+      Lv[lbase + bc + wc[wid] + __popc(mc & below)] = gid;
+    } else if (valid) {
+      Rout[br + wr[wid] + __popc(mr & below)] = gid;
+    }
+    if (rem_out) {  // per-mask counts (several masks only; with one mask rtot[j] is the count)
+      const int surv = valid && !coast;
+      const unsigned int peers = __match_any_sync(0xffffffffu, surv ? ms : 0xffffffffu);
+      if (surv && lane == (unsigned int)(__ffs(peers) - 1)) atomicAdd(&rem_out[ms], __popc(peers));
+    }
+    __syncthreads();   // wc / wr are rewritten by the next iteration
+  }
+}
+
+// values of the level-j cells for every slab of their mask, in place (the sweep kernel's arithmetic)
+__global__ void __launch_bounds__(256)
+k_bdl_level(BdGeom g, float* Xb, const uint8_t* __restrict__ mwb, const unsigned int* __restrict__ Lv, BdlCounters C, int j,
+            int mask_per_slab, int nslab, int slabs_per_item, float zmin, float zmax) {
+  const unsigned int n = (unsigned int)g.ni * (unsigned int)g.nj;
+  const unsigned int cnt = C.lvcount()[j];
+  if (cnt == 0) return;
+  const unsigned int lbase = C.rtot()[0] - C.rtot()[j - 1];
+  // work item = (level entry, chunk of slabs); the mask-derived part of a cell is shared by the slabs of its chunk
+  const unsigned int nchunk = mask_per_slab ? 1u : (unsigned int)((nslab + slabs_per_item - 1) / slabs_per_item);
+  const unsigned long long nitem = (unsigned long long)cnt * nchunk;
+  for (unsigned long long it = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; it < nitem;
+       it += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned int q = (unsigned int)(it % cnt), c = (unsigned int)(it / cnt);
+    const unsigned int gid = Lv[lbase + q];
+    const unsigned int ms = gid / n, k = gid - ms * n;
+    const int jj = (int)(k / (unsigned int)g.ni) + 1, ji = (int)(k % (unsigned int)g.ni) + 1;
+    const uint8_t* mw = mwb + (size_t)ms * n;
+    int sa = (int)ms, sb = (int)ms + 1;
+    if (!mask_per_slab) { sa = (int)c * slabs_per_item; sb = min(nslab, sa + slabs_per_item); }
+    for (int s = sa; s < sb; s++) {
+      float val;
+      bd_cell<true>(g, mw, Xb + (size_t)s * n, ji, jj, j == 1, zmin, zmax, val, j);
+      Xb[(size_t)s * n + k] = fminf(fmaxf(val, zmin), zmax);
+    }
+  }
+}
+
+// sweeps entered per slab: IF(.NOT. ANY(maskv == 0)) EXIT at the top of each sweep (:125)
+__global__ void k_bdl_nsw(int32_t* rem, const unsigned int* __restrict__ rtot, int nmask, int nb_inc, int mask_per_slab, int nslab,
+                          int32_t* nsw) {
+  for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nslab; s += gridDim.x * blockDim.x) {
+    const int ms = mask_per_slab ? s : 0;
+    int c = 0;
+    for (int j = 1; j <= nb_inc; j++) c += ((nmask == 1 ? (int)rtot[j - 1] : rem[(size_t)(j - 1) * nmask + ms]) > 0);
+    nsw[s] = c;
+    if (nmask == 1 && s == 0) rem[nb_inc] = (int)rtot[nb_inc];   // land left after the last sweep (pval_land fill)
+  }
+}
+
+// ---- land-only SMOOTHER for BDROWN (msk = 1 - mask, l_emp absent): sea cells never change, so only the listed land
+// cells are recomputed each pass; both ping-pong buffers hold the (constant) sea values.
+__global__ void k_sml_prepare(const float* __restrict__ Xb, float* Yb, size_t tot, unsigned int n, int ni, int nj, int* flag) {
+  // Y = X ; flag |= any non-finite or negative-zero value in rows 2..nj-1 (those make `msk*X - (msk-1)*xorig` differ
+  // from "land: smoothed value, sea: unchanged": the dense kernel handles them)
+  int bad = 0;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const float v = Xb[t];
+    Yb[t] = v;
+    const unsigned int u = __float_as_uint(v);
+    if (u == 0x80000000u || (u & 0x7f800000u) == 0x7f800000u) {
+      const unsigned int k = (unsigned int)(t % n);
+      const int jj = (int)(k / (unsigned int)ni) + 1;
+      if (jj >= 2 && jj <= nj - 1) bad = 1;
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+__global__ void k_sml_gather(const float* __restrict__ Xb, const unsigned int* __restrict__ R0, unsigned int cnt, unsigned int n,
+                             int mask_per_slab, int nslab, float* xo) {
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+    const unsigned int gid = R0[q];
+    if (mask_per_slab) xo[q] = Xb[gid];
+    else for (int s = 0; s < nslab; s++) xo[(size_t)s * cnt + q] = Xb[(size_t)s * n + gid];
+  }
+}
+__global__ void __launch_bounds__(256)
+k_sml_pass(BdGeom g, const float* __restrict__ xinb, float* xoutb, const float* __restrict__ xo, const unsigned int* __restrict__ R0,
+           unsigned int cnt, int mask_per_slab, int nslab, int slabs_per_block) {
+  const int ni = g.ni, nj = g.nj;
+  const unsigned int n = (unsigned int)ni * (unsigned int)nj;
+  const float w0 = 0.35f, omw = 1.f - w0, c4 = 4.f * (1.f + RIS2F);
+  const int s0 = blockIdx.y * slabs_per_block, s1 = min(nslab, s0 + slabs_per_block);
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+    const unsigned int gid = R0[q];
+    const unsigned int ms = gid / n, k = gid - ms * n;
+    const int jj = (int)(k / (unsigned int)ni) + 1, ji = (int)(k % (unsigned int)ni) + 1;
+    if (jj < 2 || jj > nj - 1) continue;
+    int jim = ji - 1, jip = ji + 1;
+    if (ji == 1) { if (g.k_ew >= 0) { jim = g.jimW; jip = g.jipW; } else continue; }
+    else if (ji == ni) { if (g.k_ew >= 0) { jim = g.jimE; jip = g.jipE; } else continue; }
+    const unsigned int r0 = (unsigned int)(jj - 1) * ni, rm = r0 - ni, rp = r0 + ni;
+    const unsigned int cW = jim - 1, cE = jip - 1, cC = ji - 1;
+    int sa = s0, sb = s1;
+    if (mask_per_slab) { if ((int)ms < s0 || (int)ms >= s1) continue; sa = (int)ms; sb = sa + 1; }
+    for (int s = sa; s < sb; s++) {
+      const float* xin = xinb + (size_t)s * n;
+      // ( X(jip,jj) + X(ji,jj+1) + X(jim,jj) + X(ji,jj-1) ) + ris2*( X(jip,jj+1) + X(jip,jj-1) + X(jim,jj-1) + X(jim,jj+1) )
+      const float s4 = __fadd_rn(__fadd_rn(__fadd_rn(xin[r0 + cE], xin[rp + cC]), xin[r0 + cW]), xin[rm + cC]);
+      const float sd = __fadd_rn(__fadd_rn(__fadd_rn(xin[rp + cE], xin[rm + cE]), xin[rm + cW]), xin[rp + cW]);
+      float v = __fadd_rn(__fmul_rn(w0, xin[k]), __fdiv_rn(__fmul_rn(omw, __fadd_rn(s4, __fmul_rn(RIS2F, sd))), c4));
+      const float o = mask_per_slab ? xo[q] : xo[(size_t)s * cnt + q];
+      v = __fsub_rn(__fmul_rn(1.f, v), __fmul_rn(0.f, o));   // msk*X - (msk-1)*xorig with msk = 1  (:600)
+      xoutb[(size_t)s * n + k] = v;
+    }
+  }
+}
+__global__ void k_sml_copyback(const float* __restrict__ src, float* dst, const unsigned int* __restrict__ R0, unsigned int cnt,
+                               unsigned int n, int mask_per_slab, int nslab) {
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+    const unsigned int gid = R0[q];
+    if (mask_per_slab) dst[gid] = src[gid];
+    else for (int s = 0; s < nslab; s++) dst[(size_t)s * n + gid] = src[(size_t)s * n + gid];
   }
 }
 
@@ -447,7 +653,7 @@ k_smooth_pass(BdGeom g, const float* __restrict__ xinb, float* xoutb, const floa
     return v;
   };
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
-    const int jj = (int)(k / ni) + 1, ji = (int)(k % ni) + 1;
+    const int jj = (int)((unsigned int)k / (unsigned int)ni) + 1, ji = (int)((unsigned int)k % (unsigned int)ni) + 1;  // n < 2^31
     float v = xin[k];
     if (jj >= 2 && jj <= nj - 1) {
       int jim = ji - 1, jip = ji + 1;
@@ -626,6 +832,99 @@ int smoother_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX
   return smoother_dev(ctx, g, nslab, dX, nb_smooth, dmsk, 0, l_emp);
 }
 
+// general path: level lists (see k_bdl_sweep / k_bdl_level) + land-only smoothing
+static int bdrown_levels(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, const int32_t* dmask, int mask_per_slab, int nb_inc,
+                         int nb_smooth, float pmin, float pmax, float pval_land, int32_t* nsweeps_host) {
+  cudaStream_t st = ctx->stream;
+  const int ni = g.ni, nj = g.nj;
+  const size_t n = (size_t)ni * nj;
+  const int nmask = mask_per_slab ? nslab : 1;
+  const size_t ncell = n * nmask, tot = n * nslab;
+  CK(ctx->dr_m0.alloc(ncell));
+  CK(ctx->dr_cnt.alloc((size_t)(nb_inc + 1) * nmask + nslab));
+  CK(cudaMemsetAsync(ctx->dr_cnt.p, 0, sizeof(int32_t) * ((size_t)(nb_inc + 1) * nmask + nslab), st));
+  int32_t* rem = ctx->dr_cnt.p;                            // rem[j][ms]: land cells left after sweep j
+  int32_t* nsw = rem + (size_t)(nb_inc + 1) * nmask;
+  const size_t nctr = 2 * (size_t)(nb_inc + 1) + 4;
+  CK(ctx->dr_ctr.alloc(nctr));
+  CK(cudaMemsetAsync(ctx->dr_ctr.p, 0, sizeof(unsigned int) * nctr, st));
+  BdlCounters C;
+  C.base = ctx->dr_ctr.p; C.nb = nb_inc;
+  unsigned int* nsel = ctx->dr_ctr.p + 2 * (size_t)(nb_inc + 1);   // [0] land cells, [1] smoothing fallback flag
+  CK(ctx->dr_R0.alloc(ncell)); CK(ctx->dr_Ra.alloc(ncell)); CK(ctx->dr_Rb.alloc(ncell)); CK(ctx->dr_Lv.alloc(ncell));
+  uint8_t* mw = reinterpret_cast<uint8_t*>(ctx->dr_m0.p);
+  k_bd_init<<<dim3(grid_for(ctx, n, 256, 4), nmask), 256, 0, st>>>(dmask, n, nmask, ctx->dr_m0.p, rem); KLAUNCH_CHECK();
+  k_bd_prefill<<<grid_for(ctx, (size_t)nj * nslab * 32, 256, 8), 256, 0, st>>>(dX, dmask, ni, nj, nslab, mask_per_slab); KLAUNCH_CHECK();
+  {  // R0 = ordered list of all land cells (global index ms*n + k)
+    cub::CountingInputIterator<unsigned int> it(0u);
+    IsLandByte pred{ctx->dr_m0.p};
+    size_t tmpb = 0;
+    cub::DeviceSelect::If(nullptr, tmpb, it, ctx->dr_R0.p, nsel, (int64_t)ncell, pred, st);
+    CK(ctx->dr_tmp.alloc(tmpb + 16));
+    CK(cub::DeviceSelect::If(ctx->dr_tmp.p, tmpb, it, ctx->dr_R0.p, nsel, (int64_t)ncell, pred, st));
+    ctx->launches += 2;
+    k_bdl_rtot0<<<1, 1, 0, st>>>(nsel, C.rtot()); KLAUNCH_CHECK();
+  }
+  prof_begin(ctx, SOSIE_T_BDROWN);
+  {  // phase A: the mask dynamics, once per mask
+    const unsigned int* Rin = ctx->dr_R0.p;
+    unsigned int* Rout = ctx->dr_Ra.p;
+    const int gx = grid_for(ctx, ncell, 256, 4);
+    for (int j = 1; j <= nb_inc; j++) {
+      k_bdl_sweep<<<gx, 256, 0, st>>>(g, mw, Rin, Rout, ctx->dr_Lv.p, C, nmask > 1 ? rem + (size_t)j * nmask : nullptr, j); KLAUNCH_CHECK();
+      Rin = Rout;
+      Rout = (Rout == ctx->dr_Ra.p) ? ctx->dr_Rb.p : ctx->dr_Ra.p;
+    }
+  }
+  {  // phase B: values, level by level, every slab of a mask in the same launch
+    const int spi = mask_per_slab ? 1 : std::max(1, (nslab + 63) / 64);   // slabs per work item
+    const int gx = ctx->num_sms * 4;   // persistent-style: the level sizes live on the device, blocks stride over them
+    for (int j = 1; j <= nb_inc; j++) {
+      k_bdl_level<<<gx, 256, 0, st>>>(g, dX, mw, ctx->dr_Lv.p, C, j, mask_per_slab, nslab, spi, pmin, pmax); KLAUNCH_CHECK();
+    }
+  }
+  prof_end(ctx, SOSIE_T_BDROWN);
+  k_bdl_nsw<<<cdiv(nslab, 128), 128, 0, st>>>(rem, C.rtot(), nmask, nb_inc, mask_per_slab, nslab, nsw); KLAUNCH_CHECK();
+  dim3 gridc(grid_for(ctx, n, 256, 4), nslab);
+  k_bd_clamp<<<gridc, 256, 0, st>>>(dX, n, nsw, pmin, pmax); KLAUNCH_CHECK();
+  if (nb_smooth > 0) {
+    CK(ctx->dr_x2.alloc(tot));
+    k_sml_prepare<<<grid_for(ctx, tot, 256, 8), 256, 0, st>>>(dX, ctx->dr_x2.p, tot, (unsigned int)n, ni, nj, (int*)(nsel + 1)); KLAUNCH_CHECK();
+    unsigned int h[2];
+    if (int rc = fetch_small(ctx, nsel, h, sizeof(h))) return rc;
+    if (h[1]) {  // negative zeros / non-finite values: the dense kernel follows `msk*X - (msk-1)*xorig` literally
+      CK(ctx->dr_mask32.alloc(ncell));
+      k_land_msk<<<grid_for(ctx, ncell, 256), 256, 0, st>>>(dmask, ncell, ctx->dr_mask32.p); KLAUNCH_CHECK();
+      if (int rc = smoother_dev(ctx, g, nslab, dX, nb_smooth, ctx->dr_mask32.p, mask_per_slab, 0)) return rc;
+    } else if (h[0] > 0) {
+      const unsigned int cnt = h[0];
+      CK(ctx->dr_x.alloc((size_t)cnt * (mask_per_slab ? 1 : nslab)));
+      k_sml_gather<<<grid_for(ctx, cnt, 256, 8), 256, 0, st>>>(dX, ctx->dr_R0.p, cnt, (unsigned int)n, mask_per_slab, nslab, ctx->dr_x.p); KLAUNCH_CHECK();
+      const int spb = mask_per_slab ? nslab : std::max(1, (nslab + 15) / 16);
+      dim3 grid(grid_for(ctx, cnt, 256, 8), mask_per_slab ? 1 : (nslab + spb - 1) / spb);
+      float* a = dX;
+      float* b = ctx->dr_x2.p;
+      prof_begin(ctx, SOSIE_T_SMOOTH);
+      for (int js = 0; js < nb_smooth; js++) {
+        k_sml_pass<<<grid, 256, 0, st>>>(g, a, b, ctx->dr_x.p, ctx->dr_R0.p, cnt, mask_per_slab, nslab, spb); KLAUNCH_CHECK();
+        std::swap(a, b);
+      }
+      prof_end(ctx, SOSIE_T_SMOOTH);
+      if (a != dX) { k_sml_copyback<<<grid_for(ctx, cnt, 256, 8), 256, 0, st>>>(a, dX, ctx->dr_R0.p, cnt, (unsigned int)n, mask_per_slab, nslab); KLAUNCH_CHECK(); }
+    }
+  }
+  if (fabsf(pval_land) > 1.e-12f) {
+    // cells never reached (mw == 0) of the masks that still hold land after the last sweep
+    k_bd_pval<<<gridc, 256, 0, st>>>(dX, n, ctx->dr_m0.p, mask_per_slab, pval_land, rem + (size_t)nb_inc * nmask); KLAUNCH_CHECK();
+  }
+  if (nsweeps_host) {
+    std::vector<int32_t> h(nslab);
+    if (int rc = fetch_small(ctx, nsw, h.data(), sizeof(int32_t) * nslab)) return rc;
+    memcpy(nsweeps_host, h.data(), sizeof(int32_t) * nslab);
+  }
+  return SOSIE_OK;
+}
+
 int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, const int32_t* dmask, int mask_per_slab,
                 int nb_inc, int nb_smooth, float pmin, float pmax, float pval_land, int32_t* nsweeps_host) {
   cudaStream_t st = ctx->stream;
@@ -650,13 +949,18 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
     }
     return SOSIE_OK;
   }
+  if (n > 2147483647ULL) { ctx->err = "sosie_bdrown: slab too large"; return SOSIE_ERR_ARG; }
+  if (ctx->force_general_bdrown != 2 && n * nmask < 4000000000ULL && nb_inc <= 250)
+    return bdrown_levels(ctx, g, nslab, dX, dmask, mask_per_slab, nb_inc, nb_smooth, pmin, pmax, pval_land, nsweeps_host);
+  // ---- legacy dense path: one whole-array kernel per sweep (kept for slabs stacks beyond 32-bit list indices, and as
+  // an independent implementation the tests compare with)
   CK(ctx->dr_m0.alloc(n * nmask)); CK(ctx->dr_m1.alloc(n * nmask));
   CK(ctx->dr_cnt.alloc((size_t)(nb_inc + 1) * nmask + nslab));
   CK(cudaMemsetAsync(ctx->dr_cnt.p, 0, sizeof(int32_t) * ((size_t)(nb_inc + 1) * nmask + nslab), st));
   int32_t* cnt = ctx->dr_cnt.p;
   int32_t* nsw = cnt + (size_t)(nb_inc + 1) * nmask;
   k_bd_init<<<dim3(grid_for(ctx, n, 256, 4), nmask), 256, 0, st>>>(dmask, n, nmask, ctx->dr_m0.p, cnt); KLAUNCH_CHECK();
-  k_bd_prefill<<<grid_for(ctx, (size_t)nj * nslab, 128), 128, 0, st>>>(dX, dmask, ni, nj, nslab, mask_per_slab); KLAUNCH_CHECK();
+  k_bd_prefill<<<grid_for(ctx, (size_t)nj * nslab * 32, 256, 8), 256, 0, st>>>(dX, dmask, ni, nj, nslab, mask_per_slab); KLAUNCH_CHECK();
   int8_t* mc = ctx->dr_m0.p;
   int8_t* mn = ctx->dr_m1.p;
   dim3 grid(grid_for(ctx, n, 256, 4), nslab);
@@ -677,7 +981,6 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
     if (int rc = smoother_dev(ctx, g, nslab, dX, nb_smooth, ctx->dr_mask32.p, mask_per_slab, 0)) return rc;
   }
   if (fabsf(pval_land) > 1.e-12f) {
-    if (nb_inc == 0) { /* maskv == mask */ }
     // cells still 0 in the final running mask of slabs that never emptied
     k_bd_pval<<<grid, 256, 0, st>>>(dX, n, mc, mask_per_slab, pval_land, cnt + (size_t)nb_inc * nmask); KLAUNCH_CHECK();
   }

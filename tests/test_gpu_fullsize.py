@@ -129,7 +129,7 @@ def test_config_C_full_bdrown(gpu, orc):
     masks[-1] = 0
     X[masks == 0] = -9999.0
     Xo, no = orc.bdrown(cfg["ewper_src"], X, masks, cfg["nb_inc"], cfg["nb_smooth"], cfg["vmin"], cfg["vmax"], 0.0, nthreads=orc.max_threads())
-    for general in (False, True):
+    for general in (0, 1, 2):
         gpu.bdrown_force_general(general)
         try:
             Xg, ng = gpu.bdrown(cfg["ewper_src"], X, masks, cfg["nb_inc"], cfg["nb_smooth"], cfg["vmin"], cfg["vmax"], 0.0)

@@ -111,7 +111,7 @@ def test_bdrown_vs_oracle(gpu, orc, scale, kew, per_slab):
     X = np.where(np.broadcast_to(mask, X.shape) == 0, np.float32(-9999.0), X).astype(np.float32)
     for nb_inc, nb_smooth, pval in ((20, 5, 0.0), (3, 0, -5.0), (200, 50, 0.0)):
         Xo, no = orc.bdrown(kew, X, mask, nb_inc, nb_smooth, -1.0e3, 1.0e3, pval)
-        for general in (False, True):      # on-chip one-CTA-per-slab kernel, and the general multi-launch path
+        for general in (0, 1, 2):      # on-chip one-CTA-per-slab kernel, and the general multi-launch path
             gpu.bdrown_force_general(general)
             try:
                 Xg, ng = gpu.bdrown(kew, X, mask, nb_inc, nb_smooth, -1.0e3, 1.0e3, pval)
@@ -121,6 +121,32 @@ def test_bdrown_vs_oracle(gpu, orc, scale, kew, per_slab):
             assert np.array_equal(Xg, Xo), f"bdrown(general={general}) differs at {(Xg != Xo).sum()} points, max {np.nanmax(np.abs(Xg - Xo))}"
             sea = np.broadcast_to(mask, X.shape) == 1
             assert np.array_equal(Xg[sea], np.clip(X[sea], -1.0e3, 1.0e3))    # mask==1 untouched (mod_bdrown.f90:22-24)
+
+
+def test_bdrown_negative_zero_and_big_slab(gpu, orc):
+    """(1) sea / land values that are exactly -0.0: `msk*X - (msk-1)*xorig` (mod_bdrown.f90:600) can flip their sign, the
+    land-only smoother must notice and hand over to the dense kernel; (2) a slab too large for the on-chip kernel with
+    a mask shared by several records (level lists, all slabs of a level in one launch)."""
+    cfg = G.config("D", 0.2)            # 512 x 256 regular
+    Xs, Ys = G.src_2d(cfg)
+    mask = G.land_mask(Xs, Ys)
+    X = (G.field_slabs(Xs, Ys, 3, seed=12) - 15.0).astype(np.float32)
+    X[:, mask == 0] = -9999.0
+    for variant in ("plain", "negzero"):
+        Xv = X.copy()
+        if variant == "negzero":
+            Xv[:, 5:60:3, 7:200:5] = np.float32(-0.0)
+            Xv[:, mask == 0] = np.where(Xv[:, mask == 0] == 0, np.float32(-0.0), np.float32(-9999.0))
+        for kew in (0, -1):
+            Xo, no = orc.bdrown(kew, Xv, mask, 30, 7, -1.0e3, 1.0e3, 0.0)
+            for general in (0, 2):
+                gpu.bdrown_force_general(general)
+                try:
+                    Xg, ng = gpu.bdrown(kew, Xv, mask, 30, 7, -1.0e3, 1.0e3, 0.0)
+                finally:
+                    gpu.bdrown_force_general(0)
+                assert np.array_equal(ng, no), (variant, kew, general)
+                assert np.array_equal(Xg.view(np.uint32), Xo.view(np.uint32)), (variant, kew, general, (Xg.view(np.uint32) != Xo.view(np.uint32)).sum())
 
 
 def test_bdrown_clamp_active(gpu, orc):
