@@ -181,7 +181,7 @@ __device__ __forceinline__ double d_guard(double rx) { return d_sign(1.0, rx) * 
 
 __global__ void __launch_bounds__(128)
 k_slopes(const double* __restrict__ ZX, const double* __restrict__ ZY, const double* __restrict__ ZFb, int nx, int ny,
-         double* dFdX, double* dFdY, double* d2F, size_t zf_stride, size_t out_stride) {
+         double* dFdX, double* dFdY, double* d2F, size_t zf_stride, size_t out_stride, const uint8_t* __restrict__ needed) {
   const int n8 = nx + 4;  // leading dimension of the extended arrays (nx is already the frame-extended extent)
   const double* ZF = ZFb + blockIdx.y * zf_stride;
   double* ox = dFdX + blockIdx.y * out_stride;
@@ -189,6 +189,7 @@ k_slopes(const double* __restrict__ ZX, const double* __restrict__ ZY, const dou
   double* oxy = d2F + blockIdx.y * out_stride;
   size_t n = (size_t)nx * ny;
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    if (needed && !needed[k]) continue;   // never read by the evaluation
     int jj = (int)(k / nx) + 1, ji = (int)(k % nx) + 1;
     int ip1 = ji + 1, ip2 = ji + 2, jp1 = jj + 1, jp2 = jj + 2;
     double m1, m2, m3, m4, Wx2 = 0., Wx3 = 0., Wy2 = 0., Wy3 = 0.;
@@ -284,6 +285,19 @@ __global__ void k_check_axes(const double* __restrict__ X, const double* __restr
     if (Y[k] != Y[(size_t)j * nx]) atomicOr(bad, 1);
     if (j == 0 && i > 0 && !(X[i] > X[i - 1])) atomicOr(bad, 1);
     if (i == 0 && j > 0 && !(Y[k] > Y[k - nx])) atomicOr(bad, 1);
+  }
+}
+
+// source points (frame-extended indexing) whose slopes the evaluation reads: the 4 corners of every cell that holds a
+// target inside the source range.  The slopes kernel skips the others (a regional target uses a fraction of the source).
+__global__ void k_akima_needed(const double* __restrict__ X2, const double* __restrict__ Y2, const int32_t* __restrict__ ixy, size_t nt,
+                               double x0, double x1, double y0, double y1, int ni1, uint8_t* needed) {
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
+    const double px2 = X2[k], py2 = Y2[k];
+    if (!(((px2 >= x0) && (px2 <= x1)) && ((py2 >= y0) && (py2 <= y1)))) continue;
+    const int ji = ixy[k], jj = ixy[k + nt];
+    const size_t c = (size_t)(ji - 1) + (size_t)(jj - 1) * ni1;
+    needed[c] = 1; needed[c + 1] = 1; needed[c + ni1] = 1; needed[c + ni1 + 1] = 1;
   }
 }
 
@@ -496,6 +510,10 @@ int akima_prepare_impl(sosie_ctx* ctx) {
   k_find_nearest_akima<<<grid_for(ctx, nt, 128), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ni1, nj1, ctx->ak_range[0], ctx->ak_range[1],
                                                                ctx->ak_range[2], ctx->ak_range[3], ctx->ak_X2.p, ctx->ak_Y2.p, nt,
                                                                hbad ? 0 : 1, ctx->ak_ixy.p); KLAUNCH_CHECK();
+  CK(ctx->ak_needed.alloc(ne));
+  CK(cudaMemsetAsync(ctx->ak_needed.p, 0, ne, st));
+  k_akima_needed<<<grid_for(ctx, nt, 256), 256, 0, st>>>(ctx->ak_X2.p, ctx->ak_Y2.p, ctx->ak_ixy.p, nt, ctx->ak_range[0], ctx->ak_range[1],
+                                                          ctx->ak_range[2], ctx->ak_range[3], ni1, ctx->ak_needed.p); KLAUNCH_CHECK();
   CK(cudaStreamSynchronize(st));
   ctx->ak_set = true;
   return SOSIE_OK;
@@ -525,7 +543,7 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
     k_feb_center<double><<<dim3(grid_for(ctx, ne8, 256), ns), 256, 0, st>>>(ctx->ak_zF.p, ni1, nj1, ctx->ak_ZF8.p, ne, ne8); KLAUNCH_CHECK();
     if (int rc = feb_field(ctx, kewp, ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, 0, ns, tmp)) return rc;
     k_slopes<<<dim3(grid_for(ctx, ne, 128), ns), 128, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
-                                                                ctx->ak_sxy.p, ne8, ne); KLAUNCH_CHECK();
+                                                                ctx->ak_sxy.p, ne8, ne, ctx->ak_needed.p); KLAUNCH_CHECK();
     prof_end(ctx, SOSIE_T_AKIMA_PREP);
     prof_begin(ctx, SOSIE_T_AKIMA_EVAL);
     k_akima_eval<<<dim3(grid_for(ctx, nt, 128), ns), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, ctx->ak_sx.p, ctx->ak_sy.p, ctx->ak_sxy.p,
