@@ -30,6 +30,7 @@ sys.path.insert(0, ROOT)
 from sosie_b200 import grids as G  # noqa: E402
 
 METRIC = "target points interpolated/sec (mapping + apply)"
+NCU_MAP_TRAFFIC_BYTES = 2148888000   # 0.794958 GB read + 1.353930 GB written per full-size launch (profiles/r01_ncu_E.md)
 UNIT = "points/s"
 
 
@@ -490,13 +491,18 @@ def run_ours(args):
         ctx._ck(rc)
 
     e2e_steps = max(1, min(args.steps, 5))
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    if args.no_e2e:   # profiling runs (ncu launch lists of the device-resident step only)
+        e2e_steps = 0
+        e2e_s = float("nan")
+        ctx.bilin_apply_dev(1, d_Z1, d_Z2)   # packed records exist for the bookkeeping below
+    else:
         step_host()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_host()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / e2e_steps
     if world > 1:
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -516,16 +522,20 @@ def run_ours(args):
 
     # sanity: the timed device path and the host path produce the same field on this rank's rows
     d_chk = d_Z2[r0 - 1:r1].cpu()
-    same = bool(torch.equal(d_chk, Z2_host[r0 - 1:r1]))
+    same = bool(torch.equal(d_chk, Z2_host[r0 - 1:r1])) if not args.no_e2e else None
 
     line = None
     if rank == 0:
         t_map = float(np.mean(kmap))
+        # 16 B target coordinates in; 30 B mapping (metrics, alpha/beta, iproblem, dist_np) out
         algo_map = (16 + 30) * my_targets + 8 * (nx1 + ny1)
         roofline = {
             "kernel": "k_map_easy (EASY search + MAPPING_BL body, fused)", "bound": "hbm",
             "achieved": algo_map / (t_map * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-            "frac": algo_map / (t_map * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "frac": algo_map / (t_map * 1e-3) / 1e9 / hbm_peak,
+            # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch, ncu --set full (profiles/r01_ncu_E.md);
+            # a constant of the N=1 full-scale workload, not measured live
+            "traffic": (NCU_MAP_TRAFFIC_BYTES if (world == 1 and args.scale == 1.0) else None), "peak_source": peak_src,
             "kernel_ms": t_map, "algorithmic_bytes": algo_map, "targets_per_s": my_targets / (t_map * 1e-3),
             "note": "the search is fp64-transcendental/latency bound, not HBM bound (SURVEY 8d): judged by targets/s and L2 hit rate; "
                     "the HBM-bound kernels (apply, drown) are listed under 'kernels' and 'others'",
@@ -537,7 +547,9 @@ def run_ours(args):
             {"kernel": "k_apply (E, 1 slab)", "ms": t_app, "algorithmic_bytes": algo_app,
              "achieved_gbs": algo_app / (t_app * 1e-3) / 1e9, "frac_hbm": algo_app / (t_app * 1e-3) / 1e9 / hbm_peak,
              "note": "algorithmic bytes count the whole 933 MB source slab although the regional target only touches ~15% of it"},
-            {"kernel": "k_pack (E)", "ms": float(np.mean(kpack))},
+            {"kernel": "k_pack (E)", "ms": float(np.mean(kpack)), "algorithmic_bytes": 62 * my_targets,
+             "achieved_gbs": 62 * my_targets / (float(np.mean(kpack)) * 1e-3) / 1e9,
+             "frac_hbm": 62 * my_targets / (float(np.mean(kpack)) * 1e-3) / 1e9 / hbm_peak},
         ]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -583,6 +595,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configs")
     ap.add_argument("--quick", action="store_true", help="smaller 'others' (fewer records for D)")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-pointer e2e leg (profiling runs only: the line is then not a bench result)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = max(args.warmup, 3)

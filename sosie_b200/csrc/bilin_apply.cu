@@ -16,63 +16,19 @@
 //   * optional fused post-ops of INTERP_2D (clamp :97-98, target mask :133-137) and the
 //     corr_vect rotation (src/corr_vect.f90:622-632).
 // Arithmetic is REAL(4) in the reference's order with FMA contraction off -> bit-identical fields.
-#include "geom.cuh"
-
-#define REC_COPY (-1)   // idx.x: copy Z1w(idx.y)
-#define REC_CONST (-2)  // idx.x: constant w.x
+#include "pack.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_pack(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ MT, const double* __restrict__ AB, int4* pidx,
        float4* pw, size_t k0, size_t kcnt) {
   const size_t nt = (size_t)tg.nx * tg.ny;
-  const int nxi = sg.nx, nyi = sg.nyw;
-  const double eps5 = (double)1.E-5f;
   for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < kcnt; kk += (size_t)gridDim.x * blockDim.x) {
     const size_t k = k0 + kk;
     int jj = (int)(k / tg.nx) + 1, ji = (int)(k % tg.nx) + 1;
-    int iP = max(MT[k], 1), jP = max(MT[k + nt], 1);  // IMETRICS(:,:,1:2) = MAX(IMETRICS(:,:,1:2), 1)  (:217)
-    int iqd = MT[k + 2 * nt];
-    double xa = AB[k], xb = AB[k + nt];
     int4 id;
-    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-    // a stale mapping could hold iP/jP beyond the source: the reference would read out of bounds
-    int iPc = min(iP, nxi), jPc = min(jP, nyi);
-    bool same = (fabs(d_degE_to_degWE(src_lon(sg, iPc, jPc)) - d_degE_to_degWE(trg_lon(tg, ji, jj))) < eps5) &&
-                (fabs(src_lat(sg, iPc, jPc) - trg_lat(tg, ji, jj)) < eps5);
-    if (same) {
-      id = make_int4(REC_COPY, (iPc - 1) + (jPc - 1) * nxi, 0, 0);
-    } else {
-      int jiPm1 = iP - 1, jiPp1 = iP + 1;
-      if ((jiPm1 == 0) && (k_ew >= 0)) jiPm1 = nxi - k_ew;
-      if ((jiPp1 == nxi + 1) && (k_ew >= 0)) jiPp1 = 1 + k_ew;
-      int i1 = 0, j1 = 0, i2 = 0, j2 = 0, i3 = 0, j3 = 0, i4 = 0, j4 = 0;  // Q19 (iqd outside 1..4 cannot occur after the fix-ups)
-      switch (iqd) {
-        case 1: i1 = iP; j1 = jP; i2 = jiPp1; j2 = jP; i3 = jiPp1; j3 = jP + 1; i4 = iP; j4 = jP + 1; break;
-        case 2: i1 = iP; j1 = jP; i2 = iP; j2 = jP - 1; i3 = jiPp1; j3 = jP - 1; i4 = jiPp1; j4 = jP; break;
-        case 3: i1 = iP; j1 = jP; i2 = jiPm1; j2 = jP; i3 = jiPm1; j3 = jP - 1; i4 = iP; j4 = jP - 1; break;
-        case 4: i1 = iP; j1 = jP; i2 = iP; j2 = jP + 1; i3 = jiPm1; j3 = jP + 1; i4 = jiPm1; j4 = jP; break;
-        default: break;
-      }
-      float w1 = (float)((1.0 - xa) * (1.0 - xb));
-      float w2 = (float)(xa * (1.0 - xb));
-      float w3 = (float)(xa * xb);
-      float w4 = (float)((1.0 - xa) * xb);
-      float wup = w1 + w2 + w3 + w4;
-      float cst = 0.f;
-      bool isc = true;
-      if (wup == 0.f) cst = -9998.f;
-      else if ((i1 < 1) || (i2 < 1) || (i3 < 1) || (i4 < 1)) cst = -9997.f;
-      else if ((j1 < 1) || (j2 < 1) || (j3 < 1) || (j4 < 1)) cst = -9996.f;
-      else if ((j1 > nyi) || (j2 > nyi) || (j3 > nyi) || (j4 > nyi)) cst = -9995.f;
-      else if ((i1 > nxi) || (i2 > nxi) || (i3 > nxi) || (i4 > nxi)) cst = -9994.f;
-      else isc = false;
-      if (isc) { id = make_int4(REC_CONST, 0, 0, 0); w.x = cst; }
-      else {
-        id = make_int4((i1 - 1) + (j1 - 1) * nxi, (i2 - 1) + (j2 - 1) * nxi, (i3 - 1) + (j3 - 1) * nxi, (i4 - 1) + (j4 - 1) * nxi);
-        w = make_float4(w1, w2, w3, w4);
-      }
-    }
+    float4 w;
+    pack_record(sg, k_ew, MT[k], MT[k + nt], MT[k + 2 * nt], AB[k], AB[k + nt], trg_lon(tg, ji, jj), trg_lat(tg, ji, jj), id, w);
     pidx[k] = id;
     pw[k] = w;
   }
