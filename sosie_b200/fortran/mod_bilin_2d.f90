@@ -23,13 +23,14 @@ CONTAINS
       INTEGER, OPTIONAL, DIMENSION(:,:), INTENT(in), TARGET :: mask_domain_trg
       !!
       INTEGER :: nx1, ny1, nx2, ny2, is1d, it1d
+      INTEGER(C_INT) :: ierr
       LOGICAL :: lefw
       CHARACTER(len=400) :: cf_wght
-      REAL(8),    DIMENSION(:,:),   ALLOCATABLE :: xs, ys, xt, yt     ! contiguous copies (assumed-shape actuals may be sections)
-      REAL(4),    DIMENSION(:,:),   ALLOCATABLE :: z1c, z2c
+      REAL(8),    DIMENSION(:,:),   ALLOCATABLE, TARGET :: xs, ys, xt, yt     ! contiguous copies (assumed-shape actuals may be sections)
+      REAL(4),    DIMENSION(:,:),   ALLOCATABLE, TARGET :: z1c, z2c
       INTEGER(4), DIMENSION(:,:),   ALLOCATABLE, TARGET :: mskc
-      INTEGER(4), DIMENSION(:,:,:), ALLOCATABLE :: imetrics
-      REAL(8),    DIMENSION(:,:,:), ALLOCATABLE :: rab
+      INTEGER(4), DIMENSION(:,:,:), ALLOCATABLE, TARGET :: imetrics
+      REAL(8),    DIMENSION(:,:,:), ALLOCATABLE, TARGET :: rab
       INTEGER(2), DIMENSION(:,:),   ALLOCATABLE :: ipb
       REAL(4),    DIMENSION(:,:),   ALLOCATABLE :: d2np
       TYPE(C_PTR) :: pmask
@@ -47,18 +48,28 @@ CONTAINS
          IF ( PRESENT(mask_domain_trg) ) THEN
             ALLOCATE ( mskc(nx2,ny2) ) ; mskc = mask_domain_trg ; pmask = C_LOC(mskc)
          END IF
-         CALL GPU_CHECK( sosie_bilin_set_grids(gpu_ctx, k_ew_per, nx1, ny1, xs, ys, is1d, MERGE(1,0,l_reg_src), &
-            &                                  nx2, ny2, xt, yt, it1d, pmask, i_orca_trg), 'BILIN_2D/set_grids' )
          ALLOCATE ( imetrics(nx2,ny2,3), rab(nx2,ny2,2), ipb(nx2,ny2), d2np(nx2,ny2) )
          WRITE(cf_wght,'("sosie_mapping_",a,".nc")') TRIM(cnpat)
          INQUIRE(FILE=cf_wght, EXIST=lefw )
          IF ( lefw ) THEN
             !! same cache file as stock SOSIE: a CPU-built mapping is reused as is
+            CALL GPU_CHECK( sosie_bilin_set_grids(gpu_ctx, k_ew_per, nx1, ny1, xs, ys, is1d, MERGE(1,0,l_reg_src), &
+               &                                  nx2, ny2, xt, yt, it1d, pmask, i_orca_trg), 'BILIN_2D/set_grids' )
             CALL RD_MAPPING_AB(cf_wght, imetrics, rab, ipb)
             CALL GPU_CHECK( sosie_bilin_load_map(gpu_ctx, nx2, ny2, imetrics, rab, ipb), 'BILIN_2D/load_map' )
+            CALL GPU_CHECK( sosie_bilin_apply(gpu_ctx, 1, z1c, z2c, 1), 'BILIN_2D/apply' )
          ELSE
-            CALL GPU_CHECK( sosie_bilin_map(gpu_ctx), 'MAPPING_BL' )
-            CALL GPU_CHECK( sosie_bilin_get_map(gpu_ctx, imetrics, rab, ipb, d2np, C_NULL_PTR), 'BILIN_2D/get_map' )
+            !! MAPPING_BL + first apply in ONE call: coordinate upload, search + weights, mapping download and the
+            !! apply overlap on three streams (csrc/bilin_pipeline.cu); the arrays are page-locked for the duration
+            ierr = sosie_host_register(C_LOC(xt),  INT(SIZE(xt),  C_SIZE_T)*8_C_SIZE_T)   ! best effort: unpinned arrays
+            ierr = sosie_host_register(C_LOC(yt),  INT(SIZE(yt),  C_SIZE_T)*8_C_SIZE_T)   ! still work, the copies then
+            ierr = sosie_host_register(C_LOC(rab), INT(SIZE(rab), C_SIZE_T)*8_C_SIZE_T)   ! do not overlap
+            ierr = sosie_host_register(C_LOC(imetrics), INT(SIZE(imetrics), C_SIZE_T)*4_C_SIZE_T)
+            ierr = sosie_host_register(C_LOC(z1c), INT(SIZE(z1c), C_SIZE_T)*4_C_SIZE_T)
+            CALL GPU_CHECK( sosie_bilin_2d_first(gpu_ctx, k_ew_per, nx1, ny1, xs, ys, is1d, z1c, nx2, ny2, xt, yt, it1d, z2c, &
+               &                                 pmask, MERGE(1,0,l_reg_src), i_orca_trg, 1, imetrics, rab, ipb, d2np), 'BILIN_2D/first' )
+            ierr = sosie_host_unregister(C_LOC(xt)) ; ierr = sosie_host_unregister(C_LOC(yt)) ; ierr = sosie_host_unregister(C_LOC(rab))
+            ierr = sosie_host_unregister(C_LOC(imetrics)) ; ierr = sosie_host_unregister(C_LOC(z1c))
             IF ( it1d == 1 ) THEN
                CALL P2D_MAPPING_AB(cf_wght, SPREAD(xt(:,1),2,ny2), SPREAD(yt(:,1),1,nx2), imetrics, rab, REAL(rmissval,8), ipb, d2np=d2np)
             ELSE
@@ -66,9 +77,10 @@ CONTAINS
             END IF
          END IF
          DEALLOCATE ( imetrics, rab, ipb, d2np, xs, ys, xt, yt )
+      ELSE
+         CALL GPU_CHECK( sosie_bilin_apply(gpu_ctx, 1, z1c, z2c, 0), 'BILIN_2D/apply' )
       END IF
 
-      CALL GPU_CHECK( sosie_bilin_apply(gpu_ctx, 1, z1c, z2c, MERGE(1,0,l_first_call_interp_routine)), 'BILIN_2D/apply' )
       Z2 = z2c
       DEALLOCATE ( z1c, z2c )
       l_first_call_interp_routine = .FALSE.

@@ -27,6 +27,30 @@ MODULE SOSIE_GPU_C
          INTEGER(C_INT), VALUE :: k_ew, nx1, ny1, src_1d, l_reg_src, nx2, ny2, trg_1d, i_orca_trg
          REAL(C_DOUBLE), INTENT(in) :: X10(*), Y10(*), X20(*), Y20(*)
       END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_2d_first(ctx, k_ew, nx1, ny1, X10, Y10, src_1d, Z1, nx2, ny2, X20, Y20, trg_1d, Z2, mask, &
+         &                                         l_reg_src, i_orca_trg, nslab, metrics, alphabeta, id_problem, dist_np) &
+         &                                         BIND(C, name='sosie_bilin_2d_first')
+         !! first call of BILIN_2D: MAPPING_BL + mapping arrays for P2D_MAPPING_AB + apply, pipelined (include/sosie_b200.h)
+         IMPORT :: C_PTR, C_INT, C_DOUBLE, C_FLOAT, C_SHORT
+         TYPE(C_PTR), VALUE    :: ctx, mask
+         INTEGER(C_INT), VALUE :: k_ew, nx1, ny1, src_1d, nx2, ny2, trg_1d, l_reg_src, i_orca_trg, nslab
+         REAL(C_DOUBLE), INTENT(in)  :: X10(*), Y10(*), X20(*), Y20(*)
+         REAL(C_FLOAT),  INTENT(in)  :: Z1(*)
+         REAL(C_FLOAT),  INTENT(out) :: Z2(*)
+         INTEGER(C_INT)   :: metrics(*)
+         REAL(C_DOUBLE)   :: alphabeta(*)
+         INTEGER(C_SHORT) :: id_problem(*)
+         REAL(C_FLOAT)    :: dist_np(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_host_register(p, nbytes) BIND(C, name='sosie_host_register')
+         IMPORT :: C_PTR, C_INT, C_SIZE_T
+         TYPE(C_PTR), VALUE       :: p
+         INTEGER(C_SIZE_T), VALUE :: nbytes
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_host_unregister(p) BIND(C, name='sosie_host_unregister')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: p
+      END FUNCTION
       INTEGER(C_INT) FUNCTION sosie_bilin_map(ctx) BIND(C, name='sosie_bilin_map')
          IMPORT :: C_PTR, C_INT
          TYPE(C_PTR), VALUE :: ctx
