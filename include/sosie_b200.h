@@ -194,6 +194,32 @@ int sosie_rotate_uv(sosie_ctx* ctx, int64_t n, int32_t nslab, const float* U, co
 int sosie_rotate_uv_dev(sosie_ctx* ctx, int64_t n, int32_t nslab, const float* dU, const float* dV,
                         const double* dxcos, const double* dxsin, float* dUo, float* dVo, int32_t inverse);
 
+/* ---- vertical stage of INTERP_3D: the cube stays in HBM between the horizontal and the vertical
+ * interpolation ----------------------------------------------------------------------------------------------------
+ * AKIMA_1D_3D(vz1, xf1, vz2, xf2, rfill_val), src/mod_akima_1d.f90:243-389 (z -> z levels, REAL(4)): xf1(nx,ny,nk1) ->
+ * xf2(nx,ny,nk2); vz1(nk1), vz2(nk2) are HOST arrays in both variants (the level search is done on the host once).   */
+int sosie_akima_1d_3d(sosie_ctx* ctx, int32_t nx, int32_t ny, int32_t nk1, const float* vz1, const float* xf1, int32_t nk2,
+                      const float* vz2, float* xf2, float rfill_val);
+int sosie_akima_1d_3d_dev(sosie_ctx* ctx, int32_t nx, int32_t ny, int32_t nk1, const float* vz1, const float* dxf1,
+                          int32_t nk2, const float* vz2, float* dxf2, float rfill_val);
+/* lbc_lnk(nperio, pt2d, cd_type, psgn [, pval]) on nslab REAL(4) slabs X(jpi,jpj,nslab), src/mod_nemotools.f90:65-417
+ * (E-W cyclic / closed, south row, north fold with T-point pivot nperio 3,4 or F-point pivot 5,6); cd_type is the
+ * character code ('T','U','V','F','W').  Callers: src/mod_interp.f90:131,504, src/corr_vect.f90:629-632.            */
+int sosie_lbc_lnk(sosie_ctx* ctx, int32_t nperio, int32_t jpi, int32_t jpj, int32_t nslab, float* X, int32_t cd_type,
+                  double psgn, int32_t has_pval, double pval);
+int sosie_lbc_lnk_dev(sosie_ctx* ctx, int32_t nperio, int32_t jpi, int32_t jpj, int32_t nslab, float* dX, int32_t cd_type,
+                      double psgn, int32_t has_pval, double pval);
+/* the post-interpolation block of INTERP_3D, src/mod_interp.f90:447-511, on X(ni,nj,nk) in place: persistence of the
+ * last wet value into the sea-bed (ixtrpl_bot == 1), bounds vmin/vmax (rmiss_val untouched), lbc_lnk when
+ * i_orca_trg > 0 (c_orca_trg = 'T','U','V','F'), target mask when lmout.  mask_trg(ni,nj,nk) INTEGER(4), may be NULL
+ * when neither ixtrpl_bot == 1 nor lmout.  The optional SMOOTHER calls of that block are sosie_smoother.            */
+int sosie_interp3d_post(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk, float* X, const int32_t* mask_trg,
+                        int32_t ixtrpl_bot, float vmin, float vmax, float rmiss_val, int32_t i_orca_trg,
+                        int32_t c_orca_trg, int32_t lmout);
+int sosie_interp3d_post_dev(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk, float* dX, const int32_t* dmask_trg,
+                            int32_t ixtrpl_bot, float vmin, float vmax, float rmiss_val, int32_t i_orca_trg,
+                            int32_t c_orca_trg, int32_t lmout);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ _lib = None
 
 def build(force: bool = False):
     """Compile the oracle with the committed Makefile (g++ -O3 -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("orc_bilin.cpp", "orc_akima_drown.cpp", "orc_common.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("orc_bilin.cpp", "orc_akima_drown.cpp", "orc_vert.cpp", "orc_common.hpp")]
     srcs.append(os.path.join(_HERE, "..", "sosie_b200", "csrc", "pmath.h"))
     if not force and os.path.exists(_LIB_PATH):
         t = os.path.getmtime(_LIB_PATH)
@@ -285,3 +285,36 @@ def rotate_uv(U, V, xcos, xsin, inverse=False):
     lib().orc_rotate_uv(C.c_int64(n), nslab, _p(U, C.c_float), _p(V, C.c_float), _p(xcos, C.c_double), _p(xsin, C.c_double),
                         _p(Uo, C.c_float), _p(Vo, C.c_float), int(inverse))
     return Uo, Vo
+
+
+# ---- vertical stage of INTERP_3D (orc_vert.cpp)
+def akima_1d_3d(vz1, xf1, vz2, rfill_val=-9999.0):
+    """AKIMA_1D_3D, src/mod_akima_1d.f90:243-389: xf1 (nk1, ny, nx) -> (nk2, ny, nx)"""
+    vz1, vz2, xf1 = _f32(vz1), _f32(vz2), _f32(xf1)
+    nk1, ny, nx = xf1.shape
+    xf2 = np.empty((vz2.size, ny, nx), np.float32)
+    lib().orc_akima_1d_3d(nx, ny, nk1, _p(vz1, C.c_float), _p(xf1, C.c_float), vz2.size, _p(vz2, C.c_float), _p(xf2, C.c_float),
+                          C.c_float(rfill_val))
+    return xf2
+
+
+def lbc_lnk(nperio, X, cd_type="T", psgn=1.0, pval=None):
+    """lbc_lnk_2d_r4, src/mod_nemotools.f90:154: slabs X (nslab, jpj, jpi) or (jpj, jpi)"""
+    X = _f32(X).copy()
+    sq = X.ndim == 2
+    if sq:
+        X = X[None]
+    nslab, jpj, jpi = X.shape
+    lib().orc_lbc_lnk(int(nperio), jpi, jpj, nslab, _p(X, C.c_float), ord(cd_type), C.c_double(psgn), int(pval is not None),
+                      C.c_double(0.0 if pval is None else pval))
+    return X[0] if sq else X
+
+
+def interp3d_post(X, mask_trg=None, ixtrpl_bot=0, vmin=-1.0e30, vmax=1.0e30, rmiss_val=-9999.0, i_orca_trg=0, c_orca_trg="T", lmout=False):
+    """post-interpolation block of INTERP_3D, src/mod_interp.f90:447-511: X (nk, nj, ni)"""
+    X = _f32(X).copy()
+    nk, nj, ni = X.shape
+    m = None if mask_trg is None else _i32(mask_trg)
+    lib().orc_interp3d_post(ni, nj, nk, _p(X, C.c_float), _p(m, C.c_int32), int(ixtrpl_bot), C.c_float(vmin), C.c_float(vmax),
+                            C.c_float(rmiss_val), int(i_orca_trg), ord(c_orca_trg), int(lmout))
+    return X

@@ -1,0 +1,319 @@
+// TEST INFRASTRUCTURE -- CPU oracle for sosie_b200 (parity unpinned by the reference: see DESIGN.md).
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this library.
+//
+// Vertical stage of INTERP_3D, restated statement by statement:
+//   AKIMA_1D_3D + slopes_3d + extra_2_top_3d / extra_2_bottom_3d   src/mod_akima_1d.f90:243-389, 461-515, 521-606
+//   lbc_lnk_2d_r4 / lbc_lnk_2d_r8 / lbc_nfd_2d                      src/mod_nemotools.f90:65-417
+//   post-interpolation block of INTERP_3D                           src/mod_interp.f90:447-511
+// All arithmetic REAL(4) in source order (compiled -ffp-contract=off); whole-array statements are
+// evaluated right-hand side first, as Fortran requires.
+#include "orc_common.hpp"
+
+namespace orc {
+
+// extra_2_top_3d (:521-560): Xf4, Xf5 from Xf1..Xf3, per (i,j)
+static void extra_2_top_3d(float x1, float x2, float x3, float x4, float x5, const float* Xf1, const float* Xf2, const float* Xf3,
+                           float* Xf4, float* Xf5, int64_t n) {
+  float A = x2 - x1, B = x3 - x2, C = x4 - x3, D = x5 - x4;
+  for (int64_t k = 0; k < n; k++) {
+    float ALF = Xf2[k] - Xf1[k], BET = Xf3[k] - Xf2[k];
+    if ((A == 0.f) || (B == 0.f) || (C == 0.f)) { Xf4[k] = Xf3[k]; Xf5[k] = Xf3[k]; }
+    else {
+      float v4 = C * (2 * BET / B - ALF / A) + Xf3[k];
+      Xf4[k] = v4;
+      Xf5[k] = v4 + v4 * D / C + BET * D / B - ALF * D / A - Xf3[k] * D / C;
+    }
+  }
+}
+// extra_2_bottom_3d (:563-606): Xf2, Xf1 from Xf5, Xf4, Xf3
+static void extra_2_bottom_3d(float x5, float x4, float x3, float x2, float x1, const float* Xf5, const float* Xf4, const float* Xf3,
+                              float* Xf2, float* Xf1, int64_t n) {
+  float A = x4 - x5, B = x3 - x4, C = x2 - x3, D = x1 - x2;
+  for (int64_t k = 0; k < n; k++) {
+    float ALF = Xf4[k] - Xf5[k], BET = Xf3[k] - Xf4[k];
+    if ((A == 0.f) || (B == 0.f) || (C == 0.f)) { Xf2[k] = Xf3[k]; Xf1[k] = Xf3[k]; }
+    else {
+      float v2 = C * (2 * BET / B - ALF / A) + Xf3[k];
+      Xf2[k] = v2;
+      Xf1[k] = v2 + v2 * D / C + BET * D / B - ALF * D / A - Xf3[k] * D / C;
+    }
+  }
+}
+
+// slopes_3d (:461-515); vz(1..nz), Xf / slope (n, nz) with n = nx*ny
+static void slopes_3d(const float* vz, const float* Xf, float* slope, int64_t n, int nz) {
+  auto F = [&](int k) { return Xf + (int64_t)(k - 1) * n; };
+  auto S = [&](int k) { return slope + (int64_t)(k - 1) * n; };
+  auto Z = [&](int k) { return vz[k - 1]; };
+  for (int k = 3; k <= nz - 2; k++) {
+    for (int64_t p = 0; p < n; p++) {
+      float m1 = (F(k - 1)[p] - F(k - 2)[p]) / (Z(k - 1) - Z(k - 2));
+      float m2 = (F(k)[p] - F(k - 1)[p]) / (Z(k) - Z(k - 1));
+      float m3 = (F(k + 1)[p] - F(k)[p]) / (Z(k + 1) - Z(k));
+      float m4 = (F(k + 2)[p] - F(k + 1)[p]) / (Z(k + 2) - Z(k + 1));
+      if ((m1 == m2) && (m3 == m4)) S(k)[p] = 0.5f * (m2 + m3);
+      else S(k)[p] = (std::fabs(m4 - m3) * m2 + std::fabs(m2 - m1) * m3) / (std::fabs(m4 - m3) + std::fabs(m2 - m1));
+    }
+  }
+  for (int64_t p = 0; p < n; p++) {
+    float m2 = (F(2)[p] - F(1)[p]) / (Z(2) - Z(1));
+    float m3 = (F(3)[p] - F(2)[p]) / (Z(3) - Z(2));
+    S(2)[p] = 0.5f * (m2 + m3);
+    m2 = (F(nz - 1)[p] - F(nz - 2)[p]) / (Z(nz - 1) - Z(nz - 2));
+    m3 = (F(nz)[p] - F(nz - 1)[p]) / (Z(nz) - Z(nz - 1));
+    S(nz - 1)[p] = 0.5f * (m2 + m3);
+    m3 = (F(2)[p] - F(1)[p]) / (Z(2) - Z(1));
+    S(1)[p] = m3;
+    m2 = (F(nz)[p] - F(nz - 1)[p]) / (Z(nz) - Z(nz - 1));
+    S(nz)[p] = m2;
+  }
+}
+
+// AKIMA_1D_3D (:243-389)
+static void akima_1d_3d(int nx, int ny, int nk1, const float* vz1, const float* xf1, int nk2, const float* vz2, float* xf2,
+                        float rfill_val) {
+  const int64_t n = (int64_t)nx * ny;
+  const int nk1e = nk1 + 4;
+  std::vector<float> vz1e(nk1e + 1), xf1e((size_t)n * nk1e), xslp((size_t)n * nk1e);
+  auto VZ1 = [&](int k) { return vz1[k - 1]; };
+  auto VZ2 = [&](int k) { return vz2[k - 1]; };
+  auto E = [&](int k) -> float& { return vz1e[k]; };  // 1-based
+  auto FE = [&](int k) { return xf1e.data() + (int64_t)(k - 1) * n; };
+  auto SL = [&](int k) { return xslp.data() + (int64_t)(k - 1) * n; };
+  auto F1 = [&](int k) { return xf1 + (int64_t)(k - 1) * n; };
+  auto F2 = [&](int k) { return xf2 + (int64_t)(k - 1) * n; };
+  for (int k = 1; k <= nk1; k++) { E(k + 2) = VZ1(k); std::memcpy(FE(k + 2), F1(k), sizeof(float) * n); }
+  E(2) = E(4) - (E(5) - E(3));
+  E(1) = E(3) - (E(5) - E(3));
+  E(nk1e - 1) = E(nk1e - 3) + E(nk1e - 2) - E(nk1e - 4);
+  E(nk1e) = E(nk1e - 2) + E(nk1e - 2) - E(nk1e - 4);
+  extra_2_bottom_3d(E(5), E(4), E(3), E(2), E(1), FE(5), FE(4), FE(3), FE(2), FE(1), n);
+  extra_2_top_3d(E(nk1e - 4), E(nk1e - 3), E(nk1e - 2), E(nk1e - 1), E(nk1e), FE(nk1e - 4), FE(nk1e - 3), FE(nk1e - 2), FE(nk1e - 1),
+                 FE(nk1e), n);
+  slopes_3d(vz1e.data() + 1, xf1e.data(), xslp.data(), n, nk1e);
+  for (int jk2 = 1; jk2 <= nk2; jk2++) {
+    bool l_do_interp = true, lfnd = false;
+    int jk1 = 1, jp1 = 0, jp2 = 0;
+    if (VZ2(jk2) < VZ1(1)) { std::memcpy(F2(jk2), F1(1), sizeof(float) * n); l_do_interp = false; }
+    while ((!lfnd) && l_do_interp) {
+      if (jk1 == nk1) break;
+      if ((VZ2(jk2) > VZ1(jk1)) && (VZ2(jk2) <= VZ1(jk1 + 1))) {
+        int jk1e = jk1 + 2;
+        jp1 = jk1e; jp2 = jk1e + 1;
+        lfnd = true;
+      } else {
+        if (VZ2(jk2) == VZ1(jk1)) { std::memcpy(F2(jk2), F1(jk1), sizeof(float) * n); l_do_interp = false; break; }
+        else if (VZ2(jk2) == VZ1(jk1 + 1)) { std::memcpy(F2(jk2), F1(jk1 + 1), sizeof(float) * n); l_do_interp = false; break; }
+      }
+      jk1 = jk1 + 1;
+    }
+    if ((jk1 == nk1) && (!lfnd)) { std::memcpy(F2(jk2), F1(nk1), sizeof(float) * n); l_do_interp = false; }
+    if (!lfnd) { for (int64_t p = 0; p < n; p++) F2(jk2)[p] = rfill_val; l_do_interp = false; }
+    if (l_do_interp) {
+      float dz = 1.f / (E(jp2) - E(jp1));
+      float dz2 = dz * dz;
+      float dzt = VZ2(jk2) - E(jp1);
+      float dzt2 = dzt * dzt;
+      const float dv = E(jp2) - E(jp1);
+      for (int64_t p = 0; p < n; p++) {
+        float a0 = FE(jp1)[p];
+        float a1 = SL(jp1)[p];
+        float a2 = (3 * (FE(jp2)[p] - FE(jp1)[p]) * dz - 2 * SL(jp1)[p] - SL(jp2)[p]) * dz;
+        float a3 = (SL(jp1)[p] + SL(jp2)[p] - 2 * (FE(jp2)[p] - FE(jp1)[p]) / dv) * dz2;
+        F2(jk2)[p] = a0 + a1 * dzt + a2 * dzt2 + a3 * dzt2 * dzt;
+      }
+    }
+  }
+  // SURFACE persistence (:372-377)
+  int jk2 = 1;
+  while ((VZ2(jk2) < VZ1(1)) && (jk2 < nk2)) { std::memcpy(F2(jk2), F1(1), sizeof(float) * n); jk2 = jk2 + 1; }
+  // BOTTOM persistence (:381-385); the reference reads vz2(0) when every target level is deeper: DEFINED stop at 0
+  jk2 = nk2;
+  while ((jk2 > 0) && (VZ2(jk2) > VZ1(nk1))) { std::memcpy(F2(jk2), F1(nk1), sizeof(float) * n); jk2 = jk2 - 1; }
+}
+
+// lbc_nfd_2d (src/mod_nemotools.f90:199-417) on a REAL(8) work array, jpni = 1
+static void lbc_nfd_2d(int npolj, A2<double> pt2d, char cd_type, double psgn) {
+  const int jpiglo = (int)pt2d.ni, ijpj = (int)pt2d.nj, ipr2dj = 0, ijpjm1 = ijpj - 1;
+  switch (npolj) {
+    case 3: case 4:
+      switch (cd_type) {
+        case 'T': case 'W':
+          for (int jl = 0; jl <= ipr2dj; jl++)
+            for (int ji = 2; ji <= jpiglo; ji++) { int ijt = jpiglo - ji + 2; pt2d(ji, ijpj + jl) = psgn * pt2d(ijt, ijpj - 2 - jl); }
+          pt2d(1, ijpj) = psgn * pt2d(3, ijpj - 2);
+          for (int ji = jpiglo / 2 + 1; ji <= jpiglo; ji++) { int ijt = jpiglo - ji + 2; pt2d(ji, ijpj - 1) = psgn * pt2d(ijt, ijpj - 1); }
+          break;
+        case 'U':
+          for (int jl = 0; jl <= ipr2dj; jl++)
+            for (int ji = 1; ji <= jpiglo - 1; ji++) { int iju = jpiglo - ji + 1; pt2d(ji, ijpj + jl) = psgn * pt2d(iju, ijpj - 2 - jl); }
+          pt2d(1, ijpj) = psgn * pt2d(2, ijpj - 2);
+          pt2d(jpiglo, ijpj) = psgn * pt2d(jpiglo - 1, ijpj - 2);
+          pt2d(1, ijpj - 1) = psgn * pt2d(jpiglo, ijpj - 1);
+          for (int ji = jpiglo / 2; ji <= jpiglo - 1; ji++) { int iju = jpiglo - ji + 1; pt2d(ji, ijpjm1) = psgn * pt2d(iju, ijpjm1); }
+          break;
+        case 'V':
+          for (int jl = -1; jl <= ipr2dj; jl++)
+            for (int ji = 2; ji <= jpiglo; ji++) { int ijt = jpiglo - ji + 2; pt2d(ji, ijpj + jl) = psgn * pt2d(ijt, ijpj - 3 - jl); }
+          pt2d(1, ijpj) = psgn * pt2d(3, ijpj - 3);
+          break;
+        case 'F':
+          for (int jl = -1; jl <= ipr2dj; jl++)
+            for (int ji = 1; ji <= jpiglo - 1; ji++) { int iju = jpiglo - ji + 1; pt2d(ji, ijpj + jl) = psgn * pt2d(iju, ijpj - 3 - jl); }
+          pt2d(1, ijpj) = psgn * pt2d(2, ijpj - 3);
+          pt2d(jpiglo, ijpj) = psgn * pt2d(jpiglo - 1, ijpj - 3);
+          pt2d(jpiglo, ijpj - 1) = psgn * pt2d(jpiglo - 1, ijpj - 2);
+          pt2d(1, ijpj - 1) = psgn * pt2d(2, ijpj - 2);
+          break;
+        default: g_error |= 64; break;  // ice points: not used by SOSIE's callers
+      }
+      break;
+    case 5: case 6:
+      switch (cd_type) {
+        case 'T': case 'W':
+          for (int jl = 0; jl <= ipr2dj; jl++)
+            for (int ji = 1; ji <= jpiglo; ji++) { int ijt = jpiglo - ji + 1; pt2d(ji, ijpj + jl) = psgn * pt2d(ijt, ijpj - 1 - jl); }
+          break;
+        case 'U':
+          for (int jl = 0; jl <= ipr2dj; jl++)
+            for (int ji = 1; ji <= jpiglo - 1; ji++) { int iju = jpiglo - ji; pt2d(ji, ijpj + jl) = psgn * pt2d(iju, ijpj - 1 - jl); }
+          pt2d(jpiglo, ijpj) = psgn * pt2d(1, ijpj - 1);
+          break;
+        case 'V':
+          for (int jl = 0; jl <= ipr2dj; jl++)
+            for (int ji = 1; ji <= jpiglo; ji++) { int ijt = jpiglo - ji + 1; pt2d(ji, ijpj + jl) = psgn * pt2d(ijt, ijpj - 2 - jl); }
+          for (int ji = jpiglo / 2 + 1; ji <= jpiglo; ji++) { int ijt = jpiglo - ji + 1; pt2d(ji, ijpjm1) = psgn * pt2d(ijt, ijpjm1); }
+          break;
+        case 'F':
+          for (int jl = 0; jl <= ipr2dj; jl++)
+            for (int ji = 1; ji <= jpiglo - 1; ji++) { int iju = jpiglo - ji; pt2d(ji, ijpj + jl) = psgn * pt2d(iju, ijpj - 2 - jl); }
+          pt2d(jpiglo, ijpj) = psgn * pt2d(1, ijpj - 2);
+          for (int ji = jpiglo / 2 + 1; ji <= jpiglo - 1; ji++) { int iju = jpiglo - ji; pt2d(ji, ijpjm1) = psgn * pt2d(iju, ijpjm1); }
+          break;
+        default: g_error |= 64; break;
+      }
+      break;
+    default:
+      switch (cd_type) {
+        case 'T': case 'U': case 'V': case 'W':
+          for (int ji = 1; ji <= jpiglo; ji++) { pt2d(ji, 1) = 0.0; pt2d(ji, ijpj) = 0.0; }
+          break;
+        case 'F':
+          for (int ji = 1; ji <= jpiglo; ji++) pt2d(ji, ijpj) = 0.0;
+          break;
+        default: g_error |= 64; break;
+      }
+      break;
+  }
+}
+
+// lbc_lnk_2d_r8 (:65-150)
+static void lbc_lnk_2d_r8(int nperio, A2<double> pt2d, char cd_type, double psgn, bool has_pval, double pval) {
+  const double zland = has_pval ? pval : 0.0;
+  const int jpi = (int)pt2d.ni, jpj = (int)pt2d.nj, jpim1 = jpi - 1;
+  switch (nperio) {
+    case 1: case 4: case 6:
+      for (int j = 1; j <= jpj; j++) pt2d(1, j) = pt2d(jpim1, j);
+      for (int j = 1; j <= jpj; j++) pt2d(jpi, j) = pt2d(2, j);
+      break;
+    default:
+      switch (cd_type) {
+        case 'T': case 'U': case 'V': case 'W':
+          for (int j = 1; j <= jpj; j++) { pt2d(1, j) = zland; }
+          for (int j = 1; j <= jpj; j++) { pt2d(jpi, j) = zland; }
+          break;
+        case 'F':
+          for (int j = 1; j <= jpj; j++) pt2d(jpi, j) = zland;
+          break;
+        default: break;
+      }
+      break;
+  }
+  switch (nperio) {
+    case 2:
+      switch (cd_type) {
+        case 'T': case 'U': case 'W':
+          for (int i = 1; i <= jpi; i++) pt2d(i, 1) = pt2d(i, 3);
+          for (int i = 1; i <= jpi; i++) pt2d(i, jpj) = zland;
+          break;
+        case 'V': case 'F':
+          for (int i = 1; i <= jpi; i++) pt2d(i, 1) = psgn * pt2d(i, 2);
+          for (int i = 1; i <= jpi; i++) pt2d(i, jpj) = zland;
+          break;
+        default: break;
+      }
+      break;
+    case 3: case 4: case 5: case 6:
+      switch (cd_type) {
+        case 'T': case 'U': case 'V': case 'W': case 'I':
+          for (int i = 1; i <= jpi; i++) pt2d(i, 1) = zland;
+          break;
+        default: break;
+      }
+      lbc_nfd_2d(nperio, pt2d, cd_type, psgn);
+      break;
+    default:
+      switch (cd_type) {
+        case 'T': case 'U': case 'V': case 'W':
+          for (int i = 1; i <= jpi; i++) pt2d(i, 1) = zland;
+          for (int i = 1; i <= jpi; i++) pt2d(i, jpj) = zland;
+          break;
+        case 'F':
+          for (int i = 1; i <= jpi; i++) pt2d(i, jpj) = zland;
+          break;
+        default: break;
+      }
+      break;
+  }
+}
+
+// lbc_lnk_2d_r4 (:154-190): through a REAL(8) copy
+static void lbc_lnk_2d_r4(int nperio, float* X, int jpi, int jpj, char cd_type, double psgn, bool has_pval, double pval) {
+  std::vector<double> w((size_t)jpi * jpj);
+  for (size_t k = 0; k < w.size(); k++) w[k] = (double)X[k];
+  lbc_lnk_2d_r8(nperio, A2<double>(w.data(), jpi, jpj), cd_type, psgn, has_pval, pval);
+  for (size_t k = 0; k < w.size(); k++) X[k] = (float)w[k];
+}
+
+}  // namespace orc
+
+extern "C" {
+
+void orc_akima_1d_3d(int nx, int ny, int nk1, const float* vz1, const float* xf1, int nk2, const float* vz2, float* xf2, float rfill_val) {
+  orc::akima_1d_3d(nx, ny, nk1, vz1, xf1, nk2, vz2, xf2, rfill_val);
+}
+
+void orc_lbc_lnk(int nperio, int jpi, int jpj, int nslab, float* X, int cd_type, double psgn, int has_pval, double pval) {
+  for (int s = 0; s < nslab; s++) orc::lbc_lnk_2d_r4(nperio, X + (size_t)s * jpi * jpj, jpi, jpj, (char)cd_type, psgn, has_pval != 0, pval);
+}
+
+// post-interpolation block of INTERP_3D (src/mod_interp.f90:447-511) without the optional SMOOTHER calls:
+// bottom persistence (ixtrpl_bot == 1), bounds, lbc_lnk on ORCA targets, target mask
+void orc_interp3d_post(int ni, int nj, int nk, float* X, const int32_t* mask_trg, int ixtrpl_bot, float vmin, float vmax, float rmiss_val,
+                       int i_orca_trg, int c_orca_trg, int lmout) {
+  const int64_t n = (int64_t)ni * nj;
+  if (ixtrpl_bot == 1) {
+    for (int64_t p = 0; p < n; p++) {
+      if (mask_trg[p] == 1) {
+        int jk_bot = 0;  // FINDLOC(mask_trg(ji,jj,:), 0, DIM=1): first bedrock point (0 when none)
+        for (int k = 1; k <= nk; k++) if (mask_trg[p + (int64_t)(k - 1) * n] == 0) { jk_bot = k; break; }
+        if (jk_bot > 1) {
+          float zwet = (float)(double)X[p + (int64_t)(jk_bot - 2) * n];  // zwet is REAL(8): exact round trip
+          for (int k = jk_bot; k <= nk; k++) X[p + (int64_t)(k - 1) * n] = zwet;
+        }
+      }
+    }
+  }
+  for (int k = 1; k <= nk; k++) {
+    float* Xk = X + (int64_t)(k - 1) * n;
+    for (int64_t p = 0; p < n; p++) if ((Xk[p] > vmax) && (Xk[p] != rmiss_val)) Xk[p] = vmax;
+    for (int64_t p = 0; p < n; p++) if ((Xk[p] < vmin) && (Xk[p] != rmiss_val)) Xk[p] = vmin;
+    if (i_orca_trg > 0) orc::lbc_lnk_2d_r4(i_orca_trg, Xk, ni, nj, (char)c_orca_trg, 1.0, false, 0.0);
+    if (lmout) {
+      const int32_t* mk = mask_trg + (int64_t)(k - 1) * n;
+      for (int64_t p = 0; p < n; p++) Xk[p] = Xk[p] * (float)mk[p] + (1.f - (float)mk[p]) * rmiss_val;
+    }
+  }
+}
+
+}  // extern "C"

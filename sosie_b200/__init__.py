@@ -40,6 +40,7 @@ EXPORTS = [
     "sosie_akima_apply_dev", "sosie_akima_get_ixy", "sosie_bdrown", "sosie_bdrown_dev", "sosie_bdrown_force_general", "sosie_smoother", "sosie_drown",
     "sosie_rotate_uv", "sosie_rotate_uv_dev", "sosie_bilin_2d_first", "sosie_set_pipeline_min_targets",
     "sosie_host_register", "sosie_host_unregister", "sosie_bilin_src_rows",
+    "sosie_akima_1d_3d", "sosie_akima_1d_3d_dev", "sosie_lbc_lnk", "sosie_lbc_lnk_dev", "sosie_interp3d_post", "sosie_interp3d_post_dev",
 ]
 
 _lib = None
@@ -364,6 +365,43 @@ class Sosie:
         nsw = np.zeros(nslab, np.int32)
         self._ck(self._lib.sosie_drown(self._h, int(k_ew), ni, nj, nslab, _p(X), _p(mask), int(nb_inc), _p(nsw)))
         return (X[0] if sq else X), nsw
+
+    # ---------------------------------------------------------------- vertical stage of INTERP_3D
+    def akima_1d_3d(self, vz1, xf1, vz2, rfill_val=-9999.0):
+        """AKIMA_1D_3D(vz1, xf1, vz2, xf2, rfill_val), src/mod_akima_1d.f90:243: xf1 (nk1, ny, nx) -> (nk2, ny, nx)"""
+        vz1, vz2, xf1 = _f32(vz1), _f32(vz2), _f32(xf1)
+        nk1, ny, nx = xf1.shape
+        xf2 = np.empty((vz2.size, ny, nx), np.float32)
+        self._ck(self._lib.sosie_akima_1d_3d(self._h, nx, ny, nk1, _p(vz1), _p(xf1), vz2.size, _p(vz2), _p(xf2), C.c_float(rfill_val)))
+        return xf2
+
+    def akima_1d_3d_dev(self, nx, ny, vz1, dxf1, vz2, dxf2, rfill_val=-9999.0):
+        vz1, vz2 = _f32(vz1), _f32(vz2)
+        self._ck(self._lib.sosie_akima_1d_3d_dev(self._h, nx, ny, vz1.size, _p(vz1), _dp(dxf1), vz2.size, _p(vz2), _dp(dxf2), C.c_float(rfill_val)))
+
+    def lbc_lnk(self, nperio, X, cd_type="T", psgn=1.0, pval=None):
+        """lbc_lnk(nperio, pt2d, cd_type, psgn [, pval]) on slabs X (nslab, jpj, jpi), src/mod_nemotools.f90:65"""
+        X = _f32(X).copy()
+        sq = X.ndim == 2
+        if sq:
+            X = X[None]
+        nslab, jpj, jpi = X.shape
+        self._ck(self._lib.sosie_lbc_lnk(self._h, int(nperio), jpi, jpj, nslab, _p(X), ord(cd_type), C.c_double(psgn),
+                                         int(pval is not None), C.c_double(0.0 if pval is None else pval)))
+        return X[0] if sq else X
+
+    def interp3d_post(self, X, mask_trg=None, ixtrpl_bot=0, vmin=-1.0e30, vmax=1.0e30, rmiss_val=-9999.0, i_orca_trg=0, c_orca_trg="T", lmout=False):
+        """post-interpolation block of INTERP_3D (src/mod_interp.f90:447-511) on X (nk, nj, ni)"""
+        X = _f32(X).copy()
+        nk, nj, ni = X.shape
+        m = None if mask_trg is None else _i32(mask_trg)
+        self._ck(self._lib.sosie_interp3d_post(self._h, ni, nj, nk, _p(X), _p(m), int(ixtrpl_bot), C.c_float(vmin), C.c_float(vmax),
+                                               C.c_float(rmiss_val), int(i_orca_trg), ord(c_orca_trg), int(lmout)))
+        return X
+
+    def interp3d_post_dev(self, ni, nj, nk, dX, dmask_trg, ixtrpl_bot, vmin, vmax, rmiss_val, i_orca_trg, c_orca_trg, lmout):
+        self._ck(self._lib.sosie_interp3d_post_dev(self._h, int(ni), int(nj), int(nk), _dp(dX), _dp(dmask_trg), int(ixtrpl_bot), C.c_float(vmin),
+                                                   C.c_float(vmax), C.c_float(rmiss_val), int(i_orca_trg), ord(c_orca_trg), int(lmout)))
 
     def rotate_uv(self, U, V, xcos, xsin, inverse=False):
         U, V = _f32(U), _f32(V)

@@ -520,6 +520,73 @@ int sosie_drown(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nsla
   return SOSIE_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------
+int sosie_akima_1d_3d_dev(sosie_ctx* c, int32_t nx, int32_t ny, int32_t nk1, const float* vz1, const float* dxf1, int32_t nk2,
+                          const float* vz2, float* dxf2, float rfill_val) {
+  NEED(c);
+  return akima_1d_3d_impl(ctx, nx, ny, nk1, vz1, dxf1, nk2, vz2, dxf2, rfill_val);
+}
+
+int sosie_akima_1d_3d(sosie_ctx* c, int32_t nx, int32_t ny, int32_t nk1, const float* vz1, const float* xf1, int32_t nk2, const float* vz2,
+                      float* xf2, float rfill_val) {
+  NEED(c);
+  if (nx < 1 || ny < 1 || nk1 < 3 || nk2 < 1 || !xf1 || !xf2) { ctx->err = "sosie_akima_1d_3d: bad arguments"; return SOSIE_ERR_ARG; }
+  const size_t n = (size_t)nx * ny;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->v_in.alloc(n * nk1)); CK(ctx->v_out.alloc(n * nk2));
+  CK(cudaMemcpyAsync(ctx->v_in.p, xf1, n * nk1 * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = akima_1d_3d_impl(ctx, nx, ny, nk1, vz1, ctx->v_in.p, nk2, vz2, ctx->v_out.p, rfill_val)) return rc;
+  CK(cudaMemcpyAsync(xf2, ctx->v_out.p, n * nk2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_lbc_lnk_dev(sosie_ctx* c, int32_t nperio, int32_t jpi, int32_t jpj, int32_t nslab, float* dX, int32_t cd_type, double psgn,
+                      int32_t has_pval, double pval) {
+  NEED(c);
+  return lbc_lnk_impl(ctx, nperio, jpi, jpj, nslab, dX, cd_type, psgn, has_pval, pval);
+}
+
+int sosie_lbc_lnk(sosie_ctx* c, int32_t nperio, int32_t jpi, int32_t jpj, int32_t nslab, float* X, int32_t cd_type, double psgn,
+                  int32_t has_pval, double pval) {
+  NEED(c);
+  if (jpi < 4 || jpj < 4 || nslab < 1 || !X) { ctx->err = "sosie_lbc_lnk: bad arguments"; return SOSIE_ERR_ARG; }
+  const size_t tot = (size_t)jpi * jpj * nslab;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->v_in.alloc(tot));
+  CK(cudaMemcpyAsync(ctx->v_in.p, X, tot * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = lbc_lnk_impl(ctx, nperio, jpi, jpj, nslab, ctx->v_in.p, cd_type, psgn, has_pval, pval)) return rc;
+  CK(cudaMemcpyAsync(X, ctx->v_in.p, tot * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_interp3d_post_dev(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk, float* dX, const int32_t* dmask_trg, int32_t ixtrpl_bot,
+                            float vmin, float vmax, float rmiss_val, int32_t i_orca_trg, int32_t c_orca_trg, int32_t lmout) {
+  NEED(c);
+  return interp3d_post_impl(ctx, ni, nj, nk, dX, dmask_trg, ixtrpl_bot, vmin, vmax, rmiss_val, i_orca_trg, c_orca_trg, lmout);
+}
+
+int sosie_interp3d_post(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk, float* X, const int32_t* mask_trg, int32_t ixtrpl_bot, float vmin,
+                        float vmax, float rmiss_val, int32_t i_orca_trg, int32_t c_orca_trg, int32_t lmout) {
+  NEED(c);
+  if (ni < 1 || nj < 1 || nk < 1 || !X) { ctx->err = "sosie_interp3d_post: bad arguments"; return SOSIE_ERR_ARG; }
+  const size_t tot = (size_t)ni * nj * nk;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->v_in.alloc(tot));
+  CK(cudaMemcpyAsync(ctx->v_in.p, X, tot * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int32_t* dm = nullptr;
+  if (mask_trg) {
+    CK(ctx->v_mask.alloc(tot));
+    CK(cudaMemcpyAsync(ctx->v_mask.p, mask_trg, tot * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    dm = ctx->v_mask.p;
+  }
+  if (int rc = interp3d_post_impl(ctx, ni, nj, nk, ctx->v_in.p, dm, ixtrpl_bot, vmin, vmax, rmiss_val, i_orca_trg, c_orca_trg, lmout)) return rc;
+  CK(cudaMemcpyAsync(X, ctx->v_in.p, tot * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
 int sosie_rotate_uv_dev(sosie_ctx* c, int64_t n, int32_t nslab, const float* dU, const float* dV, const double* dxcos,
                         const double* dxsin, float* dUo, float* dVo, int32_t inverse) {
   NEED(c);

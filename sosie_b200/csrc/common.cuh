@@ -145,6 +145,10 @@ struct sosie_ctx {
   DBuf<float> ak_stage1, ak_stage2;
   double ak_range[4] = {0, 0, 0, 0};
 
+  // ---- vertical stage (vert.cu)
+  DBuf<float> v_vze, v_vz2, v_in, v_out;
+  DBuf<int32_t> v_plan, v_mask;
+
   // ---- drown work buffers
   DBuf<int8_t> dr_m0, dr_m1;
   DBuf<float> dr_x, dr_x2;
@@ -260,5 +264,10 @@ int smoother_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX
                   const int32_t* dmsk, int l_emp);
 int drown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, const int8_t* dmask, int nb_inc,
                int32_t* nsweeps_host);
+int akima_1d_3d_impl(sosie_ctx* ctx, int nx, int ny, int nk1, const float* vz1_host, const float* dxf1, int nk2, const float* vz2_host,
+                     float* dxf2, float rfill_val);
+int lbc_lnk_impl(sosie_ctx* ctx, int nperio, int jpi, int jpj, int nslab, float* dX, int cd_type, double psgn, int has_pval, double pval);
+int interp3d_post_impl(sosie_ctx* ctx, int ni, int nj, int nk, float* dX, const int32_t* dmask_trg, int ixtrpl_bot, float vmin, float vmax,
+                       float rmiss_val, int i_orca_trg, int c_orca_trg, int lmout);
 int rotate_impl(sosie_ctx* ctx, int64_t n, int nslab, const float* dU, const float* dV, const double* dcos,
                 const double* dsin, float* dUo, float* dVo, int inverse);

@@ -1,0 +1,317 @@
+// vert.cu -- the vertical stage of INTERP_3D on device: a 3D job keeps data3d_tmp in HBM between
+// the per-level horizontal interpolation and the vertical one instead of going back to the host.
+//
+// GPU counterparts of
+//   AKIMA_1D_3D, slopes_3d, extra_2_top_3d, extra_2_bottom_3d   src/mod_akima_1d.f90:243-389, 461-515, 521-606
+//   lbc_lnk_2d_r4 / lbc_lnk_2d_r8 / lbc_nfd_2d                   src/mod_nemotools.f90:65-417
+//   the post-interpolation block of INTERP_3D                    src/mod_interp.f90:447-511
+// REAL(4) arithmetic in the reference's order, FMA contraction off -> bit-identical results.
+//
+// AKIMA_1D_3D materialises the n+4 extended cube and its slopes (2 x (nk1+4) planes written and read back) and then
+// evaluates each target level.  The level search depends on the two depth vectors only, so it is done once on the host
+// (LevelPlan); on the device one thread per (point, target level) rebuilds what the polynomial needs -- six source
+// values around the bracketing interval, extrapolated on the fly where they fall in the 2-point frames -- and the
+// two slopes from the five divided differences they share.  HBM traffic: the source cube once (planes are re-read
+// from L2 by the neighbouring target levels) + the target cube once.
+#include <algorithm>
+
+#include "geom.cuh"
+
+#define LV_FILL 0
+#define LV_COPY 1
+#define LV_INTERP 2
+
+struct LevelPlan {  // per target level
+  int mode;         // LV_*
+  int k;            // LV_COPY: source level (1-based); LV_INTERP: jp1 in the n+4 extended numbering
+};
+
+// value of the extended cube xf1e(:,:,ke) at point p (ke = 1..nk1+4), :266-289
+__device__ __forceinline__ float ak1_fe(const float* __restrict__ xf1, size_t n, size_t p, int nk1, const float* __restrict__ vze,
+                                        int ke) {
+  if (ke >= 3 && ke <= nk1 + 2) return xf1[(size_t)(ke - 3) * n + p];
+  const int nk1e = nk1 + 4;
+  if (ke <= 2) {  // extra_2_bottom_3d(vz1e(5), vz1e(4), vz1e(3), vz1e(2), vz1e(1), xf1e(5), xf1e(4), xf1e(3) -> xf1e(2), xf1e(1))
+    const float x5 = vze[5], x4 = vze[4], x3 = vze[3], x2 = vze[2], x1 = vze[1];
+    const float A = __fsub_rn(x4, x5), B = __fsub_rn(x3, x4), C = __fsub_rn(x2, x3), D = __fsub_rn(x1, x2);
+    const float f5 = xf1[2 * n + p], f4 = xf1[n + p], f3 = xf1[p];
+    if ((A == 0.f) || (B == 0.f) || (C == 0.f)) return f3;
+    const float ALF = __fsub_rn(f4, f5), BET = __fsub_rn(f3, f4);
+    const float v2 = __fadd_rn(__fmul_rn(C, __fsub_rn(__fdiv_rn(__fmul_rn(2.f, BET), B), __fdiv_rn(ALF, A))), f3);
+    if (ke == 2) return v2;
+    float r = __fadd_rn(v2, __fdiv_rn(__fmul_rn(v2, D), C));
+    r = __fadd_rn(r, __fdiv_rn(__fmul_rn(BET, D), B));
+    r = __fsub_rn(r, __fdiv_rn(__fmul_rn(ALF, D), A));
+    r = __fsub_rn(r, __fdiv_rn(__fmul_rn(f3, D), C));
+    return r;
+  }
+  // extra_2_top_3d(vz1e(nk1e-4..nk1e), xf1e(nk1e-4), xf1e(nk1e-3), xf1e(nk1e-2) -> xf1e(nk1e-1), xf1e(nk1e))
+  const float x1 = vze[nk1e - 4], x2 = vze[nk1e - 3], x3 = vze[nk1e - 2], x4 = vze[nk1e - 1], x5 = vze[nk1e];
+  const float A = __fsub_rn(x2, x1), B = __fsub_rn(x3, x2), C = __fsub_rn(x4, x3), D = __fsub_rn(x5, x4);
+  const float f1 = xf1[(size_t)(nk1 - 3) * n + p], f2 = xf1[(size_t)(nk1 - 2) * n + p], f3 = xf1[(size_t)(nk1 - 1) * n + p];
+  if ((A == 0.f) || (B == 0.f) || (C == 0.f)) return f3;
+  const float ALF = __fsub_rn(f2, f1), BET = __fsub_rn(f3, f2);
+  const float v4 = __fadd_rn(__fmul_rn(C, __fsub_rn(__fdiv_rn(__fmul_rn(2.f, BET), B), __fdiv_rn(ALF, A))), f3);
+  if (ke == nk1e - 1) return v4;
+  float r = __fadd_rn(v4, __fdiv_rn(__fmul_rn(v4, D), C));
+  r = __fadd_rn(r, __fdiv_rn(__fmul_rn(BET, D), B));
+  r = __fsub_rn(r, __fdiv_rn(__fmul_rn(ALF, D), A));
+  r = __fsub_rn(r, __fdiv_rn(__fmul_rn(f3, D), C));
+  return r;
+}
+
+__device__ __forceinline__ float ak1_slope(float m1, float m2, float m3, float m4) {  // slopes_3d, :478-489
+  if ((m1 == m2) && (m3 == m4)) return __fmul_rn(0.5f, __fadd_rn(m2, m3));
+  const float w2 = fabsf(__fsub_rn(m4, m3)), w3 = fabsf(__fsub_rn(m2, m1));
+  return __fdiv_rn(__fadd_rn(__fmul_rn(w2, m2), __fmul_rn(w3, m3)), __fadd_rn(w2, w3));
+}
+
+// vze: vz1e(1..nk1+4) at [1..]; vz2: target depths (0-based array)
+__global__ void __launch_bounds__(256)
+k_ak1d_eval(const float* __restrict__ xf1, float* __restrict__ xf2, size_t n, int nk1, int nk2, const float* __restrict__ vze,
+            const float* __restrict__ vz2, const LevelPlan* __restrict__ plan, float rfill) {
+  const int jk2 = blockIdx.y;  // 0-based target level
+  const LevelPlan lp = plan[jk2];
+  float* out = xf2 + (size_t)jk2 * n;
+  if (lp.mode == LV_FILL) {
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) __stcs(out + p, rfill);
+    return;
+  }
+  if (lp.mode == LV_COPY) {
+    const float* src = xf1 + (size_t)(lp.k - 1) * n;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) __stcs(out + p, src[p]);
+    return;
+  }
+  const int jp1 = lp.k, jp2 = lp.k + 1;
+  float z[6];
+#pragma unroll
+  for (int q = 0; q < 6; q++) z[q] = vze[jp1 - 2 + q];
+  float rz[5];
+#pragma unroll
+  for (int q = 0; q < 5; q++) rz[q] = __fsub_rn(z[q + 1], z[q]);  // vz(k+1) - vz(k): the divisors of slopes_3d
+  const float dv = __fsub_rn(vze[jp2], vze[jp1]);
+  const float dz = __fdiv_rn(1.f, dv), dz2 = __fmul_rn(dz, dz);
+  const float dzt = __fsub_rn(vz2[jk2], vze[jp1]), dzt2 = __fmul_rn(dzt, dzt);
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+    float f[6];
+#pragma unroll
+    for (int q = 0; q < 6; q++) f[q] = ak1_fe(xf1, n, p, nk1, vze, jp1 - 2 + q);
+    float d[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) d[q] = __fdiv_rn(__fsub_rn(f[q + 1], f[q]), rz[q]);
+    const float s1 = ak1_slope(d[0], d[1], d[2], d[3]);  // xslp(jp1)
+    const float s2 = ak1_slope(d[1], d[2], d[3], d[4]);  // xslp(jp2)
+    const float a0 = f[2], a1 = s1, df = __fsub_rn(f[3], f[2]);
+    // a2 = ( 3*(xf1e(jp2)-xf1e(jp1))*dz - 2*xslp(jp1) - xslp(jp2) ) * dz
+    const float a2 = __fmul_rn(__fsub_rn(__fsub_rn(__fmul_rn(__fmul_rn(3.f, df), dz), __fmul_rn(2.f, s1)), s2), dz);
+    // a3 = ( xslp(jp1) + xslp(jp2) - 2*(xf1e(jp2)-xf1e(jp1))/(vz1e(jp2)-vz1e(jp1)) ) * dz2
+    const float a3 = __fmul_rn(__fsub_rn(__fadd_rn(s1, s2), __fdiv_rn(__fmul_rn(2.f, df), dv)), dz2);
+    // xf2 = a0 + a1*dz + a2*dz2 + a3*dz2*dz
+    float r = __fadd_rn(a0, __fmul_rn(a1, dzt));
+    r = __fadd_rn(r, __fmul_rn(a2, dzt2));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(a3, dzt2), dzt));
+    __stcs(out + p, r);
+  }
+}
+
+// the level search of AKIMA_1D_3D (:293-333) and the two persistence loops after it (:372-385), on the host
+static void ak1d_plan(int nk1, const float* vz1, int nk2, const float* vz2, std::vector<LevelPlan>& plan) {
+  plan.assign(nk2, LevelPlan{LV_FILL, 0});
+  auto VZ1 = [&](int k) { return vz1[k - 1]; };
+  auto VZ2 = [&](int k) { return vz2[k - 1]; };
+  for (int jk2 = 1; jk2 <= nk2; jk2++) {
+    LevelPlan lp{LV_FILL, 0};
+    bool l_do_interp = true, lfnd = false;
+    int jk1 = 1;
+    if (VZ2(jk2) < VZ1(1)) { lp = LevelPlan{LV_COPY, 1}; l_do_interp = false; }
+    while ((!lfnd) && l_do_interp) {
+      if (jk1 == nk1) break;
+      if ((VZ2(jk2) > VZ1(jk1)) && (VZ2(jk2) <= VZ1(jk1 + 1))) { lp = LevelPlan{LV_INTERP, jk1 + 2}; lfnd = true; }
+      else {
+        if (VZ2(jk2) == VZ1(jk1)) { lp = LevelPlan{LV_COPY, jk1}; l_do_interp = false; break; }
+        else if (VZ2(jk2) == VZ1(jk1 + 1)) { lp = LevelPlan{LV_COPY, jk1 + 1}; l_do_interp = false; break; }
+      }
+      jk1 = jk1 + 1;
+    }
+    if ((jk1 == nk1) && (!lfnd)) { lp = LevelPlan{LV_COPY, nk1}; l_do_interp = false; }
+    if (!lfnd) { lp = LevelPlan{LV_FILL, 0}; l_do_interp = false; }   // (:329-332) overrides every copy above
+    plan[jk2 - 1] = lp;
+  }
+  int jk2 = 1;
+  while ((VZ2(jk2) < VZ1(1)) && (jk2 < nk2)) { plan[jk2 - 1] = LevelPlan{LV_COPY, 1}; jk2 = jk2 + 1; }
+  jk2 = nk2;
+  while ((jk2 > 0) && (VZ2(jk2) > VZ1(nk1))) { plan[jk2 - 1] = LevelPlan{LV_COPY, nk1}; jk2 = jk2 - 1; }  // defined stop at 0
+}
+
+int akima_1d_3d_impl(sosie_ctx* ctx, int nx, int ny, int nk1, const float* vz1_host, const float* dxf1, int nk2, const float* vz2_host,
+                     float* dxf2, float rfill_val) {
+  if (nx < 1 || ny < 1 || nk1 < 3 || nk2 < 1 || !vz1_host || !vz2_host || !dxf1 || !dxf2) {
+    ctx->err = "sosie_akima_1d_3d: bad arguments (at least 3 source levels are needed)"; return SOSIE_ERR_ARG;
+  }
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)nx * ny;
+  const int nk1e = nk1 + 4;
+  std::vector<float> vze(nk1e + 1, 0.f);
+  for (int k = 1; k <= nk1; k++) vze[k + 2] = vz1_host[k - 1];
+  vze[2] = vze[4] - (vze[5] - vze[3]);                              // (:268-273), REAL(4)
+  vze[1] = vze[3] - (vze[5] - vze[3]);
+  vze[nk1e - 1] = vze[nk1e - 3] + vze[nk1e - 2] - vze[nk1e - 4];
+  vze[nk1e] = vze[nk1e - 2] + vze[nk1e - 2] - vze[nk1e - 4];
+  std::vector<LevelPlan> plan;
+  ak1d_plan(nk1, vz1_host, nk2, vz2_host, plan);
+  CK(ctx->v_vze.alloc(nk1e + 1)); CK(ctx->v_vz2.alloc(nk2)); CK(ctx->v_plan.alloc((size_t)nk2 * 2));
+  CK(cudaMemcpyAsync(ctx->v_vze.p, vze.data(), sizeof(float) * (nk1e + 1), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->v_vz2.p, vz2_host, sizeof(float) * nk2, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->v_plan.p, plan.data(), sizeof(LevelPlan) * nk2, cudaMemcpyHostToDevice, st));
+  dim3 grid(grid_for(ctx, n, 256, 4), nk2);
+  k_ak1d_eval<<<grid, 256, 0, st>>>(dxf1, dxf2, n, nk1, nk2, ctx->v_vze.p, ctx->v_vz2.p, reinterpret_cast<const LevelPlan*>(ctx->v_plan.p),
+                                    rfill_val);
+  KLAUNCH_CHECK();
+  CK(cudaStreamSynchronize(st));  // the pageable host vectors above must outlive the copies
+  return SOSIE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// lbc_lnk (REAL(4) variant: through REAL(8), src/mod_nemotools.f90:154-190): one block per slab executes the
+// statements of lbc_lnk_2d_r8 / lbc_nfd_2d in order.  Loops that copy between different rows (or columns) are
+// parallel; loops that read and write the SAME row are replayed by one thread in the reference's index order (the
+// T-pivot U-point fold reads elements it has just overwritten).
+__device__ __forceinline__ float lbc_mul(double psgn, float x) { return (float)__dmul_rn(psgn, (double)x); }
+
+__global__ void __launch_bounds__(1024)
+k_lbc_lnk(float* Xb, int jpi, int jpj, int nperio, int cd, double psgn, int has_pval, double pval) {
+  float* X = Xb + (size_t)blockIdx.x * jpi * jpj;
+#define P(i, j) X[(size_t)((i)-1) + (size_t)((j)-1) * jpi]
+  const float zland = has_pval ? (float)pval : 0.f;
+  const int t = threadIdx.x, nt = blockDim.x;
+  const bool tuvw = (cd == 'T' || cd == 'U' || cd == 'V' || cd == 'W');
+  // ---- East-West
+  if (nperio == 1 || nperio == 4 || nperio == 6) {
+    for (int j = 1 + t; j <= jpj; j += nt) P(1, j) = P(jpi - 1, j);
+    __syncthreads();
+    for (int j = 1 + t; j <= jpj; j += nt) P(jpi, j) = P(2, j);
+  } else {
+    if (tuvw) { for (int j = 1 + t; j <= jpj; j += nt) { P(1, j) = zland; P(jpi, j) = zland; } }
+    else if (cd == 'F') { for (int j = 1 + t; j <= jpj; j += nt) P(jpi, j) = zland; }
+  }
+  __syncthreads();
+  // ---- North-South
+  if (nperio == 2) {
+    if (cd == 'T' || cd == 'U' || cd == 'W') { for (int i = 1 + t; i <= jpi; i += nt) { P(i, 1) = P(i, 3); P(i, jpj) = zland; } }
+    else if (cd == 'V' || cd == 'F') { for (int i = 1 + t; i <= jpi; i += nt) { P(i, 1) = lbc_mul(psgn, P(i, 2)); P(i, jpj) = zland; } }
+  } else if (nperio >= 3 && nperio <= 6) {
+    if (tuvw || cd == 'I') { for (int i = 1 + t; i <= jpi; i += nt) P(i, 1) = zland; }
+    __syncthreads();
+    const int jg = jpi, jj = jpj, jm1 = jpj - 1;
+    if (nperio == 3 || nperio == 4) {  // T-point pivot
+      if (cd == 'T' || cd == 'W') {
+        for (int ji = 2 + t; ji <= jg; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji + 2, jj - 2));
+        __syncthreads();
+        if (t == 0) {
+          P(1, jj) = lbc_mul(psgn, P(3, jj - 2));
+          for (int ji = jg / 2 + 1; ji <= jg; ji++) P(ji, jj - 1) = lbc_mul(psgn, P(jg - ji + 2, jj - 1));
+        }
+      } else if (cd == 'U') {
+        for (int ji = 1 + t; ji <= jg - 1; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji + 1, jj - 2));
+        __syncthreads();
+        if (t == 0) {
+          P(1, jj) = lbc_mul(psgn, P(2, jj - 2));
+          P(jg, jj) = lbc_mul(psgn, P(jg - 1, jj - 2));
+          P(1, jj - 1) = lbc_mul(psgn, P(jg, jj - 1));
+          for (int ji = jg / 2; ji <= jg - 1; ji++) P(ji, jm1) = lbc_mul(psgn, P(jg - ji + 1, jm1));
+        }
+      } else if (cd == 'V') {
+        for (int ji = 2 + t; ji <= jg; ji += nt) P(ji, jj - 1) = lbc_mul(psgn, P(jg - ji + 2, jj - 2));  // jl = -1
+        __syncthreads();
+        for (int ji = 2 + t; ji <= jg; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji + 2, jj - 3));      // jl = 0
+        __syncthreads();
+        if (t == 0) P(1, jj) = lbc_mul(psgn, P(3, jj - 3));
+      } else if (cd == 'F') {
+        for (int ji = 1 + t; ji <= jg - 1; ji += nt) P(ji, jj - 1) = lbc_mul(psgn, P(jg - ji + 1, jj - 2));
+        __syncthreads();
+        for (int ji = 1 + t; ji <= jg - 1; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji + 1, jj - 3));
+        __syncthreads();
+        if (t == 0) {
+          P(1, jj) = lbc_mul(psgn, P(2, jj - 3));
+          P(jg, jj) = lbc_mul(psgn, P(jg - 1, jj - 3));
+          P(jg, jj - 1) = lbc_mul(psgn, P(jg - 1, jj - 2));
+          P(1, jj - 1) = lbc_mul(psgn, P(2, jj - 2));
+        }
+      }
+    } else {  // F-point pivot
+      if (cd == 'T' || cd == 'W') {
+        for (int ji = 1 + t; ji <= jg; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji + 1, jj - 1));
+      } else if (cd == 'U') {
+        for (int ji = 1 + t; ji <= jg - 1; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji, jj - 1));
+        __syncthreads();
+        if (t == 0) P(jg, jj) = lbc_mul(psgn, P(1, jj - 1));
+      } else if (cd == 'V') {
+        for (int ji = 1 + t; ji <= jg; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji + 1, jj - 2));
+        __syncthreads();
+        if (t == 0) for (int ji = jg / 2 + 1; ji <= jg; ji++) P(ji, jm1) = lbc_mul(psgn, P(jg - ji + 1, jm1));
+      } else if (cd == 'F') {
+        for (int ji = 1 + t; ji <= jg - 1; ji += nt) P(ji, jj) = lbc_mul(psgn, P(jg - ji, jj - 2));
+        __syncthreads();
+        if (t == 0) {
+          P(jg, jj) = lbc_mul(psgn, P(1, jj - 2));
+          for (int ji = jg / 2 + 1; ji <= jg - 1; ji++) P(ji, jm1) = lbc_mul(psgn, P(jg - ji, jm1));
+        }
+      }
+    }
+  } else {
+    if (tuvw) { for (int i = 1 + t; i <= jpi; i += nt) { P(i, 1) = zland; P(i, jpj) = zland; } }
+    else if (cd == 'F') { for (int i = 1 + t; i <= jpi; i += nt) P(i, jpj) = zland; }
+  }
+#undef P
+}
+
+int lbc_lnk_impl(sosie_ctx* ctx, int nperio, int jpi, int jpj, int nslab, float* dX, int cd_type, double psgn, int has_pval, double pval) {
+  if (jpi < 4 || jpj < 4 || nslab < 1 || !dX) { ctx->err = "sosie_lbc_lnk: bad arguments"; return SOSIE_ERR_ARG; }
+  const bool fold = nperio >= 3 && nperio <= 6;
+  if (fold && !(cd_type == 'T' || cd_type == 'W' || cd_type == 'U' || cd_type == 'V' || cd_type == 'F')) {
+    ctx->err = "sosie_lbc_lnk: ice-point types (I, J, K) are not used by SOSIE and not implemented"; return SOSIE_ERR_ARG;
+  }
+  k_lbc_lnk<<<nslab, 1024, 0, ctx->stream>>>(dX, jpi, jpj, nperio, cd_type, psgn, has_pval, pval);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// post-interpolation block of INTERP_3D (src/mod_interp.f90:447-511), the optional SMOOTHER calls excepted
+__global__ void k_i3d_persist_clamp(float* X, const int32_t* __restrict__ mask, size_t n, int nk, int ixtrpl_bot, float vmin, float vmax,
+                                    float rmiss) {
+  for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+    int jk_bot = 0;
+    float zwet = 0.f;
+    if (ixtrpl_bot == 1 && mask[p] == 1) {
+      for (int k = 1; k <= nk; k++) if (mask[p + (size_t)(k - 1) * n] == 0) { jk_bot = k; break; }  // FINDLOC(mask_trg(ji,jj,:), 0)
+      if (jk_bot > 1) zwet = X[p + (size_t)(jk_bot - 2) * n];
+    }
+    for (int k = 1; k <= nk; k++) {
+      float v = X[p + (size_t)(k - 1) * n];
+      if (jk_bot > 1 && k >= jk_bot) v = zwet;                 // persistence into the sea-bed (:447-466)
+      if ((v > vmax) && (v != rmiss)) v = vmax;                // (:474-477)
+      if ((v < vmin) && (v != rmiss)) v = vmin;
+      X[p + (size_t)(k - 1) * n] = v;
+    }
+  }
+}
+__global__ void k_i3d_mask(float* X, const int32_t* __restrict__ mask, size_t tot, float rmiss) {
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < tot; t += (size_t)gridDim.x * blockDim.x) {
+    const float m = (float)mask[t];
+    // data3d_trg*mask_trg + (1. - mask_trg)*rmiss_val  (:507)
+    X[t] = __fadd_rn(__fmul_rn(X[t], m), __fmul_rn(__fsub_rn(1.f, m), rmiss));
+  }
+}
+
+int interp3d_post_impl(sosie_ctx* ctx, int ni, int nj, int nk, float* dX, const int32_t* dmask_trg, int ixtrpl_bot, float vmin, float vmax,
+                       float rmiss_val, int i_orca_trg, int c_orca_trg, int lmout) {
+  if (ni < 1 || nj < 1 || nk < 1 || !dX) { ctx->err = "sosie_interp3d_post: bad arguments"; return SOSIE_ERR_ARG; }
+  if ((ixtrpl_bot == 1 || lmout) && !dmask_trg) { ctx->err = "sosie_interp3d_post: mask_trg is required (ixtrpl_bot = 1 or lmout)"; return SOSIE_ERR_ARG; }
+  const size_t n = (size_t)ni * nj;
+  k_i3d_persist_clamp<<<grid_for(ctx, n, 256, 8), 256, 0, ctx->stream>>>(dX, dmask_trg, n, nk, ixtrpl_bot, vmin, vmax, rmiss_val);
+  KLAUNCH_CHECK();
+  if (i_orca_trg > 0) { if (int rc = lbc_lnk_impl(ctx, i_orca_trg, ni, nj, nk, dX, c_orca_trg, 1.0, 0, 0.0)) return rc; }
+  if (lmout) { k_i3d_mask<<<grid_for(ctx, n * nk, 256, 8), 256, 0, ctx->stream>>>(dX, dmask_trg, n * nk, rmiss_val); KLAUNCH_CHECK(); }
+  return SOSIE_OK;
+}

@@ -457,3 +457,182 @@ def fill_extra_bands(k_ew, XX, YY, XF):
     y2, y1 = _extra_2_east(YP4[:, 4], YP4[:, 3], YP4[:, 2], YP4[:, 1], YP4[:, 0], FP4[:, 4], FP4[:, 3], FP4[:, 2])
     FP4[:, 1], FP4[:, 0] = y2, y1
     return XP4, YP4, FP4
+
+
+# ---------------------------------------------------------------------------------------------------
+# vertical stage of INTERP_3D: independent numpy (float32, array syntax) / pure-Python-loop transliterations
+def akima_1d_3d_np(vz1, xf1, vz2, rfill_val):
+    """AKIMA_1D_3D, src/mod_akima_1d.f90:243-389, written with whole-array float32 numpy statements like the
+    Fortran source (extended cube + slope cube materialised); xf1 (nk1, ny, nx) -> (nk2, ny, nx)."""
+    f4 = np.float32
+    vz1 = np.asarray(vz1, f4); vz2 = np.asarray(vz2, f4); xf1 = np.asarray(xf1, f4)
+    nk1, nk2 = vz1.size, vz2.size
+    nk1e = nk1 + 4
+    vz1e = np.zeros(nk1e + 1, f4)                      # 1-based
+    xf1e = np.zeros((nk1e + 1,) + xf1.shape[1:], f4)
+    vz1e[3:nk1 + 3] = vz1
+    xf1e[3:nk1 + 3] = xf1
+    vz1e[2] = vz1e[4] - (vz1e[5] - vz1e[3])
+    vz1e[1] = vz1e[3] - (vz1e[5] - vz1e[3])
+    vz1e[nk1e - 1] = vz1e[nk1e - 3] + vz1e[nk1e - 2] - vz1e[nk1e - 4]
+    vz1e[nk1e] = vz1e[nk1e - 2] + vz1e[nk1e - 2] - vz1e[nk1e - 4]
+
+    def extra(xa, xb, xc, xd, xe, Fa, Fb, Fc):     # extra_2_top_3d (x1..x5, Xf1..Xf3) == extra_2_bottom_3d mirrored
+        A = f4(xb - xa); B = f4(xc - xb); Cc = f4(xd - xc); D = f4(xe - xd)
+        ALF = Fb - Fa; BET = Fc - Fb
+        if A == 0 or B == 0 or Cc == 0:
+            return Fc.copy(), Fc.copy()
+        F4 = Cc * (f4(2) * BET / B - ALF / A) + Fc
+        F5 = F4 + F4 * D / Cc + BET * D / B - ALF * D / A - Fc * D / Cc
+        return F4, F5
+    xf1e[2], xf1e[1] = extra(vz1e[5], vz1e[4], vz1e[3], vz1e[2], vz1e[1], xf1e[5], xf1e[4], xf1e[3])
+    xf1e[nk1e - 1], xf1e[nk1e] = extra(vz1e[nk1e - 4], vz1e[nk1e - 3], vz1e[nk1e - 2], vz1e[nk1e - 1], vz1e[nk1e],
+                                      xf1e[nk1e - 4], xf1e[nk1e - 3], xf1e[nk1e - 2])
+    nz = nk1e
+    slope = np.zeros_like(xf1e)
+    with np.errstate(all="ignore"):
+        for k in range(3, nz - 1):
+            m1 = (xf1e[k - 1] - xf1e[k - 2]) / f4(vz1e[k - 1] - vz1e[k - 2])
+            m2 = (xf1e[k] - xf1e[k - 1]) / f4(vz1e[k] - vz1e[k - 1])
+            m3 = (xf1e[k + 1] - xf1e[k]) / f4(vz1e[k + 1] - vz1e[k])
+            m4 = (xf1e[k + 2] - xf1e[k + 1]) / f4(vz1e[k + 2] - vz1e[k + 1])
+            gen = (np.abs(m4 - m3) * m2 + np.abs(m2 - m1) * m3) / (np.abs(m4 - m3) + np.abs(m2 - m1))
+            slope[k] = np.where((m1 == m2) & (m3 == m4), f4(0.5) * (m2 + m3), gen)
+    xf2 = np.zeros((nk2,) + xf1.shape[1:], f4)
+    for jk2 in range(1, nk2 + 1):
+        z = vz2[jk2 - 1]
+        do, fnd, jk1, jp1 = True, False, 1, 0
+        if z < vz1[0]:
+            xf2[jk2 - 1] = xf1[0]; do = False
+        while (not fnd) and do:
+            if jk1 == nk1:
+                break
+            if z > vz1[jk1 - 1] and z <= vz1[jk1]:
+                jp1 = jk1 + 2; fnd = True
+            else:
+                if z == vz1[jk1 - 1]:
+                    xf2[jk2 - 1] = xf1[jk1 - 1]; do = False; break
+                elif z == vz1[jk1]:
+                    xf2[jk2 - 1] = xf1[jk1]; do = False; break
+            jk1 += 1
+        if jk1 == nk1 and not fnd:
+            xf2[jk2 - 1] = xf1[nk1 - 1]; do = False
+        if not fnd:
+            xf2[jk2 - 1] = f4(rfill_val); do = False
+        if do:
+            jp2 = jp1 + 1
+            a0 = xf1e[jp1]; a1 = slope[jp1]
+            dz = f4(1.0) / f4(vz1e[jp2] - vz1e[jp1]); dz2 = f4(dz * dz)
+            a2 = (f4(3) * (xf1e[jp2] - xf1e[jp1]) * dz - f4(2) * slope[jp1] - slope[jp2]) * dz
+            a3 = (slope[jp1] + slope[jp2] - f4(2) * (xf1e[jp2] - xf1e[jp1]) / f4(vz1e[jp2] - vz1e[jp1])) * dz2
+            dz = f4(z - vz1e[jp1]); dz2 = f4(dz * dz)
+            xf2[jk2 - 1] = a0 + a1 * dz + a2 * dz2 + a3 * dz2 * dz
+    jk2 = 1
+    while vz2[jk2 - 1] < vz1[0] and jk2 < nk2:
+        xf2[jk2 - 1] = xf1[0]; jk2 += 1
+    jk2 = nk2
+    while jk2 > 0 and vz2[jk2 - 1] > vz1[nk1 - 1]:
+        xf2[jk2 - 1] = xf1[nk1 - 1]; jk2 -= 1
+    return xf2
+
+
+def lbc_lnk_py(nperio, X, cd_type, psgn, pval=None):
+    """lbc_lnk_2d_r8 + lbc_nfd_2d (src/mod_nemotools.f90:65-417) with explicit sequential Python loops on a float64 copy;
+    X (jpj, jpi) float32; returns float32."""
+    P = np.asarray(X, np.float64).T.copy()       # P[i-1, j-1]
+    jpi, jpj = P.shape
+    zland = 0.0 if pval is None else float(pval)
+
+    def g(i, j):
+        return P[i - 1, j - 1]
+
+    def s(i, j, v):
+        P[i - 1, j - 1] = v
+    if nperio in (1, 4, 6):
+        col = P[jpi - 2, :].copy(); P[0, :] = col
+        col = P[1, :].copy(); P[jpi - 1, :] = col
+    else:
+        if cd_type in "TUVW":
+            P[0, :] = zland; P[jpi - 1, :] = zland
+        elif cd_type == "F":
+            P[jpi - 1, :] = zland
+    if nperio == 2:
+        if cd_type in "TUW":
+            P[:, 0] = P[:, 2].copy(); P[:, jpj - 1] = zland
+        elif cd_type in "VF":
+            P[:, 0] = psgn * P[:, 1]; P[:, jpj - 1] = zland
+    elif nperio in (3, 4, 5, 6):
+        if cd_type in "TUVWI":
+            P[:, 0] = zland
+        J, G = jpj, jpi
+        if nperio in (3, 4):
+            if cd_type in "TW":
+                for ji in range(2, G + 1):
+                    s(ji, J, psgn * g(G - ji + 2, J - 2))
+                s(1, J, psgn * g(3, J - 2))
+                for ji in range(G // 2 + 1, G + 1):
+                    s(ji, J - 1, psgn * g(G - ji + 2, J - 1))
+            elif cd_type == "U":
+                for ji in range(1, G):
+                    s(ji, J, psgn * g(G - ji + 1, J - 2))
+                s(1, J, psgn * g(2, J - 2)); s(G, J, psgn * g(G - 1, J - 2)); s(1, J - 1, psgn * g(G, J - 1))
+                for ji in range(G // 2, G):
+                    s(ji, J - 1, psgn * g(G - ji + 1, J - 1))
+            elif cd_type == "V":
+                for jl in (-1, 0):
+                    for ji in range(2, G + 1):
+                        s(ji, J + jl, psgn * g(G - ji + 2, J - 3 - jl))
+                s(1, J, psgn * g(3, J - 3))
+            elif cd_type == "F":
+                for jl in (-1, 0):
+                    for ji in range(1, G):
+                        s(ji, J + jl, psgn * g(G - ji + 1, J - 3 - jl))
+                s(1, J, psgn * g(2, J - 3)); s(G, J, psgn * g(G - 1, J - 3))
+                s(G, J - 1, psgn * g(G - 1, J - 2)); s(1, J - 1, psgn * g(2, J - 2))
+        else:
+            if cd_type in "TW":
+                for ji in range(1, G + 1):
+                    s(ji, J, psgn * g(G - ji + 1, J - 1))
+            elif cd_type == "U":
+                for ji in range(1, G):
+                    s(ji, J, psgn * g(G - ji, J - 1))
+                s(G, J, psgn * g(1, J - 1))
+            elif cd_type == "V":
+                for ji in range(1, G + 1):
+                    s(ji, J, psgn * g(G - ji + 1, J - 2))
+                for ji in range(G // 2 + 1, G + 1):
+                    s(ji, J - 1, psgn * g(G - ji + 1, J - 1))
+            elif cd_type == "F":
+                for ji in range(1, G):
+                    s(ji, J, psgn * g(G - ji, J - 2))
+                s(G, J, psgn * g(1, J - 2))
+                for ji in range(G // 2 + 1, G):
+                    s(ji, J - 1, psgn * g(G - ji, J - 1))
+    else:
+        if cd_type in "TUVW":
+            P[:, 0] = zland; P[:, jpj - 1] = zland
+        elif cd_type == "F":
+            P[:, jpj - 1] = zland
+    return P.T.astype(np.float32)
+
+
+def interp3d_post_np(X, mask, ixtrpl_bot, vmin, vmax, rmiss, i_orca_trg, c_orca_trg, lmout):
+    """post-interpolation block of INTERP_3D (src/mod_interp.f90:447-511), numpy; X (nk, nj, ni)"""
+    f4 = np.float32
+    X = np.asarray(X, f4).copy()
+    nk = X.shape[0]
+    if ixtrpl_bot == 1:
+        first0 = np.where((mask == 0).any(axis=0), (mask == 0).argmax(axis=0) + 1, 0)    # FINDLOC(mask(ji,jj,:), 0)
+        for jj, ji in zip(*np.nonzero((mask[0] == 1) & (first0 > 1))):
+            kb = first0[jj, ji]
+            X[kb - 1:, jj, ji] = X[kb - 2, jj, ji]
+    for k in range(nk):
+        Xk = X[k]
+        Xk[(Xk > f4(vmax)) & (Xk != f4(rmiss))] = f4(vmax)
+        Xk[(Xk < f4(vmin)) & (Xk != f4(rmiss))] = f4(vmin)
+        if i_orca_trg > 0:
+            X[k] = lbc_lnk_py(i_orca_trg, Xk, c_orca_trg, 1.0)
+        if lmout:
+            m = mask[k].astype(f4)
+            X[k] = X[k] * m + (f4(1.0) - m) * f4(rmiss)
+    return X

@@ -1,0 +1,111 @@
+"""GPU parity, vertical stage of INTERP_3D (csrc/vert.cu) through the C ABI against the CPU oracle: bit-exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _levels(n, zmax, stretch=2.2):
+    s = np.linspace(0.0, 1.0, n)
+    return (5.0 + (zmax - 5.0) * (np.sinh(stretch * s) / np.sinh(stretch))).astype(np.float32)
+
+
+@pytest.mark.parametrize("nk1,nk2,ny,nx", [(31, 75, 40, 52), (3, 5, 7, 9), (46, 31, 33, 17), (75, 31, 292, 362)])
+def test_akima_1d_3d_vs_oracle(gpu, orc, nk1, nk2, ny, nx):
+    rng = np.random.default_rng(nk1 * 100 + nk2)
+    vz1 = _levels(nk1, 5500.0)
+    vz2 = _levels(nk2, 5900.0, 1.7)
+    vz2[0] = 1.0
+    if nk2 > 3:
+        vz2[2] = vz1[1]
+    xf1 = (np.linspace(25.0, 2.0, nk1, dtype=np.float32)[:, None, None] + rng.normal(0.0, 0.4, (nk1, ny, nx))).astype(np.float32)
+    xf1[:, ::5, ::3] = 0.0                     # flat columns: equal slopes (m1 == m2 and m3 == m4) and 0/0-free paths
+    a = gpu.akima_1d_3d(vz1, xf1, vz2, -9999.0)
+    b = orc.akima_1d_3d(vz1, xf1, vz2, -9999.0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"max diff {np.abs(a - b).max()} at {(a != b).sum()} points"
+
+
+def test_akima_1d_3d_identical_and_degenerate_levels(gpu, orc):
+    """source == target levels (every level hits an equality or the `<=` bracket), and repeated source depths
+    (A == 0 / B == 0 in the frame extrapolation, zero divisors in the slopes -> inf/NaN must match too)."""
+    rng = np.random.default_rng(3)
+    vz1 = _levels(10, 3000.0)
+    xf1 = rng.normal(5.0, 2.0, (10, 6, 8)).astype(np.float32)
+    a = gpu.akima_1d_3d(vz1, xf1, vz1.copy(), -9999.0)
+    b = orc.akima_1d_3d(vz1, xf1, vz1.copy(), -9999.0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    vzd = vz1.copy(); vzd[1] = vzd[0]; vzd[-1] = vzd[-2]
+    vz2 = _levels(14, 3100.0, 1.5)
+    with np.errstate(all="ignore"):
+        a = gpu.akima_1d_3d(vzd, xf1, vz2, -9999.0)
+        b = orc.akima_1d_3d(vzd, xf1, vz2, -9999.0)
+    # NaN payload / sign bits are not specified by IEEE-754 (x86 gives 0xFFC00000 for 0/0, the GPU 0x7FFFFFFF): NaNs must sit
+    # at the same places, everything else must be bit-identical
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    ok = ~np.isnan(a)
+    assert np.array_equal(a[ok].view(np.uint32), b[ok].view(np.uint32))
+
+
+@pytest.mark.parametrize("nperio", [0, 1, 2, 3, 4, 5, 6])
+def test_lbc_lnk_vs_oracle(gpu, orc, nperio):
+    rng = np.random.default_rng(5)
+    for (jpj, jpi, ns) in ((149, 182, 3), (292, 362, 2), (9, 12, 4), (10, 13, 1), (3059, 4322, 1) if nperio == 6 else (11, 16, 1)):
+        X = rng.normal(size=(ns, jpj, jpi)).astype(np.float32)
+        for cd in "TUVF":
+            for psgn, pval in ((1.0, None), (-1.0, None), (1.0, -2.5)):
+                a = gpu.lbc_lnk(nperio, X, cd, psgn, pval)
+                b = orc.lbc_lnk(nperio, X, cd, psgn, pval)
+                assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (nperio, jpi, jpj, cd, psgn, pval, (a != b).sum())
+
+
+def test_interp3d_post_vs_oracle(gpu, orc):
+    rng = np.random.default_rng(13)
+    nk, nj, ni = 75, 60, 82
+    X = rng.normal(10.0, 8.0, (nk, nj, ni)).astype(np.float32)
+    X[5, 7, 9] = -9999.0
+    bed = rng.integers(0, nk + 1, (nj, ni))
+    mask = (np.arange(nk)[:, None, None] < bed[None]).astype(np.int32)
+    for ixb, iorca, cd, lmout in ((1, 0, "T", True), (0, 6, "T", True), (1, 4, "U", False), (0, 0, "T", False), (1, 6, "V", True)):
+        a = gpu.interp3d_post(X, mask, ixb, 0.0, 20.0, -9999.0, iorca, cd, lmout)
+        b = orc.interp3d_post(X, mask, ixb, 0.0, 20.0, -9999.0, iorca, cd, lmout)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (ixb, iorca, cd, lmout, (a != b).sum())
+    a = gpu.interp3d_post(X, None, 0, -5.0, 15.0)      # no mask needed when neither persistence nor lmout
+    b = orc.interp3d_post(X, None, 0, -5.0, 15.0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_3d_job_on_device(gpu, orc):
+    """config C end to end on the device, one record: per-level BDROWN + bilinear (TWISTED mapping) of 31 levels, the
+    cube stays in HBM for AKIMA_1D_3D to 75 levels and the INTERP_3D post-ops; compared with the oracle's chain."""
+    import torch
+    from sosie_b200 import grids as G
+    cfg = G.config("C", 0.35)
+    nk1, nk2 = 31, 75
+    Xs, Ys = cfg["src_lon"], cfg["src_lat"]
+    X = G.field_slabs(Xs, Ys, nk1, seed=21)
+    masks = np.stack([G.land_mask(Xs, Ys, thresh=0.25 - 0.4 * k / nk1) for k in range(nk1)])
+    X[masks == 0] = -9999.0
+    vz1, vz2 = _levels(nk1, 5000.0), _levels(nk2, 5800.0, 2.6)
+    nxt, nyt = cfg["nxt"], cfg["nyt"]
+    rng = np.random.default_rng(2)
+    bed = rng.integers(0, nk2 + 1, (nyt, nxt))
+    mask_trg = (np.arange(nk2)[:, None, None] < bed[None]).astype(np.int32)
+    # oracle chain
+    Xd, _ = orc.bdrown(cfg["ewper_src"], X, masks, 20, 5, -1.0e3, 1.0e3, 0.0)
+    T, _ = orc.bilin_2d(cfg["ewper_src"], Xs, Ys, Xd, cfg["trg_lon"], cfg["trg_lat"], i_orca_trg=cfg["i_orca_trg"])
+    V = orc.akima_1d_3d(vz1, T, vz2, -9999.0)
+    R = orc.interp3d_post(V, mask_trg, 1, -2.0, 35.0, -9999.0, cfg["i_orca_trg"], "T", True)
+    # device chain
+    dev = torch.device("cuda", 0)
+    dX, dM = torch.from_numpy(X).to(dev), torch.from_numpy(masks).to(dev)
+    gpu.bdrown_dev(cfg["ewper_src"], cfg["nxs"], cfg["nys"], nk1, dX, dM, 1, 20, 5, -1.0e3, 1.0e3, 0.0)
+    gpu.bilin_set_grids(cfg["ewper_src"], Xs, Ys, cfg["trg_lon"], cfg["trg_lat"], i_orca_trg=cfg["i_orca_trg"])
+    gpu.bilin_map()
+    dT = torch.empty((nk1, nyt, nxt), device=dev, dtype=torch.float32)
+    gpu.bilin_apply_dev(nk1, dX, dT, first_call=True)
+    dV = torch.empty((nk2, nyt, nxt), device=dev, dtype=torch.float32)
+    gpu.akima_1d_3d_dev(nxt, nyt, vz1, dT, vz2, dV, -9999.0)
+    gpu.interp3d_post_dev(nxt, nyt, nk2, dV, torch.from_numpy(mask_trg).to(dev), 1, -2.0, 35.0, -9999.0, cfg["i_orca_trg"], "T", True)
+    gpu.sync()
+    out = dV.cpu().numpy()
+    assert np.array_equal(out.view(np.uint32), R.view(np.uint32)), (out != R).sum()
