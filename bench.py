@@ -249,7 +249,7 @@ def bench_others(ctx, torch, dev, hbm_peak, quick=False):
             ctx.bdrown_dev(cfg["ewper_src"], cfg["nxs"], cfg["nys"], S, X, mk, 1, cfg["nb_inc"], cfg["nb_smooth"], cfg["vmin"],
                            cfg["vmax"], 0.0)
             ctx.bilin_apply_dev(S, X, Z2)
-        t_job = timed(job, reps=3, warm=1)
+        t_job = timed(job, reps=10, warm=3)
         sweeps = int(nsw.sum())
         bytes_bd = 10 * n1 * (sweeps + S * cfg["nb_smooth"])
         t_bd = float(np.mean(tb))
@@ -261,7 +261,7 @@ def bench_others(ctx, torch, dev, hbm_peak, quick=False):
             ctx.bdrown_dev(cfg["ewper_src"], cfg["nxs"], cfg["nys"], S, X, mk, 1, cfg["nb_inc"], cfg["nb_smooth"], cfg["vmin"],
                            cfg["vmax"], 0.0)
             ctx.akima_apply_dev(S, X, Z2)
-        t_job_ak = timed(job_ak, reps=3, warm=1)
+        t_job_ak = timed(job_ak, reps=10, warm=3)
         # the whole INTERP_3D chain of one record on the device: per-level BDROWN + bilinear, then (cube still in HBM)
         # AKIMA_1D_3D 31 -> 75 levels and the post-interpolation block (bounds, lbc_lnk, target mask)
         nk1, nk2 = 31, 75
@@ -278,7 +278,7 @@ def bench_others(ctx, torch, dev, hbm_peak, quick=False):
             for r in range(12):
                 ctx.akima_1d_3d_dev(cfg["nxt"], cfg["nyt"], vz1, Z2[r * nk1:(r + 1) * nk1], vz2, V[r], -9999.0)
                 ctx.interp3d_post_dev(cfg["nxt"], cfg["nyt"], nk2, V[r], mtrg, 0, cfg["vmin"], cfg["vmax"], -9999.0, cfg["i_orca_trg"], "T", True)
-        t_job3d = timed(job3d, reps=3, warm=1)
+        t_job3d = timed(job3d, reps=10, warm=3)
         cpu = {"job3d_ms": t_job3d, "job3d_note": "12 records: BDROWN + bilinear on 31 levels, vertical Akima to 75 levels, bounds + lbc_lnk + mask; "
                                                   "nothing leaves HBM between the stages",
                "job3d_target_points_per_s": 12 * nk2 * nt / (t_job3d * 1e-3)}
@@ -391,7 +391,7 @@ def bench_others(ctx, torch, dev, hbm_peak, quick=False):
             X.copy_(X0)
             ctx.bdrown_dev(cfg["ewper_src"], cfg["nxs"], cfg["nys"], 1, X, mk, 0, cfg["nb_inc"], cfg["nb_smooth"], cfg["vmin"], cfg["vmax"], 0.0)
             ctx.akima_apply_dev(1, X, Z2)
-        t_job = timed(jobA, reps=5)
+        t_job = timed(jobA, reps=20, warm=5)
         out["A"] = {"workload": "example1 shape: 360x180 -> 362x292, BDROWN(100,50) + Akima, 1 record", "job_ms": t_job,
                     "points_per_s": nt / (t_job * 1e-3), "note": "single 259 KB slab: launch-latency bound"}
     except Exception as e:  # noqa: BLE001

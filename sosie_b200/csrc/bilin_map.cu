@@ -23,6 +23,10 @@ __device__ __forceinline__ unsigned long long enc_d(double x) {
   unsigned long long u = (unsigned long long)__double_as_longlong(x);
   return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
 }
+__device__ __forceinline__ double dec_d(unsigned long long u) {
+  unsigned long long v = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
+  return __longlong_as_double((long long)v);
+}
 static inline double dec_d_host(unsigned long long u) {
   unsigned long long v = (u >> 63) ? (u & 0x7fffffffffffffffULL) : ~u;
   double x;
@@ -112,41 +116,11 @@ __global__ void k_rtmp(TrgGeom tg, Prelude* p) {
   if (threadIdx.x == 0) p->rtmp = r;
 }
 
-__global__ void k_min_dlat(TrgGeom tg, Prelude* p) {
-  double sg = d_sign(1.0, p->rtmp);
-  unsigned long long lmin = ~0ULL;
-  size_t n = (size_t)tg.nx * tg.ny;
-  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
-    int j = (int)(k / tg.nx) + 1, i = (int)(k % tg.nx) + 1;
-    if (j < 2) continue;
-    double v = sg * (trg_lat(tg, i, j) - trg_lat(tg, i, j - 1));
-    lmin = min(lmin, enc_d(v));
-  }
-  for (int o = 16; o > 0; o >>= 1) lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
-  if ((threadIdx.x & 31) == 0) atomicMin(&p->rmin_dlat, lmin);
-}
-
 // i1dum = MINLOC(Ytrg, mask=(Ytrg>=y_min_s), dim=2) ; MAXLOC(Ytrg, mask=(Ytrg<=y_max_s), dim=2)  (:939-941)
 // Two exact parallel passes per column: (1) the extreme VALUE (atomicMin/Max on order-preserving encodings),
 // (2) the FIRST row attaining it (atomicMin on the row index) -- MINLOC/MAXLOC return the first occurrence.
 __global__ void k_fill_i32(int32_t* a, size_t n, int32_t v);
 #define JR_ROWS 64
-__global__ void k_jrange_val(TrgGeom tg, double y_min_s, double y_max_s, unsigned long long* cmin, unsigned long long* cmax) {
-  int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
-  size_t total = (size_t)tg.nx * nchunk;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    int i = (int)(t % tg.nx) + 1, c = (int)(t / tg.nx);
-    unsigned long long lmin = ~0ULL, lmax = 0ULL;
-    int j1 = min(tg.ny, (c + 1) * JR_ROWS);
-    for (int j = c * JR_ROWS + 1; j <= j1; j++) {
-      double v = trg_lat(tg, i, j);
-      if (v >= y_min_s) lmin = min(lmin, enc_d(v));
-      if (v <= y_max_s) lmax = max(lmax, enc_d(v));
-    }
-    if (lmin != ~0ULL) atomicMin(&cmin[i - 1], lmin);
-    if (lmax != 0ULL) atomicMax(&cmax[i - 1], lmax);
-  }
-}
 __global__ void k_jrange_idx(TrgGeom tg, const unsigned long long* __restrict__ cmin, const unsigned long long* __restrict__ cmax,
                              int* jn, int* jx) {
   int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
@@ -169,6 +143,48 @@ __global__ void k_jrange_fin(int nx, const int* __restrict__ jn, const int* __re
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
     if (jn[i] != 2147483647) atomicMin(&p->j_strt, jn[i]);            // MINVAL(i1dum, mask=(i1dum>0))
     atomicMax(&p->j_stop, jx[i] != 2147483647 ? jx[i] : 0);           // MAXVAL(MAXLOC(...)) (0 where the mask is empty)
+  }
+}
+// ONE pass over the target latitudes for everything the prelude reduces from them: MINVAL/MAXVAL(Ytrg) (:888-889),
+// rmin_dlat_dj = MINVAL(SIGN(1,rtmp)*(Ytrg(:,j) - Ytrg(:,j-1))) (:921-923) and the per-column extreme values of
+// k_jrange_val.  y_min_s / y_max_s / rtmp are read from the Prelude on the device (written by earlier kernels of the
+// stream), so no host round trip separates the reductions.  All of them are min/max: order independent, exact.
+__global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, unsigned long long* cmin, unsigned long long* cmax) {
+  const double y_min_s = dec_d(p->ymin_s), y_max_s = dec_d(p->ymax_s);   // MINVAL / MAXVAL(Ysrc), reduced by k_minmax before
+  const double sgn = d_sign(1.0, p->rtmp);
+  const int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
+  const size_t total = (size_t)tg.nx * nchunk;
+  unsigned long long gmin = ~0ULL, gmax = 0ULL, gdl = ~0ULL;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % tg.nx) + 1, c = (int)(t / tg.nx);
+    const int j0 = c * JR_ROWS + 1, j1 = min(tg.ny, (c + 1) * JR_ROWS);
+    unsigned long long lmin = ~0ULL, lmax = 0ULL;
+    double prev = (j0 > 1 && do_dlat) ? trg_lat(tg, i, j0 - 1) : 0.0;
+    for (int j = j0; j <= j1; j++) {
+      const double v = trg_lat(tg, i, j);
+      const unsigned long long e = enc_d(v);
+      gmin = min(gmin, e); gmax = max(gmax, e);
+      if (do_dlat && j >= 2) gdl = min(gdl, enc_d(sgn * (v - prev)));
+      prev = v;
+      if (v >= y_min_s) lmin = min(lmin, e);
+      if (v <= y_max_s) lmax = max(lmax, e);
+    }
+    if (lmin != ~0ULL) atomicMin(&cmin[i - 1], lmin);
+    if (lmax != 0ULL) atomicMax(&cmax[i - 1], lmax);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+    gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    gdl = min(gdl, __shfl_xor_sync(0xffffffffu, gdl, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&p->ymin_t, gmin); atomicMax(&p->ymax_t, gmax);
+    if (do_dlat) atomicMin(&p->rmin_dlat, gdl);
+  }
+}
+__global__ void k_jrange_init(int nx, unsigned long long* cmin, unsigned long long* cmax, int* jn, int* jx) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    cmin[i] = ~0ULL; cmax[i] = 0ULL; jn[i] = 2147483647; jx[i] = 2147483647;
   }
 }
 __global__ void k_fill_u64(unsigned long long* a, size_t n, unsigned long long v) {
@@ -816,7 +832,11 @@ int bilin_prepare_src(sosie_ctx* ctx) {
   if (ctx->l_reg_src && (ny > 20) && (nx > 20)) {
     double ymx, ym1;
     int ih = nx / 2;  // Y1(nx1/2, ny1)
-    if (in_1d) { if (fetch_d(ctx, Yin + (ny - 1), &ymx)) return SOSIE_ERR_CUDA; if (fetch_d(ctx, Yin + (ny - 2), &ym1)) return SOSIE_ERR_CUDA; }
+    if (in_1d) {  // Y(ny-1), Y(ny) are adjacent: one read-back
+      double two[2];
+      if (int rc = fetch_small(ctx, Yin + (ny - 2), two, sizeof(two))) return rc;
+      ym1 = two[0]; ymx = two[1];
+    }
     else {
       if (fetch_d(ctx, Yin + (size_t)(ih - 1) + (size_t)(ny - 1) * nx, &ymx)) return SOSIE_ERR_CUDA;
       if (fetch_d(ctx, Yin + (size_t)(ih - 1) + (size_t)(ny - 2) * nx, &ym1)) return SOSIE_ERR_CUDA;
@@ -902,18 +922,22 @@ int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool*
   // y_min_s / y_max_s : MINVAL/MAXVAL(Ysrc) over the working array (pole rows included)
   if (sg.separable) { k_minmax<<<grid_for(ctx, sg.nyw, 256), 256, 0, st>>>(sg.lat1, sg.nyw, &dpre.p->ymin_s, &dpre.p->ymax_s); KLAUNCH_CHECK(); }
   else { k_minmax<<<grid_for(ctx, nsrc, 256), 256, 0, st>>>(sg.Y, nsrc, &dpre.p->ymin_s, &dpre.p->ymax_s); KLAUNCH_CHECK(); }
-  { size_t nty = tg.is_1d ? (size_t)tg.ny : nt;
-    k_minmax<<<grid_for(ctx, nty, 256), 256, 0, st>>>(tg.Y, nty, &dpre.p->ymin_t, &dpre.p->ymax_t); KLAUNCH_CHECK(); }
   if (!sg.separable) { k_is_regular<<<grid_for(ctx, (size_t)sg.nyw * 32, 256), 256, 0, st>>>(sg.X, sg.Y, sg.nx, sg.nyw, 2, sg.nyw, &dpre.p->irreg_s); KLAUNCH_CHECK(); }
   const bool partial_x = !tg.is_1d && xrow_a >= 1 && !(xrow_a <= 2 && xrow_b >= tg.ny);
   if (!tg.is_1d) {
     int ja = partial_x ? std::max(2, xrow_a) : 2, jb = partial_x ? xrow_b : tg.ny;
     k_is_regular<<<grid_for(ctx, (size_t)tg.ny * 32, 256), 256, 0, st>>>(tg.X, tg.Y, tg.nx, tg.ny, ja, jb, &dpre.p->irreg_t); KLAUNCH_CHECK();
   }
-  if (tg.nx > 2) {
-    k_rtmp<<<1, 1024, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
-    k_min_dlat<<<grid_for(ctx, nt, 256), 256, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK();
-  }
+  // the target latitudes are read twice in all: k_ypass (every reduction) and k_jrange_idx (first rows attaining the
+  // per-column extremes); the row range is computed unconditionally and used only when the reference computes it
+  const int do_dlat = (tg.nx > 2) ? 1 : 0;
+  if (do_dlat) { k_rtmp<<<1, 1024, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK(); }
+  WS(unsigned long long, cmin, tg.nx); WS(unsigned long long, cmax, tg.nx); WS(int, jn, tg.nx); WS(int, jx, tg.nx);
+  k_jrange_init<<<cdiv(tg.nx, 256), 256, 0, st>>>(tg.nx, cmin.p, cmax.p, jn.p, jx.p); KLAUNCH_CHECK();
+  const size_t tot = (size_t)tg.nx * ((tg.ny + JR_ROWS - 1) / JR_ROWS);
+  k_ypass<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, dpre.p, do_dlat, cmin.p, cmax.p); KLAUNCH_CHECK();
+  k_jrange_idx<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, cmin.p, cmax.p, jn.p, jx.p); KLAUNCH_CHECK();
+  k_jrange_fin<<<cdiv(tg.nx, 256), 256, 0, st>>>(tg.nx, jn.p, jx.p, dpre.p); KLAUNCH_CHECK();
   Prelude hp;
   if (int rc = fetch_small(ctx, dpre.p, &hp, sizeof(Prelude))) return rc;
   if (partial_x && hp.irreg_t == 0) { if (need_full_x) *need_full_x = true; return SOSIE_OK; }
@@ -924,18 +948,6 @@ int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool*
   if (tg.nx > 2 && tg.ny >= 2) rmin_dlat_dj = dec_d_host(hp.rmin_dlat);
   int j_strt_t = 1, j_stop_t = tg.ny, jlat_icr = 1;
   if ((rmin_dlat_dj > (double)-1.E-12f) || l_is_reg_t) {
-    {
-      WS(unsigned long long, cmin, tg.nx); WS(unsigned long long, cmax, tg.nx); WS(int, jn, tg.nx); WS(int, jx, tg.nx);
-      k_fill_u64<<<cdiv(tg.nx, 256), 256, 0, st>>>(cmin.p, tg.nx, ~0ULL); KLAUNCH_CHECK();
-      CK(cudaMemsetAsync(cmax.p, 0, sizeof(unsigned long long) * tg.nx, st));
-      k_fill_i32<<<cdiv(tg.nx, 256), 256, 0, st>>>(jn.p, tg.nx, 2147483647); KLAUNCH_CHECK();
-      k_fill_i32<<<cdiv(tg.nx, 256), 256, 0, st>>>(jx.p, tg.nx, 2147483647); KLAUNCH_CHECK();
-      size_t tot = (size_t)tg.nx * ((tg.ny + JR_ROWS - 1) / JR_ROWS);
-      k_jrange_val<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, y_min_s, y_max_s, cmin.p, cmax.p); KLAUNCH_CHECK();
-      k_jrange_idx<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, cmin.p, cmax.p, jn.p, jx.p); KLAUNCH_CHECK();
-      k_jrange_fin<<<cdiv(tg.nx, 256), 256, 0, st>>>(tg.nx, jn.p, jx.p, dpre.p); KLAUNCH_CHECK();
-    }
-    if (int rc = fetch_small(ctx, dpre.p, &hp, sizeof(Prelude))) return rc;
     j_strt_t = hp.j_strt; j_stop_t = hp.j_stop;
     if (j_strt_t > j_stop_t) jlat_icr = -1;
     if (j_strt_t < 1 || j_strt_t > tg.ny || j_stop_t < 1 || j_stop_t > tg.ny) {
