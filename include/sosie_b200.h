@@ -220,6 +220,16 @@ int sosie_interp3d_post_dev(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk, 
                             int32_t ixtrpl_bot, float vmin, float vmax, float rmiss_val, int32_t i_orca_trg,
                             int32_t c_orca_trg, int32_t lmout);
 
+/* ---- raw-binary twin of the mapping file (layout documented in csrc/mapfile.cu) ---------------------
+ * Same variables, order, types and layout as the NetCDF file written by P2D_MAPPING_AB (src/io_ezcdf.f90:2195) and read
+ * by RD_MAPPING_AB (:2280).  Host-side file I/O only (no context).  Return 0 or SOSIE_ERR_ARG (cannot open / bad file). */
+int sosie_mapping_write_bin(const char* path, int32_t nx, int32_t ny, const double* lon, const double* lat,
+                            const int32_t* metrics, const double* alphabeta, const int16_t* id_problem,
+                            const float* dist_np /* nullable */, double vflag);
+int sosie_mapping_read_header_bin(const char* path, int32_t* nx, int32_t* ny, int32_t* has_dist_np);
+int sosie_mapping_read_bin(const char* path, int32_t nx, int32_t ny, double* lon /* nullable */, double* lat /* nullable */,
+                           int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np /* nullable */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,7 +21,7 @@ import os
 
 import numpy as np
 
-__all__ = ["Sosie", "SosieError", "lib_path", "load_library", "EXPORTS"]
+__all__ = ["Sosie", "SosieError", "lib_path", "load_library", "EXPORTS", "mapping_write_bin", "mapping_read_bin"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -41,6 +41,7 @@ EXPORTS = [
     "sosie_rotate_uv", "sosie_rotate_uv_dev", "sosie_bilin_2d_first", "sosie_set_pipeline_min_targets",
     "sosie_host_register", "sosie_host_unregister", "sosie_bilin_src_rows",
     "sosie_akima_1d_3d", "sosie_akima_1d_3d_dev", "sosie_lbc_lnk", "sosie_lbc_lnk_dev", "sosie_interp3d_post", "sosie_interp3d_post_dev",
+    "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin",
 ]
 
 _lib = None
@@ -92,6 +93,37 @@ def _dp(t):
     if isinstance(t, int):
         return C.c_void_p(t)
     return C.c_void_p(t.data_ptr())
+
+
+def mapping_write_bin(path, lon, lat, mapping, vflag=-9999.0):
+    """binary twin of P2D_MAPPING_AB (src/io_ezcdf.f90:2195); mapping = dict(metrics, alphabeta, ipb[, dist_np])"""
+    lib = load_library()
+    lon, lat = _f64(lon), _f64(lat)
+    ny, nx = lon.shape
+    met, ab = _i32(mapping["metrics"]), _f64(mapping["alphabeta"])
+    ipb = np.ascontiguousarray(mapping["ipb"], np.int16)
+    dnp = mapping.get("dist_np")
+    dnp = None if dnp is None else _f32(dnp)
+    rc = lib.sosie_mapping_write_bin(os.fsencode(path), nx, ny, _p(lon), _p(lat), _p(met), _p(ab), _p(ipb), _p(dnp), C.c_double(vflag))
+    if rc != 0:
+        raise SosieError(f"sosie_mapping_write_bin({path}) failed with code {rc}")
+
+
+def mapping_read_bin(path):
+    """binary twin of RD_MAPPING_AB (src/io_ezcdf.f90:2280): returns dict(lon, lat, metrics, alphabeta, ipb, dist_np)"""
+    lib = load_library()
+    nx, ny, has = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = lib.sosie_mapping_read_header_bin(os.fsencode(path), C.byref(nx), C.byref(ny), C.byref(has))
+    if rc != 0:
+        raise SosieError(f"{path}: not a sosie_b200 mapping file")
+    nx, ny = nx.value, ny.value
+    out = dict(lon=np.empty((ny, nx)), lat=np.empty((ny, nx)), metrics=np.empty((3, ny, nx), np.int32),
+               alphabeta=np.empty((2, ny, nx)), ipb=np.empty((ny, nx), np.int16), dist_np=np.empty((ny, nx), np.float32))
+    rc = lib.sosie_mapping_read_bin(os.fsencode(path), nx, ny, _p(out["lon"]), _p(out["lat"]), _p(out["metrics"]), _p(out["alphabeta"]),
+                                    _p(out["ipb"]), _p(out["dist_np"]))
+    if rc != 0:
+        raise SosieError(f"sosie_mapping_read_bin({path}) failed with code {rc}")
+    return out
 
 
 class Sosie:

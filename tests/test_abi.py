@@ -65,3 +65,32 @@ def test_sass_is_sm100a():
         pytest.skip("no cuobjdump")
     out = subprocess.run([cuobjdump, "-lelf", sosie_b200.lib_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_mapping_binary_twin_roundtrip(tmp_path):
+    """the raw-binary twin of the mapping file (csrc/mapfile.cu) -- host-side I/O, no GPU needed.
+    A mapping built by the oracle (as stock CPU SOSIE would) survives the round trip bit for bit; the header is checked."""
+    import numpy as np
+    import sosie_b200
+    from oracle import oracle as O
+    from sosie_b200 import grids as G
+    O.build(); O.set_libm(O.PMATH)
+    cfg = G.config("E", 0.01)
+    Xt, Yt = G.trg_2d(cfg)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, 1)
+    _, mo = O.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt, l_reg_src=True)
+    f = str(tmp_path / "sosie_mapping_test.bin")
+    sosie_b200.mapping_write_bin(f, Xt, Yt, mo)
+    ny, nx = Xt.shape
+    import os
+    assert os.path.getsize(f) == 64 + nx * ny * (8 + 8 + 12 + 16 + 4 + 4)
+    back = sosie_b200.mapping_read_bin(f)
+    assert np.array_equal(back["lon"], Xt) and np.array_equal(back["lat"], Yt)
+    for k in ("metrics", "alphabeta", "ipb", "dist_np"):
+        assert np.array_equal(back[k], mo[k]), k
+    with open(f, "r+b") as fh:
+        fh.write(b"NOTAMAPF")
+    import pytest
+    with pytest.raises(sosie_b200.SosieError):
+        sosie_b200.mapping_read_bin(f)

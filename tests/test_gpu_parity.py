@@ -296,3 +296,37 @@ def test_pipelined_regular_2d_target_sharded(gpu, orc):
     Z1 = G.field_slabs(Xs, Ys, 2, seed=8)
     mg, mo = _first_vs_oracle(gpu, orc, 0, cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt, shard=(20, 41), tag="reg2d")
     assert mg["info"][4] == 1   # l_is_reg_t
+
+
+# ---------------------------------------------------------------------------------------------------
+# the 1 x N trajectory front ends (interp_to_ground_track.f90:627,750, interp_to_hydro_section.f90:464,601)
+# call MAPPING_BL with (1, N) target arrays and INTERP_BL point by point
+@pytest.mark.parametrize("src", ["orca", "regular"])
+def test_trajectory_mapping_and_interp_bl(gpu, orc, src):
+    rng = np.random.default_rng(17)
+    N = 3000
+    t = np.linspace(0.0, 1.0, N)
+    lon = np.mod(200.0 + 170.0 * t + 3.0 * np.sin(40 * t), 360.0)          # a satellite-like ground track
+    lat = 60.0 * np.sin(2 * np.pi * 3.3 * t) + rng.normal(0.0, 0.01, N)
+    Xt, Yt = lon[:, None].copy(), lat[:, None].copy()                       # Fortran (1, N) == numpy (N, 1)
+    if src == "orca":
+        cfg = G.config("B", 0.5)
+        Xs, Ys, kew, lreg = cfg["src_lon"], cfg["src_lat"], -1, False       # the tools call MAPPING_BL(-1, ...)
+    else:
+        cfg = G.config("D", 0.1)
+        Xs, Ys = G.src_2d(cfg)
+        kew, lreg = -1, False                                               # 2-D arrays of a regular grid: EASY search, no pole rows
+    Z = G.field_slabs(Xs, Ys, 1, seed=3)[0]
+    gpu.bilin_set_grids(kew, Xs, Ys, Xt, Yt, l_reg_src=lreg)
+    gpu.bilin_map()
+    mg = gpu.bilin_get_map()
+    mo = orc.mapping_bl(kew, Xs, Ys, Xt, Yt)
+    for k in ("metrics", "alphabeta", "ipb", "dist_np"):
+        assert np.array_equal(mg[k], mo[k]), (src, k, (mg[k] != mo[k]).sum())
+    iP, jP, iq = (mg["metrics"][q][:, 0] for q in range(3))
+    xa, xb = mg["alphabeta"][0][:, 0], mg["alphabeta"][1][:, 0]
+    out = gpu.interp_bl(kew, iP, jP, iq, xa, xb, Z)
+    ref = np.array([orc.interp_bl(kew, iP[k], jP[k], iq[k], xa[k], xb[k], Z) for k in range(0, N, 7)], np.float32)
+    assert np.array_equal(out[::7], ref)
+    found = mg["metrics"][0][:, 0] > 0
+    assert found.mean() > 0.8          # most of the track lies inside the model domain
