@@ -74,52 +74,26 @@ struct PostOps {
   float rmiss;
 };
 
-#define SLAB_UNROLL 4
 #define APPLY_SLABS_PER_CHUNK 8
 #define APPLY_SLABS_PER_CHUNK_STAGED 32
-// grid: x = target tiles, y = slab chunks.  Each thread: one target, all slabs of its chunk.
-__global__ void __launch_bounds__(256)
-k_apply(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ Z1,
-        float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm) {
-  const size_t src_stride = (size_t)v.nreal;
-  const int s0 = blockIdx.y * slabs_per_chunk;
-  const int s1 = min(s0 + slabs_per_chunk, nslab);
-  // 32 x 8 target tile per block: a compact source footprint (L1/L2 reuse of the gathers) for any smooth mapping,
-  // and still one full 128-byte store per warp
+// One slab (the first call of a 2-D job, the per-record call of the unchanged driver loop): nothing to amortise the
+// record over, so the kernel is a latency chain record -> 4 gathers -> store.  A lean body (no slab unrolling: half the
+// registers of a slab-unrolled body) keeps every SM at full occupancy to cover it.
+__global__ void __launch_bounds__(256, 8)
+k_apply1(const int4* __restrict__ pidx, const float4* __restrict__ pw, SlabView v, const float* __restrict__ Z1, float* __restrict__ Z2,
+         PostOps po, TileGeom tgm) {
   for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
     const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
     const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);  // 0-based
     if (i >= tgm.nx || j > tgm.j1) continue;
     const size_t k = (size_t)i + (size_t)j * tgm.nx;
-    const int4 id = pidx[k];
-    const float4 w = pw[k];
+    const int4 id = __ldcs(pidx + k);     // streamed once: do not displace the source slab in L2
+    const float4 w = __ldcs(pw + k);
     const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
-    const bool masked = po.mask_trg ? (po.mask_trg[k] == 0) : false;
-    int s = s0;
-    if (id.x >= 0 && id.w < v.nreal && id.x < v.nreal && id.y < v.nreal && id.z < v.nreal) {
-      // fast path: four plain gathers per slab, SLAB_UNROLL slabs in flight
-      for (; s + SLAB_UNROLL <= s1; s += SLAB_UNROLL) {
-        float z[SLAB_UNROLL][4];
-#pragma unroll
-        for (int u = 0; u < SLAB_UNROLL; u++) {
-          const float* Z = Z1 + (size_t)(s + u) * src_stride;
-          z[u][0] = __ldg(Z + id.x); z[u][1] = __ldg(Z + id.y); z[u][2] = __ldg(Z + id.z); z[u][3] = __ldg(Z + id.w);
-        }
-#pragma unroll
-        for (int u = 0; u < SLAB_UNROLL; u++) {
-          float r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z[u][0], w.x), __fmul_rn(z[u][1], w.y)), __fmul_rn(z[u][2], w.z)), __fmul_rn(z[u][3], w.w)), wup);
-          if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
-          if (masked) r = po.rmiss;
-          __stcs(Z2 + (size_t)(s + u) * nt + k, r);
-        }
-      }
-    }
-    for (; s < s1; s++) {
-      float r = interp_one(Z1 + (size_t)s * src_stride, v, id, w, wup);
-      if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
-      if (masked) r = po.rmiss;
-      __stcs(Z2 + (size_t)s * nt + k, r);
-    }
+    float r = interp_one(Z1, v, id, w, wup);
+    if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+    if (po.mask_trg && po.mask_trg[k] == 0) r = po.rmiss;
+    __stcs(Z2 + k, r);
   }
 }
 
@@ -457,7 +431,7 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
     prof_end(ctx, SOSIE_T_APPLY);
   } else {
     prof_begin(ctx, SOSIE_T_APPLY);
-    k_apply<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po, tgm);
+    k_apply1<<<grid.x, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, v, dZ1, dZ2, po, tgm);   // nslab == 1 here
     KLAUNCH_CHECK();
     prof_end(ctx, SOSIE_T_APPLY);
   }
