@@ -162,6 +162,8 @@ int sosie_akima_set_grids(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t
                           const double* X20, const double* Y20, int32_t trg_1d);
 int sosie_akima_apply(sosie_ctx* ctx, int32_t nslab, const float* Z1, float* Z2);
 int sosie_akima_apply_dev(sosie_ctx* ctx, int32_t nslab, const float* dZ1, float* dZ2);
+/* test hook: per-point slopes kernel instead of the shared-memory tiled one (identical results) */
+int sosie_akima_untiled_slopes(sosie_ctx* ctx, int32_t on);
 /* the SAVE'd ixy_pos(nx2,ny2,2) table (src/mod_akima_2d.f90:41) */
 int sosie_akima_get_ixy(sosie_ctx* ctx, int32_t* ixy_pos);
 

@@ -41,7 +41,7 @@ EXPORTS = [
     "sosie_rotate_uv", "sosie_rotate_uv_dev", "sosie_bilin_2d_first", "sosie_set_pipeline_min_targets",
     "sosie_host_register", "sosie_host_unregister", "sosie_bilin_src_rows",
     "sosie_akima_1d_3d", "sosie_akima_1d_3d_dev", "sosie_lbc_lnk", "sosie_lbc_lnk_dev", "sosie_interp3d_post", "sosie_interp3d_post_dev",
-    "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin",
+    "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
 ]
 
 _lib = None
@@ -340,6 +340,10 @@ class Sosie:
 
     def akima_apply_dev(self, nslab, dZ1, dZ2):
         self._ck(self._lib.sosie_akima_apply_dev(self._h, int(nslab), _dp(dZ1), _dp(dZ2)))
+
+    def akima_untiled_slopes(self, on=True):
+        """test hook: per-point slopes kernel instead of the shared-memory tiled one"""
+        self._ck(self._lib.sosie_akima_untiled_slopes(self._h, int(on)))
 
     def akima_get_ixy(self):
         nx1, ny1, nx2, ny2 = self._ashape

@@ -233,6 +233,93 @@ k_slopes(const double* __restrict__ ZX, const double* __restrict__ ZY, const dou
   }
 }
 
+
+// ---- SLOPES_AKIMA (:483-664) with the divided differences shared through shared memory ---------------------------------
+// Per point the reference forms 12 divided differences (4 along x on its row, 4 along y on its column, 4 along y on the
+// neighbouring columns) and 7 more quotients.  Neighbouring points use the same differences: a 32x8 tile needs 35x8
+// x-differences and 34x11 y-differences instead of 12x256, so the fp64 divides per point drop from 19 to ~9.6 (the
+// kernel is fp64-divide bound).  Same operands, same operations -> same bits as k_slopes.
+#define SLT_X 32
+#define SLT_Y 8
+__global__ void __launch_bounds__(SLT_X * SLT_Y)
+k_slopes_tiled(const double* __restrict__ ZX, const double* __restrict__ ZY, const double* __restrict__ ZFb, int nx, int ny,
+               double* dFdX, double* dFdY, double* d2F, size_t zf_stride, size_t out_stride, const uint8_t* __restrict__ needed,
+               int tiles_x, int ntiles) {
+  const int n8 = nx + 4;
+  const double* ZF = ZFb + blockIdx.y * zf_stride;
+  double* ox = dFdX + blockIdx.y * out_stride;
+  double* oy = dFdY + blockIdx.y * out_stride;
+  double* oxy = d2F + blockIdx.y * out_stride;
+  __shared__ double sDX[SLT_Y][SLT_X + 3];        // DXe(I-2 .. I+1, J)      : columns c0 .. c0+SLT_X+2 (8-extended), rows of the tile
+  __shared__ double sDY[SLT_Y + 3][SLT_X + 2];    // DYe(I-1 .. I+1, J-2..J+1): columns c0+1 .. c0+SLT_X+2, rows r0 .. r0+SLT_Y+2
+  __shared__ int s_any;
+  const int tx = threadIdx.x % SLT_X, ty = threadIdx.x / SLT_X;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int i0 = (tile % tiles_x) * SLT_X, j0 = (tile / tiles_x) * SLT_Y;   // 0-based origin of the tile in (nx, ny)
+    const int ji = i0 + tx + 1, jj = j0 + ty + 1;                               // 1-based point
+    const bool inside = (ji <= nx) && (jj <= ny);
+    const size_t k = (size_t)(ji - 1) + (size_t)(jj - 1) * nx;
+    const bool need = inside && (!needed || needed[k]);
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    if (need) s_any = 1;
+    __syncthreads();
+    if (!s_any) continue;   // block-uniform
+    // 8-extended index of point (ji,jj) is (ji+2, jj+2).  DXe(i,j) = (F(i+1,j)-F(i,j)) / guard(X(i+1,j)-X(i,j)), i = ji .. ji+3
+    for (int e = threadIdx.x; e < SLT_Y * (SLT_X + 3); e += SLT_X * SLT_Y) {
+      const int cy = e / (SLT_X + 3), cx = e % (SLT_X + 3);
+      const int i = i0 + 1 + cx, j = j0 + cy + 1 + 2;          // i = (i0+1) .. : DXe(ji + q), q = 0..3 for the tile's first point
+      double v = 0.0;
+      if (i + 1 <= n8 && j <= ny + 4) v = (A2D(ZF, n8, i + 1, j) - A2D(ZF, n8, i, j)) / d_guard(A2D(ZX, n8, i + 1, j) - A2D(ZX, n8, i, j));
+      sDX[cy][cx] = v;
+    }
+    // DYe(i,j) = (F(i,j+1)-F(i,j)) / guard(Y(i,j+1)-Y(i,j)), i = ji+1 .. ji+3, j = jj .. jj+3
+    for (int e = threadIdx.x; e < (SLT_Y + 3) * (SLT_X + 2); e += SLT_X * SLT_Y) {
+      const int cy = e / (SLT_X + 2), cx = e % (SLT_X + 2);
+      const int i = i0 + 2 + cx, j = j0 + 1 + cy;
+      double v = 0.0;
+      if (i <= n8 && j + 1 <= ny + 4) v = (A2D(ZF, n8, i, j + 1) - A2D(ZF, n8, i, j)) / d_guard(A2D(ZY, n8, i, j + 1) - A2D(ZY, n8, i, j));
+      sDY[cy][cx] = v;
+    }
+    __syncthreads();
+    if (need) {
+      const int ip1 = ji + 1, ip2 = ji + 2, jp1 = jj + 1, jp2 = jj + 2;
+      double Wx2 = 0., Wx3 = 0., Wy2 = 0., Wy3 = 0.;
+      double m1 = sDX[ty][tx], m2 = sDX[ty][tx + 1], m3 = sDX[ty][tx + 2], m4 = sDX[ty][tx + 3];   // DXe(ji..ji+3, jp2)
+      double rx;
+      if ((m1 == m2) && (m3 == m4)) rx = 0.5 * (m2 + m3);
+      else {
+        Wx2 = fabs(m4 - m3);
+        Wx3 = fabs(m2 - m1);
+        rx = (Wx2 * m2 + Wx3 * m3) / (Wx2 + Wx3);
+      }
+      ox[k] = rx;
+      // column ip2 -> cx = ip2 - (i0+2) = tx + 1 ; rows jj..jj+3 -> cy = ty .. ty+3
+      m1 = sDY[ty][tx + 1]; m2 = sDY[ty + 1][tx + 1]; m3 = sDY[ty + 2][tx + 1]; m4 = sDY[ty + 3][tx + 1];
+      double ry;
+      if ((m1 == m2) && (m3 == m4)) ry = 0.5 * (m2 + m3);
+      else {
+        Wy2 = fabs(m4 - m3);
+        Wy3 = fabs(m2 - m1);
+        ry = (Wy2 * m2 + Wy3 * m3) / (Wy2 + Wy3);
+      }
+      oy[k] = ry;
+      const double d22 = sDY[ty + 1][tx], d23 = sDY[ty + 2][tx];           // column ip1, rows jp1, jp2
+      const double d42 = sDY[ty + 1][tx + 2], d43 = sDY[ty + 2][tx + 2];   // column ji+3
+      const double e22 = (m2 - d22) / d_guard(A2D(ZX, n8, ip2, jp1) - A2D(ZX, n8, ip1, jp1));
+      const double e23 = (m3 - d23) / d_guard(A2D(ZX, n8, ip2, jp2) - A2D(ZX, n8, ip1, jp2));
+      const double e32 = (d42 - m2) / d_guard(A2D(ZX, n8, ji + 3, jp2) - A2D(ZX, n8, ip2, jp2));
+      const double e33 = (d43 - m3) / d_guard(A2D(ZX, n8, ji + 3, jp2) - A2D(ZX, n8, ip2, jp2));
+      if (((Wx2 == 0) && (Wx3 == 0)) || ((Wy2 == 0) && (Wy3 == 0))) {
+        if ((Wx2 == 0) && (Wx3 == 0)) { Wx2 = 1.; Wx3 = 1.; }
+        if ((Wy2 == 0) && (Wy3 == 0)) { Wy2 = 1.; Wy3 = 1.; }
+      }
+      oxy[k] = (Wx2 * (Wy2 * e22 + Wy3 * e23) + Wx3 * (Wy2 * e32 + Wy3 * e33)) / ((Wx2 + Wx3) * (Wy2 + Wy3));
+    }
+    __syncthreads();   // the next tile rewrites the shared differences
+  }
+}
+
 // ---- find_nearest_akima (:670-745): literal state machine, one thread per target ---------------------
 __global__ void k_find_nearest_akima(const double* __restrict__ plon, const double* __restrict__ plat, int nxs, int nys,
                                      double x0, double x1, double y0, double y1, const double* __restrict__ X2,
@@ -542,8 +629,15 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
     if (int rc = feb_field(ctx, ctx->ak_kew, ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, nx1, ny1, ctx->ak_iorca, ns, tmp)) return rc;
     k_feb_center<double><<<dim3(grid_for(ctx, ne8, 256), ns), 256, 0, st>>>(ctx->ak_zF.p, ni1, nj1, ctx->ak_ZF8.p, ne, ne8); KLAUNCH_CHECK();
     if (int rc = feb_field(ctx, kewp, ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, 0, ns, tmp)) return rc;
-    k_slopes<<<dim3(grid_for(ctx, ne, 128), ns), 128, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
-                                                                ctx->ak_sxy.p, ne8, ne, ctx->ak_needed.p); KLAUNCH_CHECK();
+    if (ctx->ak_untiled_slopes) {
+      k_slopes<<<dim3(grid_for(ctx, ne, 128), ns), 128, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
+                                                                  ctx->ak_sxy.p, ne8, ne, ctx->ak_needed.p); KLAUNCH_CHECK();
+    } else {
+      const int tiles_x = (ni1 + SLT_X - 1) / SLT_X, ntiles = tiles_x * ((nj1 + SLT_Y - 1) / SLT_Y);
+      const int gx = std::min(ntiles, ctx->num_sms * 16);
+      k_slopes_tiled<<<dim3(gx, ns), SLT_X * SLT_Y, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
+                                                            ctx->ak_sxy.p, ne8, ne, ctx->ak_needed.p, tiles_x, ntiles); KLAUNCH_CHECK();
+    }
     prof_end(ctx, SOSIE_T_AKIMA_PREP);
     prof_begin(ctx, SOSIE_T_AKIMA_EVAL);
     k_akima_eval<<<dim3(grid_for(ctx, nt, 128), ns), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, ctx->ak_sx.p, ctx->ak_sy.p, ctx->ak_sxy.p,

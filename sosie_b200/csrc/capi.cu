@@ -448,6 +448,12 @@ int sosie_akima_apply(sosie_ctx* c, int32_t nslab, const float* Z1, float* Z2) {
   return SOSIE_OK;
 }
 
+int sosie_akima_untiled_slopes(sosie_ctx* c, int32_t on) {
+  NEED(c);
+  ctx->ak_untiled_slopes = on != 0;
+  return SOSIE_OK;
+}
+
 int sosie_akima_get_ixy(sosie_ctx* c, int32_t* ixy) {
   NEED(c);
   if (!ctx->ak_set || !ixy) return SOSIE_ERR_STATE;

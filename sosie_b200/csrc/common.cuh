@@ -140,6 +140,7 @@ struct sosie_ctx {
   DBuf<double> ak_ZX8, ak_ZY8;       // twice-extended coordinates (nx1+8, ny1+8)
   DBuf<double> ak_X2, ak_Y2;         // target coordinates (2-D)
   DBuf<int32_t> ak_ixy;              // (nx2,ny2,2)
+  bool ak_untiled_slopes = false;    // tests: the per-point slopes kernel instead of the shared-memory tiled one
   DBuf<uint8_t> ak_needed;           // (nx1+4,ny1+4): source points whose slopes some target reads
   DBuf<double> ak_zF, ak_ZF8, ak_sx, ak_sy, ak_sxy;  // per-slab work arrays
   DBuf<float> ak_stage1, ak_stage2;

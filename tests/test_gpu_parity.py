@@ -190,10 +190,15 @@ def test_akima_vs_oracle(gpu, orc, scale, nslab):
     cfg = G.config("A", scale)
     Xs, Ys = G.src_2d(cfg)
     Z1 = G.field_slabs(Xs, Ys, nslab, seed=6)
-    Z2g = gpu.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"])
     Z2o, ixy = orc.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"])
-    assert np.array_equal(gpu.akima_get_ixy(), ixy)
-    assert np.array_equal(Z2g, Z2o), f"akima differs at {(Z2g != Z2o).sum()} points, max {np.abs(Z2g - Z2o).max()}"
+    for untiled in (False, True):        # shared-memory tiled slopes (default) and the per-point kernel
+        gpu.akima_untiled_slopes(untiled)
+        try:
+            Z2g = gpu.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"])
+        finally:
+            gpu.akima_untiled_slopes(False)
+        assert np.array_equal(gpu.akima_get_ixy(), ixy)
+        assert np.array_equal(Z2g, Z2o), f"akima(untiled={untiled}) differs at {(Z2g != Z2o).sum()} points, max {np.abs(Z2g - Z2o).max()}"
 
 
 def test_akima_nonperiodic_regional(gpu, orc):
@@ -204,6 +209,11 @@ def test_akima_nonperiodic_regional(gpu, orc):
     tl = 12.0 + 0.37 * np.arange(70); tt = -18.0 + 0.29 * np.arange(55)
     Z2g = gpu.akima_2d(-1, lon, lat, Z1, tl, tt)
     Z2o, _ = orc.akima_2d(-1, lon, lat, Z1, tl, tt)
+    assert np.array_equal(Z2g, Z2o)
+    # a target that uses a corner of the source only: most slope tiles are skipped (needed map), partial tiles at the edges
+    tl2 = 33.1 + 0.11 * np.arange(45); tt2 = -4.9 + 0.13 * np.arange(37)
+    Z2g = gpu.akima_2d(-1, lon, lat, Z1, tl2, tt2)
+    Z2o, _ = orc.akima_2d(-1, lon, lat, Z1, tl2, tt2)
     assert np.array_equal(Z2g, Z2o)
 
 
