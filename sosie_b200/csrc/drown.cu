@@ -25,6 +25,27 @@ struct BdGeom {
   int jimW, jipW, jimE, jipE;  // periodic neighbours of column 1 (W) and column ni (E): vim_per/vip_per (:98-101)
 };
 
+// exact unsigned 32-bit division by an invariant divisor (Granlund & Montgomery 1994): the list kernels decode
+// (mask, j, i) from a linear cell index for every entry; three hardware divides cost more than the cell update itself
+struct FastDiv {
+  unsigned int d, M, s1, s2;
+};
+static FastDiv make_fastdiv(unsigned int d) {
+  FastDiv f;
+  f.d = d; f.M = 0; f.s1 = 0; f.s2 = 0;
+  if (d <= 1) return f;
+  unsigned int l = 0;
+  while ((1ull << l) < d) l++;
+  f.M = (unsigned int)((((1ull << l) - d) << 32) / d + 1);
+  f.s1 = l < 1 ? l : 1; f.s2 = l > 1 ? l - 1 : 0;
+  return f;
+}
+__device__ __forceinline__ unsigned int fdiv(unsigned int a, const FastDiv& f) {
+  if (f.d <= 1) return a;
+  const unsigned int t = __umulhi(f.M, a);
+  return (t + ((a - t) >> f.s1)) >> f.s2;
+}
+
 static BdGeom make_bdgeom(int ni, int nj, int k_ew) {
   BdGeom g;
   g.ni = ni; g.nj = nj; g.k_ew = k_ew;
@@ -33,8 +54,10 @@ static BdGeom make_bdgeom(int ni, int nj, int k_ew) {
 }
 
 // ---- BDROWN --------------------------------------------------------------------------------------------
-__global__ void k_bd_init(const int32_t* __restrict__ mask, size_t n, int nmask, int8_t* m0, int32_t* cnt) {
-  // m0 = mask (1 byte), cnt[0][ms] = number of land cells
+__global__ void __launch_bounds__(256)
+k_bd_init(const int32_t* __restrict__ mask, size_t n, int nmask, int8_t* m0, int32_t* cnt) {
+  // m0 = mask (1 byte), cnt[0][ms] = number of land cells (one atomic per block: with hundreds of masks the per-warp
+  // atomics on a few hundred addresses were 10x the cost of the copy)
   int ms = blockIdx.y;
   const int32_t* mk = mask + (size_t)ms * n;
   int8_t* m = m0 + (size_t)ms * n;
@@ -44,8 +67,15 @@ __global__ void k_bd_init(const int32_t* __restrict__ mask, size_t n, int nmask,
     m[k] = (int8_t)v;
     local += (v == 0);
   }
+  __shared__ int sh[8];
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-  if ((threadIdx.x & 31) == 0 && local) atomicAdd(&cnt[ms], local);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
+    if (t) atomicAdd(&cnt[ms], t);
+  }
 }
 
 // zonal-mean prefill (:109-120): one WARP per (row, slab).  The REAL(4) sum is sequential in i as in the reference
@@ -298,61 +328,80 @@ struct BdlCounters {   // device-resident, zeroed per call
 
 __global__ void k_bdl_rtot0(const unsigned int* __restrict__ nsel, unsigned int* rtot0) { *rtot0 = *nsel; }
 
+// One sweep of the mask dynamics.  Each WARP owns a contiguous run of the remaining-land list and walks it twice:
+// pass 1 counts the cells that turn coastline / stay land, ONE atomic per list then reserves the warp's output ranges,
+// pass 2 repeats the (L1-resident) tests and writes in list order -- no block barrier, ~2 same-address atomics per
+// warp per sweep, neighbouring cells stay neighbours in the lists.
+#define BDL_RUN 8   // 32-entry groups per warp run
 __global__ void __launch_bounds__(256)
-k_bdl_sweep(BdGeom g, uint8_t* mwb, const unsigned int* __restrict__ Rin, unsigned int* Rout, unsigned int* Lv, BdlCounters C,
-            int32_t* rem_out, int j) {
-  const unsigned int n = (unsigned int)g.ni * (unsigned int)g.nj;
+k_bdl_sweep(BdGeom g, FastDiv dn, FastDiv dni, uint8_t* mwb, const unsigned int* __restrict__ Rin, unsigned int* Rout, unsigned int* Lv,
+            BdlCounters C, int32_t* rem_out, int j) {
+  const unsigned int n = dn.d;
   const unsigned int cnt = C.rtot()[j - 1];
   if (cnt == 0) return;
   const unsigned int lbase = C.rtot()[0] - cnt;   // cells drowned before this sweep = all land - land left after sweep j-1
-  for (unsigned int q0 = blockIdx.x * blockDim.x; q0 < cnt; q0 += gridDim.x * blockDim.x) {
-    const unsigned int q = q0 + threadIdx.x;
-    int coast = 0, valid = q < cnt;
-    unsigned int gid = 0, ms = 0;
-    if (valid) {
-      gid = Rin[q];
-      ms = gid / n;
-      const unsigned int k = gid - ms * n;
-      const int jj = (int)(k / (unsigned int)g.ni) + 1, ji = (int)(k % (unsigned int)g.ni) + 1;
-      float dummy;
-      coast = bd_cell<false>(g, mwb + (size_t)ms * n, nullptr, ji, jj, 0, 0.f, 0.f, dummy, j);
+  const unsigned int lane = threadIdx.x & 31;
+  const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = (gridDim.x * blockDim.x) >> 5;
+  const unsigned int below = (1u << lane) - 1u;
+  const unsigned int run = 32u * BDL_RUN;
+  for (unsigned long long r0 = (unsigned long long)warp * run; r0 < cnt; r0 += (unsigned long long)nwarp * run) {
+    const unsigned int q0 = (unsigned int)r0;
+    unsigned int nc = 0, nr = 0, mcs[BDL_RUN];
+#pragma unroll
+    for (int u = 0; u < BDL_RUN; u++) {
+      const unsigned int q = q0 + 32u * u + lane;
+      int coast = 0;
+      const bool valid = q < cnt;
+      if (valid) {
+        const unsigned int gid = Rin[q];
+        const unsigned int ms = fdiv(gid, dn), k = gid - ms * n;
+        const unsigned int jr = fdiv(k, dni);
+        float dummy;
+        coast = bd_cell<false>(g, mwb + (size_t)ms * n, nullptr, (int)(k - jr * dni.d) + 1, (int)jr + 1, 0, 0.f, 0.f, dummy, j);
+      }
+      const unsigned int mc = __ballot_sync(0xffffffffu, valid && coast);
+      const unsigned int mv = __ballot_sync(0xffffffffu, valid);
+      mcs[u] = mc;
+      nc += __popc(mc); nr += __popc(mv & ~mc);
     }
-    // block-aggregated appends: one global atomic per list per block iteration (same-address atomics serialise in
-    // L2; per-thread ones made a sweep cost 0.25 ms); order inside a block is kept, so neighbouring cells stay
-    // neighbours in the lists
-    const unsigned int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const unsigned int mc = __ballot_sync(0xffffffffu, valid && coast), mr = __ballot_sync(0xffffffffu, valid && !coast);
-    __shared__ unsigned int wc[8], wr[8], bc, br;
-    if (lane == 0) { wc[wid] = __popc(mc); wr[wid] = __popc(mr); }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      unsigned int tc = 0, tr = 0;
-      for (int w = 0; w < 8; w++) { unsigned int a = wc[w], b = wr[w]; wc[w] = tc; wr[w] = tr; tc += a; tr += b; }
-      bc = tc ? atomicAdd(&C.lvcount()[j], tc) : 0u;
-      br = tr ? atomicAdd(&C.rtot()[j], tr) : 0u;
+    unsigned int bc = 0, br = 0;
+    if (lane == 0) {
+      if (nc) bc = atomicAdd(&C.lvcount()[j], nc);
+      if (nr) br = atomicAdd(&C.rtot()[j], nr);
     }
-    __syncthreads();
-    const unsigned int below = (1u << lane) - 1u;
-    if (valid && coast) {
-      mwb[gid] = (uint8_t)(j + 1);   // invisible to this sweep's tests (lim = j)
-      Lv[lbase + bc + wc[wid] + __popc(mc & below)] = gid;
-    } else if (valid) {
-      Rout[br + wr[wid] + __popc(mr & below)] = gid;
+    bc = __shfl_sync(0xffffffffu, bc, 0) + lbase;
+    br = __shfl_sync(0xffffffffu, br, 0);
+    // pass 2: the outcome of the tests is in mcs[].  No ordering with other warps is needed: a cell drowned during this
+    // sweep (mw = j+1) reads as land (lim = j) before AND after the write.
+#pragma unroll
+    for (int u = 0; u < BDL_RUN; u++) {
+      const unsigned int q = q0 + 32u * u + lane;
+      const bool valid = q < cnt;
+      const unsigned int mc = mcs[u], mv = __ballot_sync(0xffffffffu, valid), mr = mv & ~mc;
+      if (valid) {
+        const unsigned int gid = Rin[q];
+        if ((mc >> lane) & 1u) {
+          mwb[gid] = (uint8_t)(j + 1);
+          Lv[bc + __popc(mc & below)] = gid;
+        } else {
+          Rout[br + __popc(mr & below)] = gid;
+          if (rem_out) {  // per-mask counts (several masks only; with one mask rtot[j] is the count)
+            const unsigned int ms = fdiv(gid, dn);
+            const unsigned int peers = __match_any_sync(mr, ms);
+            if (lane == (unsigned int)(__ffs(peers) - 1)) atomicAdd(&rem_out[ms], __popc(peers));
+          }
+        }
+      }
+      bc += __popc(mc); br += __popc(mr);
     }
-    if (rem_out) {  // per-mask counts (several masks only; with one mask rtot[j] is the count)
-      const int surv = valid && !coast;
-      const unsigned int peers = __match_any_sync(0xffffffffu, surv ? ms : 0xffffffffu);
-      if (surv && lane == (unsigned int)(__ffs(peers) - 1)) atomicAdd(&rem_out[ms], __popc(peers));
-    }
-    __syncthreads();   // wc / wr are rewritten by the next iteration
   }
 }
 
 // values of the level-j cells for every slab of their mask, in place (the sweep kernel's arithmetic)
-__global__ void __launch_bounds__(256)
-k_bdl_level(BdGeom g, float* Xb, const uint8_t* __restrict__ mwb, const unsigned int* __restrict__ Lv, BdlCounters C, int j,
-            int mask_per_slab, int nslab, int slabs_per_item, float zmin, float zmax) {
-  const unsigned int n = (unsigned int)g.ni * (unsigned int)g.nj;
+__global__ void __launch_bounds__(256, 3)
+k_bdl_level(BdGeom g, FastDiv dn, FastDiv dni, float* Xb, const uint8_t* __restrict__ mwb, const unsigned int* __restrict__ Lv,
+            BdlCounters C, int j, int mask_per_slab, int nslab, int slabs_per_item, float zmin, float zmax) {
+  const unsigned int n = dn.d;
   const unsigned int cnt = C.lvcount()[j];
   if (cnt == 0) return;
   const unsigned int lbase = C.rtot()[0] - C.rtot()[j - 1];
@@ -363,8 +412,9 @@ k_bdl_level(BdGeom g, float* Xb, const uint8_t* __restrict__ mwb, const unsigned
        it += (unsigned long long)gridDim.x * blockDim.x) {
     const unsigned int q = (unsigned int)(it % cnt), c = (unsigned int)(it / cnt);
     const unsigned int gid = Lv[lbase + q];
-    const unsigned int ms = gid / n, k = gid - ms * n;
-    const int jj = (int)(k / (unsigned int)g.ni) + 1, ji = (int)(k % (unsigned int)g.ni) + 1;
+    const unsigned int ms = fdiv(gid, dn), k = gid - ms * n;
+    const unsigned int jr = fdiv(k, dni);
+    const int jj = (int)jr + 1, ji = (int)(k - jr * dni.d) + 1;
     const uint8_t* mw = mwb + (size_t)ms * n;
     int sa = (int)ms, sb = (int)ms + 1;
     if (!mask_per_slab) { sa = (int)c * slabs_per_item; sb = min(nslab, sa + slabs_per_item); }
@@ -414,17 +464,18 @@ __global__ void k_sml_gather(const float* __restrict__ Xb, const unsigned int* _
     else for (int s = 0; s < nslab; s++) xo[(size_t)s * cnt + q] = Xb[(size_t)s * n + gid];
   }
 }
-__global__ void __launch_bounds__(256)
-k_sml_pass(BdGeom g, const float* __restrict__ xinb, float* xoutb, const float* __restrict__ xo, const unsigned int* __restrict__ R0,
-           unsigned int cnt, int mask_per_slab, int nslab, int slabs_per_block) {
+__global__ void __launch_bounds__(256, 8)   // 32 registers: the gather is latency bound, occupancy wins over the small spill (measured)
+k_sml_pass(BdGeom g, FastDiv dn, FastDiv dni, const float* __restrict__ xinb, float* xoutb, const float* __restrict__ xo,
+           const unsigned int* __restrict__ R0, unsigned int cnt, int mask_per_slab, int nslab, int slabs_per_block) {
   const int ni = g.ni, nj = g.nj;
-  const unsigned int n = (unsigned int)ni * (unsigned int)nj;
+  const unsigned int n = dn.d;
   const float w0 = 0.35f, omw = 1.f - w0, c4 = 4.f * (1.f + RIS2F);
   const int s0 = blockIdx.y * slabs_per_block, s1 = min(nslab, s0 + slabs_per_block);
   for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
     const unsigned int gid = R0[q];
-    const unsigned int ms = gid / n, k = gid - ms * n;
-    const int jj = (int)(k / (unsigned int)ni) + 1, ji = (int)(k % (unsigned int)ni) + 1;
+    const unsigned int ms = fdiv(gid, dn), k = gid - ms * n;
+    const unsigned int jr = fdiv(k, dni);
+    const int jj = (int)jr + 1, ji = (int)(k - jr * dni.d) + 1;
     if (jj < 2 || jj > nj - 1) continue;
     int jim = ji - 1, jip = ji + 1;
     if (ji == 1) { if (g.k_ew >= 0) { jim = g.jimW; jip = g.jipW; } else continue; }
@@ -853,6 +904,7 @@ static int bdrown_levels(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, 
   unsigned int* nsel = ctx->dr_ctr.p + 2 * (size_t)(nb_inc + 1);   // [0] land cells, [1] smoothing fallback flag
   CK(ctx->dr_R0.alloc(ncell)); CK(ctx->dr_Ra.alloc(ncell)); CK(ctx->dr_Rb.alloc(ncell)); CK(ctx->dr_Lv.alloc(ncell));
   uint8_t* mw = reinterpret_cast<uint8_t*>(ctx->dr_m0.p);
+  const FastDiv dn = make_fastdiv((unsigned int)n), dni = make_fastdiv((unsigned int)ni);
   k_bd_init<<<dim3(grid_for(ctx, n, 256, 4), nmask), 256, 0, st>>>(dmask, n, nmask, ctx->dr_m0.p, rem); KLAUNCH_CHECK();
   k_bd_prefill<<<grid_for(ctx, (size_t)nj * nslab * 32, 256, 8), 256, 0, st>>>(dX, dmask, ni, nj, nslab, mask_per_slab); KLAUNCH_CHECK();
   {  // R0 = ordered list of all land cells (global index ms*n + k)
@@ -869,9 +921,9 @@ static int bdrown_levels(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, 
   {  // phase A: the mask dynamics, once per mask
     const unsigned int* Rin = ctx->dr_R0.p;
     unsigned int* Rout = ctx->dr_Ra.p;
-    const int gx = grid_for(ctx, ncell, 256, 4);
+    const int gx = grid_for(ctx, ncell / BDL_RUN + 1, 256, 8);
     for (int j = 1; j <= nb_inc; j++) {
-      k_bdl_sweep<<<gx, 256, 0, st>>>(g, mw, Rin, Rout, ctx->dr_Lv.p, C, nmask > 1 ? rem + (size_t)j * nmask : nullptr, j); KLAUNCH_CHECK();
+      k_bdl_sweep<<<gx, 256, 0, st>>>(g, dn, dni, mw, Rin, Rout, ctx->dr_Lv.p, C, nmask > 1 ? rem + (size_t)j * nmask : nullptr, j); KLAUNCH_CHECK();
       Rin = Rout;
       Rout = (Rout == ctx->dr_Ra.p) ? ctx->dr_Rb.p : ctx->dr_Ra.p;
     }
@@ -880,7 +932,7 @@ static int bdrown_levels(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, 
     const int spi = mask_per_slab ? 1 : std::max(1, (nslab + 63) / 64);   // slabs per work item
     const int gx = ctx->num_sms * 4;   // persistent-style: the level sizes live on the device, blocks stride over them
     for (int j = 1; j <= nb_inc; j++) {
-      k_bdl_level<<<gx, 256, 0, st>>>(g, dX, mw, ctx->dr_Lv.p, C, j, mask_per_slab, nslab, spi, pmin, pmax); KLAUNCH_CHECK();
+      k_bdl_level<<<gx, 256, 0, st>>>(g, dn, dni, dX, mw, ctx->dr_Lv.p, C, j, mask_per_slab, nslab, spi, pmin, pmax); KLAUNCH_CHECK();
     }
   }
   prof_end(ctx, SOSIE_T_BDROWN);
@@ -906,7 +958,7 @@ static int bdrown_levels(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, 
       float* b = ctx->dr_x2.p;
       prof_begin(ctx, SOSIE_T_SMOOTH);
       for (int js = 0; js < nb_smooth; js++) {
-        k_sml_pass<<<grid, 256, 0, st>>>(g, a, b, ctx->dr_x.p, ctx->dr_R0.p, cnt, mask_per_slab, nslab, spb); KLAUNCH_CHECK();
+        k_sml_pass<<<grid, 256, 0, st>>>(g, dn, dni, a, b, ctx->dr_x.p, ctx->dr_R0.p, cnt, mask_per_slab, nslab, spb); KLAUNCH_CHECK();
         std::swap(a, b);
       }
       prof_end(ctx, SOSIE_T_SMOOTH);
