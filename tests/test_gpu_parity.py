@@ -340,3 +340,16 @@ def test_trajectory_mapping_and_interp_bl(gpu, orc, src):
     assert np.array_equal(out[::7], ref)
     found = mg["metrics"][0][:, 0] > 0
     assert found.mean() > 0.8          # most of the track lies inside the model domain
+
+
+def test_akima_config_E_shape(gpu, orc):
+    """the reference's own etopo_2_eNATL60 namelist interpolates with Akima (etopo_2_eNATL60.namelist:220): regular source,
+    rotated regional curvilinear target, k_ew = 0; the slopes are only needed under the target (needed map)."""
+    cfg = G.config("E", 0.02)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, 2, seed=14)
+    Xt, Yt = G.trg_2d(cfg)
+    Z2g = gpu.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt)
+    Z2o, ixy = orc.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt)
+    assert np.array_equal(gpu.akima_get_ixy(), ixy)
+    assert np.array_equal(Z2g, Z2o), f"{(Z2g != Z2o).sum()} points differ, max {np.abs(Z2g - Z2o).max()}"
