@@ -222,6 +222,13 @@ int sosie_interp3d_post_dev(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk, 
                             int32_t ixtrpl_bot, float vmin, float vmax, float rmiss_val, int32_t i_orca_trg,
                             int32_t c_orca_trg, int32_t lmout);
 
+/* extrp_hl(X2d), src/mod_interp.f90:521-542: on a regular target the rows from jj_ex_top to the top and
+ * from the bottom to jj_ex_btm (mod_conf globals, 0 = none; nlat_icr_trg = +1 / -1) take the last interpolated row.   */
+int sosie_extrp_hl(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nslab, float* X, int32_t jj_ex_top, int32_t jj_ex_btm,
+                   int32_t nlat_icr_trg);
+int sosie_extrp_hl_dev(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nslab, float* dX, int32_t jj_ex_top,
+                       int32_t jj_ex_btm, int32_t nlat_icr_trg);
+
 /* ---- raw-binary twin of the mapping file (layout documented in csrc/mapfile.cu) ---------------------
  * Same variables, order, types and layout as the NetCDF file written by P2D_MAPPING_AB (src/io_ezcdf.f90:2195) and read
  * by RD_MAPPING_AB (:2280).  Host-side file I/O only (no context).  Return 0 or SOSIE_ERR_ARG (cannot open / bad file). */

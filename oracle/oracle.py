@@ -318,3 +318,14 @@ def interp3d_post(X, mask_trg=None, ixtrpl_bot=0, vmin=-1.0e30, vmax=1.0e30, rmi
     lib().orc_interp3d_post(ni, nj, nk, _p(X, C.c_float), _p(m, C.c_int32), int(ixtrpl_bot), C.c_float(vmin), C.c_float(vmax),
                             C.c_float(rmiss_val), int(i_orca_trg), ord(c_orca_trg), int(lmout))
     return X
+
+
+def extrp_hl(X, jj_ex_top, jj_ex_btm, nlat_icr_trg=1):
+    """extrp_hl, src/mod_interp.f90:521-542: X (nslab, nj, ni) or (nj, ni)"""
+    X = _f32(X).copy()
+    sq = X.ndim == 2
+    if sq:
+        X = X[None]
+    nslab, nj, ni = X.shape
+    lib().orc_extrp_hl(ni, nj, nslab, _p(X, C.c_float), int(jj_ex_top), int(jj_ex_btm), int(nlat_icr_trg))
+    return X[0] if sq else X

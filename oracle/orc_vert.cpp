@@ -316,4 +316,22 @@ void orc_interp3d_post(int ni, int nj, int nk, float* X, const int32_t* mask_trg
   }
 }
 
+// extrp_hl (src/mod_interp.f90:521-542): persistence of the last valid row towards the top / bottom of a regular target
+void orc_extrp_hl(int ni, int nj, int nslab, float* X, int jj_ex_top, int jj_ex_btm, int nlat_icr_trg) {
+  const int icr = nlat_icr_trg;
+  for (int s = 0; s < nslab; s++) {
+    orc::A2<float> X2d(X + (size_t)s * ni * nj, ni, nj);
+    if (jj_ex_top > 0) {
+      const int jend = (icr + 1) / 2 * nj + (1 - icr) / 2;
+      for (int jj = jj_ex_top; (icr > 0) ? (jj <= jend) : (jj >= jend); jj += icr)
+        for (int i = 1; i <= ni; i++) X2d(i, jj) = X2d(i, jj_ex_top - icr);
+    }
+    if (jj_ex_btm > 0) {
+      const int jbeg = (icr + 1) / 2 + (1 - icr) / 2 * nj;
+      for (int jj = jbeg; (icr > 0) ? (jj <= jj_ex_btm) : (jj >= jj_ex_btm); jj += icr)
+        for (int i = 1; i <= ni; i++) X2d(i, jj) = X2d(i, jj_ex_btm + icr);
+    }
+  }
+}
+
 }  // extern "C"

@@ -42,6 +42,7 @@ EXPORTS = [
     "sosie_host_register", "sosie_host_unregister", "sosie_bilin_src_rows",
     "sosie_akima_1d_3d", "sosie_akima_1d_3d_dev", "sosie_lbc_lnk", "sosie_lbc_lnk_dev", "sosie_interp3d_post", "sosie_interp3d_post_dev",
     "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
+    "sosie_extrp_hl", "sosie_extrp_hl_dev",
 ]
 
 _lib = None
@@ -434,6 +435,16 @@ class Sosie:
         self._ck(self._lib.sosie_interp3d_post(self._h, ni, nj, nk, _p(X), _p(m), int(ixtrpl_bot), C.c_float(vmin), C.c_float(vmax),
                                                C.c_float(rmiss_val), int(i_orca_trg), ord(c_orca_trg), int(lmout)))
         return X
+
+    def extrp_hl(self, X, jj_ex_top, jj_ex_btm, nlat_icr_trg=1):
+        """extrp_hl, src/mod_interp.f90:521-542, on slabs X (nslab, nj, ni) or (nj, ni)"""
+        X = _f32(X).copy()
+        sq = X.ndim == 2
+        if sq:
+            X = X[None]
+        nslab, nj, ni = X.shape
+        self._ck(self._lib.sosie_extrp_hl(self._h, ni, nj, nslab, _p(X), int(jj_ex_top), int(jj_ex_btm), int(nlat_icr_trg)))
+        return X[0] if sq else X
 
     def interp3d_post_dev(self, ni, nj, nk, dX, dmask_trg, ixtrpl_bot, vmin, vmax, rmiss_val, i_orca_trg, c_orca_trg, lmout):
         self._ck(self._lib.sosie_interp3d_post_dev(self._h, int(ni), int(nj), int(nk), _dp(dX), _dp(dmask_trg), int(ixtrpl_bot), C.c_float(vmin),

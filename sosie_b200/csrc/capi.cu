@@ -593,6 +593,24 @@ int sosie_interp3d_post(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk, float*
   return SOSIE_OK;
 }
 
+int sosie_extrp_hl_dev(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nslab, float* dX, int32_t jj_ex_top, int32_t jj_ex_btm, int32_t nlat_icr_trg) {
+  NEED(c);
+  return extrp_hl_impl(ctx, ni, nj, nslab, dX, jj_ex_top, jj_ex_btm, nlat_icr_trg);
+}
+
+int sosie_extrp_hl(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nslab, float* X, int32_t jj_ex_top, int32_t jj_ex_btm, int32_t nlat_icr_trg) {
+  NEED(c);
+  if (ni < 1 || nj < 2 || nslab < 1 || !X) { ctx->err = "sosie_extrp_hl: bad arguments"; return SOSIE_ERR_ARG; }
+  const size_t tot = (size_t)ni * nj * nslab;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->v_in.alloc(tot));
+  CK(cudaMemcpyAsync(ctx->v_in.p, X, tot * sizeof(float), cudaMemcpyHostToDevice, st));
+  if (int rc = extrp_hl_impl(ctx, ni, nj, nslab, ctx->v_in.p, jj_ex_top, jj_ex_btm, nlat_icr_trg)) return rc;
+  CK(cudaMemcpyAsync(X, ctx->v_in.p, tot * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
 int sosie_rotate_uv_dev(sosie_ctx* c, int64_t n, int32_t nslab, const float* dU, const float* dV, const double* dxcos,
                         const double* dxsin, float* dUo, float* dVo, int32_t inverse) {
   NEED(c);

@@ -315,3 +315,36 @@ int interp3d_post_impl(sosie_ctx* ctx, int ni, int nj, int nk, float* dX, const 
   if (lmout) { k_i3d_mask<<<grid_for(ctx, n * nk, 256, 8), 256, 0, ctx->stream>>>(dX, dmask_trg, n * nk, rmiss_val); KLAUNCH_CHECK(); }
   return SOSIE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// extrp_hl (src/mod_interp.f90:521-542): rows beyond the source's latitude range of a regular target take the last
+// interpolated row (persistence).  The source rows (jj_ex_top - icr, jj_ex_btm + icr) are never written themselves.
+__global__ void k_extrp_hl(float* Xb, int ni, int nj, int jj_ex_top, int jj_ex_btm, int icr) {
+  float* X = Xb + (size_t)blockIdx.y * ni * nj;
+  const size_t n = (size_t)ni * nj;
+  const int jend = (icr + 1) / 2 * nj + (1 - icr) / 2, jbeg = (icr + 1) / 2 + (1 - icr) / 2 * nj;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const int jj = (int)(k / ni) + 1, i = (int)(k % ni);
+    // the two loops of the reference run one after the other: a row in both ranges ends with the bottom source row
+    int src = 0;
+    if (jj_ex_top > 0 && ((icr > 0) ? (jj >= jj_ex_top && jj <= jend) : (jj <= jj_ex_top && jj >= jend))) src = jj_ex_top - icr;
+    if (jj_ex_btm > 0 && ((icr > 0) ? (jj >= jbeg && jj <= jj_ex_btm) : (jj <= jbeg && jj >= jj_ex_btm))) src = -(jj_ex_btm + icr);
+    if (src > 0) X[k] = X[(size_t)i + (size_t)(src - 1) * ni];
+    else if (src < 0) X[k] = X[(size_t)i + (size_t)(-src - 1) * ni];
+  }
+}
+
+int extrp_hl_impl(sosie_ctx* ctx, int ni, int nj, int nslab, float* dX, int jj_ex_top, int jj_ex_btm, int nlat_icr_trg) {
+  if (ni < 1 || nj < 2 || nslab < 1 || !dX || (nlat_icr_trg != 1 && nlat_icr_trg != -1)) { ctx->err = "sosie_extrp_hl: bad arguments"; return SOSIE_ERR_ARG; }
+  const int icr = nlat_icr_trg;
+  // source rows must exist and must not be rewritten by the other loop (then the reference reads an already replaced row)
+  const int st = jj_ex_top > 0 ? jj_ex_top - icr : 0, sb = jj_ex_btm > 0 ? jj_ex_btm + icr : 0;
+  if ((jj_ex_top > 0 && (st < 1 || st > nj || jj_ex_top > nj)) || (jj_ex_btm > 0 && (sb < 1 || sb > nj || jj_ex_btm > nj)) ||
+      (jj_ex_top > 0 && jj_ex_btm > 0 && ((icr > 0) ? (jj_ex_btm >= jj_ex_top - 1) : (jj_ex_btm <= jj_ex_top + 1)))) {
+    ctx->err = "sosie_extrp_hl: jj_ex_top / jj_ex_btm out of range or overlapping"; return SOSIE_ERR_ARG;
+  }
+  if (jj_ex_top <= 0 && jj_ex_btm <= 0) return SOSIE_OK;
+  k_extrp_hl<<<dim3(grid_for(ctx, (size_t)ni * nj, 256, 4), nslab), 256, 0, ctx->stream>>>(dX, ni, nj, jj_ex_top, jj_ex_btm, icr);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
+}

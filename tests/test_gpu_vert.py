@@ -109,3 +109,14 @@ def test_3d_job_on_device(gpu, orc):
     gpu.sync()
     out = dV.cpu().numpy()
     assert np.array_equal(out.view(np.uint32), R.view(np.uint32)), (out != R).sum()
+
+
+def test_extrp_hl_vs_oracle(gpu, orc):
+    rng = np.random.default_rng(4)
+    X = rng.normal(size=(3, 40, 25)).astype(np.float32)
+    for top, btm, icr in ((33, 6, 1), (0, 4, 1), (37, 0, 1), (8, 31, -1), (0, 0, 1)):
+        a = gpu.extrp_hl(X, top, btm, icr)
+        b = orc.extrp_hl(X, top, btm, icr)
+        assert np.array_equal(a, b), (top, btm, icr)
+    a = orc.extrp_hl(X, 33, 6, 1)
+    assert np.array_equal(a[:, 32:], np.broadcast_to(X[:, 31:32], a[:, 32:].shape)) and np.array_equal(a[:, :6], np.broadcast_to(X[:, 6:7], a[:, :6].shape))
