@@ -990,7 +990,7 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
     CK(ctx->dr_cnt.alloc(nslab));
     static bool attr_set = false;
     if (!attr_set) { CK(cudaFuncSetAttribute(k_bdrown_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
-    int grid = nslab < ctx->num_sms ? nslab : ctx->num_sms;
+    int grid = nslab;   // one CTA per slab, dispatched as SMs free up: slabs differ in land fraction (work), a static stride left SMs idle
     prof_begin(ctx, SOSIE_T_BDROWN);
     k_bdrown_smem<<<grid, BDS_THREADS, smem_need, st>>>(g, dX, dmask, mask_per_slab, nslab, nb_inc, nb_smooth, pmin, pmax, pval_land, ctx->dr_cnt.p);
     KLAUNCH_CHECK();
