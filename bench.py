@@ -173,6 +173,7 @@ def workload_name(cfg):
 # ------------------------------------------------------------------------------------------------
 def bench_others(ctx, torch, dev, hbm_peak, quick=False):
     """Kernel-level numbers of the other BASELINE configs at N=1 (device-resident inputs, CUDA events)."""
+    import sosie_b200
     out = {}
 
     def timed(fn, reps=3, warm=1):
@@ -213,6 +214,28 @@ def bench_others(ctx, torch, dev, hbm_peak, quick=False):
                     "achieved_gbs": algo / (t_apply * 1e-3) / 1e9, "frac_hbm": algo / (t_apply * 1e-3) / 1e9 / hbm_peak,
                     "map_plus_apply_points_per_s": S * nt / ((t_map + t_apply) * 1e-3)}
         del Z1, Z2
+        if not quick:
+            # the same apply through the host-pointer entry (what the unchanged record loop calls): pinned host slabs,
+            # double-buffered chunks on three streams, only the source rows in use go up
+            import ctypes as C
+            Sh = 146
+            Z1h = torch.empty((Sh, cfg["nys"], cfg["nxs"]), dtype=torch.float32).pin_memory()
+            Z1h.copy_(torch.rand((Sh, cfg["nys"], cfg["nxs"])) * 80 + 230)
+            Z2h = torch.empty((Sh, cfg["nyt"], cfg["nxt"]), dtype=torch.float32).pin_memory()
+            lib = sosie_b200.load_library()
+
+            def host_apply():
+                ctx._ck(lib.sosie_bilin_apply(ctx._h, Sh, C.c_void_p(Z1h.data_ptr()), C.c_void_p(Z2h.data_ptr()), 0))
+            host_apply()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                host_apply()
+            th = (time.perf_counter() - t0) / 3
+            r = ctx.src_rows()
+            up = Sh * 4 * cfg["nxs"] * (r[1] - r[0] + 1)
+            out["D"]["e2e_host_apply"] = {"records": Sh, "ms": th * 1e3, "points_per_s": Sh * nt / th, "h2d_bytes": up, "d2h_bytes": Sh * 4 * nt,
+                                          "h2d_gbs": up / th / 1e9, "source_rows_uploaded": [r[0] + 1, r[1] + 1, cfg["nys"]]}
+            del Z1h, Z2h
     except Exception as e:  # noqa: BLE001
         out["D"] = {"error": repr(e)}
     torch.cuda.empty_cache()

@@ -1002,7 +1002,10 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
     return SOSIE_OK;
   }
   if (n > 2147483647ULL) { ctx->err = "sosie_bdrown: slab too large"; return SOSIE_ERR_ARG; }
-  if (ctx->force_general_bdrown != 2 && n * nmask < 4000000000ULL && nb_inc <= 250)
+  // a stack this small is launch bound either way: the dense path needs nb_inc + nb_smooth launches, the level lists twice
+  // nb_inc + nb_smooth and one read-back
+  const bool tiny = n * (size_t)nslab < ((size_t)1 << 18);
+  if (ctx->force_general_bdrown != 2 && !(tiny && ctx->force_general_bdrown == 0) && n * nmask < 4000000000ULL && nb_inc <= 250)
     return bdrown_levels(ctx, g, nslab, dX, dmask, mask_per_slab, nb_inc, nb_smooth, pmin, pmax, pval_land, nsweeps_host);
   // ---- legacy dense path: one whole-array kernel per sweep (kept for slabs stacks beyond 32-bit list indices, and as
   // an independent implementation the tests compare with)
