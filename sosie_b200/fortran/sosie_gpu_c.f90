@@ -123,6 +123,38 @@ MODULE SOSIE_GPU_C
          REAL(C_FLOAT)         :: X(*)
          INTEGER(C_SIGNED_CHAR), INTENT(in) :: mask(*)
       END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_akima_1d_3d(ctx, nx, ny, nk1, vz1, xf1, nk2, vz2, xf2, rfill_val) BIND(C, name='sosie_akima_1d_3d')
+         !! AKIMA_1D_3D (src/mod_akima_1d.f90:243): the z -> z vertical interpolation of INTERP_3D (src/mod_interp.f90:366)
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: nx, ny, nk1, nk2
+         REAL(C_FLOAT), INTENT(in)  :: vz1(*), xf1(*), vz2(*)
+         REAL(C_FLOAT), INTENT(out) :: xf2(*)
+         REAL(C_FLOAT), VALUE  :: rfill_val
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_lbc_lnk(ctx, nperio, jpi, jpj, nslab, X, cd_type, psgn, has_pval, pval) BIND(C, name='sosie_lbc_lnk')
+         !! lbc_lnk (src/mod_nemotools.f90:65) on nslab REAL(4) slabs; cd_type = ICHAR('T'), ...
+         IMPORT :: C_PTR, C_INT, C_FLOAT, C_DOUBLE
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: nperio, jpi, jpj, nslab, cd_type, has_pval
+         REAL(C_FLOAT)         :: X(*)
+         REAL(C_DOUBLE), VALUE :: psgn, pval
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_interp3d_post(ctx, ni, nj, nk, X, mask_trg, ixtrpl_bot, vmin, vmax, rmiss_val, i_orca_trg, &
+         &                                        c_orca_trg, lmout) BIND(C, name='sosie_interp3d_post')
+         !! post-interpolation block of INTERP_3D (src/mod_interp.f90:447-511); mask_trg: C_NULL_PTR or c_loc(INTEGER(4) (ni,nj,nk))
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx, mask_trg
+         INTEGER(C_INT), VALUE :: ni, nj, nk, ixtrpl_bot, i_orca_trg, c_orca_trg, lmout
+         REAL(C_FLOAT)         :: X(*)
+         REAL(C_FLOAT), VALUE  :: vmin, vmax, rmiss_val
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_extrp_hl(ctx, ni, nj, nslab, X, jj_ex_top, jj_ex_btm, nlat_icr_trg) BIND(C, name='sosie_extrp_hl')
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: ni, nj, nslab, jj_ex_top, jj_ex_btm, nlat_icr_trg
+         REAL(C_FLOAT)         :: X(*)
+      END FUNCTION
       INTEGER(C_INT) FUNCTION sosie_rotate_uv(ctx, n, nslab, U, V, xcos, xsin, Uo, Vo, inverse) BIND(C, name='sosie_rotate_uv')
          IMPORT :: C_PTR, C_INT, C_FLOAT, C_DOUBLE, C_INT64_T
          TYPE(C_PTR), VALUE        :: ctx
