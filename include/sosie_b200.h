@@ -222,6 +222,18 @@ int sosie_interp3d_post_dev(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk, 
                             int32_t ixtrpl_bot, float vmin, float vmax, float rmiss_val, int32_t i_orca_trg,
                             int32_t c_orca_trg, int32_t lmout);
 
+/* ANGLE2(nperio, plamt, pphit, plamu, pphiu, plamv, pphiv, plamf, pphif, gcost, gsint, ..., gcosf, gsinf),
+ * src/mod_nemotools.f90:607-823: the rotation coefficients corr_vect feeds to the rotation
+ * (src/corr_vect.f90:553-560).  All arrays REAL(8) (nx,ny).  nperio > 0: NEMO grid (lbc_lnk with psgn = -1), 0: Akima
+ * extrapolation of the edges.  _dev: dcoords = the 8 coordinate arrays one after the other (lamt, phit, lamu, phiu, lamv,
+ * phiv, lamf, phif), dangles = the 8 results in the reference's argument order.  Cells the reference leaves unassigned
+ * are 0.                                                                                                            */
+int sosie_angle2(sosie_ctx* ctx, int32_t nperio, int32_t nx, int32_t ny, const double* plamt, const double* pphit,
+                 const double* plamu, const double* pphiu, const double* plamv, const double* pphiv, const double* plamf,
+                 const double* pphif, double* gcost, double* gsint, double* gcosu, double* gsinu, double* gcosv,
+                 double* gsinv, double* gcosf, double* gsinf);
+int sosie_angle2_dev(sosie_ctx* ctx, int32_t nperio, int32_t nx, int32_t ny, const double* dcoords, double* dangles);
+
 /* extrp_hl(X2d), src/mod_interp.f90:521-542: on a regular target the rows from jj_ex_top to the top and
  * from the bottom to jj_ex_btm (mod_conf globals, 0 = none; nlat_icr_trg = +1 / -1) take the last interpolated row.   */
 int sosie_extrp_hl(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nslab, float* X, int32_t jj_ex_top, int32_t jj_ex_btm,

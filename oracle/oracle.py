@@ -329,3 +329,12 @@ def extrp_hl(X, jj_ex_top, jj_ex_btm, nlat_icr_trg=1):
     nslab, nj, ni = X.shape
     lib().orc_extrp_hl(ni, nj, nslab, _p(X, C.c_float), int(jj_ex_top), int(jj_ex_btm), int(nlat_icr_trg))
     return X[0] if sq else X
+
+
+def angle2(nperio, lamt, phit, lamu, phiu, lamv, phiv, lamf, phif):
+    """angle2, src/mod_nemotools.f90:607-823: returns (cost, sint, cosu, sinu, cosv, sinv, cosf, sinf), each (ny, nx) f64"""
+    ins = [_f64(a) for a in (lamt, phit, lamu, phiu, lamv, phiv, lamf, phif)]
+    ny, nx = ins[0].shape
+    outs = [np.empty((ny, nx), np.float64) for _ in range(8)]
+    lib().orc_angle2(int(nperio), nx, ny, *[_p(a, C.c_double) for a in ins], *[_p(a, C.c_double) for a in outs])
+    return tuple(outs)

@@ -275,6 +275,113 @@ static void lbc_lnk_2d_r4(int nperio, float* X, int jpi, int jpj, char cd_type, 
   for (size_t k = 0; k < w.size(); k++) X[k] = (float)w[k];
 }
 
+// extra_1_east_r8 / extra_1_west_r8 (src/mod_manip.f90:465-525)
+static inline double extra_1(double xa, double xb, double xc, double xd, double ya, double yb, double yc) {
+  const double A = xb - xa, B = xc - xb, C = xd - xc;
+  const double ALF = yb - ya, BET = yc - yb;
+  if ((A == 0.) || (B == 0.) || (C == 0.)) return yc;
+  return C * (2 * BET / B - ALF / A) + yc;
+}
+
+// angle2 (src/mod_nemotools.f90:607-823).  rpi = 3.141592653 is a default-REAL literal (Q1) -> 3.1415927410125732.
+// Cells the reference leaves unassigned (allocated, never written: column 1 before the boundary treatment, the south
+// row of the F arrays on a folded grid) are DEFINED as 0.
+static void angle2(int nperio, int nx, int ny, const double* plamt, const double* pphit, const double* plamu, const double* pphiu,
+                   const double* plamv, const double* pphiv, const double* plamf, const double* pphif, double* gcost, double* gsint,
+                   double* gcosu, double* gsinu, double* gcosv, double* gsinv, double* gcosf, double* gsinf) {
+  const double rpi = (double)3.141592653f, rad = rpi / (double)180.0f;
+  const size_t n = (size_t)nx * ny;
+  double* outs[8] = {gcost, gsint, gcosu, gsinu, gcosv, gsinv, gcosf, gsinf};
+  for (auto* o : outs) std::fill(o, o + n, 0.0);
+  A2<const double> LT(plamt, nx, ny), PT(pphit, nx, ny), LU(plamu, nx, ny), PU(pphiu, nx, ny), LV(plamv, nx, ny), PV(pphiv, nx, ny),
+      LF(plamf, nx, ny), PF(pphif, nx, ny);
+  A2<double> CT(gcost, nx, ny), ST(gsint, nx, ny), CU(gcosu, nx, ny), SU(gsinu, nx, ny), CV(gcosv, nx, ny), SV(gsinv, nx, ny),
+      CF(gcosf, nx, ny), SF(gsinf, nx, ny);
+  double mx = plamt[0], mn = plamt[0];
+  for (size_t k = 1; k < n; k++) { mx = std::max(mx, plamt[k]); mn = std::min(mn, plamt[k]); }
+  const bool l_cut_180 = (mx <= 180.) && (mx > 175.) && (mn >= -180.) && (mn < -175.);
+  auto T = [&](double zphi) { return m_tan(rpi / 4. - rad * zphi / 2.); };
+  for (int jj = 2; jj <= ny - 1; jj++) {
+    for (int ji = 2; ji <= nx; ji++) {
+      double zlamt = LT(ji, jj), zlamu = LU(ji, jj), zlamv = LV(ji, jj), zlamf = LF(ji, jj);
+      double zlamvjm1 = LV(ji, jj - 1), zlamfjm1 = LF(ji, jj - 1), zlamfim1 = LF(ji - 1, jj), zlamujp1 = LU(ji, jj + 1);
+      if (l_cut_180) {
+        if ((std::fabs(zlamt) > 170.) || (std::fabs(zlamu) > 170.) || (std::fabs(zlamv) > 170.) || (std::fabs(zlamf) > 170.)) {
+          zlamt = f_mod(360. + LT(ji, jj), 360.); zlamu = f_mod(360. + LU(ji, jj), 360.);
+          zlamv = f_mod(360. + LV(ji, jj), 360.); zlamf = f_mod(360. + LF(ji, jj), 360.);
+          zlamvjm1 = f_mod(360. + LV(ji, jj - 1), 360.); zlamfjm1 = f_mod(360. + LF(ji, jj - 1), 360.);
+          zlamfim1 = f_mod(360. + LF(ji - 1, jj), 360.); zlamujp1 = f_mod(360. + LU(ji, jj + 1), 360.);
+        }
+      }
+      double zphi = PT(ji, jj);
+      const double zxnpt = 0. - 2. * m_cos(rad * zlamt) * T(zphi), zynpt = 0. - 2. * m_sin(rad * zlamt) * T(zphi);
+      const double znnpt = zxnpt * zxnpt + zynpt * zynpt;
+      zphi = PU(ji, jj);
+      const double zxnpu = 0. - 2. * m_cos(rad * zlamu) * T(zphi), zynpu = 0. - 2. * m_sin(rad * zlamu) * T(zphi);
+      const double znnpu = zxnpu * zxnpu + zynpu * zynpu;
+      zphi = PV(ji, jj);
+      const double zxnpv = 0. - 2. * m_cos(rad * zlamv) * T(zphi), zynpv = 0. - 2. * m_sin(rad * zlamv) * T(zphi);
+      const double znnpv = zxnpv * zxnpv + zynpv * zynpv;
+      zphi = PF(ji, jj);
+      const double zxnpf = 0. - 2. * m_cos(rad * zlamf) * T(zphi), zynpf = 0. - 2. * m_sin(rad * zlamf) * T(zphi);
+      const double znnpf = zxnpf * zxnpf + zynpf * zynpf;
+      zphi = PV(ji, jj); double zphh = PV(ji, jj - 1);
+      const double zxvvt = 2. * m_cos(rad * zlamv) * T(zphi) - 2. * m_cos(rad * zlamvjm1) * T(zphh);
+      const double zyvvt = 2. * m_sin(rad * zlamv) * T(zphi) - 2. * m_sin(rad * zlamvjm1) * T(zphh);
+      double znvvt = std::sqrt(znnpt * (zxvvt * zxvvt + zyvvt * zyvvt));
+      znvvt = std::max(znvvt, (double)1.e-14f);
+      zphi = PF(ji, jj); zphh = PF(ji, jj - 1);
+      const double zxffu = 2. * m_cos(rad * zlamf) * T(zphi) - 2. * m_cos(rad * zlamfjm1) * T(zphh);
+      const double zyffu = 2. * m_sin(rad * zlamf) * T(zphi) - 2. * m_sin(rad * zlamfjm1) * T(zphh);
+      double znffu = std::sqrt(znnpu * (zxffu * zxffu + zyffu * zyffu));
+      znffu = std::max(znffu, (double)1.e-14f);
+      zphi = PF(ji, jj); zphh = PF(ji - 1, jj);
+      const double zxffv = 2. * m_cos(rad * zlamf) * T(zphi) - 2. * m_cos(rad * zlamfim1) * T(zphh);
+      const double zyffv = 2. * m_sin(rad * zlamf) * T(zphi) - 2. * m_sin(rad * zlamfim1) * T(zphh);
+      double znffv = std::sqrt(znnpv * (zxffv * zxffv + zyffv * zyffv));
+      znffv = std::max(znffv, (double)1.e-14f);
+      zphi = PU(ji, jj + 1); zphh = PU(ji, jj);
+      const double zxuuf = 2. * m_cos(rad * zlamujp1) * T(zphi) - 2. * m_cos(rad * zlamu) * T(zphh);
+      const double zyuuf = 2. * m_sin(rad * zlamujp1) * T(zphi) - 2. * m_sin(rad * zlamu) * T(zphh);
+      double znuuf = std::sqrt(znnpf * (zxuuf * zxuuf + zyuuf * zyuuf));
+      znuuf = std::max(znuuf, (double)1.e-14f);
+      ST(ji, jj) = (zxnpt * zyvvt - zynpt * zxvvt) / znvvt;
+      CT(ji, jj) = (zxnpt * zxvvt + zynpt * zyvvt) / znvvt;
+      SU(ji, jj) = (zxnpu * zyffu - zynpu * zxffu) / znffu;
+      CU(ji, jj) = (zxnpu * zxffu + zynpu * zyffu) / znffu;
+      SF(ji, jj) = (zxnpf * zyuuf - zynpf * zxuuf) / znuuf;
+      CF(ji, jj) = (zxnpf * zxuuf + zynpf * zyuuf) / znuuf;
+      SV(ji, jj) = (zxnpv * zxffv + zynpv * zyffv) / znffv;
+      CV(ji, jj) = -(zxnpv * zyffv - zynpv * zxffv) / znffv;
+    }
+  }
+  if (nperio > 0) {
+    lbc_lnk_2d_r8(nperio, CT, 'T', -1.0, false, 0.0); lbc_lnk_2d_r8(nperio, ST, 'T', -1.0, false, 0.0);
+    lbc_lnk_2d_r8(nperio, CU, 'U', -1.0, false, 0.0); lbc_lnk_2d_r8(nperio, SU, 'U', -1.0, false, 0.0);
+    lbc_lnk_2d_r8(nperio, CV, 'V', -1.0, false, 0.0); lbc_lnk_2d_r8(nperio, SV, 'V', -1.0, false, 0.0);
+    lbc_lnk_2d_r8(nperio, CF, 'F', -1.0, false, 0.0); lbc_lnk_2d_r8(nperio, SF, 'F', -1.0, false, 0.0);
+  } else {
+    A2<const double>* PH[4] = {&PT, &PU, &PV, &PF};
+    A2<const double>* LA[4] = {&LT, &LU, &LV, &LF};
+    A2<double>* G[8] = {&CT, &ST, &CU, &SU, &CV, &SV, &CF, &SF};
+    for (int ji = 1; ji <= nx; ji++)      // northernmost row
+      for (int q = 0; q < 8; q++) {
+        A2<const double>& P = *PH[q / 2]; A2<double>& g = *G[q];
+        g(ji, ny) = extra_1(P(ji, ny - 3), P(ji, ny - 2), P(ji, ny - 1), P(ji, ny), g(ji, ny - 3), g(ji, ny - 2), g(ji, ny - 1));
+      }
+    for (int ji = 1; ji <= nx; ji++)      // southernmost row
+      for (int q = 0; q < 8; q++) {
+        A2<const double>& P = *PH[q / 2]; A2<double>& g = *G[q];
+        g(ji, 1) = extra_1(P(ji, 4), P(ji, 3), P(ji, 2), P(ji, 1), g(ji, 4), g(ji, 3), g(ji, 2));
+      }
+    for (int jj = 1; jj <= ny; jj++)      // westernmost column
+      for (int q = 0; q < 8; q++) {
+        A2<const double>& L = *LA[q / 2]; A2<double>& g = *G[q];
+        g(1, jj) = extra_1(L(4, jj), L(3, jj), L(2, jj), L(1, jj), g(4, jj), g(3, jj), g(2, jj));
+      }
+  }
+}
+
 }  // namespace orc
 
 extern "C" {
@@ -314,6 +421,12 @@ void orc_interp3d_post(int ni, int nj, int nk, float* X, const int32_t* mask_trg
       for (int64_t p = 0; p < n; p++) Xk[p] = Xk[p] * (float)mk[p] + (1.f - (float)mk[p]) * rmiss_val;
     }
   }
+}
+
+void orc_angle2(int nperio, int nx, int ny, const double* plamt, const double* pphit, const double* plamu, const double* pphiu,
+                const double* plamv, const double* pphiv, const double* plamf, const double* pphif, double* gcost, double* gsint,
+                double* gcosu, double* gsinu, double* gcosv, double* gsinv, double* gcosf, double* gsinf) {
+  orc::angle2(nperio, nx, ny, plamt, pphit, plamu, pphiu, plamv, pphiv, plamf, pphif, gcost, gsint, gcosu, gsinu, gcosv, gsinv, gcosf, gsinf);
 }
 
 // extrp_hl (src/mod_interp.f90:521-542): persistence of the last valid row towards the top / bottom of a regular target

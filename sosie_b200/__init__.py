@@ -42,7 +42,7 @@ EXPORTS = [
     "sosie_host_register", "sosie_host_unregister", "sosie_bilin_src_rows",
     "sosie_akima_1d_3d", "sosie_akima_1d_3d_dev", "sosie_lbc_lnk", "sosie_lbc_lnk_dev", "sosie_interp3d_post", "sosie_interp3d_post_dev",
     "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
-    "sosie_extrp_hl", "sosie_extrp_hl_dev",
+    "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev",
 ]
 
 _lib = None
@@ -435,6 +435,14 @@ class Sosie:
         self._ck(self._lib.sosie_interp3d_post(self._h, ni, nj, nk, _p(X), _p(m), int(ixtrpl_bot), C.c_float(vmin), C.c_float(vmax),
                                                C.c_float(rmiss_val), int(i_orca_trg), ord(c_orca_trg), int(lmout)))
         return X
+
+    def angle2(self, nperio, lamt, phit, lamu, phiu, lamv, phiv, lamf, phif):
+        """ANGLE2, src/mod_nemotools.f90:607-823: (cost, sint, cosu, sinu, cosv, sinv, cosf, sinf), each (ny, nx) f64"""
+        ins = [_f64(a) for a in (lamt, phit, lamu, phiu, lamv, phiv, lamf, phif)]
+        ny, nx = ins[0].shape
+        outs = [np.empty((ny, nx), np.float64) for _ in range(8)]
+        self._ck(self._lib.sosie_angle2(self._h, int(nperio), nx, ny, *[_p(a) for a in ins], *[_p(a) for a in outs]))
+        return tuple(outs)
 
     def extrp_hl(self, X, jj_ex_top, jj_ex_btm, nlat_icr_trg=1):
         """extrp_hl, src/mod_interp.f90:521-542, on slabs X (nslab, nj, ni) or (nj, ni)"""

@@ -593,6 +593,29 @@ int sosie_interp3d_post(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk, float*
   return SOSIE_OK;
 }
 
+int sosie_angle2(sosie_ctx* c, int32_t nperio, int32_t nx, int32_t ny, const double* plamt, const double* pphit, const double* plamu,
+                 const double* pphiu, const double* plamv, const double* pphiv, const double* plamf, const double* pphif, double* gcost,
+                 double* gsint, double* gcosu, double* gsinu, double* gcosv, double* gsinv, double* gcosf, double* gsinf) {
+  NEED(c);
+  const double* in[8] = {plamt, pphit, plamu, pphiu, plamv, pphiv, plamf, pphif};
+  double* out[8] = {gcost, gsint, gcosu, gsinu, gcosv, gsinv, gcosf, gsinf};
+  for (int q = 0; q < 8; q++) if (!in[q] || !out[q]) { ctx->err = "sosie_angle2: null pointer"; return SOSIE_ERR_ARG; }
+  if (nx < 4 || ny < 5) { ctx->err = "sosie_angle2: bad extents"; return SOSIE_ERR_ARG; }
+  const size_t n = (size_t)nx * ny;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->v_ang.alloc(16 * n));
+  for (int q = 0; q < 8; q++) CK(cudaMemcpyAsync(ctx->v_ang.p + (size_t)q * n, in[q], n * sizeof(double), cudaMemcpyHostToDevice, st));
+  if (int rc = angle2_impl(ctx, nperio, nx, ny, ctx->v_ang.p, ctx->v_ang.p + 8 * n)) return rc;
+  for (int q = 0; q < 8; q++) CK(cudaMemcpyAsync(out[q], ctx->v_ang.p + (size_t)(8 + q) * n, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
+int sosie_angle2_dev(sosie_ctx* c, int32_t nperio, int32_t nx, int32_t ny, const double* dcoords, double* dangles) {
+  NEED(c);
+  return angle2_impl(ctx, nperio, nx, ny, dcoords, dangles);
+}
+
 int sosie_extrp_hl_dev(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nslab, float* dX, int32_t jj_ex_top, int32_t jj_ex_btm, int32_t nlat_icr_trg) {
   NEED(c);
   return extrp_hl_impl(ctx, ni, nj, nslab, dX, jj_ex_top, jj_ex_btm, nlat_icr_trg);

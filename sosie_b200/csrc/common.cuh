@@ -148,6 +148,7 @@ struct sosie_ctx {
 
   // ---- vertical stage (vert.cu)
   DBuf<float> v_vze, v_vz2, v_in, v_out;
+  DBuf<double> v_ang;
   DBuf<int32_t> v_plan, v_mask;
 
   // ---- drown work buffers
@@ -271,5 +272,6 @@ int lbc_lnk_impl(sosie_ctx* ctx, int nperio, int jpi, int jpj, int nslab, float*
 int interp3d_post_impl(sosie_ctx* ctx, int ni, int nj, int nk, float* dX, const int32_t* dmask_trg, int ixtrpl_bot, float vmin, float vmax,
                        float rmiss_val, int i_orca_trg, int c_orca_trg, int lmout);
 int extrp_hl_impl(sosie_ctx* ctx, int ni, int nj, int nslab, float* dX, int jj_ex_top, int jj_ex_btm, int nlat_icr_trg);
+int angle2_impl(sosie_ctx* ctx, int nperio, int nx, int ny, const double* din, double* dout);
 int rotate_impl(sosie_ctx* ctx, int64_t n, int nslab, const float* dU, const float* dV, const double* dcos,
                 const double* dsin, float* dUo, float* dVo, int inverse);

@@ -177,12 +177,15 @@ int akima_1d_3d_impl(sosie_ctx* ctx, int nx, int ny, int nk1, const float* vz1_h
 // parallel; loops that read and write the SAME row are replayed by one thread in the reference's index order (the
 // T-pivot U-point fold reads elements it has just overwritten).
 __device__ __forceinline__ float lbc_mul(double psgn, float x) { return (float)__dmul_rn(psgn, (double)x); }
+__device__ __forceinline__ double lbc_mul(double psgn, double x) { return __dmul_rn(psgn, x); }
 
+// T = float: lbc_lnk_2d_r4 (through REAL(8)); T = double: lbc_lnk_2d_r8.  slab_stride in elements.
+template <class T>
 __global__ void __launch_bounds__(1024)
-k_lbc_lnk(float* Xb, int jpi, int jpj, int nperio, int cd, double psgn, int has_pval, double pval) {
-  float* X = Xb + (size_t)blockIdx.x * jpi * jpj;
+k_lbc_lnk(T* Xb, size_t slab_stride, int jpi, int jpj, int nperio, int cd, double psgn, int has_pval, double pval) {
+  T* X = Xb + (size_t)blockIdx.x * slab_stride;
 #define P(i, j) X[(size_t)((i)-1) + (size_t)((j)-1) * jpi]
-  const float zland = has_pval ? (float)pval : 0.f;
+  const T zland = has_pval ? (T)pval : (T)0;
   const int t = threadIdx.x, nt = blockDim.x;
   const bool tuvw = (cd == 'T' || cd == 'U' || cd == 'V' || cd == 'W');
   // ---- East-West
@@ -271,7 +274,7 @@ int lbc_lnk_impl(sosie_ctx* ctx, int nperio, int jpi, int jpj, int nslab, float*
   if (fold && !(cd_type == 'T' || cd_type == 'W' || cd_type == 'U' || cd_type == 'V' || cd_type == 'F')) {
     ctx->err = "sosie_lbc_lnk: ice-point types (I, J, K) are not used by SOSIE and not implemented"; return SOSIE_ERR_ARG;
   }
-  k_lbc_lnk<<<nslab, 1024, 0, ctx->stream>>>(dX, jpi, jpj, nperio, cd_type, psgn, has_pval, pval);
+  k_lbc_lnk<float><<<nslab, 1024, 0, ctx->stream>>>(dX, (size_t)jpi * jpj, jpi, jpj, nperio, cd_type, psgn, has_pval, pval);
   KLAUNCH_CHECK();
   return SOSIE_OK;
 }
@@ -346,5 +349,118 @@ int extrp_hl_impl(sosie_ctx* ctx, int ni, int nj, int nslab, float* dX, int jj_e
   if (jj_ex_top <= 0 && jj_ex_btm <= 0) return SOSIE_OK;
   k_extrp_hl<<<dim3(grid_for(ctx, (size_t)ni * nj, 256, 4), nslab), 256, 0, ctx->stream>>>(dX, ni, nj, jj_ex_top, jj_ex_btm, icr);
   KLAUNCH_CHECK();
+  return SOSIE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// angle2 (src/mod_nemotools.f90:607-823): cos / sin of the angle between the grid lines and north at T, U, V, F points
+// (the XCOS_t, XSIN_t ... that corr_vect rotates with, src/corr_vect.f90:553-560).  One thread per point for the
+// interior, then lbc_lnk (psgn = -1) on a NEMO grid or the three Akima edge extrapolations otherwise.
+// rpi = 3.141592653 is a default-REAL literal in the reference (Q1).  Unassigned cells of the reference are DEFINED 0.
+#define A2_RPI ((double)3.141592653f)
+#define A2_RAD (A2_RPI / (double)180.0f)
+__device__ __forceinline__ double a2_tan(double zphi) { return pm_tan(A2_RPI / 4. - A2_RAD * zphi / 2.); }
+
+__global__ void __launch_bounds__(128)
+k_angle2(int nx, int ny, int l_cut_180, const double* __restrict__ plamt, const double* __restrict__ pphit,
+         const double* __restrict__ plamu, const double* __restrict__ pphiu, const double* __restrict__ plamv,
+         const double* __restrict__ pphiv, const double* __restrict__ plamf, const double* __restrict__ pphif, double* out) {
+  const size_t n = (size_t)nx * ny;
+  for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const int jj = (int)(k / nx) + 1, ji = (int)(k % nx) + 1;
+    double r[8] = {0., 0., 0., 0., 0., 0., 0., 0.};   // cost, sint, cosu, sinu, cosv, sinv, cosf, sinf
+    if (jj >= 2 && jj <= ny - 1 && ji >= 2) {
+      double zlamt = plamt[k], zlamu = plamu[k], zlamv = plamv[k], zlamf = plamf[k];
+      double zlamvjm1 = plamv[k - nx], zlamfjm1 = plamf[k - nx], zlamfim1 = plamf[k - 1], zlamujp1 = plamu[k + nx];
+      if (l_cut_180 && ((fabs(zlamt) > 170.) || (fabs(zlamu) > 170.) || (fabs(zlamv) > 170.) || (fabs(zlamf) > 170.))) {
+        zlamt = fmod(360. + zlamt, 360.); zlamu = fmod(360. + zlamu, 360.); zlamv = fmod(360. + zlamv, 360.); zlamf = fmod(360. + zlamf, 360.);
+        zlamvjm1 = fmod(360. + zlamvjm1, 360.); zlamfjm1 = fmod(360. + zlamfjm1, 360.);
+        zlamfim1 = fmod(360. + zlamfim1, 360.); zlamujp1 = fmod(360. + zlamujp1, 360.);
+      }
+      double st, ct, su, cu, sv, cv, sf, cf, sq, cq;
+      pm_sincos(A2_RAD * zlamt, &st, &ct); pm_sincos(A2_RAD * zlamu, &su, &cu);
+      pm_sincos(A2_RAD * zlamv, &sv, &cv); pm_sincos(A2_RAD * zlamf, &sf, &cf);
+      const double tt = a2_tan(pphit[k]), tu = a2_tan(pphiu[k]), tv = a2_tan(pphiv[k]), tf = a2_tan(pphif[k]);
+      const double zxnpt = 0. - 2. * ct * tt, zynpt = 0. - 2. * st * tt, znnpt = zxnpt * zxnpt + zynpt * zynpt;
+      const double zxnpu = 0. - 2. * cu * tu, zynpu = 0. - 2. * su * tu, znnpu = zxnpu * zxnpu + zynpu * zynpu;
+      const double zxnpv = 0. - 2. * cv * tv, zynpv = 0. - 2. * sv * tv, znnpv = zxnpv * zxnpv + zynpv * zynpv;
+      const double zxnpf = 0. - 2. * cf * tf, zynpf = 0. - 2. * sf * tf, znnpf = zxnpf * zxnpf + zynpf * zynpf;
+      double th;
+      th = a2_tan(pphiv[k - nx]); pm_sincos(A2_RAD * zlamvjm1, &sq, &cq);
+      const double zxvvt = 2. * cv * tv - 2. * cq * th, zyvvt = 2. * sv * tv - 2. * sq * th;
+      const double znvvt = fmax(sqrt(znnpt * (zxvvt * zxvvt + zyvvt * zyvvt)), (double)1.e-14f);
+      th = a2_tan(pphif[k - nx]); pm_sincos(A2_RAD * zlamfjm1, &sq, &cq);
+      const double zxffu = 2. * cf * tf - 2. * cq * th, zyffu = 2. * sf * tf - 2. * sq * th;
+      const double znffu = fmax(sqrt(znnpu * (zxffu * zxffu + zyffu * zyffu)), (double)1.e-14f);
+      th = a2_tan(pphif[k - 1]); pm_sincos(A2_RAD * zlamfim1, &sq, &cq);
+      const double zxffv = 2. * cf * tf - 2. * cq * th, zyffv = 2. * sf * tf - 2. * sq * th;
+      const double znffv = fmax(sqrt(znnpv * (zxffv * zxffv + zyffv * zyffv)), (double)1.e-14f);
+      th = a2_tan(pphiu[k + nx]); pm_sincos(A2_RAD * zlamujp1, &sq, &cq);
+      const double zxuuf = 2. * cq * th - 2. * cu * tu, zyuuf = 2. * sq * th - 2. * su * tu;
+      const double znuuf = fmax(sqrt(znnpf * (zxuuf * zxuuf + zyuuf * zyuuf)), (double)1.e-14f);
+      r[1] = (zxnpt * zyvvt - zynpt * zxvvt) / znvvt; r[0] = (zxnpt * zxvvt + zynpt * zyvvt) / znvvt;
+      r[3] = (zxnpu * zyffu - zynpu * zxffu) / znffu; r[2] = (zxnpu * zxffu + zynpu * zyffu) / znffu;
+      r[7] = (zxnpf * zyuuf - zynpf * zxuuf) / znuuf; r[6] = (zxnpf * zxuuf + zynpf * zyuuf) / znuuf;
+      r[5] = (zxnpv * zxffv + zynpv * zyffv) / znffv; r[4] = -(zxnpv * zyffv - zynpv * zxffv) / znffv;
+    }
+#pragma unroll
+    for (int q = 0; q < 8; q++) out[(size_t)q * n + k] = r[q];
+  }
+}
+
+__device__ __forceinline__ double a2_extra_1(double xa, double xb, double xc, double xd, double ya, double yb, double yc) {
+  const double A = xb - xa, B = xc - xb, C = xd - xc, ALF = yb - ya, BET = yc - yb;
+  if ((A == 0.) || (B == 0.) || (C == 0.)) return yc;
+  return C * (2 * BET / B - ALF / A) + yc;
+}
+// which = 0 northernmost row, 1 southernmost row, 2 westernmost column (in that order, :789-819)
+__global__ void k_angle2_edges(int nx, int ny, int which, const double* __restrict__ plamt, const double* __restrict__ pphit,
+                               const double* __restrict__ plamu, const double* __restrict__ pphiu, const double* __restrict__ plamv,
+                               const double* __restrict__ pphiv, const double* __restrict__ plamf, const double* __restrict__ pphif,
+                               double* out) {
+  const size_t n = (size_t)nx * ny;
+  const double* PH[4] = {pphit, pphiu, pphiv, pphif};
+  const double* LA[4] = {plamt, plamu, plamv, plamf};
+  const int len = (which == 2) ? ny : nx;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < len * 8; t += gridDim.x * blockDim.x) {
+    const int q = t / len, e = t % len + 1;
+    double* g = out + (size_t)q * n;
+#define GI(i, j) g[(size_t)((i)-1) + (size_t)((j)-1) * nx]
+#define CI(A_, i, j) A_[(size_t)((i)-1) + (size_t)((j)-1) * nx]
+    if (which == 0) { const double* P = PH[q / 2]; GI(e, ny) = a2_extra_1(CI(P, e, ny - 3), CI(P, e, ny - 2), CI(P, e, ny - 1), CI(P, e, ny), GI(e, ny - 3), GI(e, ny - 2), GI(e, ny - 1)); }
+    else if (which == 1) { const double* P = PH[q / 2]; GI(e, 1) = a2_extra_1(CI(P, e, 4), CI(P, e, 3), CI(P, e, 2), CI(P, e, 1), GI(e, 4), GI(e, 3), GI(e, 2)); }
+    else { const double* L = LA[q / 2]; GI(1, e) = a2_extra_1(CI(L, 4, e), CI(L, 3, e), CI(L, 2, e), CI(L, 1, e), GI(4, e), GI(3, e), GI(2, e)); }
+#undef GI
+#undef CI
+  }
+}
+
+// din: 8 coordinate arrays (lamt, phit, lamu, phiu, lamv, phiv, lamf, phif), each (nx,ny), contiguous one after the other
+// dout: the 8 results in the reference's argument order (cost, sint, cosu, sinu, cosv, sinv, cosf, sinf)
+int angle2_impl(sosie_ctx* ctx, int nperio, int nx, int ny, const double* din, double* dout) {
+  if (nx < 4 || ny < 5 || !din || !dout) { ctx->err = "sosie_angle2: bad arguments"; return SOSIE_ERR_ARG; }
+  cudaStream_t st = ctx->stream;
+  const size_t n = (size_t)nx * ny;
+  const double* a[8];
+  for (int q = 0; q < 8; q++) a[q] = din + (size_t)q * n;
+  // l_cut_180 (:661-662): MAXVAL / MINVAL of plamt
+  std::vector<double> hl(n);   // small grids only reach this routine (one horizontal grid); read back and reduce on the host
+  CK(cudaMemcpyAsync(hl.data(), a[0], n * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  double mx = hl[0], mn = hl[0];
+  for (size_t k = 1; k < n; k++) { mx = std::max(mx, hl[k]); mn = std::min(mn, hl[k]); }
+  const int l_cut_180 = ((mx <= 180.) && (mx > 175.) && (mn >= -180.) && (mn < -175.)) ? 1 : 0;
+  k_angle2<<<grid_for(ctx, n, 128, 8), 128, 0, st>>>(nx, ny, l_cut_180, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], dout); KLAUNCH_CHECK();
+  if (nperio > 0) {
+    static const char cd[4] = {'T', 'U', 'V', 'F'};
+    for (int q = 0; q < 4; q++) {   // cos and sin of one point type are adjacent: two slabs per launch
+      k_lbc_lnk<double><<<2, 1024, 0, st>>>(dout + (size_t)(2 * q) * n, n, nx, ny, nperio, cd[q], -1.0, 0, 0.0); KLAUNCH_CHECK();
+    }
+  } else {
+    for (int which = 0; which < 3; which++) {
+      const int len = (which == 2) ? ny : nx;
+      k_angle2_edges<<<cdiv((int64_t)len * 8, 128), 128, 0, st>>>(nx, ny, which, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], dout); KLAUNCH_CHECK();
+    }
+  }
   return SOSIE_OK;
 }

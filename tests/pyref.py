@@ -537,8 +537,12 @@ def akima_1d_3d_np(vz1, xf1, vz2, rfill_val):
 
 
 def lbc_lnk_py(nperio, X, cd_type, psgn, pval=None):
-    """lbc_lnk_2d_r8 + lbc_nfd_2d (src/mod_nemotools.f90:65-417) with explicit sequential Python loops on a float64 copy;
-    X (jpj, jpi) float32; returns float32."""
+    """lbc_lnk_2d_r4 (through REAL(8), src/mod_nemotools.f90:154-190): X (jpj, jpi) float32; returns float32."""
+    return _lbc_core(nperio, np.asarray(X, np.float64), cd_type, psgn, pval).astype(np.float32)
+
+
+def _lbc_core(nperio, X, cd_type, psgn, pval=None):
+    """lbc_lnk_2d_r8 + lbc_nfd_2d (src/mod_nemotools.f90:65-417) with explicit sequential Python loops; X (jpj, jpi) f64."""
     P = np.asarray(X, np.float64).T.copy()       # P[i-1, j-1]
     jpi, jpj = P.shape
     zland = 0.0 if pval is None else float(pval)
@@ -613,7 +617,7 @@ def lbc_lnk_py(nperio, X, cd_type, psgn, pval=None):
             P[:, 0] = zland; P[:, jpj - 1] = zland
         elif cd_type == "F":
             P[:, jpj - 1] = zland
-    return P.T.astype(np.float32)
+    return P.T.copy()
 
 
 def interp3d_post_np(X, mask, ixtrpl_bot, vmin, vmax, rmiss, i_orca_trg, c_orca_trg, lmout):
@@ -636,3 +640,64 @@ def interp3d_post_np(X, mask, ixtrpl_bot, vmin, vmax, rmiss, i_orca_trg, c_orca_
             m = mask[k].astype(f4)
             X[k] = X[k] * m + (f4(1.0) - m) * f4(rmiss)
     return X
+
+
+def angle2_np(nperio, lamt, phit, lamu, phiu, lamv, phiv, lamf, phif):
+    """angle2 (src/mod_nemotools.f90:607-823), vectorised numpy (numpy's own libm: compare with a tolerance)."""
+    f8 = np.float64
+    rpi = f8(np.float32(3.141592653)); rad = rpi / f8(180.0)
+    ny, nx = lamt.shape
+    outs = [np.zeros((ny, nx)) for _ in range(8)]
+    cut = (lamt.max() <= 180.) and (lamt.max() > 175.) and (lamt.min() >= -180.) and (lamt.min() < -175.)
+    J = slice(1, ny - 1); I = slice(1, nx)
+    Jm = slice(0, ny - 2); Jp = slice(2, ny); Im = slice(0, nx - 1)
+    zt, zu, zv, zf = lamt[J, I].copy(), lamu[J, I].copy(), lamv[J, I].copy(), lamf[J, I].copy()
+    zvjm1, zfjm1, zfim1, zujp1 = lamv[Jm, I].copy(), lamf[Jm, I].copy(), lamf[J, Im].copy(), lamu[Jp, I].copy()
+    if cut:
+        near = (np.abs(zt) > 170.) | (np.abs(zu) > 170.) | (np.abs(zv) > 170.) | (np.abs(zf) > 170.)
+        for a in (zt, zu, zv, zf, zvjm1, zfjm1, zfim1, zujp1):
+            a[near] = np.fmod(360. + a[near], 360.)
+    T = lambda ph: np.tan(rpi / 4. - rad * ph / 2.)
+    xn = lambda lam, ph: 0. - 2. * np.cos(rad * lam) * T(ph)
+    yn = lambda lam, ph: 0. - 2. * np.sin(rad * lam) * T(ph)
+    zxnpt, zynpt = xn(zt, phit[J, I]), yn(zt, phit[J, I]); znnpt = zxnpt ** 2 + zynpt ** 2
+    zxnpu, zynpu = xn(zu, phiu[J, I]), yn(zu, phiu[J, I]); znnpu = zxnpu ** 2 + zynpu ** 2
+    zxnpv, zynpv = xn(zv, phiv[J, I]), yn(zv, phiv[J, I]); znnpv = zxnpv ** 2 + zynpv ** 2
+    zxnpf, zynpf = xn(zf, phif[J, I]), yn(zf, phif[J, I]); znnpf = zxnpf ** 2 + zynpf ** 2
+    d = lambda la, pa, lb, pb, fn: 2. * fn(rad * la) * T(pa) - 2. * fn(rad * lb) * T(pb)
+    eps = f8(np.float32(1.e-14))
+    zxvvt, zyvvt = d(zv, phiv[J, I], zvjm1, phiv[Jm, I], np.cos), d(zv, phiv[J, I], zvjm1, phiv[Jm, I], np.sin)
+    znvvt = np.maximum(np.sqrt(znnpt * (zxvvt ** 2 + zyvvt ** 2)), eps)
+    zxffu, zyffu = d(zf, phif[J, I], zfjm1, phif[Jm, I], np.cos), d(zf, phif[J, I], zfjm1, phif[Jm, I], np.sin)
+    znffu = np.maximum(np.sqrt(znnpu * (zxffu ** 2 + zyffu ** 2)), eps)
+    zxffv, zyffv = d(zf, phif[J, I], zfim1, phif[J, Im], np.cos), d(zf, phif[J, I], zfim1, phif[J, Im], np.sin)
+    znffv = np.maximum(np.sqrt(znnpv * (zxffv ** 2 + zyffv ** 2)), eps)
+    zxuuf, zyuuf = d(zujp1, phiu[Jp, I], zu, phiu[J, I], np.cos), d(zujp1, phiu[Jp, I], zu, phiu[J, I], np.sin)
+    znuuf = np.maximum(np.sqrt(znnpf * (zxuuf ** 2 + zyuuf ** 2)), eps)
+    cost, sint, cosu, sinu, cosv, sinv, cosf, sinf = outs
+    sint[J, I] = (zxnpt * zyvvt - zynpt * zxvvt) / znvvt; cost[J, I] = (zxnpt * zxvvt + zynpt * zyvvt) / znvvt
+    sinu[J, I] = (zxnpu * zyffu - zynpu * zxffu) / znffu; cosu[J, I] = (zxnpu * zxffu + zynpu * zyffu) / znffu
+    sinf[J, I] = (zxnpf * zyuuf - zynpf * zxuuf) / znuuf; cosf[J, I] = (zxnpf * zxuuf + zynpf * zyuuf) / znuuf
+    sinv[J, I] = (zxnpv * zxffv + zynpv * zyffv) / znffv; cosv[J, I] = -(zxnpv * zyffv - zynpv * zxffv) / znffv
+    if nperio > 0:
+        for a, cd in zip(outs, "TTUUVVFF"):
+            a[:] = lbc_lnk_r8_py(nperio, a, cd, -1.0)
+    else:
+        def ex1(xa, xb, xc, xd, ya, yb, yc):
+            A, B, Cc = xb - xa, xc - xb, xd - xc
+            with np.errstate(all="ignore"):
+                r = Cc * (2 * (yc - yb) / B - (yb - ya) / A) + yc
+            return np.where((A == 0) | (B == 0) | (Cc == 0), yc, r)
+        PH = (phit, phit, phiu, phiu, phiv, phiv, phif, phif); LA = (lamt, lamt, lamu, lamu, lamv, lamv, lamf, lamf)
+        for a, P in zip(outs, PH):
+            a[ny - 1, :] = ex1(P[ny - 4], P[ny - 3], P[ny - 2], P[ny - 1], a[ny - 4], a[ny - 3], a[ny - 2])
+        for a, P in zip(outs, PH):
+            a[0, :] = ex1(P[3], P[2], P[1], P[0], a[3], a[2], a[1])
+        for a, L in zip(outs, LA):
+            a[:, 0] = ex1(L[:, 3], L[:, 2], L[:, 1], L[:, 0], a[:, 3], a[:, 2], a[:, 1])
+    return tuple(outs)
+
+
+def lbc_lnk_r8_py(nperio, X, cd_type, psgn, pval=None):
+    """lbc_lnk_2d_r8 on a float64 array: same loops as lbc_lnk_py without the REAL(4) round trip."""
+    return _lbc_core(nperio, np.asarray(X, np.float64), cd_type, psgn, pval)

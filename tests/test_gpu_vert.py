@@ -120,3 +120,35 @@ def test_extrp_hl_vs_oracle(gpu, orc):
         assert np.array_equal(a, b), (top, btm, icr)
     a = orc.extrp_hl(X, 33, 6, 1)
     assert np.array_equal(a[:, 32:], np.broadcast_to(X[:, 31:32], a[:, 32:].shape)) and np.array_equal(a[:, :6], np.broadcast_to(X[:, 6:7], a[:, :6].shape))
+
+
+def _staggered(lon, lat):
+    lon = np.asarray(lon, np.float64); lat = np.asarray(lat, np.float64)
+    dl = np.diff(np.unwrap(np.deg2rad(lon), axis=1), axis=1)
+    dl = np.rad2deg(np.concatenate([dl, dl[:, -1:]], axis=1))
+    dp = np.diff(lat, axis=0); dp = np.concatenate([dp, dp[-1:]], axis=0)
+    dq = np.diff(np.rad2deg(np.unwrap(np.deg2rad(lon), axis=0)), axis=0); dq = np.concatenate([dq, dq[-1:]], axis=0)
+    dr = np.diff(lat, axis=1); dr = np.concatenate([dr, dr[:, -1:]], axis=1)
+    lamu, phiu = lon + 0.5 * dl, lat + 0.5 * dr
+    lamv, phiv = lon + 0.5 * dq, lat + 0.5 * dp
+    return lon, lat, lamu, phiu, lamv, phiv, lamu + 0.5 * dq, phiu + 0.5 * dp
+
+
+def test_angle2_vs_oracle(gpu, orc):
+    """ANGLE2 (src/mod_nemotools.f90:607-823): ORCA grids with both fold pivots (lbc_lnk, psgn = -1), a regional grid
+    (Akima edge extrapolation) and a -180..180 grid that crosses the cut line (l_cut_180)."""
+    from sosie_b200 import grids as G
+    cases = []
+    cfg = G.config("B", 1.0); cases.append((6, cfg["src_lon"], cfg["src_lat"]))
+    cfg = G.config("C", 1.0); cases.append((4, cfg["src_lon"], cfg["src_lat"]))
+    cfg = G.config("E", 0.03); Xt, Yt = G.trg_2d(cfg); cases.append((0, Xt, Yt))
+    lo = np.where(Xt > 180.0, Xt - 360.0, Xt)
+    cases.append((0, lo - 178.0 + (-179.9 - (lo - 178.0).min()) * ((lo - 178.0).min() < -180.0), Yt))
+    for nperio, lo, la in cases:
+        args = _staggered(lo, la)
+        a = gpu.angle2(nperio, *args)
+        b = orc.angle2(nperio, *args)
+        for q in range(8):
+            assert np.array_equal(np.isnan(a[q]), np.isnan(b[q])), (nperio, q)
+            ok = ~np.isnan(a[q])
+            assert np.array_equal(a[q][ok].view(np.uint64), b[q][ok].view(np.uint64)), (nperio, q, np.nanmax(np.abs(a[q] - b[q])))

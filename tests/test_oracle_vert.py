@@ -76,3 +76,49 @@ def test_interp3d_post_vs_numpy(orc):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (ixb, iorca, lmout)
         keep = a[a != np.float32(-9999.0)]
         assert keep.min() >= 0.0 and keep.max() <= 20.0
+
+
+def _staggered(lon, lat):
+    """synthetic T/U/V/F coordinates from a T grid: U half a cell east, V half a cell north, F both"""
+    lon = np.asarray(lon, np.float64); lat = np.asarray(lat, np.float64)
+    dl = np.diff(np.unwrap(np.deg2rad(lon), axis=1), axis=1)
+    dl = np.rad2deg(np.concatenate([dl, dl[:, -1:]], axis=1))
+    dp = np.diff(lat, axis=0); dp = np.concatenate([dp, dp[-1:]], axis=0)
+    dq = np.diff(np.rad2deg(np.unwrap(np.deg2rad(lon), axis=0)), axis=0); dq = np.concatenate([dq, dq[-1:]], axis=0)
+    dr = np.diff(lat, axis=1); dr = np.concatenate([dr, dr[:, -1:]], axis=1)
+    lamu, phiu = lon + 0.5 * dl, lat + 0.5 * dr
+    lamv, phiv = lon + 0.5 * dq, lat + 0.5 * dp
+    lamf, phif = lamu + 0.5 * dq, phiu + 0.5 * dp
+    return lon, lat, lamu, phiu, lamv, phiv, lamf, phif
+
+
+def test_angle2_known_answers_and_transliteration(orc):
+    from sosie_b200 import grids as G
+    orc.set_libm(orc.GLIBC)
+    try:
+        # (1) regular lat-lon grid: grid lines ARE the meridians / parallels -> cos = 1, sin = 0 at every point type
+        lon, lat = np.meshgrid(np.linspace(10.0, 60.0, 26), np.linspace(-30.0, 40.0, 36))
+        cs = orc.angle2(0, *_staggered(lon, lat))
+        for q in range(0, 8, 2):
+            assert np.allclose(cs[q][1:-1, 1:], 1.0, atol=1e-9) and np.allclose(cs[q + 1][1:-1, 1:], 0.0, atol=1e-7), q
+        # (2) the same grid rotated by 90 degrees in index space (i runs north): j-lines point west -> cos = 0, sin = +-1
+        cs = orc.angle2(0, *_staggered(lon.T[:, ::-1].copy(), lat.T[:, ::-1].copy()))
+        assert np.allclose(np.abs(cs[1][2:-2, 2:-2]), 1.0, atol=1e-6) and np.allclose(cs[0][2:-2, 2:-2], 0.0, atol=1e-6)
+        # (3) ORCA-shaped grids (both fold pivots), regional grid, and a -180..180 grid crossing the cut line, vs numpy
+        cases = []
+        cfgB = G.config("B", 0.3); cases.append((6, cfgB["src_lon"], cfgB["src_lat"]))
+        cfgC = G.config("C", 0.5); cases.append((4, cfgC["src_lon"], cfgC["src_lat"]))
+        cfgE = G.config("E", 0.008); Xt, Yt = G.trg_2d(cfgE); cases.append((0, Xt, Yt))
+        cases.append((0, np.where(Xt > 180.0, Xt - 360.0, Xt) - 178.0 + 0.0, Yt))
+        for nperio, lo, la in cases:
+            if lo.min() < -180.0:
+                lo = lo + (-179.9 - lo.min())
+            args = _staggered(lo, la)
+            a = orc.angle2(nperio, *args)
+            b = pyref.angle2_np(nperio, *args)
+            for q in range(8):
+                assert np.allclose(a[q], b[q], rtol=1e-9, atol=1e-9), (nperio, q, np.abs(a[q] - b[q]).max())
+            nrm = a[0][2:-2, 2:-2] ** 2 + a[1][2:-2, 2:-2] ** 2
+            assert np.allclose(nrm, 1.0, atol=1e-9)        # cos^2 + sin^2 = 1 in the interior
+    finally:
+        orc.set_libm(orc.PMATH)
