@@ -92,6 +92,11 @@ int sosie_bilin_get_map(sosie_ctx* ctx, int32_t* metrics, double* alphabeta, int
  * before or after sosie_bilin_set_grids (a set_grids with the same target extents keeps it).        */
 int sosie_bilin_load_map(sosie_ctx* ctx, int32_t nx2, int32_t ny2, const int32_t* metrics,
                          const double* alphabeta, const int16_t* id_problem);
+/* device-pointer variants (enqueued on the context stream): the multi-GPU flow builds the mapping on one GPU, broadcasts the
+ * arrays GPU -> GPU (NCCL over NVLink) and loads them on the others without touching the host              */
+int sosie_bilin_get_map_dev(sosie_ctx* ctx, int32_t* dmetrics, double* dalphabeta, int16_t* did_problem, float* ddist_np);
+int sosie_bilin_load_map_dev(sosie_ctx* ctx, int32_t nx2, int32_t ny2, const int32_t* dmetrics, const double* dalphabeta,
+                             const int16_t* did_problem);
 /* search diagnostics: info[0..7] = j_strt_t, j_stop_t, jlat_icr, l_is_reg_s, l_is_reg_t,
  * algorithm (0 EASY, 1 TWISTED), TWISTED chain iterations, l_add_extra_j                          */
 int sosie_bilin_map_info(sosie_ctx* ctx, int32_t* info);

@@ -42,7 +42,7 @@ EXPORTS = [
     "sosie_host_register", "sosie_host_unregister", "sosie_bilin_src_rows",
     "sosie_akima_1d_3d", "sosie_akima_1d_3d_dev", "sosie_lbc_lnk", "sosie_lbc_lnk_dev", "sosie_interp3d_post", "sosie_interp3d_post_dev",
     "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
-    "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev",
+    "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev", "sosie_bilin_get_map_dev", "sosie_bilin_load_map_dev",
 ]
 
 _lib = None
@@ -232,6 +232,13 @@ class Sosie:
         r = np.zeros(2, np.int32)
         self._ck(self._lib.sosie_bilin_src_rows(self._h, _p(r)))
         return int(r[0]), int(r[1])
+
+    def bilin_get_map_dev(self, dmetrics, dalphabeta, dipb=None, ddnp=None):
+        """copy the cached mapping into the caller's device tensors (metrics i32 (3,ny,nx), alphabeta f64 (2,ny,nx), ...)"""
+        self._ck(self._lib.sosie_bilin_get_map_dev(self._h, _dp(dmetrics), _dp(dalphabeta), _dp(dipb), _dp(ddnp)))
+
+    def bilin_load_map_dev(self, nx2, ny2, dmetrics, dalphabeta, dipb=None):
+        self._ck(self._lib.sosie_bilin_load_map_dev(self._h, int(nx2), int(ny2), _dp(dmetrics), _dp(dalphabeta), _dp(dipb)))
 
     def bilin_load_map(self, metrics, alphabeta, ipb=None):
         met, ab = _i32(metrics), _f64(alphabeta)

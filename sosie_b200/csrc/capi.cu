@@ -186,6 +186,41 @@ int sosie_bilin_load_map(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32_t* 
   return SOSIE_OK;
 }
 
+// device-resident variants of get_map / load_map: the multi-GPU flow broadcasts the mapping GPU -> GPU (NCCL over NVLink)
+int sosie_bilin_get_map_dev(sosie_ctx* c, int32_t* dmetrics, double* dalphabeta, int16_t* did_problem, float* ddist_np) {
+  NEED(c);
+  if (!ctx->map_ready) { ctx->err = "sosie_bilin_get_map_dev: no mapping"; return SOSIE_ERR_STATE; }
+  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
+  cudaStream_t st = ctx->stream;
+  if (dmetrics) CK(cudaMemcpyAsync(dmetrics, ctx->d_metrics.p, 3 * nt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  if (dalphabeta) CK(cudaMemcpyAsync(dalphabeta, ctx->d_ab.p, 2 * nt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (did_problem) CK(cudaMemcpyAsync(did_problem, ctx->d_ipb.p, nt * sizeof(int16_t), cudaMemcpyDeviceToDevice, st));
+  if (ddist_np && ctx->d_dnp.p) CK(cudaMemcpyAsync(ddist_np, ctx->d_dnp.p, nt * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return SOSIE_OK;
+}
+
+int sosie_bilin_load_map_dev(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32_t* dmetrics, const double* dalphabeta,
+                             const int16_t* did_problem) {
+  NEED(c);
+  if (!dmetrics || !dalphabeta || nx2 < 1 || ny2 < 1) { ctx->err = "sosie_bilin_load_map_dev: bad arguments"; return SOSIE_ERR_ARG; }
+  if (ctx->grids_set && (ctx->tg.nx != nx2 || ctx->tg.ny != ny2)) ctx->grids_set = false;
+  const size_t nt = (size_t)nx2 * ny2;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->d_metrics.alloc(3 * nt)); CK(ctx->d_ab.alloc(2 * nt)); CK(ctx->d_ipb.alloc(nt)); CK(ctx->d_dnp.alloc(nt));
+  ctx->map_nt = nt;
+  CK(cudaMemcpyAsync(ctx->d_metrics.p, dmetrics, 3 * nt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(ctx->d_ab.p, dalphabeta, 2 * nt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  if (did_problem) CK(cudaMemcpyAsync(ctx->d_ipb.p, did_problem, nt * sizeof(int16_t), cudaMemcpyDeviceToDevice, st));
+  else CK(cudaMemsetAsync(ctx->d_ipb.p, 0, nt * sizeof(int16_t), st));
+  CK(cudaMemsetAsync(ctx->d_dnp.p, 0, nt * sizeof(float), st));
+  if (!ctx->grids_set) { ctx->tg.nx = nx2; ctx->tg.ny = ny2; }
+  ctx->map_ready = true;
+  ctx->pack_ready = false;
+  for (int k = 0; k < 8; k++) ctx->map_info[k] = 0;
+  ctx->map_info[5] = -1;
+  return SOSIE_OK;
+}
+
 // host-pointer apply: slab chunks flow through two staging buffer pairs on three streams (H2D | kernels | D2H run
 // concurrently: PCIe is full duplex); only the source rows the packed records read are uploaded, only this
 // shard's target rows come back.
