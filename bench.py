@@ -45,52 +45,55 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled DURING the timed region, in-process through NVML (nvidia_ml_py) from one
+    thread of rank 0 only: one `nvidia-smi -lms` poller per rank takes the driver lock often enough to stretch the
+    launch / sync latencies of a 2 ms step (measured: 8 pollers cost 0.7 ms per step at N = 8)."""
 
-    def __init__(self, index=0):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    def __init__(self, index=0, period=0.02):
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.mx = [], set(), None
+        self._stop = threading.Event()
+        self.t = None
+        self.ok = False
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
-                                          str(self.index), "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+            import pynvml as N
+            N.nvmlInit()
+            self.N = N
+            self.h = N.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.ok = True
         except Exception:
-            self.proc = None
+            self.ok = False
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _run(self):
+        N = self.N
+        bits = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                r = N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self._stop.set()
+        self.t.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "source": "NVML, sampled every 20 ms on rank 0 during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -501,7 +504,8 @@ def run_ours(args):
         step_dev()
     barrier()
     sampler = ClockSampler(local)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     ctx.profile(True)
     l0 = ctx.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -523,6 +527,9 @@ def run_ours(args):
         kmap.append(ctx.timing_ms(ctx.T_MAP)); kapp.append(ctx.timing_ms(ctx.T_APPLY)); kpack.append(ctx.timing_ms(ctx.T_PACK))
     ctx.profile(False)
     clocks = sampler.stop()
+    if os.environ.get("SOSIE_BENCH_DEBUG"):
+        sys.stderr.write(f"[rank {rank}] rows {r0}..{r1} step {elapsed_ms / args.steps:.3f} ms  map {np.mean(kmap):.3f}  pack {np.mean(kpack):.3f}  "
+                         f"apply {np.mean(kapp):.3f}\n")
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
