@@ -116,40 +116,19 @@ __global__ void k_rtmp(TrgGeom tg, Prelude* p) {
   if (threadIdx.x == 0) p->rtmp = r;
 }
 
-// i1dum = MINLOC(Ytrg, mask=(Ytrg>=y_min_s), dim=2) ; MAXLOC(Ytrg, mask=(Ytrg<=y_max_s), dim=2)  (:939-941)
-// Two exact parallel passes per column: (1) the extreme VALUE (atomicMin/Max on order-preserving encodings),
-// (2) the FIRST row attaining it (atomicMin on the row index) -- MINLOC/MAXLOC return the first occurrence.
+// i1dum = MINLOC(Ytrg, mask=(Ytrg>=y_min_s), dim=2) ; MAXLOC(Ytrg, mask=(Ytrg<=y_max_s), dim=2)  (:939-941): see k_ypass
 __global__ void k_fill_i32(int32_t* a, size_t n, int32_t v);
 #define JR_ROWS 64
-__global__ void k_jrange_idx(TrgGeom tg, const unsigned long long* __restrict__ cmin, const unsigned long long* __restrict__ cmax,
-                             int* jn, int* jx) {
-  int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
-  size_t total = (size_t)tg.nx * nchunk;
-  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
-    int i = (int)(t % tg.nx) + 1, c = (int)(t / tg.nx);
-    unsigned long long vmin = cmin[i - 1], vmax = cmax[i - 1];
-    int j1 = min(tg.ny, (c + 1) * JR_ROWS);
-    int fn = 2147483647, fx = 2147483647;
-    for (int j = c * JR_ROWS + 1; j <= j1; j++) {
-      unsigned long long e = enc_d(trg_lat(tg, i, j));
-      if (e == vmin && fn == 2147483647) fn = j;
-      if (e == vmax && fx == 2147483647) fx = j;
-    }
-    if (vmin != ~0ULL && fn != 2147483647) atomicMin(&jn[i - 1], fn);
-    if (vmax != 0ULL && fx != 2147483647) atomicMin(&jx[i - 1], fx);
-  }
-}
-__global__ void k_jrange_fin(int nx, const int* __restrict__ jn, const int* __restrict__ jx, Prelude* p) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-    if (jn[i] != 2147483647) atomicMin(&p->j_strt, jn[i]);            // MINVAL(i1dum, mask=(i1dum>0))
-    atomicMax(&p->j_stop, jx[i] != 2147483647 ? jx[i] : 0);           // MAXVAL(MAXLOC(...)) (0 where the mask is empty)
-  }
-}
 // ONE pass over the target latitudes for everything the prelude reduces from them: MINVAL/MAXVAL(Ytrg) (:888-889),
-// rmin_dlat_dj = MINVAL(SIGN(1,rtmp)*(Ytrg(:,j) - Ytrg(:,j-1))) (:921-923) and the per-column extreme values of
-// k_jrange_val.  y_min_s / y_max_s / rtmp are read from the Prelude on the device (written by earlier kernels of the
+// rmin_dlat_dj = MINVAL(SIGN(1,rtmp)*(Ytrg(:,j) - Ytrg(:,j-1))) (:921-923) and, per (column, chunk of JR_ROWS rows), the
+// extreme value under the mask of :939-941 together with the FIRST row attaining it (MINLOC / MAXLOC return the first
+// occurrence).  y_min_s / y_max_s / rtmp are read from the Prelude on the device (written by earlier kernels of the
 // stream), so no host round trip separates the reductions.  All of them are min/max: order independent, exact.
-__global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, unsigned long long* cmin, unsigned long long* cmax) {
+struct ColPart {
+  unsigned long long emin, emax;   // order-preserving encodings; ~0 / 0 = mask empty in this chunk
+  int jmin, jmax;                  // first rows (1-based) attaining them
+};
+__global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, ColPart* part) {
   const double y_min_s = dec_d(p->ymin_s), y_max_s = dec_d(p->ymax_s);   // MINVAL / MAXVAL(Ysrc), reduced by k_minmax before
   const double sgn = d_sign(1.0, p->rtmp);
   const int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
@@ -158,7 +137,8 @@ __global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, unsigned long long*
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(t % tg.nx) + 1, c = (int)(t / tg.nx);
     const int j0 = c * JR_ROWS + 1, j1 = min(tg.ny, (c + 1) * JR_ROWS);
-    unsigned long long lmin = ~0ULL, lmax = 0ULL;
+    ColPart cp;
+    cp.emin = ~0ULL; cp.emax = 0ULL; cp.jmin = 0; cp.jmax = 0;
     double prev = (j0 > 1 && do_dlat) ? trg_lat(tg, i, j0 - 1) : 0.0;
     for (int j = j0; j <= j1; j++) {
       const double v = trg_lat(tg, i, j);
@@ -166,11 +146,10 @@ __global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, unsigned long long*
       gmin = min(gmin, e); gmax = max(gmax, e);
       if (do_dlat && j >= 2) gdl = min(gdl, enc_d(sgn * (v - prev)));
       prev = v;
-      if (v >= y_min_s) lmin = min(lmin, e);
-      if (v <= y_max_s) lmax = max(lmax, e);
+      if ((v >= y_min_s) && e < cp.emin) { cp.emin = e; cp.jmin = j; }   // strict: the first occurrence wins
+      if ((v <= y_max_s) && (e > cp.emax || cp.jmax == 0)) { cp.emax = e; cp.jmax = j; }
     }
-    if (lmin != ~0ULL) atomicMin(&cmin[i - 1], lmin);
-    if (lmax != 0ULL) atomicMax(&cmax[i - 1], lmax);
+    part[t] = cp;   // [chunk][column]
   }
   for (int o = 16; o > 0; o >>= 1) {
     gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
@@ -182,9 +161,18 @@ __global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, unsigned long long*
     if (do_dlat) atomicMin(&p->rmin_dlat, gdl);
   }
 }
-__global__ void k_jrange_init(int nx, unsigned long long* cmin, unsigned long long* cmax, int* jn, int* jx) {
+// per column: combine the chunks in row order, then j_strt = MINVAL(i1dum, mask=(i1dum>0)), j_stop = MAXVAL(MAXLOC(...))
+__global__ void k_jrange_cols(int nx, int nchunk, const ColPart* __restrict__ part, Prelude* p) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
-    cmin[i] = ~0ULL; cmax[i] = 0ULL; jn[i] = 2147483647; jx[i] = 2147483647;
+    unsigned long long emin = ~0ULL, emax = 0ULL;
+    int jmin = 0, jmax = 0;
+    for (int c = 0; c < nchunk; c++) {
+      const ColPart cp = part[(size_t)c * nx + i];
+      if (cp.jmin > 0 && cp.emin < emin) { emin = cp.emin; jmin = cp.jmin; }
+      if (cp.jmax > 0 && (cp.emax > emax || jmax == 0)) { emax = cp.emax; jmax = cp.jmax; }
+    }
+    if (jmin > 0) atomicMin(&p->j_strt, jmin);
+    atomicMax(&p->j_stop, jmax);   // MAXLOC of an empty mask is 0
   }
 }
 __global__ void k_fill_u64(unsigned long long* a, size_t n, unsigned long long v) {
@@ -783,6 +771,15 @@ __global__ void k_twisted_scatter(const int64_t* __restrict__ order, int T, cons
 __global__ void k_fill_i32(int32_t* a, size_t n, int32_t v) {
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) a[k] = v;
 }
+int bilin_materialize_mask(sosie_ctx* ctx) {
+  if (!ctx->mask_is_ones) return SOSIE_OK;
+  const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
+  CK(ctx->t_mask.alloc(nt));
+  k_fill_i32<<<grid_for(ctx, nt, 256), 256, 0, ctx->stream>>>(ctx->t_mask.p, nt, 1);
+  KLAUNCH_CHECK();
+  ctx->mask_is_ones = false;
+  return SOSIE_OK;
+}
 int fill_i32_dev(sosie_ctx* ctx, int32_t* p, size_t n, int32_t v) {
   k_fill_i32<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(p, n, v);
   KLAUNCH_CHECK();
@@ -817,6 +814,20 @@ int fetch_small(sosie_ctx* ctx, const void* dsrc, void* hdst, size_t bytes) {
   memcpy(hdst, ctx->mailbox, bytes);
   return SOSIE_OK;
 }
+// two objects, one stream synchronisation
+static int fetch_pair(sosie_ctx* ctx, const void* d1, void* h1, size_t b1, const void* d2, void* h2, size_t b2) {
+  const size_t o2 = (b1 + 15) & ~(size_t)15;
+  if (o2 + b2 > SOSIE_MAILBOX_BYTES) { if (int rc = fetch_small(ctx, d1, h1, b1)) return rc; return fetch_small(ctx, d2, h2, b2); }
+  if (!ctx->mailbox) CK(cudaHostAlloc((void**)&ctx->mailbox, SOSIE_MAILBOX_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
+  unsigned char* dmb = nullptr;
+  CK(cudaHostGetDevicePointer((void**)&dmb, ctx->mailbox, 0));
+  k_to_mailbox<<<32, 256, 0, ctx->stream>>>((const unsigned char*)d1, dmb, b1); KLAUNCH_CHECK();
+  k_to_mailbox<<<32, 256, 0, ctx->stream>>>((const unsigned char*)d2, dmb + o2, b2); KLAUNCH_CHECK();
+  CK(cudaStreamSynchronize(ctx->stream));
+  memcpy(h1, ctx->mailbox, b1);
+  memcpy(h2, ctx->mailbox + o2, b2);
+  return SOSIE_OK;
+}
 static int fetch_d(sosie_ctx* ctx, const double* dptr, double* out) { return fetch_small(ctx, dptr, out, sizeof(double)); }
 
 // coordinate part of BILIN_2D's prologue (:97-148): decide l_add_extra_j, build the working source
@@ -829,14 +840,15 @@ int bilin_prepare_src(sosie_ctx* ctx) {
   cudaStream_t st = ctx->stream;
   ctx->l_add_extra_j = 0;
   double dyp = 0.0;
+  ctx->h_axes.clear();
+  if (in_1d) {  // one read-back of both axes serves everything the host decides from them (this routine and the EASY search)
+    ctx->h_axes.resize((size_t)nx + ny + 2);
+    if (int rc = fetch_pair(ctx, Xin, ctx->h_axes.data(), sizeof(double) * nx, Yin, ctx->h_axes.data() + nx, sizeof(double) * ny)) return rc;
+  }
   if (ctx->l_reg_src && (ny > 20) && (nx > 20)) {
     double ymx, ym1;
     int ih = nx / 2;  // Y1(nx1/2, ny1)
-    if (in_1d) {  // Y(ny-1), Y(ny) are adjacent: one read-back
-      double two[2];
-      if (int rc = fetch_small(ctx, Yin + (ny - 2), two, sizeof(two))) return rc;
-      ym1 = two[0]; ymx = two[1];
-    }
+    if (in_1d) { ym1 = ctx->h_axes[nx + ny - 2]; ymx = ctx->h_axes[nx + ny - 1]; }
     else {
       if (fetch_d(ctx, Yin + (size_t)(ih - 1) + (size_t)(ny - 1) * nx, &ymx)) return SOSIE_ERR_CUDA;
       if (fetch_d(ctx, Yin + (size_t)(ih - 1) + (size_t)(ny - 2) * nx, &ym1)) return SOSIE_ERR_CUDA;
@@ -853,6 +865,10 @@ int bilin_prepare_src(sosie_ctx* ctx) {
         if (s > (double)1.E-12f) { ctx->err = "EXT_NORTH_TO_90_REGG: grid doesnt seem to be regular"; return SOSIE_ERR_REF_STOP; }
       }
     }
+  }
+  if (in_1d) {  // the working latitude axis (pole rows included), as k_lat_table builds it on the device
+    if (ctx->l_add_extra_j) { ctx->h_axes[nx + ny] = 90.0; ctx->h_axes[nx + ny + 1] = 90.0 + dyp; }
+    else ctx->h_axes.resize((size_t)nx + ny);
   }
   sg.nyw = ny + (ctx->l_add_extra_j ? 2 : 0);
   const int nyw = sg.nyw;
@@ -886,11 +902,15 @@ int bilin_prepare_src(sosie_ctx* ctx) {
   if (ctx->l_add_extra_j) {
     CK(ctx->d_im.alloc(nx));
     const double* lonrow = in_1d ? Xin : Xin + (size_t)(ny - 1) * nx;
-    CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
-    CK(cudaMemsetAsync(ctx->d_iscratch.p + 1, 0, sizeof(int), st));
-    k_check_sorted<<<cdiv(nx, 256), 256, 0, st>>>(lonrow, nx, ctx->d_iscratch.p + 1); KLAUNCH_CHECK();
     int unsorted = 0;
-    if (int rc = fetch_small(ctx, ctx->d_iscratch.p + 1, &unsorted, sizeof(int))) return rc;
+    if (in_1d) {
+      for (int i = 1; i < nx; i++) if (ctx->h_axes[i] < ctx->h_axes[i - 1]) { unsorted = 1; break; }
+    } else {
+      CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
+      CK(cudaMemsetAsync(ctx->d_iscratch.p + 1, 0, sizeof(int), st));
+      k_check_sorted<<<cdiv(nx, 256), 256, 0, st>>>(lonrow, nx, ctx->d_iscratch.p + 1); KLAUNCH_CHECK();
+      if (int rc = fetch_small(ctx, ctx->d_iscratch.p + 1, &unsorted, sizeof(int))) return rc;
+    }
     k_jim_table<<<cdiv(nx, 128), 128, 0, st>>>(lonrow, nx, unsorted ? 0 : 1, ctx->d_im.p); KLAUNCH_CHECK();
   }
   return SOSIE_OK;
@@ -928,16 +948,15 @@ int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool*
     int ja = partial_x ? std::max(2, xrow_a) : 2, jb = partial_x ? xrow_b : tg.ny;
     k_is_regular<<<grid_for(ctx, (size_t)tg.ny * 32, 256), 256, 0, st>>>(tg.X, tg.Y, tg.nx, tg.ny, ja, jb, &dpre.p->irreg_t); KLAUNCH_CHECK();
   }
-  // the target latitudes are read twice in all: k_ypass (every reduction) and k_jrange_idx (first rows attaining the
-  // per-column extremes); the row range is computed unconditionally and used only when the reference computes it
+  // the target latitudes are read ONCE (k_ypass); the row range is computed unconditionally and used only when the
+  // reference computes it
   const int do_dlat = (tg.nx > 2) ? 1 : 0;
   if (do_dlat) { k_rtmp<<<1, 1024, 0, st>>>(tg, dpre.p); KLAUNCH_CHECK(); }
-  WS(unsigned long long, cmin, tg.nx); WS(unsigned long long, cmax, tg.nx); WS(int, jn, tg.nx); WS(int, jx, tg.nx);
-  k_jrange_init<<<cdiv(tg.nx, 256), 256, 0, st>>>(tg.nx, cmin.p, cmax.p, jn.p, jx.p); KLAUNCH_CHECK();
-  const size_t tot = (size_t)tg.nx * ((tg.ny + JR_ROWS - 1) / JR_ROWS);
-  k_ypass<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, dpre.p, do_dlat, cmin.p, cmax.p); KLAUNCH_CHECK();
-  k_jrange_idx<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, cmin.p, cmax.p, jn.p, jx.p); KLAUNCH_CHECK();
-  k_jrange_fin<<<cdiv(tg.nx, 256), 256, 0, st>>>(tg.nx, jn.p, jx.p, dpre.p); KLAUNCH_CHECK();
+  const int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
+  const size_t tot = (size_t)tg.nx * nchunk;
+  WS(ColPart, part, tot);
+  k_ypass<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, dpre.p, do_dlat, part.p); KLAUNCH_CHECK();
+  k_jrange_cols<<<cdiv(tg.nx, 128), 128, 0, st>>>(tg.nx, nchunk, part.p, dpre.p); KLAUNCH_CHECK();
   Prelude hp;
   if (int rc = fetch_small(ctx, dpre.p, &hp, sizeof(Prelude))) return rc;
   if (partial_x && hp.irreg_t == 0) { if (need_full_x) *need_full_x = true; return SOSIE_OK; }
@@ -972,7 +991,8 @@ int bilin_easy_prepare(sosie_ctx* ctx) {
   double* vax = ctx->d_vax.p;
   k_gather_axes<<<cdiv(sg.nx + sg.nyw, 256), 256, 0, st>>>(sg, vax, vax + sg.nx); KLAUNCH_CHECK();
   std::vector<double> hax(sg.nx + sg.nyw);
-  if (int rc = fetch_small(ctx, vax, hax.data(), sizeof(double) * hax.size())) return rc;
+  if (sg.separable && ctx->h_axes.size() == hax.size()) hax = ctx->h_axes;   // Xsrc(:,3) = lon axis, Ysrc(3,:) = working lat axis
+  else if (int rc = fetch_small(ctx, vax, hax.data(), sizeof(double) * hax.size())) return rc;
   ctx->easy_sorted_lon = is_sorted_host(hax, 0, sg.nx);
   ctx->easy_sorted_lat = is_sorted_host(hax, sg.nx, sg.nyw);
   sg.lon0 = sg.inv_dlon = sg.lat0 = sg.inv_dlat = 0.0;
@@ -991,11 +1011,11 @@ int bilin_easy_rows(sosie_ctx* ctx, int jlo, int jhi, size_t k0, size_t kcnt, in
   if (kcnt == 0) return SOSIE_OK;
   const double* vax = ctx->d_vax.p;
   if (sg.separable)
-    k_map_easy<true><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
+    k_map_easy<true><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->mask_is_ones ? nullptr : ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
                                                                  ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
                                                                  ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt);
   else
-    k_map_easy<false><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
+    k_map_easy<false><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->mask_is_ones ? nullptr : ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
                                                                   ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
                                                                   ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt);
   KLAUNCH_CHECK();
@@ -1041,6 +1061,7 @@ int bilin_map_impl(sosie_ctx* ctx) {
   } else {
     // ---- FIND_NEAREST_TWISTED
     ctx->map_info[5] = 1;
+    if (int rc = bilin_materialize_mask(ctx)) return rc;   // this search writes -1 / -2 into the mask
     if ((y_min_t >= y_max_s) || (y_max_t <= y_min_s)) { ctx->err = "FIND_NEAREST_TWISTED: Target and source latitudes do not overlap!"; return SOSIE_ERR_REF_STOP; }
     if (sg.separable) { ctx->err = "internal: TWISTED with separable source"; return SOSIE_ERR_ARG; }
     WS(double, e1, nsrc); WS(double, e2, nsrc);

@@ -81,6 +81,7 @@ int bilin_map_rows_d2h(sosie_ctx* ctx, cudaStream_t st, int j0, int j1, int32_t*
       CK(cudaMemcpyAsync(alphabeta + pl * nt + off, ctx->d_ab.p + pl * nt + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (id_problem) CK(cudaMemcpyAsync(id_problem + off, ctx->d_ipb.p + off, cnt * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   if (dist_np && ctx->d_dnp.p) CK(cudaMemcpyAsync(dist_np + off, ctx->d_dnp.p + off, cnt * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (mask_out && ctx->mask_is_ones) { if (int rc = bilin_materialize_mask(ctx)) return rc; }
   if (mask_out && ctx->t_mask.p) CK(cudaMemcpyAsync(mask_out + off, ctx->t_mask.p + off, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   return SOSIE_OK;
 }
@@ -155,7 +156,7 @@ static int pipelined_run(sosie_ctx* ctx, Pipe& P, int k_ew, int nx1, int ny1, co
 
   // ---- compute stream: source preparation, then one (map, pack) pair per chunk as its rows arrive
   CK(cudaStreamWaitEvent(sc, e_src, 0));
-  if (!mask) { if (int rc = fill_i32_dev(ctx, ctx->t_mask.p, nt, 1)) return rc; }
+  ctx->mask_is_ones = (mask == nullptr);
   if (int rc = bilin_prepare_src(ctx)) return rc;
   if (int rc = bilin_easy_prepare(ctx)) return rc;
   P.mark("source prepared (compute)", sc);

@@ -104,8 +104,9 @@ static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_
   CK(ctx->t_mask.alloc(nt));
   if (dmask) {
     CK(cudaMemcpyAsync(ctx->t_mask.p, dmask, nt * sizeof(int32_t), mask_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    ctx->mask_is_ones = false;
   } else {
-    if (int rc = fill_i32_dev(ctx, ctx->t_mask.p, nt, 1)) return rc;
+    ctx->mask_is_ones = true;   // filled lazily (TWISTED search, get_map): the EASY path never reads an all-ones mask
   }
   if (int rc = bilin_prepare_src(ctx)) return rc;
   ctx->grids_set = true;

@@ -100,6 +100,7 @@ struct sosie_ctx {
   DBuf<double> s_in_X, s_in_Y;   // uploaded (or borrowed) raw source coordinates
   DBuf<double> t_X, t_Y;
   DBuf<int32_t> t_mask;          // mask_domain_trg as modified by the search
+  bool mask_is_ones = false;     // no mask was given: t_mask is NOT filled (kernels take a null mask = all 1) until somebody writes it
   DBuf<int32_t> d_metrics;       // (nx2,ny2,3)
   DBuf<double> d_ab;             // (nx2,ny2,2)
   DBuf<int16_t> d_ipb;
@@ -131,6 +132,7 @@ struct sosie_ctx {
   }
   int32_t map_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int easy_sorted_lon = 0, easy_sorted_lat = 0;
+  std::vector<double> h_axes;    // host copy of a 1-D source's axes: lon(nx), working lat(nyw)
   int l_last_y_row_missing = 0;
 
   // ---- akima state
@@ -236,6 +238,7 @@ struct MapPlan {
 int fetch_small(sosie_ctx* ctx, const void* dsrc, void* hdst, size_t bytes);
 
 // entry points implemented in the other translation units
+int bilin_materialize_mask(sosie_ctx* ctx);   // fills t_mask with 1 if it is still virtual
 int bilin_map_impl(sosie_ctx* ctx);
 int bilin_map_alloc(sosie_ctx* ctx);
 int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool* need_full_x);
