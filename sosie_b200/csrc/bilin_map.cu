@@ -96,22 +96,42 @@ __global__ void k_is_regular(const double* __restrict__ X, const double* __restr
   }
 }
 
-// rtmp = SUM(Ytrg(:,jm) - Ytrg(:,jm-1)) sequentially (only its sign is used, :921-922)
+// rtmp = SUM(Ytrg(:,jm) - Ytrg(:,jm-1)) (:921); only SIGN(1., rtmp) is used (:922).  A floating-point sum of terms that
+// are all >= 0 (or all <= 0) has that sign in any order, so the usual case (latitudes monotone along j on that row pair)
+// is decided by a parallel sign census and rtmp is set to +-(number of non-zero terms); only mixed signs need the
+// sequential sum in index order, as SUM() does.
 __global__ void k_rtmp(TrgGeom tg, Prelude* p) {
   __shared__ double sh[1024];
+  __shared__ int npos, nneg;
   int jm = tg.ny / 2;
-  double r = 0.0;  // carried by thread 0 only
+  if (threadIdx.x == 0) { npos = 0; nneg = 0; }
+  __syncthreads();
   if (jm >= 2) {
-    for (int i0 = 1; i0 <= tg.nx; i0 += 1024) {
-      int i = i0 + threadIdx.x;
-      if (i <= tg.nx) sh[threadIdx.x] = trg_lat(tg, i, jm) - trg_lat(tg, i, jm - 1);
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int n = min(1024, tg.nx - i0 + 1);
-        for (int k = 0; k < n; k++) r += sh[k];  // sequential, in index order, as SUM() does
-      }
-      __syncthreads();
+    int lp = 0, ln = 0;
+    for (int i = 1 + threadIdx.x; i <= tg.nx; i += blockDim.x) {
+      const double d = trg_lat(tg, i, jm) - trg_lat(tg, i, jm - 1);
+      lp += (d > 0.0); ln += (d < 0.0) || (d != d);   // a NaN term: let the sequential sum produce the reference's NaN
     }
+    if (lp) atomicAdd(&npos, lp);
+    if (ln) atomicAdd(&nneg, ln);
+  }
+  __syncthreads();
+  if (jm < 2 || nneg == 0 || npos == 0) {
+    // all terms >= 0 -> sum >= 0 (zero only if every term is zero: SIGN(1., +0.) = +1 as for any non-negative sum);
+    // all terms <= 0 -> sum <= 0; a sum of non-positive terms that are all zero is +0 in Fortran's SUM (starts from +0)
+    if (threadIdx.x == 0) p->rtmp = (jm >= 2 && nneg > 0) ? -(double)nneg : (double)npos;
+    return;
+  }
+  double r = 0.0;  // carried by thread 0 only
+  for (int i0 = 1; i0 <= tg.nx; i0 += 1024) {
+    int i = i0 + threadIdx.x;
+    if (i <= tg.nx) sh[threadIdx.x] = trg_lat(tg, i, jm) - trg_lat(tg, i, jm - 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int n = min(1024, tg.nx - i0 + 1);
+      for (int k = 0; k < n; k++) r += sh[k];  // sequential, in index order, as SUM() does
+    }
+    __syncthreads();
   }
   if (threadIdx.x == 0) p->rtmp = r;
 }
