@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 from sosie_b200 import grids as G  # noqa: E402
 
 METRIC = "target points interpolated/sec (mapping + apply)"
-NCU_MAP_TRAFFIC_BYTES = 2148888000   # 0.794958 GB read + 1.353930 GB written per full-size launch (profiles/r01_ncu_E.md)
+NCU_MAP_TRAFFIC_BYTES = 1986979000   # 0.634432 GB read + 1.352547 GB written per full-size launch (profiles/r01_ncu_E.md)
 UNIT = "points/s"
 
 
