@@ -209,6 +209,36 @@ int sosie_akima_1d_3d(sosie_ctx* ctx, int32_t nx, int32_t ny, int32_t nk1, const
                       const float* vz2, float* xf2, float rfill_val);
 int sosie_akima_1d_3d_dev(sosie_ctx* ctx, int32_t nx, int32_t ny, int32_t nk1, const float* vz1, const float* dxf1,
                           int32_t nk2, const float* vz2, float* dxf2, float rfill_val);
+/* AKIMA_1D_1D(vz1, vf1, vz2, vf2 [, rmask_val, l_surf_persist, l_botm_persist]), src/mod_akima_1d.f90:26-232 (the
+ * per-column variant: REAL(8) in, REAL(4) out; callers src/mod_interp.f90:420, src/interp_to_hydro_section.f90:628-629),
+ * over ncol independent columns in one launch.  Element (column c, level k), both 0-based, of an array lives at
+ * base[c*cs + k*ks] (strides in elements, >= 0; cs = 0 shares one vector between all columns).  Targets outside the
+ * source column come out as -6666 unless the persistence flags say otherwise, exactly as in the reference; a column
+ * whose source values are all rmask_val is left at -6666 ("DOING NOTHING").  Inputs for which the reference itself is
+ * undefined -- missing values elsewhere than in a leading run followed by a trailing run, or fewer than 3 valid source
+ * points -- give SOSIE_ERR_REF_STOP.  status (ncol INTEGER(4), may be NULL; a DEVICE array in the _dev variant): per
+ * column 0 done, 1 all missing, -1 / -2 the two undefined cases.                                                     */
+int sosie_akima_1d_1d(sosie_ctx* ctx, int64_t ncol, int32_t nk1, const double* vz1, int64_t vz1_cs, int64_t vz1_ks,
+                      const double* vf1, int64_t vf1_cs, int64_t vf1_ks, int32_t nk2, const double* vz2, int64_t vz2_cs,
+                      int64_t vz2_ks, float* vf2, int64_t vf2_cs, int64_t vf2_ks, int32_t has_rmask, double rmask_val,
+                      int32_t l_surf_persist, int32_t l_botm_persist, int32_t* status);
+int sosie_akima_1d_1d_dev(sosie_ctx* ctx, int64_t ncol, int32_t nk1, const double* dvz1, int64_t vz1_cs, int64_t vz1_ks,
+                          const double* dvf1, int64_t vf1_cs, int64_t vf1_ks, int32_t nk2, const double* dvz2,
+                          int64_t vz2_cs, int64_t vz2_ks, float* dvf2, int64_t vf2_cs, int64_t vf2_ks, int32_t has_rmask,
+                          double rmask_val, int32_t l_surf_persist, int32_t l_botm_persist, int32_t* dstatus);
+/* the generic-coordinate (z <-> sigma) branch of INTERP_3D, src/mod_interp.f90:374-438: for every target column,
+ * AKIMA_1D_1D from depth_src(ni,nj,nk_src) / data3d_tmp(ni,nj,nk_src) (the source depths and the field already carried
+ * to the target grid) to depth_trg(ni,nj,nk_trg), sigma columns flipped (src_is_sigma / trg_is_sigma), the number of
+ * target levels limited by the target mask when lmout (mask_trg(ni,nj,nk_trg) INTEGER(4), else may be NULL), persistence
+ * below the last target level the source reaches.  data3d_trg(ni,nj,nk_trg) is INOUT (land columns and levels the
+ * reference does not assign keep their values).  The reference flips its work arrays in place; here the three inputs
+ * are left untouched.                                                                                                 */
+int sosie_interp3d_sigma(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk_src, const float* depth_src,
+                         const float* data3d_tmp, int32_t nk_trg, const float* depth_trg, const int32_t* mask_trg,
+                         int32_t lmout, int32_t src_is_sigma, int32_t trg_is_sigma, float* data3d_trg);
+int sosie_interp3d_sigma_dev(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk_src, const float* ddepth_src,
+                             const float* ddata3d_tmp, int32_t nk_trg, const float* ddepth_trg, const int32_t* dmask_trg,
+                             int32_t lmout, int32_t src_is_sigma, int32_t trg_is_sigma, float* ddata3d_trg);
 /* lbc_lnk(nperio, pt2d, cd_type, psgn [, pval]) on nslab REAL(4) slabs X(jpi,jpj,nslab), src/mod_nemotools.f90:65-417
  * (E-W cyclic / closed, south row, north fold with T-point pivot nperio 3,4 or F-point pivot 5,6); cd_type is the
  * character code ('T','U','V','F','W').  Callers: src/mod_interp.f90:131,504, src/corr_vect.f90:629-632.            */

@@ -298,6 +298,37 @@ def akima_1d_3d(vz1, xf1, vz2, rfill_val=-9999.0):
     return xf2
 
 
+def akima_1d_1d(vz1, vf1, vz2, rmask_val=None, l_surf_persist=False, l_botm_persist=False):
+    """AKIMA_1D_1D, src/mod_akima_1d.f90:26-232, over columns: vz1 (nk1,) or (ncol, nk1), vf1 (ncol, nk1) or (nk1,),
+    vz2 (nk2,) or (ncol, nk2) -> (vf2 (ncol, nk2) f32, status (ncol,) i32)"""
+    vf1 = np.atleast_2d(_f64(vf1))
+    ncol, nk1 = vf1.shape
+    vz1 = _f64(vz1)
+    vz2 = _f64(vz2)
+    z1cs = nk1 if vz1.ndim == 2 else 0
+    nk2 = vz2.shape[-1]
+    z2cs = nk2 if vz2.ndim == 2 else 0
+    vf2 = np.empty((ncol, nk2), np.float32)
+    status = np.zeros(ncol, np.int32)
+    lib().orc_akima_1d_1d(C.c_int64(ncol), nk1, _p(vz1, C.c_double), C.c_int64(z1cs), C.c_int64(1), _p(vf1, C.c_double), C.c_int64(nk1),
+                          C.c_int64(1), nk2, _p(vz2, C.c_double), C.c_int64(z2cs), C.c_int64(1), _p(vf2, C.c_float), C.c_int64(nk2),
+                          C.c_int64(1), int(rmask_val is not None), C.c_double(0.0 if rmask_val is None else rmask_val),
+                          int(l_surf_persist), int(l_botm_persist), _p(status, C.c_int32))
+    return vf2, status
+
+
+def interp3d_sigma(depth_src, data3d_tmp, depth_trg, data3d_trg, mask_trg=None, lmout=False, src_sigma=False, trg_sigma=False):
+    """generic-coordinate branch of INTERP_3D, src/mod_interp.f90:374-438: cubes (nk, nj, ni); returns (data3d_trg, worst status)"""
+    depth_src, data3d_tmp, depth_trg = _f32(depth_src), _f32(data3d_tmp), _f32(depth_trg)
+    out = _f32(data3d_trg).copy()
+    nk_src, nj, ni = data3d_tmp.shape
+    nk_trg = depth_trg.shape[0]
+    mk = _i32(mask_trg) if mask_trg is not None else None
+    st = lib().orc_interp3d_sigma(ni, nj, nk_src, _p(depth_src, C.c_float), _p(data3d_tmp, C.c_float), nk_trg, _p(depth_trg, C.c_float),
+                                  _p(mk, C.c_int32), int(lmout), int(src_sigma), int(trg_sigma), _p(out, C.c_float))
+    return out, st
+
+
 def lbc_lnk(nperio, X, cd_type="T", psgn=1.0, pval=None):
     """lbc_lnk_2d_r4, src/mod_nemotools.f90:154: slabs X (nslab, jpj, jpi) or (jpj, jpi)"""
     X = _f32(X).copy()

@@ -382,9 +382,193 @@ static void angle2(int nperio, int nx, int ny, const double* plamt, const double
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// AKIMA_1D_1D (src/mod_akima_1d.f90:26-232) with slopes_1d (:392-455) and extra_2_west_r4 / extra_2_east_r4
+// (src/mod_manip.f90:571-587, 634-649): one column.  vz1, vf1, vz2 are REAL(8); the extended arrays vz1e, vf1e and the
+// slopes are REAL(4); the polynomial is evaluated in REAL(8) with the REAL(4) sub-expressions the source implies.
+// Returns 0 = done, 1 = every source value is missing ("DOING NOTHING", vf2 stays -6666), < 0 = the reference's
+// behaviour is undefined for this input (array-shape mismatch or reads of unset elements):
+//   -1  missing values not confined to "a run at the start (optional) and a run at the end" (:88-95)
+//   -2  fewer than 3 valid source points (vz1e(5) unset)
+int akima_1d_1d(int nk1, const double* vz1_, const double* vf1_, int nk2, const double* vz2_, float* vf2_, bool has_rmv, double rmv,
+                bool l_sp, bool l_bp) {
+  auto vz1 = [&](int k) { return vz1_[k - 1]; };
+  auto vf1 = [&](int k) { return vf1_[k - 1]; };
+  auto vz2 = [&](int k) { return vz2_[k - 1]; };
+  for (int k = 0; k < nk2; k++) vf2_[k] = -6666.0f;
+  int nz1 = nk1, k1_1 = 1, k1_n = nk1, nmissv = 0;
+  std::vector<int> imiss1;
+  if (has_rmv) {
+    imiss1.assign(nk1 + 1, 0);
+    for (int k = 1; k <= nk1; k++) if (vf1(k) == rmv) { imiss1[k] = 1; nmissv++; }
+  }
+  if (!(nmissv < nk1)) return 1;
+  if (nmissv > 0) {
+    k1_1 = 0;
+    for (int k = 1; k <= nk1; k++) if (imiss1[k] == 0) { k1_1 = k; break; }            // FINDLOC(imiss1, 0)
+    int f = 0;
+    for (int k = k1_1; k <= nk1; k++) if (imiss1[k] == 1) { f = k - k1_1 + 1; break; }  // FINDLOC(imiss1(k1_1:), 1)
+    k1_n = f + k1_1 - 2;
+    nz1 = nk1 - nmissv;
+    if (k1_n - k1_1 + 1 != nz1) return -1;
+  }
+  if (nz1 < 3) return -2;
+  const int nk1e = nz1 + 4;
+  std::vector<float> vz1e(nk1e + 1), vf1e(nk1e + 1), vslp(nk1e + 1);
+  for (int k = 3; k <= nz1 + 2; k++) { vz1e[k] = (float)vz1(k1_1 + k - 3); vf1e[k] = (float)vf1(k1_1 + k - 3); }
+  vz1e[2] = vz1e[4] - (vz1e[5] - vz1e[3]);
+  vz1e[1] = vz1e[3] - (vz1e[5] - vz1e[3]);
+  vz1e[nk1e - 1] = vz1e[nk1e - 3] + vz1e[nk1e - 2] - vz1e[nk1e - 4];
+  vz1e[nk1e] = vz1e[nk1e - 2] + vz1e[nk1e - 2] - vz1e[nk1e - 4];
+  {  // extra_2_west_r4(x5, x4, x3, x2, x1, y5, y4, y3 -> y2, y1)
+    float x5 = vz1e[5], x4 = vz1e[4], x3 = vz1e[3], x2 = vz1e[2], x1 = vz1e[1], y5 = vf1e[5], y4 = vf1e[4], y3 = vf1e[3];
+    float A = x4 - x5, B = x3 - x4, C = x2 - x3, D = x1 - x2, ALF = y4 - y5, BET = y3 - y4;
+    if ((A == 0.f) || (B == 0.f) || (C == 0.f)) { vf1e[2] = y3; vf1e[1] = y3; }
+    else {
+      float y2 = C * (2 * BET / B - ALF / A) + y3;
+      vf1e[2] = y2;
+      vf1e[1] = y2 + y2 * D / C + BET * D / B - ALF * D / A - y3 * D / C;
+    }
+  }
+  {  // extra_2_east_r4(x1..x5, y1, y2, y3 -> y4, y5)
+    float x1 = vz1e[nk1e - 4], x2 = vz1e[nk1e - 3], x3 = vz1e[nk1e - 2], x4 = vz1e[nk1e - 1], x5 = vz1e[nk1e];
+    float y1 = vf1e[nk1e - 4], y2 = vf1e[nk1e - 3], y3 = vf1e[nk1e - 2];
+    float A = x2 - x1, B = x3 - x2, C = x4 - x3, D = x5 - x4, ALF = y2 - y1, BET = y3 - y2;
+    if ((A == 0.f) || (B == 0.f) || (C == 0.f)) { vf1e[nk1e - 1] = y3; vf1e[nk1e] = y3; }
+    else {
+      float y4 = C * (2 * BET / B - ALF / A) + y3;
+      vf1e[nk1e - 1] = y4;
+      vf1e[nk1e] = y4 + y4 * D / C + BET * D / B - ALF * D / A - y3 * D / C;
+    }
+  }
+  {  // slopes_1d
+    const int nz = nk1e;
+    auto x = [&](int k) { return vz1e[k]; };
+    auto y = [&](int k) { return vf1e[k]; };
+    for (int k = 3; k <= nz - 2; k++) {
+      float m1 = (y(k - 1) - y(k - 2)) / (x(k - 1) - x(k - 2));
+      float m2 = (y(k) - y(k - 1)) / (x(k) - x(k - 1));
+      float m3 = (y(k + 1) - y(k)) / (x(k + 1) - x(k));
+      float m4 = (y(k + 2) - y(k + 1)) / (x(k + 2) - x(k + 1));
+      if ((m1 == m2) && (m3 == m4)) vslp[k] = 0.5f * (m2 + m3);
+      else vslp[k] = (std::fabs(m4 - m3) * m2 + std::fabs(m2 - m1) * m3) / (std::fabs(m4 - m3) + std::fabs(m2 - m1));
+    }
+    float m2 = (y(2) - y(1)) / (x(2) - x(1)), m3 = (y(3) - y(2)) / (x(3) - x(2));
+    vslp[2] = 0.5f * (m2 + m3);
+    m2 = (y(nz - 1) - y(nz - 2)) / (x(nz - 1) - x(nz - 2));
+    m3 = (y(nz) - y(nz - 1)) / (x(nz) - x(nz - 1));
+    vslp[nz - 1] = 0.5f * (m2 + m3);
+    vslp[1] = (y(2) - y(1)) / (x(2) - x(1));
+    vslp[nz] = (y(nz) - y(nz - 1)) / (x(nz) - x(nz - 1));
+  }
+  for (int jk2 = 1; jk2 <= nk2; jk2++) {
+    bool l_do_interp = true, lfnd = false;
+    int jk1 = k1_1, jp1 = 0, jp2 = 0;
+    if ((vz2(jk2) < vz1(k1_1)) && l_sp) { vf2_[jk2 - 1] = (float)vf1(k1_1); l_do_interp = false; lfnd = true; }
+    while ((!lfnd) && l_do_interp) {
+      if (jk1 == k1_n) break;
+      if ((vz2(jk2) > vz1(jk1)) && (vz2(jk2) <= vz1(jk1 + 1))) {
+        const int jk1e = jk1 + 2 - k1_1 + 1;
+        jp1 = jk1e; jp2 = jk1e + 1; lfnd = true;
+      } else {
+        if (vz2(jk2) == vz1(jk1)) { vf2_[jk2 - 1] = (float)vf1(jk1); l_do_interp = false; break; }
+        else if (vz2(jk2) == vz1(jk1 + 1)) { vf2_[jk2 - 1] = (float)vf1(jk1 + 1); l_do_interp = false; break; }
+      }
+      jk1 = jk1 + 1;
+    }
+    if (!lfnd) {
+      l_do_interp = false;
+      if ((jk1 == k1_n) && l_bp) vf2_[jk2 - 1] = (float)vf1(k1_n);
+    }
+    if (l_do_interp) {
+      double a0 = vf1e[jp1];
+      double a1 = vslp[jp1];
+      double dz = 1.f / (vz1e[jp2] - vz1e[jp1]);                       // REAL(4) quotient stored in a REAL(8)
+      double dz2 = dz * dz;
+      double a2 = ((double)(3 * (vf1e[jp2] - vf1e[jp1])) * dz - (double)(2 * vslp[jp1]) - (double)vslp[jp2]) * dz;
+      double a3 = (double)(vslp[jp1] + vslp[jp2] - 2 * (vf1e[jp2] - vf1e[jp1]) / (vz1e[jp2] - vz1e[jp1])) * dz2;
+      dz = vz2(jk2) - (double)vz1e[jp1];
+      dz2 = dz * dz;
+      vf2_[jk2 - 1] = (float)(a0 + a1 * dz + a2 * dz2 + a3 * dz2 * dz);
+    }
+  }
+  return 0;
+}
+
+// the generic-coordinate branch of INTERP_3D (src/mod_interp.f90:374-438): per target column, AKIMA_1D_1D between the
+// source depths carried to the target grid and the target depths, sigma columns flipped, persistence below the last
+// level the source reaches.  The reference flips its work arrays in place (and leaves them flipped for masked
+// columns); here the inputs are left untouched and only data3d_trg is produced.  Returns the worst column status.
+int interp3d_sigma(int ni, int nj, int nk_src, const float* depth_src, const float* data3d_tmp, int nk_trg, const float* depth_trg,
+                   const int32_t* mask_trg, bool lmout, bool src_sigma, bool trg_sigma, float* data3d_trg) {
+  const int64_t n = (int64_t)ni * nj;
+  int worst = 0;
+  std::vector<double> zs(nk_src), fs(nk_src), zt(nk_trg);
+  std::vector<float> t(nk_trg);
+  for (int64_t p = 0; p < n; p++) {
+    for (int k = 0; k < nk_src; k++) {
+      const int kk = src_sigma ? nk_src - 1 - k : k;   // FLIP_UD
+      zs[k] = (double)depth_src[p + (int64_t)kk * n];
+      fs[k] = (double)data3d_tmp[p + (int64_t)kk * n];
+    }
+    for (int k = 0; k < nk_trg; k++) zt[k] = (double)depth_trg[p + (int64_t)(trg_sigma ? nk_trg - 1 - k : k) * n];
+    float zmax_src = (float)zs[0], zmax_trg = (float)zt[0];
+    for (int k = 1; k < nk_src; k++) if ((float)zs[k] > zmax_src) zmax_src = (float)zs[k];
+    for (int k = 1; k < nk_trg; k++) if ((float)zt[k] > zmax_trg) zmax_trg = (float)zt[k];
+    int jklast;
+    if (zmax_trg > zmax_src) {
+      jklast = 1;
+      while (jklast < nk_trg) {
+        if ((float)zt[jklast] > zmax_src) break;   // depth_trg(ji,jj,jklast+1)
+        jklast = jklast + 1;
+      }
+    } else jklast = nk_trg;
+    if ((!lmout) || (mask_trg[p] == 1)) {
+      int nlev;
+      if (lmout) {
+        nlev = 1;
+        for (int jk = 1; jk <= nk_trg; jk++) if (mask_trg[p + (int64_t)(jk - 1) * n] == 1) nlev = nlev + 1;
+        nlev = nlev - 1;
+      } else nlev = jklast;
+      for (int k = 0; k < nk_trg; k++) t[k] = data3d_trg[p + (int64_t)k * n];
+      int st = akima_1d_1d(nk_src, zs.data(), fs.data(), nlev, zt.data(), t.data(), false, 0.0, false, false);
+      if (st < worst) worst = st;
+      if ((jklast > 0) && (jklast < nk_trg))
+        for (int jk = jklast + 1; jk <= nk_trg; jk++) t[jk - 1] = t[jklast - 1];
+      if (trg_sigma) std::reverse(t.begin(), t.end());
+      for (int k = 0; k < nk_trg; k++) data3d_trg[p + (int64_t)k * n] = t[k];
+    }
+  }
+  return worst;
+}
+
 }  // namespace orc
 
 extern "C" {
+
+// AKIMA_1D_1D over ncol columns; element (column c, level k) of an array at base[c*cs + k*ks].  status (ncol) may be NULL.
+int orc_akima_1d_1d(int64_t ncol, int nk1, const double* vz1, int64_t z1cs, int64_t z1ks, const double* vf1, int64_t f1cs, int64_t f1ks,
+                    int nk2, const double* vz2, int64_t z2cs, int64_t z2ks, float* vf2, int64_t f2cs, int64_t f2ks, int has_rmask,
+                    double rmask_val, int l_surf_persist, int l_botm_persist, int32_t* status) {
+  int worst = 0;
+  std::vector<double> a(nk1), b(nk1), c(nk2);
+  std::vector<float> o(nk2);
+  for (int64_t q = 0; q < ncol; q++) {
+    for (int k = 0; k < nk1; k++) { a[k] = vz1[q * z1cs + k * z1ks]; b[k] = vf1[q * f1cs + k * f1ks]; }
+    for (int k = 0; k < nk2; k++) c[k] = vz2[q * z2cs + k * z2ks];
+    int st = orc::akima_1d_1d(nk1, a.data(), b.data(), nk2, c.data(), o.data(), has_rmask != 0, rmask_val, l_surf_persist != 0, l_botm_persist != 0);
+    for (int k = 0; k < nk2; k++) vf2[q * f2cs + k * f2ks] = o[k];
+    if (status) status[q] = st;
+    if (st < worst) worst = st;
+  }
+  return worst;
+}
+
+int orc_interp3d_sigma(int ni, int nj, int nk_src, const float* depth_src, const float* data3d_tmp, int nk_trg, const float* depth_trg,
+                       const int32_t* mask_trg, int lmout, int src_sigma, int trg_sigma, float* data3d_trg) {
+  return orc::interp3d_sigma(ni, nj, nk_src, depth_src, data3d_tmp, nk_trg, depth_trg, mask_trg, lmout != 0, src_sigma != 0, trg_sigma != 0, data3d_trg);
+}
 
 void orc_akima_1d_3d(int nx, int ny, int nk1, const float* vz1, const float* xf1, int nk2, const float* vz2, float* xf2, float rfill_val) {
   orc::akima_1d_3d(nx, ny, nk1, vz1, xf1, nk2, vz2, xf2, rfill_val);

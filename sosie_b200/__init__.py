@@ -43,6 +43,7 @@ EXPORTS = [
     "sosie_akima_1d_3d", "sosie_akima_1d_3d_dev", "sosie_lbc_lnk", "sosie_lbc_lnk_dev", "sosie_interp3d_post", "sosie_interp3d_post_dev",
     "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
     "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev", "sosie_bilin_get_map_dev", "sosie_bilin_load_map_dev",
+    "sosie_akima_1d_1d", "sosie_akima_1d_1d_dev", "sosie_interp3d_sigma", "sosie_interp3d_sigma_dev",
 ]
 
 _lib = None
@@ -422,6 +423,50 @@ class Sosie:
     def akima_1d_3d_dev(self, nx, ny, vz1, dxf1, vz2, dxf2, rfill_val=-9999.0):
         vz1, vz2 = _f32(vz1), _f32(vz2)
         self._ck(self._lib.sosie_akima_1d_3d_dev(self._h, nx, ny, vz1.size, _p(vz1), _dp(dxf1), vz2.size, _p(vz2), _dp(dxf2), C.c_float(rfill_val)))
+
+    def akima_1d_1d(self, vz1, vf1, vz2, rmask_val=None, l_surf_persist=False, l_botm_persist=False):
+        """AKIMA_1D_1D(vz1, vf1, vz2, vf2, rmask_val, l_surf_persist, l_botm_persist), src/mod_akima_1d.f90:26-232, over columns:
+        vz1 (nk1,) shared or (ncol, nk1); vf1 (ncol, nk1); vz2 (nk2,) shared or (ncol, nk2) -> (vf2 (ncol, nk2) f32, status (ncol,)).
+        Raises SosieError on columns for which the reference is undefined (status still reports which)."""
+        vf1 = np.atleast_2d(_f64(vf1))
+        ncol, nk1 = vf1.shape
+        vz1, vz2 = _f64(vz1), _f64(vz2)
+        nk2 = vz2.shape[-1]
+        vf2 = np.empty((ncol, nk2), np.float32)
+        status = np.zeros(ncol, np.int32)
+        i64 = C.c_int64
+        rc = self._lib.sosie_akima_1d_1d(self._h, i64(ncol), nk1, _p(vz1), i64(nk1 if vz1.ndim == 2 else 0), i64(1), _p(vf1), i64(nk1), i64(1),
+                                         nk2, _p(vz2), i64(nk2 if vz2.ndim == 2 else 0), i64(1), _p(vf2), i64(nk2), i64(1),
+                                         int(rmask_val is not None), C.c_double(0.0 if rmask_val is None else rmask_val),
+                                         int(l_surf_persist), int(l_botm_persist), _p(status))
+        self.last_status = status
+        self.last_vf2 = vf2
+        self._ck(rc)
+        return vf2, status
+
+    def akima_1d_1d_dev(self, ncol, nk1, dvz1, z1s, dvf1, f1s, nk2, dvz2, z2s, dvf2, f2s, rmask_val=None, l_surf_persist=False,
+                        l_botm_persist=False, dstatus=None):
+        """device arrays (f64 in, f32 out); each *s = (column stride, level stride) in elements"""
+        i64 = C.c_int64
+        self._ck(self._lib.sosie_akima_1d_1d_dev(self._h, i64(ncol), int(nk1), _dp(dvz1), i64(z1s[0]), i64(z1s[1]), _dp(dvf1), i64(f1s[0]), i64(f1s[1]),
+                                                 int(nk2), _dp(dvz2), i64(z2s[0]), i64(z2s[1]), _dp(dvf2), i64(f2s[0]), i64(f2s[1]),
+                                                 int(rmask_val is not None), C.c_double(0.0 if rmask_val is None else rmask_val),
+                                                 int(l_surf_persist), int(l_botm_persist), _dp(dstatus)))
+
+    def interp3d_sigma(self, depth_src, data3d_tmp, depth_trg, data3d_trg, mask_trg=None, lmout=False, src_sigma=False, trg_sigma=False):
+        """generic-coordinate branch of INTERP_3D (src/mod_interp.f90:374-438): cubes (nk, nj, ni); returns the new data3d_trg"""
+        depth_src, data3d_tmp, depth_trg = _f32(depth_src), _f32(data3d_tmp), _f32(depth_trg)
+        out = _f32(data3d_trg).copy()
+        nk_src, nj, ni = data3d_tmp.shape
+        nk_trg = depth_trg.shape[0]
+        m = None if mask_trg is None else _i32(mask_trg)
+        self._ck(self._lib.sosie_interp3d_sigma(self._h, ni, nj, nk_src, _p(depth_src), _p(data3d_tmp), nk_trg, _p(depth_trg), _p(m), int(lmout),
+                                                int(src_sigma), int(trg_sigma), _p(out)))
+        return out
+
+    def interp3d_sigma_dev(self, ni, nj, nk_src, ddepth_src, ddata3d_tmp, nk_trg, ddepth_trg, dmask_trg, lmout, src_sigma, trg_sigma, ddata3d_trg):
+        self._ck(self._lib.sosie_interp3d_sigma_dev(self._h, int(ni), int(nj), int(nk_src), _dp(ddepth_src), _dp(ddata3d_tmp), int(nk_trg),
+                                                    _dp(ddepth_trg), _dp(dmask_trg), int(lmout), int(src_sigma), int(trg_sigma), _dp(ddata3d_trg)))
 
     def lbc_lnk(self, nperio, X, cd_type="T", psgn=1.0, pval=None):
         """lbc_lnk(nperio, pt2d, cd_type, psgn [, pval]) on slabs X (nslab, jpj, jpi), src/mod_nemotools.f90:65"""

@@ -583,6 +583,78 @@ int sosie_akima_1d_3d(sosie_ctx* c, int32_t nx, int32_t ny, int32_t nk1, const f
   return SOSIE_OK;
 }
 
+int sosie_akima_1d_1d_dev(sosie_ctx* c, int64_t ncol, int32_t nk1, const double* dvz1, int64_t vz1_cs, int64_t vz1_ks, const double* dvf1,
+                          int64_t vf1_cs, int64_t vf1_ks, int32_t nk2, const double* dvz2, int64_t vz2_cs, int64_t vz2_ks, float* dvf2,
+                          int64_t vf2_cs, int64_t vf2_ks, int32_t has_rmask, double rmask_val, int32_t l_surf_persist, int32_t l_botm_persist,
+                          int32_t* dstatus) {
+  NEED(c);
+  if (vz1_cs < 0 || vz1_ks < 0 || vf1_cs < 0 || vf1_ks < 0 || vz2_cs < 0 || vz2_ks < 0 || vf2_cs < 0 || vf2_ks < 0) {
+    ctx->err = "sosie_akima_1d_1d: negative stride"; return SOSIE_ERR_ARG;
+  }
+  return akima_1d_1d_impl(ctx, ncol, nk1, dvz1, vz1_cs, vz1_ks, dvf1, vf1_cs, vf1_ks, nk2, dvz2, vz2_cs, vz2_ks, dvf2, vf2_cs, vf2_ks, has_rmask,
+                          rmask_val, l_surf_persist, l_botm_persist, dstatus);
+}
+
+int sosie_akima_1d_1d(sosie_ctx* c, int64_t ncol, int32_t nk1, const double* vz1, int64_t vz1_cs, int64_t vz1_ks, const double* vf1,
+                      int64_t vf1_cs, int64_t vf1_ks, int32_t nk2, const double* vz2, int64_t vz2_cs, int64_t vz2_ks, float* vf2, int64_t vf2_cs,
+                      int64_t vf2_ks, int32_t has_rmask, double rmask_val, int32_t l_surf_persist, int32_t l_botm_persist, int32_t* status) {
+  NEED(c);
+  if (ncol < 1 || nk1 < 1 || nk2 < 1 || !vz1 || !vf1 || !vz2 || !vf2 || vz1_cs < 0 || vz1_ks < 0 || vf1_cs < 0 || vf1_ks < 0 || vz2_cs < 0 ||
+      vz2_ks < 0 || vf2_cs < 0 || vf2_ks < 0) { ctx->err = "sosie_akima_1d_1d: bad arguments"; return SOSIE_ERR_ARG; }
+  auto extent = [&](int64_t cs, int64_t ks, int nk) { return (size_t)((ncol - 1) * cs + (int64_t)(nk - 1) * ks + 1); };
+  const size_t e1 = extent(vz1_cs, vz1_ks, nk1), e2 = extent(vf1_cs, vf1_ks, nk1), e3 = extent(vz2_cs, vz2_ks, nk2), e4 = extent(vf2_cs, vf2_ks, nk2);
+  cudaStream_t st = ctx->stream;
+  CK(ctx->v_d1.alloc(e1)); CK(ctx->v_d2.alloc(e2)); CK(ctx->v_d3.alloc(e3)); CK(ctx->v_out.alloc(e4));
+  if (status) CK(ctx->v_mask.alloc((size_t)ncol));
+  CK(cudaMemcpyAsync(ctx->v_d1.p, vz1, e1 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->v_d2.p, vf1, e2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->v_d3.p, vz2, e3 * sizeof(double), cudaMemcpyHostToDevice, st));
+  // strided outputs: elements of vf2 outside the columns keep the caller's values
+  if (!(vf2_ks == 1 && vf2_cs == nk2) && !(vf2_cs == 1 && vf2_ks == ncol)) CK(cudaMemcpyAsync(ctx->v_out.p, vf2, e4 * sizeof(float), cudaMemcpyHostToDevice, st));
+  int rc = akima_1d_1d_impl(ctx, ncol, nk1, ctx->v_d1.p, vz1_cs, vz1_ks, ctx->v_d2.p, vf1_cs, vf1_ks, nk2, ctx->v_d3.p, vz2_cs, vz2_ks, ctx->v_out.p,
+                            vf2_cs, vf2_ks, has_rmask, rmask_val, l_surf_persist, l_botm_persist, status ? ctx->v_mask.p : nullptr);
+  if (rc != SOSIE_OK && rc != SOSIE_ERR_REF_STOP) return rc;
+  CK(cudaMemcpyAsync(vf2, ctx->v_out.p, e4 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (status) CK(cudaMemcpyAsync(status, ctx->v_mask.p, (size_t)ncol * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return rc;
+}
+
+int sosie_interp3d_sigma_dev(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk_src, const float* ddepth_src, const float* ddata3d_tmp,
+                             int32_t nk_trg, const float* ddepth_trg, const int32_t* dmask_trg, int32_t lmout, int32_t src_is_sigma,
+                             int32_t trg_is_sigma, float* ddata3d_trg) {
+  NEED(c);
+  return interp3d_sigma_impl(ctx, ni, nj, nk_src, ddepth_src, ddata3d_tmp, nk_trg, ddepth_trg, dmask_trg, lmout, src_is_sigma, trg_is_sigma,
+                             ddata3d_trg);
+}
+
+int sosie_interp3d_sigma(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk_src, const float* depth_src, const float* data3d_tmp, int32_t nk_trg,
+                         const float* depth_trg, const int32_t* mask_trg, int32_t lmout, int32_t src_is_sigma, int32_t trg_is_sigma,
+                         float* data3d_trg) {
+  NEED(c);
+  if (ni < 1 || nj < 1 || nk_src < 1 || nk_trg < 1 || !depth_src || !data3d_tmp || !depth_trg || !data3d_trg || (lmout && !mask_trg)) {
+    ctx->err = "sosie_interp3d_sigma: bad arguments"; return SOSIE_ERR_ARG;
+  }
+  const size_t n = (size_t)ni * nj;
+  cudaStream_t st = ctx->stream;
+  CK(ctx->v_f1.alloc(n * nk_src)); CK(ctx->v_f2.alloc(n * nk_src)); CK(ctx->v_f3.alloc(n * nk_trg)); CK(ctx->v_out.alloc(n * nk_trg));
+  CK(cudaMemcpyAsync(ctx->v_f1.p, depth_src, n * nk_src * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->v_f2.p, data3d_tmp, n * nk_src * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->v_f3.p, depth_trg, n * nk_trg * sizeof(float), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->v_out.p, data3d_trg, n * nk_trg * sizeof(float), cudaMemcpyHostToDevice, st));
+  const int32_t* dm = nullptr;
+  if (mask_trg) {
+    CK(ctx->v_mask.alloc(n * nk_trg));
+    CK(cudaMemcpyAsync(ctx->v_mask.p, mask_trg, n * nk_trg * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    dm = ctx->v_mask.p;
+  }
+  if (int rc = interp3d_sigma_impl(ctx, ni, nj, nk_src, ctx->v_f1.p, ctx->v_f2.p, nk_trg, ctx->v_f3.p, dm, lmout, src_is_sigma, trg_is_sigma,
+                                   ctx->v_out.p)) return rc;
+  CK(cudaMemcpyAsync(data3d_trg, ctx->v_out.p, n * nk_trg * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
 int sosie_lbc_lnk_dev(sosie_ctx* c, int32_t nperio, int32_t jpi, int32_t jpj, int32_t nslab, float* dX, int32_t cd_type, double psgn,
                       int32_t has_pval, double pval) {
   NEED(c);

@@ -150,7 +150,8 @@ struct sosie_ctx {
 
   // ---- vertical stage (vert.cu)
   DBuf<float> v_vze, v_vz2, v_in, v_out;
-  DBuf<double> v_ang;
+  DBuf<double> v_ang, v_d1, v_d2, v_d3;
+  DBuf<float> v_f1, v_f2, v_f3;
   DBuf<int32_t> v_plan, v_mask;
 
   // ---- drown work buffers
@@ -271,6 +272,11 @@ int drown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, c
                int32_t* nsweeps_host);
 int akima_1d_3d_impl(sosie_ctx* ctx, int nx, int ny, int nk1, const float* vz1_host, const float* dxf1, int nk2, const float* vz2_host,
                      float* dxf2, float rfill_val);
+int akima_1d_1d_impl(sosie_ctx* ctx, long long ncol, int nk1, const double* vz1, long long z1cs, long long z1ks, const double* vf1, long long f1cs,
+                     long long f1ks, int nk2, const double* vz2, long long z2cs, long long z2ks, float* vf2, long long f2cs, long long f2ks,
+                     int has_rmask, double rmask_val, int l_sp, int l_bp, int32_t* dstatus);
+int interp3d_sigma_impl(sosie_ctx* ctx, int ni, int nj, int nk_src, const float* ddepth_src, const float* ddata3d_tmp, int nk_trg,
+                        const float* ddepth_trg, const int32_t* dmask_trg, int lmout, int src_sigma, int trg_sigma, float* ddata3d_trg);
 int lbc_lnk_impl(sosie_ctx* ctx, int nperio, int jpi, int jpj, int nslab, float* dX, int cd_type, double psgn, int has_pval, double pval);
 int interp3d_post_impl(sosie_ctx* ctx, int ni, int nj, int nk, float* dX, const int32_t* dmask_trg, int ixtrpl_bot, float vmin, float vmax,
                        float rmiss_val, int i_orca_trg, int c_orca_trg, int lmout);

@@ -172,6 +172,216 @@ int akima_1d_3d_impl(sosie_ctx* ctx, int nx, int ny, int nk1, const float* vz1_h
 }
 
 // ---------------------------------------------------------------------------------------------------
+// AKIMA_1D_1D (src/mod_akima_1d.f90:26-232): the per-column variant, used by the generic-coordinate (sigma) branch of
+// INTERP_3D (src/mod_interp.f90:374-438) and by interp_to_hydro_section (:628-629).  One thread per column.  As for the
+// cube variant nothing is materialised: the four frame depths / values of the REAL(4) extended arrays are computed once
+// per column, the six values and five divided differences a target level needs are rebuilt at its interval.
+// The scan for the interval is the reference's (first match from k1_1 upwards, no monotonicity assumed on vz2).
+template <class T>
+struct ColView {      // element k (1-based, in the possibly flipped frame) of one column
+  const T* p;
+  long long ks;
+  int n;
+  int flip;
+  __device__ __forceinline__ double at(int k) const { const int kk = flip ? n + 1 - k : k; return (double)p[(long long)(kk - 1) * ks]; }
+};
+
+__device__ __forceinline__ void ak11_extra(float xa, float xb, float xc, float xd, float xe, float ya, float yb, float yc, float* y4, float* y5) {
+  // extra_2_east_r4(x1..x5, y1..y3) and, with the arguments reversed by the caller, extra_2_west_r4 (src/mod_manip.f90:571-587, 634-649)
+  const float A = xb - xa, B = xc - xb, C = xd - xc, D = xe - xd, ALF = yb - ya, BET = yc - yb;
+  if ((A == 0.f) || (B == 0.f) || (C == 0.f)) { *y4 = yc; *y5 = yc; return; }
+  const float v4 = C * (2.f * BET / B - ALF / A) + yc;
+  *y4 = v4;
+  *y5 = v4 + v4 * D / C + BET * D / B - ALF * D / A - yc * D / C;
+}
+
+// returns the column status (0 done, 1 all missing, -1 / -2 undefined in the reference: see include/sosie_b200.h)
+template <class T>
+__device__ int ak11_column(const ColView<T>& z1, const ColView<T>& f1, int nk1, const ColView<T>& z2, int nk2, float* out, long long oks,
+                           bool has_rmv, double rmv, bool l_sp, bool l_bp) {
+  for (int k = 0; k < nk2; k++) out[(long long)k * oks] = -6666.0f;
+  int nz1 = nk1, k1_1 = 1, k1_n = nk1;
+  if (has_rmv) {
+    int nmissv = 0, first0 = 0;
+    for (int k = 1; k <= nk1; k++) { const bool m = (f1.at(k) == rmv); nmissv += m; if (!m && !first0) first0 = k; }
+    if (!(nmissv < nk1)) return 1;
+    if (nmissv > 0) {
+      k1_1 = first0;
+      int f = 0;
+      for (int k = k1_1; k <= nk1; k++) if (f1.at(k) == rmv) { f = k - k1_1 + 1; break; }
+      k1_n = f + k1_1 - 2;
+      nz1 = nk1 - nmissv;
+      if (k1_n - k1_1 + 1 != nz1) return -1;
+    }
+  }
+  if (nz1 < 3) return -2;
+  const int nk1e = nz1 + 4;
+  auto zi = [&](int i) { return (float)z1.at(k1_1 + i - 3); };   // interior of vz1e / vf1e, i = 3 .. nz1+2
+  auto fi = [&](int i) { return (float)f1.at(k1_1 + i - 3); };
+  float zb2, zb1, zt1, zt2, fb2, fb1, ft1, ft2;                    // vz1e(2), vz1e(1), vz1e(nk1e-1), vz1e(nk1e); same for vf1e
+  {
+    const float z3 = zi(3), z4 = zi(4), z5 = zi(5);
+    zb2 = z4 - (z5 - z3);
+    zb1 = z3 - (z5 - z3);
+    const float za = zi(nk1e - 4), zb = zi(nk1e - 3), zc = zi(nk1e - 2);
+    zt1 = zb + zc - za;
+    zt2 = zc + zc - za;
+    ak11_extra(z5, z4, z3, zb2, zb1, fi(5), fi(4), fi(3), &fb2, &fb1);
+    ak11_extra(za, zb, zc, zt1, zt2, fi(nk1e - 4), fi(nk1e - 3), fi(nk1e - 2), &ft1, &ft2);
+  }
+  auto ze = [&](int i) { return i <= 2 ? (i == 2 ? zb2 : zb1) : (i >= nk1e - 1 ? (i == nk1e ? zt2 : zt1) : zi(i)); };
+  auto fe = [&](int i) { return i <= 2 ? (i == 2 ? fb2 : fb1) : (i >= nk1e - 1 ? (i == nk1e ? ft2 : ft1) : fi(i)); };
+  const double z1_first = z1.at(k1_1);
+  for (int jk2 = 1; jk2 <= nk2; jk2++) {
+    const double zt = z2.at(jk2);
+    float* o = out + (long long)(jk2 - 1) * oks;
+    bool l_do_interp = true, lfnd = false;
+    int jk1 = k1_1, jp1 = 0;
+    if ((zt < z1_first) && l_sp) { *o = (float)f1.at(k1_1); l_do_interp = false; lfnd = true; }
+    if (!lfnd) {
+      double za = z1_first;
+      while (true) {
+        if (jk1 == k1_n) break;
+        const double zb = z1.at(jk1 + 1);
+        if ((zt > za) && (zt <= zb)) { jp1 = jk1 + 2 - k1_1 + 1; lfnd = true; break; }
+        if (zt == za) { *o = (float)f1.at(jk1); l_do_interp = false; break; }
+        if (zt == zb) { *o = (float)f1.at(jk1 + 1); l_do_interp = false; break; }
+        jk1 = jk1 + 1;
+        za = zb;
+      }
+    }
+    if (!lfnd) {
+      l_do_interp = false;
+      if ((jk1 == k1_n) && l_bp) *o = (float)f1.at(k1_n);
+    }
+    if (!l_do_interp) continue;
+    const int jp2 = jp1 + 1;
+    float z[6], f[6], d[5];
+#pragma unroll
+    for (int q = 0; q < 6; q++) { z[q] = ze(jp1 - 2 + q); f[q] = fe(jp1 - 2 + q); }
+#pragma unroll
+    for (int q = 0; q < 5; q++) d[q] = (f[q + 1] - f[q]) / (z[q + 1] - z[q]);
+    const float s1 = ak1_slope(d[0], d[1], d[2], d[3]);   // vslp(jp1): the generic branch of slopes_1d (3 <= jp1, jp2 <= nk1e-2)
+    const float s2 = ak1_slope(d[1], d[2], d[3], d[4]);   // vslp(jp2)
+    const float df = f[3] - f[2], dv = z[3] - z[2];
+    const double a0 = (double)f[2], a1 = (double)s1;
+    double dz = (double)(1.f / dv), dz2 = dz * dz;
+    const double a2 = ((double)(3.f * df) * dz - (double)(2.f * s1) - (double)s2) * dz;
+    const double a3 = (double)(s1 + s2 - 2.f * df / dv) * dz2;
+    dz = zt - (double)z[2];
+    dz2 = dz * dz;
+    *o = (float)(a0 + a1 * dz + a2 * dz2 + a3 * dz2 * dz);
+    (void)jp2;
+  }
+  return 0;
+}
+
+template <class T>
+__global__ void __launch_bounds__(128)
+k_ak11_cols(long long ncol, int nk1, const T* vz1, long long z1cs, long long z1ks, const T* vf1, long long f1cs, long long f1ks, int nk2,
+            const T* vz2, long long z2cs, long long z2ks, float* vf2, long long f2cs, long long f2ks, int has_rmv, double rmv, int l_sp,
+            int l_bp, int* worst, int32_t* status) {
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < ncol; c += (long long)gridDim.x * blockDim.x) {
+    ColView<T> z1{vz1 + c * z1cs, z1ks, nk1, 0}, f1{vf1 + c * f1cs, f1ks, nk1, 0}, z2{vz2 + c * z2cs, z2ks, nk2, 0};
+    const int st = ak11_column(z1, f1, nk1, z2, nk2, vf2 + c * f2cs, f2ks, has_rmv != 0, rmv, l_sp != 0, l_bp != 0);
+    if (status) status[c] = st;
+    if (st < 0) atomicMin(worst, st);
+  }
+}
+
+// the generic-coordinate branch of INTERP_3D (src/mod_interp.f90:374-438), one thread per target column; the
+// reference's in-place flips of its work arrays become index reversals, the inputs are not modified
+__global__ void __launch_bounds__(128)
+k_i3d_sigma(long long n, int nk_src, const float* __restrict__ depth_src, const float* __restrict__ data3d_tmp, int nk_trg,
+            const float* __restrict__ depth_trg, const int32_t* __restrict__ mask_trg, int lmout, int src_sigma, int trg_sigma,
+            float* data3d_trg, int* worst) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
+    ColView<float> zs{depth_src + p, n, nk_src, src_sigma}, fs{data3d_tmp + p, n, nk_src, src_sigma}, zt{depth_trg + p, n, nk_trg, trg_sigma};
+    float zmax_src = depth_src[p], zmax_trg = depth_trg[p];
+    for (int k = 1; k < nk_src; k++) zmax_src = fmaxf(zmax_src, depth_src[p + (long long)k * n]);
+    for (int k = 1; k < nk_trg; k++) zmax_trg = fmaxf(zmax_trg, depth_trg[p + (long long)k * n]);
+    int jklast;
+    if (zmax_trg > zmax_src) {
+      jklast = 1;
+      while (jklast < nk_trg) {
+        if ((float)zt.at(jklast + 1) > zmax_src) break;
+        jklast = jklast + 1;
+      }
+    } else jklast = nk_trg;
+    if (lmout && mask_trg[p] != 1) continue;
+    int nlev = jklast;
+    if (lmout) {
+      nlev = 0;
+      for (int jk = 0; jk < nk_trg; jk++) nlev += (mask_trg[p + (long long)jk * n] == 1);
+    }
+    float* col = data3d_trg + p;
+    zt.n = nk_trg;   // the flip is of the WHOLE column; only the first nlev levels of the flipped column are targets
+    const int st = ak11_column(zs, fs, nk_src, zt, nlev, col, n, false, 0.0, false, false);
+    if (st < 0) atomicMin(worst, st);
+    if ((jklast > 0) && (jklast < nk_trg)) {
+      const float v = col[(long long)(jklast - 1) * n];
+      for (int jk = jklast + 1; jk <= nk_trg; jk++) col[(long long)(jk - 1) * n] = v;
+    }
+    if (trg_sigma) {
+      for (int a = 0, b = nk_trg - 1; a < b; a++, b--) {
+        const float t = col[(long long)a * n];
+        col[(long long)a * n] = col[(long long)b * n];
+        col[(long long)b * n] = t;
+      }
+    }
+  }
+}
+
+static int ak11_status(sosie_ctx* ctx, int* dworst, const char* who) {
+  int hw = 0;
+  if (int rc = fetch_small(ctx, dworst, &hw, sizeof(int))) return rc;
+  if (hw == -1) {
+    ctx->err = std::string(who) + ": AKIMA_1D_1D: missing values are not confined to the ends of a column (array shapes mismatch in the reference)";
+    return SOSIE_ERR_REF_STOP;
+  }
+  if (hw == -2) { ctx->err = std::string(who) + ": AKIMA_1D_1D: a column has fewer than 3 valid source points (the reference reads unset elements)"; return SOSIE_ERR_REF_STOP; }
+  return SOSIE_OK;
+}
+
+template <class T>
+static int akima_1d_1d_launch(sosie_ctx* ctx, long long ncol, int nk1, const T* vz1, long long z1cs, long long z1ks, const T* vf1, long long f1cs,
+                              long long f1ks, int nk2, const T* vz2, long long z2cs, long long z2ks, float* vf2, long long f2cs, long long f2ks,
+                              int has_rmask, double rmask_val, int l_sp, int l_bp, int32_t* dstatus) {
+  cudaStream_t st = ctx->stream;
+  CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
+  int* dworst = ctx->d_iscratch.p;
+  CK(cudaMemsetAsync(dworst, 0, sizeof(int), st));
+  k_ak11_cols<T><<<grid_for(ctx, (size_t)ncol, 128), 128, 0, st>>>(ncol, nk1, vz1, z1cs, z1ks, vf1, f1cs, f1ks, nk2, vz2, z2cs, z2ks, vf2, f2cs,
+                                                                    f2ks, has_rmask, rmask_val, l_sp, l_bp, dworst, dstatus);
+  KLAUNCH_CHECK();
+  return ak11_status(ctx, dworst, "sosie_akima_1d_1d");
+}
+
+int akima_1d_1d_impl(sosie_ctx* ctx, long long ncol, int nk1, const double* vz1, long long z1cs, long long z1ks, const double* vf1, long long f1cs,
+                     long long f1ks, int nk2, const double* vz2, long long z2cs, long long z2ks, float* vf2, long long f2cs, long long f2ks,
+                     int has_rmask, double rmask_val, int l_sp, int l_bp, int32_t* dstatus) {
+  if (ncol < 1 || nk1 < 1 || nk2 < 1 || !vz1 || !vf1 || !vz2 || !vf2) { ctx->err = "sosie_akima_1d_1d: bad arguments"; return SOSIE_ERR_ARG; }
+  return akima_1d_1d_launch<double>(ctx, ncol, nk1, vz1, z1cs, z1ks, vf1, f1cs, f1ks, nk2, vz2, z2cs, z2ks, vf2, f2cs, f2ks, has_rmask, rmask_val,
+                                    l_sp, l_bp, dstatus);
+}
+
+int interp3d_sigma_impl(sosie_ctx* ctx, int ni, int nj, int nk_src, const float* ddepth_src, const float* ddata3d_tmp, int nk_trg,
+                        const float* ddepth_trg, const int32_t* dmask_trg, int lmout, int src_sigma, int trg_sigma, float* ddata3d_trg) {
+  if (ni < 1 || nj < 1 || nk_src < 1 || nk_trg < 1 || !ddepth_src || !ddata3d_tmp || !ddepth_trg || !ddata3d_trg || (lmout && !dmask_trg)) {
+    ctx->err = "sosie_interp3d_sigma: bad arguments"; return SOSIE_ERR_ARG;
+  }
+  cudaStream_t st = ctx->stream;
+  const long long n = (long long)ni * nj;
+  CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
+  int* dworst = ctx->d_iscratch.p;
+  CK(cudaMemsetAsync(dworst, 0, sizeof(int), st));
+  k_i3d_sigma<<<grid_for(ctx, (size_t)n, 128), 128, 0, st>>>(n, nk_src, ddepth_src, ddata3d_tmp, nk_trg, ddepth_trg, dmask_trg, lmout, src_sigma,
+                                                             trg_sigma, ddata3d_trg, dworst);
+  KLAUNCH_CHECK();
+  return ak11_status(ctx, dworst, "sosie_interp3d_sigma");
+}
+
+// ---------------------------------------------------------------------------------------------------
 // lbc_lnk (REAL(4) variant: through REAL(8), src/mod_nemotools.f90:154-190): one block per slab executes the
 // statements of lbc_lnk_2d_r8 / lbc_nfd_2d in order.  Loops that copy between different rows (or columns) are
 // parallel; loops that read and write the SAME row are replayed by one thread in the reference's index order (the

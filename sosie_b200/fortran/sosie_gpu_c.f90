@@ -132,6 +132,29 @@ MODULE SOSIE_GPU_C
          REAL(C_FLOAT), INTENT(out) :: xf2(*)
          REAL(C_FLOAT), VALUE  :: rfill_val
       END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_akima_1d_1d(ctx, ncol, nk1, vz1, vz1_cs, vz1_ks, vf1, vf1_cs, vf1_ks, nk2, vz2, vz2_cs, vz2_ks, &
+         &                                      vf2, vf2_cs, vf2_ks, has_rmask, rmask_val, l_surf_persist, l_botm_persist, status) &
+         &                                      BIND(C, name='sosie_akima_1d_1d')
+         !! AKIMA_1D_1D (src/mod_akima_1d.f90:26) over ncol columns; element (c,k), 0-based, of an array at base(1 + c*cs + k*ks)
+         IMPORT :: C_PTR, C_INT, C_INT64_T, C_FLOAT, C_DOUBLE
+         TYPE(C_PTR), VALUE       :: ctx
+         INTEGER(C_INT64_T), VALUE :: ncol, vz1_cs, vz1_ks, vf1_cs, vf1_ks, vz2_cs, vz2_ks, vf2_cs, vf2_ks
+         INTEGER(C_INT), VALUE    :: nk1, nk2, has_rmask, l_surf_persist, l_botm_persist
+         REAL(C_DOUBLE), INTENT(in) :: vz1(*), vf1(*), vz2(*)
+         REAL(C_FLOAT)            :: vf2(*)
+         REAL(C_DOUBLE), VALUE    :: rmask_val
+         TYPE(C_PTR), VALUE       :: status    !! C_NULL_PTR or C_LOC of an INTEGER(4) (ncol) array
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_interp3d_sigma(ctx, ni, nj, nk_src, depth_src, data3d_tmp, nk_trg, depth_trg, mask_trg, lmout, &
+         &                                         src_is_sigma, trg_is_sigma, data3d_trg) BIND(C, name='sosie_interp3d_sigma')
+         !! the z <-> sigma branch of INTERP_3D (src/mod_interp.f90:374-438), all target columns in one call
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: ni, nj, nk_src, nk_trg, lmout, src_is_sigma, trg_is_sigma
+         REAL(C_FLOAT), INTENT(in) :: depth_src(*), data3d_tmp(*), depth_trg(*)
+         TYPE(C_PTR), VALUE    :: mask_trg     !! C_LOC of INTEGER(4) (ni,nj,nk_trg), or C_NULL_PTR when .NOT. lmout
+         REAL(C_FLOAT)         :: data3d_trg(*)
+      END FUNCTION
       INTEGER(C_INT) FUNCTION sosie_lbc_lnk(ctx, nperio, jpi, jpj, nslab, X, cd_type, psgn, has_pval, pval) BIND(C, name='sosie_lbc_lnk')
          !! lbc_lnk (src/mod_nemotools.f90:65) on nslab REAL(4) slabs; cd_type = ICHAR('T'), ...
          IMPORT :: C_PTR, C_INT, C_FLOAT, C_DOUBLE

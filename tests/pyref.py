@@ -701,3 +701,125 @@ def angle2_np(nperio, lamt, phit, lamu, phiu, lamv, phiv, lamf, phif):
 def lbc_lnk_r8_py(nperio, X, cd_type, psgn, pval=None):
     """lbc_lnk_2d_r8 on a float64 array: same loops as lbc_lnk_py without the REAL(4) round trip."""
     return _lbc_core(nperio, np.asarray(X, np.float64), cd_type, psgn, pval)
+
+
+def akima_1d_1d_py(vz1, vf1, vz2, rmask_val=None, l_sp=False, l_bp=False):
+    """AKIMA_1D_1D, src/mod_akima_1d.f90:26-232 (+ slopes_1d :392-455, extra_2_west_r4 / extra_2_east_r4 of mod_manip.f90),
+    one column, Python loops on numpy scalars: 1-based arrays with a dummy element 0.  Returns (vf2 f32, status) with the
+    status convention of the oracle (0 ok, 1 all missing, -1 / -2 undefined in the reference)."""
+    f4, f8 = np.float32, np.float64
+    vz1 = np.concatenate([[0.0], np.asarray(vz1, f8)]); vf1 = np.concatenate([[0.0], np.asarray(vf1, f8)])
+    vz2 = np.concatenate([[0.0], np.asarray(vz2, f8)])
+    nk1, nk2 = vz1.size - 1, vz2.size - 1
+    vf2 = np.full(nk2 + 1, f4(-6666.0), f4)
+    nz1, k1_1, k1_n, nmissv = nk1, 1, nk1, 0
+    if rmask_val is not None:
+        imiss1 = np.zeros(nk1 + 1, np.int32)
+        imiss1[1:][vf1[1:] == f8(rmask_val)] = 1
+        nmissv = int(imiss1.sum())
+    if not nmissv < nk1:
+        return vf2[1:], 1
+    if nmissv > 0:
+        k1_1 = int(np.nonzero(imiss1[1:] == 0)[0][0]) + 1
+        w = np.nonzero(imiss1[k1_1:] == 1)[0]
+        k1_n = (int(w[0]) + 1 if w.size else 0) + k1_1 - 2
+        nz1 = nk1 - nmissv
+        if k1_n - k1_1 + 1 != nz1:
+            return vf2[1:], -1
+    if nz1 < 3:
+        return vf2[1:], -2
+    nk1e = nz1 + 4
+    ze = np.zeros(nk1e + 1, f4); fe = np.zeros(nk1e + 1, f4); sl = np.zeros(nk1e + 1, f4)
+    ze[3:nz1 + 3] = vz1[k1_1:k1_n + 1].astype(f4)
+    fe[3:nz1 + 3] = vf1[k1_1:k1_n + 1].astype(f4)
+    ze[2] = ze[4] - (ze[5] - ze[3])
+    ze[1] = ze[3] - (ze[5] - ze[3])
+    ze[nk1e - 1] = ze[nk1e - 3] + ze[nk1e - 2] - ze[nk1e - 4]
+    ze[nk1e] = ze[nk1e - 2] + ze[nk1e - 2] - ze[nk1e - 4]
+    two = f4(2)
+
+    def extra(xa, xb, xc, xd, xe, ya, yb, yc):   # same body for east (1..5) and west (5..1)
+        A = xb - xa; B = xc - xb; Cc = xd - xc; D = xe - xd
+        ALF = yb - ya; BET = yc - yb
+        if A == 0 or B == 0 or Cc == 0:
+            return yc, yc
+        y4 = Cc * (two * BET / B - ALF / A) + yc
+        y5 = y4 + y4 * D / Cc + BET * D / B - ALF * D / A - yc * D / Cc
+        return y4, y5
+    with np.errstate(all="ignore"):
+        fe[2], fe[1] = extra(ze[5], ze[4], ze[3], ze[2], ze[1], fe[5], fe[4], fe[3])
+        fe[nk1e - 1], fe[nk1e] = extra(ze[nk1e - 4], ze[nk1e - 3], ze[nk1e - 2], ze[nk1e - 1], ze[nk1e], fe[nk1e - 4], fe[nk1e - 3], fe[nk1e - 2])
+        nz = nk1e
+        for k in range(3, nz - 1):
+            m1 = (fe[k - 1] - fe[k - 2]) / (ze[k - 1] - ze[k - 2])
+            m2 = (fe[k] - fe[k - 1]) / (ze[k] - ze[k - 1])
+            m3 = (fe[k + 1] - fe[k]) / (ze[k + 1] - ze[k])
+            m4 = (fe[k + 2] - fe[k + 1]) / (ze[k + 2] - ze[k + 1])
+            if m1 == m2 and m3 == m4:
+                sl[k] = f4(0.5) * (m2 + m3)
+            else:
+                sl[k] = (abs(m4 - m3) * m2 + abs(m2 - m1) * m3) / (abs(m4 - m3) + abs(m2 - m1))
+        for jk2 in range(1, nk2 + 1):
+            do, fnd = True, False
+            jk1 = k1_1
+            if vz2[jk2] < vz1[k1_1] and l_sp:
+                vf2[jk2] = f4(vf1[k1_1]); do = False; fnd = True
+            while (not fnd) and do:
+                if jk1 == k1_n:
+                    break
+                if vz2[jk2] > vz1[jk1] and vz2[jk2] <= vz1[jk1 + 1]:
+                    jp1 = jk1 + 2 - k1_1 + 1; jp2 = jp1 + 1; fnd = True
+                elif vz2[jk2] == vz1[jk1]:
+                    vf2[jk2] = f4(vf1[jk1]); do = False
+                    break
+                elif vz2[jk2] == vz1[jk1 + 1]:
+                    vf2[jk2] = f4(vf1[jk1 + 1]); do = False
+                    break
+                jk1 += 1
+            if not fnd:
+                do = False
+                if jk1 == k1_n and l_bp:
+                    vf2[jk2] = f4(vf1[k1_n])
+            if do:
+                a0 = f8(fe[jp1]); a1 = f8(sl[jp1])
+                dz = f8(f4(1.0) / (ze[jp2] - ze[jp1])); dz2 = dz * dz
+                a2 = (f8(f4(3) * (fe[jp2] - fe[jp1])) * dz - f8(two * sl[jp1]) - f8(sl[jp2])) * dz
+                a3 = f8(sl[jp1] + sl[jp2] - two * (fe[jp2] - fe[jp1]) / (ze[jp2] - ze[jp1])) * dz2
+                dz = vz2[jk2] - f8(ze[jp1]); dz2 = dz * dz
+                vf2[jk2] = f4(a0 + a1 * dz + a2 * dz2 + a3 * dz2 * dz)
+    return vf2[1:], 0
+
+
+def interp3d_sigma_py(depth_src, data3d_tmp, depth_trg, data3d_trg, mask_trg=None, lmout=False, src_sigma=False, trg_sigma=False):
+    """generic-coordinate branch of INTERP_3D, src/mod_interp.f90:374-438 (inputs left untouched); cubes (nk, nj, ni)"""
+    f4 = np.float32
+    depth_src = np.asarray(depth_src, f4); data3d_tmp = np.asarray(data3d_tmp, f4); depth_trg = np.asarray(depth_trg, f4)
+    out = np.array(data3d_trg, f4)
+    nk_trg, nj, ni = depth_trg.shape
+    for jj in range(nj):
+        for ji in range(ni):
+            zs = depth_src[:, jj, ji]; fs = data3d_tmp[:, jj, ji]; zt = depth_trg[:, jj, ji]
+            if src_sigma:
+                zs = zs[::-1]; fs = fs[::-1]
+            if trg_sigma:
+                zt = zt[::-1]
+            zmax_src, zmax_trg = zs.max(), zt.max()
+            if zmax_trg > zmax_src:
+                jklast = 1
+                while jklast < nk_trg:
+                    if zt[jklast] > zmax_src:
+                        break
+                    jklast += 1
+            else:
+                jklast = nk_trg
+            if (not lmout) or mask_trg[0, jj, ji] == 1:
+                nlev = int((mask_trg[:, jj, ji] == 1).sum()) if lmout else jklast
+                t = out[:, jj, ji].copy()
+                v, _ = akima_1d_1d_py(zs.astype(np.float64), fs.astype(np.float64), zt[:nlev].astype(np.float64))
+                t[:nlev] = v
+                if 0 < jklast < nk_trg:
+                    t[jklast:] = t[jklast - 1]
+                if trg_sigma:
+                    t = t[::-1]
+                out[:, jj, ji] = t
+    return out

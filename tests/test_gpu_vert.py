@@ -152,3 +152,118 @@ def test_angle2_vs_oracle(gpu, orc):
             assert np.array_equal(np.isnan(a[q]), np.isnan(b[q])), (nperio, q)
             ok = ~np.isnan(a[q])
             assert np.array_equal(a[q][ok].view(np.uint64), b[q][ok].view(np.uint64)), (nperio, q, np.nanmax(np.abs(a[q] - b[q])))
+
+
+# ---- AKIMA_1D_1D (column variant) and the generic-coordinate branch of INTERP_3D
+def _columns(seed, ncol, nk1, nk2):
+    rng = np.random.default_rng(seed)
+    vz1 = np.cumsum(rng.uniform(3.0, 200.0, (ncol, nk1)), axis=1)
+    vf1 = 20.0 - 0.004 * vz1 + rng.normal(0.0, 0.5, (ncol, nk1))
+    vz2 = np.sort(rng.uniform(0.0, vz1.max() * 1.05, (ncol, nk2)), axis=1)
+    vz2[:, 1] = vz1[:, 0]
+    if nk1 > 3 and nk2 > 4:
+        vz2[:, 3] = vz1[:, 2]
+        vz2[:, 4] = vz1[:, 3].astype(np.float32).astype(np.float64) + 1e-9
+    return vz1, vf1, vz2
+
+
+@pytest.mark.parametrize("ncol,nk1,nk2", [(3000, 31, 75), (17, 3, 4), (500, 46, 12), (1, 8, 8)])
+@pytest.mark.parametrize("opts", [dict(), dict(l_surf_persist=True, l_botm_persist=True), dict(l_botm_persist=True)])
+def test_akima_1d_1d_vs_oracle(gpu, orc, ncol, nk1, nk2, opts):
+    vz1, vf1, vz2 = _columns(ncol + nk1, ncol, nk1, nk2)
+    vf1[::7] = 3.25                                          # flat columns: the equal-slope branch
+    a, sa = gpu.akima_1d_1d(vz1, vf1, vz2, **opts)
+    b, sb = orc.akima_1d_1d(vz1, vf1, vz2, **opts)
+    assert np.array_equal(sa, sb) and np.all(sa == 0)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{(a != b).sum()} differ, max {np.abs(a - b).max()}"
+    # one source depth vector / one target vector shared by every column (interp_to_hydro_section passes vdp_m like that)
+    a, sa = gpu.akima_1d_1d(vz1[0], vf1, vz2[0], **opts)
+    b, sb = orc.akima_1d_1d(vz1[0], vf1, vz2[0], **opts)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_akima_1d_1d_missing_values(gpu, orc):
+    vz1, vf1, vz2 = _columns(5, 400, 20, 30)
+    vf1[::2, -4:] = -9999.0                                   # trailing run
+    vf1[1::4, :3] = -9999.0; vf1[1::4, -2:] = -9999.0         # leading + trailing
+    vf1[3::8, :] = -9999.0                                    # everything missing: DOING NOTHING
+    opts = dict(rmask_val=-9999.0, l_surf_persist=True, l_botm_persist=True)
+    a, sa = gpu.akima_1d_1d(vz1, vf1, vz2, **opts)
+    b, sb = orc.akima_1d_1d(vz1, vf1, vz2, **opts)
+    assert np.array_equal(sa, sb) and set(np.unique(sa)) == {0, 1}
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # inputs for which the reference is undefined are refused, the status says which columns
+    import sosie_b200
+    vf1[6, 9] = -9999.0                                       # a hole in the middle
+    with pytest.raises(sosie_b200.SosieError, match="missing values"):
+        gpu.akima_1d_1d(vz1, vf1, vz2, **opts)
+    b, sb = orc.akima_1d_1d(vz1, vf1, vz2, **opts)
+    assert np.array_equal(gpu.last_status, sb) and sb[6] == -1
+    with pytest.raises(sosie_b200.SosieError, match="fewer than 3"):
+        gpu.akima_1d_1d(vz1[:, :2], np.abs(vf1[:, :2]), vz2)
+
+
+def _sigma_cubes(seed, nk_src, nk_trg, nj, ni, src_sigma, trg_sigma):
+    rng = np.random.default_rng(seed)
+    H = rng.uniform(200.0, 4000.0, (nj, ni))
+    s_src = np.linspace(0.02, 1.0, nk_src)[:, None, None] ** 1.5
+    s_trg = np.linspace(0.0, 1.0, nk_trg)[:, None, None] ** 1.3
+    depth_src = (s_src * H * rng.uniform(0.8, 1.0, (1, nj, ni))).astype(np.float32)
+    depth_trg = (s_trg * H * rng.uniform(0.9, 1.2, (1, nj, ni))).astype(np.float32)
+    data = (18.0 - 0.003 * depth_src + rng.normal(0, 0.3, depth_src.shape)).astype(np.float32)
+    if src_sigma:
+        depth_src = depth_src[::-1].copy(); data = data[::-1].copy()
+    if trg_sigma:
+        depth_trg = depth_trg[::-1].copy()
+    nwet = rng.integers(0, nk_trg + 1, (nj, ni))
+    mask = (np.arange(nk_trg)[:, None, None] < nwet[None]).astype(np.int32)
+    prev = rng.normal(size=(nk_trg, nj, ni)).astype(np.float32)
+    return depth_src, data, depth_trg, prev, mask
+
+
+@pytest.mark.parametrize("src_sigma,trg_sigma,lmout", [(False, False, False), (True, False, False), (False, True, True), (True, True, True),
+                                                       (False, False, True), (True, True, False)])
+def test_interp3d_sigma_vs_oracle(gpu, orc, src_sigma, trg_sigma, lmout):
+    ds, da, dt, prev, mask = _sigma_cubes(21, 31, 40, 60, 90, src_sigma, trg_sigma)
+    a = gpu.interp3d_sigma(ds, da, dt, prev, mask, lmout, src_sigma, trg_sigma)
+    b, st = orc.interp3d_sigma(ds, da, dt, prev, mask, lmout, src_sigma, trg_sigma)
+    assert st == 0
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{(a != b).sum()} differ"
+    if lmout:
+        land = mask[0] != 1
+        assert np.array_equal(a[:, land], prev[:, land])
+    else:
+        assert not np.array_equal(a, prev)
+
+
+def test_interp3d_sigma_on_device_after_horizontal(gpu, orc):
+    """z -> sigma job with everything resident: bilinear per level into data3d_tmp, source depths carried to the target grid
+    the same way (as INTERP_3D does, src/mod_interp.f90:300-320), then the column stage; nothing leaves HBM in between."""
+    import torch
+    rng = np.random.default_rng(8)
+    lon_s = (np.arange(72) + 0.5) * 5.0
+    lat_s = -90.0 + (np.arange(36) + 0.5) * 5.0
+    lon_t = np.linspace(20.0, 120.0, 50)[None, :].repeat(30, 0) + np.linspace(0, 3.0, 30)[:, None]
+    lat_t = np.linspace(-40.0, 40.0, 30)[:, None].repeat(50, 1) + np.linspace(0, 2.0, 50)[None, :]
+    nk_src, nk_trg = 12, 20
+    vz = np.cumsum(rng.uniform(5, 300, nk_src)).astype(np.float32)
+    cube = (15.0 - 0.002 * vz[:, None, None] + rng.normal(0, 0.3, (nk_src, 36, 72))).astype(np.float32)
+    depth_src_cube = np.broadcast_to(vz[:, None, None], cube.shape).astype(np.float32).copy()
+    H = rng.uniform(300.0, float(vz[-1]) * 1.1, lon_t.shape)
+    depth_trg = (np.linspace(0.01, 1.0, nk_trg)[:, None, None] * H).astype(np.float32)
+    gpu.bilin_set_grids(0, lon_s, lat_s, lon_t, lat_t, l_reg_src=True)
+    gpu.bilin_map()
+    dev = torch.device("cuda:0")
+    d_cube = torch.from_numpy(cube).to(dev); d_dsrc = torch.from_numpy(depth_src_cube).to(dev)
+    d_tmp = torch.empty((nk_src, 30, 50), dtype=torch.float32, device=dev); d_dtmp = torch.empty_like(d_tmp)
+    gpu.bilin_apply_dev(nk_src, d_cube, d_tmp)
+    gpu.bilin_apply_dev(nk_src, d_dsrc, d_dtmp)
+    d_dtrg = torch.from_numpy(depth_trg).to(dev)
+    d_out = torch.zeros((nk_trg, 30, 50), dtype=torch.float32, device=dev)
+    gpu.interp3d_sigma_dev(50, 30, nk_src, d_dtmp, d_tmp, nk_trg, d_dtrg, None, False, False, True, d_out)
+    gpu.sync()
+    tmp = np.stack([orc.bilin_2d(0, lon_s, lat_s, cube[k], lon_t, lat_t, l_reg_src=True)[0][0] for k in range(nk_src)])
+    dtmp = np.stack([orc.bilin_2d(0, lon_s, lat_s, depth_src_cube[k], lon_t, lat_t, l_reg_src=True)[0][0] for k in range(nk_src)])
+    ref, st = orc.interp3d_sigma(dtmp, tmp, depth_trg, np.zeros((nk_trg, 30, 50), np.float32), None, False, False, True)
+    assert st == 0
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32), ref.view(np.uint32))

@@ -122,3 +122,95 @@ def test_angle2_known_answers_and_transliteration(orc):
             assert np.allclose(nrm, 1.0, atol=1e-9)        # cos^2 + sin^2 = 1 in the interior
     finally:
         orc.set_libm(orc.PMATH)
+
+
+# ---- AKIMA_1D_1D (the column variant, src/mod_akima_1d.f90:26-232) and the generic-coordinate branch of INTERP_3D
+def _column_case(seed, nk1=14, nk2=20, ncol=9):
+    rng = np.random.default_rng(seed)
+    vz1 = np.cumsum(rng.uniform(3.0, 200.0, (ncol, nk1)), axis=1)
+    vf1 = 20.0 - 0.004 * vz1 + rng.normal(0.0, 0.5, (ncol, nk1))
+    vz2 = np.sort(rng.uniform(0.0, vz1.max() * 1.05, (ncol, nk2)), axis=1)
+    vz2[:, 3] = vz1[:, 2]                       # exact equality with a source level
+    vz2[:, 5] = vz1[:, 4].astype(np.float32).astype(np.float64) + 1e-9   # differs from the source level only beyond REAL(4)
+    return vz1, vf1, vz2
+
+
+def test_akima_1d_1d_known_answers(orc):
+    vz1 = np.array([0.0, 10.0, 30.0, 60.0, 100.0, 150.0, 400.0])
+    vf1 = 3.0 - 0.02 * vz1                                           # a line
+    vz2 = np.array([-5.0, 0.0, 5.0, 10.0, 45.0, 150.0, 399.0, 500.0])
+    out, st = orc.akima_1d_1d(vz1, vf1, vz2)
+    assert st[0] == 0
+    o = out[0]
+    assert o[0] == np.float32(-6666.0) and o[7] == np.float32(-6666.0)     # outside, no persistence asked: target missing value
+    assert o[1] == np.float32(3.0)          # equal to the FIRST source depth: the source value (:170-173)
+    for k in (2, 3, 4, 5, 6):               # equal to a deeper source depth: the `<=` of :162 interpolates in the interval above it
+        assert abs(float(o[k]) - (3.0 - 0.02 * vz2[k])) < 2e-5, (k, o[k])
+    out, st = orc.akima_1d_1d(vz1, vf1, vz2, l_surf_persist=True, l_botm_persist=True)
+    assert out[0][0] == np.float32(3.0) and out[0][7] == np.float32(vf1[-1])
+    # quirk: with bottom persistence only, a target ABOVE the first source level also ends the scan at k1_n (:189)
+    out, st = orc.akima_1d_1d(vz1, vf1, vz2, l_botm_persist=True)
+    assert out[0][0] == np.float32(vf1[-1])
+    # trailing (and leading) missing values shrink the column; everything missing: nothing done
+    vf1m = vf1.copy(); vf1m[-2:] = -9999.0
+    out, st = orc.akima_1d_1d(vz1, vf1m, vz2, rmask_val=-9999.0, l_botm_persist=True)
+    assert st[0] == 0 and out[0][6] == np.float32(vf1[4]) and abs(float(out[0][4]) - (3.0 - 0.02 * 45.0)) < 2e-5
+    out, st = orc.akima_1d_1d(vz1, np.full(7, -9999.0), vz2, rmask_val=-9999.0)
+    assert st[0] == 1 and np.all(out[0] == np.float32(-6666.0))
+    vf1m = vf1.copy(); vf1m[0] = -9999.0                                   # leading run only: FINDLOC returns 0 -> shape mismatch
+    assert orc.akima_1d_1d(vz1, vf1m, vz2, rmask_val=-9999.0)[1][0] == -1
+    vf1m = vf1.copy(); vf1m[3] = -9999.0; vf1m[-1] = -9999.0               # a hole in the middle
+    assert orc.akima_1d_1d(vz1, vf1m, vz2, rmask_val=-9999.0)[1][0] == -1
+    assert orc.akima_1d_1d(vz1[:2], vf1[:2], vz2)[1][0] == -2
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("opts", [dict(), dict(l_surf_persist=True), dict(l_botm_persist=True), dict(rmask_val=-9999.0, l_surf_persist=True, l_botm_persist=True)])
+def test_akima_1d_1d_vs_python_transliteration(orc, seed, opts):
+    vz1, vf1, vz2 = _column_case(seed)
+    if "rmask_val" in opts:
+        vf1[::2, -3:] = -9999.0
+        vf1[1::4, :2] = -9999.0
+        vf1[1::4, -1:] = -9999.0
+        vf1[4, 5] = -9999.0      # a hole: undefined in the reference, flagged
+    out, st = orc.akima_1d_1d(vz1, vf1, vz2, **opts)
+    for c in range(vz1.shape[0]):
+        b, sb = pyref.akima_1d_1d_py(vz1[c], vf1[c], vz2[c], opts.get("rmask_val"), opts.get("l_surf_persist", False), opts.get("l_botm_persist", False))
+        assert st[c] == sb, (c, st[c], sb)
+        if sb >= 0:
+            assert np.array_equal(out[c].view(np.uint32), b.view(np.uint32)), (c, out[c], b)
+    if "rmask_val" in opts:
+        assert st[4] == -1
+
+
+def _sigma_case(seed, nk_src=9, nk_trg=12, nj=4, ni=5, src_sigma=False, trg_sigma=False):
+    rng = np.random.default_rng(seed)
+    H = rng.uniform(200.0, 4000.0, (nj, ni))
+    s_src = np.linspace(0.02, 1.0, nk_src)[:, None, None] ** 1.5
+    s_trg = np.linspace(0.0, 1.0, nk_trg)[:, None, None] ** 1.3
+    depth_src = (s_src * H * rng.uniform(0.8, 1.0, (1, nj, ni))).astype(np.float32)
+    depth_trg = (s_trg * H * rng.uniform(0.9, 1.2, (1, nj, ni))).astype(np.float32)
+    data = (18.0 - 0.003 * depth_src + rng.normal(0, 0.3, depth_src.shape)).astype(np.float32)
+    if src_sigma:
+        depth_src = depth_src[::-1].copy(); data = data[::-1].copy()
+    if trg_sigma:
+        depth_trg = depth_trg[::-1].copy()
+    mask = np.ones((nk_trg, nj, ni), np.int32)
+    for jj in range(nj):
+        for ji in range(ni):
+            nwet = int(rng.integers(0, nk_trg + 1))
+            mask[nwet:, jj, ji] = 0
+    prev = rng.normal(size=(nk_trg, nj, ni)).astype(np.float32)
+    return depth_src, data, depth_trg, prev, mask
+
+
+@pytest.mark.parametrize("src_sigma,trg_sigma,lmout", [(False, False, False), (True, False, False), (False, True, True), (True, True, True), (False, False, True)])
+def test_interp3d_sigma_vs_python_transliteration(orc, src_sigma, trg_sigma, lmout):
+    ds, da, dt, prev, mask = _sigma_case(11, src_sigma=src_sigma, trg_sigma=trg_sigma)
+    a, st = orc.interp3d_sigma(ds, da, dt, prev, mask, lmout, src_sigma, trg_sigma)
+    b = pyref.interp3d_sigma_py(ds, da, dt, prev, mask, lmout, src_sigma, trg_sigma)
+    assert st == 0
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    if lmout:   # land columns are left alone
+        land = mask[0] != 1
+        assert np.array_equal(a[:, land], prev[:, land])
