@@ -158,6 +158,26 @@ int sosie_interp_bl(sosie_ctx* ctx, int32_t k_ew_per, int32_t nxi, int32_t nyi, 
                     const int32_t* jiP, const int32_t* jjP, const int32_t* iqd, const double* xa,
                     const double* xb, float* out);
 
+/* The per-point block of the trajectory front ends for n track points that fall between the same two
+ * model records: src/interp_to_ground_track.f90:718-779 (nk = 1; F1, F2 = xvar1, xvar2 (ni,nj) REAL(4) at times vt1 < vt2;
+ * rt(n) the track times; the reference rebuilds the whole time-interpolated field per point, here only the elements a
+ * point reads are formed, with the same roundings) and src/interp_to_hydro_section.f90:567-607 (nk levels of one record:
+ * F2 = NULL, rt unused).  imask(ni,nj,nk) INTEGER(1).  jiP, jjP, iqd, xa, xb: IMETRICS(1,:,1..3), RAB(1,:,1..2) of the
+ * points (from sosie_bilin_map on the (1,N) target).  A point is valid when iP, jP > 0, imask(iP,jP,k) == 1, obs_lo < r_obs <
+ * obs_hi (:738, -20/20; hydro: -20/50) and its 8 neighbours (indices clamped to the grid) are sea (:741-745).  For valid
+ * points only: f_np(k,p) = nearest-point value, f_bl(k,p) = REAL(INTERP_BL(-1, ...),8) (set to rmissval when clip_missing
+ * and < -9990, :787), fmask(k,p) = 1; the others keep the caller's pre-fill, as in the reference.  Level index fastest. */
+int sosie_track_interp(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk, const float* F1, const float* F2, double vt1,
+                       double vt2, const int8_t* imask, int64_t n, const double* rt, const int32_t* jiP,
+                       const int32_t* jjP, const int32_t* iqd, const double* xa, const double* xb, const double* r_obs,
+                       double obs_lo, double obs_hi, int32_t clip_missing, double rmissval, double* f_bl, double* f_np,
+                       int8_t* fmask);
+int sosie_track_interp_dev(sosie_ctx* ctx, int32_t ni, int32_t nj, int32_t nk, const float* dF1, const float* dF2,
+                           double vt1, double vt2, const int8_t* dimask, int64_t n, const double* drt,
+                           const int32_t* djiP, const int32_t* djjP, const int32_t* diqd, const double* dxa,
+                           const double* dxb, const double* dr_obs, double obs_lo, double obs_hi, int32_t clip_missing,
+                           double rmissval, double* df_bl, double* df_np, int8_t* dfmask);
+
 /* ---- Akima 2D ------------------------------------------------------------------------------------
  * Replaces AKIMA_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2, icall), src/mod_akima_2d.f90:59-239
  * (FILL_EXTRA_BANDS src/mod_manip.f90:69, SLOPES_AKIMA :483, build_pol :249, pol_val :445,

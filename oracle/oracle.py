@@ -162,6 +162,27 @@ def interp_bl(k_ew, iP, jP, iqd, xa, xb, Z_in):
     return lib().orc_interp_bl(int(k_ew), nx, ny, int(iP), int(jP), int(iqd), C.c_double(xa), C.c_double(xb), _p(Z, C.c_float))
 
 
+def track_interp(F1, F2, vt1, vt2, imask, rt, jiP, jjP, iqd, xa, xb, r_obs, obs_lo=-20.0, obs_hi=20.0, clip_missing=True, rmissval=-9999.0):
+    """per-point block of interp_to_ground_track.f90:718-779 / interp_to_hydro_section.f90:567-607.  F1 (and F2 or None):
+    (nk, nj, ni) or (nj, ni) f32; imask same shape i8.  Returns (f_bl, f_np, fmask), each (n, nk), pre-filled with rmissval / 0."""
+    F1 = _f32(F1)
+    if F1.ndim == 2:
+        F1 = F1[None]
+    nk, nj, ni = F1.shape
+    F2 = None if F2 is None else _f32(F2).reshape(F1.shape)
+    imask = np.ascontiguousarray(imask, np.int8).reshape(F1.shape)
+    jiP, jjP, iqd = _i32(jiP), _i32(jjP), _i32(iqd)
+    xa, xb, r_obs = _f64(xa), _f64(xb), _f64(r_obs)
+    n = jiP.size
+    rt = _f64(rt) if rt is not None else np.zeros(n)
+    f_bl = np.full((n, nk), rmissval, np.float64); f_np = np.full((n, nk), rmissval, np.float64); fmask = np.zeros((n, nk), np.int8)
+    lib().orc_track_interp(ni, nj, nk, _p(F1, C.c_float), _p(F2, C.c_float), C.c_double(vt1), C.c_double(vt2), _p(imask, C.c_int8),
+                           C.c_int64(n), _p(rt, C.c_double), _p(jiP, C.c_int32), _p(jjP, C.c_int32), _p(iqd, C.c_int32),
+                           _p(xa, C.c_double), _p(xb, C.c_double), _p(r_obs, C.c_double), C.c_double(obs_lo), C.c_double(obs_hi),
+                           int(clip_missing), C.c_double(rmissval), _p(f_bl, C.c_double), _p(f_np, C.c_double), _p(fmask, C.c_int8))
+    return f_bl, f_np, fmask
+
+
 def bilin_2d(k_ew, X10, Y10, Z1, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0, mapping=None,
              elide_fill=True, nthreads=1, virtual_src=False):
     """BILIN_2D over nslab source slabs Z1 (nslab, ny1, nx1).  X10/Y10 (and X20/Y20) are either 1-D axes or

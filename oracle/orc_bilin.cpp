@@ -739,9 +739,8 @@ void mapping_bl(int k_ew_per, const A2<const double>& X1, const A2<const double>
 // ------------------------------------------------------------------------------------------
 // src/mod_bilin_2d.f90:275-361.  Q19: i1..j4 are SAVE'd; an iqd outside 1..4 reuses them.
 struct InterpBLState { int i1 = 0, j1 = 0, i2 = 0, j2 = 0, i3 = 0, j3 = 0, i4 = 0, j4 = 0; };
-float interp_bl(InterpBLState& st, int k_ew_per, int jiP, int jjP, int iqd, double xa, double xb,
-                const A2<const float>& Z_in) {
-  int nxi = (int)Z_in.ni, nyi = (int)Z_in.nj;
+template <class FZ>
+float interp_bl_f(InterpBLState& st, int k_ew_per, int nxi, int nyi, int jiP, int jjP, int iqd, double xa, double xb, const FZ& Z_in) {
   int jiPm1 = jiP - 1, jiPp1 = jiP + 1;
   if ((jiPm1 == 0) && (k_ew_per >= 0)) jiPm1 = nxi - k_ew_per;
   if ((jiPp1 == nxi + 1) && (k_ew_per >= 0)) jiPp1 = 1 + k_ew_per;
@@ -764,6 +763,10 @@ float interp_bl(InterpBLState& st, int k_ew_per, int jiP, int jjP, int iqd, doub
   if ((j1 > nyi) || (j2 > nyi) || (j3 > nyi) || (j4 > nyi)) return -9995.f;
   if ((i1 > nxi) || (i2 > nxi) || (i3 > nxi) || (i4 > nxi)) return -9994.f;
   return (Z_in(i1, j1) * w1 + Z_in(i2, j2) * w2 + Z_in(i3, j3) * w3 + Z_in(i4, j4) * w4) / wup;
+}
+float interp_bl(InterpBLState& st, int k_ew_per, int jiP, int jjP, int iqd, double xa, double xb,
+                const A2<const float>& Z_in) {
+  return interp_bl_f(st, k_ew_per, (int)Z_in.ni, (int)Z_in.nj, jiP, jjP, iqd, xa, xb, Z_in);
 }
 
 }  // namespace orc
@@ -836,6 +839,55 @@ void orc_ext_north_to_90_regg(int nx, int ny, const double* XX, const double* YY
 float orc_interp_bl(int k_ew_per, int nxi, int nyi, int jiP, int jjP, int iqd, double xa, double xb, const float* Z_in) {
   InterpBLState st;
   return interp_bl(st, k_ew_per, jiP, jjP, iqd, xa, xb, A2<const float>(Z_in, nxi, nyi));
+}
+
+// The per-point block of the trajectory front ends: src/interp_to_ground_track.f90:718-779 (nk = 1, linear interpolation in
+// time between the two surrounding model records F1, F2) and src/interp_to_hydro_section.f90:567-607 (nk levels of one
+// record, F2 == NULL).  The reference rebuilds the WHOLE field xvar = xvar1 + xdum_r4*(rt - vt_mod(jtm_1)) for every track
+// point (:724) and reads five of its elements; the array statement is elementwise, so those elements are evaluated on
+// demand here (tests/pyref.py keeps the literal whole-array version).  Outputs are written for valid points only, as in
+// the reference (the caller pre-fills them with rmissval / 0).  f_bl, f_np, fmask: (nk, n), level fastest.
+void orc_track_interp(int ni, int nj, int nk, const float* F1, const float* F2, double vt1, double vt2, const int8_t* imask, int64_t n,
+                      const double* rt, const int32_t* jiP, const int32_t* jjP, const int32_t* iqdv, const double* xav, const double* xbv,
+                      const double* r_obs_v, double obs_lo, double obs_hi, int clip_missing, double rmissval, double* f_bl, double* f_np,
+                      int8_t* fmask) {
+  const int64_t nij = (int64_t)ni * nj;
+  std::vector<float> xdum_r4;
+  if (F2) {   // :718  xdum_r4 = (xvar2 - xvar1) / (vt_mod(jtm_2) - vt_mod(jtm_1)), REAL(4) <- REAL(8)
+    xdum_r4.resize((size_t)nij * nk);
+    for (int64_t q = 0; q < nij * nk; q++) xdum_r4[q] = (float)((double)(F2[q] - F1[q]) / (vt2 - vt1));
+  }
+  for (int64_t p = 0; p < n; p++) {
+    const int iP = jiP[p], jP = jjP[p], iquadran = iqdv[p];
+    const double alpha = xav[p], beta = xbv[p];
+    if (!((iP > 0) && (jP > 0))) continue;
+    for (int jk = 1; jk <= nk; jk++) {
+      const int64_t off = (int64_t)(jk - 1) * nij;
+      auto M = [&](int i, int j) { return (int)imask[off + (i - 1) + (int64_t)(j - 1) * ni]; };
+      auto xvar = [&](int64_t i, int64_t j) -> float {   // :724, REAL(4) <- REAL(4) + REAL(4)*REAL(8)
+        const int64_t q = off + (i - 1) + (j - 1) * ni;
+        if (!F2) return F1[q];
+        return (float)((double)F1[q] + (double)xdum_r4[q] * (rt[p] - vt1));
+      };
+      if (M(iP, jP) == 1) {
+        const double r_obs = r_obs_v[p];
+        const bool l_obs_ok = (r_obs > obs_lo) && (r_obs < obs_hi);
+        if (l_obs_ok) {
+          const int ip1 = std::min(iP + 1, ni), jp1 = std::min(jP + 1, nj), im1 = std::max(iP - 1, 1), jm1 = std::max(jP - 1, 1);
+          const int idot = M(ip1, jP) + M(ip1, jp1) + M(iP, jp1) + M(im1, jp1) + M(im1, jP) + M(im1, jm1) + M(iP, jm1) + M(ip1, jm1);
+          if (idot == 8) {
+            InterpBLState st;
+            const int64_t o = (int64_t)(jk - 1) + p * nk;
+            f_np[o] = (double)xvar(iP, jP);
+            double v = (double)interp_bl_f(st, -1, ni, nj, iP, jP, iquadran, alpha, beta, xvar);
+            if (clip_missing && (v < (double)-9990.f)) v = rmissval;   // :787
+            f_bl[o] = v;
+            fmask[o] = 1;
+          }
+        }
+      }
+    }
+  }
 }
 
 // BILIN_2D (src/mod_bilin_2d.f90:44-269) with the module SAVE state (IMETRICS, RAB, IPB,

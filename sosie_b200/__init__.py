@@ -44,6 +44,7 @@ EXPORTS = [
     "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
     "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev", "sosie_bilin_get_map_dev", "sosie_bilin_load_map_dev",
     "sosie_akima_1d_1d", "sosie_akima_1d_1d_dev", "sosie_interp3d_sigma", "sosie_interp3d_sigma_dev",
+    "sosie_track_interp", "sosie_track_interp_dev",
 ]
 
 _lib = None
@@ -410,6 +411,33 @@ class Sosie:
         nsw = np.zeros(nslab, np.int32)
         self._ck(self._lib.sosie_drown(self._h, int(k_ew), ni, nj, nslab, _p(X), _p(mask), int(nb_inc), _p(nsw)))
         return (X[0] if sq else X), nsw
+
+    def track_interp(self, F1, F2, vt1, vt2, imask, rt, jiP, jjP, iqd, xa, xb, r_obs, obs_lo=-20.0, obs_hi=20.0, clip_missing=True,
+                     rmissval=-9999.0):
+        """per-point block of interp_to_ground_track.f90:718-779 / interp_to_hydro_section.f90:567-607 for the points between two
+        model records; F1 (and F2 or None) (nk, nj, ni) or (nj, ni) f32, imask i8.  Returns (f_bl, f_np, fmask), each (n, nk)."""
+        F1 = _f32(F1)
+        if F1.ndim == 2:
+            F1 = F1[None]
+        nk, nj, ni = F1.shape
+        F2 = None if F2 is None else _f32(F2).reshape(F1.shape)
+        imask = np.ascontiguousarray(imask, np.int8).reshape(F1.shape)
+        jiP, jjP, iqd = _i32(jiP), _i32(jjP), _i32(iqd)
+        xa, xb, r_obs = _f64(xa), _f64(xb), _f64(r_obs)
+        n = jiP.size
+        rt = None if rt is None else _f64(rt)
+        f_bl = np.full((n, nk), rmissval, np.float64); f_np = np.full((n, nk), rmissval, np.float64); fmask = np.zeros((n, nk), np.int8)
+        self._ck(self._lib.sosie_track_interp(self._h, ni, nj, nk, _p(F1), _p(F2), C.c_double(vt1), C.c_double(vt2), _p(imask), C.c_int64(n),
+                                              _p(rt), _p(jiP), _p(jjP), _p(iqd), _p(xa), _p(xb), _p(r_obs), C.c_double(obs_lo),
+                                              C.c_double(obs_hi), int(clip_missing), C.c_double(rmissval), _p(f_bl), _p(f_np), _p(fmask)))
+        return f_bl, f_np, fmask
+
+    def track_interp_dev(self, ni, nj, nk, dF1, dF2, vt1, vt2, dimask, n, drt, djiP, djjP, diqd, dxa, dxb, dr_obs, obs_lo, obs_hi,
+                         clip_missing, rmissval, df_bl, df_np, dfmask):
+        self._ck(self._lib.sosie_track_interp_dev(self._h, int(ni), int(nj), int(nk), _dp(dF1), _dp(dF2), C.c_double(vt1), C.c_double(vt2),
+                                                  _dp(dimask), C.c_int64(n), _dp(drt), _dp(djiP), _dp(djjP), _dp(diqd), _dp(dxa), _dp(dxb),
+                                                  _dp(dr_obs), C.c_double(obs_lo), C.c_double(obs_hi), int(clip_missing),
+                                                  C.c_double(rmissval), _dp(df_bl), _dp(df_np), _dp(dfmask)))
 
     # ---------------------------------------------------------------- vertical stage of INTERP_3D
     def akima_1d_3d(self, vz1, xf1, vz2, rfill_val=-9999.0):

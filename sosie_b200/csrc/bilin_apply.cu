@@ -478,42 +478,98 @@ int bilin_apply_uv_impl(sosie_ctx* ctx, int nslab, const float* dU1, const float
 }
 
 // ---------------------------------------------------------------------------------------------------
-// scalar INTERP_BL for trajectory points (src/mod_bilin_2d.f90:275-361)
+// scalar INTERP_BL for trajectory points (src/mod_bilin_2d.f90:275-361); FZ(i, j) returns Z_in(i,j), 1-based
+template <class FZ>
+__device__ __forceinline__ float interp_bl_point(int k_ew, int nxi, int nyi, int iP, int jP, int iqd, double xa, double xb, const FZ& Z) {
+  int jiPm1 = iP - 1, jiPp1 = iP + 1;
+  if ((jiPm1 == 0) && (k_ew >= 0)) jiPm1 = nxi - k_ew;
+  if ((jiPp1 == nxi + 1) && (k_ew >= 0)) jiPp1 = 1 + k_ew;
+  int i1 = 0, j1 = 0, i2 = 0, j2 = 0, i3 = 0, j3 = 0, i4 = 0, j4 = 0;
+  switch (iqd) {
+    case 1: i1 = iP; j1 = jP; i2 = jiPp1; j2 = jP; i3 = jiPp1; j3 = jP + 1; i4 = iP; j4 = jP + 1; break;
+    case 2: i1 = iP; j1 = jP; i2 = iP; j2 = jP - 1; i3 = jiPp1; j3 = jP - 1; i4 = jiPp1; j4 = jP; break;
+    case 3: i1 = iP; j1 = jP; i2 = jiPm1; j2 = jP; i3 = jiPm1; j3 = jP - 1; i4 = iP; j4 = jP - 1; break;
+    case 4: i1 = iP; j1 = jP; i2 = iP; j2 = jP + 1; i3 = jiPm1; j3 = jP + 1; i4 = jiPm1; j4 = jP; break;
+    default: break;
+  }
+  float w1 = (float)((1.0 - xa) * (1.0 - xb));
+  float w2 = (float)(xa * (1.0 - xb));
+  float w3 = (float)(xa * xb);
+  float w4 = (float)((1.0 - xa) * xb);
+  float wup = __fadd_rn(__fadd_rn(__fadd_rn(w1, w2), w3), w4);
+  if (wup == 0.f) return -9998.f;
+  if ((i1 < 1) || (i2 < 1) || (i3 < 1) || (i4 < 1)) return -9997.f;
+  if ((j1 < 1) || (j2 < 1) || (j3 < 1) || (j4 < 1)) return -9996.f;
+  if ((j1 > nyi) || (j2 > nyi) || (j3 > nyi) || (j4 > nyi)) return -9995.f;
+  if ((i1 > nxi) || (i2 > nxi) || (i3 > nxi) || (i4 > nxi)) return -9994.f;
+  const float z1 = Z(i1, j1), z2 = Z(i2, j2), z3 = Z(i3, j3), z4 = Z(i4, j4);
+  return __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z1, w1), __fmul_rn(z2, w2)), __fmul_rn(z3, w3)), __fmul_rn(z4, w4)), wup);
+}
+
 __global__ void k_interp_bl(int k_ew, int nxi, int nyi, const float* __restrict__ Z, int n, const int32_t* __restrict__ jiP,
                             const int32_t* __restrict__ jjP, const int32_t* __restrict__ iqdv, const double* __restrict__ xav,
                             const double* __restrict__ xbv, float* out) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    int iP = jiP[k], jP = jjP[k], iqd = iqdv[k];
-    double xa = xav[k], xb = xbv[k];
-    int jiPm1 = iP - 1, jiPp1 = iP + 1;
-    if ((jiPm1 == 0) && (k_ew >= 0)) jiPm1 = nxi - k_ew;
-    if ((jiPp1 == nxi + 1) && (k_ew >= 0)) jiPp1 = 1 + k_ew;
-    int i1 = 0, j1 = 0, i2 = 0, j2 = 0, i3 = 0, j3 = 0, i4 = 0, j4 = 0;
-    switch (iqd) {
-      case 1: i1 = iP; j1 = jP; i2 = jiPp1; j2 = jP; i3 = jiPp1; j3 = jP + 1; i4 = iP; j4 = jP + 1; break;
-      case 2: i1 = iP; j1 = jP; i2 = iP; j2 = jP - 1; i3 = jiPp1; j3 = jP - 1; i4 = jiPp1; j4 = jP; break;
-      case 3: i1 = iP; j1 = jP; i2 = jiPm1; j2 = jP; i3 = jiPm1; j3 = jP - 1; i4 = iP; j4 = jP - 1; break;
-      case 4: i1 = iP; j1 = jP; i2 = iP; j2 = jP + 1; i3 = jiPm1; j3 = jP + 1; i4 = jiPm1; j4 = jP; break;
-      default: break;
-    }
-    float w1 = (float)((1.0 - xa) * (1.0 - xb));
-    float w2 = (float)(xa * (1.0 - xb));
-    float w3 = (float)(xa * xb);
-    float w4 = (float)((1.0 - xa) * xb);
-    float wup = __fadd_rn(__fadd_rn(__fadd_rn(w1, w2), w3), w4);
-    float r;
-    if (wup == 0.f) r = -9998.f;
-    else if ((i1 < 1) || (i2 < 1) || (i3 < 1) || (i4 < 1)) r = -9997.f;
-    else if ((j1 < 1) || (j2 < 1) || (j3 < 1) || (j4 < 1)) r = -9996.f;
-    else if ((j1 > nyi) || (j2 > nyi) || (j3 > nyi) || (j4 > nyi)) r = -9995.f;
-    else if ((i1 > nxi) || (i2 > nxi) || (i3 > nxi) || (i4 > nxi)) r = -9994.f;
-    else {
-      float z1 = Z[(size_t)(i1 - 1) + (size_t)(j1 - 1) * nxi], z2 = Z[(size_t)(i2 - 1) + (size_t)(j2 - 1) * nxi];
-      float z3 = Z[(size_t)(i3 - 1) + (size_t)(j3 - 1) * nxi], z4 = Z[(size_t)(i4 - 1) + (size_t)(j4 - 1) * nxi];
-      r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z1, w1), __fmul_rn(z2, w2)), __fmul_rn(z3, w3)), __fmul_rn(z4, w4)), wup);
-    }
-    out[k] = r;
+  auto fz = [&](int i, int j) { return Z[(size_t)(i - 1) + (size_t)(j - 1) * nxi]; };
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+    out[k] = interp_bl_point(k_ew, nxi, nyi, jiP[k], jjP[k], iqdv[k], xav[k], xbv[k], fz);
+}
+
+// The per-point block of the trajectory front ends: src/interp_to_ground_track.f90:718-779 (nk = 1,
+// linear interpolation in time between the two surrounding model records) and src/interp_to_hydro_section.f90:567-607
+// (nk levels of one record, F2 == NULL).  One thread per (level, point).  The reference rebuilds the whole field
+// xvar = xvar1 + xdum_r4*(rt - vt_mod(jtm_1)) for EVERY track point; only the five elements a point reads are formed here,
+// with the reference's roundings (slope REAL(4) <- REAL(8) quotient; xvar REAL(4) <- REAL(8) sum).
+__global__ void __launch_bounds__(256)
+k_track_interp(int ni, int nj, int nk, const float* __restrict__ F1, const float* __restrict__ F2, double vt1, double vt2,
+               const int8_t* __restrict__ imask, long long n, const double* __restrict__ rt, const int32_t* __restrict__ jiP,
+               const int32_t* __restrict__ jjP, const int32_t* __restrict__ iqdv, const double* __restrict__ xav,
+               const double* __restrict__ xbv, const double* __restrict__ r_obs_v, double obs_lo, double obs_hi, int clip_missing,
+               double rmissval, double* f_bl, double* f_np, int8_t* fmask) {
+  const long long tot = n * nk;
+  const size_t nij = (size_t)ni * nj;
+  const double dvt = vt2 - vt1;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+    const long long p = q / nk;
+    const int jk = (int)(q - p * nk);
+    const int iP = jiP[p], jP = jjP[p];
+    if (!((iP > 0) && (jP > 0)) || iP > ni || jP > nj) continue;
+    const size_t off = (size_t)jk * nij;
+    auto M = [&](int i, int j) { return (int)imask[off + (size_t)(i - 1) + (size_t)(j - 1) * ni]; };
+    if (M(iP, jP) != 1) continue;
+    const double r_obs = r_obs_v[p];
+    if (!((r_obs > obs_lo) && (r_obs < obs_hi))) continue;
+    const int ip1 = min(iP + 1, ni), jp1 = min(jP + 1, nj), im1 = max(iP - 1, 1), jm1 = max(jP - 1, 1);
+    const int idot = M(ip1, jP) + M(ip1, jp1) + M(iP, jp1) + M(im1, jp1) + M(im1, jP) + M(im1, jm1) + M(iP, jm1) + M(ip1, jm1);
+    if (idot != 8) continue;
+    const double dt = F2 ? __dsub_rn(rt[p], vt1) : 0.0;
+    auto xvar = [&](int i, int j) -> float {
+      const size_t e = off + (size_t)(i - 1) + (size_t)(j - 1) * ni;
+      const float a = F1[e];
+      if (!F2) return a;
+      const float slope = (float)__ddiv_rn((double)__fsub_rn(F2[e], a), dvt);
+      return (float)__dadd_rn((double)a, __dmul_rn((double)slope, dt));
+    };
+    f_np[q] = (double)xvar(iP, jP);
+    double v = (double)interp_bl_point(-1, ni, nj, iP, jP, iqdv[p], xav[p], xbv[p], xvar);
+    if (clip_missing && (v < (double)-9990.f)) v = rmissval;
+    f_bl[q] = v;
+    fmask[q] = 1;
   }
+}
+
+int track_interp_impl(sosie_ctx* ctx, int ni, int nj, int nk, const float* F1, const float* F2, double vt1, double vt2, const int8_t* imask,
+                      long long n, const double* rt, const int32_t* jiP, const int32_t* jjP, const int32_t* iqd, const double* xa,
+                      const double* xb, const double* r_obs, double obs_lo, double obs_hi, int clip_missing, double rmissval, double* f_bl,
+                      double* f_np, int8_t* fmask) {
+  if (n <= 0) return SOSIE_OK;
+  if (ni < 1 || nj < 1 || nk < 1 || !F1 || !imask || !jiP || !jjP || !iqd || !xa || !xb || !r_obs || !f_bl || !f_np || !fmask || (F2 && !rt)) {
+    ctx->err = "sosie_track_interp: bad arguments"; return SOSIE_ERR_ARG;
+  }
+  if (F2 && !(vt2 != vt1)) { ctx->err = "sosie_track_interp: the two model records have the same time"; return SOSIE_ERR_ARG; }
+  k_track_interp<<<grid_for(ctx, (size_t)n * nk, 256), 256, 0, ctx->stream>>>(ni, nj, nk, F1, F2, vt1, vt2, imask, n, rt, jiP, jjP, iqd, xa, xb,
+                                                                                 r_obs, obs_lo, obs_hi, clip_missing, rmissval, f_bl, f_np, fmask);
+  KLAUNCH_CHECK();
+  return SOSIE_OK;
 }
 
 int interp_bl_impl(sosie_ctx* ctx, int k_ew, int nxi, int nyi, const float* dZ, int n, const int32_t* ji, const int32_t* jj,

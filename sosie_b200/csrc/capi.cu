@@ -424,6 +424,54 @@ int sosie_interp_bl(sosie_ctx* c, int32_t k_ew, int32_t nxi, int32_t nyi, const 
   return SOSIE_OK;
 }
 
+int sosie_track_interp_dev(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk, const float* dF1, const float* dF2, double vt1, double vt2,
+                           const int8_t* dimask, int64_t n, const double* drt, const int32_t* djiP, const int32_t* djjP, const int32_t* diqd,
+                           const double* dxa, const double* dxb, const double* dr_obs, double obs_lo, double obs_hi, int32_t clip_missing,
+                           double rmissval, double* df_bl, double* df_np, int8_t* dfmask) {
+  NEED(c);
+  return track_interp_impl(ctx, ni, nj, nk, dF1, dF2, vt1, vt2, dimask, n, drt, djiP, djjP, diqd, dxa, dxb, dr_obs, obs_lo, obs_hi, clip_missing,
+                           rmissval, df_bl, df_np, dfmask);
+}
+
+int sosie_track_interp(sosie_ctx* c, int32_t ni, int32_t nj, int32_t nk, const float* F1, const float* F2, double vt1, double vt2,
+                       const int8_t* imask, int64_t n, const double* rt, const int32_t* jiP, const int32_t* jjP, const int32_t* iqd,
+                       const double* xa, const double* xb, const double* r_obs, double obs_lo, double obs_hi, int32_t clip_missing,
+                       double rmissval, double* f_bl, double* f_np, int8_t* fmask) {
+  NEED(c);
+  if (n <= 0) return SOSIE_OK;
+  if (ni < 1 || nj < 1 || nk < 1 || !F1 || !imask || !jiP || !jjP || !iqd || !xa || !xb || !r_obs || !f_bl || !f_np || !fmask || (F2 && !rt)) {
+    ctx->err = "sosie_track_interp: bad arguments"; return SOSIE_ERR_ARG;
+  }
+  cudaStream_t st = ctx->stream;
+  const size_t nf = (size_t)ni * nj * nk, np_ = (size_t)n, no = np_ * nk;
+  DBuf<float> dF1, dF2; DBuf<int8_t> dM, dfm; DBuf<int32_t> di, dj, dq; DBuf<double> drt, da, db, dro, dbl, dnp;
+  CK(dF1.alloc(nf)); CK(dM.alloc(nf)); CK(di.alloc(np_)); CK(dj.alloc(np_)); CK(dq.alloc(np_)); CK(da.alloc(np_)); CK(db.alloc(np_));
+  CK(dro.alloc(np_)); CK(dbl.alloc(no)); CK(dnp.alloc(no)); CK(dfm.alloc(no));
+  CK(cudaMemcpyAsync(dF1.p, F1, nf * 4, cudaMemcpyHostToDevice, st));
+  if (F2) {
+    CK(dF2.alloc(nf)); CK(drt.alloc(np_));
+    CK(cudaMemcpyAsync(dF2.p, F2, nf * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(drt.p, rt, np_ * 8, cudaMemcpyHostToDevice, st));
+  }
+  CK(cudaMemcpyAsync(dM.p, imask, nf, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(di.p, jiP, np_ * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dj.p, jjP, np_ * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dq.p, iqd, np_ * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(da.p, xa, np_ * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(db.p, xb, np_ * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dro.p, r_obs, np_ * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dbl.p, f_bl, no * 8, cudaMemcpyHostToDevice, st));   // pre-filled by the caller, kept for invalid points
+  CK(cudaMemcpyAsync(dnp.p, f_np, no * 8, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(dfm.p, fmask, no, cudaMemcpyHostToDevice, st));
+  if (int rc = track_interp_impl(ctx, ni, nj, nk, dF1.p, F2 ? dF2.p : nullptr, vt1, vt2, dM.p, n, F2 ? drt.p : nullptr, di.p, dj.p, dq.p, da.p,
+                                 db.p, dro.p, obs_lo, obs_hi, clip_missing, rmissval, dbl.p, dnp.p, dfm.p)) return rc;
+  CK(cudaMemcpyAsync(f_bl, dbl.p, no * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(f_np, dnp.p, no * 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(fmask, dfm.p, no, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SOSIE_OK;
+}
+
 // ---------------------------------------------------------------------------------------------------
 int sosie_akima_set_grids(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, const double* X10, const double* Y10, int32_t src_1d,
                           int32_t i_orca_src, int32_t nx2, int32_t ny2, const double* X20, const double* Y20, int32_t trg_1d) {

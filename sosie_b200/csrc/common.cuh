@@ -259,6 +259,10 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
 int bilin_apply_uv_impl(sosie_ctx* ctx, int nslab, const float* dU1, const float* dV1, float* dUo, float* dVo,
                         const double* dcos, const double* dsin);
 int bilin_prepare_src(sosie_ctx* ctx);
+int track_interp_impl(sosie_ctx* ctx, int ni, int nj, int nk, const float* F1, const float* F2, double vt1, double vt2, const int8_t* imask,
+                      long long n, const double* rt, const int32_t* jiP, const int32_t* jjP, const int32_t* iqd, const double* xa,
+                      const double* xb, const double* r_obs, double obs_lo, double obs_hi, int clip_missing, double rmissval, double* f_bl,
+                      double* f_np, int8_t* fmask);
 int interp_bl_impl(sosie_ctx* ctx, int k_ew, int nxi, int nyi, const float* dZ, int n, const int32_t* ji,
                    const int32_t* jj, const int32_t* iq, const double* xa, const double* xb, float* out);
 int akima_prepare_impl(sosie_ctx* ctx);

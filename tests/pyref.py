@@ -823,3 +823,78 @@ def interp3d_sigma_py(depth_src, data3d_tmp, depth_trg, data3d_trg, mask_trg=Non
                     t = t[::-1]
                 out[:, jj, ji] = t
     return out
+
+
+def interp_bl_np(k_ew, iP, jP, iqd, xa, xb, Z):
+    """INTERP_BL, src/mod_bilin_2d.f90:275-361, on Z (nj, ni) float32 (1-based indices translated at the reads)"""
+    f4 = np.float32
+    nyi, nxi = Z.shape
+    im1, ip1 = iP - 1, iP + 1
+    if im1 == 0 and k_ew >= 0:
+        im1 = nxi - k_ew
+    if ip1 == nxi + 1 and k_ew >= 0:
+        ip1 = 1 + k_ew
+    quad = {1: ((iP, jP), (ip1, jP), (ip1, jP + 1), (iP, jP + 1)), 2: ((iP, jP), (iP, jP - 1), (ip1, jP - 1), (ip1, jP)),
+            3: ((iP, jP), (im1, jP), (im1, jP - 1), (iP, jP - 1)), 4: ((iP, jP), (iP, jP + 1), (im1, jP + 1), (im1, jP))}[iqd]
+    w = [f4((1.0 - xa) * (1.0 - xb)), f4(xa * (1.0 - xb)), f4(xa * xb), f4((1.0 - xa) * xb)]
+    wup = w[0] + w[1] + w[2] + w[3]
+    if wup == 0:
+        return f4(-9998.0)
+    if any(i < 1 for i, _ in quad):
+        return f4(-9997.0)
+    if any(j < 1 for _, j in quad):
+        return f4(-9996.0)
+    if any(j > nyi for _, j in quad):
+        return f4(-9995.0)
+    if any(i > nxi for i, _ in quad):
+        return f4(-9994.0)
+    z = [Z[j - 1, i - 1] for i, j in quad]
+    return (z[0] * w[0] + z[1] * w[1] + z[2] * w[2] + z[3] * w[3]) / wup
+
+
+def ground_track_loop_np(fields, vt_mod, imask, vtf, metrics, ab, F_gt_f, rmissval=-9999.0):
+    """the time loop of interp_to_ground_track.f90:674-787, literally: the whole field xvar is rebuilt for every track point.
+    fields (Ntm, nj, ni) f32 (what GETVAR_2D would read), imask (nj, ni) i8, metrics (3, Ntf) i32, ab (2, Ntf) f64."""
+    f4, f8 = np.float32, np.float64
+    Ntm, nj, ni = fields.shape
+    Ntf = vtf.size
+    t_min_m, t_max_m = vt_mod.min(), vt_mod.max()
+    mod_np = np.full(Ntf, rmissval, f8); obs = np.full(Ntf, rmissval, f8); mod = np.full(Ntf, rmissval, f8); Fmask = np.zeros(Ntf, np.int8)
+    jtm_1_o = jtm_2_o = -100
+    jt_s = 1
+    xvar1 = xvar2 = xdum_r4 = None
+    M = lambda i, j: int(imask[j - 1, i - 1])
+    for jtf in range(Ntf):
+        rt = f8(vtf[jtf])
+        if rt >= t_min_m and rt < t_max_m:
+            jt = jt_s
+            while jt <= Ntm - 1:
+                if rt >= vt_mod[jt - 1] and rt < vt_mod[jt]:
+                    break
+                jt += 1
+            jtm_1, jtm_2 = jt, jt + 1
+            if jtm_1 > jtm_1_o and jtm_2 > jtm_2_o:
+                if jtm_1_o == -100 or jtm_1 > jtm_2_o:
+                    xvar1 = fields[jtm_1 - 1].copy()
+                else:
+                    xvar1 = xvar2.copy()
+                xvar2 = fields[jtm_2 - 1].copy()
+                xdum_r4 = ((xvar2 - xvar1).astype(f8) / (vt_mod[jtm_2 - 1] - vt_mod[jtm_1 - 1])).astype(f4)
+            xvar = (xvar1.astype(f8) + xdum_r4.astype(f8) * (rt - vt_mod[jtm_1 - 1])).astype(f4)
+            iP, jP, iq = int(metrics[0, jtf]), int(metrics[1, jtf]), int(metrics[2, jtf])
+            alpha, beta = f8(ab[0, jtf]), f8(ab[1, jtf])
+            if iP > 0 and jP > 0:
+                if M(iP, jP) == 1:
+                    r_obs = F_gt_f[jtf]
+                    if r_obs > -20.0 and r_obs < 20.0:
+                        ip1, jp1, im1, jm1 = min(iP + 1, ni), min(jP + 1, nj), max(iP - 1, 1), max(jP - 1, 1)
+                        idot = M(ip1, jP) + M(ip1, jp1) + M(iP, jp1) + M(im1, jp1) + M(im1, jP) + M(im1, jm1) + M(iP, jm1) + M(ip1, jm1)
+                        if idot == 8:
+                            mod_np[jtf] = f8(xvar[jP - 1, iP - 1])
+                            mod[jtf] = f8(interp_bl_np(-1, iP, jP, iq, alpha, beta, xvar))
+                            obs[jtf] = r_obs
+                            Fmask[jtf] = 1
+            jtm_1_o, jtm_2_o, jt_s = jtm_1, jtm_2, jtm_1
+    mod[Fmask == 0] = rmissval; mod_np[Fmask == 0] = rmissval; obs[Fmask == 0] = rmissval
+    mod[mod < f8(f4(-9990.0))] = rmissval
+    return mod, mod_np, obs, Fmask

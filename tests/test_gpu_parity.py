@@ -342,6 +342,60 @@ def test_trajectory_mapping_and_interp_bl(gpu, orc, src):
     assert found.mean() > 0.8          # most of the track lies inside the model domain
 
 
+def test_track_interp_random_metrics(gpu, orc):
+    """per-point block of the ground-track tool (time interpolation between two records) and of the hydro-section tool (levels)
+    on arbitrary index/weight combinations, incl. indices on the grid edge, land neighbours, obs outside the window"""
+    from tests.test_oracle_kat import track_case, track_by_intervals
+    case = track_case(seed=9, ni=90, nj=70, Ntm=6, Ntf=20000)
+    a = track_by_intervals(gpu.track_interp, *case)
+    b = track_by_intervals(orc.track_interp, *case)
+    assert b[3].sum() > 5000
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    rng = np.random.default_rng(5)
+    nk, nj, ni, n = 7, 40, 55, 5000
+    F = rng.normal(size=(nk, nj, ni)).astype(np.float32)
+    imask = (rng.uniform(size=(nk, nj, ni)) > 0.03).astype(np.int8)
+    iP, jP, iq = rng.integers(0, ni + 1, n), rng.integers(0, nj + 1, n), rng.integers(1, 5, n)
+    xa, xb, r_obs = rng.uniform(size=n), rng.uniform(size=n), rng.uniform(-30, 60, n)
+    a = gpu.track_interp(F, None, 0.0, 1.0, imask, None, iP, jP, iq, xa, xb, r_obs, -20.0, 50.0, False)
+    b = orc.track_interp(F, None, 0.0, 1.0, imask, None, iP, jP, iq, xa, xb, r_obs, -20.0, 50.0, False)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_ground_track_job(gpu, orc):
+    """a whole ground-track job: MAPPING_BL(-1, ...) of a satellite-like track on an ORCA-shaped model grid, then the track points
+    of each model interval interpolated in space and time; everything against the oracle chain"""
+    from tests.test_oracle_kat import track_by_intervals
+    rng = np.random.default_rng(23)
+    N, Ntm = 40000, 4
+    t = np.linspace(0.0, 1.0, N)
+    lon = np.mod(200.0 + 170.0 * t + 3.0 * np.sin(40 * t), 360.0)
+    lat = 60.0 * np.sin(2 * np.pi * 3.3 * t) + rng.normal(0.0, 0.01, N)
+    Xt, Yt = lon[:, None].copy(), lat[:, None].copy()
+    cfg = G.config("B", 0.5)
+    Xs, Ys = cfg["src_lon"], cfg["src_lat"]
+    fields = G.field_slabs(Xs, Ys, Ntm, seed=4)
+    imask = G.land_mask(Xs, Ys).astype(np.int8)
+    gpu.bilin_set_grids(-1, Xs, Ys, Xt, Yt)
+    gpu.bilin_map()
+    mg = gpu.bilin_get_map()
+    mo = orc.mapping_bl(-1, Xs, Ys, Xt, Yt)
+    for k in ("metrics", "alphabeta"):
+        assert np.array_equal(mg[k], mo[k])
+    metrics = np.stack([mg["metrics"][q][:, 0] for q in range(3)])
+    ab = np.stack([mg["alphabeta"][q][:, 0] for q in range(2)])
+    vt_mod = 20000.0 + np.arange(Ntm) * 1.25
+    vtf = vt_mod[0] - 0.1 + t * (vt_mod[-1] - vt_mod[0] + 0.2)
+    F_gt_f = rng.normal(0.0, 8.0, N)
+    a = track_by_intervals(gpu.track_interp, fields, vt_mod, imask, vtf, metrics, ab, F_gt_f)
+    b = track_by_intervals(orc.track_interp, fields, vt_mod, imask, vtf, metrics, ab, F_gt_f)
+    assert b[3].sum() > N // 4
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
 def test_akima_config_E_shape(gpu, orc):
     """the reference's own etopo_2_eNATL60 namelist interpolates with Akima (etopo_2_eNATL60.namelist:220): regular source,
     rotated regional curvilinear target, k_ew = 0; the slopes are only needed under the target (needed map)."""

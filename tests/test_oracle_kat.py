@@ -257,3 +257,73 @@ def test_faithful_fill_equals_elided(orc):
         b, mb = orc.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"],
                              l_reg_src=cfg["l_reg_src"], elide_fill=True, nthreads=2)
         assert np.array_equal(a, b) and all(np.array_equal(ma[k], mb[k]) for k in ("metrics", "alphabeta", "ipb"))
+
+
+# ---- trajectory front end: the time loop of interp_to_ground_track.f90
+def track_case(seed=3, ni=40, nj=30, Ntm=5, Ntf=300):
+    rng = np.random.default_rng(seed)
+    fields = rng.normal(0.0, 1.0, (Ntm, nj, ni)).astype(np.float32)
+    fields[:, 5, 7] = -9999.0                                   # a missing value inside the field: the < -9990 clip
+    vt_mod = np.cumsum(rng.uniform(0.5, 1.5, Ntm)) + 20000.0
+    imask = (rng.uniform(size=(nj, ni)) > 0.04).astype(np.int8)
+    vtf = np.sort(rng.uniform(vt_mod[0] - 0.3, vt_mod[-1] + 0.3, Ntf))
+    vtf[10] = vt_mod[1]                                         # exactly on a model record
+    vtf.sort()                                                  # the reference scans forward from the last interval
+    metrics = np.stack([rng.integers(0, ni + 1, Ntf), rng.integers(0, nj + 1, Ntf), rng.integers(1, 5, Ntf)]).astype(np.int32)
+    metrics[0, :40] = 7; metrics[1, :40] = 6                    # neighbours of the missing value
+    ab = rng.uniform(0.0, 1.0, (2, Ntf))
+    F_gt_f = rng.normal(0.0, 9.0, Ntf)                          # some outside (-20, 20)
+    return fields, vt_mod, imask, vtf, metrics, ab, F_gt_f
+
+
+def track_by_intervals(run, fields, vt_mod, imask, vtf, metrics, ab, F_gt_f, rmissval=-9999.0):
+    """what a tool using the library does: group the track points by model interval, one call per interval"""
+    Ntf = vtf.size
+    mod = np.full(Ntf, rmissval); mod_np = np.full(Ntf, rmissval); fmask = np.zeros(Ntf, np.int8)
+    for jt in range(vt_mod.size - 1):
+        sel = np.nonzero((vtf >= vt_mod[jt]) & (vtf < vt_mod[jt + 1]) & (vtf >= vt_mod.min()) & (vtf < vt_mod.max()))[0]
+        if sel.size == 0:
+            continue
+        a, b, m = run(fields[jt], fields[jt + 1], vt_mod[jt], vt_mod[jt + 1], imask, vtf[sel], metrics[0, sel], metrics[1, sel], metrics[2, sel],
+                      ab[0, sel], ab[1, sel], F_gt_f[sel])
+        mod[sel] = a[:, 0]; mod_np[sel] = b[:, 0]; fmask[sel] = m[:, 0]
+    obs = np.where(fmask == 1, F_gt_f, rmissval)
+    return mod, mod_np, obs, fmask
+
+
+def test_ground_track_loop_vs_transliteration(orc):
+    from tests import pyref
+    case = track_case()
+    a = track_by_intervals(orc.track_interp, *case)
+    b = pyref.ground_track_loop_np(*case)
+    assert b[3].sum() > 50 and (b[3] == 0).sum() > 20
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+    assert (b[0][b[3] == 1] == -9999.0).sum() > 0                # the clip fired on valid points
+
+
+def test_track_interp_levels_no_time(orc):
+    """interp_to_hydro_section.f90:567-607: nk levels of one record, per-level masks, obs window (-20, 50)"""
+    from tests import pyref
+    rng = np.random.default_rng(5)
+    nk, nj, ni, n = 6, 20, 25, 80
+    F = rng.normal(size=(nk, nj, ni)).astype(np.float32)
+    imask = (rng.uniform(size=(nk, nj, ni)) > 0.03).astype(np.int8)
+    iP, jP, iq = rng.integers(0, ni + 1, n), rng.integers(0, nj + 1, n), rng.integers(1, 5, n)
+    xa, xb = rng.uniform(size=n), rng.uniform(size=n)
+    r_obs = rng.uniform(-30, 60, n)
+    f_bl, f_np, fm = orc.track_interp(F, None, 0.0, 1.0, imask, None, iP, jP, iq, xa, xb, r_obs, -20.0, 50.0, False)
+    for p in range(n):
+        for k in range(nk):
+            M = lambda i, j: int(imask[k, j - 1, i - 1])
+            ok = iP[p] > 0 and jP[p] > 0 and M(iP[p], jP[p]) == 1 and -20.0 < r_obs[p] < 50.0
+            if ok:
+                i, j = int(iP[p]), int(jP[p])
+                ip1, jp1, im1, jm1 = min(i + 1, ni), min(j + 1, nj), max(i - 1, 1), max(j - 1, 1)
+                ok = M(ip1, j) + M(ip1, jp1) + M(i, jp1) + M(im1, jp1) + M(im1, j) + M(im1, jm1) + M(i, jm1) + M(ip1, jm1) == 8
+            assert fm[p, k] == int(ok)
+            if ok:
+                assert f_np[p, k] == np.float64(F[k, j - 1, i - 1])
+                assert f_bl[p, k] == np.float64(pyref.interp_bl_np(-1, i, j, int(iq[p]), xa[p], xb[p], F[k]))
+            else:
+                assert f_bl[p, k] == -9999.0 and f_np[p, k] == -9999.0
