@@ -343,7 +343,7 @@ struct Best {
 #define MAP_MIN_BLOCKS 6
 #endif
 template <bool SEP>
-__device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
+static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
                                             int j2, Best& b, int ic, int jc) {
   // MINLOC = lexicographic minimum of (distance, column-major position).  The window centre (ic,jc) -- the
   // index-nearest point, almost always the winner or next to it -- is evaluated first, so that nearly every other
@@ -414,6 +414,58 @@ __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double
       if (d < b.d || (d == b.d && earlier)) { b.d = d; b.pds = zpds; b.i = ji; b.j = jj; }
     }
   }
+}
+
+// The scan the kernel runs.  Regular source: the decision is taken on the dot products alone -- the candidate with the
+// largest u.v wins outright when every other candidate is more than PDS_MARGIN below it (acos is monotone and a margin
+// of 1e-13 in u.v is far above what its rounding can hide), and only ONE acos is evaluated per target, after the loop,
+// by all lanes together.  (With the acos inside the loop, the lanes of a warp that met a better candidate at different
+// iterations each made the whole warp execute the 18-term polynomial again: ~10 executions per warp.)  A second
+// candidate within the margin of the best -- equidistant source points, the rows at and beyond the pole -- sends the
+// target to the exact scan above, which evaluates and compares distances like the reference.
+template <bool SEP>
+__device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
+                                            int j2, Best& b, int ic, int jc) {
+  if (!SEP) { scan_window_exact<SEP>(sg, ux, uy, uz, i1, i2, j1, j2, b, ic, jc); return; }
+  ic = min(max(ic, i1), i2);
+  jc = min(max(jc, j1), j2);
+  double a[9];
+  double amax = -4.0, amin = 4.0;
+#pragma unroll
+  for (int q = 0; q < 9; q++) {
+    int ji = min(i1 + q, i2);
+    a[q] = ux * sg.clon[ji - 1] + uy * sg.slon[ji - 1];
+    amax = fmax(amax, a[q]); amin = fmin(amin, a[q]);
+  }
+  const int nq = i2 - i1 + 1;
+  double p1, p2 = -4.0;   // largest and second largest exact u.v met so far
+  int bi = ic, bj = jc;
+  {
+    const double cl = sg.clat[jc - 1], sl = sg.slat[jc - 1];
+    p1 = ux * (sg.clon[ic - 1] * cl) + uy * (sg.slon[ic - 1] * cl) + uz * sl;
+  }
+  for (int jj = j1; jj <= j2; jj++) {
+    const double cl = sg.clat[jj - 1], sl = sg.slat[jj - 1];
+    const double c0 = uz * sl;
+    const double thr = p1 - (PDS_MARGIN + 1.0e-14);
+    if (((cl >= 0.0) ? cl * amax : cl * amin) + c0 < thr) continue;
+    unsigned surv = 0;
+#pragma unroll
+    for (int q = 0; q < 9; q++)
+      if (q < nq && !(cl * a[q] + c0 < thr)) surv |= 1u << q;
+    if (jj == jc) surv &= ~(1u << (ic - i1));  // the centre seeded p1
+    while (surv) {
+      const int q = __ffs(surv) - 1;
+      surv &= surv - 1;
+      const int ji = i1 + q;
+      const double zpds = ux * (sg.clon[ji - 1] * cl) + uy * (sg.slon[ji - 1] * cl) + uz * sl;
+      if (zpds > p1) { p2 = p1; p1 = zpds; bi = ji; bj = jj; }
+      else p2 = fmax(p2, zpds);
+    }
+  }
+  if (p2 >= p1 - PDS_MARGIN) { scan_window_exact<SEP>(sg, ux, uy, uz, i1, i2, j1, j2, b, ic, jc); return; }
+  b.pds = p1; b.i = bi; b.j = bj;
+  b.d = G_ZR * pm_acos(fmin(p1, 1.0));
 }
 
 // ---------------------------------------------------------------------------------------------------
