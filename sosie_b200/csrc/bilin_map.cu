@@ -235,7 +235,7 @@ __global__ void k_merc_table(const double* __restrict__ lat, size_t n, double* m
 }
 // hE/hW per column and hN/hS per row of a separable source (see map_body): the arguments are exactly those the
 // body would form -- lonN = lonS = lonP (same column), yb = ya for the E/W neighbours (same row)
-__global__ void k_heading_tables(SrcGeom sg, int k_ew, double* hE, double* hW, double* hN, double* hS) {
+__global__ void k_heading_tables(SrcGeom sg, int k_ew, double* hE, double* hW, double* hN, double* hS, double* lonm) {
   const int nx = sg.nx, nyw = sg.nyw;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nx + nyw; k += gridDim.x * blockDim.x) {
     if (k < nx) {
@@ -247,7 +247,7 @@ __global__ void k_heading_tables(SrcGeom sg, int k_ew, double* hE, double* hW, d
       double e = 0.0, w = 0.0;
       if (iPp1 >= 1 && iPp1 <= nx) e = d_heading_y(lonP, d_mod(sg.lon1[iPp1 - 1], 360.0), 0.0, 0.0);
       if (iPm1 >= 1 && iPm1 <= nx) w = d_heading_y(lonP, d_mod(sg.lon1[iPm1 - 1], 360.0), 0.0, 0.0);
-      hE[k] = e; hW[k] = w;
+      hE[k] = e; hW[k] = w; lonm[k] = lonP;
     } else {
       const int j = k - nx;  // 0-based row jP-1
       double n = 0.0, s_ = 0.0;
@@ -500,13 +500,20 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
   if (iPm1 == 0) { if (k_ew >= 0) iPm1 = nxi - k_ew; }
   if (iPp1 == nxi + 1) { if (k_ew >= 0) iPp1 = 1 + k_ew; }
   if ((iPm1 < 1) || (jPm1 < 1) || (iPp1 > nxi)) return;
-  double lonP = d_mod(src_lon(sg, iP, jP), 360.0), latP = src_lat(sg, iP, jP);
-  double lonN = d_mod(src_lon(sg, iP, jPp1), 360.0), latN = src_lat(sg, iP, jPp1);
-  double lonE = d_mod(src_lon(sg, iPp1, jP), 360.0), latE = src_lat(sg, iPp1, jP);
-  double lonS = d_mod(src_lon(sg, iP, jPm1), 360.0), latS = src_lat(sg, iP, jPm1);
-  double lonW = d_mod(src_lon(sg, iPm1, jP), 360.0), latW = src_lat(sg, iPm1, jP);
+  double lonP, latP, lonN, latN, lonE, latE, lonS, latS, lonW, latW;
+  if (SEP) {  // regular source: three longitudes (already MOD 360: sg.lonm) and three latitudes describe the whole cross
+    lonP = sg.lonm[iP - 1]; lonE = sg.lonm[iPp1 - 1]; lonW = sg.lonm[iPm1 - 1];
+    latP = sg.lat1[jP - 1]; latN = sg.lat1[jPp1 - 1]; latS = sg.lat1[jPm1 - 1];
+    lonN = lonP; lonS = lonP; latE = latP; latW = latP;
+  } else {
+    lonP = d_mod(src_lon(sg, iP, jP), 360.0); latP = src_lat(sg, iP, jP);
+    lonN = d_mod(src_lon(sg, iP, jPp1), 360.0); latN = src_lat(sg, iP, jPp1);
+    lonE = d_mod(src_lon(sg, iPp1, jP), 360.0); latE = src_lat(sg, iPp1, jP);
+    lonS = d_mod(src_lon(sg, iP, jPm1), 360.0); latS = src_lat(sg, iP, jPm1);
+    lonW = d_mod(src_lon(sg, iPm1, jP), 360.0); latW = src_lat(sg, iPm1, jP);
+  }
   xP = d_mod(xP, 360.0);
-  double ya = src_merc(sg, iP, jP);
+  double ya = SEP ? sg.merc[jP - 1] : src_merc(sg, iP, jP);
   double hP = d_heading_y(lonP, xP, ya, d_merc(yP));
   double hN, hE, hS, hW;
   if (SEP) {
@@ -532,7 +539,7 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
   {
     // DISTANCE(xP, lonP, yP, latP) (:549).  The unit vectors are pure functions of (lon, lat): reuse the target's
     // (computed by the search for the same xP) and the source table entry when MOD() left the longitudes unchanged.
-    if (SEP && have_u && (lonP == src_lon(sg, iP, jP))) {
+    if (SEP && have_u && (sg.lonm_same || lonP == sg.lon1[iP - 1])) {
       // the search's winning dot product was formed from these very unit vectors in this very order, and its
       // distance is zr*ACOS(MIN(pds,1)): DISTANCE differs only by returning 0 when pds >= 1
       o.dnp = (best_pds >= 1.0) ? 0.f : (float)best_d;
@@ -547,22 +554,26 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
     switch (iqdrn) {
       case 1:
         loni[2] = lonE; lati[2] = latE;
-        loni[3] = d_mod(src_lon(sg, iPp1, jPp1), 360.0); lati[3] = src_lat(sg, iPp1, jPp1);
+        if (SEP) { loni[3] = lonE; lati[3] = latN; }
+        else { loni[3] = d_mod(src_lon(sg, iPp1, jPp1), 360.0); lati[3] = src_lat(sg, iPp1, jPp1); }
         loni[4] = lonN; lati[4] = latN;
         break;
       case 2:
         loni[2] = lonS; lati[2] = latS;
-        loni[3] = d_mod(src_lon(sg, iPp1, jPm1), 360.0); lati[3] = src_lat(sg, iPp1, jPm1);
+        if (SEP) { loni[3] = lonE; lati[3] = latS; }
+        else { loni[3] = d_mod(src_lon(sg, iPp1, jPm1), 360.0); lati[3] = src_lat(sg, iPp1, jPm1); }
         loni[4] = lonE; lati[4] = latE;
         break;
       case 3:
         loni[2] = lonW; lati[2] = latW;
-        loni[3] = d_mod(src_lon(sg, iPm1, jPm1), 360.0); lati[3] = src_lat(sg, iPm1, jPm1);
+        if (SEP) { loni[3] = lonW; lati[3] = latS; }
+        else { loni[3] = d_mod(src_lon(sg, iPm1, jPm1), 360.0); lati[3] = src_lat(sg, iPm1, jPm1); }
         loni[4] = lonS; lati[4] = latS;
         break;
       case 4:
         loni[2] = lonN; lati[2] = latN;
-        loni[3] = d_mod(src_lon(sg, iPm1, jPp1), 360.0); lati[3] = src_lat(sg, iPm1, jPp1);
+        if (SEP) { loni[3] = lonW; lati[3] = latN; }
+        else { loni[3] = d_mod(src_lon(sg, iPm1, jPp1), 360.0); lati[3] = src_lat(sg, iPm1, jPp1); }
         loni[4] = lonW; lati[4] = latW;
         break;
       default: break;
@@ -956,10 +967,12 @@ int bilin_prepare_src(sosie_ctx* ctx) {
     sg.separable = 1;
     sg.lon1 = Xin; sg.lat1 = ctx->s_lat1.p;
     sg.clon = ctx->s_clon.p; sg.slon = ctx->s_slon.p; sg.clat = ctx->s_clat.p; sg.slat = ctx->s_slat.p;
-    CK(ctx->s_head.alloc(2 * (size_t)nx + 2 * (size_t)nyw));
+    CK(ctx->s_head.alloc(3 * (size_t)nx + 2 * (size_t)nyw));
     double* hd = ctx->s_head.p;
-    k_heading_tables<<<cdiv(nx + nyw, 128), 128, 0, st>>>(sg, ctx->k_ew, hd, hd + nx, hd + 2 * nx, hd + 2 * nx + nyw); KLAUNCH_CHECK();
-    sg.hE = hd; sg.hW = hd + nx; sg.hN = hd + 2 * nx; sg.hS = hd + 2 * nx + nyw;
+    k_heading_tables<<<cdiv(nx + nyw, 128), 128, 0, st>>>(sg, ctx->k_ew, hd, hd + nx, hd + 2 * nx, hd + 2 * nx + nyw, hd + 2 * nx + 2 * nyw); KLAUNCH_CHECK();
+    sg.hE = hd; sg.hW = hd + nx; sg.hN = hd + 2 * nx; sg.hS = hd + 2 * nx + nyw; sg.lonm = hd + 2 * nx + 2 * nyw;
+    sg.lonm_same = 1;
+    for (int i = 0; i < nx; i++) if (!(fabs(ctx->h_axes[i]) < 360.0)) { sg.lonm_same = 0; break; }
   } else {
     size_t n = (size_t)nx * nyw;
     CK(ctx->s_X.alloc(n)); CK(ctx->s_Y.alloc(n)); CK(ctx->s_vx.alloc(n)); CK(ctx->s_vy.alloc(n)); CK(ctx->s_vz.alloc(n));

@@ -66,6 +66,8 @@ struct SrcGeom {
   const double* hW = nullptr;    // [nx]
   const double* hN = nullptr;    // [nyw]
   const double* hS = nullptr;    // [nyw]
+  const double* lonm = nullptr;  // [nx] MOD(lon1, 360.) as the body forms it (:495-499)
+  int lonm_same = 0;             // 1: every lon1 already satisfies |lon| < 360, MOD() changed nothing
   // uniform-axis hints of the EASY bracket search (0 = none): index guess = (r - v0) * inv_d, verified exactly
   double lon0 = 0.0, inv_dlon = 0.0, lat0 = 0.0, inv_dlat = 0.0;
 };
