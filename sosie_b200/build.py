@@ -64,7 +64,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     with open(os.path.join(OUT_DIR, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"]
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ccbin", "/usr/bin/g++", "-lcudart"]
     subprocess.check_call(cmd)
     if verbose:
         print("\n".join(log))
