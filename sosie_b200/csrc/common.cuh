@@ -149,6 +149,7 @@ struct sosie_ctx {
   DBuf<double> ak_zF, ak_ZF8, ak_sx, ak_sy, ak_sxy;  // per-slab work arrays
   DBuf<float> ak_stage1, ak_stage2;
   double ak_range[4] = {0, 0, 0, 0};
+  int ak_row_lo = 0, ak_row_hi = -1;  // rows of the (nx1+4,ny1+4) frame-extended slab holding needed points (1-based; empty: hi < lo)
 
   // ---- vertical stage (vert.cu)
   DBuf<float> v_vze, v_vz2, v_in, v_out;
