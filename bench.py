@@ -488,6 +488,16 @@ def run_ours(args):
     r0, r1 = row_shard(ny2, rank, world)
     if world > 1:
         ctx.bilin_set_shard(r0, r1)
+
+        # the search prelude of the end-to-end first call is assembled from the ranks' partial reductions (sosie_set_exchange):
+        # one small record per rank (~24 B per target column) all-gathered over NCCL, the only collective of the path
+        def allgather(send: bytes) -> bytes:
+            t = torch.frombuffer(bytearray(send), dtype=torch.uint8).to(dev)
+            out = torch.empty(world * t.numel(), dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(out, t)
+            return out.cpu().numpy().tobytes()
+        if not os.environ.get("SOSIE_BENCH_NO_EXCHANGE"):
+            ctx.set_exchange(world, allgather)
     my_targets = (r1 - r0 + 1) * nx2
 
     def step_dev():
@@ -595,10 +605,11 @@ def run_ours(args):
     nrow_src = max(0, src_rows[1] - src_rows[0] + 1)
     # bytes actually copied by the pipelined first call on this rank (csrc/bilin_pipeline.cu): both coordinate arrays
     # of the rank's target rows + the whole latitude array (search prelude) + the source rows its mapping reads
-    h2d = 8 * (nx1 + ny1) + 8 * my_targets + 8 * nt + 4 * nx1 * nrow_src
+    xchg = bool(ctx.exchange_used()) if not args.no_e2e else False
+    h2d = 8 * (nx1 + ny1) + 8 * my_targets + (8 * (my_targets + 4 * nx2) if xchg else 8 * nt) + 4 * nx1 * nrow_src
     d2h = 4 * my_targets + (3 * 4 + 2 * 8 + 2 + 4) * my_targets
     e2e = {"value": nt / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
-           "source_rows_uploaded": [int(src_rows[0]) + 1, int(src_rows[1]) + 1, ny1],
+           "source_rows_uploaded": [int(src_rows[0]) + 1, int(src_rows[1]) + 1, ny1], "prelude_exchange": xchg,
            "without_mapping_download": {"value": nt / e2e_nomap_s, "ms_per_step": e2e_nomap_s * 1e3, "d2h_bytes_per_step": 4 * my_targets,
                                         "note": "same call with NULL mapping pointers: the mapping stays in HBM (no mapping file wanted)"},
            "note": "sosie_bilin_2d_first from pinned host arrays, per rank: target coordinates + the source rows the mapping "

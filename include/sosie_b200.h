@@ -59,6 +59,20 @@ int sosie_get_timing(sosie_ctx* ctx, int32_t id, float* ms);
  * Only the regular-source (EASY) search shards; the curvilinear-source chain is not split.           */
 int sosie_bilin_set_shard(sosie_ctx* ctx, int32_t j0, int32_t j1);
 
+/* Row-sharded jobs, end to end from host arrays (sosie_bilin_2d_first on a context with sosie_bilin_set_shard): the
+ * search prelude FIND_NEAREST_POINT (src/mod_manip.f90:888-947) reduces the WHOLE target latitude array (row range covered
+ * by the source, monotony, regularity), which would make every rank upload every row.  With an all-gather callback the
+ * ranks reduce their own rows and exchange one small record each (some scalars + 24 bytes per target column): the only
+ * collective of the path, supplied by the host program (MPI_Allgather, torch.distributed, ...).  fn(user, send, recv,
+ * bytes) must gather `bytes` bytes from every rank into recv (nranks * bytes, any rank order), return 0, and is called at
+ * most once per first call, by all ranks or by none.  The ranks' shards must tile the target rows.  The combined prelude is
+ * the sequential one bit for bit (min / max / first occurrence only); if no rank can prove the target grid irregular the
+ * library falls back to the whole-array prelude.  fn = NULL switches the exchange off.
+ * sosie_exchange_used: 1 when the last first call took the exchange path.                                          */
+typedef int (*sosie_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
+int sosie_set_exchange(sosie_ctx* ctx, int32_t nranks, sosie_allgather_fn fn, void* user);
+int sosie_exchange_used(sosie_ctx* ctx);
+
 /* ---- bilinear: grids -> mapping -> apply -------------------------------------------------------
  * Replaces BILIN_2D / MAPPING_BL / INTERP_BL, src/mod_bilin_2d.f90:44-361,366-691, and the search
  * FIND_NEAREST_POINT/_EASY/_TWISTED, src/mod_manip.f90:834-1440.

@@ -44,7 +44,7 @@ EXPORTS = [
     "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
     "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev", "sosie_bilin_get_map_dev", "sosie_bilin_load_map_dev",
     "sosie_akima_1d_1d", "sosie_akima_1d_1d_dev", "sosie_interp3d_sigma", "sosie_interp3d_sigma_dev",
-    "sosie_track_interp", "sosie_track_interp_dev",
+    "sosie_track_interp", "sosie_track_interp_dev", "sosie_set_exchange", "sosie_exchange_used",
 ]
 
 _lib = None
@@ -190,6 +190,33 @@ class Sosie:
         self._ck(self._lib.sosie_bilin_set_shard(self._h, int(j0), int(j1)))
 
     # ---------------------------------------------------------------- bilinear
+    ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t)
+
+    def set_exchange(self, nranks, allgather):
+        """prelude exchange of row-sharded first calls (sosie_set_exchange).  allgather(send: bytes) -> bytes of every rank's
+        record concatenated (nranks * len(send)); None switches it off."""
+        if allgather is None:
+            self._xchg_cb = None
+            self._ck(self._lib.sosie_set_exchange(self._h, 0, None, None))
+            return
+
+        def _cb(user, send, recv, nbytes):
+            try:
+                out = allgather(C.string_at(send, nbytes))
+                if len(out) != nbytes * nranks:
+                    return 2
+                C.memmove(recv, out, len(out))
+                return 0
+            except Exception:  # noqa: BLE001 - reported through the C return code
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._xchg_cb = self.ALLGATHER_FN(_cb)   # keep the trampoline alive
+        self._ck(self._lib.sosie_set_exchange(self._h, int(nranks), self._xchg_cb, None))
+
+    def exchange_used(self):
+        return bool(self._lib.sosie_exchange_used(self._h))
+
     def bilin_set_grids(self, k_ew_per, X10, Y10, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0):
         X10, Y10, X20, Y20 = _f64(X10), _f64(Y10), _f64(X20), _f64(Y20)
         src_1d, trg_1d = X10.ndim == 1, X20.ndim == 1

@@ -15,6 +15,7 @@
 //     (a margin 100x larger than any rounding wiggle of acos): identical argmin, ~10x fewer acos.
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include "geom.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -63,8 +64,10 @@ __global__ void k_minmax(const double* __restrict__ a, size_t n, unsigned long l
 }
 
 // L_IS_GRID_REGULAR (src/mod_manip.f90:1632-1663), both tests, on a 2-D (nx,ny) pair
+// ya..yb (1-based): the rows the column test b/ sums over -- all of them, or (prelude exchange) one rank's rows, where a
+// partial sum above the tolerance already proves the total is
 __global__ void k_is_regular(const double* __restrict__ X, const double* __restrict__ Y, int nx, int ny, int ja, int jb,
-                             int* irreg) {
+                             int* irreg, int ya = 1, int yb = 0x7fffffff) {
   const double tol = (double)1.E-12f;
   __shared__ double sh[32];
   __shared__ int stop;
@@ -91,7 +94,7 @@ __global__ void k_is_regular(const double* __restrict__ X, const double* __restr
   if (*(volatile int*)irreg) return;
   for (int ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nx; ji += gridDim.x * blockDim.x) {
     double s = 0.0;
-    for (int jj = 0; jj < ny; jj++) s += fabs(Y[(size_t)ji + (size_t)jj * nx] - Y[(size_t)jj * nx]);
+    for (int jj = max(ya, 1) - 1; jj < min(yb, ny); jj++) s += fabs(Y[(size_t)ji + (size_t)jj * nx] - Y[(size_t)jj * nx]);
     if (s > tol) atomicOr(irreg, 2);
   }
 }
@@ -148,15 +151,15 @@ struct ColPart {
   unsigned long long emin, emax;   // order-preserving encodings; ~0 / 0 = mask empty in this chunk
   int jmin, jmax;                  // first rows (1-based) attaining them
 };
-__global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, ColPart* part) {
+__global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, ColPart* part, int jfirst, int jlast) {
   const double y_min_s = dec_d(p->ymin_s), y_max_s = dec_d(p->ymax_s);   // MINVAL / MAXVAL(Ysrc), reduced by k_minmax before
   const double sgn = d_sign(1.0, p->rtmp);
-  const int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
+  const int nchunk = (jlast - jfirst + 1 + JR_ROWS - 1) / JR_ROWS;   // rows jfirst..jlast (1-based): all of them, or one rank's
   const size_t total = (size_t)tg.nx * nchunk;
   unsigned long long gmin = ~0ULL, gmax = 0ULL, gdl = ~0ULL;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
     const int i = (int)(t % tg.nx) + 1, c = (int)(t / tg.nx);
-    const int j0 = c * JR_ROWS + 1, j1 = min(tg.ny, (c + 1) * JR_ROWS);
+    const int j0 = jfirst + c * JR_ROWS, j1 = min(jlast, j0 + JR_ROWS - 1);
     ColPart cp;
     cp.emin = ~0ULL; cp.emax = 0ULL; cp.jmin = 0; cp.jmax = 0;
     double prev = (j0 > 1 && do_dlat) ? trg_lat(tg, i, j0 - 1) : 0.0;
@@ -193,6 +196,19 @@ __global__ void k_jrange_cols(int nx, int nchunk, const ColPart* __restrict__ pa
     }
     if (jmin > 0) atomicMin(&p->j_strt, jmin);
     atomicMax(&p->j_stop, jmax);   // MAXLOC of an empty mask is 0
+  }
+}
+// the same combination, kept per column: what one rank contributes to the prelude exchange
+__global__ void k_colpart_combine(int nx, int nchunk, const ColPart* __restrict__ part, ColPart* out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    ColPart r;
+    r.emin = ~0ULL; r.emax = 0ULL; r.jmin = 0; r.jmax = 0;
+    for (int c = 0; c < nchunk; c++) {
+      const ColPart cp = part[(size_t)c * nx + i];
+      if (cp.jmin > 0 && cp.emin < r.emin) { r.emin = cp.emin; r.jmin = cp.jmin; }
+      if (cp.jmax > 0 && (cp.emax > r.emax || r.jmax == 0)) { r.emax = cp.emax; r.jmax = cp.jmax; }
+    }
+    out[i] = r;
   }
 }
 __global__ void k_fill_u64(unsigned long long* a, size_t n, unsigned long long v) {
@@ -898,7 +914,7 @@ int fetch_small(sosie_ctx* ctx, const void* dsrc, void* hdst, size_t bytes) {
   return SOSIE_OK;
 }
 // two objects, one stream synchronisation
-static int fetch_pair(sosie_ctx* ctx, const void* d1, void* h1, size_t b1, const void* d2, void* h2, size_t b2) {
+int fetch_pair(sosie_ctx* ctx, const void* d1, void* h1, size_t b1, const void* d2, void* h2, size_t b2) {
   const size_t o2 = (b1 + 15) & ~(size_t)15;
   if (o2 + b2 > SOSIE_MAILBOX_BYTES) { if (int rc = fetch_small(ctx, d1, h1, b1)) return rc; return fetch_small(ctx, d2, h2, b2); }
   if (!ctx->mailbox) CK(cudaHostAlloc((void**)&ctx->mailbox, SOSIE_MAILBOX_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));
@@ -1011,6 +1027,7 @@ static int is_sorted_host(const std::vector<double>& v, int off, int n) {
 // pipelined first call (bilin_pipeline.cu) uploads only row 1 and its shard's rows.  L_IS_GRID_REGULAR is then
 // evaluated on those rows; an irregular row settles it (any one does), otherwise *need_full_x is set and the
 // caller must complete the array and call again.
+int prelude_finish(sosie_ctx* ctx, MapPlan* pl, const Prelude& hp);
 int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool* need_full_x) {
   SrcGeom& sg = ctx->sg;
   TrgGeom& tg = ctx->tg;
@@ -1040,11 +1057,94 @@ int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool*
   const int nchunk = (tg.ny + JR_ROWS - 1) / JR_ROWS;
   const size_t tot = (size_t)tg.nx * nchunk;
   WS(ColPart, part, tot);
-  k_ypass<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, dpre.p, do_dlat, part.p); KLAUNCH_CHECK();
+  k_ypass<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, dpre.p, do_dlat, part.p, 1, tg.ny); KLAUNCH_CHECK();
   k_jrange_cols<<<cdiv(tg.nx, 128), 128, 0, st>>>(tg.nx, nchunk, part.p, dpre.p); KLAUNCH_CHECK();
   Prelude hp;
   if (int rc = fetch_small(ctx, dpre.p, &hp, sizeof(Prelude))) return rc;
   if (partial_x && hp.irreg_t == 0) { if (need_full_x) *need_full_x = true; return SOSIE_OK; }
+  return prelude_finish(ctx, pl, hp);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The prelude over ONE rank's target rows, exchanged between the ranks of a row-sharded job (sosie_set_exchange): every
+// quantity the prelude reduces from the target latitudes is a min / max / first-occurrence over rows, so the ranks reduce
+// their own rows (plus the row below, for the row-to-row differences; plus the two rows of :921, which every rank holds),
+// all-gather one small record each -- scalars and one ColPart per target column -- and combine them in row order into
+// exactly the Prelude a pass over the whole array gives.  The regularity test is only conclusive one way: a rank whose
+// rows differ from row 1 proves the grid irregular (sums of non-negative terms only grow); when no rank can tell, the
+// caller uploads the whole arrays and runs the ordinary prelude.
+struct XchgHead {
+  int32_t j_a, j_b;         // rows reduced by this rank (1-based, inclusive)
+  int32_t irreg_t, nx;
+  unsigned long long ymin_t, ymax_t, rmin_dlat;
+  double rtmp;
+};
+
+int bilin_map_prelude_exchange(sosie_ctx* ctx, MapPlan* pl, int ja, int jb, bool* undecided) {
+  SrcGeom& sg = ctx->sg;
+  TrgGeom& tg = ctx->tg;
+  cudaStream_t st = ctx->stream;
+  *undecided = false;
+  const size_t blob = sizeof(XchgHead) + sizeof(ColPart) * (size_t)tg.nx;
+  if (!ctx->xchg_fn || ctx->xchg_nranks < 2 || blob > SOSIE_MAILBOX_BYTES || tg.is_1d || !sg.separable) { *undecided = true; return SOSIE_OK; }
+  ctx->ws_cursor = 0;
+  CK(ctx->d_scratch.alloc(64)); CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
+  Prelude* dp = reinterpret_cast<Prelude*>(ctx->d_scratch.p);
+  k_prelude_init<<<1, 1, 0, st>>>(dp); KLAUNCH_CHECK();
+  k_minmax<<<grid_for(ctx, sg.nyw, 256), 256, 0, st>>>(sg.lat1, sg.nyw, &dp->ymin_s, &dp->ymax_s); KLAUNCH_CHECK();
+  k_is_regular<<<grid_for(ctx, (size_t)tg.ny * 32, 256), 256, 0, st>>>(tg.X, tg.Y, tg.nx, tg.ny, std::max(2, ja), jb, &dp->irreg_t, ja, jb); KLAUNCH_CHECK();
+  const int do_dlat = (tg.nx > 2) ? 1 : 0;
+  if (do_dlat) { k_rtmp<<<1, 1024, 0, st>>>(tg, dp); KLAUNCH_CHECK(); }
+  const int nchunk = (jb - ja + 1 + JR_ROWS - 1) / JR_ROWS;
+  const size_t tot = (size_t)tg.nx * nchunk;
+  WS(ColPart, part, tot);
+  WS(unsigned char, dblob, blob);
+  k_ypass<<<grid_for(ctx, tot, 256), 256, 0, st>>>(tg, dp, do_dlat, part.p, ja, jb); KLAUNCH_CHECK();
+  k_colpart_combine<<<cdiv(tg.nx, 128), 128, 0, st>>>(tg.nx, nchunk, part.p, reinterpret_cast<ColPart*>(dblob.p + sizeof(XchgHead))); KLAUNCH_CHECK();
+  std::vector<unsigned char> mine(blob), all(blob * (size_t)ctx->xchg_nranks);
+  Prelude hp;
+  if (int rc = fetch_pair(ctx, dp, &hp, sizeof(Prelude), dblob.p + sizeof(XchgHead), mine.data() + sizeof(XchgHead), sizeof(ColPart) * (size_t)tg.nx)) return rc;
+  XchgHead hd;
+  hd.j_a = ja; hd.j_b = jb; hd.irreg_t = hp.irreg_t; hd.nx = tg.nx;
+  hd.ymin_t = hp.ymin_t; hd.ymax_t = hp.ymax_t; hd.rmin_dlat = hp.rmin_dlat; hd.rtmp = hp.rtmp;
+  memcpy(mine.data(), &hd, sizeof(hd));
+  if (ctx->xchg_fn(ctx->xchg_user, mine.data(), all.data(), blob) != 0) { ctx->err = "prelude exchange: the all-gather callback failed"; return SOSIE_ERR_ARG; }
+  // combine in row order
+  std::vector<int> order(ctx->xchg_nranks);
+  for (int r = 0; r < ctx->xchg_nranks; r++) order[r] = r;
+  auto head = [&](int r) { XchgHead h; memcpy(&h, all.data() + blob * (size_t)r, sizeof(h)); return h; };
+  std::sort(order.begin(), order.end(), [&](int a, int b) { return head(a).j_a < head(b).j_a; });
+  int expect = 1, irreg = 0;
+  for (int q = 0; q < ctx->xchg_nranks; q++) {
+    const XchgHead h = head(order[q]);
+    if (h.nx != tg.nx || h.j_a != expect || h.j_b < h.j_a) { ctx->err = "prelude exchange: the ranks' row shards do not tile the target grid"; return SOSIE_ERR_ARG; }
+    expect = h.j_b + 1;
+    hp.ymin_t = std::min(hp.ymin_t, h.ymin_t); hp.ymax_t = std::max(hp.ymax_t, h.ymax_t); hp.rmin_dlat = std::min(hp.rmin_dlat, h.rmin_dlat);
+    irreg |= h.irreg_t;
+  }
+  if (expect != tg.ny + 1) { ctx->err = "prelude exchange: the ranks' row shards do not tile the target grid"; return SOSIE_ERR_ARG; }
+  if (!irreg) { *undecided = true; return SOSIE_OK; }
+  hp.irreg_t = irreg;
+  int j_strt = 2147483647, j_stop = 0;
+  for (int i = 0; i < tg.nx; i++) {
+    unsigned long long emin = ~0ULL, emax = 0ULL;
+    int jmin = 0, jmax = 0;
+    for (int q = 0; q < ctx->xchg_nranks; q++) {
+      ColPart cp;
+      memcpy(&cp, all.data() + blob * (size_t)order[q] + sizeof(XchgHead) + sizeof(ColPart) * (size_t)i, sizeof(cp));
+      if (cp.jmin > 0 && cp.emin < emin) { emin = cp.emin; jmin = cp.jmin; }
+      if (cp.jmax > 0 && (cp.emax > emax || jmax == 0)) { emax = cp.emax; jmax = cp.jmax; }
+    }
+    if (jmin > 0) j_strt = std::min(j_strt, jmin);
+    j_stop = std::max(j_stop, jmax);
+  }
+  hp.j_strt = j_strt; hp.j_stop = j_stop;
+  return prelude_finish(ctx, pl, hp);
+}
+
+// host part of the prelude: the decisions of FIND_NEAREST_POINT (:888-947) from the reduced scalars
+int prelude_finish(sosie_ctx* ctx, MapPlan* pl, const Prelude& hp) {
+  TrgGeom& tg = ctx->tg;
   const double y_min_s = dec_d_host(hp.ymin_s), y_max_s = dec_d_host(hp.ymax_s);
   const double y_min_t = dec_d_host(hp.ymin_t), y_max_t = dec_d_host(hp.ymax_t);
   const bool l_is_reg_s = (hp.irreg_s == 0), l_is_reg_t = (hp.irreg_t == 0);
@@ -1115,6 +1215,10 @@ int bilin_map_alloc(sosie_ctx* ctx) {
 
 int bilin_map_impl(sosie_ctx* ctx) {
   if (!ctx->grids_set) { ctx->err = "sosie_bilin_map: grids not set"; return SOSIE_ERR_STATE; }
+  if (ctx->trg_partial) {
+    ctx->err = "sosie_bilin_map: the sharded first call kept only this rank's target coordinates on the device; call sosie_bilin_set_grids again";
+    return SOSIE_ERR_STATE;
+  }
   SrcGeom& sg = ctx->sg;
   TrgGeom& tg = ctx->tg;
   cudaStream_t st = ctx->stream;

@@ -139,17 +139,38 @@ static int pipelined_run(sosie_ctx* ctx, Pipe& P, int k_ew, int nx1, int ny1, co
     e_in[c] = P.ev();
     CK(cudaEventRecord(e_in[c], P.h2d));
   }
-  // the rest of the latitudes (prelude), row 1 of the longitudes (L_IS_GRID_REGULAR compares every row with it)
-  if (r0 > 0) {
-    CK(cudaMemcpyAsync(ctx->t_Y.p, Y20, (size_t)r0 * nx2 * 8, cudaMemcpyHostToDevice, P.h2d));
-    CK(cudaMemcpyAsync(ctx->t_X.p, X20, (size_t)nx2 * 8, cudaMemcpyHostToDevice, P.h2d));
-    if (mask) CK(cudaMemcpyAsync(ctx->t_mask.p, mask, (size_t)r0 * nx2 * 4, cudaMemcpyHostToDevice, P.h2d));
-  }
-  if (r1 < ny2 - 1) {
-    const size_t off = (size_t)(r1 + 1) * nx2, cnt = (size_t)(ny2 - 1 - r1) * nx2;
-    CK(cudaMemcpyAsync(ctx->t_Y.p + off, Y20 + off, cnt * 8, cudaMemcpyHostToDevice, P.h2d));
-    if (mask) CK(cudaMemcpyAsync(ctx->t_mask.p + off, mask + off, cnt * 4, cudaMemcpyHostToDevice, P.h2d));
-  }
+  // What the prelude needs beyond this shard's rows.  With an exchange callback (sosie_set_exchange) the ranks reduce their
+  // own rows and swap the results: only the row below the shard (row-to-row differences), the two rows of :921 and row 1
+  // of the longitudes (L_IS_GRID_REGULAR compares every row with it) are uploaded.  Without it: the rest of the latitudes.
+  const bool partial = (r0 > 0 || r1 < ny2 - 1);
+  const bool xchg = partial && ctx->xchg_fn && ctx->xchg_nranks > 1 && nx2 > 2 &&
+                    sizeof(double) * 8 + (size_t)24 * nx2 + 64 <= SOSIE_MAILBOX_BYTES;
+  auto up_rows = [&](const double* src, double* dst, int ja, int jb) -> int {   // 0-based inclusive rows, skipped when inside the shard
+    for (int j = ja; j <= jb; j++) {
+      if (j < 0 || j >= ny2 || (j >= r0 && j <= r1)) continue;
+      CK(cudaMemcpyAsync(dst + (size_t)j * nx2, src + (size_t)j * nx2, (size_t)nx2 * 8, cudaMemcpyHostToDevice, P.h2d));
+    }
+    return SOSIE_OK;
+  };
+  auto up_rest = [&]() -> int {
+    if (r0 > 0) {
+      CK(cudaMemcpyAsync(ctx->t_Y.p, Y20, (size_t)r0 * nx2 * 8, cudaMemcpyHostToDevice, P.h2d));
+      CK(cudaMemcpyAsync(ctx->t_X.p, X20, (size_t)nx2 * 8, cudaMemcpyHostToDevice, P.h2d));
+      if (mask) CK(cudaMemcpyAsync(ctx->t_mask.p, mask, (size_t)r0 * nx2 * 4, cudaMemcpyHostToDevice, P.h2d));
+    }
+    if (r1 < ny2 - 1) {
+      const size_t off = (size_t)(r1 + 1) * nx2, cnt = (size_t)(ny2 - 1 - r1) * nx2;
+      CK(cudaMemcpyAsync(ctx->t_Y.p + off, Y20 + off, cnt * 8, cudaMemcpyHostToDevice, P.h2d));
+      if (mask) CK(cudaMemcpyAsync(ctx->t_mask.p + off, mask + off, cnt * 4, cudaMemcpyHostToDevice, P.h2d));
+    }
+    return SOSIE_OK;
+  };
+  if (xchg) {
+    const int jm = ny2 / 2;                                    // 1-based row of :921; rows jm-1, jm -> 0-based jm-2, jm-1
+    if (int rc = up_rows(Y20, ctx->t_Y.p, r0 - 1, r0 - 1)) return rc;
+    if (int rc = up_rows(Y20, ctx->t_Y.p, jm - 2, jm - 1)) return rc;
+    if (int rc = up_rows(X20, ctx->t_X.p, 0, 0)) return rc;
+  } else if (int rc = up_rest()) return rc;
   cudaEvent_t e_coords = P.ev();
   CK(cudaEventRecord(e_coords, P.h2d));
   P.mark("coords uploaded (h2d)", P.h2d);
@@ -181,12 +202,23 @@ static int pipelined_run(sosie_ctx* ctx, Pipe& P, int k_ew, int nx1, int ny1, co
   // ---- prelude on the complete latitude array; validate the speculation
   CK(cudaStreamWaitEvent(sc, e_coords, 0));
   MapPlan pl;
-  bool need_full_x = false;
-  const bool partial = (r0 > 0 || r1 < ny2 - 1);
-  if (int rc = bilin_map_prelude(ctx, &pl, partial ? r0 + 1 : 0, partial ? r1 + 1 : 0, &need_full_x)) return rc;
-  if (need_full_x) {  // every resident row equals row 1: the grid may be regular, the test needs all rows
-    CK(cudaMemcpyAsync(ctx->t_X.p, X20, nt * 8, cudaMemcpyHostToDevice, sc));
-    if (int rc = bilin_map_prelude(ctx, &pl, 0, 0, nullptr)) return rc;
+  bool need_full_x = false, undecided = !xchg;
+  ctx->xchg_used = 0;
+  if (xchg) {
+    if (int rc = bilin_map_prelude_exchange(ctx, &pl, r0 + 1, r1 + 1, &undecided)) return rc;
+    if (undecided) {   // no rank could prove the target irregular: the ordinary prelude, on the whole arrays
+      if (int rc = up_rest()) return rc;
+      cudaEvent_t e_rest = P.ev();
+      CK(cudaEventRecord(e_rest, P.h2d));
+      CK(cudaStreamWaitEvent(sc, e_rest, 0));
+    } else ctx->xchg_used = 1;
+  }
+  if (undecided) {
+    if (int rc = bilin_map_prelude(ctx, &pl, partial ? r0 + 1 : 0, partial ? r1 + 1 : 0, &need_full_x)) return rc;
+    if (need_full_x) {  // every resident row equals row 1: the grid may be regular, the test needs all rows
+      CK(cudaMemcpyAsync(ctx->t_X.p, X20, nt * 8, cudaMemcpyHostToDevice, sc));
+      if (int rc = bilin_map_prelude(ctx, &pl, 0, 0, nullptr)) return rc;
+    }
   }
   if (!pl.reg_s) { ctx->err = "internal: pipelined first call with an irregular source"; return SOSIE_ERR_ARG; }
   std::vector<int> herr(SOSIE_ISCRATCH);
@@ -211,7 +243,7 @@ static int pipelined_run(sosie_ctx* ctx, Pipe& P, int k_ew, int nx1, int ny1, co
   for (int c = 0; c < nchunk; c++) e_all |= herr[8 + c];
   if (e_all & 1) { ctx->err = "ERROR (L_InPoly of mod_poly.f90): we only expect positive longitudes!"; return SOSIE_ERR_REF_STOP; }
   if (e_all & 6) { ctx->err = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)"; return SOSIE_ERR_REF_STOP; }
-  ctx->grids_set = true; ctx->map_ready = true; ctx->map_nt = nt;
+  ctx->grids_set = true; ctx->map_ready = true; ctx->map_nt = nt; ctx->trg_partial = partial;
   ctx->pack_ready = true; ctx->pack_gen++; ctx->boxes_ready = false;
 
   // ---- source slab rows the records read, apply, result

@@ -88,6 +88,14 @@ int sosie_bilin_set_shard(sosie_ctx* c, int32_t j0, int32_t j1) {
   return SOSIE_OK;
 }
 
+int sosie_set_exchange(sosie_ctx* c, int32_t nranks, sosie_allgather_fn fn, void* user) {
+  NEED(c);
+  if (fn && nranks < 1) { ctx->err = "sosie_set_exchange: nranks must be >= 1"; return SOSIE_ERR_ARG; }
+  ctx->xchg_fn = fn; ctx->xchg_user = user; ctx->xchg_nranks = fn ? nranks : 0;
+  return SOSIE_OK;
+}
+int sosie_exchange_used(sosie_ctx* c) { return c ? c->xchg_used : 0; }
+
 // ---------------------------------------------------------------------------------------------------
 static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_1d, int l_reg_src, int nx2, int ny2, int trg_1d,
                             const int32_t* dmask, bool mask_on_device, int i_orca_trg) {
@@ -101,6 +109,7 @@ static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_
   ctx->tg.nx = nx2; ctx->tg.ny = ny2; ctx->tg.is_1d = trg_1d ? 1 : 0;
   ctx->tg.X = ctx->t_X.p; ctx->tg.Y = ctx->t_Y.p;
   const size_t nt = (size_t)nx2 * ny2;
+  ctx->trg_partial = false;
   CK(ctx->t_mask.alloc(nt));
   if (dmask) {
     CK(cudaMemcpyAsync(ctx->t_mask.p, dmask, nt * sizeof(int32_t), mask_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));

@@ -92,6 +92,12 @@ struct sosie_ctx {
   bool grids_set = false, map_ready = false, pack_ready = false;
   size_t map_nt = 0;             // target count the cached mapping was built/loaded for
   int shard_j0 = 0, shard_j1 = 0; // 1-based inclusive target rows handled by this context (0,0 = all)
+  // prelude exchange between the ranks of a row-sharded job (sosie_set_exchange); NULL: every rank reduces the whole grid
+  int (*xchg_fn)(void*, const void*, void*, size_t) = nullptr;
+  void* xchg_user = nullptr;
+  int xchg_nranks = 0;
+  int xchg_used = 0;            // 1: the last pipelined first call took the exchange path
+  bool trg_partial = false;     // the pipelined first call of a sharded context left only part of the target coordinates in HBM
   // ---- per-kernel CUDA-event timing (sosie_profile / sosie_get_timing)
   bool prof = false;
   cudaEvent_t ev0[SOSIE_T_COUNT] = {}, ev1[SOSIE_T_COUNT] = {};
@@ -240,12 +246,15 @@ struct MapPlan {
 #define SOSIE_MAILBOX_BYTES (512 * 1024)
 // device -> host read-back of a small object through the mailbox (synchronises the context stream)
 int fetch_small(sosie_ctx* ctx, const void* dsrc, void* hdst, size_t bytes);
+int fetch_pair(sosie_ctx* ctx, const void* d1, void* h1, size_t b1, const void* d2, void* h2, size_t b2);
 
 // entry points implemented in the other translation units
 int bilin_materialize_mask(sosie_ctx* ctx);   // fills t_mask with 1 if it is still virtual
 int bilin_map_impl(sosie_ctx* ctx);
 int bilin_map_alloc(sosie_ctx* ctx);
 int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool* need_full_x);
+// rows ja..jb (1-based) reduced here, the rest obtained from the other ranks; *undecided: fall back to the full prelude
+int bilin_map_prelude_exchange(sosie_ctx* ctx, MapPlan* pl, int ja, int jb, bool* undecided);
 int bilin_easy_prepare(sosie_ctx* ctx);
 int bilin_easy_rows(sosie_ctx* ctx, int jlo, int jhi, size_t k0, size_t kcnt, int* derr);
 int bilin_pack_range(sosie_ctx* ctx, size_t k0, size_t kcnt);

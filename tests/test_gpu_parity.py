@@ -308,6 +308,83 @@ def test_pipelined_regular_2d_target_sharded(gpu, orc):
     assert mg["info"][4] == 1   # l_is_reg_t
 
 
+def _run_ranks_with_exchange(nranks, shards, call):
+    """nranks contexts on this GPU, one thread each, as the ranks of a row-sharded job; the all-gather is a barrier over a list"""
+    import threading
+    import sosie_b200
+    ctxs = [sosie_b200.Sosie(0) for _ in range(nranks)]
+    slots = [None] * nranks
+    bar = threading.Barrier(nranks)
+    out, errs = [None] * nranks, [None] * nranks
+
+    def worker(r):
+        def allgather(send):
+            slots[r] = send
+            bar.wait(timeout=60)
+            allb = b"".join(slots[(q + 1) % nranks] for q in range(nranks))   # any rank order is allowed
+            bar.wait(timeout=60)
+            return allb
+        try:
+            c = ctxs[r]
+            c.set_pipeline_min_targets(0)
+            c.bilin_set_shard(*shards[r])
+            c.set_exchange(nranks, allgather)
+            out[r] = call(c) + (c.exchange_used(),)
+        except Exception as e:  # noqa: BLE001
+            errs[r] = e
+            bar.abort()
+    th = [threading.Thread(target=worker, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for c in ctxs:
+        c.close() if hasattr(c, "close") else None
+    for e in errs:
+        if e is not None:
+            raise e
+    return out
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+@pytest.mark.parametrize("case", ["E", "restricted", "reg2d"])
+def test_sharded_first_call_with_prelude_exchange(orc, nranks, case):
+    """Row-sharded first call where each rank uploads only its own target rows and the FIND_NEAREST_POINT prelude is
+    assembled from the ranks' partial reductions (sosie_set_exchange): mapping, fields and the prelude's decisions equal the
+    oracle's.  'restricted': the prelude cuts the searched rows (speculation redone); 'reg2d': no rank can prove the target
+    irregular, the library falls back to the whole-array prelude."""
+    if case == "E":
+        cfg = G.config("E", 0.02)
+        lon_s, lat_s = cfg["src_lon"], cfg["src_lat"]
+        Xt, Yt = G.trg_2d(cfg)
+    elif case == "restricted":
+        lon_s = (np.arange(720) + 0.5) * 0.5
+        lat_s = 24.0 + np.arange(70) * 0.5
+        Xt, Yt = G.trg_2d(G.config("E", 0.012))
+    else:
+        cfg = G.config("D", 0.06)
+        lon_s, lat_s = cfg["src_lon"], cfg["src_lat"]
+        Xt, Yt = G.expand_2d((np.arange(90) + 0.5) * 4.0, -80.0 + np.arange(60) * 2.5)
+    Xs, Ys = G.expand_2d(lon_s, lat_s)
+    Z1 = G.field_slabs(Xs, Ys, 2, seed=12)
+    ny = Xt.shape[0]
+    cuts = [0] + [ny * (r + 1) // nranks for r in range(nranks)]
+    shards = [(cuts[r] + 1, cuts[r + 1]) for r in range(nranks)]
+    res = _run_ranks_with_exchange(nranks, shards, lambda c: c.bilin_2d_first(0, lon_s, lat_s, Z1, Xt, Yt, l_reg_src=True))
+    Z2o, mo = orc.bilin_2d(0, lon_s, lat_s, Z1, Xt, Yt, l_reg_src=True)
+    for r, (Z2g, mg, used) in enumerate(res):
+        assert used == (case != "reg2d"), (case, r, used)
+        rows = slice(shards[r][0] - 1, shards[r][1])
+        for k in ("metrics", "alphabeta"):
+            assert np.array_equal(mg[k][:, rows], mo[k][:, rows]), (case, r, k)
+        for k in ("ipb", "dist_np"):
+            assert np.array_equal(mg[k][rows], mo[k][rows]), (case, r, k)
+        assert np.array_equal(Z2g[:, rows], Z2o[:, rows]), (case, r)
+        assert tuple(mg["info"][:5]) == tuple(mo["info"][:5]), (case, r, mg["info"], mo["info"])
+    if case == "restricted":
+        assert mo["info"][0] > 1 and mo["info"][1] < ny
+
+
 # ---------------------------------------------------------------------------------------------------
 # SURVEY 8f rank 3: the 1 x N trajectory front ends (interp_to_ground_track.f90:627,750, interp_to_hydro_section.f90:464,601)
 # call MAPPING_BL with (1, N) target arrays and INTERP_BL point by point
