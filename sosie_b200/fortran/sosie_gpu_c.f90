@@ -132,6 +132,28 @@ MODULE SOSIE_GPU_C
          REAL(C_FLOAT), INTENT(out) :: xf2(*)
          REAL(C_FLOAT), VALUE  :: rfill_val
       END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_set_exchange(ctx, nranks, fn, user) BIND(C, name='sosie_set_exchange')
+         !! prelude exchange of a row-sharded first call: fn = C_FUNLOC of an all-gather (e.g. a wrapper of MPI_Allgather on bytes)
+         IMPORT :: C_PTR, C_INT, C_FUNPTR
+         TYPE(C_PTR), VALUE    :: ctx, user
+         INTEGER(C_INT), VALUE :: nranks
+         TYPE(C_FUNPTR), VALUE :: fn
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_track_interp(ctx, ni, nj, nk, F1, F2, vt1, vt2, imask, n, rt, jiP, jjP, iqd, xa, xb, r_obs, &
+         &                                       obs_lo, obs_hi, clip_missing, rmissval, f_bl, f_np, fmask) BIND(C, name='sosie_track_interp')
+         !! per-point block of interp_to_ground_track.f90:718-779 (F2 = second model record) / interp_to_hydro_section.f90:567-607 (F2 = C_NULL_PTR)
+         IMPORT :: C_PTR, C_INT, C_INT64_T, C_FLOAT, C_DOUBLE, C_SIGNED_CHAR
+         TYPE(C_PTR), VALUE        :: ctx, F2, rt       !! F2, rt: C_LOC(array) or C_NULL_PTR
+         INTEGER(C_INT), VALUE     :: ni, nj, nk, clip_missing
+         INTEGER(C_INT64_T), VALUE :: n
+         REAL(C_FLOAT), INTENT(in) :: F1(*)
+         REAL(C_DOUBLE), VALUE     :: vt1, vt2, obs_lo, obs_hi, rmissval
+         INTEGER(C_SIGNED_CHAR), INTENT(in) :: imask(*)
+         INTEGER(C_INT), INTENT(in) :: jiP(*), jjP(*), iqd(*)
+         REAL(C_DOUBLE), INTENT(in) :: xa(*), xb(*), r_obs(*)
+         REAL(C_DOUBLE)            :: f_bl(*), f_np(*)
+         INTEGER(C_SIGNED_CHAR)    :: fmask(*)
+      END FUNCTION
       INTEGER(C_INT) FUNCTION sosie_akima_1d_1d(ctx, ncol, nk1, vz1, vz1_cs, vz1_ks, vf1, vf1_cs, vf1_ks, nk2, vz2, vz2_cs, vz2_ks, &
          &                                      vf2, vf2_cs, vf2_ks, has_rmask, rmask_val, l_surf_persist, l_botm_persist, status) &
          &                                      BIND(C, name='sosie_akima_1d_1d')
