@@ -643,6 +643,7 @@ int orc_bdrown(int k_ew, int ni, int nj, int nslab, float* X, const int32_t* mas
 }
 
 int orc_smoother(int k_ew, int ni, int nj, int nslab, float* X, int nb_smooth, const int32_t* msk, int l_emp) {
+  g_error = 0;
   int64_t n = (int64_t)ni * nj;
   for (int s = 0; s < nslab; s++) {
     A2<float> Xs(X + s * n, ni, nj);

@@ -437,6 +437,9 @@ int find_nearest_point(const A2<const double>& Xtrg, const A2<const double>& Ytr
     if (j_strt_t > j_stop_t) jlat_icr = -1;
   }
   if (info) { info[0] = j_strt_t; info[1] = j_stop_t; info[2] = jlat_icr; info[3] = l_is_reg_s; info[4] = l_is_reg_t; }
+  // MINVAL over an empty mask is HUGE and MAXLOC of an empty mask 0: the reference then runs its row loop outside the
+  // arrays (undefined).  The oracle reports it (the GPU library returns SOSIE_ERR_REF_STOP for the same inputs).
+  if (j_strt_t < 1 || j_strt_t > ny_t || j_stop_t < 1 || j_stop_t > ny_t) { g_error = 6; return 0; }
   int used;
   if (l_is_reg_s) {
     find_nearest_easy(Xtrg, Ytrg, Xsrc, Ysrc, JIp, JJp, mask_ignore_t, j_strt_t, j_stop_t, jlat_icr, elide_fill, nthreads);
@@ -905,6 +908,7 @@ int orc_bilin_2d(int k_ew_per, int nx1, int ny1, const double* X10, const double
   // virtual_src != 0 (1-D source axes only): the 2-D expansions X1/Y1/X1w/Y1w of :100-148 are strided VIEWS of
   // the axes instead of copies (identical values; needed to run the 21600x10800 shape on a sample of targets
   // without 8 GB of coordinate copies per call).
+  g_error = 0;   // a STOP reported by an earlier call must not leak into this one
   const double rmv = kRmv;
   const bool virt = (src_1d != 0) && (virtual_src != 0);
   int64_t n1 = (int64_t)nx1 * ny1, n2 = (int64_t)nx2 * ny2;
