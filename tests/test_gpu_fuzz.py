@@ -1,7 +1,7 @@
 """Randomised GPU-vs-oracle parity (tools/fuzz_parity.py): random grids (regular axes cell- or node-centred, with overlap
 columns, regional; ORCA-shaped curvilinear), random targets (1-D axes, rotated/sheared, polar caps), masks, periodicity,
 sequential and pipelined first calls, Akima, BDROWN (all three implementations) / DROWN / SMOOTHER with random masks and
-options.  Results must be bit-identical; where the oracle says the reference would STOP the library must raise as well."""
+options, the vertical stage (AKIMA_1D_3D / _1D with missing values, the sigma branch, lbc_lnk, post-ops, extrp_hl), rotation.  Results must be bit-identical; where the oracle says the reference would STOP the library must raise as well."""
 import os
 import sys
 
@@ -20,7 +20,7 @@ def test_fuzz_parity(gpu, orc, seed):
     fails, done, stops = [], 0, 0
     for k in range(160):
         sub = np.random.default_rng(rng.integers(1 << 62))
-        fn = (F.case_bilin, F.case_bilin, F.case_akima, F.case_drown)[k % 4]
+        fn = F.CASES[k % len(F.CASES)]
         try:
             tag = fn(gpu, sub, k)
             done += tag is not None

@@ -50,8 +50,8 @@ def rnd_target(rng, lon_s, lat_s):
     kind = rng.integers(0, 4)
     lo0, lo1 = float(np.min(lon_s)), float(np.max(lon_s))
     la0, la1 = float(np.min(lat_s)), float(np.max(lat_s))
-    cx, cy = rng.uniform(lo0, lo1), rng.uniform(max(la0, -85.0), min(la1, 85.0))
-    w, h = rng.uniform(2.0, 0.6 * (lo1 - lo0 + 1.0)), rng.uniform(2.0, 0.6 * (la1 - la0 + 1.0))
+    cx, cy = rng.uniform(lo0, lo1), rng.uniform(min(max(la0, -85.0), 84.0), max(min(la1, 85.0), min(max(la0, -85.0), 84.0) + 0.5))
+    w, h = rng.uniform(2.0, max(2.5, 0.6 * (lo1 - lo0 + 1.0))), rng.uniform(2.0, max(2.5, 0.6 * (la1 - la0 + 1.0)))
     if kind == 0:      # regular 1-D axes
         return np.mod(np.linspace(cx - w / 2, cx + w / 2, nx), 360.0), np.clip(np.linspace(cy - h / 2, cy + h / 2, ny), -89.9, 89.9)
     u = np.linspace(-0.5, 0.5, nx)[None, :].repeat(ny, 0)
@@ -231,6 +231,126 @@ def case_drown(gpu, rng, k):
     return tag
 
 
+def case_vert(gpu, rng, k):
+    """vertical stage: AKIMA_1D_3D, AKIMA_1D_1D (missing values, persistence), the sigma branch, lbc_lnk, post-ops, extrp_hl,
+    rotation"""
+    which = int(rng.integers(0, 7))
+    tag = f"vert#{k} kind={which}"
+    with np.errstate(all="ignore"):
+        if which == 0:
+            nk1, nk2, ny, nx = int(rng.integers(3, 40)), int(rng.integers(1, 50)), int(rng.integers(1, 30)), int(rng.integers(1, 40))
+            vz1 = np.cumsum(rng.uniform(1.0, 300.0, nk1)).astype(np.float32)
+            if rng.random() < 0.15:
+                vz1[int(rng.integers(1, nk1))] = vz1[0]                  # repeated / non-monotone depth
+            vz2 = np.sort(rng.uniform(0.0, float(vz1.max()) * 1.1, nk2)).astype(np.float32)
+            if nk2 > 2 and rng.random() < 0.5:
+                vz2[int(rng.integers(0, nk2))] = vz1[int(rng.integers(0, nk1))]
+            xf1 = rng.normal(5.0, 3.0, (nk1, ny, nx)).astype(np.float32)
+            rg, ro = both(tag, lambda: gpu.akima_1d_3d(vz1, xf1, vz2, -9999.0), lambda: orc.akima_1d_3d(vz1, xf1, vz2, -9999.0))
+            if rg is None:
+                return tag
+            eq(tag, rg, ro)
+        elif which == 1:
+            ncol, nk1, nk2 = int(rng.integers(1, 300)), int(rng.integers(3, 40)), int(rng.integers(1, 40))
+            vz1 = np.cumsum(rng.uniform(1.0, 300.0, (ncol, nk1)), axis=1)
+            vf1 = rng.normal(5.0, 3.0, (ncol, nk1))
+            vz2 = np.sort(rng.uniform(-10.0, vz1.max() * 1.1, (ncol, nk2)), axis=1)
+            vz2[:, 0] = vz1[:, 0] if rng.random() < 0.5 else vz2[:, 0]
+            rmv = -9999.0 if rng.random() < 0.5 else None
+            if rmv is not None:
+                for c in range(ncol):
+                    a, b = (int(rng.integers(0, 3)), int(rng.integers(1, 4))) if rng.random() < 0.7 else (0, 0)
+                    if a:
+                        vf1[c, :a] = rmv
+                    if b and (a or rng.random() < 0.8):
+                        vf1[c, nk1 - b:] = rmv
+            opts = dict(rmask_val=rmv, l_surf_persist=bool(rng.random() < 0.5), l_botm_persist=bool(rng.random() < 0.5))
+            if ORACLE_ONLY:
+                orc.akima_1d_1d(vz1, vf1, vz2, **opts)
+                return tag
+            sg = None
+            try:
+                a, sg = gpu.akima_1d_1d(vz1, vf1, vz2, **opts)
+            except sosie_b200.SosieError:
+                a, sg = gpu.last_vf2, gpu.last_status
+                assert sg.min() < 0, tag
+            b, sb = orc.akima_1d_1d(vz1, vf1, vz2, **opts)
+            eq(tag + " status", sg, sb)
+            ok = sb >= 0
+            eq(tag, a[ok], b[ok])
+        elif which == 2:
+            nk_src, nk_trg, nj, ni = int(rng.integers(3, 30)), int(rng.integers(1, 30)), int(rng.integers(1, 20)), int(rng.integers(1, 30))
+            ss, ts, lm = bool(rng.random() < 0.5), bool(rng.random() < 0.5), bool(rng.random() < 0.5)
+            H = rng.uniform(100.0, 4000.0, (nj, ni))
+            ds = (np.sort(rng.uniform(0.01, 1.0, (nk_src, nj, ni)), axis=0) * H).astype(np.float32)
+            dt = (np.sort(rng.uniform(0.0, 1.2, (nk_trg, nj, ni)), axis=0) * H).astype(np.float32)
+            da = rng.normal(10.0, 4.0, ds.shape).astype(np.float32)
+            if ss:
+                ds, da = ds[::-1].copy(), da[::-1].copy()
+            if ts:
+                dt = dt[::-1].copy()
+            nwet = rng.integers(0, nk_trg + 1, (nj, ni))
+            mask = (np.arange(nk_trg)[:, None, None] < nwet[None]).astype(np.int32)
+            prev = rng.normal(size=dt.shape).astype(np.float32)
+            rg, ro = both(tag, lambda: gpu.interp3d_sigma(ds, da, dt, prev, mask, lm, ss, ts), lambda: orc.interp3d_sigma(ds, da, dt, prev, mask, lm, ss, ts)[0])
+            if rg is None:
+                return tag
+            eq(tag, rg, ro)
+        elif which == 3:
+            jpj, jpi, ns = int(rng.integers(4, 40)), int(rng.integers(4, 60)), int(rng.integers(1, 4))
+            X = rng.normal(size=(ns, jpj, jpi)).astype(np.float32)
+            nperio, cd = int(rng.integers(0, 7)), str(rng.choice(["T", "U", "V", "F", "W"]))
+            psgn, pval = float(rng.choice([1.0, -1.0])), (float(rng.normal()) if rng.random() < 0.3 else None)
+            tag += f" nperio={nperio} cd={cd} {jpi}x{jpj}"
+            rg, ro = both(tag, lambda: gpu.lbc_lnk(nperio, X, cd, psgn, pval), lambda: orc.lbc_lnk(nperio, X, cd, psgn, pval))
+            if rg is None:
+                return tag
+            eq(tag, rg, ro)
+        elif which == 4:
+            nk, nj, ni = int(rng.integers(1, 20)), int(rng.integers(4, 30)), int(rng.integers(4, 40))
+            X = rng.normal(10.0, 8.0, (nk, nj, ni)).astype(np.float32)
+            X[rng.random(X.shape) < 0.05] = -9999.0
+            nwet = rng.integers(0, nk + 1, (nj, ni))
+            mask = (np.arange(nk)[:, None, None] < nwet[None]).astype(np.int32)
+            args = (mask, int(rng.integers(0, 2)), 2.0, 18.0, -9999.0, int(rng.choice([0, 0, 4, 6])), str(rng.choice(["T", "U", "V"])), bool(rng.random() < 0.5))
+            rg, ro = both(tag, lambda: gpu.interp3d_post(X, *args), lambda: orc.interp3d_post(X, *args))
+            if rg is None:
+                return tag
+            eq(tag, rg, ro)
+        elif which == 5:
+            ns, nj, ni = int(rng.integers(1, 4)), int(rng.integers(6, 40)), int(rng.integers(2, 30))
+            X = rng.normal(size=(ns, nj, ni)).astype(np.float32)
+            icr = int(rng.choice([1, -1]))
+            # as INTERP_2D/3D set them (src/mod_interp.f90:56-65): the "top" rows lie beyond the "bottom" rows in the direction icr
+            hi_rows, lo_rows = int(rng.integers(nj // 2 + 1, nj + 1)), int(rng.integers(1, nj // 2))
+            top, btm = (hi_rows, lo_rows) if icr == 1 else (lo_rows, hi_rows)
+            if rng.random() < 0.3:
+                top = 0
+            if rng.random() < 0.3:
+                btm = 0
+            if icr == 1:
+                top, btm = (max(top, 2) if top else 0), btm
+            else:
+                top, btm = (min(top, nj - 1) if top else 0), btm
+            rg, ro = both(tag, lambda: gpu.extrp_hl(X, top, btm, icr), lambda: orc.extrp_hl(X, top, btm, icr))
+            if rg is None:
+                return tag
+            eq(tag, rg, ro)
+        else:
+            ns, n = int(rng.integers(1, 4)), int(rng.integers(1, 3000))
+            U, V = rng.normal(size=(ns, n)).astype(np.float32), rng.normal(size=(ns, n)).astype(np.float32)
+            th = rng.uniform(0, 2 * np.pi, n)
+            inv = bool(rng.random() < 0.5)
+            rg, ro = both(tag, lambda: gpu.rotate_uv(U, V, np.cos(th), np.sin(th), inv), lambda: orc.rotate_uv(U, V, np.cos(th), np.sin(th), inv))
+            if rg is None:
+                return tag
+            eq(tag + " U", rg[0], ro[0]); eq(tag + " V", rg[1], ro[1])
+    return tag
+
+
+CASES = (case_bilin, case_bilin, case_akima, case_drown, case_vert)
+
+
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 150
     seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
@@ -241,7 +361,7 @@ def main():
     fails, done = [], 0
     for k in range(n):
         sub = np.random.default_rng(rng.integers(1 << 62))
-        fn = (case_bilin, case_bilin, case_akima, case_drown)[k % 4]
+        fn = CASES[k % len(CASES)]
         if ONLY and k not in ONLY:
             continue
         try:
