@@ -79,16 +79,34 @@ struct PostOps {
 // One slab (the first call of a 2-D job, the per-record call of the unchanged driver loop): nothing to amortise the
 // record over, so the kernel is a latency chain record -> 4 gathers -> store.  A lean body (no slab unrolling: half the
 // registers of a slab-unrolled body) keeps every SM at full occupancy to cover it.
-__global__ void __launch_bounds__(256, 8)
+// FUSE: the first apply after a mapping was built (no packed records yet) builds the record of each target from the
+// mapping arrays right here, stores it for the later calls and uses it from registers: one pass instead of k_pack
+// (mapping in, records out) followed by a second one that reads the records back.
+#ifndef APPLY1_FUSE_BLOCKS
+#define APPLY1_FUSE_BLOCKS 8
+#endif
+template <bool FUSE>
+__global__ void __launch_bounds__(256, FUSE ? APPLY1_FUSE_BLOCKS : 8)
 k_apply1(const int4* __restrict__ pidx, const float4* __restrict__ pw, SlabView v, const float* __restrict__ Z1, float* __restrict__ Z2,
-         PostOps po, TileGeom tgm) {
+         PostOps po, TileGeom tgm, SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ MT, const double* __restrict__ AB,
+         int4* pidx_out, float4* pw_out) {
+  const size_t nt = FUSE ? (size_t)tg.nx * tg.ny : 0;
   for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
     const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
     const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);  // 0-based
     if (i >= tgm.nx || j > tgm.j1) continue;
     const size_t k = (size_t)i + (size_t)j * tgm.nx;
-    const int4 id = __ldcs(pidx + k);     // streamed once: do not displace the source slab in L2
-    const float4 w = __ldcs(pw + k);
+    int4 id;
+    float4 w;
+    if (FUSE) {
+      pack_record(sg, k_ew, __ldcs(MT + k), __ldcs(MT + k + nt), __ldcs(MT + k + 2 * nt), __ldcs(AB + k), __ldcs(AB + k + nt),
+                  trg_lon(tg, i + 1, j + 1), trg_lat(tg, i + 1, j + 1), id, w);
+      __stcs(pidx_out + k, id);
+      __stcs(pw_out + k, w);
+    } else {
+      id = __ldcs(pidx + k);     // streamed once: do not displace the source slab in L2
+      w = __ldcs(pw + k);
+    }
     const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
     float r = interp_one(Z1, v, id, w, wup);
     if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
@@ -404,7 +422,9 @@ static int orca_lastrow_patch(sosie_ctx* ctx, float* dZ2s) {
 
 int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, int first_call, int use_clamp, float vmin,
                      float vmax, const int32_t* dmask_trg, float rmiss) {
-  if (!ctx->pack_ready) { if (int rc = bilin_pack_impl(ctx)) return rc; }
+  // one slab and no records yet (the first call after the mapping was built): pack inside the apply kernel
+  const bool fuse = !ctx->pack_ready && nslab == 1 && ctx->map_ready;
+  if (!ctx->pack_ready && !fuse) { if (int rc = bilin_pack_impl(ctx)) return rc; }
   if (nslab <= 0) return SOSIE_OK;
   const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;
   SlabView v;
@@ -431,8 +451,18 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
     prof_end(ctx, SOSIE_T_APPLY);
   } else {
     prof_begin(ctx, SOSIE_T_APPLY);
-    k_apply1<<<grid.x, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, v, dZ1, dZ2, po, tgm);   // nslab == 1 here
-    KLAUNCH_CHECK();
+    if (fuse) {
+      if ((size_t)ctx->sg.nx * ctx->sg.nyw > 2147483647ULL) { ctx->err = "source slab too large for 32-bit offsets"; return SOSIE_ERR_ARG; }
+      CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt));
+      k_apply1<true><<<grid.x, 256, 0, ctx->stream>>>(nullptr, nullptr, v, dZ1, dZ2, po, tgm, ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p,
+                                                      ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p);
+      KLAUNCH_CHECK();
+      ctx->pack_ready = true; ctx->pack_gen++; ctx->boxes_ready = false;
+    } else {
+      k_apply1<false><<<grid.x, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, v, dZ1, dZ2, po, tgm, ctx->sg, ctx->tg, ctx->k_ew, nullptr,
+                                                       nullptr, nullptr, nullptr);   // nslab == 1 here
+      KLAUNCH_CHECK();
+    }
     prof_end(ctx, SOSIE_T_APPLY);
   }
   // l_last_y_row_missing (:241-247) is evaluated on the first call only, the patch (:254-263) on every call
