@@ -121,8 +121,8 @@ def eq(tag, a, b):
 def case_bilin(gpu, rng, k):
     curvi = rng.random() < 0.3
     if curvi:
-        cfg = G.config(str(rng.choice(["B", "C"])), float(rng.uniform(0.12, 0.3)))
-        Xs, Ys, kew, lreg = cfg["src_lon"], cfg["src_lat"], cfg["ewper_src"], False
+        Xs, Ys = G.orca_like(int(rng.integers(24, 100)), int(rng.integers(24, 80)), str(rng.choice(["F", "T"])), float(rng.uniform(0.0, 300.0)))
+        kew, lreg = 2, False
         lon_s, lat_s = Xs, Ys
         X2, Y2 = Xs, Ys
     else:
@@ -132,6 +132,11 @@ def case_bilin(gpu, rng, k):
         if rng.random() < 0.25:
             lon_s, lat_s, lreg = X2, Y2, bool(rng.random() < 0.5)   # 2-D arrays of a regular grid
     Xt, Yt = rnd_target(rng, X2, Y2)
+    iorca = 0
+    if rng.random() < 0.2:
+        piv = str(rng.choice(["F", "T"]))
+        Xt, Yt = G.orca_like(int(rng.integers(24, 70)), int(rng.integers(24, 60)), piv, float(rng.uniform(0.0, 300.0)))
+        iorca = int(rng.choice([0, 6 if piv == "F" else 4]))
     nslab = int(rng.integers(1, 4))
     Z1 = G.field_slabs(X2, Y2, nslab, seed=int(rng.integers(1 << 30)))
     mask = None
@@ -139,17 +144,17 @@ def case_bilin(gpu, rng, k):
         mask = (rng.random(Xt.shape) > 0.2).astype(np.int32)
     first = rng.random() < 0.5 and mask is None
     gpu.set_pipeline_min_targets(0 if rng.random() < 0.5 else 1 << 30)
-    tag = f"bilin#{k} curvi={curvi} src={np.shape(lon_s)} trg={np.shape(Xt)} kew={kew} lreg={lreg} mask={mask is not None} first={first}"
+    tag = f"bilin#{k} curvi={curvi} src={np.shape(lon_s)} trg={np.shape(Xt)} kew={kew} lreg={lreg} mask={mask is not None} first={first} iorca={iorca}"
 
     gpu.l_first_call_interp_routine = True
 
     def fg():
         if first:
-            return gpu.bilin_2d_first(kew, lon_s, lat_s, Z1, Xt, Yt, l_reg_src=lreg)
-        Z2 = gpu.bilin_2d(kew, lon_s, lat_s, Z1, Xt, Yt, mask_domain_trg=mask, l_reg_src=lreg)
+            return gpu.bilin_2d_first(kew, lon_s, lat_s, Z1, Xt, Yt, l_reg_src=lreg, i_orca_trg=iorca)
+        Z2 = gpu.bilin_2d(kew, lon_s, lat_s, Z1, Xt, Yt, mask_domain_trg=mask, l_reg_src=lreg, i_orca_trg=iorca)
         return Z2, gpu.bilin_get_map()
     with np.errstate(all="ignore"):
-        rg, ro = both(tag, fg, lambda: orc.bilin_2d(kew, lon_s, lat_s, Z1, Xt, Yt, mask_domain_trg=mask, l_reg_src=lreg))
+        rg, ro = both(tag, fg, lambda: orc.bilin_2d(kew, lon_s, lat_s, Z1, Xt, Yt, mask_domain_trg=mask, l_reg_src=lreg, i_orca_trg=iorca))
     if rg is None:
         return tag + " (both STOP)"
     if os.environ.get("FUZZ_VERBOSE"):
@@ -170,16 +175,23 @@ def case_bilin(gpu, rng, k):
 
 
 def case_akima(gpu, rng, k):
-    lon_s, lat_s, kew = rnd_regular_axes(rng)
-    if lon_s.size < 6 or lat_s.size < 6 or np.any(np.diff(lon_s) <= 0):
-        return None
-    X2, Y2 = G.expand_2d(lon_s, lat_s)
+    iorca = 0
+    if rng.random() < 0.25:   # ORCA-shaped source below its north cap (AKIMA_2D wants longitudes increasing along i): fold options still run
+        piv = str(rng.choice(["F", "T"]))
+        lon_s, lat_s = G.orca_like(int(rng.integers(24, 90)), int(rng.integers(24, 70)), piv, float(rng.uniform(0.0, 200.0)))
+        kew, iorca = 2, int(rng.choice([0, 6 if piv == "F" else 4]))
+        X2, Y2 = lon_s, lat_s
+    else:
+        lon_s, lat_s, kew = rnd_regular_axes(rng)
+        if lon_s.size < 6 or lat_s.size < 6 or np.any(np.diff(lon_s) <= 0):
+            return None
+        X2, Y2 = G.expand_2d(lon_s, lat_s)
     Xt, Yt = rnd_target(rng, X2, Y2)
     Z1 = G.field_slabs(X2, Y2, int(rng.integers(1, 4)), seed=int(rng.integers(1 << 30)))
-    tag = f"akima#{k} src={X2.shape} trg={np.shape(Xt)} kew={kew}"
+    tag = f"akima#{k} src={X2.shape} trg={np.shape(Xt)} kew={kew} iorca={iorca}"
     gpu.akima_untiled_slopes(bool(rng.random() < 0.3))
     with np.errstate(all="ignore"):
-        rg, ro = both(tag, lambda: gpu.akima_2d(kew, lon_s, lat_s, Z1, Xt, Yt), lambda: orc.akima_2d(kew, lon_s, lat_s, Z1, Xt, Yt)[0])
+        rg, ro = both(tag, lambda: gpu.akima_2d(kew, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca), lambda: orc.akima_2d(kew, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca)[0])
     if rg is None:
         return tag + " (both STOP)"
     eq(tag, rg, ro)
@@ -348,7 +360,32 @@ def case_vert(gpu, rng, k):
     return tag
 
 
-CASES = (case_bilin, case_bilin, case_akima, case_drown, case_vert)
+def case_track(gpu, rng, k):
+    nk = int(rng.choice([1, 1, int(rng.integers(2, 9))]))
+    nj, ni, n = int(rng.integers(3, 60)), int(rng.integers(3, 80)), int(rng.integers(1, 4000))
+    F1 = rng.normal(size=(nk, nj, ni)).astype(np.float32)
+    timed = nk == 1 and rng.random() < 0.7
+    F2 = rng.normal(size=(nk, nj, ni)).astype(np.float32) if timed else None
+    if rng.random() < 0.3:
+        F1[rng.random(F1.shape) < 0.02] = -9999.0
+    imask = (rng.random((nk, nj, ni)) > rng.uniform(0.0, 0.2)).astype(np.int8)
+    iP, jP, iq = rng.integers(0, ni + 1, n), rng.integers(0, nj + 1, n), rng.integers(1, 5, n)
+    xa, xb = rng.uniform(-0.1, 1.1, n), rng.uniform(-0.1, 1.1, n)
+    r_obs = rng.uniform(-30, 60, n)
+    vt1 = float(rng.uniform(1.0e4, 3.0e4)); vt2 = vt1 + float(rng.uniform(0.01, 30.0))
+    rt = rng.uniform(vt1, vt2, n) if timed else None
+    lo, hi, clip = (-20.0, 20.0, True) if timed else (-20.0, 50.0, bool(rng.random() < 0.5))
+    tag = f"track#{k} nk={nk} {ni}x{nj} n={n} timed={timed}"
+    args = (F1, F2, vt1, vt2, imask, rt, iP, jP, iq, xa, xb, r_obs, lo, hi, clip)
+    rg, ro = both(tag, lambda: gpu.track_interp(*args), lambda: orc.track_interp(*args))
+    if rg is None:
+        return tag
+    for a_, b_, nm in zip(rg, ro, ("f_bl", "f_np", "fmask")):
+        eq(tag + " " + nm, a_, b_)
+    return tag
+
+
+CASES = (case_bilin, case_bilin, case_akima, case_drown, case_vert, case_track)
 
 
 def main():
