@@ -163,14 +163,25 @@ __global__ void k_ypass(TrgGeom tg, Prelude* p, int do_dlat, ColPart* part, int 
     ColPart cp;
     cp.emin = ~0ULL; cp.emax = 0ULL; cp.jmin = 0; cp.jmax = 0;
     double prev = (j0 > 1 && do_dlat) ? trg_lat(tg, i, j0 - 1) : 0.0;
-    for (int j = j0; j <= j1; j++) {
-      const double v = trg_lat(tg, i, j);
-      const unsigned long long e = enc_d(v);
-      gmin = min(gmin, e); gmax = max(gmax, e);
-      if (do_dlat && j >= 2) gdl = min(gdl, enc_d(sgn * (v - prev)));
-      prev = v;
-      if ((v >= y_min_s) && e < cp.emin) { cp.emin = e; cp.jmin = j; }   // strict: the first occurrence wins
-      if ((v <= y_max_s) && (e > cp.emax || cp.jmax == 0)) { cp.emax = e; cp.jmax = j; }
+    // the loads of a batch of rows are issued together (they are independent; the reductions below are not)
+    const double* __restrict__ colp = tg.is_1d ? tg.Y : tg.Y + (i - 1);
+    const size_t rstride = tg.is_1d ? 1 : (size_t)tg.nx;
+    for (int jb = j0; jb <= j1; jb += 8) {
+      double vv[8];
+#pragma unroll
+      for (int q = 0; q < 8; q++) vv[q] = (jb + q <= j1) ? __ldcs(colp + (size_t)(jb + q - 1) * rstride) : 0.0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const int j = jb + q;
+        if (j > j1) break;
+        const double v = vv[q];
+        const unsigned long long e = enc_d(v);
+        gmin = min(gmin, e); gmax = max(gmax, e);
+        if (do_dlat && j >= 2) gdl = min(gdl, enc_d(sgn * (v - prev)));
+        prev = v;
+        if ((v >= y_min_s) && e < cp.emin) { cp.emin = e; cp.jmin = j; }   // strict: the first occurrence wins
+        if ((v <= y_max_s) && (e > cp.emax || cp.jmax == 0)) { cp.emax = e; cp.jmax = j; }
+      }
     }
     part[t] = cp;   // [chunk][column]
   }
