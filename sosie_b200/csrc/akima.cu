@@ -249,7 +249,7 @@ k_slopes(const double* __restrict__ ZX, const double* __restrict__ ZY, const dou
 __global__ void __launch_bounds__(SLT_X * SLT_Y)
 k_slopes_tiled(const double* __restrict__ ZX, const double* __restrict__ ZY, const double* __restrict__ ZFb, int nx, int ny,
                double* dFdX, double* dFdY, double* d2F, size_t zf_stride, size_t out_stride, const uint8_t* __restrict__ needed,
-               int tiles_x, int ntiles) {
+               int tiles_x, int ntiles, const int32_t* __restrict__ tile_list) {
   const int n8 = nx + 4;
   const double* ZF = ZFb + blockIdx.y * zf_stride;
   double* ox = dFdX + blockIdx.y * out_stride;
@@ -259,7 +259,8 @@ k_slopes_tiled(const double* __restrict__ ZX, const double* __restrict__ ZY, con
   __shared__ double sDY[SLT_Y + 3][SLT_X + 2];    // DYe(I-1 .. I+1, J-2..J+1): columns c0+1 .. c0+SLT_X+2, rows r0 .. r0+SLT_Y+2
   __shared__ int s_any;
   const int tx = threadIdx.x % SLT_X, ty = threadIdx.x / SLT_X;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tq = blockIdx.x; tq < ntiles; tq += gridDim.x) {
+    const int tile = tile_list ? tile_list[tq] : tq;   // with a list: only tiles that hold a needed point (ntiles = its length)
     const int i0 = (tile % tiles_x) * SLT_X, j0 = (tile / tiles_x) * SLT_Y;   // 0-based origin of the tile in (nx, ny)
     const int ji = i0 + tx + 1, jj = j0 + ty + 1;                               // 1-based point
     const bool inside = (ji <= nx) && (jj <= ny);
@@ -395,6 +396,21 @@ __global__ void k_akima_needed(const double* __restrict__ X2, const double* __re
   }
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
   if ((threadIdx.x & 31) == 0 && hi >= lo) { atomicMin(rows, lo); atomicMax(rows + 1, hi); }
+}
+
+// 32x8 tiles (the tiling of k_slopes_tiled) that hold at least one needed point, in any order
+__global__ void k_akima_tile_list(const uint8_t* __restrict__ needed, int nx, int ny, int tiles_x, int ntiles, int32_t* list, int* count) {
+  for (int tile = blockIdx.x * blockDim.x + threadIdx.x; tile < ntiles; tile += gridDim.x * blockDim.x) {
+    const int i0 = (tile % tiles_x) * 32, j0 = (tile / tiles_x) * 8;
+    int any = 0;
+    for (int r = 0; r < 8 && !any; r++) {
+      const int jj = j0 + r;
+      if (jj >= ny) break;
+      const uint8_t* row = needed + (size_t)jj * nx;
+      for (int c = i0; c < min(i0 + 32, nx); c++) any |= row[c];
+    }
+    if (any) list[atomicAdd(count, 1)] = tile;
+  }
 }
 
 // ---- evaluation: build_pol (one cell, in registers) + pol_val; grid.y = slab ----------------------------
@@ -619,6 +635,17 @@ int akima_prepare_impl(sosie_ctx* ctx) {
   CK(cudaMemcpyAsync(hrows, ctx->d_iscratch.p, sizeof(hrows), cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   ctx->ak_row_lo = hrows[0]; ctx->ak_row_hi = hrows[1];
+  {
+    const int tiles_x = (ni1 + SLT_X - 1) / SLT_X, ntiles = tiles_x * ((nj1 + SLT_Y - 1) / SLT_Y);
+    CK(ctx->ak_tiles.alloc(ntiles));
+    int* dcount = ctx->d_iscratch.p + 2;
+    CK(cudaMemsetAsync(dcount, 0, sizeof(int), st));
+    k_akima_tile_list<<<grid_for(ctx, ntiles, 128), 128, 0, st>>>(ctx->ak_needed.p, ni1, nj1, tiles_x, ntiles, ctx->ak_tiles.p, dcount); KLAUNCH_CHECK();
+    int hc = 0;
+    CK(cudaMemcpyAsync(&hc, dcount, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ctx->ak_ntiles_needed = hc;
+  }
   ctx->ak_set = true;
   return SOSIE_OK;
 }
@@ -661,10 +688,15 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
       k_slopes<<<dim3(grid_for(ctx, ne, 128), ns), 128, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
                                                                   ctx->ak_sxy.p, ne8, ne, ctx->ak_needed.p); KLAUNCH_CHECK();
     } else {
-      const int tiles_x = (ni1 + SLT_X - 1) / SLT_X, ntiles = tiles_x * ((nj1 + SLT_Y - 1) / SLT_Y);
-      const int gx = std::min(ntiles, ctx->num_sms * 16);
-      k_slopes_tiled<<<dim3(gx, ns), SLT_X * SLT_Y, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
-                                                            ctx->ak_sxy.p, ne8, ne, ctx->ak_needed.p, tiles_x, ntiles); KLAUNCH_CHECK();
+      const int tiles_x = (ni1 + SLT_X - 1) / SLT_X;
+      const bool listed = ctx->ak_ntiles_needed >= 0;
+      const int ntiles = listed ? ctx->ak_ntiles_needed : tiles_x * ((nj1 + SLT_Y - 1) / SLT_Y);
+      if (ntiles > 0) {
+        const int gx = std::min(ntiles, ctx->num_sms * 16);
+        k_slopes_tiled<<<dim3(gx, ns), SLT_X * SLT_Y, 0, st>>>(ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, ctx->ak_sx.p, ctx->ak_sy.p,
+                                                              ctx->ak_sxy.p, ne8, ne, ctx->ak_needed.p, tiles_x, ntiles,
+                                                              listed ? ctx->ak_tiles.p : nullptr); KLAUNCH_CHECK();
+      }
     }
     prof_end(ctx, SOSIE_T_AKIMA_PREP);
     prof_begin(ctx, SOSIE_T_AKIMA_EVAL);

@@ -155,6 +155,8 @@ struct sosie_ctx {
   DBuf<double> ak_zF, ak_ZF8, ak_sx, ak_sy, ak_sxy;  // per-slab work arrays
   DBuf<float> ak_stage1, ak_stage2;
   double ak_range[4] = {0, 0, 0, 0};
+  DBuf<int32_t> ak_tiles;            // 32x8 tiles of the frame-extended slab that hold a needed point (k_slopes_tiled walks this list)
+  int ak_ntiles_needed = -1;         // -1: no list (every tile)
   int ak_row_lo = 0, ak_row_hi = -1;  // rows of the (nx1+4,ny1+4) frame-extended slab holding needed points (1-based; empty: hi < lo)
 
   // ---- vertical stage (vert.cu)
