@@ -414,7 +414,10 @@ __global__ void k_akima_tile_list(const uint8_t* __restrict__ needed, int nx, in
 }
 
 // ---- evaluation: build_pol (one cell, in registers) + pol_val; grid.y = slab ----------------------------
-__global__ void __launch_bounds__(128)
+#ifndef AK_EVAL_BLOCKS
+#define AK_EVAL_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(128, AK_EVAL_BLOCKS)
 k_akima_eval(const double* __restrict__ zX, const double* __restrict__ zY, const double* __restrict__ zFb,
              const double* __restrict__ sxb, const double* __restrict__ syb, const double* __restrict__ sxyb, int ni1, int nj1,
              const double* __restrict__ X2, const double* __restrict__ Y2, const int32_t* __restrict__ ixy, size_t nt, double x0,
