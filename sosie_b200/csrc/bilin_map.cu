@@ -801,14 +801,46 @@ k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ 
       long long ncand = (j2s >= j1s) ? (long long)sg.nx * (j2s - j1s + 1) : 0;
       double bd = 0.0, bp = -4.0;
       long long bk = -1;
-      for (long long c = lane; c < ncand; c += 32) {
-        int ji = (int)(c % sg.nx) + 1, jj = (int)(c / sg.nx) + j1s;
-        double vx, vy, vz;
-        src_vec(sg, ji, jj, vx, vy, vz);
-        double zpds = ux * vx + uy * vy + uz * vz;
-        if (bk >= 0 && zpds < bp - PDS_MARGIN) continue;
-        double d = G_ZR * pm_acos(fmin(zpds, 1.0));
-        if (bk < 0 || d < bd) { bd = d; bp = zpds; bk = c; }
+      // Pass 1 decides on the dot products alone (rows outer, lane-strided columns inner: no 64-bit division, no acos in the
+      // loop): every lane keeps its largest and second largest u.v; if, over the whole warp, the runner-up lies more than
+      // PDS_MARGIN below the winner, the winner is the unique nearest point and ONE acos gives its distance.  Otherwise
+      // (equidistant candidates) pass 2 compares distances exactly like the reference: first minimum in flattened order.
+      bool exact = sg.separable || ncand <= 0;
+      if (!exact) {
+        double p1 = -4.0, p2 = -4.0;
+        long long k1 = -1;
+        for (int jj = j1s; jj <= j2s; jj++) {
+          const size_t ro = (size_t)(jj - 1) * sg.nx;
+          const long long cb = (long long)(jj - j1s) * sg.nx;
+          for (int ji = lane; ji < sg.nx; ji += 32) {
+            const double zpds = ux * __ldg(sg.vx + ro + ji) + uy * __ldg(sg.vy + ro + ji) + uz * __ldg(sg.vz + ro + ji);
+            if (zpds > p1) { p2 = p1; p1 = zpds; k1 = cb + ji; }
+            else p2 = fmax(p2, zpds);
+          }
+        }
+        double g1 = p1;
+        long long gk = k1;
+        for (int o = 16; o > 0; o >>= 1) {
+          const double op = __shfl_xor_sync(0xffffffffu, g1, o);
+          const long long ok = __shfl_xor_sync(0xffffffffu, gk, o);
+          if (ok >= 0 && (gk < 0 || op > g1 || (op == g1 && ok < gk))) { g1 = op; gk = ok; }
+        }
+        double m2 = (k1 == gk) ? p2 : p1;
+        for (int o = 16; o > 0; o >>= 1) m2 = fmax(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+        if (gk >= 0 && !(m2 >= g1 - PDS_MARGIN) && !(g1 != g1)) { bd = G_ZR * pm_acos(fmin(g1, 1.0)); bp = g1; bk = (lane == 0) ? gk : -1; }
+        else exact = true;
+      }
+      if (exact && ncand > 0) {
+        bd = 0.0; bp = -4.0; bk = -1;
+        for (long long c = lane; c < ncand; c += 32) {
+          int ji = (int)(c % sg.nx) + 1, jj = (int)(c / sg.nx) + j1s;
+          double vx, vy, vz;
+          src_vec(sg, ji, jj, vx, vy, vz);
+          double zpds = ux * vx + uy * vy + uz * vz;
+          if (bk >= 0 && zpds < bp - PDS_MARGIN) continue;
+          double d = G_ZR * pm_acos(fmin(zpds, 1.0));
+          if (bk < 0 || d < bd) { bd = d; bp = zpds; bk = c; }
+        }
       }
       MinIdx m;
       m.v = bd; m.k = bk;
@@ -843,8 +875,15 @@ k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ 
 __global__ void __launch_bounds__(128)
 k_twisted_chain(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ order, int T,
                 const int2* __restrict__ band_pos, const int8_t* __restrict__ band_found,
-                const int2* __restrict__ S_old, int2* S_new, int8_t* found, int* changed) {
+                const int2* __restrict__ S_old, int2* S_new, int8_t* found, int* changed, const int2* __restrict__ S_prev) {
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < T; q += gridDim.x * blockDim.x) {
+    // S_prev (a third buffer, not written by this pass) is the state of two passes ago.  A target whose predecessor did
+    // not move between that pass and the last one would recompute exactly what it produced last time (S_old[q],
+    // found[q]): copy it.  After the first couple of passes only the few targets downstream of a change do any work.
+    if (S_prev && q > 0) {
+      const int2 pp = S_prev[q - 1], pl = S_old[q - 1];
+      if (pp.x == pl.x && pp.y == pl.y) { S_new[q] = S_old[q]; continue; }
+    }
     size_t k = (size_t)order[q];
     int jj_t = (int)(k / tg.nx) + 1, ji_t = (int)(k % tg.nx) + 1;
     double rlat = trg_lat(tg, ji_t, jj_t);
@@ -1360,23 +1399,33 @@ int bilin_map_impl(sosie_ctx* ctx) {
       CK(cudaStreamSynchronize(st));
     }
     if (T > 0) {
-      WS(int2, bpos, T); WS(int2, S0, T); WS(int2, S1, T); WS(int8_t, bfound, T); WS(int8_t, found, T); WS(int, dchg, 1);
+      WS(int2, bpos, T); WS(int2, S0, T); WS(int2, S1, T); WS(int2, S2, T); WS(int8_t, bfound, T); WS(int8_t, found, T);
       prof_begin(ctx, SOSIE_T_MAP);
       k_twisted_band<<<grid_for(ctx, (size_t)T * 32, 256), 256, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, derr.p); KLAUNCH_CHECK();
       prof_end(ctx, SOSIE_T_MAP);
       CK(cudaMemcpyAsync(S0.p, bpos.p, sizeof(int2) * T, cudaMemcpyDeviceToDevice, st));
       int2* Sa = S0.p;
       int2* Sb = S1.p;
+      int2* Sp = nullptr;   // no state of two passes ago before the second pass
+      // The chain is iterated to its fixed point; once a pass changes nothing, none does.  Passes are launched four at a
+      // time with one "changed" flag each, so the host synchronises once per batch instead of once per pass.
       int iters = 0;
-      while (true) {
-        CK(cudaMemsetAsync(dchg.p, 0, sizeof(int), st));
-        k_twisted_chain<<<grid_for(ctx, T, 128), 128, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, Sa, Sb, found.p, dchg.p); KLAUNCH_CHECK();
-        int chg = 0;
-        if (int rc = fetch_small(ctx, dchg.p, &chg, sizeof(int))) return rc;
-        iters++;
-        std::swap(Sa, Sb);
-        if (!chg) break;
-        if (iters > T + 2) { ctx->err = "internal: TWISTED chain did not converge"; return SOSIE_ERR_CUDA; }
+      const int NB = 4;
+      WS(int, dchg4, NB);
+      bool done = false;
+      while (!done) {
+        CK(cudaMemsetAsync(dchg4.p, 0, sizeof(int) * NB, st));
+        for (int b = 0; b < NB; b++) {
+          k_twisted_chain<<<grid_for(ctx, T, 128), 128, 0, st>>>(sg, tg, tp, order.p, T, bpos.p, bfound.p, Sa, Sb, found.p, dchg4.p + b, Sp); KLAUNCH_CHECK();
+          { int2* t = Sp ? Sp : S2.p; Sp = Sa; Sa = Sb; Sb = t; }   // (prev, old, new) <- (old, new, prev)
+        }
+        int chg[NB];
+        if (int rc = fetch_small(ctx, dchg4.p, chg, sizeof(int) * NB)) return rc;
+        for (int b = 0; b < NB; b++) {
+          iters++;
+          if (!chg[b]) { done = true; break; }   // iters = passes up to and including the first one that changed nothing
+        }
+        if (!done && iters > T + 2) { ctx->err = "internal: TWISTED chain did not converge"; return SOSIE_ERR_CUDA; }
       }
       ctx->map_info[6] = iters;
       k_twisted_scatter<<<grid_for(ctx, T, 256), 256, 0, st>>>(order.p, T, Sa, found.p, JI.p, JJ.p); KLAUNCH_CHECK();
