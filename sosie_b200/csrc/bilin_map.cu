@@ -767,9 +767,48 @@ struct TwParams {
   const double* e1;
   const double* e2;
   double frac_emax, sqrt2f;
+  const double* seg;  // [nyw * nseg * 5]: centre (3), cos and sin of the angular radius of each 32-column segment of a source row
+  int nseg;
 };
 
 // chain-independent band search (niter = 0,1,...), one warp per target (:1350-1426)
+// Spherical cap around each 32-column segment of a source row: centre = normalised mean of the unit vectors, radius =
+// largest angle to a member (its cosine lowered by 1e-12, its sine raised: the cap can only be too large).  One warp per
+// segment.  A degenerate mean (points spread around a pole) gets the whole sphere.
+__global__ void k_seg_table(SrcGeom sg, int nseg, double* seg) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5, total = sg.nyw * nseg;
+  for (int t = warp; t < total; t += nwarps) {
+    const int jj = t / nseg, sgi = t % nseg, ji = sgi * 32 + lane;
+    const bool in = ji < sg.nx;
+    const size_t k = (size_t)jj * sg.nx + (in ? ji : sg.nx - 1);
+    const double vx = sg.vx[k], vy = sg.vy[k], vz = sg.vz[k];
+    double sx = in ? vx : 0.0, sy = in ? vy : 0.0, sz = in ? vz : 0.0;
+    for (int o = 16; o > 0; o >>= 1) {
+      sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); sz += __shfl_xor_sync(0xffffffffu, sz, o);
+    }
+    const double nrm = sqrt(sx * sx + sy * sy + sz * sz);
+    double cx = 0.0, cy = 0.0, cz = 1.0, cr = -1.0;
+    if (nrm > 1.0e-3) {
+      cx = sx / nrm; cy = sy / nrm; cz = sz / nrm;
+      double d = cx * vx + cy * vy + cz * vz;     // lanes beyond nx repeat the last column
+      for (int o = 16; o > 0; o >>= 1) d = fmin(d, __shfl_xor_sync(0xffffffffu, d, o));
+      cr = fmax(d - 1.0e-12, -1.0);
+    }
+    if (!(cr == cr)) cr = -1.0;   // NaN coordinates: never prune
+    if (lane == 0) {
+      double* o = seg + (size_t)t * 5;
+      o[0] = cx; o[1] = cy; o[2] = cz; o[3] = cr; o[4] = fmin(sqrt(fmax(0.0, 1.0 - cr * cr)) + 1.0e-12, 1.0);
+    }
+  }
+}
+// upper bound of u.v over the cap (slack 1e-12 for the rounding of this very expression)
+__device__ __forceinline__ double seg_bound(const double* __restrict__ e, double ux, double uy, double uz) {
+  const double a = ux * e[0] + uy * e[1] + uz * e[2];
+  if (!(a < e[3]) || a < -0.99) return 2.0;   // inside the cap (or NaN): anything is possible; near the antipode sqrt(1-a*a) loses its digits
+  return a * e[3] + sqrt(fmax(0.0, 1.0 - a * a)) * e[4] + 1.0e-12;
+}
+
 __global__ void __launch_bounds__(256)
 k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ order, int T, int2* band_pos,
                int8_t* band_found, int* err) {
@@ -809,14 +848,51 @@ k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ 
       if (!exact) {
         double p1 = -4.0, p2 = -4.0;
         long long k1 = -1;
-        for (int jj = j1s; jj <= j2s; jj++) {
-          const size_t ro = (size_t)(jj - 1) * sg.nx;
-          const long long cb = (long long)(jj - j1s) * sg.nx;
-          for (int ji = lane; ji < sg.nx; ji += 32) {
+        // one 32-column segment: a candidate per lane
+        auto scan_seg = [&](int sid) {
+          const int jj = sid / tp.nseg + j1s, ji = (sid % tp.nseg) * 32 + lane;   // 1-based row, 0-based column
+          if (ji < sg.nx) {
+            const size_t ro = (size_t)(jj - 1) * sg.nx;
             const double zpds = ux * __ldg(sg.vx + ro + ji) + uy * __ldg(sg.vy + ro + ji) + uz * __ldg(sg.vz + ro + ji);
-            if (zpds > p1) { p2 = p1; p1 = zpds; k1 = cb + ji; }
+            if (zpds > p1) { p2 = p1; p1 = zpds; k1 = (long long)(jj - j1s) * sg.nx + ji; }
             else p2 = fmax(p2, zpds);
           }
+        };
+        const int nsb = (j2s - j1s + 1) * tp.nseg;                       // segments of the band, row-major
+        const double* segb = tp.seg ? tp.seg + (size_t)(j1s - 1) * tp.nseg * 5 : nullptr;
+        if (tp.seg) {
+          // (a) the segment whose cap comes closest to the target seeds the running best
+          double bb = -8.0;
+          int bs = 0;
+          for (int sid = lane; sid < nsb; sid += 32) {
+            const double b = seg_bound(segb + (size_t)sid * 5, ux, uy, uz);
+            if (b > bb) { bb = b; bs = sid; }
+          }
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, bb, o);
+            const int os = __shfl_xor_sync(0xffffffffu, bs, o);
+            if (ob > bb || (ob == bb && os < bs)) { bb = ob; bs = os; }
+          }
+          scan_seg(bs);
+          double best = p1;
+          for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+          // (b) every other segment whose cap can hold a point within the margin of the best is scanned; the rest cannot
+          //     contain the nearest point nor tie with it
+          for (int base = 0; base < nsb; base += 32) {
+            const int sid = base + lane;
+            const bool want = (sid < nsb) && (sid != bs) && !(seg_bound(segb + (size_t)sid * 5, ux, uy, uz) < best - (PDS_MARGIN + 1.0e-12));
+            unsigned todo = __ballot_sync(0xffffffffu, want);
+            while (todo) {
+              const int b = __ffs(todo) - 1;
+              todo &= todo - 1;
+              scan_seg(base + b);
+              double nb = p1;
+              for (int o = 16; o > 0; o >>= 1) nb = fmax(nb, __shfl_xor_sync(0xffffffffu, nb, o));
+              best = nb;
+            }
+          }
+        } else {
+          for (int sid = 0; sid < nsb; sid++) scan_seg(sid);
         }
         double g1 = p1;
         long long gk = k1;
@@ -1378,6 +1454,12 @@ int bilin_map_impl(sosie_ctx* ctx) {
     TwParams tp;
     tp.lStupido = lStupido ? 1 : 0; tp.nsplit = nsplit; tp.VB = dVB.p; tp.JV = dJV.p; tp.e1 = e1.p; tp.e2 = e2.p;
     tp.frac_emax = (double)0.51f; tp.sqrt2f = (double)sqrtf(2.0f);
+    tp.seg = nullptr; tp.nseg = (sg.nx + 31) / 32;
+    WS(double, segt, (size_t)sg.nyw * tp.nseg * 5 + 8);
+    if (!sg.separable && !getenv("SOSIE_TWISTED_NO_PRUNE")) {
+      k_seg_table<<<grid_for(ctx, (size_t)sg.nyw * tp.nseg * 32, 256), 256, 0, st>>>(sg, tp.nseg, segt.p); KLAUNCH_CHECK();
+      tp.seg = segt.p;
+    }
     // processing order of the searched targets
     long ntrip = ((long)j_stop_t - (long)j_strt_t + jlat_icr) / jlat_icr;
     if (ntrip < 0) ntrip = 0;
