@@ -169,6 +169,7 @@ struct sosie_ctx {
   DBuf<int8_t> dr_m0, dr_m1;
   DBuf<float> dr_x, dr_x2;
   DBuf<int32_t> dr_cnt, dr_mask32;
+  DBuf<unsigned int> dr_Ri, dr_Re;   // land-only smoother: interior cells / periodic edge-column cells of dr_R0
   DBuf<unsigned int> dr_R0, dr_Ra, dr_Rb, dr_Lv, dr_ctr;   // level-list BDROWN: land lists, level list, counters
   DBuf<unsigned char> dr_tmp;                               // cub scratch
   int force_general_bdrown = 0;  // tests: 0 auto, 1 level-list general path even for on-chip sized slabs, 2 legacy dense path

@@ -496,6 +496,60 @@ k_sml_pass(BdGeom g, FastDiv dn, FastDiv dni, const float* __restrict__ xinb, fl
     }
   }
 }
+// The land list split once per call: interior cells (rows 2..nj-1, columns 2..ni-1: every neighbour at a fixed offset, no
+// index decoding in the 50 passes) and the periodic edge-column cells (generic kernel above).  Cells of rows 1 / nj, and of
+// the edge columns of a closed domain, are never smoothed and dropped here.  cnts = {interior, edge}.
+__global__ void k_sml_split(BdGeom g, FastDiv dn, FastDiv dni, const unsigned int* __restrict__ R0, unsigned int cnt, unsigned int* Ri,
+                            unsigned int* Re, unsigned int* cnts) {
+  const int ni = g.ni, nj = g.nj;
+  for (unsigned int q0 = blockIdx.x * blockDim.x; q0 < cnt; q0 += gridDim.x * blockDim.x) {
+    const unsigned int q = q0 + threadIdx.x;
+    int kind = 0;   // 1 interior, 2 edge
+    unsigned int gid = 0;
+    if (q < cnt) {
+      gid = R0[q];
+      const unsigned int ms = fdiv(gid, dn), k = gid - ms * dn.d;
+      const unsigned int jr = fdiv(k, dni);
+      const int jj = (int)jr + 1, ji = (int)(k - jr * dni.d) + 1;
+      if (jj >= 2 && jj <= nj - 1) kind = (ji >= 2 && ji <= ni - 1) ? 1 : (g.k_ew >= 0 ? 2 : 0);
+    }
+    // warp-aggregated appends
+    const unsigned int mi = __ballot_sync(0xffffffffu, kind == 1), me = __ballot_sync(0xffffffffu, kind == 2);
+    const int lane = threadIdx.x & 31;
+    unsigned int bi = 0, be = 0;
+    if (lane == 0) { if (mi) bi = atomicAdd(&cnts[0], __popc(mi)); if (me) be = atomicAdd(&cnts[1], __popc(me)); }
+    bi = __shfl_sync(0xffffffffu, bi, 0); be = __shfl_sync(0xffffffffu, be, 0);
+    const unsigned int below = (1u << lane) - 1u;
+    if (kind == 1) Ri[bi + __popc(mi & below)] = gid;
+    else if (kind == 2) Re[be + __popc(me & below)] = gid;
+  }
+}
+__device__ __forceinline__ float sml_update(const float* __restrict__ p, int ni, float o) {
+  const float w0 = 0.35f, omw = 1.f - w0, c4 = 4.f * (1.f + RIS2F);
+  // ( X(ip,j) + X(i,j+1) + X(im,j) + X(i,j-1) ) + ris2*( X(ip,j+1) + X(ip,j-1) + X(im,j-1) + X(im,j+1) )   (:555-558)
+  const float* pp = p + ni;
+  const float* pm = p - ni;
+  const float s4 = __fadd_rn(__fadd_rn(__fadd_rn(p[1], pp[0]), p[-1]), pm[0]);
+  const float sd = __fadd_rn(__fadd_rn(__fadd_rn(pp[1], pm[1]), pm[-1]), pp[-1]);
+  const float v = __fadd_rn(__fmul_rn(w0, p[0]), __fdiv_rn(__fmul_rn(omw, __fadd_rn(s4, __fmul_rn(RIS2F, sd))), c4));
+  return __fsub_rn(__fmul_rn(1.f, v), __fmul_rn(0.f, o));   // msk*X - (msk-1)*xorig with msk = 1  (:600)
+}
+__global__ void __launch_bounds__(256, 8)
+k_sml_pass_int(const float* __restrict__ xinb, float* xoutb, const float* __restrict__ xo, const unsigned int* __restrict__ Ri,
+               unsigned int cnt, unsigned int n, int ni, int mask_per_slab, int nslab, int slabs_per_block) {
+  const int s0 = blockIdx.y * slabs_per_block, s1 = min(nslab, s0 + slabs_per_block);
+  for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
+    const unsigned int gid = Ri[q];
+    if (mask_per_slab) {   // gid = slab * n + cell: the offset in the stack
+      xoutb[gid] = sml_update(xinb + gid, ni, xo[q]);
+    } else {
+      const float* p = xinb + (size_t)s0 * n + gid;
+      float* out = xoutb + (size_t)s0 * n + gid;
+      const float* po = xo + (size_t)s0 * cnt + q;
+      for (int s = s0; s < s1; s++, p += n, out += n, po += cnt) *out = sml_update(p, ni, *po);
+    }
+  }
+}
 __global__ void k_sml_copyback(const float* __restrict__ src, float* dst, const unsigned int* __restrict__ R0, unsigned int cnt,
                                unsigned int n, int mask_per_slab, int nslab) {
   for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < cnt; q += gridDim.x * blockDim.x) {
@@ -896,7 +950,7 @@ static int bdrown_levels(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, 
   CK(cudaMemsetAsync(ctx->dr_cnt.p, 0, sizeof(int32_t) * ((size_t)(nb_inc + 1) * nmask + nslab), st));
   int32_t* rem = ctx->dr_cnt.p;                            // rem[j][ms]: land cells left after sweep j
   int32_t* nsw = rem + (size_t)(nb_inc + 1) * nmask;
-  const size_t nctr = 2 * (size_t)(nb_inc + 1) + 4;
+  const size_t nctr = 2 * (size_t)(nb_inc + 1) + 4;   // level counters | land cells, fallback flag | smoother list sizes (interior, edge)
   CK(ctx->dr_ctr.alloc(nctr));
   CK(cudaMemsetAsync(ctx->dr_ctr.p, 0, sizeof(unsigned int) * nctr, st));
   BdlCounters C;
@@ -950,19 +1004,34 @@ static int bdrown_levels(sosie_ctx* ctx, const BdGeom& g, int nslab, float* dX, 
       if (int rc = smoother_dev(ctx, g, nslab, dX, nb_smooth, ctx->dr_mask32.p, mask_per_slab, 0)) return rc;
     } else if (h[0] > 0) {
       const unsigned int cnt = h[0];
-      CK(ctx->dr_x.alloc((size_t)cnt * (mask_per_slab ? 1 : nslab)));
-      k_sml_gather<<<grid_for(ctx, cnt, 256, 8), 256, 0, st>>>(dX, ctx->dr_R0.p, cnt, (unsigned int)n, mask_per_slab, nslab, ctx->dr_x.p); KLAUNCH_CHECK();
+      // split the land list once: interior cells take the lean kernel, periodic edge-column cells the generic one
+      CK(ctx->dr_Ri.alloc(cnt)); CK(ctx->dr_Re.alloc(cnt));
+      unsigned int* dc = nsel + 2;   // zeroed with the other counters at the start of the call
+      k_sml_split<<<grid_for(ctx, cnt, 256, 8), 256, 0, st>>>(g, dn, dni, ctx->dr_R0.p, cnt, ctx->dr_Ri.p, ctx->dr_Re.p, dc); KLAUNCH_CHECK();
+      unsigned int hc[2];
+      if (int rc = fetch_small(ctx, dc, hc, sizeof(hc))) return rc;
+      const unsigned int ci = hc[0], ce = hc[1];
+      const size_t per = mask_per_slab ? 1 : (size_t)nslab;
+      CK(ctx->dr_x.alloc((size_t)(ci + ce) * per + 1));
+      float* xoi = ctx->dr_x.p;
+      float* xoe = ctx->dr_x.p + (size_t)ci * per;
+      if (ci) { k_sml_gather<<<grid_for(ctx, ci, 256, 8), 256, 0, st>>>(dX, ctx->dr_Ri.p, ci, (unsigned int)n, mask_per_slab, nslab, xoi); KLAUNCH_CHECK(); }
+      if (ce) { k_sml_gather<<<grid_for(ctx, ce, 256, 8), 256, 0, st>>>(dX, ctx->dr_Re.p, ce, (unsigned int)n, mask_per_slab, nslab, xoe); KLAUNCH_CHECK(); }
       const int spb = mask_per_slab ? nslab : std::max(1, (nslab + 15) / 16);
-      dim3 grid(grid_for(ctx, cnt, 256, 8), mask_per_slab ? 1 : (nslab + spb - 1) / spb);
+      const int gy = mask_per_slab ? 1 : (nslab + spb - 1) / spb;
       float* a = dX;
       float* b = ctx->dr_x2.p;
       prof_begin(ctx, SOSIE_T_SMOOTH);
       for (int js = 0; js < nb_smooth; js++) {
-        k_sml_pass<<<grid, 256, 0, st>>>(g, dn, dni, a, b, ctx->dr_x.p, ctx->dr_R0.p, cnt, mask_per_slab, nslab, spb); KLAUNCH_CHECK();
+        if (ci) { k_sml_pass_int<<<dim3(grid_for(ctx, ci, 256, 8), gy), 256, 0, st>>>(a, b, xoi, ctx->dr_Ri.p, ci, (unsigned int)n, ni, mask_per_slab, nslab, spb); KLAUNCH_CHECK(); }
+        if (ce) { k_sml_pass<<<dim3(grid_for(ctx, ce, 256, 8), gy), 256, 0, st>>>(g, dn, dni, a, b, xoe, ctx->dr_Re.p, ce, mask_per_slab, nslab, spb); KLAUNCH_CHECK(); }
         std::swap(a, b);
       }
       prof_end(ctx, SOSIE_T_SMOOTH);
-      if (a != dX) { k_sml_copyback<<<grid_for(ctx, cnt, 256, 8), 256, 0, st>>>(a, dX, ctx->dr_R0.p, cnt, (unsigned int)n, mask_per_slab, nslab); KLAUNCH_CHECK(); }
+      if (a != dX) {
+        if (ci) { k_sml_copyback<<<grid_for(ctx, ci, 256, 8), 256, 0, st>>>(a, dX, ctx->dr_Ri.p, ci, (unsigned int)n, mask_per_slab, nslab); KLAUNCH_CHECK(); }
+        if (ce) { k_sml_copyback<<<grid_for(ctx, ce, 256, 8), 256, 0, st>>>(a, dX, ctx->dr_Re.p, ce, (unsigned int)n, mask_per_slab, nslab); KLAUNCH_CHECK(); }
+      }
     }
   }
   if (fabsf(pval_land) > 1.e-12f) {
