@@ -767,21 +767,25 @@ struct TwParams {
   const double* e1;
   const double* e2;
   double frac_emax, sqrt2f;
-  const double* seg;  // [nyw * nseg * 5]: centre (3), cos and sin of the angular radius of each 32-column segment of a source row
-  int nseg;
+  const double* seg;  // [nty * ntx * 5]: centre (3), cos and sin of the angular radius of each 8x4 tile of the source grid
+  int nseg;           // ntx: tiles per tile row
 };
 
 // chain-independent band search (niter = 0,1,...), one warp per target (:1350-1426)
-// Spherical cap around each 32-column segment of a source row: centre = normalised mean of the unit vectors, radius =
-// largest angle to a member (its cosine lowered by 1e-12, its sine raised: the cap can only be too large).  One warp per
-// segment.  A degenerate mean (points spread around a pole) gets the whole sphere.
-__global__ void k_seg_table(SrcGeom sg, int nseg, double* seg) {
+// Spherical cap around each tile of 8 columns x 4 rows of the source grid: centre = normalised mean of the unit vectors,
+// radius = largest angle to a member (its cosine lowered by 1e-12, its sine raised: the cap can only be too large).  One
+// warp per tile, one lane per cell (cells beyond the grid repeat the tile's first cell).  A degenerate mean (points spread
+// around a pole) gets the whole sphere.  Tile t = tj * ntx + ti covers columns 8*ti .. 8*ti+7, rows 4*tj .. 4*tj+3 (0-based).
+#define TW_TX 8
+#define TW_TY 4
+__global__ void k_seg_table(SrcGeom sg, int ntx, int nty, double* seg) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5, total = sg.nyw * nseg;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5, total = ntx * nty;
   for (int t = warp; t < total; t += nwarps) {
-    const int jj = t / nseg, sgi = t % nseg, ji = sgi * 32 + lane;
-    const bool in = ji < sg.nx;
-    const size_t k = (size_t)jj * sg.nx + (in ? ji : sg.nx - 1);
+    const int tj = t / ntx, ti = t % ntx;
+    const int ji = ti * TW_TX + (lane & (TW_TX - 1)), jj = tj * TW_TY + (lane >> 3);
+    const bool in = (ji < sg.nx) && (jj < sg.nyw);
+    const size_t k = in ? (size_t)jj * sg.nx + ji : (size_t)(tj * TW_TY) * sg.nx + ti * TW_TX;
     const double vx = sg.vx[k], vy = sg.vy[k], vz = sg.vz[k];
     double sx = in ? vx : 0.0, sy = in ? vy : 0.0, sz = in ? vz : 0.0;
     for (int o = 16; o > 0; o >>= 1) {
@@ -791,7 +795,7 @@ __global__ void k_seg_table(SrcGeom sg, int nseg, double* seg) {
     double cx = 0.0, cy = 0.0, cz = 1.0, cr = -1.0;
     if (nrm > 1.0e-3) {
       cx = sx / nrm; cy = sy / nrm; cz = sz / nrm;
-      double d = cx * vx + cy * vy + cz * vz;     // lanes beyond nx repeat the last column
+      double d = cx * vx + cy * vy + cz * vz;
       for (int o = 16; o > 0; o >>= 1) d = fmin(d, __shfl_xor_sync(0xffffffffu, d, o));
       cr = fmax(d - 1.0e-12, -1.0);
     }
@@ -848,18 +852,23 @@ k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ 
       if (!exact) {
         double p1 = -4.0, p2 = -4.0;
         long long k1 = -1;
-        // one 32-column segment: a candidate per lane
+        // one 8x4 tile: a candidate per lane (rows outside the band and cells beyond the grid are skipped)
+        const int tj0 = (j1s - 1) / TW_TY, tj1 = (j2s - 1) / TW_TY;             // tile rows the band touches
         auto scan_seg = [&](int sid) {
-          const int jj = sid / tp.nseg + j1s, ji = (sid % tp.nseg) * 32 + lane;   // 1-based row, 0-based column
-          if (ji < sg.nx) {
+          const int tj = sid / tp.nseg + tj0, ti = sid % tp.nseg;
+          const int ji = ti * TW_TX + (lane & (TW_TX - 1)), jj = tj * TW_TY + (lane >> 3) + 1;   // 0-based column, 1-based row
+          if (ji < sg.nx && jj >= j1s && jj <= j2s) {
             const size_t ro = (size_t)(jj - 1) * sg.nx;
             const double zpds = ux * __ldg(sg.vx + ro + ji) + uy * __ldg(sg.vy + ro + ji) + uz * __ldg(sg.vz + ro + ji);
-            if (zpds > p1) { p2 = p1; p1 = zpds; k1 = (long long)(jj - j1s) * sg.nx + ji; }
-            else p2 = fmax(p2, zpds);
+            const long long kc = (long long)(jj - j1s) * sg.nx + ji;
+            // several tiles feed one lane in no particular order: the first index among equal dot products is kept
+            // explicitly (an exact tie makes the target ambiguous anyway: p2 == p1)
+            if (zpds > p1) { p2 = p1; p1 = zpds; k1 = kc; }
+            else { p2 = fmax(p2, zpds); if (zpds == p1 && kc < k1) k1 = kc; }
           }
         };
-        const int nsb = (j2s - j1s + 1) * tp.nseg;                       // segments of the band, row-major
-        const double* segb = tp.seg ? tp.seg + (size_t)(j1s - 1) * tp.nseg * 5 : nullptr;
+        const int nsb = (tj1 - tj0 + 1) * tp.nseg;                       // tiles of the band, row-major
+        const double* segb = tp.seg ? tp.seg + (size_t)tj0 * tp.nseg * 5 : nullptr;
         if (tp.seg) {
           // (a) the segment whose cap comes closest to the target seeds the running best
           double bb = -8.0;
@@ -882,17 +891,20 @@ k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ 
             const int sid = base + lane;
             const bool want = (sid < nsb) && (sid != bs) && !(seg_bound(segb + (size_t)sid * 5, ux, uy, uz) < best - (PDS_MARGIN + 1.0e-12));
             unsigned todo = __ballot_sync(0xffffffffu, want);
+            const bool any = todo != 0;
             while (todo) {
               const int b = __ffs(todo) - 1;
               todo &= todo - 1;
               scan_seg(base + b);
+            }
+            if (any) {   // tighten the threshold once per batch of 32 segments (the seed is almost always the winner already)
               double nb = p1;
               for (int o = 16; o > 0; o >>= 1) nb = fmax(nb, __shfl_xor_sync(0xffffffffu, nb, o));
               best = nb;
             }
           }
         } else {
-          for (int sid = 0; sid < nsb; sid++) scan_seg(sid);
+          for (int sid = 0; sid < nsb; sid++) scan_seg(sid);   // no table: every tile
         }
         double g1 = p1;
         long long gk = k1;
@@ -1454,10 +1466,11 @@ int bilin_map_impl(sosie_ctx* ctx) {
     TwParams tp;
     tp.lStupido = lStupido ? 1 : 0; tp.nsplit = nsplit; tp.VB = dVB.p; tp.JV = dJV.p; tp.e1 = e1.p; tp.e2 = e2.p;
     tp.frac_emax = (double)0.51f; tp.sqrt2f = (double)sqrtf(2.0f);
-    tp.seg = nullptr; tp.nseg = (sg.nx + 31) / 32;
-    WS(double, segt, (size_t)sg.nyw * tp.nseg * 5 + 8);
+    tp.seg = nullptr; tp.nseg = (sg.nx + TW_TX - 1) / TW_TX;
+    const int nty = (sg.nyw + TW_TY - 1) / TW_TY;
+    WS(double, segt, (size_t)nty * tp.nseg * 5 + 8);
     if (!sg.separable && !getenv("SOSIE_TWISTED_NO_PRUNE")) {
-      k_seg_table<<<grid_for(ctx, (size_t)sg.nyw * tp.nseg * 32, 256), 256, 0, st>>>(sg, tp.nseg, segt.p); KLAUNCH_CHECK();
+      k_seg_table<<<grid_for(ctx, (size_t)nty * tp.nseg * 32, 256), 256, 0, st>>>(sg, tp.nseg, nty, segt.p); KLAUNCH_CHECK();
       tp.seg = segt.p;
     }
     // processing order of the searched targets
