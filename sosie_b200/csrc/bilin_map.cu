@@ -516,6 +516,41 @@ static __device__ __noinline__ float dnp_noinline(const SrcGeom& sg, double xP, 
   return (zpds >= 1.0) ? 0.f : (float)(G_ZR * pm_acos(zpds));
 }
 
+// first-guess quadrant of MAPPING_BL (:511-540), literal: five headings and the four interval tests
+template <bool SEP>
+__device__ __forceinline__ int first_guess_quadrant(const SrcGeom& sg, double xP, double yP, int iP, int jP, int iPm1, int iPp1,
+                                                        int jPm1, int jPp1, double lonP, double lonN, double lonE, double lonS,
+                                                        double lonW) {
+  double ya = SEP ? sg.merc[jP - 1] : src_merc(sg, iP, jP);
+  double hP = d_heading_y(lonP, xP, ya, d_merc(yP));
+  double hN, hE, hS, hW;
+  if (SEP) {
+    // regular source: lonN == lonS == lonP and the E/W neighbours share the row's ordinate, so these four are
+    // functions of jP (N, S) or iP (E, W) alone -- read from the tables k_heading_tables built with this very function
+    hN = sg.hN[jP - 1]; hE = sg.hE[iP - 1]; hS = sg.hS[jP - 1]; hW = sg.hW[iP - 1];
+  } else {
+    hN = d_heading_y(lonP, lonN, ya, src_merc(sg, iP, jPp1));
+    hE = d_heading_y(lonP, lonE, ya, src_merc(sg, iPp1, jP));
+    hS = d_heading_y(lonP, lonS, ya, src_merc(sg, iP, jPm1));
+    hW = d_heading_y(lonP, lonW, ya, src_merc(sg, iPm1, jP));
+  }
+  int iqdrn = 4;
+  double hPp = d_degE_to_degWE(hP);
+  if (hN > hE) hN = hN - 360.0;
+  if (hPp > hN && hPp <= hE) iqdrn = 1;
+  if (hP > hE && hP <= hS) iqdrn = 2;
+  if (hP > hS && hP <= hW) iqdrn = 3;
+  if (hP > hW && hPp <= hN) iqdrn = 4;
+  return iqdrn;
+}
+
+// the same for a regular source, out of line: only targets within 1e-7 degrees of a grid line (or beyond 89 degrees) get here
+static __device__ __noinline__ int first_guess_quadrant_rare(const SrcGeom& sg, double xP, double yP, int iP, int jP, int iPm1,
+                                                             int iPp1, int jPm1, int jPp1, double lonP, double lonN, double lonE,
+                                                             double lonS, double lonW) {
+  return first_guess_quadrant<true>(sg, xP, yP, iP, jP, iPm1, iPp1, jPm1, jPp1, lonP, lonN, lonE, lonS, lonW);
+}
+
 template <bool SEP>
 __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP, double yP, int iP, int jP, MapOut& o,
                                          int* err, bool have_u = false, double ux0 = 0.0, double uy0 = 0.0, double uz0 = 0.0,
@@ -540,26 +575,34 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
     lonW = d_mod(src_lon(sg, iPm1, jP), 360.0); latW = src_lat(sg, iPm1, jP);
   }
   xP = d_mod(xP, 360.0);
-  double ya = SEP ? sg.merc[jP - 1] : src_merc(sg, iP, jP);
-  double hP = d_heading_y(lonP, xP, ya, d_merc(yP));
-  double hN, hE, hS, hW;
-  if (SEP) {
-    // regular source: lonN == lonS == lonP and the E/W neighbours share the row's ordinate, so these four are
-    // functions of jP (N, S) or iP (E, W) alone -- read from the tables k_heading_tables built with this very function
-    hN = sg.hN[jP - 1]; hE = sg.hE[iP - 1]; hS = sg.hS[jP - 1]; hW = sg.hW[iP - 1];
-  } else {
-    hN = d_heading_y(lonP, lonN, ya, src_merc(sg, iP, jPp1));
-    hE = d_heading_y(lonP, lonE, ya, src_merc(sg, iPp1, jP));
-    hS = d_heading_y(lonP, lonS, ya, src_merc(sg, iP, jPm1));
-    hW = d_heading_y(lonP, lonW, ya, src_merc(sg, iPm1, jP));
-  }
   int iqdrn = 4;
-  double hPp = d_degE_to_degWE(hP);
-  if (hN > hE) hN = hN - 360.0;
-  if (hPp > hN && hPp <= hE) iqdrn = 1;
-  if (hP > hE && hP <= hS) iqdrn = 2;
-  if (hP > hS && hP <= hW) iqdrn = 3;
-  if (hP > hW && hPp <= hN) iqdrn = 4;
+  bool quad_known = false;
+  if (SEP) {
+    // Regular source: the neighbour headings are table entries (functions of jP or iP alone, see k_heading_tables) and on
+    // a grid whose rows / columns are parallels / meridians they are exactly 0, 90, 180, 270.  The first-guess quadrant
+    // (:531-540) is then decided by the signs of the two arguments of heading()'s ATAN2 -- the wrapped longitude
+    // difference, formed here exactly as heading() forms it, and the difference of the Mercator ordinates, whose sign is
+    // that of yP - latP (the ordinate is increasing with slope >= 1 and both values carry < 1e-13 of rounding error below
+    // 89 degrees; a margin of 1e-7 degrees is 1.7e-9).  With both arguments at least 2e-10 of each other the angle stays
+    // > 1e-10 rad inside its quarter, far above the rounding of ATAN2 and of the conversion to degrees: the comparisons
+    // of the reference cannot come out differently.  Anything closer to an axis takes the literal path below.
+    const double hN = sg.hN[jP - 1], hE = sg.hE[iP - 1], hS = sg.hS[jP - 1], hW = sg.hW[iP - 1];
+    if (hN == 0.0 && hE == 90.0 && hS == 180.0 && hW == 270.0) {
+      double dx = d_mod((xP * G_ZCONV - lonP * G_ZCONV), 2 * G_PI);
+      if (dx >= G_PI) dx = dx - 2 * G_PI;
+      if (dx <= -G_PI) dx = dx + 2 * G_PI;
+      const double dphi = yP - latP;
+      const double adx = fabs(dx), adp = fabs(dphi);
+      if (adx >= 2.0e-9 && adx <= 0.8 && adp >= 1.0e-7 && adp <= 45.0 && fabs(yP) <= 89.0 && fabs(latP) <= 89.0) {
+        quad_known = true;
+        iqdrn = (dx > 0.0) ? ((dphi > 0.0) ? 1 : 2) : ((dphi > 0.0) ? 4 : 3);
+      }
+    }
+  }
+  if (!quad_known) {
+    if (SEP) iqdrn = first_guess_quadrant_rare(sg, xP, yP, iP, jP, iPm1, iPp1, jPm1, jPp1, lonP, lonN, lonE, lonS, lonW);
+    else iqdrn = first_guess_quadrant<false>(sg, xP, yP, iP, jP, iPm1, iPp1, jPm1, jPp1, lonP, lonN, lonE, lonS, lonW);
+  }
   double loni[5], lati[5];
   loni[0] = xP; lati[0] = yP;
   loni[1] = lonP; lati[1] = latP;

@@ -484,3 +484,55 @@ def test_akima_config_E_shape(gpu, orc):
     Z2o, ixy = orc.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, Xt, Yt)
     assert np.array_equal(gpu.akima_get_ixy(), ixy)
     assert np.array_equal(Z2g, Z2o), f"{(Z2g != Z2o).sum()} points differ, max {np.abs(Z2g - Z2o).max()}"
+
+
+@pytest.mark.parametrize("kind", ["cell", "node", "overlap", "regional"])
+def test_first_guess_quadrant_near_grid_lines(gpu, orc, kind):
+    """The regular-source mapping decides MAPPING_BL's first-guess quadrant (src/mod_bilin_2d.f90:511-540) from the signs
+    of heading()'s ATAN2 arguments when the target is at least 1e-7 degrees away from the grid lines through the nearest
+    point, and literally otherwise.  Targets ON source nodes, on grid lines, and at offsets straddling that threshold
+    (where two quadrants pass L_InPoly and the first guess decides the stored iqdrn / alpha / beta) must match the oracle."""
+    rng = np.random.default_rng(42)
+    if kind == "cell":
+        nx, ny, kew = 72, 36, 0
+        lon = (np.arange(nx) + 0.5) * 360.0 / nx
+        lat = -90.0 + (np.arange(ny) + 0.5) * 180.0 / ny
+    elif kind == "node":
+        nx, ny, kew = 90, 61, 0
+        lon = np.arange(nx) * 360.0 / nx
+        lat = np.linspace(-90.0, 90.0, ny)
+    elif kind == "overlap":
+        nx, ny, kew = 62, 40, 2
+        lon = np.mod(13.0 + np.arange(nx) * 360.0 / (nx - 2), 360.0)
+        lat = np.linspace(-78.0, 89.5, ny)
+    else:
+        nx, ny, kew = 80, 50, -1
+        lon = 20.0 + np.arange(nx) * 0.25
+        lat = 70.0 + np.arange(ny) * 0.4            # crosses the 89-degree limit of the shortcut
+        lat = lat[lat < 89.9]
+        ny = lat.size
+    offs = np.array([0.0, 1e-9, -1e-9, 5e-8, -5e-8, 0.99e-7, -0.99e-7, 1e-7, -1e-7, 1.01e-7, -1.01e-7, 3e-7, -3e-7, 1e-3, -1e-3])
+    ii = rng.integers(1, nx - 1, 40)
+    jj = rng.integers(1, ny - 1, 40)
+    cell_x, cell_y = np.abs(lon[1] - lon[0]), np.abs(lat[1] - lat[0])
+    X, Y = [], []
+    for i, j in zip(ii, jj):
+        for dx in np.concatenate([offs, [0.3 * cell_x, -0.3 * cell_x]]):
+            for dy in np.concatenate([offs, [0.3 * cell_y, -0.3 * cell_y]]):
+                X.append(np.mod(lon[i] + dx, 360.0)); Y.append(min(max(lat[j] + dy, -89.99), 89.99))
+    n = len(X)
+    ncol = 17 * 5
+    nrow = n // ncol
+    Xt = np.array(X[:nrow * ncol]).reshape(nrow, ncol)
+    Yt = np.array(Y[:nrow * ncol]).reshape(nrow, ncol)
+    Z1 = (np.cos(4 * np.deg2rad(lon))[None, :] * np.sin(4 * np.deg2rad(lat))[:, None]).astype(np.float32)
+    gpu.l_first_call_interp_routine = True
+    Z2g = gpu.bilin_2d(kew, lon, lat, Z1, Xt, Yt, l_reg_src=True)
+    mg = gpu.bilin_get_map()
+    Z2o, mo = orc.bilin_2d(kew, lon, lat, Z1, Xt, Yt, l_reg_src=True)
+    for k in ("metrics", "ipb", "alphabeta", "dist_np"):
+        bad = np.argwhere(np.asarray(mg[k]) != np.asarray(mo[k]))
+        assert bad.size == 0, f"{kind}: {k} differs at {len(bad)} targets, first {bad[:5].tolist()}"
+    assert np.array_equal(Z2g, Z2o)
+    # the case is only meaningful if all four quadrants occur
+    assert set(np.unique(np.asarray(mo["metrics"])[2])) >= {1, 2, 3, 4}
