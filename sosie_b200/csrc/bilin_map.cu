@@ -617,44 +617,70 @@ __device__ __forceinline__ void map_body(const SrcGeom& sg, int k_ew, double xP,
       o.dnp = dnp_noinline(sg, xP, yP, lonP, latP, iP, jP, have_u, ux0, uy0, uz0);
     }
   }
-  int icpt = 0;
-  bool lagain = true;
-  const int iqdrn0 = 0;  // Q2
-  while (lagain) {
-    switch (iqdrn) {
-      case 1:
-        loni[2] = lonE; lati[2] = latE;
-        if (SEP) { loni[3] = lonE; lati[3] = latN; }
-        else { loni[3] = d_mod(src_lon(sg, iPp1, jPp1), 360.0); lati[3] = src_lat(sg, iPp1, jPp1); }
-        loni[4] = lonN; lati[4] = latN;
-        break;
-      case 2:
-        loni[2] = lonS; lati[2] = latS;
-        if (SEP) { loni[3] = lonE; lati[3] = latS; }
-        else { loni[3] = d_mod(src_lon(sg, iPp1, jPm1), 360.0); lati[3] = src_lat(sg, iPp1, jPm1); }
-        loni[4] = lonE; lati[4] = latE;
-        break;
-      case 3:
-        loni[2] = lonW; lati[2] = latW;
-        if (SEP) { loni[3] = lonW; lati[3] = latS; }
-        else { loni[3] = d_mod(src_lon(sg, iPm1, jPm1), 360.0); lati[3] = src_lat(sg, iPm1, jPm1); }
-        loni[4] = lonS; lati[4] = latS;
-        break;
-      case 4:
-        loni[2] = lonN; lati[2] = latN;
-        if (SEP) { loni[3] = lonW; lati[3] = latN; }
-        else { loni[3] = d_mod(src_lon(sg, iPm1, jPp1), 360.0); lati[3] = src_lat(sg, iPm1, jPp1); }
-        loni[4] = lonW; lati[4] = latW;
-        break;
-      default: break;
+  if (SEP) {
+    // regular source: the quad of quadrant q is an axis-parallel cell with corners (lonP | lonE/W) x (latP | latN/S); the
+    // "WHERE(loni <= 0) loni + 360" of :577 depends on the value alone and is applied to the three longitudes once
+    const double xa = (lonP <= 0.0) ? lonP + 360.0 : lonP;
+    const double xe = (lonE <= 0.0) ? lonE + 360.0 : lonE;
+    const double xw = (lonW <= 0.0) ? lonW + 360.0 : lonW;
+    int icpt = 0, qbuilt = iqdrn;
+    bool lagain = true;
+    const int iqdrn0 = 0;  // Q2
+    while (lagain) {
+      qbuilt = iqdrn;      // 1..4 here: the first guess, then icpt = 1..4
+      const double xb = (iqdrn <= 2) ? xe : xw;
+      const double yb = (iqdrn == 1 || iqdrn == 4) ? latN : latS;
+      int ok = d_l_inpoly_rect(xa, xb, latP, yb, (iqdrn & 1) != 0, xP, yP);  // Q8: the un-moved xP
+      if (ok < 0) { atomicOr(err, 1); ok = 0; }
+      if ((!ok) && (yP < 88.0)) { icpt = icpt + 1; iqdrn = icpt; }
+      else lagain = false;
+      if (icpt == 5) { lagain = false; iqdrn = iqdrn0; }
     }
+    // the arrays LOCAL_COORD sees are those of the last quad built
+    const double xb = (qbuilt <= 2) ? xe : xw;
+    const double yb = (qbuilt == 1 || qbuilt == 4) ? latN : latS;
+    const bool pa = (qbuilt & 1) != 0;
+    if (loni[0] <= 0.0) loni[0] = loni[0] + 360.0;
+    loni[1] = xa; lati[1] = latP;
+    loni[2] = pa ? xb : xa; lati[2] = pa ? latP : yb;
+    loni[3] = xb; lati[3] = yb;
+    loni[4] = pa ? xa : xb; lati[4] = pa ? yb : latP;
+  } else {
+    int icpt = 0;
+    bool lagain = true;
+    const int iqdrn0 = 0;  // Q2
+    while (lagain) {
+      switch (iqdrn) {
+        case 1:
+          loni[2] = lonE; lati[2] = latE;
+          loni[3] = d_mod(src_lon(sg, iPp1, jPp1), 360.0); lati[3] = src_lat(sg, iPp1, jPp1);
+          loni[4] = lonN; lati[4] = latN;
+          break;
+        case 2:
+          loni[2] = lonS; lati[2] = latS;
+          loni[3] = d_mod(src_lon(sg, iPp1, jPm1), 360.0); lati[3] = src_lat(sg, iPp1, jPm1);
+          loni[4] = lonE; lati[4] = latE;
+          break;
+        case 3:
+          loni[2] = lonW; lati[2] = latW;
+          loni[3] = d_mod(src_lon(sg, iPm1, jPm1), 360.0); lati[3] = src_lat(sg, iPm1, jPm1);
+          loni[4] = lonS; lati[4] = latS;
+          break;
+        case 4:
+          loni[2] = lonN; lati[2] = latN;
+          loni[3] = d_mod(src_lon(sg, iPm1, jPp1), 360.0); lati[3] = src_lat(sg, iPm1, jPp1);
+          loni[4] = lonW; lati[4] = latW;
+          break;
+        default: break;
+      }
 #pragma unroll
-    for (int k = 0; k < 5; k++) if (loni[k] <= 0.0) loni[k] = loni[k] + 360.0;
-    int ok = d_l_inpoly(&loni[1], &lati[1], xP, yP);  // Q8: the un-moved xP
-    if (ok < 0) { atomicOr(err, 1); ok = 0; }
-    if ((!ok) && (yP < 88.0)) { icpt = icpt + 1; iqdrn = icpt; }
-    else lagain = false;
-    if (icpt == 5) { lagain = false; iqdrn = iqdrn0; }
+      for (int k = 0; k < 5; k++) if (loni[k] <= 0.0) loni[k] = loni[k] + 360.0;
+      int ok = d_l_inpoly(&loni[1], &lati[1], xP, yP);  // Q8: the un-moved xP
+      if (ok < 0) { atomicOr(err, 1); ok = 0; }
+      if ((!ok) && (yP < 88.0)) { icpt = icpt + 1; iqdrn = icpt; }
+      else lagain = false;
+      if (icpt == 5) { lagain = false; iqdrn = iqdrn0; }
+    }
   }
   d_local_coord(loni, lati, o.a, o.b, o.ipb);
   o.iq = iqdrn;

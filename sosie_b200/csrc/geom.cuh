@@ -171,6 +171,49 @@ __device__ __forceinline__ int d_l_inpoly(const double* vplon, const double* vpl
   return (icross & 1);
 }
 
+// L_InPoly for the cells of a regular source: the quad is (xa,ya) -> (xb,ya) -> (xb,yb) -> (xa,yb) (pattern A: quadrants 1
+// and 3 of MAPPING_BL) or (xa,ya) -> (xa,yb) -> (xb,yb) -> (xb,ya) (pattern B: quadrants 2 and 4).  Same statements as
+// d_l_inpoly on those vertices, with what is known about them folded in: equal REAL(8) values stay equal through the
+// re-framing, the REAL(4) cast and the +0.001 nudge, so two edges have zrise == 0 -- PointSlope gives slope 0 (ignored),
+// or 9999 when the cast also merged the two abscissae, and then the crossing test needs zy strictly between two equal
+// ordinates: never counted either way -- and the other two have zrun == 0: slope 9999, the "vertical" branch.
+__device__ __forceinline__ int d_l_inpoly_rect(double xa, double xb, double ya, double yb, bool pattern_a, double pxpoint,
+                                               double pypoint) {
+  float fxa = (float)xa, fxb = (float)xb;
+  const float fya0 = (float)ya, fyb0 = (float)yb;
+  float rmaxx = fmaxf(fxa, fxb), rminx = fminf(fxa, fxb);
+  const float rmaxy = fmaxf(fya0, fyb0), rminy = fminf(fya0, fyb0);
+  if ((rminx < 0.f) || (pxpoint < 0.0)) return -1;
+  double zx;
+  if ((rminx < 10.f) && (rmaxx > 350.f)) {
+    zx = d_sign(1.0, 180.0 - pxpoint) * fmin(pxpoint, fabs(pxpoint - 360.0));
+    fxa = (float)(d_sign(1.0, 180.0 - xa) * fmin(xa, fabs(xa - 360.0)));
+    fxb = (float)(d_sign(1.0, 180.0 - xb) * fmin(xb, fabs(xb - 360.0)));
+    rmaxx = fmaxf(fxa, fxb);
+    rminx = fminf(fxa, fxb);
+  } else {
+    zx = pxpoint;
+  }
+  const double zy = pypoint;
+  float fya = fya0, fyb = fyb0;
+  if ((fxa - (float)(int)fxa) == 0) fxa = __fadd_rn(fxa, 0.001f);
+  if ((fxb - (float)(int)fxb) == 0) fxb = __fadd_rn(fxb, 0.001f);
+  if ((fya - (float)(int)fya) == 0) fya = __fadd_rn(fya, 0.001f);
+  if ((fyb - (float)(int)fyb) == 0) fyb = __fadd_rn(fyb, 0.001f);
+  if (!(zx <= (double)rmaxx)) return 0;
+  if (!(zx >= (double)rminx)) return 0;
+  if (!(zy <= (double)rmaxy)) return 0;
+  if (!(zy >= (double)rminy)) return 0;
+  const double Xa = fxa, Xb = fxb, Ya = fya, Yb = fyb;
+  // an edge running from Ya to Yb counts zy in the interval that includes the Ya end; the one running back includes Yb
+  const bool in_from_a = ((zy <= Ya) && (zy > Yb)) || ((zy >= Ya) && (zy < Yb));
+  const bool in_from_b = ((zy <= Yb) && (zy > Ya)) || ((zy >= Yb) && (zy < Ya));
+  // pattern A: edge (xb: ya -> yb) and edge (xa: yb -> ya); pattern B: edge (xa: ya -> yb) and edge (xb: yb -> ya)
+  const double x_from_a = pattern_a ? Xb : Xa, x_from_b = pattern_a ? Xa : Xb;
+  const int icross = (int)((zx >= x_from_a) && in_from_a) + (int)((zx >= x_from_b) && in_from_b);
+  return (icross & 1);
+}
+
 // x / y for a finite non-zero y: identical to the IEEE quotient, without the divide's slow path when x == 0
 __device__ __forceinline__ double d_div_nz(double x, double y) {
   if (x == 0.0) return (signbit(x) != signbit(y)) ? -0.0 : 0.0;
@@ -180,7 +223,6 @@ __device__ __forceinline__ double d_det(double p1, double p2, double p3, double 
 
 // LOCAL_COORD, src/mod_bilin_2d.f90:697-799
 __device__ __forceinline__ void d_local_coord(const double* xlam, const double* xphi, double& xa, double& xb, int& ipb) {
-  const double zresmax = (double)0.1f;
   const int itermax = 200;
   double zxlam[5];
   ipb = 0;
@@ -191,7 +233,11 @@ __device__ __forceinline__ void d_local_coord(const double* xlam, const double* 
 #pragma unroll
     for (int k = 0; k < 5; k++) zxlam[k] = d_degE_to_degWE(zxlam[k]);
   }
-  double zres = 1000.0, zdlam = 0.5, zdphi = 0.5, zalpha = 0.0, zbeta = 0.0;
+  // "zres > zresmax" with zres = SQRT(s) is decided on s itself: SQRT is correctly rounded and monotone, and
+  // 0x1.47ae151eb8520p-7 is the largest REAL(8) whose square root rounds to <= REAL(0.1,4) (tests/test_pmath.py), so
+  // s > that bound <=> SQRT(s) > zresmax (both false for NaN, both true for +Inf).  Saves one SQRT per iteration.
+  const double zres2max = 0x1.47ae151eb8520p-7;
+  double zres2 = 1.0e6, zdlam = 0.5, zdphi = 0.5, zalpha = 0.0, zbeta = 0.0;
   int niter = 0;
   const double z1 = (zxlam[2] - zxlam[1]);
   const double z2 = (zxlam[1] - zxlam[4]);
@@ -199,7 +245,7 @@ __device__ __forceinline__ void d_local_coord(const double* xlam, const double* 
   const double p21 = xphi[2] - xphi[1];
   const double p41 = xphi[4] - xphi[1];
   const double pc = (xphi[1] - xphi[4] + xphi[3] - xphi[2]);
-  while ((zres > zresmax) && (niter < itermax)) {
+  while ((zres2 > zres2max) && (niter < itermax)) {
     double za11 = z1 + (z2 + z3) * zbeta;
     double za12 = -z2 + (z2 + z3) * zalpha;
     double za21 = p21 + pc * zbeta;
@@ -208,7 +254,7 @@ __device__ __forceinline__ void d_local_coord(const double* xlam, const double* 
     zdeta = (d_sign(1.0, zdeta) * fmax(fabs(zdeta), G_REPS));
     double zdalp = d_div_nz(d_det(zdlam, za12, zdphi, za22), zdeta);  // |zdeta| >= repsilon: finite, non-zero
     double zdbet = d_div_nz(d_det(za11, zdlam, za21, zdphi), zdeta);
-    zres = sqrt(zdalp * zdalp + zdbet * zdbet);
+    zres2 = zdalp * zdalp + zdbet * zdbet;
     zalpha = zalpha + zdalp;
     zbeta = zbeta + zdbet;
     zdlam = zxlam[0] - ((1.0 - zalpha) * (1 - zbeta) * zxlam[1] + zalpha * (1 - zbeta) * zxlam[2] +

@@ -69,3 +69,23 @@ def test_pmath_special_values(orc):
     assert pm[0] == 0.0 and pm[1] == pi / 2 and pm[2] == pi and pm[3] == -pi / 2
     pm, _ = orc.pmath_eval(LOG, np.array([1.0, math.e]))
     assert pm[0] == 0.0 and abs(pm[1] - 1.0) < 3e-16
+
+
+def test_local_coord_squared_residual_bound():
+    """geom.cuh decides LOCAL_COORD's "zres > zresmax" (src/mod_bilin_2d.f90:741, zres = SQRT(s), zresmax = 0.1 in REAL(4))
+    on s: 0x1.47ae151eb8520p-7 must be the largest double whose correctly rounded square root is <= REAL(0.1,4)."""
+    import math
+    from fractions import Fraction as Fr
+    import re
+    import os
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sosie_b200", "csrc", "geom.cuh")).read()
+    m = re.search(r"zres2max = (0x[0-9a-fp.+-]+);", src)
+    assert m, "constant not found in geom.cuh"
+    s0 = float.fromhex(m.group(1))
+    c = float(np.float32(0.1))
+    bound = (Fr(c) + Fr(math.ulp(c)) / 2) ** 2      # sqrt(s) rounds to <= c  <=>  s <= (c + ulp/2)^2 (tie to even: c is even)
+    assert Fr(s0) <= bound < Fr(math.nextafter(s0, 1.0))
+    y_dn, y_up = s0, math.nextafter(s0, 1.0)
+    for _ in range(200):                             # math.sqrt is correctly rounded
+        assert not (math.sqrt(y_dn) > c) and (math.sqrt(y_up) > c)
+        y_dn, y_up = math.nextafter(y_dn, 0.0), math.nextafter(y_up, 1.0)
