@@ -94,6 +94,16 @@ int sosie_bilin_set_grids_dev(sosie_ctx* ctx, int32_t k_ew_per,
                               int32_t nx2, int32_t ny2, const double* dX20, const double* dY20, int32_t trg_1d,
                               const int32_t* dmask_domain_trg, int32_t i_orca_trg);
 
+/* FIND_NEAREST_POINT, src/mod_manip.f90:834-963, as the public procedure ij_from_lon_lat.f90:290 calls: for every target
+ * point the (i,j) of the nearest source point, -1 where the target was not searched (masked, outside the source's
+ * latitude range) or not found.  All four coordinate arrays are 2-D, (nx,ny) column-major, as the assumed-shape
+ * dummies of the reference; the search picks EASY or TWISTED itself (L_IS_GRID_REGULAR on the source, :1632).
+ * mask_domain_trg (INTENT(inout), OPTIONAL in the reference): NULL = absent; on return it holds mask_ignore_t (:958).
+ * Leaves no mapping in the context.                                                                                 */
+int sosie_find_nearest_point(sosie_ctx* ctx, int32_t nx_t, int32_t ny_t, const double* Xtrg, const double* Ytrg,
+                             int32_t nx_s, int32_t ny_s, const double* Xsrc, const double* Ysrc,
+                             int32_t* JIp, int32_t* JJp, int32_t* mask_domain_trg);
+
 /* MAPPING_BL (:366-691): builds, on device, metrics(nx2,ny2,3)=(iP,jP,iqdrn), alphabeta(nx2,ny2,2),
  * ID_problem(nx2,ny2) and distance_to_np(nx2,ny2), and keeps them cached in the context.          */
 int sosie_bilin_map(sosie_ctx* ctx);

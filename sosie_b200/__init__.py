@@ -44,7 +44,7 @@ EXPORTS = [
     "sosie_mapping_write_bin", "sosie_mapping_read_header_bin", "sosie_mapping_read_bin", "sosie_akima_untiled_slopes",
     "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev", "sosie_bilin_get_map_dev", "sosie_bilin_load_map_dev",
     "sosie_akima_1d_1d", "sosie_akima_1d_1d_dev", "sosie_interp3d_sigma", "sosie_interp3d_sigma_dev",
-    "sosie_track_interp", "sosie_track_interp_dev", "sosie_set_exchange", "sosie_exchange_used",
+    "sosie_track_interp", "sosie_track_interp_dev", "sosie_set_exchange", "sosie_exchange_used", "sosie_find_nearest_point",
 ]
 
 _lib = None
@@ -234,6 +234,20 @@ class Sosie:
         self._ck(self._lib.sosie_bilin_set_grids_dev(self._h, int(k_ew_per), nx1, ny1, _dp(dX10), _dp(dY10), int(src_1d),
                                                      int(l_reg_src), nx2, ny2, _dp(dX20), _dp(dY20), int(trg_1d), _dp(dmask),
                                                      int(i_orca_trg)))
+
+    def find_nearest_point(self, Xtrg, Ytrg, Xsrc, Ysrc, mask_domain_trg=None):
+        """FIND_NEAREST_POINT (src/mod_manip.f90:834): 2-D coordinate arrays in, (JIp, JJp, mask) out; mask is None when
+        mask_domain_trg is not given (the OPTIONAL dummy absent)."""
+        Xtrg, Ytrg, Xsrc, Ysrc = _f64(Xtrg), _f64(Ytrg), _f64(Xsrc), _f64(Ysrc)
+        assert Xtrg.ndim == 2 and Xsrc.ndim == 2 and Ytrg.shape == Xtrg.shape and Ysrc.shape == Xsrc.shape
+        nyt, nxt = Xtrg.shape
+        nys, nxs = Xsrc.shape
+        JI = np.empty((nyt, nxt), np.int32)
+        JJ = np.empty((nyt, nxt), np.int32)
+        m = None if mask_domain_trg is None else _i32(mask_domain_trg).copy()
+        self._ck(self._lib.sosie_find_nearest_point(self._h, nxt, nyt, _p(Xtrg), _p(Ytrg), nxs, nys, _p(Xsrc), _p(Ysrc),
+                                                    _p(JI), _p(JJ), _p(m)))
+        return JI, JJ, m
 
     def bilin_map(self):
         """MAPPING_BL on device."""

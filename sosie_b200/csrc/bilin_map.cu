@@ -715,7 +715,7 @@ template <bool SEP>
 __global__ void __launch_bounds__(128, MAP_MIN_BLOCKS)
 k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
            const double* __restrict__ vlat, int sorted_lon, int sorted_lat, int jlo, int jhi, int32_t* MT, double* AB,
-           int16_t* IDP, float* DNP, int* err, size_t k0, size_t kcnt) {
+           int16_t* IDP, float* DNP, int* err, size_t k0, size_t kcnt, int search_only) {
   const size_t nt = (size_t)tg.nx * tg.ny;
   for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < kcnt; kk += (size_t)gridDim.x * blockDim.x) {
     const size_t k = k0 + kk;
@@ -739,6 +739,7 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
     }
     MapOut o;
     o.iq = 0; o.a = 0.0; o.b = 0.0; o.ipb = 0; o.dnp = 0.f;
+    if (search_only) { MT[k] = iP; MT[k + nt] = jP; continue; }   // FIND_NEAREST_POINT alone: JIp, JJp (-1 where not searched)
     if (m == 1) map_body<SEP>(sg, k_ew, rlon, rlat, iP, jP, o, err, have_u, ux, uy, uz, bpds, bd);
     map_store(o, iP, jP, m, k, nt, MT, AB, IDP, DNP);
   }
@@ -1405,11 +1406,11 @@ int bilin_easy_rows(sosie_ctx* ctx, int jlo, int jhi, size_t k0, size_t kcnt, in
   if (sg.separable)
     k_map_easy<true><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->mask_is_ones ? nullptr : ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
                                                                  ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
-                                                                 ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt);
+                                                                 ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt, ctx->search_only ? 1 : 0);
   else
     k_map_easy<false><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->mask_is_ones ? nullptr : ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
                                                                   ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
-                                                                  ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt);
+                                                                  ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt, ctx->search_only ? 1 : 0);
   KLAUNCH_CHECK();
   return SOSIE_OK;
 }
@@ -1595,14 +1596,19 @@ int bilin_map_impl(sosie_ctx* ctx) {
       k_twisted_scatter<<<grid_for(ctx, T, 256), 256, 0, st>>>(order.p, T, Sa, found.p, JI.p, JJ.p); KLAUNCH_CHECK();
     }
     k_twisted_mask<<<grid_for(ctx, nt, 256), 256, 0, st>>>(JI.p, JJ.p, ctx->t_mask.p, nt); KLAUNCH_CHECK();
-    k_map_body<<<grid_for(ctx, nt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, JI.p, JJ.p, MT, AB, IDP, DNP, derr.p); KLAUNCH_CHECK();
+    if (ctx->search_only) {
+      CK(cudaMemcpyAsync(MT, JI.p, nt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(MT + nt, JJ.p, nt * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    } else {
+      k_map_body<<<grid_for(ctx, nt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->t_mask.p, JI.p, JJ.p, MT, AB, IDP, DNP, derr.p); KLAUNCH_CHECK();
+    }
     CK(cudaStreamSynchronize(st));
   }
   int herr = 0;
   if (int rc = fetch_small(ctx, derr.p, &herr, sizeof(int))) return rc;
   if (herr & 1) { ctx->err = "ERROR (L_InPoly of mod_poly.f90): we only expect positive longitudes!"; return SOSIE_ERR_REF_STOP; }
   if (herr & 6) { ctx->err = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)"; return SOSIE_ERR_REF_STOP; }
-  ctx->map_ready = true;
+  ctx->map_ready = !ctx->search_only;   // a search-only run leaves no mapping behind
   ctx->map_nt = nt;
   ctx->pack_ready = false;
   return SOSIE_OK;

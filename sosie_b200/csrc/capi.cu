@@ -155,6 +155,33 @@ int sosie_bilin_map(sosie_ctx* c) {
   return bilin_map_impl(ctx);
 }
 
+// FIND_NEAREST_POINT as a procedure of its own (src/mod_manip.f90:834-963; called directly by ij_from_lon_lat.f90:290)
+int sosie_find_nearest_point(sosie_ctx* c, int32_t nx_t, int32_t ny_t, const double* Xtrg, const double* Ytrg, int32_t nx_s,
+                             int32_t ny_s, const double* Xsrc, const double* Ysrc, int32_t* JIp, int32_t* JJp,
+                             int32_t* mask_domain_trg) {
+  NEED(c);
+  if (!JIp || !JJp) { ctx->err = "sosie_find_nearest_point: null output pointer"; return SOSIE_ERR_ARG; }
+  if (ctx->shard_j0 > 0) { ctx->err = "sosie_find_nearest_point: not available on a sharded context"; return SOSIE_ERR_STATE; }
+  // the arrays as they are: no pole extension (l_reg_src = 0 keeps BILIN_2D's prologue out), no periodicity (unused by the search)
+  if (int rc = sosie_bilin_set_grids(ctx, -1, nx_s, ny_s, Xsrc, Ysrc, 0, 0, nx_t, ny_t, Xtrg, Ytrg, 0, mask_domain_trg, 0)) return rc;
+  ctx->search_only = true;
+  int rc = bilin_map_impl(ctx);
+  ctx->search_only = false;
+  ctx->map_ready = false;
+  if (rc) return rc;
+  const size_t nt = (size_t)nx_t * ny_t;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(JIp, ctx->d_metrics.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(JJp, ctx->d_metrics.p + nt, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (mask_domain_trg) {   // mask_domain_trg(:,:) = mask_ignore_t(:,:) (:958): TWISTED marks the targets it could not place
+    if (ctx->mask_is_ones) { if (int r2 = bilin_materialize_mask(ctx)) return r2; }
+    CK(cudaMemcpyAsync(mask_domain_trg, ctx->t_mask.p, nt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  ctx->grids_set = false;   // the next BILIN_2D-style call sets its own grids
+  return SOSIE_OK;
+}
+
 int sosie_bilin_map_info(sosie_ctx* c, int32_t* info) {
   NEED(c);
   if (!info) return SOSIE_ERR_ARG;

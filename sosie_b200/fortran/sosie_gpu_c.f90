@@ -51,6 +51,16 @@ MODULE SOSIE_GPU_C
          IMPORT :: C_PTR, C_INT
          TYPE(C_PTR), VALUE :: p
       END FUNCTION
+      ! FIND_NEAREST_POINT (mod_manip.f90:834) for its direct callers (ij_from_lon_lat.f90:290); mask = C_NULL_PTR when the
+      ! OPTIONAL mask_domain_trg is absent, else C_LOC of the INTEGER(4) array (inout)
+      INTEGER(C_INT) FUNCTION sosie_find_nearest_point(ctx, nx_t, ny_t, Xtrg, Ytrg, nx_s, ny_s, Xsrc, Ysrc, JIp, JJp, mask) &
+         &           BIND(C, name='sosie_find_nearest_point')
+         IMPORT :: C_PTR, C_INT, C_DOUBLE
+         TYPE(C_PTR), VALUE    :: ctx, mask
+         INTEGER(C_INT), VALUE :: nx_t, ny_t, nx_s, ny_s
+         REAL(C_DOUBLE)        :: Xtrg(*), Ytrg(*), Xsrc(*), Ysrc(*)
+         INTEGER(C_INT)        :: JIp(*), JJp(*)
+      END FUNCTION
       INTEGER(C_INT) FUNCTION sosie_bilin_map(ctx) BIND(C, name='sosie_bilin_map')
          IMPORT :: C_PTR, C_INT
          TYPE(C_PTR), VALUE :: ctx

@@ -536,3 +536,43 @@ def test_first_guess_quadrant_near_grid_lines(gpu, orc, kind):
     assert np.array_equal(Z2g, Z2o)
     # the case is only meaningful if all four quadrants occur
     assert set(np.unique(np.asarray(mo["metrics"])[2])) >= {1, 2, 3, 4}
+
+
+@pytest.mark.parametrize("case", ["easy_regular", "twisted_orca", "track_1xN", "masked"])
+def test_find_nearest_point_entry(gpu, orc, case):
+    """sosie_find_nearest_point = FIND_NEAREST_POINT as ij_from_lon_lat.f90:290 calls it (2-D arrays, no BILIN_2D
+    prologue, optional mask): JIp / JJp / mask_ignore_t bit-identical to the oracle's FIND_NEAREST_POINT."""
+    rng = np.random.default_rng(17)
+    mask = None
+    if case == "easy_regular":
+        lon = (np.arange(90) + 0.5) * 4.0
+        lat = -88.0 + np.arange(45) * 4.0
+        Xs, Ys = np.meshgrid(lon, lat)
+        Xt = rng.uniform(0.0, 360.0, (23, 31)); Yt = np.sort(rng.uniform(-89.0, 89.0, (23, 31)), axis=0)
+    elif case == "masked":
+        lon = 10.0 + np.arange(60) * 0.5
+        lat = 30.0 + np.arange(40) * 0.5
+        Xs, Ys = np.meshgrid(lon, lat)
+        Xt, Yt = np.meshgrid(np.linspace(12.0, 38.0, 20), np.linspace(25.0, 55.0, 25))   # rows outside the source latitudes
+        mask = (rng.random(Xt.shape) > 0.3).astype(np.int32)
+    else:
+        cfg = G.config("B", 0.25)
+        Xs, Ys = G.src_2d(cfg)
+        if case == "twisted_orca":
+            Xt, Yt = G.trg_2d(cfg)
+        else:   # a ground track: (1,N) arrays in Fortran = (N,1)... the reference passes (1,npoints): nx_t = 1
+            n = 300
+            t = np.linspace(0.0, 1.0, n)
+            Xt = np.mod(20.0 + 300.0 * t, 360.0).reshape(n, 1)
+            Yt = (60.0 * np.sin(7.0 * t)).reshape(n, 1)
+    JIg, JJg, mg = gpu.find_nearest_point(Xt, Yt, Xs, Ys, mask_domain_trg=mask)
+    JIo, JJo, mo, used, info = orc.find_nearest_point(Xt, Yt, Xs, Ys, mask=mask)
+    assert orc.get_error() == 0
+    assert np.array_equal(JIg, JIo), f"{case}: JIp differs at {(JIg != JIo).sum()} targets"
+    assert np.array_equal(JJg, JJo), f"{case}: JJp differs at {(JJg != JJo).sum()} targets"
+    if mask is not None:
+        assert np.array_equal(mg, mo)
+    assert (JIo > 0).any()
+    # the context is left without a mapping
+    with pytest.raises(Exception):
+        gpu.bilin_get_map()

@@ -35,7 +35,9 @@ def main():
         if not f.endswith(".cubin"):
             continue
         sass = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, f)], capture_output=True, text=True).stdout.split("\n")
-        want = os.environ.get("NCU_SASS_NAME", mangled)
+        # template instantiations share the substring: pick the one the report names (k_map_easy<(bool)1> -> ...ILb1...)
+        inst = re.search(r"<\(bool\)([01])>", blk["name"])
+        want = os.environ.get("NCU_SASS_NAME", mangled + ("ILb" + inst.group(1) if inst else ""))
         starts = [i for i, l in enumerate(sass) if l.startswith(".text.") and want in l and l.rstrip().endswith(":")]
         if not starts:
             continue
