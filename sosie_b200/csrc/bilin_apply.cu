@@ -101,8 +101,10 @@ k_apply1(const int4* __restrict__ pidx, const float4* __restrict__ pw, SlabView 
     if (FUSE) {
       pack_record(sg, k_ew, __ldcs(MT + k), __ldcs(MT + k + nt), __ldcs(MT + k + 2 * nt), __ldcs(AB + k), __ldcs(AB + k + nt),
                   trg_lon(tg, i + 1, j + 1), trg_lat(tg, i + 1, j + 1), id, w);
-      __stcs(pidx_out + k, id);
-      __stcs(pw_out + k, w);
+      if (pidx_out) {   // kept for the later calls (not on the very first apply of a mapping: see bilin_apply_impl)
+        __stcs(pidx_out + k, id);
+        __stcs(pw_out + k, w);
+      }
     } else {
       id = __ldcs(pidx + k);     // streamed once: do not displace the source slab in L2
       w = __ldcs(pw + k);
@@ -453,11 +455,15 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
     prof_begin(ctx, SOSIE_T_APPLY);
     if (fuse) {
       if ((size_t)ctx->sg.nx * ctx->sg.nyw > 2147483647ULL) { ctx->err = "source slab too large for 32-bit offsets"; return SOSIE_ERR_ARG; }
-      CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt));
+      // The very first single-slab apply of a mapping only uses the records (a one-slab job -- a bathymetry -- never needs
+      // them again: 32 B per target not written); a second one shows the mapping is reused and stores them on its way.
+      const bool store = ctx->unpacked_applies >= 1 || ctx->always_store_records;
+      if (store) { CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt)); }
       k_apply1<true><<<grid.x, 256, 0, ctx->stream>>>(nullptr, nullptr, v, dZ1, dZ2, po, tgm, ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p,
-                                                      ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p);
+                                                      ctx->d_ab.p, store ? ctx->d_pidx.p : nullptr, store ? ctx->d_pw.p : nullptr);
       KLAUNCH_CHECK();
-      ctx->pack_ready = true; ctx->pack_gen++; ctx->boxes_ready = false;
+      if (store) { ctx->pack_ready = true; ctx->pack_gen++; ctx->boxes_ready = false; }
+      else ctx->unpacked_applies++;
     } else {
       k_apply1<false><<<grid.x, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, v, dZ1, dZ2, po, tgm, ctx->sg, ctx->tg, ctx->k_ew, nullptr,
                                                        nullptr, nullptr, nullptr);   // nslab == 1 here

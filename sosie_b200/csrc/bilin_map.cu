@@ -1610,6 +1610,6 @@ int bilin_map_impl(sosie_ctx* ctx) {
   if (herr & 6) { ctx->err = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)"; return SOSIE_ERR_REF_STOP; }
   ctx->map_ready = !ctx->search_only;   // a search-only run leaves no mapping behind
   ctx->map_nt = nt;
-  ctx->pack_ready = false;
+  ctx->pack_ready = false; ctx->unpacked_applies = 0;
   return SOSIE_OK;
 }

@@ -97,7 +97,7 @@ static int pipelined_run(sosie_ctx* ctx, Pipe& P, int k_ew, int nx1, int ny1, co
   CK(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
 
   // ---- state of set_grids (BILIN_2D prologue, :97-171)
-  ctx->grids_set = false; ctx->map_ready = false; ctx->pack_ready = false; ctx->boxes_ready = false;
+  ctx->grids_set = false; ctx->map_ready = false; ctx->pack_ready = false; ctx->unpacked_applies = 0; ctx->boxes_ready = false;
   ctx->k_ew = k_ew; ctx->l_reg_src = l_reg_src; ctx->i_orca_trg = i_orca_trg;
   ctx->sg = SrcGeom();
   ctx->sg.nx = nx1; ctx->sg.ny = ny1; ctx->sg.separable = 1;

@@ -1,6 +1,7 @@
 // capi.cu -- extern "C" entry points declared in include/sosie_b200.h.
 // Host pointers are staged through device buffers owned by the context; _dev entries work on the
 // caller's device pointers.  No CPU compute path exists: without a CUDA device every call fails.
+#include <cstdlib>
 #include <algorithm>
 
 #include "geom.cuh"
@@ -30,6 +31,7 @@ int sosie_create(sosie_ctx** out, int device) {
   c->own_stream = true;
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->num_sms = sms;
+  c->always_store_records = getenv("SOSIE_ALWAYS_STORE_RECORDS") != nullptr;
   *out = c;
   return SOSIE_OK;
 }
@@ -84,7 +86,7 @@ int sosie_bilin_set_shard(sosie_ctx* c, int32_t j0, int32_t j1) {
   NEED(c);
   if (j0 < 0 || j1 < j0) { ctx->err = "sosie_bilin_set_shard: bad row range"; return SOSIE_ERR_ARG; }
   ctx->shard_j0 = j0; ctx->shard_j1 = j1;
-  ctx->pack_ready = false;
+  ctx->pack_ready = false; ctx->unpacked_applies = 0;
   return SOSIE_OK;
 }
 
@@ -119,7 +121,7 @@ static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_
   }
   if (int rc = bilin_prepare_src(ctx)) return rc;
   ctx->grids_set = true;
-  ctx->pack_ready = false;
+  ctx->pack_ready = false; ctx->unpacked_applies = 0;
   if (!keep_map) ctx->map_ready = false;
   return SOSIE_OK;
 }
@@ -217,7 +219,7 @@ int sosie_bilin_load_map(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32_t* 
   CK(cudaStreamSynchronize(st));
   if (!ctx->grids_set) { ctx->tg.nx = nx2; ctx->tg.ny = ny2; }
   ctx->map_ready = true;
-  ctx->pack_ready = false;
+  ctx->pack_ready = false; ctx->unpacked_applies = 0;
   for (int k = 0; k < 8; k++) ctx->map_info[k] = 0;
   ctx->map_info[5] = -1;
   return SOSIE_OK;
@@ -252,7 +254,7 @@ int sosie_bilin_load_map_dev(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32
   CK(cudaMemsetAsync(ctx->d_dnp.p, 0, nt * sizeof(float), st));
   if (!ctx->grids_set) { ctx->tg.nx = nx2; ctx->tg.ny = ny2; }
   ctx->map_ready = true;
-  ctx->pack_ready = false;
+  ctx->pack_ready = false; ctx->unpacked_applies = 0;
   for (int k = 0; k < 8; k++) ctx->map_info[k] = 0;
   ctx->map_info[5] = -1;
   return SOSIE_OK;

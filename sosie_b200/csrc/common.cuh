@@ -90,6 +90,8 @@ struct sosie_ctx {
   // ---- bilinear state
   int k_ew = -1, l_reg_src = 0, i_orca_trg = 0, l_add_extra_j = 0;
   bool grids_set = false, map_ready = false, pack_ready = false;
+  bool always_store_records = false;   // test hook (SOSIE_ALWAYS_STORE_RECORDS): the first apply stores the records too
+  int unpacked_applies = 0;      // single-slab applies served straight from the mapping arrays since it was built (see bilin_apply_impl)
   bool search_only = false;     // sosie_find_nearest_point: the search stage alone (JIp, JJp into the first two planes of d_metrics)
   size_t map_nt = 0;             // target count the cached mapping was built/loaded for
   int shard_j0 = 0, shard_j1 = 0; // 1-based inclusive target rows handled by this context (0,0 = all)

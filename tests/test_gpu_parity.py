@@ -576,3 +576,27 @@ def test_find_nearest_point_entry(gpu, orc, case):
     # the context is left without a mapping
     with pytest.raises(Exception):
         gpu.bilin_get_map()
+
+
+@pytest.mark.parametrize("name,scale", [("D", 0.08), ("B", 0.3)])
+def test_apply_sequence_after_one_mapping(gpu, orc, name, scale):
+    """One mapping, then single-slab applies one after the other (the per-record loop of sosie3.x), then a batch: the first
+    apply builds the records in registers without keeping them, the second keeps them, the third reads them, the batch
+    takes the staged kernel -- every result must be the oracle's."""
+    cfg = G.config(name, scale)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, 6, seed=23)
+    Z2o, mo = orc.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"],
+                           l_reg_src=cfg["l_reg_src"], i_orca_trg=cfg["i_orca_trg"])
+    gpu.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"],
+                        l_reg_src=cfg["l_reg_src"], i_orca_trg=cfg["i_orca_trg"])
+    gpu.bilin_map()
+    for s in range(3):
+        out = gpu.bilin_apply(Z1[s], first_call=(s == 0))
+        assert np.array_equal(out[0], Z2o[s]), f"{name}: single-slab apply #{s + 1} differs at {(out[0] != Z2o[s]).sum()} points"
+    out = gpu.bilin_apply(Z1[3:], first_call=False)
+    assert np.array_equal(out, Z2o[3:])
+    # a fresh mapping followed at once by a batch (records packed by the separate kernel)
+    gpu.bilin_map()
+    out = gpu.bilin_apply(Z1[:2], first_call=True)
+    assert np.array_equal(out, Z2o[:2])
