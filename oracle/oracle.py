@@ -293,7 +293,9 @@ def drown(k_ew, X, mask, nb_inc=200, nthreads=1):
     nslab, nj, ni = X.shape
     mask = np.ascontiguousarray(mask, np.int8)
     nsw = np.zeros(nslab, np.int32)
-    lib().orc_drown(int(k_ew), ni, nj, nslab, _p(X, C.c_float), _p(mask, C.c_int8), int(nb_inc), _p(nsw, C.c_int32), int(nthreads))
+    rc = lib().orc_drown(int(k_ew), ni, nj, nslab, _p(X, C.c_float), _p(mask, C.c_int8), int(nb_inc), _p(nsw, C.c_int32), int(nthreads))
+    if rc:
+        raise RuntimeError(f"oracle DROWN: the reference would index out of bounds (code {rc})")
     return (X[0] if sq else X), nsw
 
 

@@ -653,6 +653,9 @@ int orc_smoother(int k_ew, int ni, int nj, int nslab, float* X, int nb_smooth, c
 }
 
 int orc_drown(int k_ew, int ni, int nj, int nslab, float* X, const int8_t* mask, int nb_inc, int* nsweeps, int nthreads) {
+  // src/mod_drown.f90:110-117: the folded indices stay inside 1..ni only when ni >= 2*k_ew + 1; below that the reference
+  // reads maskv out of bounds (undefined behaviour): reported, nothing computed
+  if (k_ew >= 0 && ni < 2 * k_ew + 1) return 40;
   int64_t n = (int64_t)ni * nj;
   if (nthreads < 1) nthreads = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nthreads)

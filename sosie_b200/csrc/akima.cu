@@ -678,6 +678,9 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
   if (ctx->ak_row_hi >= ctx->ak_row_lo) { fa = std::max(1, ctx->ak_row_lo - 4); fb = std::min(nj1, ctx->ak_row_hi + 4); }
   if (fa <= 8) fa = 1;
   if (fb >= nj1 - 8) fb = nj1;
+  // an ORCA north fold builds the two top frame rows from rows nj1-5 / nj1-6 (T pivot) or nj1-4 / nj1-5 (F pivot) of the same
+  // array (src/mod_manip.f90:179-190): a range that holds the top frame must hold those rows too
+  if (fb == nj1 && (ctx->ak_iorca == 4 || ctx->ak_iorca == 6)) { fa = std::min(fa, nj1 - 6); if (fa <= 8) fa = 1; }
   const int fa8 = (fa == 1) ? 1 : fa + 2, fb8 = (fb == nj1) ? nj1 + 4 : fb + 2;   // the same rows in the (ni1+4, nj1+4) array
   const size_t nfill = (size_t)(fb8 - fa8 + 1) * (ni1 + 4);
   for (int s0 = 0; s0 < nslab; s0 += nb) {

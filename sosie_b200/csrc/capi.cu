@@ -636,6 +636,9 @@ int sosie_drown(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nsla
                 int32_t* nsweeps) {
   NEED(c);
   if (ni < 3 || nj < 3 || nslab < 1 || !X || !mask) { ctx->err = "sosie_drown: bad arguments"; return SOSIE_ERR_ARG; }
+  // the periodic index folding of src/mod_drown.f90:110-117 leaves 1..ni only when ni >= 2*k_ew + 1; below that the
+  // reference reads maskv out of bounds (undefined): refused
+  if (k_ew >= 0 && ni < 2 * k_ew + 1) { ctx->err = "sosie_drown: ni < 2*k_ew + 1 (the reference indexes out of bounds)"; return SOSIE_ERR_ARG; }
   const size_t n = (size_t)ni * nj;
   cudaStream_t st = ctx->stream;
   DBuf<float> dX; DBuf<int8_t> dM;

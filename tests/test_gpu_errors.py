@@ -41,6 +41,9 @@ def test_call_order_and_arguments():
             ctx.bilin_set_grids(0, np.zeros(2), np.zeros(2), np.zeros(4), np.zeros(4))
         with pytest.raises(sosie_b200.SosieError, match="error 2"):     # AKIMA_1D_3D needs >= 3 source levels for its frame
             ctx.akima_1d_3d(np.array([1.0, 2.0], np.float32), np.zeros((2, 3, 3), np.float32), np.array([1.5], np.float32))
+        # DROWN on a grid narrower than its periodic folding allows (src/mod_drown.f90:110-117 would index maskv out of bounds)
+        with pytest.raises(sosie_b200.SosieError, match="2\\*k_ew"):
+            ctx.drown(2, np.zeros((6, 4), np.float32), np.ones((6, 4), np.int8), 3)
     finally:
         ctx.close()
     with pytest.raises(sosie_b200.SosieError):

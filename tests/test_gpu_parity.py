@@ -600,3 +600,24 @@ def test_apply_sequence_after_one_mapping(gpu, orc, name, scale):
     gpu.bilin_map()
     out = gpu.bilin_apply(Z1[:2], first_call=True)
     assert np.array_equal(out, Z2o[:2])
+
+
+@pytest.mark.parametrize("piv,iorca,nx,ny", [("T", 4, 55, 24), ("F", 6, 62, 40), ("T", 4, 91, 66)])
+def test_akima_orca_fold_frame_under_a_polar_target(gpu, orc, piv, iorca, nx, ny):
+    """A target that only reads the top of an ORCA-shaped source: the frame rows built by the north-fold copies
+    (src/mod_manip.f90:179-190) come from rows 4-6 below the top, which the row-limited REAL(8) conversion must include
+    (found by the fuzzer: seed 32, case 2180)."""
+    lon_s, lat_s = G.orca_like(nx, ny, piv, 40.0)
+    Z1 = G.field_slabs(lon_s, lat_s, 2, seed=31)
+    t = np.linspace(0.0, 1.0, 41)
+    Xt = np.mod(360.0 * t[None, :] + np.zeros((9, 1)), 360.0)
+    Yt = np.linspace(80.0, 89.0, 9)[:, None] + np.zeros((1, 41))
+    Z2o, ixy = orc.akima_2d(2, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca)
+    for untiled in (False, True):
+        gpu.akima_untiled_slopes(untiled)
+        try:
+            Z2g = gpu.akima_2d(2, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca)
+        finally:
+            gpu.akima_untiled_slopes(False)
+        assert np.array_equal(gpu.akima_get_ixy(), ixy)
+        assert np.array_equal(Z2g, Z2o), f"{(Z2g != Z2o).sum()} of {Z2o.size} points differ"

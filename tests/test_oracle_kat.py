@@ -327,3 +327,14 @@ def test_track_interp_levels_no_time(orc):
                 assert f_bl[p, k] == np.float64(pyref.interp_bl_np(-1, i, j, int(iq[p]), xa[p], xb[p], F[k]))
             else:
                 assert f_bl[p, k] == -9999.0 and f_np[p, k] == -9999.0
+
+
+def test_drown_refuses_grids_narrower_than_the_fold(orc):
+    """src/mod_drown.f90:110-117: with ni < 2*k_ew + 1 the folded neighbour indices leave 1..ni (the reference would read
+    maskv out of bounds): the oracle reports it instead of computing something."""
+    import pytest
+    X = np.zeros((6, 4), np.float32)
+    m = np.ones((6, 4), np.int8)
+    with pytest.raises(RuntimeError):
+        orc.drown(2, X, m, 3)
+    orc.drown(2, np.zeros((6, 5), np.float32), np.ones((6, 5), np.int8), 3)   # ni = 2*k_ew + 1 is the smallest legal width
