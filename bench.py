@@ -34,6 +34,28 @@ NCU_MAP_TRAFFIC_BYTES = 1987419000   # 0.635297 GB read + 1.352122 GB written pe
 UNIT = "points/s"
 
 
+def cpu_faithful_sample(cfg, v_one, Z1_host, ntargets=6):
+    """The reference as it is written: FIND_NEAREST_EASY fills the whole (nx_s, ny_s) REAL(8) Xdist array with 1.E12 for
+    EVERY target (src/mod_manip.f90:1038; 1.87 GB per target on this source).  Timed on `ntargets` targets of one row, single
+    thread; the per-call set-up is removed by timing the same sample with the store elided.  Returns (targets/s, note)."""
+    from oracle import oracle as O
+    O.set_libm(O.GLIBC)
+    Xt, Yt = G.trg_2d(cfg)
+    j = cfg["nyt"] // 2
+    ii = np.unique(np.linspace(0, cfg["nxt"] - 1, ntargets).round().astype(int))
+    Xs_ = np.ascontiguousarray(Xt[j:j + 1, ii]); Ys_ = np.ascontiguousarray(Yt[j:j + 1, ii])
+    dt = {}
+    for elide in (True, False):
+        t0 = time.perf_counter()
+        O.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1_host, Xs_, Ys_, l_reg_src=cfg["l_reg_src"],
+                   i_orca_trg=0, elide_fill=elide, nthreads=1, virtual_src=cfg["src_1d"])
+        dt[elide] = time.perf_counter() - t0
+    n = Xs_.size
+    per_target = max(dt[False] - dt[True], 0.0) / n + 1.0 / v_one
+    return 1.0 / per_target, (f"{n} targets of one row, single thread: {dt[False]:.1f} s with the per-target 1.E12 fill of the whole "
+                              f"source-sized array, {dt[True]:.1f} s without (set-up); per-target difference + the elided per-target time")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -675,6 +697,12 @@ def run_ours(args):
                           "oracle port of the reference, glibc libm, dead 1.E12 store elided, coordinate copies elided",
                 "single_thread_value": v_one, "single_thread_sample": f"4 rows ({n_one} targets, {dt_one:.1f} s)",
             }
+            try:   # single thread, faithful (dead store included) -- extrapolated from a handful of targets
+                v_f, note_f = cpu_faithful_sample(cfg, v_one, Z1_host.numpy())
+                line["cpu_baseline"]["single_thread_faithful_value"] = v_f
+                line["cpu_baseline"]["single_thread_faithful_sample"] = note_f
+            except MemoryError:
+                line["cpu_baseline"]["single_thread_faithful_value"] = None
         if not args.no_others:
             line["others"] = bench_others(ctx, torch, dev, hbm_peak, quick=args.quick)
     if rank == 0:
