@@ -367,7 +367,7 @@ struct Best {
 };
 #define PDS_MARGIN 1.0e-13
 #ifndef MAP_MIN_BLOCKS
-#define MAP_MIN_BLOCKS 6
+#define MAP_MIN_BLOCKS 8
 #endif
 template <bool SEP>
 static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,

@@ -74,7 +74,7 @@ def test_config_E_full(gpu, orc):
     mg = gpu.bilin_get_map()
     assert mg["info"][5] == 0 and mg["info"][7] == 1          # EASY search, pole rows added
     _properties(cfg, mg, rng)
-    _sample_rows_vs_oracle(gpu, orc, cfg, mg, Z1[None], Z2, 5)
+    _sample_rows_vs_oracle(gpu, orc, cfg, mg, Z1[None], Z2, 32)
     _linear_field_reproduced(gpu, cfg, mg, 0.37, -1.3, 11.0)
     # sharded mapping (multi-GPU path) on this one device: rows 1000..1499 only, identical to the unsharded rows
     gpu.bilin_set_shard(1000, 1499)
