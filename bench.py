@@ -71,7 +71,7 @@ class ClockSampler:
     thread of rank 0 only: one `nvidia-smi -lms` poller per rank takes the driver lock often enough to stretch the
     launch / sync latencies of a 2 ms step (measured: 8 pollers cost 0.7 ms per step at N = 8)."""
 
-    def __init__(self, index=0, period=0.02):
+    def __init__(self, index=0, period=0.004):
         self.index, self.period = index, period
         self.sm, self.reasons, self.mx = [], set(), None
         self._stop = threading.Event()
@@ -115,7 +115,7 @@ class ClockSampler:
         self._stop.set()
         self.t.join(timeout=2)
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "source": "NVML, sampled every 20 ms on rank 0 during the timed region"}
+                "samples": len(self.sm), "source": "NVML, sampled every 4 ms on rank 0 during the timed region"}
 
 
 # ------------------------------------------------------------------------------------------------
