@@ -30,7 +30,7 @@ sys.path.insert(0, ROOT)
 from sosie_b200 import grids as G  # noqa: E402
 
 METRIC = "target points interpolated/sec (mapping + apply)"
-NCU_MAP_TRAFFIC_BYTES = 1987419000   # 0.635297 GB read + 1.352122 GB written per full-size launch (profiles/r01_ncu_E.md)
+NCU_MAP_TRAFFIC_BYTES = 1993270000   # 0.637099 GB read + 1.356171 GB written per full-size launch (profiles/r01_ncu_E.md)
 UNIT = "points/s"
 
 
@@ -658,6 +658,11 @@ def run_ours(args):
             "note": "the search is fp64-transcendental/latency bound, not HBM bound (SURVEY 8d): judged by targets/s and L2 hit rate; "
                     "the HBM-bound kernels (apply, drown) are listed under 'kernels' and 'others'",
         }
+        if world == 1 and args.scale == 1.0:
+            # what bounds it, from the same ncu --set full capture as `traffic` (profiles/r01_ncu_E.md; constants, not live)
+            roofline["ncu"] = {"file": "profiles/r01_ncu_E.md", "issue_active_pct": 64.3, "fp64_pipe_pct": 41.7, "l2_hit_pct": 63.8,
+                               "l1_hit_pct": 78.8, "warps_active_pct": 44.6, "registers": 64,
+                               "warp_instructions_per_32_targets": 1959, "dram_throughput_pct": 7.3}
         t_app = float(np.mean(kapp))
         # first apply of a fresh mapping, one slab: the records are built inside the apply kernel (k_apply1<fused pack>): mapping
         # arrays (28 B) + target coordinates (16 B) in, records (32 B) + field (4 B) out, plus the slab
