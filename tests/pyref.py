@@ -898,3 +898,199 @@ def ground_track_loop_np(fields, vt_mod, imask, vtf, metrics, ab, F_gt_f, rmissv
     mod[Fmask == 0] = rmissval; mod_np[Fmask == 0] = rmissval; obs[Fmask == 0] = rmissval
     mod[mod < f8(f4(-9990.0))] = rmissval
     return mod, mod_np, obs, Fmask
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FIND_NEAREST_POINT prelude (src/mod_manip.f90:884-947), IS_POLAR_PROJ (:1843-1879) and FIND_NEAREST_TWISTED (:1073-1440):
+# a second, independent transcription of the search on curvilinear sources (written from the Fortran text with numpy
+# array syntax / Python loops, glibc libm through `math`).  Arrays are Fortran-shaped [i, j], 0-based inside, indices
+# returned 1-based.  Undefined behaviour of the reference is DEFINED as SURVEY Appendix A says (Q3: ji_s = jj_s = 0 before
+# the first luck window; Q4: J_VLAT_S(nsplit+1,1) aliases J_VLAT_S(1,2); Q5: an out-of-range probe means "not polar").
+def l_is_grid_regular(Xlon, Xlat):
+    nx, ny = Xlon.shape
+    for jj in range(1, ny):
+        s = 0.0
+        for v in np.abs(Xlon[:, jj] - Xlon[:, 0]):      # SUM() in index order
+            s += float(v)
+        if s > float(F32(1.0e-12)):
+            return False
+    for ji in range(nx):
+        s = 0.0
+        for v in np.abs(Xlat[ji, :] - Xlat[0, :]):
+            s += float(v)
+        if s > float(F32(1.0e-12)):
+            return False
+    return True
+
+
+def _minloc_dim2(Y, mask, largest=False):
+    """MINLOC / MAXLOC(Y, mask=mask, dim=2): per row index i, the 1-based first j of the extreme value, 0 if the mask is empty"""
+    nx, ny = Y.shape
+    out = np.zeros(nx, np.int64)
+    for i in range(nx):
+        best = None
+        for j in range(ny):
+            if not mask[i, j]:
+                continue
+            if best is None or (Y[i, j] > best if largest else Y[i, j] < best):
+                best, out[i] = Y[i, j], j + 1
+    return out
+
+
+def find_nearest_prelude(Xtrg, Ytrg, Xsrc, Ysrc):
+    """(l_is_reg_s, l_is_reg_t, j_strt_t, j_stop_t, jlat_icr), :884-947"""
+    nx_t, ny_t = Xtrg.shape
+    reg_s, reg_t = l_is_grid_regular(Xsrc, Ysrc), l_is_grid_regular(Xtrg, Ytrg)
+    y_min_s, y_max_s = Ysrc.min(), Ysrc.max()
+    j_strt, j_stop, icr = 1, ny_t, 1
+    rmin = float(F32(-100.0))
+    if nx_t > 2:
+        z = np.zeros((nx_t, ny_t))
+        z[:, 1:] = Ytrg[:, 1:] - Ytrg[:, :-1]
+        rtmp = 0.0
+        for v in z[:, ny_t // 2 - 1]:                    # SUM(ztmp_t(:,ny_t/2)), index order
+            rtmp += float(v)
+        z = math.copysign(1.0, rtmp) * z
+        rmin = z[:, 1:].min()
+    if rmin > float(F32(-1.0e-12)) or reg_t:
+        i1 = _minloc_dim2(Ytrg, Ytrg >= y_min_s)
+        j_strt = int(i1[i1 > 0].min())
+        j_stop = int(_minloc_dim2(Ytrg, Ytrg <= y_max_s, largest=True).max())
+        if j_strt > j_stop:
+            icr = -1
+    return reg_s, reg_t, j_strt, j_stop, icr
+
+
+def is_polar_proj(XX, YY):
+    nx, ny = YY.shape
+    if not (YY > 88.0).any():
+        return False
+    d = np.abs(YY - 90.0)
+    k = int(np.argmin(d.T.reshape(-1)))                  # MINLOC: first minimum in column-major (i fastest) order
+    jNP, iNP = k // nx, k % nx                           # 0-based
+    if jNP - 3 < 0 or jNP + 3 > ny - 1:
+        return False                                     # Q5
+    lipp = (YY[iNP, jNP - 3] < YY[iNP, jNP]) and (YY[iNP, jNP + 3] < YY[iNP, jNP])
+    if lipp:
+        a = abs(XX[iNP, jNP - 3] - XX[iNP, jNP + 3])
+        lipp = (a > 100.0) and (a < 220.0)
+    return bool(lipp)
+
+
+def _distance_block(rlon, rlat, Xs, Ys, i1, i2, j1, j2):
+    """DISTANCE_2D (:1509-1573) on the section (i1:i2, j1:j2) (1-based, inclusive): array [i2-i1+1, j2-j1+1]"""
+    zconv = math.acos(-1.0) / 180.0
+    zlatar, zlonar = rlat * zconv, rlon * zconv
+    zux, zuy, zuz = math.cos(zlonar) * math.cos(zlatar), math.sin(zlonar) * math.cos(zlatar), math.sin(zlatar)
+    out = np.empty((i2 - i1 + 1, j2 - j1 + 1))
+    for jj in range(j1 - 1, j2):
+        for ji in range(i1 - 1, i2):
+            zlatbr, zlonbr = Ys[ji, jj] * zconv, Xs[ji, jj] * zconv
+            zvx, zvy, zvz = math.cos(zlonbr) * math.cos(zlatbr), math.sin(zlonbr) * math.cos(zlatbr), math.sin(zlatbr)
+            zpds = zux * zvx + zuy * zvy + zuz * zvz
+            out[ji - i1 + 1, jj - j1 + 1] = ZR * math.acos(min(zpds, 1.0))
+    return out
+
+
+def find_nearest_twisted(Xtrg, Ytrg, Xsrc, Ysrc, mask_t, j_strt_t, j_stop_t, jlat_icr):
+    """returns (JIpos, JJpos, mask_t) Fortran-shaped, or raises RuntimeError where the reference STOPs"""
+    nx_s, ny_s = Xsrc.shape
+    nx_t, ny_t = Xtrg.shape
+    mask_t = mask_t.copy()
+    y_min_s, y_max_s, y_min_t, y_max_t = Ysrc.min(), Ysrc.max(), Ytrg.min(), Ytrg.max()
+    if (y_min_t >= y_max_s) or (y_max_t <= y_min_s):
+        raise RuntimeError("Target and source latitudes do not overlap!")
+    JI = np.full((nx_t, ny_t), -1, np.int32)
+    JJ = np.full((nx_t, ny_t), -1, np.int32)
+    e1 = np.full((nx_s, ny_s), float(F32(40000.0)))
+    e2 = np.full((nx_s, ny_s), float(F32(40000.0)))
+    th = float(F32(1000.0))
+    for jj in range(ny_s):
+        for ji in range(nx_s - 1):
+            e1[ji, jj] = distance(Xsrc[ji, jj], Xsrc[ji + 1, jj], Ysrc[ji, jj], Ysrc[ji + 1, jj]) * th
+    for jj in range(ny_s - 1):
+        for ji in range(nx_s):
+            e2[ji, jj] = distance(Xsrc[ji, jj], Xsrc[ji, jj + 1], Ysrc[ji, jj], Ysrc[ji, jj + 1]) * th
+    if nx_s > 1:
+        e1[nx_s - 1, :] = e1[nx_s - 2, :]
+    if ny_s > 1:
+        e2[:, ny_s - 1] = e2[:, ny_s - 2]
+    lStupido = is_polar_proj(Xsrc, Ysrc) or is_polar_proj(Xtrg, Ytrg)
+    nsplit = 0
+    if not lStupido:
+        y_max_bnd = y_max_bnd0 = min(y_max_t, y_max_s)
+        y_min_bnd = y_min_bnd0 = max(y_min_t, y_min_s)
+        y_max_bnd = min(float(int(y_max_bnd + 2.0)), 90.0)               # INT() truncates toward zero
+        y_min_bnd = max(float(int(y_min_bnd - 2.0)), -90.0)
+        nint = lambda x: int(math.floor(abs(x) + 0.5)) * (1 if x >= 0 else -1)   # NINT: half away from zero
+        y_max_bnd = min(nint(y_max_bnd / 0.5) * 0.5, 90.0)
+        y_min_bnd = max(nint(y_min_bnd / 0.5) * 0.5, -90.0)
+        y_max_bnd = max(y_max_bnd, y_max_bnd0)
+        y_min_bnd = min(y_min_bnd, y_min_bnd0)
+        nsplit = max(int(float(F32(40.0)) * (y_max_bnd - y_min_bnd) / 180.0), 1)
+        dy = (y_max_bnd - y_min_bnd) / float(F32(nsplit))
+        VB = [y_min_bnd + float(F32(jl)) * dy for jl in range(nsplit + 1)]
+        if (y_min_bnd > y_min_bnd0) or (y_max_bnd < y_max_bnd0):
+            raise RuntimeError("Bounds for latitude for VLAT_SPLIT_BOUNDS are bad!")
+        JV = np.zeros((nsplit, 2), np.int64)
+        for jl in range(nsplit):
+            rlat_1, rlat_2 = VB[jl], VB[jl + 1]
+            jmax_band = int(_minloc_dim2(Ysrc, Ysrc <= rlat_2, largest=True).max())
+            i1dum = _minloc_dim2(Ysrc, Ysrc > rlat_1)
+            jmin_band = int(i1dum[i1dum > 0].min())
+            JV[jl, 0] = max(jmin_band - 1, 1)
+            JV[jl, 1] = min(jmax_band + 1, ny_s)
+        for jl in range(nsplit):
+            if JV[jl, 1] <= JV[jl, 0]:
+                raise RuntimeError("jj_stop > jj_start !")
+        JVflat = JV.T.reshape(-1)                                         # column-major storage of J_VLAT_S(nsplit,2)
+    frac_emax, sqrt2 = float(F32(0.51)), float(np.sqrt(F32(2.0)))
+    rlat_old = float(F32(-9999.0))
+    ji_s = jj_s = 0                                                       # Q3
+    jlat = 1
+    for jj_t in range(j_strt_t, j_stop_t + (1 if jlat_icr > 0 else -1), jlat_icr):
+        for ji_t in range(1, nx_t + 1):
+            if mask_t[ji_t - 1, jj_t - 1] != 1:
+                continue
+            rlon, rlat = Xtrg[ji_t - 1, jj_t - 1], Ytrg[ji_t - 1, jj_t - 1]
+            if not lStupido and rlat != rlat_old:
+                jlat = nsplit + 1                                         # value of the DO variable when the loop runs out
+                for jl in range(1, nsplit + 1):
+                    if rlat == VB[jl - 1] or (rlat > VB[jl - 1] and rlat <= VB[jl]):
+                        jlat = jl
+                        break
+            lagain, niter = True, -1
+            if rlat > 60.0:
+                niter = 0
+            while lagain:
+                if niter == -1:
+                    i1s, i2s = max(ji_s - 5, 1), min(ji_s + 5, nx_s)
+                    j1s, j2s = max(jj_s - 5, 1), min(jj_s + 5, ny_s)
+                else:
+                    i1s, i2s = 1, nx_s
+                    if lStupido:
+                        j1s, j2s = 1, ny_s
+                    else:
+                        j1s = int(JVflat[max(jlat - niter, 1) - 1])       # J_VLAT_S(.,1); (nsplit+1,1) aliases (1,2): Q4
+                        j2s = int(JVflat[nsplit + min(jlat + niter, nsplit) - 1])
+                D = _distance_block(rlon, rlat, Xsrc, Ysrc, i1s, i2s, j1s, j2s)
+                k = int(np.argmin(D.T.reshape(-1)))                       # MINLOC of the section, column-major first minimum
+                ni_blk = i2s - i1s + 1
+                ji_s, jj_s = k % ni_blk + i1s, k // ni_blk + j1s
+                emax = max(e1[ji_s - 1, jj_s - 1], e2[ji_s - 1, jj_s - 1]) / th * sqrt2
+                if D[ji_s - i1s, jj_s - j1s] <= frac_emax * emax:
+                    lagain = False
+                    JI[ji_t - 1, jj_t - 1], JJ[ji_t - 1, jj_t - 1] = ji_s, jj_s
+                else:
+                    if niter == 0:
+                        mlon = (Xsrc > max(rlon - 0.5, 0.0)) & (Xsrc < min(rlon + 0.5, 360.0))
+                        mlat = (Ysrc > max(rlat - 0.5, -90.0)) & (Ysrc < min(rlat + 0.5, 90.0))
+                        if (mlon & mlat).sum() == 0:
+                            lagain = False
+                    if niter > nsplit // 3:
+                        lagain = False
+                niter += 1
+            rlat_old = rlat
+    mask_t[JI == -1] = -1
+    mask_t[JJ == -1] = -2
+    return JI, JJ, mask_t

@@ -338,3 +338,55 @@ def test_drown_refuses_grids_narrower_than_the_fold(orc):
     with pytest.raises(RuntimeError):
         orc.drown(2, X, m, 3)
     orc.drown(2, np.zeros((6, 5), np.float32), np.ones((6, 5), np.int8), 3)   # ni = 2*k_ew + 1 is the smallest legal width
+
+
+@pytest.mark.parametrize("case", ["B_small", "C_small", "track", "regional_target", "masked", "polar_target"])
+def test_twisted_search_vs_second_transcription(orc, case):
+    """FIND_NEAREST_POINT on curvilinear sources (prelude + IS_POLAR_PROJ + FIND_NEAREST_TWISTED, src/mod_manip.f90:884-947,
+    1073-1440, 1843-1879): the C++ oracle against the independent Python transcription in tests/pyref.py, both on glibc's
+    libm -- JIp, JJp, the search mask and the target row range must agree exactly."""
+    rng = np.random.default_rng(5)
+    mask = None
+    if case == "B_small":
+        cfg = G.config("B", 0.12)
+        Xs, Ys = G.src_2d(cfg); Xt, Yt = G.trg_2d(cfg)
+    elif case == "C_small":
+        cfg = G.config("C", 0.2)
+        Xs, Ys = G.src_2d(cfg); Xt, Yt = G.trg_2d(cfg)
+    else:
+        Xs, Ys = G.orca_like(48, 36, "F", 30.0)
+        if case == "track":          # (1, N) target: nx_t = 1, no row-range logic
+            n = 160
+            t = np.linspace(0.0, 1.0, n)
+            Xt = np.mod(10.0 + 340.0 * t, 360.0).reshape(n, 1)
+            Yt = (70.0 * np.sin(9.0 * t)).reshape(n, 1)
+        elif case == "polar_target":      # a polar-stereographic target with the pole inside: IS_POLAR_PROJ -> the full scan (lStupido)
+            xx, yy = np.meshgrid(np.linspace(-1.0, 1.0, 15), np.linspace(-1.0, 1.0, 15))
+            Yt = 90.0 - 28.0 * np.hypot(xx, yy)
+            Xt = np.mod(np.degrees(np.arctan2(xx, -yy)), 360.0)
+        elif case == "regional_target":   # rows south of the source and a tilted grid (latitudes not monotone along j everywhere)
+            u, v = np.meshgrid(np.linspace(0, 1, 23), np.linspace(0, 1, 17))
+            Xt = np.mod(200.0 + 60.0 * u + 8.0 * v, 360.0)
+            Yt = -85.0 + 120.0 * v + 6.0 * u
+        else:
+            Xt, Yt = np.meshgrid(np.linspace(3.0, 357.0, 31), np.linspace(-70.0, 80.0, 19))
+            Xt = Xt + 0.3 * np.sin(Yt)    # irregular target
+            mask = (rng.random(Xt.shape) > 0.25).astype(np.int32)
+    orc.set_libm(orc.GLIBC)
+    try:
+        JIo, JJo, mo, used, info = orc.find_nearest_point(Xt, Yt, Xs, Ys, mask=mask)
+        assert orc.get_error() == 0
+    finally:
+        orc.set_libm(orc.PMATH)
+    XsF, YsF, XtF, YtF = P.to_f(Xs), P.to_f(Ys), P.to_f(Xt), P.to_f(Yt)
+    reg_s, reg_t, j_strt, j_stop, icr = P.find_nearest_prelude(XtF, YtF, XsF, YsF)
+    assert not reg_s
+    assert (j_strt, j_stop, icr, int(reg_s), int(reg_t)) == tuple(int(v) for v in info[:5])
+    m0 = np.ones(XtF.shape, np.int32) if mask is None else P.to_f(mask).astype(np.int32)
+    JI, JJ, m = P.find_nearest_twisted(XtF, YtF, XsF, YsF, m0, j_strt, j_stop, icr)
+    assert np.array_equal(P.from_f(JI), JIo), f"{case}: JIp differs at {(P.from_f(JI) != JIo).sum()} targets"
+    assert np.array_equal(P.from_f(JJ), JJo)
+    assert np.array_equal(P.from_f(m), mo)
+    assert (JIo > 0).mean() > 0.3
+    if case == "polar_target":
+        assert P.is_polar_proj(XtF, YtF) and not P.is_polar_proj(XsF, YsF)
