@@ -1094,3 +1094,149 @@ def find_nearest_twisted(Xtrg, Ytrg, Xsrc, Ysrc, mask_t, j_strt_t, j_stop_t, jla
     mask_t[JI == -1] = -1
     mask_t[JJ == -1] = -2
     return JI, JJ, mask_t
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# AKIMA_2D (src/mod_akima_2d.f90:59-239) with SLOPES_AKIMA (:483-664), build_pol (:249-441), pol_val (:445-480) and
+# find_nearest_akima (:670-745): second transcription, whole-array numpy for the slopes and the 16 coefficients of every
+# cell (the reference's own data flow -- the oracle and the GPU rebuild the coefficients per target instead), Python
+# loops for the index walk.  No libm: IEEE + - * / only, so the comparison with the oracle is exact in either libm mode.
+def _guard(rx):
+    return np.copysign(1.0, rx) * np.maximum(np.abs(rx), REPS)
+
+
+def slopes_akima(k_ew, XX, XY, XF):
+    nx, ny = XF.shape
+    ZX, ZY, ZF = fill_extra_bands(k_ew, XX, XY, XF)
+    I = lambda o: slice(o, o + nx)       # ji + o (0-based o: ji -> 0, ip1 -> 1, ip2 -> 2, ji+3 -> 3, ji+4 -> 4)
+    J = lambda o: slice(o, o + ny)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        def dq(A, Z, ia, ja, ib, jb):    # (Z(b) - Z(a)) / guard(A(b) - A(a))
+            return (Z[I(ib), J(jb)] - Z[I(ia), J(ja)]) / _guard(A[I(ib), J(jb)] - A[I(ia), J(ja)])
+        m1, m2, m3, m4 = dq(ZX, ZF, 0, 2, 1, 2), dq(ZX, ZF, 1, 2, 2, 2), dq(ZX, ZF, 2, 2, 3, 2), dq(ZX, ZF, 3, 2, 4, 2)
+        eqx = (m1 == m2) & (m3 == m4)
+        Wx2 = np.where(eqx, 0.0, np.abs(m4 - m3)); Wx3 = np.where(eqx, 0.0, np.abs(m2 - m1))
+        dFdX = np.where(eqx, 0.5 * (m2 + m3), (Wx2 * m2 + Wx3 * m3) / (Wx2 + Wx3))
+        m1, m2, m3, m4 = dq(ZY, ZF, 2, 0, 2, 1), dq(ZY, ZF, 2, 1, 2, 2), dq(ZY, ZF, 2, 2, 2, 3), dq(ZY, ZF, 2, 3, 2, 4)
+        eqy = (m1 == m2) & (m3 == m4)
+        Wy2 = np.where(eqy, 0.0, np.abs(m4 - m3)); Wy3 = np.where(eqy, 0.0, np.abs(m2 - m1))
+        dFdY = np.where(eqy, 0.5 * (m2 + m3), (Wy2 * m2 + Wy3 * m3) / (Wy2 + Wy3))
+        # cross derivative: m2, m3 are now the y-direction quotients (the scalars were overwritten, :570-577)
+        d22, d23 = dq(ZY, ZF, 1, 1, 1, 2), dq(ZY, ZF, 1, 2, 1, 3)
+        d42, d43 = dq(ZY, ZF, 3, 1, 3, 2), dq(ZY, ZF, 3, 2, 3, 3)
+        e22 = (m2 - d22) / _guard(ZX[I(2), J(1)] - ZX[I(1), J(1)])
+        e23 = (m3 - d23) / _guard(ZX[I(2), J(2)] - ZX[I(1), J(2)])
+        e32 = (d42 - m2) / _guard(ZX[I(3), J(2)] - ZX[I(2), J(2)])
+        e33 = (d43 - m3) / _guard(ZX[I(3), J(2)] - ZX[I(2), J(2)])
+        zx = (Wx2 == 0) & (Wx3 == 0)
+        zy = (Wy2 == 0) & (Wy3 == 0)
+        Wx2 = np.where(zx, 1.0, Wx2); Wx3 = np.where(zx, 1.0, Wx3)
+        Wy2 = np.where(zy, 1.0, Wy2); Wy3 = np.where(zy, 1.0, Wy3)
+        d2 = (Wx2 * (Wy2 * e22 + Wy3 * e23) + Wx3 * (Wy2 * e32 + Wy3 * e33)) / ((Wx2 + Wx3) * (Wy2 + Wy3))
+    return dFdX, dFdY, d2
+
+
+def build_pol(ZX, ZY, ZF, sx, sy, sxy):
+    """XPLNM(nx-1, ny-1, 16) for every cell, array syntax"""
+    a = (slice(0, -1), slice(0, -1)); b = (slice(1, None), slice(0, -1)); c = (slice(1, None), slice(1, None)); d = (slice(0, -1), slice(1, None))
+    x = ZX[b] - ZX[a]
+    y = ZY[d] - ZY[a]
+    x2 = x * x; x3 = x2 * x
+    y2 = y * y; y3 = y2 * y
+    xy = x * y
+    b1, b2, b3, b4 = ZF[a], ZF[b], ZF[c], ZF[d]
+    b5, b6, b7, b8 = sx[a], sx[b], sx[c], sx[d]
+    b9, b10, b11, b12 = sy[a], sy[b], sy[c], sy[d]
+    b13, b14, b15, b16 = sxy[a], sxy[b], sxy[c], sxy[d]
+    V = np.zeros(x.shape + (16,))
+    V[..., 10], V[..., 11], V[..., 14], V[..., 15] = b13, b5, b9, b1
+    b5, b6, b7, b8 = x * b5, x * b6, x * b7, x * b8
+    b9, b10, b11, b12 = y * b9, y * b10, y * b11, y * b12
+    b13, b14, b15, b16 = xy * b13, xy * b14, xy * b15, xy * b16
+    c1, c2, c3 = b1 - b2, b3 - b4, b5 + b6
+    c4, c5, c6 = b7 + b8, b9 - b10, b11 - b12
+    c7, c8, c9 = b13 + b14, b15 + b16, 2 * b5 + b6
+    c10, c11, c12 = b7 + 2 * b8, 2 * b13 + b14, b15 + 2 * b16
+    c13, c14, c15 = b5 - b8, b1 - b4, b13 + b16
+    c16, c17, c18 = 2 * b13 + b16, b9 + b12, 2 * b9 + b12
+    d1, d2, d3 = c1 + c2, c3 - c4, c5 - c6
+    d4, d5, d6 = c7 + c8, c9 - c10, 2 * c5 - c6
+    d7, d8, d9 = 2 * c7 + c8, c11 + c12, 2 * c11 + c12
+    f1, f2, f3 = 2 * d1 + d2, 2 * d3 + d4, 2 * d6 + d7
+    f4, f5, f6 = 3 * d1 + d5, 3 * d3 + d8, 3 * d6 + d9
+    with np.errstate(divide="ignore", invalid="ignore"):
+        V[..., 0] = (2 * f1 + f2) / (x3 * y3); V[..., 1] = (-(3 * f1 + f3)) / (x3 * y2); V[..., 2] = (2 * c5 + c7) / (x3 * y)
+        V[..., 3] = (2 * c1 + c3) / x3; V[..., 4] = (-(2 * f4 + f5)) / (x2 * y3); V[..., 5] = (3 * f4 + f6) / (x2 * y2)
+        V[..., 6] = (-(3 * c5 + c11)) / (x2 * y); V[..., 7] = (-(3 * c1 + c9)) / x2; V[..., 8] = (2 * c13 + c15) / (x * y3)
+        V[..., 9] = (-(3 * c13 + c16)) / (x * y2); V[..., 12] = (2 * c14 + c17) / y3; V[..., 13] = (-(3 * c14 + c18)) / y2
+    return V
+
+
+def pol_val(x, y, V):
+    p1 = ((V[0] * y + V[1]) * y + V[2]) * y + V[3]
+    p2 = ((V[4] * y + V[5]) * y + V[6]) * y + V[7]
+    p3 = ((V[8] * y + V[9]) * y + V[10]) * y + V[11]
+    p4 = ((V[12] * y + V[13]) * y + V[14]) * y + V[15]
+    return ((p1 * x + p2) * x + p3) * x + p4
+
+
+def find_nearest_akima(plon, plat, rng4, X2, Y2):
+    nxs, nys = plon.shape
+    nxt, nyt = X2.shape
+    ixy = np.zeros((nxt, nyt, 2), np.int32)
+    for jjt in range(nyt):
+        for jit in range(nxt):
+            pxt, pyt = X2[jit, jjt], Y2[jit, jjt]
+            if not ((pxt >= rng4[0]) and (pxt <= rng4[1]) and (pyt >= rng4[2]) and (pyt <= rng4[3])):
+                continue
+            jis = jjs = 1
+            lx = ly = False
+            while not (lx and ly):
+                lx = False
+                while not lx:
+                    if jis < nxs:
+                        if plon[jis - 1, jjs - 1] <= pxt and plon[jis, jjs - 1] > pxt:
+                            lx = True
+                        else:
+                            jis += 1
+                    else:
+                        jis -= 1
+                        lx = True
+                ly = False
+                while not ly:
+                    if jjs < nys:
+                        if plat[jis - 1, jjs - 1] <= pyt and plat[jis - 1, jjs] > pyt:
+                            ly = True
+                        else:
+                            jjs += 1
+                            lx = False
+                            ly = True
+                    else:
+                        jjs = nys - 1
+                        ly = True
+            ixy[jit, jjt, :] = (jis, jjs)
+    return ixy
+
+
+def akima_2d(k_ew_per, X1, Y1, Z1, X2, Y2):
+    """one slab, 2-D Fortran-shaped arrays, i_orca_src = 0; returns (Z2 REAL(4), ixy_pos)"""
+    zXs, zYs, zFs = fill_extra_bands(k_ew_per, X1, Y1, Z1.astype(np.float64))
+    kewp = k_ew_per + 4 if k_ew_per > -1 else -1
+    slpx, slpy, slpxy = slopes_akima(kewp, zXs, zYs, zFs)
+    poly = build_pol(zXs, zYs, zFs, slpx, slpy, slpxy)
+    rng4 = (zXs.min(), zXs.max(), zYs.min(), zYs.max())
+    ixy = find_nearest_akima(zXs, zYs, rng4, X2, Y2)
+    nx2, ny2 = X2.shape
+    Z2 = np.zeros((nx2, ny2), F32)
+    for jj2 in range(ny2):
+        for ji2 in range(nx2):
+            px2, py2 = X2[ji2, jj2], Y2[ji2, jj2]
+            if (px2 >= rng4[0]) and (px2 <= rng4[1]) and (py2 >= rng4[2]) and (py2 <= rng4[3]):
+                ji1, jj1 = ixy[ji2, jj2]
+                px2 = px2 - zXs[ji1 - 1, jj1 - 1]
+                py2 = py2 - zYs[ji1 - 1, jj1 - 1]
+                with np.errstate(all="ignore"):
+                    Z2[ji2, jj2] = F32(pol_val(px2, py2, poly[ji1 - 1, jj1 - 1, :]))
+            else:
+                Z2[ji2, jj2] = 0.0
+    return Z2, ixy

@@ -390,3 +390,46 @@ def test_twisted_search_vs_second_transcription(orc, case):
     assert (JIo > 0).mean() > 0.3
     if case == "polar_target":
         assert P.is_polar_proj(XtF, YtF) and not P.is_polar_proj(XsF, YsF)
+
+
+@pytest.mark.parametrize("kind,kew", [("cell", 0), ("regional", -1), ("overlap", 2)])
+def test_akima_2d_vs_second_transcription(orc, kind, kew):
+    """AKIMA_2D end to end (frame, SLOPES_AKIMA, the 16 coefficients of build_pol for EVERY cell as the reference stores them,
+    find_nearest_akima's walk, pol_val, the REAL(4) cast, 0 outside the source): the C++ oracle -- which rebuilds the
+    coefficients per target -- against the whole-array numpy transcription in tests/pyref.py, bit for bit.  The field has
+    flat and linear patches so that the equal-slope branch (:558-564) and the zero-weight fallback (:638-647) are taken."""
+    rng = np.random.default_rng(11)
+    if kind == "cell":
+        lon = (np.arange(36) + 0.5) * 10.0; lat = -85.0 + np.arange(18) * 10.0
+    elif kind == "regional":
+        lon = 20.0 + 0.7 * np.arange(30); lat = -12.0 + 0.9 * np.arange(22)
+    else:
+        lon = np.arange(38) * (360.0 / 36.0); lat = np.linspace(-70.0, 80.0, 21)     # 2 overlap columns: lon(37) = 360, lon(38) = 370
+    X, Y = G.expand_2d(lon, lat)
+    F = (10.0 * np.cos(np.deg2rad(3 * X)) * np.sin(np.deg2rad(2 * Y)) + rng.normal(0.0, 0.5, X.shape)).astype(np.float32)
+    F[5:12, 8:20] = 3.25                              # flat patch: all divided differences equal
+    F[13:, :10] = (0.5 * X[13:, :10] - 0.25 * Y[13:, :10]).astype(np.float32)    # linear patch
+    if kind == "overlap":
+        F[:, -2:] = F[:, :2]
+    tl = np.sort(rng.uniform(lon.min() - 3.0, lon.max() + 3.0, 41)); tt = np.sort(rng.uniform(lat.min() - 3.0, lat.max() + 3.0, 33))
+    tl[:6] = lon[rng.integers(0, lon.size, 6)]; tl.sort()      # targets exactly on source nodes (half-open cell tests)
+    tt[:5] = lat[rng.integers(0, lat.size, 5)]; tt.sort()
+    TX, TY = G.expand_2d(tl, tt)
+    TX = TX + 0.05 * np.sin(TY)                       # 2-D target arrays
+    Z2o, ixo = orc.akima_2d(kew, X, Y, F, TX, TY)
+    Z2p, ixp = P.akima_2d(kew, P.to_f(X), P.to_f(Y), P.to_f(F), P.to_f(TX), P.to_f(TY))
+    assert np.array_equal(ixo[0], P.from_f(ixp[:, :, 0])) and np.array_equal(ixo[1], P.from_f(ixp[:, :, 1]))
+    Z2p = P.from_f(Z2p)
+    assert np.array_equal(np.isnan(Z2o[0]), np.isnan(Z2p))
+    ok = ~np.isnan(Z2p)
+    assert np.array_equal(Z2o[0][ok], Z2p[ok]), f"{(Z2o[0][ok] != Z2p[ok]).sum()} of {ok.sum()} differ, max {np.abs(Z2o[0][ok] - Z2p[ok]).max()}"
+    assert (ixo[0] > 0).mean() > 0.7
+    if kind == "regional":
+        assert (Z2p == 0).any()       # targets beyond the 2-cell frame: 0.0 (:222-224)
+    # the slopes alone, on the frame-extended arrays
+    a = orc.fill_extra_bands(kew, X, Y, F.astype(np.float64))
+    so = orc.slopes_akima(kew + 4 if kew > -1 else -1, *a)
+    sp = P.slopes_akima(kew + 4 if kew > -1 else -1, *(P.to_f(v) for v in a))
+    for u, v in zip(so, sp):
+        v = P.from_f(v)
+        assert np.array_equal(np.isnan(u), np.isnan(v)) and np.array_equal(u[~np.isnan(u)], v[~np.isnan(v)])
