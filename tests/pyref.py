@@ -1240,3 +1240,116 @@ def akima_2d(k_ew_per, X1, Y1, Z1, X2, Y2):
             else:
                 Z2[ji2, jj2] = 0.0
     return Z2, ixy
+
+
+def mapping_point_2d(k_ew, Xs, Ys, xP, yP, iP, jP):
+    """One target of MAPPING_BL (src/mod_bilin_2d.f90:459-634) on a curvilinear source given by Fortran-shaped 2-D arrays
+    Xs, Ys [i, j]; (iP, jP) 1-based nearest point.  Returns (iqdrn, alpha, beta, ipb) or None where the reference skips
+    the target (:468, :487-493)."""
+    nxi, nyi = Xs.shape
+    if not (jP < nyi):
+        return None
+    iPm1, iPp1, jPm1, jPp1 = iP - 1, iP + 1, jP - 1, jP + 1
+    if iPm1 == 0 and k_ew >= 0:
+        iPm1 = nxi - k_ew
+    if iPp1 == nxi + 1 and k_ew >= 0:
+        iPp1 = 1 + k_ew
+    if iPm1 < 1 or jPm1 < 1 or iPp1 > nxi:
+        return None
+    X = lambda i, j: math.fmod(Xs[i - 1, j - 1], 360.0)   # noqa: E731
+    Y = lambda i, j: float(Ys[i - 1, j - 1])              # noqa: E731
+    lonP, latP = X(iP, jP), Y(iP, jP)
+    lonN, latN, lonE, latE = X(iP, jPp1), Y(iP, jPp1), X(iPp1, jP), Y(iPp1, jP)
+    lonS, latS, lonW, latW = X(iP, jPm1), Y(iP, jPm1), X(iPm1, jP), Y(iPm1, jP)
+    xP = math.fmod(xP, 360.0)
+    hP = heading(lonP, xP, latP, yP)
+    hN, hE = heading(lonP, lonN, latP, latN), heading(lonP, lonE, latP, latE)
+    hS, hW = heading(lonP, lonS, latP, latS), heading(lonP, lonW, latP, latW)
+    iq = 4
+    hPp = degE_to_degWE(hP)
+    if hN > hE:
+        hN -= 360.0
+    if hPp > hN and hPp <= hE:
+        iq = 1
+    if hP > hE and hP <= hS:
+        iq = 2
+    if hP > hS and hP <= hW:
+        iq = 3
+    if hP > hW and hPp <= hN:
+        iq = 4
+    icpt = 0
+    while True:
+        if iq == 1:
+            quad = [(lonE, latE), (X(iPp1, jPp1), Y(iPp1, jPp1)), (lonN, latN)]
+        elif iq == 2:
+            quad = [(lonS, latS), (X(iPp1, jPm1), Y(iPp1, jPm1)), (lonE, latE)]
+        elif iq == 3:
+            quad = [(lonW, latW), (X(iPm1, jPm1), Y(iPm1, jPm1)), (lonS, latS)]
+        elif iq == 4:
+            quad = [(lonN, latN), (X(iPm1, jPp1), Y(iPm1, jPp1)), (lonW, latW)]
+        loni = [xP, lonP] + [q[0] for q in quad]
+        lati = [yP, latP] + [q[1] for q in quad]
+        loni = [v + 360.0 if v <= 0.0 else v for v in loni]
+        ok = l_inpoly(loni[1:], lati[1:], xP, yP)
+        if (not ok) and yP < 88.0:
+            icpt += 1
+            iq = icpt
+        else:
+            break
+        if icpt == 5:
+            iq = 0
+            break
+    a, b, ipb = local_coord(loni, lati)
+    return iq, a, b, ipb
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DROWN (src/mod_drown.f90:18-198), REAL(4) arithmetic spelled out; X, mask are (ni, nj) [i, j]
+def drown(k_ew, X, mask, ninc_max):
+    X = (X.astype(F32) * mask.astype(F32)).astype(F32)       # X = X * mask (:70)
+    ni, nj = X.shape
+    maskv = mask.astype(np.int64).copy()
+    nsweeps = 0
+
+    def fold(i):
+        if k_ew >= 0:
+            if i > ni - k_ew:
+                i = i - ni + 2 * k_ew
+            if i < 1 + k_ew:
+                i = i + ni - 2 * k_ew
+        return i
+    for jinc in range(1, ninc_max + 1):
+        if not (maskv == 0).any():
+            break
+        nsweeps += 1
+        coast = np.zeros((ni, nj), np.int64)
+        for jj in range(1, nj + 1):
+            for ji in range(1, ni + 1):
+                jjp1, jjm1 = min(jj + 1, nj), max(jj - 1, 1)
+                ji0, jip1, jim1 = ji, ji + 1, ji - 1
+                if k_ew >= 0:
+                    ji0, jip1, jim1 = fold(ji0), fold(jip1), fold(jim1)
+                else:
+                    jip1, jim1 = min(jip1, ni), max(jim1, 1)
+                s = maskv[jim1 - 1, jj - 1] + maskv[jip1 - 1, jj - 1] + maskv[ji0 - 1, jjm1 - 1] + maskv[ji0 - 1, jjp1 - 1]
+                coast[ji - 1, jj - 1] = min(s, 1) * (1 - maskv[ji0 - 1, jj - 1])
+        ns = min(jinc, 50)
+        xtmp = X.copy()
+        for jj in range(1, nj + 1):
+            for ji in range(1, ni + 1):
+                if coast[ji - 1, jj - 1] != 1:
+                    continue
+                summsk = datmsk = F32(0.0)
+                for jjm in range(-ns, ns + 1):
+                    for jim in range(-ns, ns + 1):
+                        jic, jjc = fold(ji + jim), jj + jjm
+                        if 1 <= jic <= ni and 1 <= jjc <= nj:
+                            arg = F32(F32(-1.0) * F32(jjm ** 2 + jim ** 2)) / F32(jinc ** 2)     # REAL(4) division
+                            zweight = F32(F32(math.exp(float(arg))) * F32(maskv[jic - 1, jjc - 1]))
+                            summsk = F32(summsk + zweight)
+                            datmsk = F32(datmsk + F32(zweight * X[jic - 1, jjc - 1]))
+                with np.errstate(all="ignore"):
+                    xtmp[ji - 1, jj - 1] = F32(datmsk / summsk)
+        X = xtmp
+        maskv = maskv + coast
+    return X, nsweeps

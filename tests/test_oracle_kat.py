@@ -433,3 +433,63 @@ def test_akima_2d_vs_second_transcription(orc, kind, kew):
     for u, v in zip(so, sp):
         v = P.from_f(v)
         assert np.array_equal(np.isnan(u), np.isnan(v)) and np.array_equal(u[~np.isnan(u)], v[~np.isnan(v)])
+
+
+@pytest.mark.parametrize("piv", ["F", "T"])
+def test_mapping_bl_on_curvilinear_source_vs_transliteration(orc, piv):
+    """MAPPING_BL on an ORCA-shaped source (TWISTED search, 2-D neighbour lookups, periodic wrap of iP-1 / iP+1, the
+    quadrant retry loop, LOCAL_COORD, the whole-array fix-ups): C++ oracle against the per-target Python transliteration,
+    both on glibc's libm (heading = TAN / LOG / ATAN2 decides the first-guess quadrant)."""
+    Xs, Ys = G.orca_like(54, 40, piv, 25.0)
+    Xt, Yt = G.expand_2d(np.linspace(1.5, 358.5, 40), np.linspace(-76.0, 87.0, 31))
+    orc.set_libm(orc.GLIBC)
+    try:
+        m = orc.mapping_bl(2, Xs, Ys, Xt, Yt)
+        assert orc.get_error() == 0
+    finally:
+        orc.set_libm(orc.PMATH)
+    met, ab, ipb = m["metrics"], m["alphabeta"], m["ipb"]
+    XsF, YsF = P.to_f(Xs), P.to_f(Ys)
+    eps = float(np.float32(1e-9))
+    ncmp, quads = 0, set()
+    for j in range(Xt.shape[0]):
+        for i in range(Xt.shape[1]):
+            iP, jP = int(met[0, j, i]), int(met[1, j, i])
+            if iP < 1:
+                assert ipb[j, i] in (-1, -2)         # not found by the search (:681-682)
+                continue
+            r = P.mapping_point_2d(2, XsF, YsF, Xt[j, i], Yt[j, i], iP, jP)
+            if r is None:
+                assert met[2, j, i] == 1 and ipb[j, i] == 1 and ab[0, j, i] == 0.0 and ab[1, j, i] == 0.0
+                continue
+            iq, a, b, ip = r
+            if a < 0 and a > -eps: a = 0.0
+            if b < 0 and b > -eps: b = 0.0
+            if a < 0: a, ip = 0.5, 4
+            if a > 1: a, ip = 0.5, 5
+            if b < 0: b, ip = 0.5, 6
+            if b > 1: b, ip = 0.5, 7
+            if iq < 1: iq, ip = 1, 1
+            assert (int(met[2, j, i]), ab[0, j, i], ab[1, j, i], int(ipb[j, i])) == (iq, a, b, ip), (i, j, iP, jP)
+            ncmp += 1
+            quads.add(iq)
+    assert ncmp > 0.7 * Xt.size and quads == {1, 2, 3, 4}
+
+
+@pytest.mark.parametrize("kew", [-1, 0, 2])
+def test_drown_gaussian_vs_transliteration(orc, kew):
+    """DROWN (src/mod_drown.f90): coastline by the four folded neighbours, Gaussian box mean with REAL(4) sums in loop order,
+    weights EXP(-r2/jinc**2) in REAL(4): C++ oracle against Python loops, bit for bit, sweep counts included."""
+    rng = np.random.default_rng(8 + kew)
+    ni, nj = 15, 11
+    X = (rng.random((nj, ni)) * 10 + 1).astype(np.float32)
+    yy, xx = np.mgrid[0:nj, 0:ni]
+    mask = ((np.sin(xx * 0.9) * np.cos(yy * 0.7) < 0.35) | (rng.random((nj, ni)) < 0.15)).astype(np.int8)
+    mask[2:9, 4:11] = 0                                   # a land mass several sweeps deep
+    for ninc in (1, 3, 7):
+        Xo, nsw = orc.drown(kew, X, mask, ninc)
+        Xp, nsp = P.drown(kew, P.to_f(X), P.to_f(mask), ninc)
+        Xp = P.from_f(Xp)
+        assert int(nsw[0]) == nsp
+        assert np.array_equal(np.isnan(Xo), np.isnan(Xp)) and np.array_equal(Xo[~np.isnan(Xo)], Xp[~np.isnan(Xp)]), (kew, ninc)
+    assert nsp >= 3
