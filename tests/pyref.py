@@ -1353,3 +1353,49 @@ def drown(k_ew, X, mask, ninc_max):
         X = xtmp
         maskv = maskv + coast
     return X, nsweeps
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BILIN_2D after the mapping is known (src/mod_bilin_2d.f90:209-263): the apply loop with the identical-point copy, the
+# identity "masking" statement, the last-row test and the ORCA north-fold patch of the last target row.  Arrays (nj, ni).
+def bilin_2d_apply(k_ew, X1w, Y1w, Z1w, X2, Y2, metrics, ab, i_orca_trg, first_call=True):
+    f4 = np.float32
+    ny2, nx2 = X2.shape
+    rmv = f4(-9999.0)
+    Z2 = np.full((ny2, nx2), rmv, f4)
+    IM = np.maximum(metrics[:2], 1)
+    eps5 = float(f4(1.0e-5))
+    for jj in range(ny2):
+        for ji in range(nx2):
+            iP, jP, iq = int(IM[0, jj, ji]), int(IM[1, jj, ji]), int(metrics[2, jj, ji])
+            if abs(degE_to_degWE(X1w[jP - 1, iP - 1]) - degE_to_degWE(X2[jj, ji])) < eps5 and abs(Y1w[jP - 1, iP - 1] - Y2[jj, ji]) < eps5:
+                Z2[jj, ji] = Z1w[jP - 1, iP - 1]
+            else:
+                Z2[jj, ji] = interp_bl_np(k_ew, iP, jP, iq, ab[0, jj, ji], ab[1, jj, ji], Z1w)
+    Z2 = (Z2 * f4(1.0) + f4(0.0) * f4(-9995.0)).astype(f4)         # mask_ignore_trg was reset to 1 (:212): Q7
+    missing = False
+    if first_call and i_orca_trg >= 4:
+        s = f4(0.0)
+        for v in Z2[ny2 - 1, :]:
+            s = f4(s + v)
+        rmeanv = f4(s / f4(nx2))
+        missing = bool((rmeanv < f4(rmv + f4(0.1))) and (rmeanv > f4(rmv - f4(0.1))))
+    if missing:
+        F = Z2.T                                                    # [i, j] view, 0-based
+        if i_orca_trg == 4:
+            nA, nB = nx2 // 2 - 1, nx2 // 2 + 3                     # extents of the two left-hand sections (the LHS governs)
+            rhs = [F[nx2 - 1 - k, ny2 - 3] for k in range(nA)]
+            for k in range(nA):
+                F[1 + k, ny2 - 1] = rhs[k]
+            rhs = [F[1 + k, ny2 - 3] for k in range(nB)]
+            for k in range(nB):
+                F[nx2 - 1 - k, ny2 - 1] = rhs[k]
+        if i_orca_trg == 6:
+            nA = nx2 // 2 - 1
+            rhs = [F[nx2 - 2 - k, ny2 - 2] for k in range(nA)]
+            for k in range(nA):
+                F[1 + k, ny2 - 1] = rhs[k]
+            rhs = [F[1 + k, ny2 - 2] for k in range(nA)]
+            for k in range(nA):
+                F[nx2 - 2 - k, ny2 - 1] = rhs[k]
+    return Z2, missing

@@ -493,3 +493,27 @@ def test_drown_gaussian_vs_transliteration(orc, kew):
         assert int(nsw[0]) == nsp
         assert np.array_equal(np.isnan(Xo), np.isnan(Xp)) and np.array_equal(Xo[~np.isnan(Xo)], Xp[~np.isnan(Xp)]), (kew, ninc)
     assert nsp >= 3
+
+
+@pytest.mark.parametrize("piv,iorca,mask_last_row", [("T", 4, True), ("F", 6, True), ("T", 4, False), ("F", 0, True)])
+def test_bilin_2d_apply_and_north_fold_patch_vs_transliteration(orc, piv, iorca, mask_last_row):
+    """BILIN_2D after the mapping (src/mod_bilin_2d.f90:209-263): index clamp, identical-point copy, INTERP_BL, the last-row
+    test (REAL(4) mean within 0.1 of rmv) and the north-fold patch of the last target row (T and F pivots; the T-pivot
+    sections do not conform: the left-hand extent governs).  The last target row is masked out of the mapping so that it
+    receives Z1w(1,1) = -9999 and the patch fires; with the row left in, or i_orca_trg = 0, it must not."""
+    Xs, Ys = G.orca_like(44, 32, "F", 10.0)
+    Xt, Yt = G.orca_like(52, 38, piv, 10.0)
+    Xt[3, 5], Yt[3, 5] = Xs[4, 7], Ys[4, 7]               # a target ON a source node: the identical-point copy
+    Z1 = G.field_slabs(Xs, Ys, 1, seed=12)
+    Z1[0, 0, 0] = -9999.0                                 # Z1w(1,1): what clamped (not searched / not found) targets receive
+    mask = np.ones(Xt.shape, np.int32)
+    if mask_last_row:
+        mask[-1, :] = 0
+    Z2o, mo = orc.bilin_2d(2, Xs, Ys, Z1, Xt, Yt, mask_domain_trg=mask, l_reg_src=False, i_orca_trg=iorca)
+    Z2p, missing = P.bilin_2d_apply(2, Xs, Ys, Z1[0], Xt, Yt, mo["metrics"], mo["alphabeta"], iorca)
+    assert missing == (mask_last_row and iorca >= 4)
+    assert bool(mo["l_last_y_row_missing"]) == missing
+    assert np.array_equal(Z2o[0], Z2p), f"{(Z2o[0] != Z2p).sum()} points differ"
+    assert Z2p[3, 5] == Z1[0, 4, 7]
+    if missing:
+        assert (Z2p[-1, 1:-1] != np.float32(-9999.0)).mean() > 0.5      # the patched row holds copies of row ny-2 / ny-1
