@@ -517,3 +517,22 @@ def test_bilin_2d_apply_and_north_fold_patch_vs_transliteration(orc, piv, iorca,
     assert Z2p[3, 5] == Z1[0, 4, 7]
     if missing:
         assert (Z2p[-1, 1:-1] != np.float32(-9999.0)).mean() > 0.5      # the patched row holds copies of row ny-2 / ny-1
+
+
+def test_bilin_2d_regular_source_with_pole_rows_vs_transliteration(orc):
+    """BILIN_2D on a regular, cell-centred global source: the two rows of EXT_NORTH_TO_90_REGG are appended
+    (src/mod_bilin_2d.f90:119-171) and targets north of the last source latitude interpolate in them.  The oracle's
+    fields against the apply transliteration fed with the extended working arrays."""
+    lon, lat = G.regular_latlon(48, 24)                   # top latitude 86.25: 2*ymx - y(ny-1) >= 90
+    X, Y = G.expand_2d(lon, lat)
+    Z1 = G.field_slabs(X, Y, 1, seed=13)
+    tl = np.linspace(2.0, 358.0, 37); tt = np.linspace(60.0, 89.5, 25)
+    tl[5], tt[3] = lon[9], lat[20]                        # one target on a source node
+    Xt, Yt = G.expand_2d(tl, tt)
+    Z2o, mo = orc.bilin_2d(0, lon, lat, Z1, tl, tt, l_reg_src=True)
+    assert mo["info"][4] == 1 or mo["metrics"][1].max() > 24        # the search saw the extended grid
+    X1w, Y1w, Z1w = orc.ext_north_to_90_regg(X, Y, Z1[0])
+    Z2p, _ = P.bilin_2d_apply(0, X1w, Y1w, Z1w, Xt, Yt, mo["metrics"], mo["alphabeta"], 0)
+    assert np.array_equal(Z2o[0], Z2p), f"{(Z2o[0] != Z2p).sum()} points differ"
+    assert (mo["metrics"][1] >= 24).any()                 # some targets have their nearest point on the last real row or the pole row
+    assert Z2p[3, 5] == Z1[0, 20, 9]
