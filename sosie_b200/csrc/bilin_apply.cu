@@ -79,9 +79,10 @@ struct PostOps {
 // One slab (the first call of a 2-D job, the per-record call of the unchanged driver loop): nothing to amortise the
 // record over, so the kernel is a latency chain record -> 4 gathers -> store.  A lean body (no slab unrolling: half the
 // registers of a slab-unrolled body) keeps every SM at full occupancy to cover it.
-// FUSE: the first apply after a mapping was built (no packed records yet) builds the record of each target from the
-// mapping arrays right here, stores it for the later calls and uses it from registers: one pass instead of k_pack
-// (mapping in, records out) followed by a second one that reads the records back.
+// FUSE: a single-slab apply that finds no packed records yet builds the record of each target from the mapping arrays
+// right here and uses it from registers: one pass instead of k_pack (mapping in, records out) followed by a second one
+// that reads the records back.  pidx_out / pw_out non-null: the records are also stored for the later calls (the second
+// such apply of a mapping; the very first one does not store them -- see bilin_apply_impl).
 #ifndef APPLY1_FUSE_BLOCKS
 #define APPLY1_FUSE_BLOCKS 8
 #endif
