@@ -13,12 +13,13 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
 
-@pytest.mark.parametrize("seed", [11, 12])
-def test_fuzz_parity(gpu, orc, seed):
+@pytest.mark.parametrize("seed,ncases", [(11, 160), (12, 160), (41, 600), (42, 600), (43, 600)])
+def test_fuzz_parity(gpu, orc, seed, ncases):
+    """the first `ncases` cases of `python tools/fuzz_parity.py N seed` (same sub-seeds): 500 cases take ~3 s on the box"""
     import fuzz_parity as F
     rng = np.random.default_rng(seed)
     fails, done, stops = [], 0, 0
-    for k in range(160):
+    for k in range(ncases):
         sub = np.random.default_rng(rng.integers(1 << 62))
         fn = F.CASES[k % len(F.CASES)]
         try:
@@ -32,4 +33,4 @@ def test_fuzz_parity(gpu, orc, seed):
     gpu.akima_untiled_slopes(False)
     gpu.l_first_call_interp_routine = True
     assert not fails, fails[:5]
-    assert done > 140 and stops < done // 4, (done, stops)
+    assert done > 0.85 * ncases and stops < done // 4, (done, stops)
