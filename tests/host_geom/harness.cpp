@@ -18,4 +18,5 @@ int h_l_inpoly_rect(double xa, double xb, double ya, double yb, int pattern_a, d
 }
 double h_heading(double lona, double lonb, double lata, double latb) { return d_heading_y(lona, lonb, d_merc(lata), d_merc(latb)); }
 double h_degE_to_degWE(double x) { return d_degE_to_degWE(x); }
+void h_local_coord(const double* xlam, const double* xphi, double* xa, double* xb, int* ipb) { d_local_coord(xlam, xphi, *xa, *xb, *ipb); }
 }

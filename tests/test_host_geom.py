@@ -29,6 +29,8 @@ def hg(tmp_path_factory):
     lib.h_heading.restype = C.c_double
     lib.h_degE_to_degWE.argtypes = [C.c_double]
     lib.h_degE_to_degWE.restype = C.c_double
+    lib.h_local_coord.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                  C.POINTER(C.c_int)]
     return lib
 
 
@@ -132,3 +134,39 @@ def test_first_guess_quadrant_sign_rule(hg):
     for la in (-60.0, 0.0, 33.3, 88.0):
         assert hg.h_heading(10.0, 10.25, la, la) == 90.0 and hg.h_heading(10.0, 9.75, la, la) == 270.0
         assert hg.h_heading(10.0, 10.0, la, la + 0.25) == 0.0 and hg.h_heading(10.0, 10.0, la, la - 0.25) == 180.0
+
+
+def test_local_coord_without_sqrt_equals_literal(hg, orc):
+    """the kernel's LOCAL_COORD decides "zres > zresmax" on the squared step (no SQRT) and skips the
+    divides whose numerator is zero; the oracle's LOCAL_COORD is the literal statement sequence (src/mod_bilin_2d.f90:
+    697-799).  Same (alpha, beta, ipb), bit for bit, on random cells: rectangles of a regular grid, skewed quads, cells
+    across the 0/360 seam (the -180..180 re-framing), collapsed cells (ipb = 12) and targets far outside (ipb = 11 / big steps)."""
+    rng = np.random.default_rng(99)
+    n = 200000
+    xl = (C.c_double * 5)(); xp = (C.c_double * 5)()
+    a, b, ip = C.c_double(), C.c_double(), C.c_int()
+    seen = set()
+    for k in range(n):
+        kind = k % 5
+        lon0 = rng.uniform(0.0, 360.0) if kind != 2 else rng.choice([359.99, 0.004, 359.5])
+        lat0 = rng.uniform(-85.0, 85.0)
+        dx, dy = rng.choice([1.0 / 60.0, 0.25, 1.0, 2.5]), rng.choice([1.0 / 60.0, 0.25, 1.0, 2.5])
+        sx, sy = rng.choice([-1.0, 1.0]), rng.choice([-1.0, 1.0])
+        corners = [(0, 0), (sx * dx, 0), (sx * dx, sy * dy), (0, sy * dy)]
+        if kind == 1:      # skewed
+            corners = [(cx + rng.normal(0, 0.15) * dx, cy + rng.normal(0, 0.15) * dy) for cx, cy in corners]
+        if kind == 3:      # all four latitudes equal
+            corners = [(cx, 0.0) for cx, cy in corners]
+        t, u = rng.uniform(-0.2, 1.2, 2) if kind != 4 else rng.uniform(-40.0, 40.0, 2)
+        px = lon0 + t * sx * dx; py = lat0 + u * sy * dy
+        lons = [px] + [lon0 + cx for cx, _ in corners]
+        lats = [py] + [lat0 + cy for _, cy in corners]
+        lons = [v % 360.0 for v in lons]
+        lons = [v + 360.0 if v <= 0.0 else v for v in lons]
+        xl[:] = lons; xp[:] = lats
+        hg.h_local_coord(xl, xp, C.byref(a), C.byref(b), C.byref(ip))
+        ao, bo, ipo = orc.local_coord(np.array(lons), np.array(lats))
+        same = (a.value == ao or (a.value != a.value and ao != ao)) and (b.value == bo or (b.value != b.value and bo != bo))
+        assert same and ip.value == ipo, (k, lons, lats, a.value, ao, b.value, bo, ip.value, ipo)
+        seen.add(ipo)
+    assert {0, 12} <= seen
