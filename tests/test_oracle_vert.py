@@ -214,3 +214,27 @@ def test_interp3d_sigma_vs_python_transliteration(orc, src_sigma, trg_sigma, lmo
     if lmout:   # land columns are left alone
         land = mask[0] != 1
         assert np.array_equal(a[:, land], prev[:, land])
+
+
+@pytest.mark.parametrize("top,btm,icr", [(33, 6, 1), (0, 4, 1), (37, 0, 1), (8, 31, -1), (0, 0, 1), (40, 1, 1), (2, 39, -1)])
+def test_extrp_hl_vs_python_loops(orc, top, btm, icr):
+    """extrp_hl (src/mod_interp.f90:521-542): persistence beyond jj_ex_top / jj_ex_btm, the DO bounds with their integer
+    divisions written out as in the source (nlat_icr_trg = +1 or -1), rows updated in loop order."""
+    rng = np.random.default_rng(4)
+    X = rng.normal(size=(2, 40, 25)).astype(np.float32)
+    nj = X.shape[1]
+    fdiv = lambda a, b: int(a / b)                        # Fortran integer division truncates toward zero
+
+    def do_range(a, b, s):                                # DO jj = a, b, s
+        n = max((b - a + s) // s, 0) if s > 0 else max((a - b - s) // (-s), 0)
+        return [a + k * s for k in range(n)]
+    R = X.copy()
+    for s in range(X.shape[0]):
+        F = R[s].T                                        # [i, j] view, 0-based
+        if top > 0:
+            for jj in do_range(top, fdiv(icr + 1, 2) * nj + fdiv(1 - icr, 2), icr):
+                F[:, jj - 1] = F[:, top - icr - 1]
+        if btm > 0:
+            for jj in do_range(fdiv(icr + 1, 2) + fdiv(1 - icr, 2) * nj, btm, icr):
+                F[:, jj - 1] = F[:, btm + icr - 1]
+    assert np.array_equal(orc.extrp_hl(X, top, btm, icr), R)
