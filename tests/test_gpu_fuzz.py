@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 
 
-@pytest.mark.parametrize("seed,ncases", [(11, 160), (12, 160), (41, 600), (42, 600), (43, 600)])
+@pytest.mark.parametrize("seed,ncases", [(11, 160), (12, 160)])
 def test_fuzz_parity(gpu, orc, seed, ncases):
     """the first `ncases` cases of `python tools/fuzz_parity.py N seed` (same sub-seeds): 500 cases take ~3 s on the box"""
     import fuzz_parity as F
