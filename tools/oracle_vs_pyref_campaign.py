@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Random campaigns of the C++ oracle against the independent Python / numpy transcriptions of tests/pyref.py (CPU only):
+
+    python tools/oracle_vs_pyref_campaign.py twisted SEED SECONDS     # FIND_NEAREST_POINT on ORCA-shaped sources
+    python tools/oracle_vs_pyref_campaign.py akima   SEED SECONDS     # AKIMA_2D on regular sources
+
+Test infrastructure: nothing here is part of the product."""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+os.environ["FUZZ_ORACLE_ONLY"] = "1"
+import numpy as np
+
+from oracle import oracle as orc
+from sosie_b200 import grids as G
+from tests import pyref as P
+import fuzz_parity as F
+
+
+def twisted(seed, seconds):
+    rng=np.random.default_rng(seed)
+    t0=time.time(); n=0; bad=0
+    while time.time()-t0 < seconds:
+        piv=str(rng.choice(["F","T"]))
+        Xs,Ys=G.orca_like(int(rng.integers(24,60)),int(rng.integers(24,44)),piv,float(rng.uniform(0,200)))
+        Xt,Yt=F.rnd_target(rng,Xs,Ys)
+        if np.ndim(Xt)==1:
+            Xt,Yt=G.expand_2d(Xt,Yt)
+        if Xt.size>1500: continue
+        mask=None
+        if rng.random()<0.3: mask=(rng.random(Xt.shape)>0.2).astype(np.int32)
+        orc.set_libm(orc.GLIBC)
+        try:
+            JIo,JJo,mo,used,info=orc.find_nearest_point(Xt,Yt,Xs,Ys,mask=mask)
+            err=orc.get_error()
+        finally:
+            orc.set_libm(orc.PMATH)
+        XsF,YsF,XtF,YtF=P.to_f(Xs),P.to_f(Ys),P.to_f(Xt),P.to_f(Yt)
+        try:
+            reg_s,reg_t,js,je,icr=P.find_nearest_prelude(XtF,YtF,XsF,YsF)
+            if reg_s: continue
+            m0=np.ones(XtF.shape,np.int32) if mask is None else P.to_f(mask).astype(np.int32)
+            if js<1 or je<1 or js>XtF.shape[1] or je>XtF.shape[1]:
+                perr=True
+            else:
+                JI,JJ,m=P.find_nearest_twisted(XtF,YtF,XsF,YsF,m0,js,je,icr); perr=False
+        except RuntimeError as e:
+            perr=True
+        n+=1
+        if perr or err:
+            if bool(perr)!=bool(err):
+                bad+=1; print("STOP mismatch", perr, err, Xs.shape, Xt.shape, flush=True)
+            continue
+        ok=(tuple(int(v) for v in info[:3])==(js,je,icr)) and np.array_equal(P.from_f(JI),JIo) and np.array_equal(P.from_f(JJ),JJo) and np.array_equal(P.from_f(m),mo)
+        if not ok:
+            bad+=1; print("MISMATCH", Xs.shape, Xt.shape, info, (js,je,icr), (P.from_f(JI)!=JIo).sum(), flush=True)
+    print("cases",n,"bad",bad)
+
+
+def akima(seed, seconds):
+    rng=np.random.default_rng(seed)
+    t0=time.time(); n=0; bad=0
+    while time.time()-t0 < seconds:
+        lon_s,lat_s,kew=F.rnd_regular_axes(rng)
+        if lon_s.size<6 or lat_s.size<6 or np.any(np.diff(lon_s)<=0): continue
+        X2,Y2=G.expand_2d(lon_s,lat_s)
+        Xt,Yt=F.rnd_target(rng,X2,Y2)
+        if np.ndim(Xt)==1: Xt,Yt=G.expand_2d(Xt,Yt)
+        if Xt.size>1200: continue
+        Z1=G.field_slabs(X2,Y2,1,seed=int(rng.integers(1<<30)))
+        if rng.random()<0.3: Z1[0,2:6,3:9]=1.5
+        with np.errstate(all="ignore"):
+            Z2o,ixo=orc.akima_2d(kew,X2,Y2,Z1,Xt,Yt)
+            Z2p,ixp=P.akima_2d(kew,P.to_f(X2),P.to_f(Y2),P.to_f(Z1[0]),P.to_f(Xt),P.to_f(Yt))
+        Z2p=P.from_f(Z2p); n+=1
+        ok=np.array_equal(ixo[0],P.from_f(ixp[:,:,0])) and np.array_equal(ixo[1],P.from_f(ixp[:,:,1])) and np.array_equal(np.isnan(Z2o[0]),np.isnan(Z2p)) and np.array_equal(Z2o[0][~np.isnan(Z2p)],Z2p[~np.isnan(Z2p)])
+        if not ok:
+            bad+=1; print("MISMATCH",X2.shape,Xt.shape,kew,(Z2o[0]!=Z2p).sum(),flush=True)
+    print("cases",n,"bad",bad)
+
+
+if __name__ == "__main__":
+    orc.build()
+    orc.set_libm(orc.PMATH)
+    {"twisted": twisted, "akima": akima}[sys.argv[1]](int(sys.argv[2]), float(sys.argv[3]))
