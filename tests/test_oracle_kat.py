@@ -121,9 +121,9 @@ def test_easy_search_and_mapping_vs_transliteration(orc):
             eps = float(np.float32(1e-9))
             if a < 0 and a > -eps: a = 0.0
             if b < 0 and b > -eps: b = 0.0
-            if a < 0: a, ip = 0.5, 4
+            if a > -9999.0 and a < 0: a, ip = 0.5, 4       # (ZAB > rmv) .AND. (ZAB < 0.)  (:657)
             if a > 1: a, ip = 0.5, 5
-            if b < 0: b, ip = 0.5, 6
+            if b > -9999.0 and b < 0: b, ip = 0.5, 6
             if b > 1: b, ip = 0.5, 7
             if iq < 1: iq, ip = 1, 1
             assert (met[2, j, i], ab[0, j, i], ab[1, j, i], ipb[j, i]) == (iq, a, b, ip), (i, j)
@@ -465,9 +465,9 @@ def test_mapping_bl_on_curvilinear_source_vs_transliteration(orc, piv):
             iq, a, b, ip = r
             if a < 0 and a > -eps: a = 0.0
             if b < 0 and b > -eps: b = 0.0
-            if a < 0: a, ip = 0.5, 4
+            if a > -9999.0 and a < 0: a, ip = 0.5, 4       # (ZAB > rmv) .AND. (ZAB < 0.)  (:657)
             if a > 1: a, ip = 0.5, 5
-            if b < 0: b, ip = 0.5, 6
+            if b > -9999.0 and b < 0: b, ip = 0.5, 6
             if b > 1: b, ip = 0.5, 7
             if iq < 1: iq, ip = 1, 1
             assert (int(met[2, j, i]), ab[0, j, i], ab[1, j, i], int(ipb[j, i])) == (iq, a, b, ip), (i, j, iP, jP)

@@ -3,6 +3,7 @@
 
     python tools/oracle_vs_pyref_campaign.py twisted SEED SECONDS     # FIND_NEAREST_POINT on ORCA-shaped sources
     python tools/oracle_vs_pyref_campaign.py akima   SEED SECONDS     # AKIMA_2D on regular sources
+    python tools/oracle_vs_pyref_campaign.py mapping SEED SECONDS     # MAPPING_BL (search by the oracle, body per target) on both source kinds
 
 Test infrastructure: nothing here is part of the product."""
 import os
@@ -82,7 +83,63 @@ def akima(seed, seconds):
     print("cases",n,"bad",bad)
 
 
+def mapping(seed, seconds):
+    rng=np.random.default_rng(seed)
+    t0=time.time(); n=0; bad=0; npts=0
+    eps=float(np.float32(1e-9))
+    while time.time()-t0 < seconds:
+        curv = rng.random()<0.5
+        if curv:
+            Xs,Ys=G.orca_like(int(rng.integers(24,50)),int(rng.integers(24,40)),str(rng.choice(["F","T"])),float(rng.uniform(0,200))); kew=2
+        else:
+            lon_s,lat_s,kew=F.rnd_regular_axes(rng)
+            if lon_s.size<6 or lat_s.size<6: continue
+            Xs,Ys=G.expand_2d(lon_s,lat_s)
+        Xt,Yt=F.rnd_target(rng,Xs,Ys)
+        if np.ndim(Xt)==1: Xt,Yt=G.expand_2d(Xt,Yt)
+        if Xt.size>400: continue
+        if not curv and rng.random()<0.5:   # snap some targets onto source nodes / grid lines
+            k=rng.integers(0,Xt.size,8); Xt.flat[k]=Xs.flat[rng.integers(0,Xs.size,8)] % 360.0
+            k=rng.integers(0,Xt.size,8); Yt.flat[k]=np.clip(Ys.flat[rng.integers(0,Ys.size,8)],-89.9,89.9)
+        orc.set_libm(orc.GLIBC)
+        try:
+            m=orc.mapping_bl(kew,Xs,Ys,Xt,Yt); err=orc.get_error()
+        finally:
+            orc.set_libm(orc.PMATH)
+        if err: continue
+        met,ab,ipb=m["metrics"],m["alphabeta"],m["ipb"]
+        XsF,YsF=P.to_f(Xs),P.to_f(Ys)
+        n+=1
+        for j in range(Xt.shape[0]):
+            for i in range(Xt.shape[1]):
+                iP,jP=int(met[0,j,i]),int(met[1,j,i])
+                if iP<1: continue
+                try:
+                    r=P.mapping_point_2d(kew,XsF,YsF,Xt[j,i],Yt[j,i],iP,jP)
+                except Exception as e:
+                    r="EXC"
+                if r=="EXC": continue
+                if r is None:
+                    ok = met[2,j,i]==1 and ipb[j,i]==1 and ab[0,j,i]==0.0 and ab[1,j,i]==0.0
+                else:
+                    iq,a,b,ip=r
+                    if a<0 and a>-eps: a=0.0
+                    if b<0 and b>-eps: b=0.0
+                    if a>-9999.0 and a<0: a,ip=0.5,4
+                    if a>1: a,ip=0.5,5
+                    if b>-9999.0 and b<0: b,ip=0.5,6
+                    if b>1: b,ip=0.5,7
+                    if iq<1: iq,ip=1,1
+                    same=lambda u,v: (u==v) or (u!=u and v!=v)
+                    ok=int(met[2,j,i])==iq and same(ab[0,j,i],a) and same(ab[1,j,i],b) and int(ipb[j,i])==ip
+                npts+=1
+                if not ok:
+                    bad+=1
+                    if bad<10: print("MISMATCH",curv,kew,Xs.shape,(i,j),(iP,jP),Xt[j,i],Yt[j,i],r,(int(met[2,j,i]),ab[0,j,i],ab[1,j,i],int(ipb[j,i])),flush=True)
+    print("grids",n,"targets",npts,"bad",bad)
+
+
 if __name__ == "__main__":
     orc.build()
     orc.set_libm(orc.PMATH)
-    {"twisted": twisted, "akima": akima}[sys.argv[1]](int(sys.argv[2]), float(sys.argv[3]))
+    {"twisted": twisted, "akima": akima, "mapping": mapping}[sys.argv[1]](int(sys.argv[2]), float(sys.argv[3]))
