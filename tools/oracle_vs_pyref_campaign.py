@@ -3,6 +3,7 @@
 
     python tools/oracle_vs_pyref_campaign.py twisted SEED SECONDS     # FIND_NEAREST_POINT on ORCA-shaped sources
     python tools/oracle_vs_pyref_campaign.py akima   SEED SECONDS     # AKIMA_2D on regular sources
+    python tools/oracle_vs_pyref_campaign.py drown   SEED SECONDS     # BDROWN / DROWN / SMOOTHER on random masks and options
     python tools/oracle_vs_pyref_campaign.py mapping SEED SECONDS     # MAPPING_BL (search by the oracle, body per target) on both source kinds
 
 Test infrastructure: nothing here is part of the product."""
@@ -139,7 +140,48 @@ def mapping(seed, seconds):
     print("grids",n,"targets",npts,"bad",bad)
 
 
+def drown(seed, seconds):
+    rng=np.random.default_rng(seed)
+    t0=time.time(); n=0; bad=0
+    def eq(a,b):
+        return np.array_equal(np.isnan(a),np.isnan(b)) and np.array_equal(a[~np.isnan(a)],b[~np.isnan(b)])
+    while time.time()-t0 < seconds:
+        ni,nj=int(rng.integers(5,40)),int(rng.integers(4,30))
+        kew=int(rng.choice([-1,0,2]))
+        if kew>=0 and ni<2*kew+3: continue
+        X=rng.normal(10.0,5.0,(nj,ni)).astype(np.float32)
+        land=rng.random((nj,ni))<rng.uniform(0.0,0.9)
+        if rng.random()<0.5:
+            yy,xx=np.mgrid[0:nj,0:ni]
+            land=(np.sin(xx*rng.uniform(0.05,0.5))*np.cos(yy*rng.uniform(0.05,0.5))>rng.uniform(-0.5,0.8))
+        if rng.random()<0.05: land[...]=True
+        mask=(~land).astype(np.int32)
+        X[mask==0]=-9999.0
+        if rng.random()<0.2: X.flat[rng.integers(0,X.size,3)]=np.float32(-0.0)
+        ninc,nsm=int(rng.integers(0,25)),int(rng.integers(0,8))
+        pmin,pmax=(-1.0e3,1.0e3) if rng.random()<0.7 else (5.0,12.0)
+        pval=float(rng.choice([0.0,-9999.0,1.0e-13]))
+        which=int(rng.integers(0,3))
+        with np.errstate(all="ignore"):
+            if which==0:
+                a,ns=orc.bdrown(kew,X,mask,ninc,nsm,pmin,pmax,pval); b,nsp=P.bdrown(kew,P.to_f(X),P.to_f(mask),ninc,nsm,pmin,pmax,pval); b=P.from_f(b)
+                ok=eq(a,b) and int(ns[0])==nsp
+            elif which==1:
+                m8=mask.astype(np.int8); k=min(ninc,6)
+                a,ns=orc.drown(kew,X,m8,k); b,nsp=P.drown(kew,P.to_f(X),P.to_f(m8),k); b=P.from_f(b)
+                ok=eq(a,b) and int(ns[0])==nsp
+            else:
+                use=rng.random()<0.6; lemp=bool(use and rng.random()<0.5)
+                a=orc.smoother(kew,X,nsm,mask if use else None,lemp); b=P.from_f(P.smoother(kew,P.to_f(X),nsm,msk=P.to_f(mask) if use else None,l_emp=lemp))
+                ok=eq(a,b)
+        n+=1
+        if not ok:
+            bad+=1
+            if bad<8: print("MISMATCH",which,ni,nj,kew,ninc,nsm,pmin,pval,(a!=b).sum(),flush=True)
+    print("cases",n,"bad",bad)
+
+
 if __name__ == "__main__":
     orc.build()
     orc.set_libm(orc.PMATH)
-    {"twisted": twisted, "akima": akima, "mapping": mapping}[sys.argv[1]](int(sys.argv[2]), float(sys.argv[3]))
+    {"twisted": twisted, "akima": akima, "mapping": mapping, "drown": drown}[sys.argv[1]](int(sys.argv[2]), float(sys.argv[3]))
