@@ -4,6 +4,7 @@
     python tools/oracle_vs_pyref_campaign.py twisted SEED SECONDS     # FIND_NEAREST_POINT on ORCA-shaped sources
     python tools/oracle_vs_pyref_campaign.py akima   SEED SECONDS     # AKIMA_2D on regular sources
     python tools/oracle_vs_pyref_campaign.py drown   SEED SECONDS     # BDROWN / DROWN / SMOOTHER on random masks and options
+    python tools/oracle_vs_pyref_campaign.py vert    SEED SECONDS     # AKIMA_1D_3D / AKIMA_1D_1D with missing values and persistence options
     python tools/oracle_vs_pyref_campaign.py mapping SEED SECONDS     # MAPPING_BL (search by the oracle, body per target) on both source kinds
 
 Test infrastructure: nothing here is part of the product."""
@@ -181,7 +182,52 @@ def drown(seed, seconds):
     print("cases",n,"bad",bad)
 
 
+def vert(seed, seconds):
+    pyref = P
+    rng=np.random.default_rng(seed)
+    t0=time.time(); n=0; bad=0
+    while time.time()-t0 < seconds:
+        which=int(rng.integers(0,2))
+        if which==0:
+            nk1,nk2=int(rng.integers(3,20)),int(rng.integers(1,25))
+            vz1=np.sort(rng.uniform(0,5500,nk1)).astype(np.float32)
+            if len(np.unique(vz1))<nk1: continue
+            vz2=np.sort(rng.uniform(0,6000,nk2)).astype(np.float32)
+            if rng.random()<0.4 and nk2>1: vz2[int(rng.integers(0,nk2))]=vz1[int(rng.integers(0,nk1))]; vz2=np.sort(vz2)
+            xf1=rng.normal(10,4,(nk1,3,4)).astype(np.float32)
+            if rng.random()<0.3: xf1[int(rng.integers(0,nk1)):, :, 1]=-9999.0
+            with np.errstate(all="ignore"):
+                a=orc.akima_1d_3d(vz1,xf1,vz2,-9999.0); b=pyref.akima_1d_3d_np(vz1,xf1,vz2,-9999.0)
+            ok=np.array_equal(a.view(np.uint32),b.view(np.uint32))
+        else:
+            ncol,nk1,nk2=4,int(rng.integers(3,16)),int(rng.integers(1,20))
+            vz1=np.sort(rng.uniform(0,5500,(ncol,nk1)),axis=1); vz2=np.sort(rng.uniform(0,6000,(ncol,nk2)),axis=1)
+            vf1=rng.normal(10,4,(ncol,nk1))
+            opts={}
+            if rng.random()<0.5: opts["l_surf_persist"]=True
+            if rng.random()<0.5: opts["l_botm_persist"]=True
+            if rng.random()<0.5:
+                opts["rmask_val"]=-9999.0
+                for c in range(ncol):
+                    r=rng.random()
+                    if r<0.3: vf1[c,int(rng.integers(1,nk1)):]=-9999.0
+                    elif r<0.4: vf1[c,:int(rng.integers(1,nk1))]=-9999.0
+                    elif r<0.5: vf1[c,int(rng.integers(0,nk1))]=-9999.0
+            with np.errstate(all="ignore"):
+                out,st=orc.akima_1d_1d(vz1,vf1,vz2,**opts)
+                ok=True
+                for c in range(ncol):
+                    b,sb=pyref.akima_1d_1d_py(vz1[c],vf1[c],vz2[c],opts.get("rmask_val"),opts.get("l_surf_persist",False),opts.get("l_botm_persist",False))
+                    if st[c]!=sb: ok=False
+                    elif sb>=0 and not np.array_equal(out[c].view(np.uint64) if out.dtype==np.float64 else out[c].view(np.uint32), b.view(np.uint64) if b.dtype==np.float64 else b.view(np.uint32)): ok=False
+        n+=1
+        if not ok:
+            bad+=1
+            if bad<8: print("MISMATCH",which,nk1,nk2,opts if which else "",flush=True)
+    print("cases",n,"bad",bad)
+
+
 if __name__ == "__main__":
     orc.build()
     orc.set_libm(orc.PMATH)
-    {"twisted": twisted, "akima": akima, "mapping": mapping, "drown": drown}[sys.argv[1]](int(sys.argv[2]), float(sys.argv[3]))
+    {"twisted": twisted, "akima": akima, "mapping": mapping, "drown": drown, "vert": vert}[sys.argv[1]](int(sys.argv[2]), float(sys.argv[3]))
