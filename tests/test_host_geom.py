@@ -29,6 +29,8 @@ def hg(tmp_path_factory):
     lib.h_heading.restype = C.c_double
     lib.h_degE_to_degWE.argtypes = [C.c_double]
     lib.h_degE_to_degWE.restype = C.c_double
+    lib.h_pack_record.argtypes = [C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_double)] * 4 + [C.c_int] * 4 + [C.c_double] * 4 + \
+        [C.POINTER(C.c_int), C.POINTER(C.c_float)]
     lib.h_local_coord.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                   C.POINTER(C.c_int)]
     return lib
@@ -170,3 +172,66 @@ def test_local_coord_without_sqrt_equals_literal(hg, orc):
         assert same and ip.value == ipo, (k, lons, lats, a.value, ao, b.value, bo, ip.value, ipo)
         seen.add(ipo)
     assert {0, 12} <= seen
+
+
+@pytest.mark.parametrize("kind", ["regular_1d", "regular_pole_rows", "curvilinear_2d"])
+def test_apply_record_equals_interp_bl(hg, orc, kind):
+    """pack.cuh builds the 32-byte record the apply kernels read (four source offsets + four REAL(4) weights, or "copy the
+    nearest point", or one of INTERP_BL's error constants).  The value the record yields -- the kernels' statement
+    (((z1*w1 + z2*w2) + z3*w3) + z4*w4) / wup in REAL(4) -- against the apply loop of BILIN_2D transliterated in tests/pyref.py
+    (index clamp, identical-point copy, INTERP_BL with its periodic wrap and error codes), on random and edge mapping entries."""
+    from tests import pyref as P
+    from sosie_b200 import grids as G
+    rng = np.random.default_rng(31)
+    f4 = np.float32
+    if kind == "curvilinear_2d":
+        Xs, Ys = G.orca_like(40, 30, "F", 15.0)
+        sep, lon1, lat1 = 0, None, None
+        X1w, Y1w = Xs, Ys
+        Z1w = rng.normal(5.0, 3.0, Xs.shape).astype(f4)
+    else:
+        lon1, lat1 = G.regular_latlon(36, 24)
+        sep = 1
+        X1w, Y1w = G.expand_2d(lon1, lat1)
+        Z1w = rng.normal(5.0, 3.0, X1w.shape).astype(f4)
+        if kind == "regular_pole_rows":       # the working arrays BILIN_2D applies on: two rows beyond the last latitude
+            X1w, Y1w, Z1w = orc.ext_north_to_90_regg(X1w, Y1w, Z1w)
+            lat1 = np.ascontiguousarray(Y1w[:, 0])
+    nyw, nx = X1w.shape
+    dp = lambda a: None if a is None else np.ascontiguousarray(a, np.float64).ctypes.data_as(C.POINTER(C.c_double))
+    keep = [np.ascontiguousarray(a, np.float64) for a in (lon1 if sep else X1w[0], lat1 if sep else Y1w[:, 0], X1w, Y1w)]
+    plon1, plat1, pX, pY = (a.ctypes.data_as(C.POINTER(C.c_double)) for a in keep)
+    id4 = (C.c_int * 4)(); w4 = (C.c_float * 4)()
+    Zflat = Z1w.reshape(-1)
+    n, ncopy, nconst = 60000, 0, 0
+    for k in range(n):
+        kew = int(rng.choice([-1, 0, 2]))
+        iP = int(rng.choice([-1, 1, 2, nx - 1, nx, int(rng.integers(1, nx + 1))]))
+        jP = int(rng.choice([-1, 1, 2, nyw - 1, nyw, int(rng.integers(1, nyw + 1))]))
+        iq = int(rng.integers(1, 5))
+        xa, xb = (float(v) for v in rng.choice([0.0, 1.0, 0.5, rng.random(), rng.random(), 1.0e-12], 2))
+        iPc, jPc = max(iP, 1), max(jP, 1)
+        lon_t, lat_t = float(rng.uniform(0, 360)), float(rng.uniform(-89, 89))
+        r = rng.random()
+        if r < 0.15:          # the target ON the nearest point, possibly 360 degrees apart or within / beyond 1e-5
+            lon_t = float(X1w[jPc - 1, iPc - 1]) + float(rng.choice([0.0, 360.0, -360.0, 5.0e-6, -5.0e-6, 2.0e-5]))
+            lat_t = float(Y1w[jPc - 1, iPc - 1]) + float(rng.choice([0.0, 5.0e-6, -5.0e-6, 2.0e-5]))
+        hg.h_pack_record(nx, nyw, sep, plon1, plat1, pX, pY, kew, iP, jP, iq, xa, xb, lon_t, lat_t, id4, w4)
+        w = [f4(v) for v in w4]
+        if id4[0] >= 0:
+            z = [Zflat[id4[q]] for q in range(4)]
+            wup = f4(f4(f4(w[0] + w[1]) + w[2]) + w[3])
+            val = f4(f4(f4(f4(z[0] * w[0]) + f4(z[1] * w[1])) + f4(z[2] * w[2])) + f4(z[3] * w[3])) / wup
+        elif id4[0] == -1:
+            val = Zflat[id4[1]]; ncopy += 1
+        else:
+            val = w[0]; nconst += 1
+        # BILIN_2D's loop body for this target (src/mod_bilin_2d.f90:217-234)
+        eps5 = float(f4(1.0e-5))
+        if abs(P.degE_to_degWE(float(X1w[jPc - 1, iPc - 1])) - P.degE_to_degWE(lon_t)) < eps5 and abs(float(Y1w[jPc - 1, iPc - 1]) - lat_t) < eps5:
+            ref = Z1w[jPc - 1, iPc - 1]
+        else:
+            with np.errstate(all="ignore"):
+                ref = P.interp_bl_np(kew, iPc, jPc, iq, xa, xb, Z1w)
+        assert f4(val) == f4(ref) or (val != val and ref != ref), (k, kew, iP, jP, iq, xa, xb, lon_t, lat_t, list(id4), list(w4), val, ref)
+    assert ncopy > 0.05 * n and nconst > 0.05 * n
