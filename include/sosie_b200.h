@@ -176,6 +176,36 @@ int sosie_set_pipeline_min_targets(sosie_ctx* ctx, int64_t n);
 int sosie_host_register(void* p, size_t bytes);
 int sosie_host_unregister(void* p);
 
+/* ---- asynchronous per-record / per-level calls: enqueue ... flush (csrc/queue.cu) ------------------------------------
+ * The reference calls INTERP_2D once per time record (src/sosie.f90:133-165) and BDROWN, then bilin_2d / akima_2d, once per
+ * level (src/mod_interp.f90:203-265, 288-337): one slab per call.  These entries take ONE slab like those call sites do,
+ * but only queue it: the slab is uploaded on a copy stream at once, up to `depth` (default 32) queued slabs of the same
+ * operation are coalesced into one batched launch, results are downloaded on a third stream while the next batch uploads.
+ * The output arrays are complete after sosie_flush -- or after any synchronous (non-_dev, non-_enqueue) entry of the same
+ * context, which flushes first.  Contract: a page-locked input (sosie_host_alloc, sosie_host_register) is BORROWED until
+ * the flush and read by DMA in place; a pageable input is copied before the call returns and may be reused at once (the
+ * reference loop re-reads data_src into the same array).  Outputs must stay valid until the flush; pageable outputs are
+ * filled by a host copy at flush time, page-locked ones by DMA.  Errors of a queued operation are reported by the enqueue
+ * or flush call that submits its batch.
+ * sosie_bilin_apply_enqueue: the apply loop of BILIN_2D (:209-263) for one slab; the grids must be set and the mapping
+ *   built or loaded (the first BILIN_2D call of a job stays synchronous: it builds the mapping and evaluates
+ *   l_last_y_row_missing).  A sharded context fills only its target rows.
+ * sosie_akima_apply_enqueue: AKIMA_2D for one slab after sosie_akima_set_grids.
+ * sosie_bdrown_enqueue: BDROWN(k_ew, X, mask, nb_inc, nb_smooth, pmin, pmax, pval_land) on one slab, X(ni,nj) in place,
+ *   mask(ni,nj) INTEGER(4) of that slab; nsweeps (nullable) receives the sweeps executed, at flush.
+ * sosie_queue_stats: stats[0..3] = batched launches, slabs queued, inputs staged through the pinned ring (pageable),
+ *   outputs staged (pageable) since the context was created.                                                        */
+int sosie_bilin_apply_enqueue(sosie_ctx* ctx, const float* Z1, float* Z2);
+int sosie_akima_apply_enqueue(sosie_ctx* ctx, const float* Z1, float* Z2);
+int sosie_bdrown_enqueue(sosie_ctx* ctx, int32_t k_ew, int32_t ni, int32_t nj, float* X, const int32_t* mask, int32_t nb_inc,
+                         int32_t nb_smooth, float pmin, float pmax, float pval_land, int32_t* nsweeps);
+int sosie_flush(sosie_ctx* ctx);
+int sosie_set_queue_depth(sosie_ctx* ctx, int32_t depth);
+int sosie_queue_stats(sosie_ctx* ctx, int64_t* stats);
+/* page-locked host memory for the record / level buffers of an enqueue loop (cudaHostAlloc; NULL on failure) */
+void* sosie_host_alloc(size_t bytes);
+int sosie_host_free(void* p);
+
 /* scalar INTERP_BL(k_ew_per, jiP, jjP, iqd, xa, xb, Z_in) for n trajectory points
  * (src/mod_bilin_2d.f90:275; callers src/interp_to_ground_track.f90:750): host pointers.           */
 int sosie_interp_bl(sosie_ctx* ctx, int32_t k_ew_per, int32_t nxi, int32_t nyi, const float* Z_in, int32_t n,

@@ -21,7 +21,7 @@ import os
 
 import numpy as np
 
-__all__ = ["Sosie", "SosieError", "lib_path", "load_library", "EXPORTS", "mapping_write_bin", "mapping_read_bin"]
+__all__ = ["Sosie", "SosieError", "lib_path", "load_library", "EXPORTS", "mapping_write_bin", "mapping_read_bin", "host_alloc", "host_free"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -45,6 +45,8 @@ EXPORTS = [
     "sosie_extrp_hl", "sosie_extrp_hl_dev", "sosie_angle2", "sosie_angle2_dev", "sosie_bilin_get_map_dev", "sosie_bilin_load_map_dev",
     "sosie_akima_1d_1d", "sosie_akima_1d_1d_dev", "sosie_interp3d_sigma", "sosie_interp3d_sigma_dev",
     "sosie_track_interp", "sosie_track_interp_dev", "sosie_set_exchange", "sosie_exchange_used", "sosie_find_nearest_point",
+    "sosie_bilin_apply_enqueue", "sosie_akima_apply_enqueue", "sosie_bdrown_enqueue", "sosie_flush", "sosie_set_queue_depth",
+    "sosie_queue_stats", "sosie_host_alloc", "sosie_host_free",
 ]
 
 _lib = None
@@ -69,6 +71,9 @@ def load_library():
     lib.sosie_launch_count.restype = C.c_int64
     lib.sosie_launch_count.argtypes = [C.c_void_p]
     lib.sosie_last_error.argtypes = [C.c_void_p]
+    lib.sosie_host_alloc.restype = C.c_void_p
+    lib.sosie_host_alloc.argtypes = [C.c_size_t]
+    lib.sosie_host_free.argtypes = [C.c_void_p]
     _lib = lib
     return lib
 
@@ -87,6 +92,43 @@ def _f32(a):
 
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _hp(a, dtype):
+    """host address of a caller-owned array for the enqueue entries: the library writes to / reads from it AFTER the call
+    returns, so no silent copy may be made here (wrong dtype or a non-contiguous view raise)"""
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):      # torch CPU tensor (pinned or not)
+        if a.is_cuda or not a.is_contiguous():
+            raise SosieError("enqueue: host tensors must be contiguous CPU tensors")
+        return C.c_void_p(a.data_ptr())
+    if not isinstance(a, np.ndarray) or a.dtype != dtype or not a.flags["C_CONTIGUOUS"]:
+        raise SosieError(f"enqueue: arrays must be C-contiguous numpy arrays of {np.dtype(dtype).name} (no hidden copies: the call is asynchronous)")
+    return C.c_void_p(a.ctypes.data)
+
+
+def host_alloc(shape, dtype=np.float32):
+    """page-locked numpy array (sosie_host_alloc); release with host_free(arr)"""
+    lib = load_library()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = lib.sosie_host_alloc(n * dtype.itemsize)
+    if not p:
+        raise SosieError("sosie_host_alloc failed")
+    buf = (C.c_char * (n * dtype.itemsize)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _pinned[arr.ctypes.data] = p
+    return arr
+
+
+def host_free(arr):
+    p = _pinned.pop(arr.ctypes.data, None)
+    if p:
+        load_library().sosie_host_free(C.c_void_p(p))
+
+
+_pinned = {}
 
 
 def _dp(t):
@@ -355,6 +397,34 @@ class Sosie:
         info = np.zeros(8, np.int32)
         self._ck(self._lib.sosie_bilin_map_info(self._h, _p(info)))
         return Z2, dict(metrics=met, alphabeta=ab, ipb=ipb, dist_np=dnp, info=info)
+
+    # ---------------------------------------------------------------- enqueue / flush (csrc/queue.cu)
+    def bilin_apply_enqueue(self, Z1, Z2):
+        """queue one slab of the BILIN_2D apply loop: Z1 (ny1, nx1) f32 -> Z2 (ny2, nx2) f32, both caller-owned numpy arrays
+        (C-contiguous) or raw addresses; Z2 is complete after flush().  Page-locked inputs are borrowed until then."""
+        self._ck(self._lib.sosie_bilin_apply_enqueue(self._h, _hp(Z1, np.float32), _hp(Z2, np.float32)))
+
+    def akima_apply_enqueue(self, Z1, Z2):
+        self._ck(self._lib.sosie_akima_apply_enqueue(self._h, _hp(Z1, np.float32), _hp(Z2, np.float32)))
+
+    def bdrown_enqueue(self, k_ew, X, mask, nb_inc=200, nb_smooth=0, pmin=-1.0e24, pmax=1.0e24, pval_land=0.0, nsweeps=None):
+        """queue BDROWN on one slab X (nj, ni) f32 IN PLACE with its mask (nj, ni) i32; nsweeps: optional 1-element i32 array"""
+        nj, ni = X.shape
+        self._ck(self._lib.sosie_bdrown_enqueue(self._h, int(k_ew), ni, nj, _hp(X, np.float32), _hp(mask, np.int32), int(nb_inc), int(nb_smooth),
+                                                C.c_float(pmin), C.c_float(pmax), C.c_float(pval_land),
+                                                None if nsweeps is None else _hp(nsweeps, np.int32)))
+
+    def flush(self):
+        """wait for every queued slab; the output arrays handed to the *_enqueue calls are complete afterwards"""
+        self._ck(self._lib.sosie_flush(self._h))
+
+    def set_queue_depth(self, depth: int):
+        self._ck(self._lib.sosie_set_queue_depth(self._h, int(depth)))
+
+    def queue_stats(self):
+        st = np.zeros(4, np.int64)
+        self._ck(self._lib.sosie_queue_stats(self._h, _p(st)))
+        return dict(batches=int(st[0]), slabs=int(st[1]), staged_in=int(st[2]), staged_out=int(st[3]))
 
     def set_pipeline_min_targets(self, n: int):
         """first calls with fewer targets take the sequential path (tests pass 0 to force the pipeline)"""

@@ -33,6 +33,17 @@ def headers():
                   glob.glob(os.path.join(HERE, "..", "include", "*.h")))
 
 
+def source_digest(names):
+    """sha256 over the named csrc files + the nvcc flags: profiles/*.json record it at capture time, bench.py compares it with
+    the tree it runs from and refuses a `roofline.traffic` taken from an older build of the kernel"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for n in sorted(names):
+        with open(os.path.join(CSRC, n), "rb") as f:
+            h.update(n.encode()); h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def up_to_date():
     if not os.path.exists(LIB):
         return False

@@ -475,7 +475,19 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
   // l_last_y_row_missing (:241-247) is evaluated on the first call only, the patch (:254-263) on every call
   if (first_call) {
     ctx->l_last_y_row_missing = 0;
-    if (ctx->i_orca_trg >= 4) {
+    // ORCA last-row test and patch read rows ny2-2 .. ny2 of Z2: on a row-sharded context only the rank whose shard holds
+    // all three can evaluate them; a shard that splits them is refused (the other ranks neither test nor patch: their rows
+    // do not include the last one)
+    bool owns_last = true;
+    if (ctx->i_orca_trg >= 4 && ctx->shard_j0 >= 1) {
+      const int ny2 = ctx->tg.ny;
+      owns_last = ctx->shard_j1 == ny2;
+      if (ctx->shard_j1 >= ny2 - 2 && !(ctx->shard_j0 <= ny2 - 2 && ctx->shard_j1 == ny2)) {
+        ctx->err = "bilin_apply: with an ORCA target (i_orca_trg >= 4) a shard must hold the last three target rows or none of them";
+        return SOSIE_ERR_ARG;
+      }
+    }
+    if (ctx->i_orca_trg >= 4 && owns_last) {
       DBuf<float> dm; CK(dm.alloc(1));
       k_lastrow_mean<<<1, 1, 0, ctx->stream>>>(dZ2, ctx->tg.nx, ctx->tg.ny, dm.p); KLAUNCH_CHECK();
       float hm;
@@ -498,6 +510,12 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
 
 int bilin_apply_uv_impl(sosie_ctx* ctx, int nslab, const float* dU1, const float* dV1, float* dUo, float* dVo,
                         const double* dcos, const double* dsin) {
+  if (ctx->l_last_y_row_missing) {
+    // the reference rotates the PATCHED last row (BILIN_2D :254-263, then corr_vect): not fusable, as in apply_ex
+    ctx->err = "bilin_apply_uv: the fused rotation cannot be combined with the ORCA last-row patch (l_last_y_row_missing): "
+               "use sosie_bilin_apply_dev + sosie_rotate_uv_dev";
+    return SOSIE_ERR_STATE;
+  }
   if (!ctx->pack_ready) { if (int rc = bilin_pack_impl(ctx)) return rc; }
   if (nslab <= 0) return SOSIE_OK;
   const size_t nt = (size_t)ctx->tg.nx * ctx->tg.ny;

@@ -1610,6 +1610,7 @@ int bilin_map_impl(sosie_ctx* ctx) {
   if (herr & 6) { ctx->err = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)"; return SOSIE_ERR_REF_STOP; }
   ctx->map_ready = !ctx->search_only;   // a search-only run leaves no mapping behind
   ctx->map_nt = nt;
+  if (l_is_reg_s) map_rows_from_shard(ctx); else ctx->map_j0 = ctx->map_j1 = 0;   // the TWISTED search is never split
   ctx->pack_ready = false; ctx->unpacked_applies = 0;
   return SOSIE_OK;
 }

@@ -103,6 +103,7 @@ static int pipelined_run(sosie_ctx* ctx, Pipe& P, int k_ew, int nx1, int ny1, co
   ctx->sg.nx = nx1; ctx->sg.ny = ny1; ctx->sg.separable = 1;
   ctx->tg = TrgGeom();
   ctx->tg.nx = nx2; ctx->tg.ny = ny2; ctx->tg.is_1d = 0;
+  if (int rc = shard_check(ctx, "sosie_bilin_2d_first")) return rc;
   CK(ctx->s_in_X.alloc(nx1)); CK(ctx->s_in_Y.alloc(ny1)); CK(ctx->t_X.alloc(nt)); CK(ctx->t_Y.alloc(nt)); CK(ctx->t_mask.alloc(nt));
   ctx->tg.X = ctx->t_X.p; ctx->tg.Y = ctx->t_Y.p;
   if (int rc = bilin_map_alloc(ctx)) return rc;
@@ -244,6 +245,7 @@ static int pipelined_run(sosie_ctx* ctx, Pipe& P, int k_ew, int nx1, int ny1, co
   if (e_all & 1) { ctx->err = "ERROR (L_InPoly of mod_poly.f90): we only expect positive longitudes!"; return SOSIE_ERR_REF_STOP; }
   if (e_all & 6) { ctx->err = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)"; return SOSIE_ERR_REF_STOP; }
   ctx->grids_set = true; ctx->map_ready = true; ctx->map_nt = nt; ctx->trg_partial = partial;
+  map_rows_from_shard(ctx);
   ctx->pack_ready = true; ctx->pack_gen++; ctx->boxes_ready = false;
 
   // ---- source slab rows the records read, apply, result

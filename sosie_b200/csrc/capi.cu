@@ -12,7 +12,8 @@ int fill_i32_dev(sosie_ctx* ctx, int32_t* p, size_t n, int32_t v);
 #define NEED(ctx_)                                   \
   if (!(ctx_)) return SOSIE_ERR_ARG;                 \
   sosie_ctx* ctx = (ctx_);                           \
-  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return SOSIE_ERR_CUDA; }
+  if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return SOSIE_ERR_CUDA; } \
+  if (ctx->q && queue_pending(ctx)) { if (int rcq__ = queue_flush(ctx)) return rcq__; }   /* a synchronous entry delivers the queued results first */
 
 extern "C" {
 
@@ -39,6 +40,7 @@ int sosie_create(sosie_ctx** out, int device) {
 int sosie_destroy(sosie_ctx* c) {
   if (!c) return SOSIE_OK;
   cudaSetDevice(c->device);
+  if (c->q) { queue_flush(c); queue_destroy(c); }
   cudaStreamSynchronize(c->stream);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -85,8 +87,19 @@ int sosie_get_timing(sosie_ctx* c, int32_t id, float* ms) {
 int sosie_bilin_set_shard(sosie_ctx* c, int32_t j0, int32_t j1) {
   NEED(c);
   if (j0 < 0 || j1 < j0) { ctx->err = "sosie_bilin_set_shard: bad row range"; return SOSIE_ERR_ARG; }
+  if ((j0 == 0) != (j1 == 0)) { ctx->err = "sosie_bilin_set_shard: rows are 1-based (0,0 = all rows)"; return SOSIE_ERR_ARG; }
+  if ((ctx->grids_set || ctx->map_ready) && ctx->tg.ny > 0 && j1 > ctx->tg.ny) {
+    ctx->err = "sosie_bilin_set_shard: row range exceeds the target grid"; return SOSIE_ERR_ARG;
+  }
   ctx->shard_j0 = j0; ctx->shard_j1 = j1;
   ctx->pack_ready = false; ctx->unpacked_applies = 0;
+  // the EASY search fills the mapping arrays (and a pipelined first call the target coordinates) only for the rows of the
+  // shard active when it ran: a mapping that does not cover the new rows is dropped (the next apply fails with
+  // SOSIE_ERR_STATE instead of packing rows that were never computed)
+  if (ctx->map_ready && ctx->map_j0 >= 1) {
+    const int n0 = j0 >= 1 ? j0 : 1, n1 = j0 >= 1 ? j1 : ctx->tg.ny;
+    if (n0 < ctx->map_j0 || n1 > ctx->map_j1) ctx->map_ready = false;
+  }
   return SOSIE_OK;
 }
 
@@ -110,6 +123,7 @@ static int set_grids_common(sosie_ctx* ctx, int k_ew, int nx1, int ny1, int src_
   ctx->tg = TrgGeom();
   ctx->tg.nx = nx2; ctx->tg.ny = ny2; ctx->tg.is_1d = trg_1d ? 1 : 0;
   ctx->tg.X = ctx->t_X.p; ctx->tg.Y = ctx->t_Y.p;
+  if (int rc = shard_check(ctx, "sosie_bilin_set_grids")) return rc;
   const size_t nt = (size_t)nx2 * ny2;
   ctx->trg_partial = false;
   CK(ctx->t_mask.alloc(nt));
@@ -219,6 +233,7 @@ int sosie_bilin_load_map(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32_t* 
   CK(cudaStreamSynchronize(st));
   if (!ctx->grids_set) { ctx->tg.nx = nx2; ctx->tg.ny = ny2; }
   ctx->map_ready = true;
+  ctx->map_j0 = ctx->map_j1 = 0;   // a loaded mapping holds every row
   ctx->pack_ready = false; ctx->unpacked_applies = 0;
   for (int k = 0; k < 8; k++) ctx->map_info[k] = 0;
   ctx->map_info[5] = -1;
@@ -254,6 +269,7 @@ int sosie_bilin_load_map_dev(sosie_ctx* c, int32_t nx2, int32_t ny2, const int32
   CK(cudaMemsetAsync(ctx->d_dnp.p, 0, nt * sizeof(float), st));
   if (!ctx->grids_set) { ctx->tg.nx = nx2; ctx->tg.ny = ny2; }
   ctx->map_ready = true;
+  ctx->map_j0 = ctx->map_j1 = 0;   // a loaded mapping holds every row
   ctx->pack_ready = false; ctx->unpacked_applies = 0;
   for (int k = 0; k < 8; k++) ctx->map_info[k] = 0;
   ctx->map_info[5] = -1;
@@ -293,6 +309,23 @@ static int apply_host_run(sosie_ctx* ctx, ApplyPipe& P, int nslab, const float* 
   const int nbuf = (nslab > chunk) ? 2 : 1;
   CK(ctx->d_stage1.alloc(n1 * chunk * nbuf));
   CK(ctx->d_out.alloc(n2 * chunk * nbuf));
+  if (nbuf == 1) {
+    // one chunk (the per-record / per-level call of the unchanged driver loop): nothing to overlap, so no extra streams or
+    // events are created -- upload, kernel and download are queued on the context stream (creating and destroying two
+    // streams and six events per call cost more than the 13 MB copy of a D-sized record)
+    float* din = ctx->d_stage1.p;
+    float* dout = ctx->d_out.p;
+    if (whole_src) CK(cudaMemcpyAsync(din, Z1, n1 * nslab * sizeof(float), cudaMemcpyHostToDevice, sc));
+    else
+      for (int s = 0; s < nslab && scnt; s++)
+        CK(cudaMemcpyAsync(din + (size_t)s * n1 + soff, Z1 + (size_t)s * n1 + soff, scnt * sizeof(float), cudaMemcpyHostToDevice, sc));
+    if (int rc = bilin_apply_impl(ctx, nslab, din, dout, first_call, 0, 0.f, 0.f, nullptr, 0.f)) return rc;
+    if (whole_trg) CK(cudaMemcpyAsync(Z2, dout, n2 * nslab * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    else
+      for (int s = 0; s < nslab; s++)
+        CK(cudaMemcpyAsync(Z2 + (size_t)s * n2 + k0, dout + (size_t)s * n2 + k0, kcnt * sizeof(float), cudaMemcpyDeviceToHost, sc));
+    return SOSIE_OK;
+  }
   CK(cudaStreamSynchronize(sc));
   CK(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking));
   CK(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
@@ -600,7 +633,7 @@ int sosie_bdrown(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t nsl
   if (ni < 3 || nj < 3 || nslab < 1 || !X || !mask) { ctx->err = "sosie_bdrown: bad arguments"; return SOSIE_ERR_ARG; }
   const size_t n = (size_t)ni * nj;
   cudaStream_t st = ctx->stream;
-  DBuf<float> dX; DBuf<int32_t> dM;
+  DBuf<float>& dX = ctx->bd_stage_x; DBuf<int32_t>& dM = ctx->bd_stage_m;   // kept between calls: the level loop calls this once per slab
   CK(dX.alloc(n * nslab)); CK(dM.alloc(n * (mask_per_slab ? nslab : 1)));
   CK(cudaMemcpyAsync(dX.p, X, n * nslab * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dM.p, mask, n * (mask_per_slab ? nslab : 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -622,7 +655,7 @@ int sosie_smoother(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, int32_t n
   if (ni < 3 || nj < 3 || nslab < 1 || !X) { ctx->err = "sosie_smoother: bad arguments"; return SOSIE_ERR_ARG; }
   const size_t n = (size_t)ni * nj;
   cudaStream_t st = ctx->stream;
-  DBuf<float> dX; DBuf<int32_t> dM;
+  DBuf<float>& dX = ctx->bd_stage_x; DBuf<int32_t>& dM = ctx->bd_stage_m;
   CK(dX.alloc(n * nslab));
   CK(cudaMemcpyAsync(dX.p, X, n * nslab * sizeof(float), cudaMemcpyHostToDevice, st));
   if (msk) { CK(dM.alloc(n)); CK(cudaMemcpyAsync(dM.p, msk, n * sizeof(int32_t), cudaMemcpyHostToDevice, st)); }

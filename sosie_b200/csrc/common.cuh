@@ -79,8 +79,11 @@ struct TrgGeom {
   const double* Y = nullptr;  // [ny] or [nx*ny]
 };
 
+struct SosieQueue;   // queue.cu: asynchronous enqueue / flush front end
+
 struct sosie_ctx {
   int device = 0;
+  SosieQueue* q = nullptr;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   std::string err;
@@ -95,6 +98,7 @@ struct sosie_ctx {
   bool search_only = false;     // sosie_find_nearest_point: the search stage alone (JIp, JJp into the first two planes of d_metrics)
   size_t map_nt = 0;             // target count the cached mapping was built/loaded for
   int shard_j0 = 0, shard_j1 = 0; // 1-based inclusive target rows handled by this context (0,0 = all)
+  int map_j0 = 0, map_j1 = 0;     // 1-based inclusive target rows the cached mapping holds (0,0 = every row: unsharded build, load_map)
   // prelude exchange between the ranks of a row-sharded job (sosie_set_exchange); NULL: every rank reduces the whole grid
   int (*xchg_fn)(void*, const void*, void*, size_t) = nullptr;
   void* xchg_user = nullptr;
@@ -175,6 +179,8 @@ struct sosie_ctx {
   DBuf<unsigned int> dr_Ri, dr_Re;   // land-only smoother: interior cells / periodic edge-column cells of dr_R0
   DBuf<unsigned int> dr_R0, dr_Ra, dr_Rb, dr_Lv, dr_ctr;   // level-list BDROWN: land lists, level list, counters
   DBuf<unsigned char> dr_tmp;                               // cub scratch
+  DBuf<float> bd_stage_x;                                   // host-pointer BDROWN / SMOOTHER: persistent staging (one cudaMalloc per job, not per level)
+  DBuf<int32_t> bd_stage_m;
   int force_general_bdrown = 0;  // tests: 0 auto, 1 level-list general path even for on-chip sized slabs, 2 legacy dense path
 };
 
@@ -225,12 +231,24 @@ static inline void prof_end(sosie_ctx* ctx, int id) {
   ctx->ev_used[id] = true;
 }
 // target index range [k0, k0+cnt) of this context's shard
+// (sosie_bilin_set_shard and the entries that fix the target extents refuse a shard that leaves the grid: no silent
+// fall-back to the whole grid)
 static inline void shard_range(const sosie_ctx* ctx, size_t* k0, size_t* cnt) {
   size_t nx = (size_t)ctx->tg.nx, ny = (size_t)ctx->tg.ny;
   if (ctx->shard_j0 >= 1 && ctx->shard_j1 >= ctx->shard_j0 && (size_t)ctx->shard_j1 <= ny) {
     *k0 = (size_t)(ctx->shard_j0 - 1) * nx;
     *cnt = (size_t)(ctx->shard_j1 - ctx->shard_j0 + 1) * nx;
   } else { *k0 = 0; *cnt = nx * ny; }
+}
+
+// rows the mapping was built for = the shard active at that moment
+static inline void map_rows_from_shard(sosie_ctx* ctx) { ctx->map_j0 = ctx->shard_j0; ctx->map_j1 = ctx->shard_j1; }
+static inline int shard_check(sosie_ctx* ctx, const char* who) {
+  if (ctx->shard_j0 >= 1 && ctx->tg.ny > 0 && ctx->shard_j1 > ctx->tg.ny) {
+    ctx->err = std::string(who) + ": the shard set by sosie_bilin_set_shard exceeds the target rows";
+    return SOSIE_ERR_ARG;
+  }
+  return SOSIE_OK;
 }
 
 // grid size for grid-stride kernels: a multiple of the SM count (148 on B200)
@@ -248,6 +266,11 @@ struct MapPlan {
   bool reg_s = true, reg_t = true;
   double y_min_s = 0, y_max_s = 0, y_min_t = 0, y_max_t = 0;
 };
+
+// queue.cu
+void queue_destroy(sosie_ctx* ctx);
+int queue_flush(sosie_ctx* ctx);          // submit the open batch, wait for every queued result
+bool queue_pending(const sosie_ctx* ctx);
 
 #define SOSIE_MAILBOX_BYTES (512 * 1024)
 // device -> host read-back of a small object through the mailbox (synchronises the context stream)

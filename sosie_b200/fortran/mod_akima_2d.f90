@@ -12,9 +12,9 @@ CONTAINS
    SUBROUTINE AKIMA_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2,    icall)
       INTEGER,                 INTENT(in)  :: k_ew_per
       REAL(8), DIMENSION(:,:), INTENT(in)  :: X10, Y10
-      REAL(4), DIMENSION(:,:), INTENT(in)  :: Z1
+      REAL(4), DIMENSION(:,:), INTENT(in),  TARGET :: Z1
       REAL(8), DIMENSION(:,:), INTENT(in)  :: X20, Y20
-      REAL(4), DIMENSION(:,:), INTENT(out) :: Z2
+      REAL(4), DIMENSION(:,:), INTENT(out), TARGET :: Z2
       INTEGER,       OPTIONAL, INTENT(in)  :: icall
       INTEGER :: nx1, ny1, nx2, ny2, is1d, it1d
       REAL(8), DIMENSION(:,:), ALLOCATABLE :: xs, ys, xt, yt
@@ -34,6 +34,13 @@ CONTAINS
          xs = X10 ; ys = Y10 ; xt = X20 ; yt = Y20
          CALL GPU_CHECK( sosie_akima_set_grids(gpu_ctx, k_ew_per, nx1, ny1, xs, ys, is1d, i_orca_src, nx2, ny2, xt, yt, it1d), 'AKIMA_2D/set_grids' )
          DEALLOCATE ( xs, ys, xt, yt )
+      END IF
+      IF ( l_gpu_async .AND. IS_CONTIGUOUS(Z1) .AND. IS_CONTIGUOUS(Z2) ) THEN
+         !! asynchronous mode: queue the slab (grids are set above on the first call); Z2 is complete after GPU_FLUSH()
+         CALL GPU_CHECK( sosie_akima_apply_enqueue(gpu_ctx, C_LOC(Z1), C_LOC(Z2)), 'AKIMA_2D/enqueue' )
+         l_first_call_interp_routine = .FALSE.
+         IF ( l_always_first_call ) l_first_call_interp_routine = .TRUE.
+         RETURN
       END IF
       ALLOCATE ( z1c(nx1,ny1), z2c(nx2,ny2) ) ; z1c = Z1
       CALL GPU_CHECK( sosie_akima_apply(gpu_ctx, 1, z1c, z2c), 'AKIMA_2D' )

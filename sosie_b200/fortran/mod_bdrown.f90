@@ -8,8 +8,8 @@ MODULE MOD_BDROWN
 CONTAINS
    SUBROUTINE BDROWN(k_ew, X, mask,   nb_inc, nb_smooth, pmin, pmax, pval_land )
       INTEGER,                    INTENT(in)    :: k_ew
-      REAL(4),    DIMENSION(:,:), INTENT(inout) :: X
-      INTEGER,    DIMENSION(:,:), INTENT(in)    :: mask
+      REAL(4),    DIMENSION(:,:), INTENT(inout), TARGET :: X
+      INTEGER,    DIMENSION(:,:), INTENT(in),    TARGET :: mask
       INTEGER,    OPTIONAL,       INTENT(in)    :: nb_inc, nb_smooth
       REAL(4),    OPTIONAL,       INTENT(in)    :: pmin, pmax, pval_land
       !! zmin/zmax/zval_land keep the reference's implicit SAVE (initialised locals, mod_bdrown.f90:56)
@@ -27,6 +27,13 @@ CONTAINS
       END IF
       CALL GPU_INIT()
       ni = SIZE(X,1) ; nj = SIZE(X,2)
+      IF ( l_gpu_async .AND. IS_CONTIGUOUS(X) .AND. IS_CONTIGUOUS(mask) .AND. (KIND(mask) == 4) ) THEN
+         !! asynchronous mode: queue the level (mod_interp.f90:213 passes data3d_src(:,:,jk), mask_src(:,:,jk)); up to
+         !! `depth` levels run in ONE launch (one CTA per slab for ORCA-sized slabs); X is drowned after GPU_FLUSH()
+         CALL GPU_CHECK( sosie_bdrown_enqueue(gpu_ctx, k_ew, ni, nj, C_LOC(X), C_LOC(mask), ninc_max, nsmooth, zmin, zmax, zval_land, &
+            &                                 C_NULL_PTR), 'BDROWN/enqueue' )
+         RETURN
+      END IF
       ALLOCATE ( xc(ni,nj), mc(ni,nj) ) ; xc = X ; mc = mask      ! contiguous copies (callers pass array sections)
       CALL GPU_CHECK( sosie_bdrown(gpu_ctx, k_ew, ni, nj, 1, xc, mc, 0, ninc_max, nsmooth, zmin, zmax, zval_land, C_NULL_PTR), 'BDROWN' )
       X = xc

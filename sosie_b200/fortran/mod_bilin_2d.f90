@@ -16,9 +16,9 @@ CONTAINS
    SUBROUTINE BILIN_2D(k_ew_per, X10, Y10, Z1, X20, Y20, Z2, cnpat,  mask_domain_trg)
       INTEGER,                 INTENT(in)  :: k_ew_per
       REAL(8), DIMENSION(:,:), INTENT(in)  :: X10, Y10
-      REAL(4), DIMENSION(:,:), INTENT(in)  :: Z1
+      REAL(4), DIMENSION(:,:), INTENT(in),  TARGET :: Z1      ! TARGET: C_LOC of the caller's own storage in asynchronous mode
       REAL(8), DIMENSION(:,:), INTENT(in)  :: X20, Y20
-      REAL(4), DIMENSION(:,:), INTENT(out) :: Z2
+      REAL(4), DIMENSION(:,:), INTENT(out), TARGET :: Z2
       CHARACTER(len=*),        INTENT(in)  :: cnpat
       INTEGER, OPTIONAL, DIMENSION(:,:), INTENT(in), TARGET :: mask_domain_trg
       !!
@@ -37,6 +37,14 @@ CONTAINS
       !!
       CALL GPU_INIT()
       nx1 = SIZE(Z1,1) ; ny1 = SIZE(Z1,2) ; nx2 = SIZE(Z2,1) ; ny2 = SIZE(Z2,2)
+      IF ( l_gpu_async .AND. (.NOT. l_first_call_interp_routine) .AND. IS_CONTIGUOUS(Z1) .AND. IS_CONTIGUOUS(Z2) ) THEN
+         !! asynchronous mode (sosie_gpu_c: GPU_ASYNC_BEGIN): queue this slab and return.  No copies: the library reads Z1 and
+         !! fills Z2 in the caller's storage -- Z1 is copied at once when it is pageable, borrowed until GPU_FLUSH when it is
+         !! page-locked (GPU_ALLOC_R4_3D); Z2 is complete after GPU_FLUSH().  The level loop of INTERP_3D passes
+         !! data3d_src(:,:,jk) / data3d_tmp(:,:,jk): contiguous sections, passed by descriptor without copy-in/out.
+         CALL GPU_CHECK( sosie_bilin_apply_enqueue(gpu_ctx, C_LOC(Z1), C_LOC(Z2)), 'BILIN_2D/enqueue' )
+         RETURN
+      END IF
       is1d = 0 ; IF ( TEST_XYZ(X10,Y10,Z1) == '1d' ) is1d = 1
       it1d = 0 ; IF ( TEST_XYZ(X20,Y20,Z2) == '1d' ) it1d = 1
       ALLOCATE ( z1c(nx1,ny1), z2c(nx2,ny2) ) ; z1c = Z1
@@ -88,7 +96,10 @@ CONTAINS
 
 
    SUBROUTINE MAPPING_BL(k_ew_per, X1, Y1, lon_trg, lat_trg, cf_w,  mask_domain_trg)
-      !! stand-alone use (interp_to_ground_track.f90:627, interp_to_hydro_section.f90:464): X1,Y1 are full 2-D arrays
+      !! stand-alone use (interp_to_ground_track.f90:627, interp_to_hydro_section.f90:464): X1,Y1 are full 2-D arrays.
+      !! NOTE: MAPPING_BL and sosie_find_nearest_point set their own grids in gpu_ctx, i.e. they replace the mapping a
+      !! previous BILIN_2D cached there (the reference keeps RAB/IMETRICS in module SAVE variables that MAPPING_BL also
+      !! overwrites through its mapping file); a program that needs both creates a second context (sosie_create).
       INTEGER,                 INTENT(in) :: k_ew_per
       REAL(8), DIMENSION(:,:), INTENT(in) :: X1, Y1
       REAL(8), DIMENSION(:,:), INTENT(in) :: lon_trg, lat_trg
@@ -120,18 +131,51 @@ CONTAINS
 
 
    FUNCTION INTERP_BL(k_ew_per, jiP, jjP, iqd, xa, xb, Z_in)
+      !! Scalar form (src/mod_bilin_2d.f90:275-361), called once per track point by interp_to_ground_track (:750) and
+      !! interp_to_hydro_section: four loads and a weighted mean, computed HERE on the host -- a device round trip (and an
+      !! upload of the whole Z_in) per point would be orders of magnitude slower than the reference, and would disturb the
+      !! mapping cached in gpu_ctx.  Same operations, order and REAL(4) roundings as the reference and as the packed
+      !! records of the GPU apply kernels (csrc/pack.cuh).  Whole tracks go through sosie_track_interp (INTEGRATION.md 5b).
       INTEGER,                 INTENT(in) :: k_ew_per
       INTEGER,                 INTENT(in) :: jiP, jjP, iqd
       REAL(8),                 INTENT(in) :: xa, xb
       REAL(4), DIMENSION(:,:), INTENT(in) :: Z_in
       REAL(4) :: INTERP_BL
-      REAL(4), DIMENSION(:,:), ALLOCATABLE :: zc
-      REAL(4) :: zout(1)
-      CALL GPU_INIT()
-      ALLOCATE ( zc(SIZE(Z_in,1),SIZE(Z_in,2)) ) ; zc = Z_in
-      CALL GPU_CHECK( sosie_interp_bl(gpu_ctx, k_ew_per, SIZE(Z_in,1), SIZE(Z_in,2), zc, 1, (/jiP/), (/jjP/), (/iqd/), (/xa/), (/xb/), zout), 'INTERP_BL' )
-      INTERP_BL = zout(1)
-      DEALLOCATE ( zc )
+      REAL(4) :: wup, w1, w2, w3, w4
+      INTEGER :: nxi, nyi, jiPm1, jiPp1, i1, j1, i2, j2, i3, j3, i4, j4
+      nxi = SIZE(Z_in,1) ; nyi = SIZE(Z_in,2)
+      jiPm1 = jiP-1 ; jiPp1 = jiP+1
+      IF ( (jiPm1 ==   0  ).AND.(k_ew_per>=0) )  jiPm1 = nxi - k_ew_per
+      IF ( (jiPp1 == nxi+1).AND.(k_ew_per>=0) )  jiPp1 = 1   + k_ew_per
+      i1=0 ; j1=0 ; i2=0 ; j2=0 ; i3=0 ; j3=0 ; i4=0 ; j4=0
+      SELECT CASE (iqd)
+      CASE (1)
+         i1=jiP ; j1=jjP ; i2=jiPp1 ; j2=jjP   ; i3=jiPp1 ; j3=jjP+1 ; i4=jiP   ; j4=jjP+1
+      CASE (2)
+         i1=jiP ; j1=jjP ; i2=jiP   ; j2=jjP-1 ; i3=jiPp1 ; j3=jjP-1 ; i4=jiPp1 ; j4=jjP
+      CASE (3)
+         i1=jiP ; j1=jjP ; i2=jiPm1 ; j2=jjP   ; i3=jiPm1 ; j3=jjP-1 ; i4=jiP   ; j4=jjP-1
+      CASE (4)
+         i1=jiP ; j1=jjP ; i2=jiP   ; j2=jjP+1 ; i3=jiPm1 ; j3=jjP+1 ; i4=jiPm1 ; j4=jjP
+      END SELECT
+      w1 = REAL( (1.d0 - xa)*(1.d0 - xb) , 4)
+      w2 = REAL(       xa   *(1.d0 - xb) , 4)
+      w3 = REAL(       xa   *    xb      , 4)
+      w4 = REAL( (1.d0 - xa)*    xb      , 4)
+      wup = w1 + w2 + w3 + w4
+      IF     ( wup == 0. ) THEN
+         INTERP_BL = -9998.
+      ELSEIF ( (i1 < 1).OR.(i2 < 1).OR.(i3 < 1).OR.(i4 < 1) ) THEN
+         INTERP_BL = -9997.
+      ELSEIF ( (j1 < 1).OR.(j2 < 1).OR.(j3 < 1).OR.(j4 < 1) ) THEN
+         INTERP_BL = -9996.
+      ELSEIF ( (j1 > nyi).OR.(j2 > nyi).OR.(j3 > nyi).OR.(j4 > nyi) ) THEN
+         INTERP_BL = -9995.
+      ELSEIF ( (i1 > nxi).OR.(i2 > nxi).OR.(i3 > nxi).OR.(i4 > nxi) ) THEN
+         INTERP_BL = -9994.
+      ELSE
+         INTERP_BL = ( Z_in(i1,j1)*w1 + Z_in(i2,j2)*w2 + Z_in(i3,j3)*w3 + Z_in(i4,j4)*w4 )/wup
+      END IF
    END FUNCTION INTERP_BL
 
 END MODULE MOD_BILIN_2D

@@ -219,9 +219,79 @@ MODULE SOSIE_GPU_C
          REAL(C_DOUBLE), INTENT(in) :: xcos(*), xsin(*)
          REAL(C_FLOAT), INTENT(out) :: Uo(*), Vo(*)
       END FUNCTION
+      !! ---- asynchronous per-record / per-level calls (include/sosie_b200.h, csrc/queue.cu): the slab arguments are passed as
+      !! TYPE(C_PTR) because the library reads / writes them AFTER the call returned (no Fortran temporary may be made)
+      INTEGER(C_INT) FUNCTION sosie_bilin_apply_enqueue(ctx, Z1, Z2) BIND(C, name='sosie_bilin_apply_enqueue')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: ctx, Z1, Z2
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_akima_apply_enqueue(ctx, Z1, Z2) BIND(C, name='sosie_akima_apply_enqueue')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: ctx, Z1, Z2
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bdrown_enqueue(ctx, k_ew, ni, nj, X, mask, nb_inc, nb_smooth, pmin, pmax, pval_land, nsweeps) &
+         &           BIND(C, name='sosie_bdrown_enqueue')
+         IMPORT :: C_PTR, C_INT, C_FLOAT
+         TYPE(C_PTR), VALUE    :: ctx, X, mask, nsweeps
+         INTEGER(C_INT), VALUE :: k_ew, ni, nj, nb_inc, nb_smooth
+         REAL(C_FLOAT), VALUE  :: pmin, pmax, pval_land
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_flush(ctx) BIND(C, name='sosie_flush')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: ctx
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_set_queue_depth(ctx, depth) BIND(C, name='sosie_set_queue_depth')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: depth
+      END FUNCTION
+      TYPE(C_PTR) FUNCTION sosie_host_alloc(nbytes) BIND(C, name='sosie_host_alloc')
+         IMPORT :: C_PTR, C_SIZE_T
+         INTEGER(C_SIZE_T), VALUE :: nbytes
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_host_free(p) BIND(C, name='sosie_host_free')
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: p
+      END FUNCTION
    END INTERFACE
 
+   !! Asynchronous mode of the drop-in modules (GPU_ASYNC_BEGIN / GPU_FLUSH below).  While it is on, the non-first calls of
+   !! BILIN_2D / AKIMA_2D and every call of BDROWN with CONTIGUOUS array arguments only QUEUE their slab
+   !! (sosie_*_enqueue) and return; the output arrays are complete after GPU_FLUSH().  The caller decides where the results
+   !! are needed: one CALL GPU_FLUSH() after each level loop of INTERP_3D, one per K records in the time loop (INTEGRATION.md 4).
+   LOGICAL, SAVE :: l_gpu_async = .FALSE.
+
 CONTAINS
+
+   SUBROUTINE GPU_ASYNC_BEGIN(kdepth)
+      !! kdepth: slabs coalesced into one batched launch (default 32)
+      INTEGER, OPTIONAL, INTENT(in) :: kdepth
+      CALL GPU_INIT()
+      IF ( PRESENT(kdepth) ) CALL GPU_CHECK( sosie_set_queue_depth(gpu_ctx, INT(kdepth,C_INT)), 'GPU_ASYNC_BEGIN' )
+      l_gpu_async = .TRUE.
+   END SUBROUTINE GPU_ASYNC_BEGIN
+
+   SUBROUTINE GPU_FLUSH()
+      !! every slab queued so far is in its output array when this returns
+      IF ( C_ASSOCIATED(gpu_ctx) ) CALL GPU_CHECK( sosie_flush(gpu_ctx), 'GPU_FLUSH' )
+   END SUBROUTINE GPU_FLUSH
+
+   SUBROUTINE GPU_ASYNC_END()
+      CALL GPU_FLUSH()
+      l_gpu_async = .FALSE.
+   END SUBROUTINE GPU_ASYNC_END
+
+   SUBROUTINE GPU_ALLOC_R4_3D(p, n1, n2, n3)
+      !! page-locked REAL(4) (n1,n2,n3) array for record / level rings: enqueue reads it by DMA in place (no staging copy)
+      REAL(4), DIMENSION(:,:,:), POINTER, INTENT(out) :: p
+      INTEGER, INTENT(in) :: n1, n2, n3
+      TYPE(C_PTR) :: cp
+      cp = sosie_host_alloc( INT(n1,C_SIZE_T)*INT(n2,C_SIZE_T)*INT(n3,C_SIZE_T)*4_C_SIZE_T )
+      IF ( .NOT. C_ASSOCIATED(cp) ) THEN
+         PRINT *, 'ERROR (sosie_gpu_c): sosie_host_alloc failed'; STOP
+      END IF
+      CALL C_F_POINTER(cp, p, (/ n1, n2, n3 /))
+   END SUBROUTINE GPU_ALLOC_R4_3D
 
    SUBROUTINE GPU_INIT()
       INTEGER(C_INT) :: ierr

@@ -11,10 +11,16 @@ from __future__ import annotations
 
 
 def row_shard(ny: int, rank: int, world: int):
-    """1-based inclusive target rows (j0, j1) of `rank`; empty shards (world > ny) return (1, 0)."""
+    """1-based inclusive target rows (j0, j1) of `rank`.  More ranks than rows would leave ranks without work while the
+    prelude exchange of a sharded first call is a collective that all ranks or none must enter: refused here, with the
+    same arguments on every rank, i.e. before any rank reaches a collective."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"row_shard: rank {rank} of {world}")
+    if world > ny:
+        raise ValueError(f"row_shard: {world} ranks for {ny} target rows (every rank needs at least one row)")
     j0 = (ny * rank) // world + 1
     j1 = (ny * (rank + 1)) // world
-    return (j0, j1) if j1 >= j0 else (1, 0)
+    return j0, j1
 
 
 def slab_shard(nslab: int, rank: int, world: int):

@@ -48,3 +48,32 @@ def test_call_order_and_arguments():
         ctx.close()
     with pytest.raises(sosie_b200.SosieError):
         sosie_b200.Sosie(99)        # no such device
+
+
+def test_shard_changes_invalidate_a_partial_mapping(gpu):
+    """the EASY search fills the mapping only for the rows of the active shard; moving the shard outside them must
+    not let an apply pack rows that were never computed, and a shard beyond the grid is an error, not "all rows"."""
+    cfg = G.config("E", 0.02)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, 1, seed=3)
+    ny2 = cfg["nyt"]
+    gpu.bilin_set_shard(0, 0)
+    gpu.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"], l_reg_src=True)
+    gpu.bilin_map()
+    full = gpu.bilin_apply(Z1, first_call=True)
+    try:
+        with pytest.raises(sosie_b200.SosieError, match="exceeds"):
+            gpu.bilin_set_shard(1, ny2 + 1)
+        gpu.bilin_set_shard(10, 40)
+        gpu.bilin_map()                                  # mapping now holds rows 10..40 only
+        gpu.bilin_set_shard(20, 30)                      # contained: the mapping is kept
+        part = gpu.bilin_apply(Z1)
+        assert np.array_equal(part[0, 19:30], full[0, 19:30])
+        gpu.bilin_set_shard(35, 60)                      # leaves the mapped rows: the mapping is dropped
+        with pytest.raises(sosie_b200.SosieError, match="error 3"):
+            gpu.bilin_apply(Z1)
+        gpu.bilin_map()
+        part = gpu.bilin_apply(Z1)
+        assert np.array_equal(part[0, 34:60], full[0, 34:60])
+    finally:
+        gpu.bilin_set_shard(0, 0)

@@ -19,6 +19,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_shards_partition_exactly():
     for n in (1, 7, 480, 4729):
         for world in (1, 2, 3, 8):
+            if world > n:   # more ranks than rows: refused identically on every rank, before any collective
+                for r in range(world):
+                    with pytest.raises(ValueError):
+                        row_shard(n, r, world)
+                continue
             rows = [row_shard(n, r, world) for r in range(world)]
             covered = [j for j0, j1 in rows for j in range(j0, j1 + 1)]
             assert covered == list(range(1, n + 1))

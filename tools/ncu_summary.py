@@ -2,6 +2,9 @@
 """Summarise ncu artefacts brought back in gpurun_out/ into small tracked text files under profiles/.
     python tools/ncu_summary.py rep  gpurun_out/prof.ncu-rep  profiles/r01_xxx.md  "title"
     python tools/ncu_summary.py list gpurun_out/launches.csv   profiles/r01_launches.md "title"
+    python tools/ncu_summary.py json gpurun_out/prof.ncu-rep  profiles/r02_ncu_E.json bilin_map.cu,geom.cuh,pmath.h,common.cuh
+        (machine-readable twin read by bench.py: per kernel the KEYS below + the digest of the named csrc files, so that a
+         capture of an older kernel is recognised as stale)
 """
 import collections
 import csv
@@ -58,5 +61,36 @@ def lst(path, out, title):
             f.write(f"| {k[:80]} | {a[0]} | {a[1]:.3f} | {100 * a[1] / tot:.1f} % |\n")
 
 
+def js(path, out, files):
+    import json
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from sosie_b200 import build as B
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    kernels = {}
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
+        d = {}
+        for k in KEYS:
+            if k in idx and r[idx[k]] != "":
+                v = float(r[idx[k]].replace(",", ""))
+                u = units[idx[k]]
+                if k.startswith("dram__bytes"):
+                    v *= scale.get(u, 1.0); u = "byte"
+                if k == "gpu__time_duration.sum":
+                    v *= {"us": 1e-3, "ns": 1e-6, "ms": 1.0, "s": 1e3}.get(u, 1.0); u = "ms"
+                d[k] = v
+        kernels.setdefault(name, d)      # first launch of each kernel
+    names = [f for f in files.split(",") if f]
+    head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+    with open(out, "w") as f:
+        json.dump({"source": path, "how": "ncu --set full --clock-control none, one launch per kernel (cold cache, serialised)",
+                   "git_head_at_summary": head, "csrc_files": names, "csrc_digest": B.source_digest(names), "kernels": kernels}, f, indent=1)
+
+
 if __name__ == "__main__":
-    {"rep": rep, "list": lst}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4])
+    {"rep": rep, "list": lst, "json": js}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4])
