@@ -166,6 +166,19 @@ int sosie_bilin_2d_first(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t 
                          const double* X20, const double* Y20, int32_t trg_1d, float* Z2,
                          const int32_t* mask_domain_trg, int32_t l_reg_src, int32_t i_orca_trg, int32_t nslab,
                          int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np);
+/* test hooks of the batched apply (results are identical whichever kernels run).  A batched apply splits the 32x8 target
+ * tiles between up to three kernels by the shape of a tile's source box (csrc/bilin_apply.cu): k_apply_grp (groups of 4
+ * slabs staged with 16-byte cp.async, one block barrier per group: the default for boxes up to 768 padded cells),
+ * k_apply_tma (3-D tensor map of the slab stack, one cp.async.bulk.tensor per tile and group; OFF by default -- switch on
+ * with sosie_apply_tma(1) or SOSIE_APPLY_TMA=1 -- because that instruction traps under the gVisor nvproxy driver of the
+ * GPU pool this library was developed on, see profiles/r02_tma_nvproxy.md) and k_apply_staged (4-byte cp.async per slab,
+ * direct gathers for boxes that fit nowhere; any alignment).  sosie_apply_tma(on): bit 0 TMA kernel on, bit 2 group
+ * kernel off.  sosie_apply_tile_classes: counts[0..2] = tiles that fit the TMA box, the group kernel, neither (-1 before the
+ * first batched apply of a mapping).  sosie_selftest_div: the reciprocal-based correctly rounded division of the apply
+ * kernels against the IEEE division on n pseudo-random operand pairs; *mismatches must come back 0.                     */
+int sosie_apply_tma(sosie_ctx* ctx, int32_t on);
+int sosie_apply_tile_classes(sosie_ctx* ctx, int32_t* counts);
+int sosie_selftest_div(sosie_ctx* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 /* rows[0..1] = first / last physical source row (0-based) read by this context's packed mapping records: the
  * host-pointer apply paths upload only those rows of every slab (a regional target touches part of a global slab) */
 int sosie_bilin_src_rows(sosie_ctx* ctx, int32_t* rows);

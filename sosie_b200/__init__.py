@@ -46,7 +46,7 @@ EXPORTS = [
     "sosie_akima_1d_1d", "sosie_akima_1d_1d_dev", "sosie_interp3d_sigma", "sosie_interp3d_sigma_dev",
     "sosie_track_interp", "sosie_track_interp_dev", "sosie_set_exchange", "sosie_exchange_used", "sosie_find_nearest_point",
     "sosie_bilin_apply_enqueue", "sosie_akima_apply_enqueue", "sosie_bdrown_enqueue", "sosie_flush", "sosie_set_queue_depth",
-    "sosie_queue_stats", "sosie_host_alloc", "sosie_host_free",
+    "sosie_queue_stats", "sosie_host_alloc", "sosie_host_free", "sosie_apply_tma", "sosie_apply_tile_classes", "sosie_selftest_div",
 ]
 
 _lib = None
@@ -425,6 +425,22 @@ class Sosie:
         st = np.zeros(4, np.int64)
         self._ck(self._lib.sosie_queue_stats(self._h, _p(st)))
         return dict(batches=int(st[0]), slabs=int(st[1]), staged_in=int(st[2]), staged_out=int(st[3]))
+
+    def apply_tma(self, on=0):
+        """test hook of the batched apply: bit 0 = TMA-staged kernel on (off by default), bit 2 = group-staged kernel off
+        (only the 4-byte cp.async kernel runs); results are identical in every combination"""
+        self._ck(self._lib.sosie_apply_tma(self._h, int(on)))
+
+    def apply_tile_classes(self):
+        """(tiles that fit the TMA box, tiles that fit the group-staged kernel, neither)"""
+        c = np.zeros(3, np.int32)
+        self._ck(self._lib.sosie_apply_tile_classes(self._h, _p(c)))
+        return int(c[0]), int(c[1]), int(c[2])
+
+    def selftest_div(self, n, seed=0):
+        m = C.c_uint64(0)
+        self._ck(self._lib.sosie_selftest_div(self._h, C.c_uint64(int(n)), C.c_uint64(int(seed)), C.byref(m)))
+        return int(m.value)
 
     def set_pipeline_min_targets(self, n: int):
         """first calls with fewer targets take the sequential path (tests pass 0 to force the pipeline)"""

@@ -16,6 +16,10 @@
 //   * optional fused post-ops of INTERP_2D (clamp :97-98, target mask :133-137) and the
 //     corr_vect rotation (src/corr_vect.f90:622-632).
 // Arithmetic is REAL(4) in the reference's order with FMA contraction off -> bit-identical fields.
+#include <algorithm>
+
+#include <cuda.h>   // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no -lcuda)
+
 #include "pack.cuh"
 
 // ---------------------------------------------------------------------------------------------------
@@ -137,9 +141,63 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// one block per tile: bounding box (0-based i0, j0, w, h) of the tile's source cells; w == 0 -> not stageable
+// ---- TMA staging (tiles whose source box fits TMA_NX sub-boxes of TMA_BW x TMA_BH cells) -----------------------------
+// A 3-D tensor map describes the slab stack Z1(nx, ny, nslab); ONE cp.async.bulk.tensor instruction, issued by one thread,
+// brings the box {TMA_BW, TMA_BH, TMA_SD} at the tile's box origin -- TMA_SD consecutive slabs at once -- into shared
+// memory and signals an mbarrier; cells beyond the slab edges are zero-filled by the hardware and never read.  The
+// sub-box is 32 floats = 128 B wide, the span of SWIZZLE_128B: the 16-byte chunk index is XOR-ed with the row index mod 8,
+// so the lanes of a warp whose corners share a column but sit in neighbouring rows (a target row cutting obliquely through
+// the source grid: the polar-stereographic target of config D) hit different banks.
+#define TMA_BW 32
+#define TMA_BH 16
+#define TMA_SD 4
+#define TMA_NX 2
+#define TMA_NSTG 3
+#define TMA_PLANE (TMA_BW * TMA_BH)                 // floats of one slab of one sub-box
+#define TMA_SUB (TMA_PLANE * TMA_SD)                // floats one TMA instruction writes (8 KB)
+#define TMA_STAGE (TMA_SUB * TMA_NX)                // floats per pipeline stage (16 KB)
+#define TMA_SMEM_BYTES (TMA_STAGE * TMA_NSTG * 4 + 1024)
+
+__device__ __forceinline__ bool box_is_tma(const int4& box) { return box.z > 0 && box.z <= TMA_NX * TMA_BW && box.w <= TMA_BH; }
+
+// ---- group staging with 16-byte cp.async (k_apply_grp) ---------------------------------------------------------------
+// The box is widened to 16-byte boundaries of the source rows (its first column rounded down to a multiple of 4: the source
+// width must be a multiple of 4 and the slab stack 16-byte aligned), so a slab's box is h rows of `cpr` 16-byte chunks; a
+// GROUP of GRP_SD consecutive slabs is staged at once, each thread copying at most GRP_CPT chunks with cp.async.cg 16, and
+// the block synchronises once per group instead of once per slab.  Row pitch in shared memory: cpr chunks, plus one when
+// cpr is even, so that the same column of neighbouring rows falls into different banks.
+#ifndef GRP_NSTG
+#define GRP_NSTG 4
+#endif
+#define GRP_STAGE 3072                                  // floats per pipeline stage: SD slabs x (GRP_STAGE / SD) floats of box
+#define GRP_CPT (GRP_STAGE / 4 / 256)                   // 16-byte chunks per thread and group at most (3)
+// The kernel is instantiated for groups of SD = 4, 2 and 1 slabs: a tile takes the deepest group its (padded) box allows --
+// 768, 1536 or 3072 floats per slab (the wide, short boxes next to the pole of a polar-stereographic target are the big ones)
+__host__ __device__ __forceinline__ int grp_cpr(const int4& box) { return ((box.x & 3) + box.z + 3) >> 2; }
+__host__ __device__ __forceinline__ int grp_pitch(const int4& box) { const int c = grp_cpr(box); return 4 * (c + ((c & 1) ? 0 : 1)); }
+__device__ __forceinline__ int grp_class(const int4& box) {   // slabs per group, 0: the box fits no instantiation
+  if (box.z <= 0) return 0;
+  const long long need = (long long)box.w * grp_pitch(box);
+  return need <= GRP_STAGE / 4 ? 4 : need <= GRP_STAGE / 2 ? 2 : need <= GRP_STAGE ? 1 : 0;
+}
+__device__ __forceinline__ bool box_fits_grp(const int4& box) { return grp_class(box) != 0; }
+// which kernel of a batched apply takes a tile: 0 the 4-byte cp.async kernel (also direct gathers), 1 k_apply_grp,
+// 2 k_apply_tma.  flags bit 0: the group kernel runs, bit 1: the TMA kernel runs
+#define OWN_OLD 0
+#define OWN_GRP 1
+#define OWN_TMA 2
+__device__ __forceinline__ int tile_owner(const int4& box, int flags) {
+  if ((flags & 2) && box_is_tma(box)) return OWN_TMA;
+  if ((flags & 1) && box_fits_grp(box)) return OWN_GRP;
+  return OWN_OLD;
+}
+
+// one block per tile: bounding box (0-based i0, j0, w, h) of the tile's source cells; w == 0 -> not stageable.
+// counts[0..2]: tiles that fit the TMA box / the group-staged kernel / neither; counts[3]: tiles the group kernel does not
+// take, counts[4..6]: tiles of its instantiations with 4 / 2 / 1 slabs per group; lists: four compact tile lists of ntiles
+// entries each (groups of 4, 2, 1, the rest), so that every kernel is launched over its own tiles only
 __global__ void __launch_bounds__(256)
-k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes) {
+k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes, int* counts, int* lists) {
   __shared__ int sh[4][8];
   __shared__ int shbad[8];
   for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
@@ -175,8 +233,16 @@ k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes) 
       }
       int w = sh[1][0] - sh[0][0] + 1, h = sh[3][0] - sh[2][0] + 1;
       int4 b = make_int4(0, 0, 0, 0);
-      if (!shbad[0] && sh[1][0] >= 0 && (long long)w * h <= BOXMAX) b = make_int4(sh[0][0], sh[2][0], w, h);
+      if (!shbad[0] && sh[1][0] >= 0 && (long long)w * h <= 65536) {
+        const int4 c = make_int4(sh[0][0], sh[2][0], w, h);
+        if ((long long)w * h <= BOXMAX || box_is_tma(c) || box_fits_grp(c)) b = c;
+      }
       boxes[tile] = b;
+      if (box_is_tma(b)) atomicAdd(&counts[0], 1);
+      const int gc = grp_class(b), li = gc == 4 ? 0 : gc == 2 ? 1 : gc == 1 ? 2 : 3;
+      if (gc) atomicAdd(&counts[1], 1);
+      lists[(size_t)li * tgm.ntiles + atomicAdd(&counts[li == 3 ? 3 : 4 + li], 1)] = tile;
+      if (!box_is_tma(b) && !box_fits_grp(b)) atomicAdd(&counts[2], 1);
     }
     __syncthreads();
   }
@@ -184,13 +250,17 @@ k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes) 
 
 __global__ void __launch_bounds__(256, 4)
 k_apply_staged(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, const float* __restrict__ Z1,
-               float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm, const int4* __restrict__ boxes) {
+               float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm, const int4* __restrict__ boxes,
+               int own_flags, const int* __restrict__ tile_list, int nlist) {
   __shared__ float buf[NSTAGE][BOXMAX];
   const size_t src_stride = (size_t)v.nreal;
   const int s0 = blockIdx.y * slabs_per_chunk;
   const int s1 = min(s0 + slabs_per_chunk, nslab);
   const int nsl = s1 - s0;
-  for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
+  for (int tl = blockIdx.x; tl < nlist; tl += gridDim.x) {
+    const int tile = tile_list ? tile_list[tl] : tl;
+    const int4 box = boxes[tile];
+    if (tile_owner(box, own_flags) != OWN_OLD) continue;   // another kernel of this apply takes the tile (block-uniform)
     const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
     const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);
     const bool valid = (i < tgm.nx && j <= tgm.j1);
@@ -200,15 +270,35 @@ k_apply_staged(const int4* __restrict__ pidx, const float4* __restrict__ pw, siz
     if (valid) { id = pidx[k]; w = pw[k]; }
     const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
     const bool masked = (valid && po.mask_trg) ? (po.mask_trg[k] == 0) : false;
-    const int4 box = boxes[tile];
-    if (box.z == 0) {  // not stageable (special records, pole rows, E-W wrap, huge footprint): direct gathers
-      if (valid)
-        for (int s = s0; s < s1; s++) {
+    if (box.z == 0 || (long long)box.z * box.w > BOXMAX) {  // not stageable (special records, pole rows, E-W wrap, huge footprint): direct gathers
+      if (valid) {
+        int s = s0;
+        if (id.x >= 0 && max(max(id.x, id.y), max(id.z, id.w)) < v.nreal) {
+          // ordinary record, no pole rows: the 16 gathers of four slabs are in flight together (the loop below is a chain of
+          // dependent latencies per slab; these tiles -- wide boxes next to the pole -- are few but were 4x slower per point)
+          for (; s + 4 <= s1; s += 4) {
+            float z[4][4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              const float* Z = Z1 + (size_t)(s + u) * src_stride;
+              z[u][0] = __ldg(Z + id.x); z[u][1] = __ldg(Z + id.y); z[u][2] = __ldg(Z + id.z); z[u][3] = __ldg(Z + id.w);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+              float r = __fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z[u][0], w.x), __fmul_rn(z[u][1], w.y)), __fmul_rn(z[u][2], w.z)), __fmul_rn(z[u][3], w.w)), wup);
+              if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+              if (masked) r = po.rmiss;
+              __stcs(Z2 + (size_t)(s + u) * nt + k, r);
+            }
+          }
+        }
+        for (; s < s1; s++) {
           float r = interp_one(Z1 + (size_t)s * src_stride, v, id, w, wup);
           if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
           if (masked) r = po.rmiss;
           __stcs(Z2 + (size_t)s * nt + k, r);
         }
+      }
       continue;  // block-uniform
     }
     const int bw = box.z, nelem = box.z * box.w;
@@ -266,6 +356,337 @@ k_apply_staged(const int4* __restrict__ pidx, const float4* __restrict__ pw, siz
     }
     __syncthreads();  // the next tile's prologue overwrites the buffers
     cp_async_wait<0>();
+  }
+}
+
+// ---- mbarrier / TMA primitives (PTX) ---------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// spin until the phase with parity `par` of `bar` has completed; a transfer that never lands (a descriptor the hardware
+// rejects) would hang the GPU: after ~2^28 probes the kernel traps instead, which the host sees as a launch failure
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned par) {
+  const unsigned a = smem_u32(bar);
+  unsigned done = 0;
+  for (unsigned spin = 0; !done; spin++) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(a), "r"(par) : "memory");
+    if (spin > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+               ::"r"(smem_u32(smem_dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+// x / wup, correctly rounded, through the reciprocal rcp = RN(1/wup) computed once per target: q = RN(x*rcp) is a faithful
+// quotient, r = RN(x - q*wup) is exact (one FMA), RN(q + r*rcp) is the correctly rounded quotient (Markstein's theorem, no
+// over/underflow: guarded by the range test; callers check 0.5 <= wup <= 2).  Zeros keep their sign through q alone.
+// Outside the guarded range the IEEE division runs.  3 instructions instead of the ~12 of __fdiv_rn with its slow path;
+// tests: sosie_selftest_div (2^28 random and edge operands against __fdiv_rn) and every apply parity test.
+__device__ __forceinline__ float div_by_rcp(float x, float wup, float rcp) {
+  const float ax = fabsf(x);
+  const float q = __fmul_rn(x, rcp);
+  if (ax >= 0x1p-90f && ax <= 0x1p90f) {
+    const float r = __fmaf_rn(-q, wup, x);
+    return __fmaf_rn(r, rcp, q);
+  }
+  if (ax == 0.f) return q;
+  return __fdiv_rn(x, wup);
+}
+
+__global__ void k_selftest_div(unsigned long long n, unsigned long long seed, unsigned long long* bad) {
+  unsigned long long nb = 0;
+  for (unsigned long long k = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; k < n; k += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long z = (k + seed) * 0x9E3779B97F4A7C15ULL;   // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL; z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL; z ^= z >> 31;
+    const unsigned xb = (unsigned)z, wb = (unsigned)(z >> 32);
+    float x = __uint_as_float(xb);                                              // any bit pattern (NaN, Inf, denormals, zeros included)
+    float wup = __uint_as_float(0x3F000000u + (wb % 0x01000001u));              // [0.5, 2.0] inclusive, every REAL(4) in it reachable
+    const unsigned sel = (unsigned)(k & 7), e0 = sel == 0 ? 27u : sel == 1 ? 207u : 117u;   // around the guards 2^-90, 2^90 and around 1
+    if (sel < 3) x = __uint_as_float((xb & 0x807FFFFFu) | ((e0 + (xb >> 23) % 20u) << 23));
+    const float a = div_by_rcp(x, wup, __frcp_rn(wup)), b = __fdiv_rn(x, wup);
+    if (__float_as_uint(a) != __float_as_uint(b) && !(a != a && b != b)) nb++;
+  }
+  if (nb) atomicAdd(bad, nb);
+}
+
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
+}
+
+// Batched slabs, group-staged (see GRP_* above).  Per tile and chunk of slabs: groups of GRP_SD slabs travel through
+// GRP_NSTG stages; per group a thread issues its (at most GRP_CPT, usually one) 16-byte copies, the block waits and
+// synchronises ONCE, and every thread interpolates its target in the GRP_SD slabs from shared memory with compile-time plane
+// offsets.  Instruction diet (ncu r02a: the first version was issue bound at 57 instructions per output, 20 % of them tile
+// set-up): the set-up is amortised over a long run of slabs (the host sizes the chunks for ~8 waves of blocks, not 32
+// slabs), its divisions go through multiply-high reciprocals, the kernel is specialised on the presence of post-ops, full
+// groups run without per-slab predicates, and the quotient by the weight sum is three instructions (div_by_rcp).
+template <int SD, bool FULL, bool POST>
+__device__ __forceinline__ void grp_compute(const float* __restrict__ b, int left, int o1, int o2, int o3, int o4, const float4& w, float wup, float rcp,
+                                            bool fast, bool masked, const PostOps& po, float*& outp, size_t nt) {
+  float acc[SD];
+#pragma unroll
+  for (int d = 0; d < SD; d++) {
+    const float* bd = b + d * (GRP_STAGE / SD);
+    acc[d] = (FULL || d < left) ? __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bd[o1], w.x), __fmul_rn(bd[o2], w.y)), __fmul_rn(bd[o3], w.z)), __fmul_rn(bd[o4], w.w)) : 1.0f;
+  }
+  // one range test for the group: every |acc| inside the guarded range of div_by_rcp.  The smallest magnitude through
+  // fminf (which drops a NaN), the largest through the SUM of the magnitudes (a NaN or an Inf poisons it, and a sum below
+  // 2^90 bounds every term): zeros, denormals, huge values, Inf and NaN all fail the test and take the general path
+  float lo = fabsf(acc[0]), sum = lo;
+#pragma unroll
+  for (int d = 1; d < SD; d++) { lo = fminf(lo, fabsf(acc[d])); sum = __fadd_rn(sum, fabsf(acc[d])); }
+  const bool all_fast = fast && lo >= 0x1p-90f && sum <= 0x1p90f;
+#pragma unroll
+  for (int d = 0; d < SD; d++) {
+    if (FULL || d < left) {
+      float r;
+      if (all_fast) {
+        const float q = __fmul_rn(acc[d], rcp);
+        r = __fmaf_rn(__fmaf_rn(-q, wup, acc[d]), rcp, q);
+      } else {
+        r = fast ? div_by_rcp(acc[d], wup, rcp) : __fdiv_rn(acc[d], wup);
+      }
+      if (POST) {
+        if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+        if (masked) r = po.rmiss;
+      }
+      __stcs(outp + (size_t)d * nt, r);
+    }
+  }
+  outp += (size_t)SD * nt;
+}
+
+// one tile, groups of SD slabs (block-uniform call)
+template <int SD, bool POST>
+__device__ __forceinline__ void grp_tile(float (*buf)[GRP_STAGE], const int4& box, int tile, const int4* __restrict__ pidx, const float4* __restrict__ pw,
+                                         size_t nt, const SlabView& v, const FastDiv& dnx, const float* __restrict__ Z1, float* __restrict__ Z2,
+                                         int s0, int s1, const PostOps& po, const TileGeom& tgm) {
+  constexpr int PLANE = GRP_STAGE / SD;
+  const size_t src_stride = (size_t)v.nreal;
+  const int ngrp = (s1 - s0 + SD - 1) / SD, nfull = (s1 - s0) / SD;
+  const int tj = tile / tgm.tiles_x, ti = tile - tj * tgm.tiles_x;
+  const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);
+  const bool valid = (i < tgm.nx && j <= tgm.j1);
+  const size_t k = valid ? (size_t)i + (size_t)j * tgm.nx : 0;
+  int4 id = make_int4(0, 0, 0, 0);
+  float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) { id = pidx[k]; w = pw[k]; }
+  const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
+  const bool fast = wup >= 0.5f && wup <= 2.0f;
+  const float rcp = fast ? __frcp_rn(wup) : 0.f;
+  const bool masked = (POST && valid && po.mask_trg) ? (po.mask_trg[k] == 0) : false;
+  const int x0a = box.x & ~3, cpr = grp_cpr(box), pitch = grp_pitch(box), nch = cpr * box.w;   // chunks per slab
+  auto off = [&](int lin) -> int {
+    const int r = (int)fdiv((unsigned)lin, dnx);
+    return (r - box.y) * pitch + (lin - r * v.nx - x0a);
+  };
+  int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+  if (valid) { o1 = off(id.x); o2 = off(id.y); o3 = off(id.z); o4 = off(id.w); }
+  // this thread's chunks of a group: slab d of the group, chunk c of the slab's box; ncp = chunks per thread in use
+  // (block-uniform).  e < 768: the quotients by nch and cpr come exactly from float reciprocals
+  const int ncp = (nch * SD + 255) >> 8;
+  const float rnch = 1.0f / (float)nch, rcpr = 1.0f / (float)cpr;
+  const float* gsrc[GRP_CPT];
+  int soff[GRP_CPT], sd_[GRP_CPT];
+#pragma unroll
+  for (int m = 0; m < GRP_CPT; m++) {
+    const int e = threadIdx.x + 256 * m;
+    const bool ok = e < nch * SD;
+    const int d = ok ? (int)(((float)e + 0.5f) * rnch) : 0;
+    const int c = ok ? e - d * nch : 0;
+    const int row = (int)(((float)c + 0.5f) * rcpr);
+    const int cc = c - row * cpr;
+    sd_[m] = ok ? d : SD;    // SD: no chunk
+    soff[m] = d * PLANE + row * pitch + cc * 4;
+    gsrc[m] = Z1 + (size_t)(s0 + d) * src_stride + (size_t)(box.y + row) * v.nx + x0a + cc * 4;
+  }
+  float* outp = Z2 + (size_t)s0 * nt + k;
+  auto issue = [&](int g, bool full) {   // group g -> stage g % GRP_NSTG
+    float* sb = &buf[g % GRP_NSTG][0];
+    const int left = full ? SD : s1 - (s0 + g * SD);   // slabs of this group that exist
+#pragma unroll
+    for (int m = 0; m < GRP_CPT; m++) {
+      if (m < ncp) {
+        if (sd_[m] < left) cp_async16(sb + soff[m], gsrc[m]);
+        gsrc[m] += (size_t)SD * src_stride;
+      }
+    }
+  };
+#pragma unroll
+  for (int q = 0; q < GRP_NSTG - 1; q++) {
+    if (q < ngrp) issue(q, q < nfull);
+    cp_async_commit();
+  }
+  int stage = 0;
+  for (int g = 0; g < ngrp; g++) {
+    cp_async_wait<GRP_NSTG - 2>();   // this thread's copies of group g have landed
+    __syncthreads();                 // ... everybody's have, and everybody is done reading the stage of group g-1
+    const int gn = g + GRP_NSTG - 1;
+    if (gn < ngrp) issue(gn, gn < nfull);   // refills the stage group g-1 used
+    cp_async_commit();
+    if (valid) {
+      const float* b = &buf[stage][0];
+      if (g < nfull) grp_compute<SD, true, POST>(b, SD, o1, o2, o3, o4, w, wup, rcp, fast, masked, po, outp, nt);
+      else grp_compute<SD, false, POST>(b, s1 - (s0 + g * SD), o1, o2, o3, o4, w, wup, rcp, fast, masked, po, outp, nt);
+    }
+    stage = stage + 1 == GRP_NSTG ? 0 : stage + 1;
+  }
+  __syncthreads();   // the next tile's prologue overwrites the stages
+  cp_async_wait<0>();
+}
+
+// a tile whose box fits no instantiation (special records, pole rows, E-W wrap, huge footprint): direct gathers
+template <bool POST>
+__device__ __forceinline__ void direct_tile(int tile, const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, const SlabView& v,
+                                            const float* __restrict__ Z1, float* __restrict__ Z2, int s0, int s1, const PostOps& po, const TileGeom& tgm) {
+  const size_t src_stride = (size_t)v.nreal;
+  const int tj = tile / tgm.tiles_x, ti = tile - tj * tgm.tiles_x;
+  const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);
+  if (!(i < tgm.nx && j <= tgm.j1)) return;
+  const size_t k = (size_t)i + (size_t)j * tgm.nx;
+  const int4 id = pidx[k];
+  const float4 w = pw[k];
+  const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
+  const bool masked = (POST && po.mask_trg) ? (po.mask_trg[k] == 0) : false;
+  auto fin = [&](float r, int s) {
+    if (POST) {
+      if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+      if (masked) r = po.rmiss;
+    }
+    __stcs(Z2 + (size_t)s * nt + k, r);
+  };
+  int s = s0;
+  if (id.x >= 0 && max(max(id.x, id.y), max(id.z, id.w)) < v.nreal) {
+    // ordinary record, no pole rows: the 16 gathers of four slabs are in flight together
+    for (; s + 4 <= s1; s += 4) {
+      float z[4][4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const float* Z = Z1 + (size_t)(s + u) * src_stride;
+        z[u][0] = __ldg(Z + id.x); z[u][1] = __ldg(Z + id.y); z[u][2] = __ldg(Z + id.z); z[u][3] = __ldg(Z + id.w);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        fin(__fdiv_rn(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(z[u][0], w.x), __fmul_rn(z[u][1], w.y)), __fmul_rn(z[u][2], w.z)), __fmul_rn(z[u][3], w.w)), wup), s + u);
+    }
+  }
+  for (; s < s1; s++) fin(interp_one(Z1 + (size_t)s * src_stride, v, id, w, wup), s);
+}
+
+// The batched apply of a 16-byte aligned slab stack in ONE launch.  blockIdx.x walks the compact tile lists in the order
+// "direct" tiles, groups of 1, of 2, of 4 slabs: the slow tiles (huge or odd boxes) start first and the many cheap ones fill
+// the tail of the launch.  cnt = lengths of the four lists (4 / 2 / 1 slabs per group, direct), lists = k_tilebox's.
+// tile_list == nullptr (the TMA kernel also runs): every tile is visited and the owner test decides.
+template <bool POST>
+__global__ void __launch_bounds__(256, 4)
+k_apply_grp(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, FastDiv dnx, const float* __restrict__ Z1,
+            float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm, const int4* __restrict__ boxes, int own_flags,
+            const int* __restrict__ lists, int4 cnt) {
+  __shared__ __align__(16) float buf[GRP_NSTG][GRP_STAGE];
+  const int s0 = blockIdx.y * slabs_per_chunk;
+  const int s1 = min(s0 + slabs_per_chunk, nslab);
+  const int nlist = lists ? cnt.x + cnt.y + cnt.z + cnt.w : tgm.ntiles;
+  for (int tl = blockIdx.x; tl < nlist; tl += gridDim.x) {
+    int tile = tl;
+    if (lists) {
+      int t = tl;
+      if (t < cnt.w) tile = lists[3 * (size_t)tgm.ntiles + t];
+      else if ((t -= cnt.w) < cnt.z) tile = lists[2 * (size_t)tgm.ntiles + t];
+      else if ((t -= cnt.z) < cnt.y) tile = lists[(size_t)tgm.ntiles + t];
+      else tile = lists[t - cnt.y];
+    }
+    const int4 box = boxes[tile];
+    if (tile_owner(box, own_flags) == OWN_TMA) continue;   // block-uniform
+    const int cls = grp_class(box);
+    if (cls == 4) grp_tile<4, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
+    else if (cls == 2) grp_tile<2, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
+    else if (cls == 1) grp_tile<1, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
+    else direct_tile<POST>(tile, pidx, pw, nt, v, Z1, Z2, s0, s1, po, tgm);
+  }
+}
+
+// Batched slabs, TMA-staged.  Pipeline per tile and chunk of slabs: groups of TMA_SD slabs travel through TMA_NSTG stages;
+// thread 0 arms the stage's mbarrier with the byte count and issues one TMA instruction per sub-box; every thread waits on
+// the barrier, interpolates its target in the TMA_SD slabs of the group from shared memory (compile-time plane offsets,
+// swizzled corner offsets computed once per tile) and stores; a block barrier frees the stage for the group TMA_NSTG ahead.
+__global__ void __launch_bounds__(256, 4)
+k_apply_tma(const __grid_constant__ CUtensorMap tm, const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v,
+            float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm, const int4* __restrict__ boxes, int own_flags) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ uint64_t full[TMA_NSTG];
+  float* const stg = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
+  const int s0 = blockIdx.y * slabs_per_chunk;
+  const int s1 = min(s0 + slabs_per_chunk, nslab);
+  const int ngrp = (s1 - s0 + TMA_SD - 1) / TMA_SD;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int st = 0; st < TMA_NSTG; st++) mbar_init(&full[st], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  unsigned phase = 0;   // bit st: parity of the next completion of full[st] (identical in every thread)
+  for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
+    const int4 box = boxes[tile];
+    if (tile_owner(box, own_flags) != OWN_TMA) continue;   // block-uniform
+    const int nsub = box.z <= TMA_BW ? 1 : 2;
+    const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
+    const int i = ti * 32 + (threadIdx.x & 31), j = tgm.j0 + tj * 8 + (threadIdx.x >> 5);
+    const bool valid = (i < tgm.nx && j <= tgm.j1);
+    const size_t k = valid ? (size_t)i + (size_t)j * tgm.nx : 0;
+    int4 id = make_int4(0, 0, 0, 0);
+    float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) { id = pidx[k]; w = pw[k]; }
+    const float wup = __fadd_rn(__fadd_rn(__fadd_rn(w.x, w.y), w.z), w.w);
+    const bool fast = wup >= 0.5f && wup <= 2.0f;
+    const float rcp = fast ? __frcp_rn(wup) : 0.f;
+    const bool masked = (valid && po.mask_trg) ? (po.mask_trg[k] == 0) : false;
+    // corner -> float offset inside one slab plane pair: sub-box, row, swizzled column
+    auto off = [&](int lin) -> int {
+      const int c = lin % v.nx - box.x, r = lin / v.nx - box.y;
+      const int sub = c >> 5, cc = c & 31;
+      return sub * TMA_SUB + r * TMA_BW + ((((cc >> 2) ^ (r & 7)) << 2) | (cc & 3));
+    };
+    int o1 = 0, o2 = 0, o3 = 0, o4 = 0;
+    if (valid) { o1 = off(id.x); o2 = off(id.y); o3 = off(id.z); o4 = off(id.w); }
+    float* outp = Z2 + (size_t)s0 * nt + k;
+    auto issue = [&](int g) {
+      const int st = g % TMA_NSTG;
+      mbar_expect_tx(&full[st], (unsigned)(nsub * TMA_SUB * 4));
+      for (int sx = 0; sx < nsub; sx++)
+        tma_load_3d(stg + st * TMA_STAGE + sx * TMA_SUB, &tm, box.x + sx * TMA_BW, box.y, s0 + g * TMA_SD, &full[st]);
+    };
+    if (threadIdx.x == 0)
+      for (int g = 0; g < TMA_NSTG && g < ngrp; g++) issue(g);
+    for (int g = 0; g < ngrp; g++) {
+      const int st = g % TMA_NSTG;
+      mbar_wait(&full[st], (phase >> st) & 1u);
+      phase ^= 1u << st;
+      const float* b = stg + st * TMA_STAGE;
+      if (valid) {
+        const int sb = s0 + g * TMA_SD;
+#pragma unroll
+        for (int d = 0; d < TMA_SD; d++) {
+          if (sb + d < s1) {
+            const float* bd = b + d * TMA_PLANE;
+            const float acc = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bd[o1], w.x), __fmul_rn(bd[o2], w.y)), __fmul_rn(bd[o3], w.z)), __fmul_rn(bd[o4], w.w));
+            float r = fast ? div_by_rcp(acc, wup, rcp) : __fdiv_rn(acc, wup);
+            if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
+            if (masked) r = po.rmiss;
+            __stcs(outp, r);
+            outp += nt;
+          }
+        }
+      }
+      __syncthreads();   // everybody is done reading this stage
+      if (threadIdx.x == 0 && g + TMA_NSTG < ngrp) issue(g + TMA_NSTG);
+    }
   }
 }
 
@@ -382,6 +803,38 @@ int bilin_src_rowrange(sosie_ctx* ctx, size_t k0, size_t kcnt, int* row_lo, int*
   return SOSIE_OK;
 }
 
+// 3-D tensor map of the slab stack Z1(nx, ny, nslab) REAL(4) with box {TMA_BW, TMA_BH, TMA_SD}, SWIZZLE_128B, zero fill
+// outside the slab.  cuTensorMapEncodeTiled is a driver entry point: resolved at run time through the runtime API.
+static bool apply_tensor_map(CUtensorMap* tm, const float* dZ1, int nx, int ny, int nslab) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn enc = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess) enc = (encode_fn)fn;
+    else cudaGetLastError();
+  }
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nslab};
+  const cuuint64_t strides[2] = {(cuuint64_t)nx * 4, (cuuint64_t)nx * ny * 4};
+  const cuuint32_t box[3] = {TMA_BW, TMA_BH, TMA_SD};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(dZ1), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int selftest_div_impl(sosie_ctx* ctx, unsigned long long n, unsigned long long seed, unsigned long long* mismatches) {
+  DBuf<unsigned long long> d;
+  CK(d.alloc(1));
+  CK(cudaMemsetAsync(d.p, 0, sizeof(unsigned long long), ctx->stream));
+  k_selftest_div<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, seed, d.p);
+  KLAUNCH_CHECK();
+  return fetch_small(ctx, d.p, mismatches, sizeof(unsigned long long));
+}
+
 static void apply_grid(const sosie_ctx* ctx, int nslab, dim3& grid, int& spc, TileGeom& tgm) {
   size_t k0, kcnt;
   shard_range(ctx, &k0, &kcnt);
@@ -442,15 +895,63 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
     // batched slabs: shared-memory staged gathers; the per-tile source boxes are cached with the packed records
     if (!ctx->boxes_ready) {
       CK(ctx->d_boxes.alloc(tgm.ntiles));
-      k_tilebox<<<grid_for(ctx, (size_t)tgm.ntiles * 256, 256), 256, 0, ctx->stream>>>(ctx->d_pidx.p, v, tgm, ctx->d_boxes.p);
+      CK(ctx->d_iscratch.alloc(SOSIE_ISCRATCH));
+      CK(ctx->d_tilecnt.alloc(8));
+      int* dcnt = ctx->d_tilecnt.p;
+      CK(cudaMemsetAsync(dcnt, 0, 8 * sizeof(int), ctx->stream));
+      CK(ctx->d_tilelist.alloc(4 * (size_t)tgm.ntiles));
+      k_tilebox<<<grid_for(ctx, (size_t)tgm.ntiles * 256, 256), 256, 0, ctx->stream>>>(ctx->d_pidx.p, v, tgm, ctx->d_boxes.p, dcnt, ctx->d_tilelist.p);
       KLAUNCH_CHECK();
+      int hc[8];
+      if (int rc = fetch_small(ctx, dcnt, hc, sizeof(hc))) return rc;   // once per mapping
+      ctx->tiles_tma = hc[0]; ctx->tiles_grp = hc[1]; ctx->tiles_other = hc[2];
+      ctx->tiles_cls[0] = hc[4]; ctx->tiles_cls[1] = hc[5]; ctx->tiles_cls[2] = hc[6]; ctx->tiles_cls[3] = hc[3];
       ctx->boxes_ready = true;
     }
     spc = nslab < APPLY_SLABS_PER_CHUNK_STAGED ? nslab : APPLY_SLABS_PER_CHUNK_STAGED;
     grid = dim3(tgm.ntiles, (nslab + spc - 1) / spc, 1);
+    // 16-byte staging (group kernel, TMA) needs a 16-byte aligned slab stack and row pitch
+    const bool aligned = (v.nx % 4) == 0 && ((uintptr_t)dZ1 % 16) == 0;
+    const bool use_grp = ctx->grp_mode != 0 && aligned;
+    // TMA staging: a tensor map of the slab stack, at least one full box depth (off unless SOSIE_APPLY_TMA=1 / sosie_apply_tma:
+    // cp.async.bulk.tensor traps as an illegal instruction under the gVisor nvproxy driver of this GPU pool -- profiles/r02_tma_nvproxy.md)
+    CUtensorMap tmap;
+    const bool use_tma = ctx->tma_mode != 0 && aligned && ctx->tiles_tma > 0 && nslab >= TMA_SD && apply_tensor_map(&tmap, dZ1, v.nx, v.ny, nslab);
+    const int own = (use_grp ? 1 : 0) | (use_tma ? 2 : 0);
+    const int n_tma = use_tma ? ctx->tiles_tma : 0;
+    // (a tile that fits both goes to the TMA kernel: the counts overlap, so the other two kernels are launched whenever
+    // they could own a tile)
     prof_begin(ctx, SOSIE_T_APPLY);
-    k_apply_staged<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po, tgm, ctx->d_boxes.p);
-    KLAUNCH_CHECK();
+    if (use_tma) {
+      static bool attr_set = false;
+      if (!attr_set) { CK(cudaFuncSetAttribute(k_apply_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES)); attr_set = true; }
+      k_apply_tma<<<grid, 256, TMA_SMEM_BYTES, ctx->stream>>>(tmap, ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ2, nslab, spc, po, tgm, ctx->d_boxes.p, own);
+      KLAUNCH_CHECK();
+    }
+    if (use_grp && n_tma < tgm.ntiles) {
+      const FastDiv dnx = make_fastdiv((unsigned)v.nx);
+      const int* lst = use_tma ? nullptr : ctx->d_tilelist.p;
+      const int4 cnt = make_int4(ctx->tiles_cls[0], ctx->tiles_cls[1], ctx->tiles_cls[2], ctx->tiles_cls[3]);
+      const int nl = tgm.ntiles;
+      // slabs per block: long runs amortise the per-tile set-up (records, offsets, copy plan); enough blocks for ~16 waves
+      const int waves_blocks = 16 * 4 * ctx->num_sms;
+      // ... but not much longer than ~128 slabs: blocks that run together then work on the same slabs, neighbouring tiles
+      // find their shared source rows in L2 (measured on D: 292 slabs per block move 1.6x the bytes of 128 per block)
+      int nchunk_g = std::max(1, std::min((nslab + 3) / 4, std::max((waves_blocks + nl - 1) / nl, (nslab + 127) / 128)));
+      if (ctx->grp_spc > 0) nchunk_g = std::max(1, (nslab + ctx->grp_spc - 1) / ctx->grp_spc);    // tuning hook (SOSIE_GRP_SPC)
+      int spc_g = (nslab + nchunk_g - 1) / nchunk_g;
+      spc_g = (spc_g + 3) / 4 * 4;
+      const dim3 gg(nl, (nslab + spc_g - 1) / spc_g, 1);
+      if (use_clamp || dmask_trg)
+        k_apply_grp<true><<<gg, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dnx, dZ1, dZ2, nslab, spc_g, po, tgm, ctx->d_boxes.p, own, lst, cnt);
+      else
+        k_apply_grp<false><<<gg, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dnx, dZ1, dZ2, nslab, spc_g, po, tgm, ctx->d_boxes.p, own, lst, cnt);
+      KLAUNCH_CHECK();
+    }
+    if (!use_grp) {   // unaligned slab stack (or the test hook): the 4-byte cp.async kernel takes everything the TMA kernel does not
+      k_apply_staged<<<grid, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ1, dZ2, nslab, spc, po, tgm, ctx->d_boxes.p, own, nullptr, tgm.ntiles);
+      KLAUNCH_CHECK();
+    }
     prof_end(ctx, SOSIE_T_APPLY);
   } else {
     prof_begin(ctx, SOSIE_T_APPLY);

@@ -33,6 +33,8 @@ int sosie_create(sosie_ctx** out, int device) {
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->num_sms = sms;
   c->always_store_records = getenv("SOSIE_ALWAYS_STORE_RECORDS") != nullptr;
+  if (const char* e = getenv("SOSIE_APPLY_TMA")) c->tma_mode = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("SOSIE_GRP_SPC")) c->grp_spc = atoi(e);
   *out = c;
   return SOSIE_OK;
 }
@@ -445,6 +447,28 @@ int sosie_bilin_2d_first(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t ny1, c
                          &first, 0, nslab, metrics, alphabeta, id_problem, dist_np);
 }
 
+int sosie_apply_tma(sosie_ctx* c, int32_t on) {
+  NEED(c);
+  ctx->tma_mode = (on & 1) ? 1 : 0;
+  ctx->grp_mode = (on & 4) ? 0 : 1;     // bit 2: also switch the group-staged kernel off (4-byte cp.async kernel only)
+  return SOSIE_OK;
+}
+int sosie_apply_tile_classes(sosie_ctx* c, int32_t* counts) {
+  NEED(c);
+  if (!counts) return SOSIE_ERR_ARG;
+  counts[0] = ctx->boxes_ready ? ctx->tiles_tma : -1; counts[1] = ctx->boxes_ready ? ctx->tiles_grp : -1;
+  counts[2] = ctx->boxes_ready ? ctx->tiles_other : -1;
+  return SOSIE_OK;
+}
+int sosie_selftest_div(sosie_ctx* c, uint64_t n, uint64_t seed, uint64_t* mismatches) {
+  NEED(c);
+  if (!mismatches) return SOSIE_ERR_ARG;
+  unsigned long long m = 0;
+  if (int rc = selftest_div_impl(ctx, n, seed, &m)) return rc;
+  *mismatches = m;
+  return SOSIE_OK;
+}
+
 int sosie_bilin_src_rows(sosie_ctx* c, int32_t* rows) {
   NEED(c);
   if (!rows) return SOSIE_ERR_ARG;
@@ -468,10 +492,13 @@ int sosie_set_pipeline_min_targets(sosie_ctx* c, int64_t n) {
 
 int sosie_host_register(void* p, size_t bytes) {
   if (!p || !bytes) return SOSIE_ERR_ARG;
-  return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? SOSIE_OK : SOSIE_ERR_CUDA;
+  if (cudaHostRegister(p, bytes, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return SOSIE_ERR_CUDA; }
+  pin_registry_add(p, bytes);
+  return SOSIE_OK;
 }
 int sosie_host_unregister(void* p) {
   if (!p) return SOSIE_ERR_ARG;
+  pin_registry_remove(p);
   return cudaHostUnregister(p) == cudaSuccess ? SOSIE_OK : SOSIE_ERR_CUDA;
 }
 

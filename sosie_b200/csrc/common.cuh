@@ -124,7 +124,14 @@ struct sosie_ctx {
   DBuf<int4> d_pidx;             // packed apply records
   DBuf<float4> d_pw;
   DBuf<int4> d_boxes;            // per-tile source bounding boxes of the staged apply
+  DBuf<int32_t> d_tilelist;      // four compact lists of ntiles entries: tiles of the group-staged kernel with 4 / 2 / 1 slabs per group, the rest
+  DBuf<int32_t> d_tilecnt;
+  int tiles_cls[4] = {0, 0, 0, 0};   // their lengths
   bool boxes_ready = false;
+  int tiles_tma = 0, tiles_grp = 0, tiles_other = 0;   // tiles that fit the TMA box / the group-staged kernel / neither (counted with the boxes)
+  int tma_mode = 0;                     // 1: batched applies stage TMA-class tiles with cp.async.bulk.tensor (SOSIE_APPLY_TMA=1, sosie_apply_tma)
+  int grp_spc = 0;                      // > 0: slabs per block of the group-staged kernel (tuning hook SOSIE_GRP_SPC; 0 = automatic)
+  int grp_mode = 1;                     // 0: no group-staged kernel either (test hook: every variant must agree bit for bit)
   DBuf<float> d_stage1, d_stage2;  // staging for host-pointer apply
   DBuf<float> d_out;               // result staging of the host-pointer paths
   size_t pipeline_min_targets = (size_t)1 << 20;  // first calls smaller than this take the sequential path
@@ -205,6 +212,31 @@ struct sosie_ctx {
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// exact unsigned 32-bit division by an invariant divisor (Granlund & Montgomery 1994): the list kernels decode
+// (mask, j, i) from a linear cell index for every entry; three hardware divides cost more than the cell update itself
+struct FastDiv {
+  unsigned int d, M, s1, s2;
+};
+static inline FastDiv make_fastdiv(unsigned int d) {
+  FastDiv f;
+  f.d = d; f.M = 0; f.s1 = 0; f.s2 = 0;
+  if (d <= 1) return f;
+  unsigned int l = 0;
+  while ((1ull << l) < d) l++;
+  f.M = (unsigned int)((((1ull << l) - d) << 32) / d + 1);
+  f.s1 = l < 1 ? l : 1; f.s2 = l > 1 ? l - 1 : 0;
+  return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ unsigned int fdiv(unsigned int a, const FastDiv& f) {
+  if (f.d <= 1) return a;
+  const unsigned int t = __umulhi(f.M, a);
+  return (t + ((a - t) >> f.s1)) >> f.s2;
+}
+
+#endif
+
+
 // scratch slot #cursor of the context, grown to hold `count` T's (nullptr on allocation failure)
 template <class T>
 static inline T* ws_get(sosie_ctx* ctx, size_t count) {
@@ -271,6 +303,8 @@ struct MapPlan {
 void queue_destroy(sosie_ctx* ctx);
 int queue_flush(sosie_ctx* ctx);          // submit the open batch, wait for every queued result
 bool queue_pending(const sosie_ctx* ctx);
+void pin_registry_add(const void* p, size_t bytes);   // page-locked host ranges the library knows about
+void pin_registry_remove(const void* p);
 
 #define SOSIE_MAILBOX_BYTES (512 * 1024)
 // device -> host read-back of a small object through the mailbox (synchronises the context stream)
@@ -300,6 +334,7 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
 int bilin_apply_uv_impl(sosie_ctx* ctx, int nslab, const float* dU1, const float* dV1, float* dUo, float* dVo,
                         const double* dcos, const double* dsin);
 int bilin_prepare_src(sosie_ctx* ctx);
+int selftest_div_impl(sosie_ctx* ctx, unsigned long long n, unsigned long long seed, unsigned long long* mismatches);
 int track_interp_impl(sosie_ctx* ctx, int ni, int nj, int nk, const float* F1, const float* F2, double vt1, double vt2, const int8_t* imask,
                       long long n, const double* rt, const int32_t* jiP, const int32_t* jjP, const int32_t* iqd, const double* xa,
                       const double* xb, const double* r_obs, double obs_lo, double obs_hi, int clip_missing, double rmissval, double* f_bl,

@@ -25,27 +25,6 @@ struct BdGeom {
   int jimW, jipW, jimE, jipE;  // periodic neighbours of column 1 (W) and column ni (E): vim_per/vip_per (:98-101)
 };
 
-// exact unsigned 32-bit division by an invariant divisor (Granlund & Montgomery 1994): the list kernels decode
-// (mask, j, i) from a linear cell index for every entry; three hardware divides cost more than the cell update itself
-struct FastDiv {
-  unsigned int d, M, s1, s2;
-};
-static FastDiv make_fastdiv(unsigned int d) {
-  FastDiv f;
-  f.d = d; f.M = 0; f.s1 = 0; f.s2 = 0;
-  if (d <= 1) return f;
-  unsigned int l = 0;
-  while ((1ull << l) < d) l++;
-  f.M = (unsigned int)((((1ull << l) - d) << 32) / d + 1);
-  f.s1 = l < 1 ? l : 1; f.s2 = l > 1 ? l - 1 : 0;
-  return f;
-}
-__device__ __forceinline__ unsigned int fdiv(unsigned int a, const FastDiv& f) {
-  if (f.d <= 1) return a;
-  const unsigned int t = __umulhi(f.M, a);
-  return (t + ((a - t) >> f.s1)) >> f.s2;
-}
-
 static BdGeom make_bdgeom(int ni, int nj, int k_ew) {
   BdGeom g;
   g.ni = ni; g.nj = nj; g.k_ew = k_ew;

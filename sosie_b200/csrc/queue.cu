@@ -14,12 +14,19 @@
 // been copied when the call returns and may be reused at once.  Output arrays must stay valid until the flush.
 #include <algorithm>
 #include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 
 namespace {
 
 enum { Q_NONE = 0, Q_BILIN = 1, Q_AKIMA = 2, Q_BDROWN = 3 };
+
+// one host -> device copy of a batch; small slabs (an ORCA level is ~100 KB) are not copied one by one at enqueue time but
+// merged at submit time: consecutive levels of a cube are adjacent in host memory and in the batch buffer, so a whole
+// level loop goes up (and comes back) in one or two cudaMemcpyAsync calls instead of 62
+struct QCopy { void* d; const void* h; size_t bytes; };
+#define Q_DEFER_BYTES ((size_t)1 << 20)
 
 struct QItem {
   float* dst = nullptr;        // caller's output slab
@@ -41,6 +48,7 @@ struct QBatch {
   BdParams bd;
   size_t n_in = 0, n_out = 0;   // elements per slab
   std::vector<QItem> items;
+  std::vector<QCopy> up;        // deferred uploads (small slabs), issued merged at submit
   bool open = false, in_flight = false;
   cudaEvent_t e_in = nullptr, e_done = nullptr, e_out = nullptr;
   DBuf<float> d_in, d_out;
@@ -71,7 +79,28 @@ static int pinned_grow(sosie_ctx* ctx, void** p, size_t* have, size_t want_bytes
   return SOSIE_OK;
 }
 
+// page-locked ranges this library created or registered itself (sosie_host_alloc / sosie_host_register): looked up without
+// a driver call; anything else is asked of the driver (cudaPointerGetAttributes, ~1 us)
+namespace {
+struct PinRange { const char* lo; const char* hi; };
+std::mutex g_pin_mu;
+std::vector<PinRange> g_pins;
+}  // namespace
+void pin_registry_add(const void* p, size_t bytes) {
+  std::lock_guard<std::mutex> g(g_pin_mu);
+  g_pins.push_back({(const char*)p, (const char*)p + bytes});
+}
+void pin_registry_remove(const void* p) {
+  std::lock_guard<std::mutex> g(g_pin_mu);
+  for (size_t i = 0; i < g_pins.size(); i++)
+    if (g_pins[i].lo == (const char*)p) { g_pins.erase(g_pins.begin() + i); return; }
+}
 static bool is_pinned(const void* p) {
+  {
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    for (const PinRange& r : g_pins)
+      if ((const char*)p >= r.lo && (const char*)p < r.hi) return true;
+  }
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
   return a.type == cudaMemoryTypeHost;
@@ -136,6 +165,8 @@ static int queue_submit(sosie_ctx* ctx, SosieQueue* q, QBatch& B) {
   const int cnt = (int)B.items.size();
   if (cnt == 0) { B.op = Q_NONE; return SOSIE_OK; }
   cudaStream_t sc = ctx->stream;
+  for (const QCopy& c : B.up) CK(cudaMemcpyAsync(c.d, c.h, c.bytes, cudaMemcpyHostToDevice, q->h2d));
+  B.up.clear();
   CK(cudaEventRecord(B.e_in, q->h2d));
   CK(cudaStreamWaitEvent(sc, B.e_in, 0));
   float* res = B.d_out.p;
@@ -155,10 +186,20 @@ static int queue_submit(sosie_ctx* ctx, SosieQueue* q, QBatch& B) {
   CK(cudaStreamWaitEvent(q->d2h, B.e_done, 0));
   size_t k0 = 0, kcnt = B.n_out;
   if (B.op == Q_BILIN) shard_range(ctx, &k0, &kcnt);   // a sharded context owns (and returns) only its target rows
-  for (int i = 0; i < cnt; i++) {
+  for (int i = 0; i < cnt && kcnt; ) {
+    // results that are adjacent on both sides (consecutive levels of a cube, whole slabs) come back in one copy
     QItem& it = B.items[i];
-    float* hd = it.stage_out ? it.stage_out : it.dst;
-    if (kcnt) CK(cudaMemcpyAsync(hd + k0, res + (size_t)i * B.n_out + k0, kcnt * sizeof(float), cudaMemcpyDeviceToHost, q->d2h));
+    float* hd = (it.stage_out ? it.stage_out : it.dst) + k0;
+    size_t run = kcnt;
+    int j = i + 1;
+    if (kcnt == B.n_out)
+      for (; j < cnt; j++) {
+        QItem& nx = B.items[j];
+        if ((nx.stage_out ? nx.stage_out : nx.dst) != hd + run) break;
+        run += kcnt;
+      }
+    CK(cudaMemcpyAsync(hd, res + (size_t)i * B.n_out + k0, run * sizeof(float), cudaMemcpyDeviceToHost, q->d2h));
+    i = j;
   }
   CK(cudaEventRecord(B.e_out, q->d2h));
   B.in_flight = true;
@@ -207,6 +248,7 @@ static int queue_open(sosie_ctx* ctx, SosieQueue* q, int op, const BdParams* bd,
   if (op == Q_BDROWN) CK(B->d_mask.alloc(n_in * q->cap));
   else CK(B->d_out.alloc(n_out * q->cap));
   B->items.clear();
+  B->up.clear();
   B->open = true;
   *out = B;
   return SOSIE_OK;
@@ -217,15 +259,22 @@ template <class T>
 static int queue_upload(sosie_ctx* ctx, SosieQueue* q, T* dslot, const T* src, size_t off, size_t cnt, T** hring, size_t* hring_n,
                         size_t slab_elems, int slot) {
   if (cnt == 0) return SOSIE_OK;
-  if (is_pinned(src)) {
-    CK(cudaMemcpyAsync(dslot + off, src + off, cnt * sizeof(T), cudaMemcpyHostToDevice, q->h2d));
+  const T* hsrc = src;
+  if (!is_pinned(src)) {
+    if (int rc = pinned_grow(ctx, (void**)hring, hring_n, slab_elems * (size_t)q->cap * sizeof(T))) return rc;
+    T* hs = *hring + (size_t)slot * slab_elems;
+    memcpy(hs + off, src + off, cnt * sizeof(T));
+    q->n_staged_in++;
+    hsrc = hs;
+  }
+  if (cnt * sizeof(T) < Q_DEFER_BYTES) {
+    std::vector<QCopy>& up = q->b[q->cur].up;
+    if (!up.empty() && (const char*)up.back().h + up.back().bytes == (const char*)(hsrc + off) &&
+        (char*)up.back().d + up.back().bytes == (char*)(dslot + off)) up.back().bytes += cnt * sizeof(T);
+    else up.push_back({dslot + off, hsrc + off, cnt * sizeof(T)});
     return SOSIE_OK;
   }
-  if (int rc = pinned_grow(ctx, (void**)hring, hring_n, slab_elems * (size_t)q->cap * sizeof(T))) return rc;
-  T* hs = *hring + (size_t)slot * slab_elems;
-  memcpy(hs + off, src + off, cnt * sizeof(T));
-  q->n_staged_in++;
-  CK(cudaMemcpyAsync(dslot + off, hs + off, cnt * sizeof(T), cudaMemcpyHostToDevice, q->h2d));
+  CK(cudaMemcpyAsync(dslot + off, hsrc + off, cnt * sizeof(T), cudaMemcpyHostToDevice, q->h2d));
   return SOSIE_OK;
 }
 
@@ -324,10 +373,12 @@ int sosie_bdrown_enqueue(sosie_ctx* c, int32_t k_ew, int32_t ni, int32_t nj, flo
 void* sosie_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  pin_registry_add(p, bytes);
   return p;
 }
 int sosie_host_free(void* p) {
   if (!p) return SOSIE_OK;
+  pin_registry_remove(p);
   return cudaFreeHost(p) == cudaSuccess ? SOSIE_OK : SOSIE_ERR_CUDA;
 }
 

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--what", default="applyD")
 ap.add_argument("--slabs", type=int, default=292)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--tma", type=int, default=1, help="0: batched apply on the cp.async-staged kernel only")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 ctx = sosie_b200.Sosie(0)
@@ -34,7 +35,9 @@ if a.what == "applyD":
     print("source rows touched:", jP.min(), jP.max(), "of", cfg["nys"])
     Z1 = torch.rand((S, cfg["nys"], cfg["nxs"]), device=dev) * 80 + 230
     Z2 = torch.empty((S, cfg["nyt"], cfg["nxt"]), device=dev)
+    ctx.apply_tma(int(a.tma))
     ctx.bilin_apply_dev(S, Z1, Z2, first_call=True)
+    print("tile classes (tma, other):", ctx.apply_tile_classes(), "tma", a.tma)
     ts = []
     for _ in range(a.reps):
         ctx.bilin_apply_dev(S, Z1, Z2)
