@@ -94,6 +94,13 @@ int sosie_bilin_set_grids_dev(sosie_ctx* ctx, int32_t k_ew_per,
                               int32_t nx2, int32_t ny2, const double* dX20, const double* dY20, int32_t trg_1d,
                               const int32_t* dmask_domain_trg, int32_t i_orca_trg);
 
+/* A device-resident caller that also holds the (small) 1-D source axes on the host declares them here: the following
+ * sosie_bilin_set_grids_dev calls with src_1d != 0 and the same extents then take the host-side decisions of BILIN_2D's
+ * prologue (pole extension :113-148, sortedness, uniform-axis hints) from this copy instead of reading the device arrays back
+ * -- with sosie_bilin_map_async the whole grids -> mapping -> apply sequence is then free of host round trips.  The copy
+ * MUST equal the device arrays (SOSIE_VERIFY_HINTS=1 in the environment checks it on every call); NULL pointers clear it.  */
+int sosie_bilin_src_axes_hint(sosie_ctx* ctx, int32_t nx1, int32_t ny1, const double* X10_host, const double* Y10_host);
+
 /* FIND_NEAREST_POINT, src/mod_manip.f90:834-963, as the public procedure ij_from_lon_lat.f90:290 calls: for every target
  * point the (i,j) of the nearest source point, -1 where the target was not searched (masked, outside the source's
  * latitude range) or not found.  All four coordinate arrays are 2-D, (nx,ny) column-major, as the assumed-shape
@@ -107,6 +114,20 @@ int sosie_find_nearest_point(sosie_ctx* ctx, int32_t nx_t, int32_t ny_t, const d
 /* MAPPING_BL (:366-691): builds, on device, metrics(nx2,ny2,3)=(iP,jP,iqdrn), alphabeta(nx2,ny2,2),
  * ID_problem(nx2,ny2) and distance_to_np(nx2,ny2), and keeps them cached in the context.          */
 int sosie_bilin_map(sosie_ctx* ctx);
+/* the same for device-resident callers, without any host round trip when the source is regular and given as 1-D axes (the
+ * EASY search): the prelude of FIND_NEAREST_POINT (:888-947) is reduced AND decided on the device, the search kernel reads
+ * its row range from there.  Returns after enqueueing; what sosie_bilin_map would have reported (rows not covered by the
+ * source, L_InPoly's STOP, nearest point not found) is returned by the next synchronising entry of the context: sosie_sync,
+ * sosie_bilin_map_info, sosie_bilin_get_map, the host-pointer applies.  Other source kinds behave like sosie_bilin_map.  */
+int sosie_bilin_map_async(sosie_ctx* ctx);
+/* device-side prelude exchange of row-sharded mappings on resident grids (sosie_bilin_map[_async] on a context with
+ * sosie_bilin_set_shard): each rank reduces only ITS target rows and the ranks all-gather one record each (32 bytes + 24 per
+ * target column) GPU -> GPU.  fn(user, dsend, drecv, bytes, cuda_stream) must ENQUEUE on cuda_stream an all-gather of `bytes`
+ * bytes from every rank into drecv (nranks * bytes, any rank order; ncclAllGather, torch.distributed.all_gather_into_tensor)
+ * and return 0; it is called once per mapping, by every rank.  The merged prelude equals the one of a pass over the whole
+ * array (min / max / first occurrence in row order).  fn = NULL switches it off (every rank then reduces the whole array). */
+typedef int (*sosie_allgather_dev_fn)(void* user, const void* dsend, void* drecv, size_t bytes_per_rank, void* cuda_stream);
+int sosie_set_exchange_dev(sosie_ctx* ctx, int32_t nranks, sosie_allgather_dev_fn fn, void* user);
 /* copy the cached mapping to host arrays (what P2D_MAPPING_AB, src/io_ezcdf.f90:2195, writes).
  * Any pointer may be NULL.  mask_out receives mask_domain_trg as modified by the search (-1/-2).
  * A sharded context (sosie_bilin_set_shard) copies only its own target rows; the others are left untouched. */

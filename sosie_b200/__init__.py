@@ -21,7 +21,7 @@ import os
 
 import numpy as np
 
-__all__ = ["Sosie", "SosieError", "lib_path", "load_library", "EXPORTS", "mapping_write_bin", "mapping_read_bin", "host_alloc", "host_free"]
+__all__ = ["Sosie", "SosieError", "lib_path", "load_library", "EXPORTS", "mapping_write_bin", "mapping_read_bin", "host_alloc", "host_free", "RawDevice"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -47,6 +47,7 @@ EXPORTS = [
     "sosie_track_interp", "sosie_track_interp_dev", "sosie_set_exchange", "sosie_exchange_used", "sosie_find_nearest_point",
     "sosie_bilin_apply_enqueue", "sosie_akima_apply_enqueue", "sosie_bdrown_enqueue", "sosie_flush", "sosie_set_queue_depth",
     "sosie_queue_stats", "sosie_host_alloc", "sosie_host_free", "sosie_apply_tma", "sosie_apply_tile_classes", "sosie_selftest_div",
+    "sosie_bilin_map_async", "sosie_set_exchange_dev", "sosie_bilin_src_axes_hint",
 ]
 
 _lib = None
@@ -129,6 +130,14 @@ def host_free(arr):
 
 
 _pinned = {}
+
+
+class RawDevice:
+    """a raw device address as a __cuda_array_interface__ object: torch.as_tensor(RawDevice(ptr, nbytes), device=...) gives a
+    uint8 tensor VIEW of library-owned device memory (used by the exchange callbacks)"""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
 
 
 def _dp(t):
@@ -277,6 +286,14 @@ class Sosie:
                                                      int(l_reg_src), nx2, ny2, _dp(dX20), _dp(dY20), int(trg_1d), _dp(dmask),
                                                      int(i_orca_trg)))
 
+    def bilin_src_axes_hint(self, X10=None, Y10=None):
+        """declare the host copy of device-resident 1-D source axes (sosie_bilin_src_axes_hint); no arguments clear it"""
+        if X10 is None or Y10 is None:
+            self._ck(self._lib.sosie_bilin_src_axes_hint(self._h, 0, 0, None, None))
+            return
+        X10, Y10 = _f64(X10), _f64(Y10)
+        self._ck(self._lib.sosie_bilin_src_axes_hint(self._h, X10.size, Y10.size, _p(X10), _p(Y10)))
+
     def find_nearest_point(self, Xtrg, Ytrg, Xsrc, Ysrc, mask_domain_trg=None):
         """FIND_NEAREST_POINT (src/mod_manip.f90:834): 2-D coordinate arrays in, (JIp, JJp, mask) out; mask is None when
         mask_domain_trg is not given (the OPTIONAL dummy absent)."""
@@ -294,6 +311,31 @@ class Sosie:
     def bilin_map(self):
         """MAPPING_BL on device."""
         self._ck(self._lib.sosie_bilin_map(self._h))
+
+    def bilin_map_async(self):
+        """MAPPING_BL enqueued on the context stream; with a regular 1-D source nothing is read back (status at the next sync())"""
+        self._ck(self._lib.sosie_bilin_map_async(self._h))
+
+    ALLGATHER_DEV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+    def set_exchange_dev(self, nranks, allgather):
+        """device-side prelude exchange of row-sharded mappings (sosie_set_exchange_dev).  allgather(dsend, drecv, nbytes, stream):
+        raw device addresses / cudaStream_t as ints; must enqueue an all-gather of nbytes bytes per rank on that stream."""
+        if allgather is None:
+            self._xchg_dev_cb = None
+            self._ck(self._lib.sosie_set_exchange_dev(self._h, 0, None, None))
+            return
+
+        def _cb(user, dsend, drecv, nbytes, stream):
+            try:
+                allgather(int(dsend), int(drecv), int(nbytes), int(stream or 0))
+                return 0
+            except Exception:  # noqa: BLE001 - reported through the C return code
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._xchg_dev_cb = self.ALLGATHER_DEV_FN(_cb)   # keep the trampoline alive
+        self._ck(self._lib.sosie_set_exchange_dev(self._h, int(nranks), self._xchg_dev_cb, None))
 
     def bilin_get_map(self):
         nx1, ny1, nx2, ny2 = self._shape

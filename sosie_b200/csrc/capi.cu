@@ -68,7 +68,7 @@ int sosie_set_stream(sosie_ctx* c, void* s) {
 int sosie_sync(sosie_ctx* c) {
   NEED(c);
   CK(cudaStreamSynchronize(ctx->stream));
-  return SOSIE_OK;
+  return bilin_map_check(ctx);   // status of a sosie_bilin_map_async that has not been delivered yet
 }
 
 int64_t sosie_launch_count(const sosie_ctx* c) { return c ? c->launches : 0; }
@@ -165,12 +165,39 @@ int sosie_bilin_set_grids_dev(sosie_ctx* c, int32_t k_ew, int32_t nx1, int32_t n
   size_t nsx = src_1d ? (size_t)nx1 : (size_t)nx1 * ny1, nsy = src_1d ? (size_t)ny1 : (size_t)nx1 * ny1;
   size_t ntx = trg_1d ? (size_t)nx2 : (size_t)nx2 * ny2, nty = trg_1d ? (size_t)ny2 : (size_t)nx2 * ny2;
   ctx->s_in_X.borrow(dX10, nsx); ctx->s_in_Y.borrow(dY10, nsy); ctx->t_X.borrow(dX20, ntx); ctx->t_Y.borrow(dY20, nty);
-  return set_grids_common(ctx, k_ew, nx1, ny1, src_1d, l_reg_src, nx2, ny2, trg_1d, dmask, true, i_orca_trg);
+  ctx->axes_hint_dev = src_1d != 0;
+  const int rc = set_grids_common(ctx, k_ew, nx1, ny1, src_1d, l_reg_src, nx2, ny2, trg_1d, dmask, true, i_orca_trg);
+  ctx->axes_hint_dev = false;
+  return rc;
+}
+
+int sosie_bilin_src_axes_hint(sosie_ctx* c, int32_t nx1, int32_t ny1, const double* X10_host, const double* Y10_host) {
+  NEED(c);
+  ctx->axes_hint.clear();
+  if (!X10_host || !Y10_host) return SOSIE_OK;
+  if (nx1 < 3 || ny1 < 3) { ctx->err = "sosie_bilin_src_axes_hint: bad extents"; return SOSIE_ERR_ARG; }
+  ctx->axes_hint.resize((size_t)nx1 + ny1);
+  memcpy(ctx->axes_hint.data(), X10_host, sizeof(double) * nx1);
+  memcpy(ctx->axes_hint.data() + nx1, Y10_host, sizeof(double) * ny1);
+  ctx->axes_hint_verify = getenv("SOSIE_VERIFY_HINTS") != nullptr;
+  return SOSIE_OK;
 }
 
 int sosie_bilin_map(sosie_ctx* c) {
   NEED(c);
-  return bilin_map_impl(ctx);
+  return bilin_map_impl(ctx, false);
+}
+
+int sosie_bilin_map_async(sosie_ctx* c) {
+  NEED(c);
+  return bilin_map_impl(ctx, true);
+}
+
+int sosie_set_exchange_dev(sosie_ctx* c, int32_t nranks, sosie_allgather_dev_fn fn, void* user) {
+  NEED(c);
+  if (fn && (nranks < 1 || nranks > 256)) { ctx->err = "sosie_set_exchange_dev: nranks must be in 1..256"; return SOSIE_ERR_ARG; }
+  ctx->xchg_dev_fn = fn; ctx->xchg_dev_user = user; ctx->xchg_dev_nranks = fn ? nranks : 0;
+  return SOSIE_OK;
 }
 
 // FIND_NEAREST_POINT as a procedure of its own (src/mod_manip.f90:834-963; called directly by ij_from_lon_lat.f90:290)
@@ -203,12 +230,14 @@ int sosie_find_nearest_point(sosie_ctx* c, int32_t nx_t, int32_t ny_t, const dou
 int sosie_bilin_map_info(sosie_ctx* c, int32_t* info) {
   NEED(c);
   if (!info) return SOSIE_ERR_ARG;
+  if (int rc = bilin_map_check(ctx)) return rc;
   for (int k = 0; k < 8; k++) info[k] = ctx->map_info[k];
   return SOSIE_OK;
 }
 
 int sosie_bilin_get_map(sosie_ctx* c, int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np, int32_t* mask_out) {
   NEED(c);
+  if (int rc = bilin_map_check(ctx)) return rc;
   if (!ctx->map_ready) { ctx->err = "sosie_bilin_get_map: no mapping"; return SOSIE_ERR_STATE; }
   size_t k0, kcnt;
   shard_range(ctx, &k0, &kcnt);  // a sharded context only owns (and only copies) its rows
@@ -363,6 +392,7 @@ static int apply_host_run(sosie_ctx* ctx, ApplyPipe& P, int nslab, const float* 
 
 static int apply_host(sosie_ctx* ctx, int nslab, const float* Z1, float* Z2, int first_call) {
   if (!ctx->grids_set) { ctx->err = "sosie_bilin_apply: grids not set"; return SOSIE_ERR_STATE; }
+  if (int rc = bilin_map_check(ctx)) return rc;
   if (nslab <= 0) return SOSIE_OK;
   ApplyPipe P;
   int rc = apply_host_run(ctx, P, nslab, Z1, Z2, first_call);

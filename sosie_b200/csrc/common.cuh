@@ -103,7 +103,11 @@ struct sosie_ctx {
   int (*xchg_fn)(void*, const void*, void*, size_t) = nullptr;
   void* xchg_user = nullptr;
   int xchg_nranks = 0;
-  int xchg_used = 0;            // 1: the last pipelined first call took the exchange path
+  int xchg_used = 0;            // 1: the last pipelined first call / device-planned mapping took the exchange path
+  int (*xchg_dev_fn)(void*, const void*, void*, size_t, void*) = nullptr;   // device-side all-gather (sosie_set_exchange_dev)
+  void* xchg_dev_user = nullptr;
+  int xchg_dev_nranks = 0;
+  bool map_check_pending = false;   // a device-planned mapping whose status (errors, map_info) has not been read back yet
   bool trg_partial = false;     // the pipelined first call of a sharded context left only part of the target coordinates in HBM
   // ---- per-kernel CUDA-event timing (sosie_profile / sosie_get_timing)
   bool prof = false;
@@ -155,6 +159,15 @@ struct sosie_ctx {
   int32_t map_info[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   int easy_sorted_lon = 0, easy_sorted_lat = 0;
   std::vector<double> h_axes;    // host copy of a 1-D source's axes: lon(nx), working lat(nyw)
+  std::vector<double> axes_hint; // sosie_bilin_src_axes_hint: the caller's host copy of device-resident 1-D source axes
+  bool axes_hint_dev = false;    // this set_grids call may use it (device-pointer entry only)
+  bool axes_hint_verify = false; // SOSIE_VERIFY_HINTS: read the device axes back and compare
+  // source tables of the previous set_grids, reusable while the hinted axes, k_ew and the pole extension stay the same
+  bool tables_valid = false, tables_reused = false, easy_valid = false;
+  int tables_kew = 0, tables_extra = 0, tables_lonm_same = 0;
+  const double* tables_Xin = nullptr;
+  std::vector<double> tables_axes;
+  double easy_hint[4] = {0, 0, 0, 0};
   int l_last_y_row_missing = 0;
 
   // ---- akima state
@@ -313,7 +326,8 @@ int fetch_pair(sosie_ctx* ctx, const void* d1, void* h1, size_t b1, const void* 
 
 // entry points implemented in the other translation units
 int bilin_materialize_mask(sosie_ctx* ctx);   // fills t_mask with 1 if it is still virtual
-int bilin_map_impl(sosie_ctx* ctx);
+int bilin_map_impl(sosie_ctx* ctx, bool async = false);
+int bilin_map_check(sosie_ctx* ctx);          // delivers the deferred status of sosie_bilin_map_async (one read-back)
 int bilin_map_alloc(sosie_ctx* ctx);
 int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool* need_full_x);
 // rows ja..jb (1-based) reduced here, the rest obtained from the other ranks; *undecided: fall back to the full prelude

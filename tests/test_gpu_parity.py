@@ -621,3 +621,104 @@ def test_akima_orca_fold_frame_under_a_polar_target(gpu, orc, piv, iorca, nx, ny
             gpu.akima_untiled_slopes(False)
         assert np.array_equal(gpu.akima_get_ixy(), ixy)
         assert np.array_equal(Z2g, Z2o), f"{(Z2g != Z2o).sum()} of {Z2o.size} points differ"
+
+
+def test_async_mapping_defers_its_status(gpu, orc):
+    """sosie_bilin_map_async on a regular 1-D source: nothing is read back; mapping identical to the synchronous call; an
+    error the synchronous call returns at once (L_InPoly's STOP on negative longitudes) comes out of the next sync()"""
+    import sosie_b200
+    cfg = G.config("E", 0.02)
+    Xs, Ys = G.src_2d(cfg)
+    Z1 = G.field_slabs(Xs, Ys, 1, seed=3)
+    gpu.bilin_set_shard(0, 0)
+    gpu.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"], l_reg_src=True)
+    gpu.bilin_map()
+    m_sync = gpu.bilin_get_map()
+    z_sync = gpu.bilin_apply(Z1, first_call=True)
+    gpu.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"], l_reg_src=True)
+    gpu.bilin_map_async()
+    z_async = gpu.bilin_apply(Z1, first_call=True)        # a synchronising entry: delivers the (clean) status first
+    m_async = gpu.bilin_get_map()
+    for k in ("metrics", "alphabeta", "ipb", "dist_np", "info"):
+        assert np.array_equal(m_sync[k], m_async[k]), k
+    assert np.array_equal(z_sync, z_async)
+    Z2o, mo = orc.bilin_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"], l_reg_src=True)
+    assert np.array_equal(m_async["metrics"], mo["metrics"]) and tuple(m_async["info"][:3]) == tuple(mo["info"][:3])
+    # the same from device-resident grids with the host copy of the axes declared: no read-back at all until sync()
+    import torch
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"])]
+    dZ1 = torch.from_numpy(Z1).to(dev)
+    dZ2 = torch.zeros((1, cfg["nyt"], cfg["nxt"]), device=dev, dtype=torch.float32)
+    torch.cuda.synchronize()
+    try:
+        gpu.bilin_src_axes_hint(cfg["src_lon"], cfg["src_lat"])
+        for _ in range(3):
+            gpu.bilin_set_grids_dev(cfg["ewper_src"], cfg["nxs"], cfg["nys"], d[0], d[1], 1, cfg["nxt"], cfg["nyt"], d[2], d[3], 0, None, l_reg_src=True)
+            gpu.bilin_map_async()
+            gpu.bilin_apply_dev(1, dZ1, dZ2, first_call=True)
+        gpu.sync()
+        assert np.array_equal(dZ2.cpu().numpy(), z_sync)
+        assert np.array_equal(gpu.bilin_get_map()["metrics"], m_sync["metrics"])
+    finally:
+        gpu.bilin_src_axes_hint()
+    # deferred error
+    lon_s = np.linspace(-20.0, 20.0, 41); lat_s = np.linspace(-10.0, 10.0, 21)
+    Xt, Yt = G.expand_2d(np.linspace(-5.0, 5.0, 7), np.linspace(-3.0, 3.0, 5))
+    Xt = Xt + 0.01 * Yt
+    gpu.bilin_set_grids(-1, lon_s, lat_s, Xt, Yt)
+    gpu.bilin_map_async()                                   # returns OK: nothing has been read back
+    with pytest.raises(sosie_b200.SosieError, match="positive longitudes"):
+        gpu.sync()
+    with pytest.raises(sosie_b200.SosieError, match="error 3"):      # the failed mapping is not usable
+        gpu.bilin_apply(np.zeros((1, 21, 41), np.float32))
+
+
+def test_device_side_prelude_exchange(gpu, orc):
+    """row-sharded mappings on resident grids with sosie_set_exchange_dev: each 'rank' (a context on this GPU) reduces only its
+    rows; the all-gather is emulated in two passes (pass 1 collects every rank's record, pass 2 hands the complete set to each
+    rank) -- the merged prelude and the mapping rows equal the unsharded ones, also when the prelude cuts the searched rows"""
+    import torch
+
+    import sosie_b200
+    from sosie_b200.shard import row_shard
+    dev = torch.device("cuda", 0)
+    cfg = G.config("E", 0.02)
+    lat_hi = G.regular_latlon(cfg["nxs"], cfg["nys"])[1]
+    cases = [(cfg["src_lat"], True), (lat_hi[: int(0.74 * cfg["nys"])], False)]    # full sphere; a source that stops short of the target's top rows
+    for src_lat, l_reg in cases:
+        gpu.bilin_set_shard(0, 0)
+        gpu.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], src_lat, cfg["trg_lon"], cfg["trg_lat"], l_reg_src=l_reg)
+        gpu.bilin_map()
+        ref = gpu.bilin_get_map()
+        world = 3
+        store = {}
+        for npass in (1, 2):
+            for r in range(world):
+                ctx = sosie_b200.Sosie(0)
+                try:
+                    j0, j1 = row_shard(cfg["nyt"], r, world)
+                    ctx.bilin_set_shard(j0, j1)
+
+                    def ag(dsend, drecv, nbytes, stream, r=r):
+                        src = torch.as_tensor(sosie_b200.RawDevice(dsend, nbytes), device=dev)
+                        dst = torch.as_tensor(sosie_b200.RawDevice(drecv, nbytes * world), device=dev)
+                        with torch.cuda.stream(torch.cuda.ExternalStream(stream)):
+                            store[r] = src.clone()
+                            for q in range(world):
+                                dst[q * nbytes:(q + 1) * nbytes].copy_(store.get(q, store[r]))
+                    ctx.set_exchange_dev(world, ag)
+                    ctx.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], src_lat, cfg["trg_lon"], cfg["trg_lat"], l_reg_src=l_reg)
+                    ctx.bilin_map_async()
+                    if npass == 2:
+                        ctx.sync()
+                        assert ctx.exchange_used()
+                        m = ctx.bilin_get_map()
+                        assert np.array_equal(m["info"], ref["info"]), (m["info"], ref["info"])
+                        for k in ("metrics", "alphabeta"):
+                            assert np.array_equal(m[k][:, j0 - 1:j1], ref[k][:, j0 - 1:j1]), (k, r)
+                        assert np.array_equal(m["ipb"][j0 - 1:j1], ref["ipb"][j0 - 1:j1])
+                    else:
+                        torch.cuda.synchronize()
+                finally:
+                    ctx.close()
