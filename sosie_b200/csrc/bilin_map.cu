@@ -571,44 +571,63 @@ static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double 
 // iterations each made the whole warp execute the 18-term polynomial again: ~10 executions per warp.)  A second
 // candidate within the margin of the best -- equidistant source points, the rows at and beyond the pole -- sends the
 // target to the exact scan above, which evaluates and compares distances like the reference.
+// acl: an upper bound of |ux*clon_i + uy*slon_i| over every column (|cos(lat_t)| plus a few ulp, unit_vec_cp): a row whose
+//   best conceivable dot product |clat_j|*acl + uz*slat_j stays below the running best is skipped without touching its
+//   columns (r01 kept the nine column terms a[0..8] in registers across the row loop for this: 18 registers, spills).
+// unimodal: the longitudes of the window are sorted and within 90 degrees of the target's, so along a row with clat_j >= 0
+//   the dot product decreases on both sides of the index-nearest column ic: the columns are visited outwards from ic and a
+//   side is abandoned at the first column the cheap form rejects -- every column beyond it is smaller still in exact
+//   arithmetic, and the 1e-14 slack of the rejection threshold (25x the rounding of either form) covers the evaluation.
+//   Typically 3-4 column evaluations per surviving row instead of 9.
 template <bool SEP>
 __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
-                                            int j2, Best& b, int ic, int jc) {
+                                            int j2, Best& b, int ic, int jc, double acl = 1.0, bool unimodal = false, bool rows_unimodal = false) {
   if (!SEP) { scan_window_exact<SEP>(sg, ux, uy, uz, i1, i2, j1, j2, b, ic, jc); return; }
   ic = min(max(ic, i1), i2);
   jc = min(max(jc, j1), j2);
-  double a[9];
-  double amax = -4.0, amin = 4.0;
-#pragma unroll
-  for (int q = 0; q < 9; q++) {
-    int ji = min(i1 + q, i2);
-    a[q] = ux * sg.clon[ji - 1] + uy * sg.slon[ji - 1];
-    amax = fmax(amax, a[q]); amin = fmin(amin, a[q]);
-  }
-  const int nq = i2 - i1 + 1;
   double p1, p2 = -4.0;   // largest and second largest exact u.v met so far
   int bi = ic, bj = jc;
   {
     const double cl = sg.clat[jc - 1], sl = sg.slat[jc - 1];
     p1 = ux * (sg.clon[ic - 1] * cl) + uy * (sg.slon[ic - 1] * cl) + uz * sl;
   }
-  for (int jj = j1; jj <= j2; jj++) {
-    const double cl = sg.clat[jj - 1], sl = sg.slat[jj - 1];
+  // rows: with a sorted latitude axis the row bound |clat_j|*acl + uz*slat_j (the cosine of the target's distance to the
+  // row's parallel) falls off on both sides of the index-nearest row jc, so the rows are visited outwards from jc as well
+  // and a side is abandoned at the first row the bound rejects (rows_unimodal); otherwise all rows j1..j2 are tested.
+  // visit order: jc, jc+1, ..., j2 (or the first reject), then jc-1, ..., j1 (or the first reject)
+  const int nrows = j2 - j1 + 1;
+  int jj = rows_unimodal ? jc : j1, dir = 1;
+  for (int it = 0; it < nrows; it++) {
+    if (jj > j2) {                    // (upward side exhausted)
+      if (!rows_unimodal || dir < 0) break;
+      dir = -1; jj = jc - 1;
+    }
+    if (jj < j1) break;
+    const int jrow = jj;
+    jj += dir;
+    const double cl = sg.clat[jrow - 1], sl = sg.slat[jrow - 1];
     const double c0 = uz * sl;
     const double thr = p1 - (PDS_MARGIN + 1.0e-14);
-    if (((cl >= 0.0) ? cl * amax : cl * amin) + c0 < thr) continue;
-    unsigned surv = 0;
-#pragma unroll
-    for (int q = 0; q < 9; q++)
-      if (q < nq && !(cl * a[q] + c0 < thr)) surv |= 1u << q;
-    if (jj == jc) surv &= ~(1u << (ic - i1));  // the centre seeded p1
-    while (surv) {
-      const int q = __ffs(surv) - 1;
-      surv &= surv - 1;
-      const int ji = i1 + q;
-      const double zpds = ux * (sg.clon[ji - 1] * cl) + uy * (sg.slon[ji - 1] * cl) + uz * sl;
-      if (zpds > p1) { p2 = p1; p1 = zpds; bi = ji; bj = jj; }
+    if (fabs(cl) * acl + c0 < thr) {
+      if (!rows_unimodal) continue;
+      if (dir > 0) { dir = -1; jj = jc - 1; continue; }
+      break;
+    }
+    auto cand = [&](int ji) -> bool {   // false: the cheap form rejects the column
+      const double c = sg.clon[ji - 1], s = sg.slon[ji - 1];
+      if (cl * (ux * c + uy * s) + c0 < thr) return false;
+      const double zpds = ux * (c * cl) + uy * (s * cl) + uz * sl;
+      if (zpds > p1) { p2 = p1; p1 = zpds; bi = ji; bj = jrow; }
       else p2 = fmax(p2, zpds);
+      return true;
+    };
+    if (unimodal && cl >= 0.0) {
+      if (jrow != jc) { if (!cand(ic)) continue; }   // (on row jc the centre seeded p1)
+      for (int ji = ic + 1; ji <= i2; ji++) if (!cand(ji)) break;
+      for (int ji = ic - 1; ji >= i1; ji--) if (!cand(ji)) break;
+    } else {
+      for (int ji = i1; ji <= i2; ji++)
+        if (!(jrow == jc && ji == ic)) cand(ji);
     }
   }
   if (p2 >= p1 - PDS_MARGIN) { scan_window_exact<SEP>(sg, ux, uy, uz, i1, i2, j1, j2, b, ic, jc); return; }
@@ -852,10 +871,12 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
       int jp = sorted_lat ? minloc_abs_sorted(vlat, sg.nyw, rlat, sg.lat0, sg.inv_dlat) : minloc_abs_linear(vlat, sg.nyw, rlat);
       int i1s = max(ip - 4, 1), i2s = min(ip + 4, sg.nx);
       int j1s = max(jp - 4, 1), j2s = min(jp + 4, sg.nyw);
-      unit_vec(rlon, rlat, ux, uy, uz);
+      double cpt;
+      unit_vec_cp(rlon, rlat, ux, uy, uz, cpt);
       have_u = (fabs(rlon) < 360.0);   // MOD(xP,360) == xP: the body's DISTANCE sees the same longitude
       Best b;
-      scan_window<SEP>(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, ip, jp);
+      const bool unimodal = SEP && sorted_lon && fabs(vlon[i1s - 1] - rlon) <= 90.0 && fabs(vlon[i2s - 1] - rlon) <= 90.0;
+      scan_window<SEP>(sg, ux, uy, uz, i1s, i2s, j1s, j2s, b, ip, jp, fabs(cpt) * (1.0 + 4.0e-15), unimodal, SEP && sorted_lat != 0);
       iP = b.i; jP = b.j; bpds = b.pds; bd = b.d;
       if (iP == 0 || jP == 0) atomicOr(err, 2);
     }

@@ -58,6 +58,20 @@ __device__ __forceinline__ void unit_vec(double lon, double lat, double& ux, dou
   uz = sp;
 }
 
+// the same, also returning cos(lat): |ux*c + uy*s| <= |cp| * (1 + a few ulp) for any (c, s) on the unit circle -- the row
+// bound of the EASY window scan
+__device__ __forceinline__ void unit_vec_cp(double lon, double lat, double& ux, double& uy, double& uz, double& cp_out) {
+  double zlatr = lat * G_ZCONV;
+  double zlonr = lon * G_ZCONV;
+  double sl, cl, sp, cp;
+  pm_sincos(zlonr, &sl, &cl);
+  pm_sincos(zlatr, &sp, &cp);
+  ux = cl * cp;
+  uy = sl * cp;
+  uz = sp;
+  cp_out = cp;
+}
+
 // DISTANCE, src/mod_manip.f90:1443-1504
 __device__ __forceinline__ double d_distance(double plona, double plonb, double plata, double platb) {
   double ux, uy, uz, vx, vy, vz;

@@ -85,7 +85,16 @@ def js(path, out, files):
                     v *= {"us": 1e-3, "ns": 1e-6, "ms": 1.0, "s": 1e3}.get(u, 1.0); u = "ms"
                 d[k] = v
         kernels.setdefault(name, d)      # first launch of each kernel
-    names = [f for f in files.split(",") if f]
+    extra = {}
+    names = []
+    for f in files.split(","):       # "slabs=292"-style items are copied into every kernel's record
+        if "=" in f:
+            k_, v_ = f.split("=", 1)
+            extra[k_] = float(v_) if v_.replace(".", "", 1).isdigit() else v_
+        elif f:
+            names.append(f)
+    for d in kernels.values():
+        d.update(extra)
     head = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
     with open(out, "w") as f:
         json.dump({"source": path, "how": "ncu --set full --clock-control none, one launch per kernel (cold cache, serialised)",
