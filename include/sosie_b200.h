@@ -275,7 +275,10 @@ int sosie_akima_set_grids(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t
                           const double* X20, const double* Y20, int32_t trg_1d);
 int sosie_akima_apply(sosie_ctx* ctx, int32_t nslab, const float* Z1, float* Z2);
 int sosie_akima_apply_dev(sosie_ctx* ctx, int32_t nslab, const float* dZ1, float* dZ2);
-/* test hook: per-point slopes kernel instead of the shared-memory tiled one (identical results) */
+/* test hook (identical results): 0 = default (slope arrays, shared-memory tiled slopes kernel, then the evaluation kernel;
+ * a regular source reads its coordinates from 1-D axes), 1 = per-point slopes kernel, 3 = a regular source runs the fused
+ * kernel (slopes of the source box under a 32x8 tile of targets built in shared memory, then the evaluation: no slope arrays
+ * in HBM -- measured slower on B200, the stage is bound by its REAL(8) divisions: DESIGN.md) */
 int sosie_akima_untiled_slopes(sosie_ctx* ctx, int32_t on);
 /* the SAVE'd ixy_pos(nx2,ny2,2) table (src/mod_akima_2d.f90:41) */
 int sosie_akima_get_ixy(sosie_ctx* ctx, int32_t* ixy_pos);

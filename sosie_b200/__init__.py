@@ -521,7 +521,8 @@ class Sosie:
         self._ck(self._lib.sosie_akima_apply_dev(self._h, int(nslab), _dp(dZ1), _dp(dZ2)))
 
     def akima_untiled_slopes(self, on=True):
-        """test hook: per-point slopes kernel instead of the shared-memory tiled one"""
+        """test hook: 0 default (slope arrays, tiled slopes kernel), 1 per-point slopes kernel, 3 regular sources through the
+        fused slopes + evaluation kernel (no slope arrays)"""
         self._ck(self._lib.sosie_akima_untiled_slopes(self._h, int(on)))
 
     def akima_get_ixy(self):

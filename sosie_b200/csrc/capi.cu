@@ -662,7 +662,8 @@ int sosie_akima_apply(sosie_ctx* c, int32_t nslab, const float* Z1, float* Z2) {
 
 int sosie_akima_untiled_slopes(sosie_ctx* c, int32_t on) {
   NEED(c);
-  ctx->ak_untiled_slopes = on != 0;
+  ctx->ak_untiled_slopes = on == 1;     // 0: tiled slopes kernel + evaluation (default), 1: per-point slopes kernel
+  ctx->ak_fused = on == 3;              // 3: regular sources through the fused slopes + evaluation kernel (no slope arrays)
   return SOSIE_OK;
 }
 

@@ -178,6 +178,9 @@ struct sosie_ctx {
   DBuf<double> ak_X2, ak_Y2;         // target coordinates (2-D)
   DBuf<int32_t> ak_ixy;              // (nx2,ny2,2)
   bool ak_untiled_slopes = false;    // tests: the per-point slopes kernel instead of the shared-memory tiled one
+  bool ak_sep8 = false;              // regular source: twice-extended coordinates are separable -> fused slopes + evaluation kernel
+  bool ak_fused = false;             // sosie_akima_untiled_slopes(3): regular sources take the fused slopes + evaluation kernel
+  DBuf<double> ak_ax8;               // the 1-D axes of the twice-extended grid: x8 (ni1+4), y8 (nj1+4)
   DBuf<uint8_t> ak_needed;           // (nx1+4,ny1+4): source points whose slopes some target reads
   DBuf<double> ak_zF, ak_ZF8, ak_sx, ak_sy, ak_sxy;  // per-slab work arrays
   DBuf<float> ak_stage1, ak_stage2;

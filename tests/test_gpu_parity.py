@@ -191,7 +191,7 @@ def test_akima_vs_oracle(gpu, orc, scale, nslab):
     Xs, Ys = G.src_2d(cfg)
     Z1 = G.field_slabs(Xs, Ys, nslab, seed=6)
     Z2o, ixy = orc.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"])
-    for untiled in (False, True):        # shared-memory tiled slopes (default) and the per-point kernel
+    for untiled in (0, 1, 3):            # tiled slopes (default), per-point slopes, fused slopes + evaluation (regular sources)
         gpu.akima_untiled_slopes(untiled)
         try:
             Z2g = gpu.akima_2d(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], Z1, cfg["trg_lon"], cfg["trg_lat"])
@@ -613,7 +613,7 @@ def test_akima_orca_fold_frame_under_a_polar_target(gpu, orc, piv, iorca, nx, ny
     Xt = np.mod(360.0 * t[None, :] + np.zeros((9, 1)), 360.0)
     Yt = np.linspace(80.0, 89.0, 9)[:, None] + np.zeros((1, 41))
     Z2o, ixy = orc.akima_2d(2, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca)
-    for untiled in (False, True):
+    for untiled in (0, 1, 3):
         gpu.akima_untiled_slopes(untiled)
         try:
             Z2g = gpu.akima_2d(2, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca)
@@ -722,3 +722,41 @@ def test_device_side_prelude_exchange(gpu, orc):
                         torch.cuda.synchronize()
                 finally:
                     ctx.close()
+
+
+@pytest.mark.parametrize("case", ["coarse_target", "fine_target", "regional_D", "outside"])
+def test_akima_fused_kernel_paths(gpu, orc, case):
+    """k_akima_fused: boxes that fit shared memory (target as fine as / finer than the source), boxes that do not (a target far
+    coarser than the source: four corner slopes per target straight from global memory), targets partly outside the source
+    range (zeros), several slabs per block -- all bit-identical to the oracle and to the slope-array kernels"""
+    rng = np.random.default_rng(5)
+    if case == "coarse_target":
+        lon, lat = G.regular_latlon(720, 360)
+        Xt, Yt = G.expand_2d(*G.regular_latlon(40, 20))
+        Xt = Xt + 0.3 * rng.random(Xt.shape); Yt = Yt * 0.97
+        kew, nslab = 0, 3
+    elif case == "fine_target":
+        lon, lat = G.regular_latlon(90, 45)
+        Xt, Yt = G.expand_2d(np.linspace(1.0, 359.0, 700), np.linspace(-85.0, 85.0, 333))
+        kew, nslab = 0, 2
+    elif case == "regional_D":
+        cfg = G.config("D", 0.25)
+        lon, lat, Xt, Yt = cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"]
+        kew, nslab = 0, 5
+    else:
+        lon = np.linspace(10.0, 60.0, 101); lat = np.linspace(-20.0, 30.0, 81)
+        Xt, Yt = G.expand_2d(np.linspace(0.0, 75.0, 230), np.linspace(-30.0, 40.0, 90))
+        kew, nslab = -1, 2
+    Xs, Ys = G.expand_2d(lon, lat)
+    Z1 = G.field_slabs(Xs, Ys, nslab, seed=12)
+    Z2o, ixy = orc.akima_2d(kew, lon, lat, Z1, Xt, Yt)
+    res = {}
+    for mode in (0, 3):
+        gpu.akima_untiled_slopes(mode)
+        try:
+            res[mode] = gpu.akima_2d(kew, lon, lat, Z1, Xt, Yt)
+        finally:
+            gpu.akima_untiled_slopes(0)
+        assert np.array_equal(gpu.akima_get_ixy(), ixy)
+    assert np.array_equal(res[3].view(np.uint32), Z2o.view(np.uint32)), f"fused differs at {(res[3] != Z2o).sum()} points"
+    assert np.array_equal(res[0].view(np.uint32), Z2o.view(np.uint32))

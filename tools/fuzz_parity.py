@@ -189,7 +189,7 @@ def case_akima(gpu, rng, k):
     Xt, Yt = rnd_target(rng, X2, Y2)
     Z1 = G.field_slabs(X2, Y2, int(rng.integers(1, 4)), seed=int(rng.integers(1 << 30)))
     tag = f"akima#{k} src={X2.shape} trg={np.shape(Xt)} kew={kew} iorca={iorca}"
-    gpu.akima_untiled_slopes(bool(rng.random() < 0.3))
+    gpu.akima_untiled_slopes(int(rng.choice([0, 1, 3])))   # tiled slope arrays / per-point slope arrays / fused
     with np.errstate(all="ignore"):
         rg, ro = both(tag, lambda: gpu.akima_2d(kew, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca), lambda: orc.akima_2d(kew, lon_s, lat_s, Z1, Xt, Yt, i_orca_src=iorca)[0])
     if rg is None:

@@ -1,0 +1,6 @@
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/r2q_pytest.log 2>&1; echo pytest_rc=$?; tail -4 gpurun_out/r2q_pytest.log
+for seed in 101 102 103 104 105 106 107 108; do
+timeout 600 python tools/fuzz_parity.py 2500 $seed > gpurun_out/fuzz_r2_$seed.log 2>&1; echo rc=$?
+grep -E "FAIL|ERROR|fuzz:" gpurun_out/fuzz_r2_$seed.log | cut -c1-300 | head -6
+done
+timeout 300 python tools/bench_akima.py 2>&1 | tail -1
