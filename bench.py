@@ -1155,7 +1155,7 @@ def run_ours(args):
             from oracle import oracle as O
             O.build()
             nthr = host_threads()
-            rows = int(min(256, max(16, 2 * nthr)))
+            rows = int(min(ny2, 1024))   # ~10-20 s of CPU work on 16-24 cores; a small sample under-uses the cores (48 rows: 0.24 M points/s, 512 rows: 0.66 M on 24 cores)
             v_all, n_all, dt_all = cpu_reference_sample(cfg, nthr, rows, Z1_host.numpy())
             v_one, n_one, dt_one = cpu_reference_sample(cfg, 1, 4, Z1_host.numpy())
             line["cpu_baseline"] = {
