@@ -54,6 +54,26 @@ __global__ void k_feb_center(const TS* __restrict__ src, int nx, int ny, double*
     d[k] = v;
   }
 }
+// The REAL(4) slab straight into the TWICE-extended array ZF8 (nx+8, ny+8): centre at offset (4,4), zero elsewhere -- the
+// zero + centre initialisation of both FILL_EXTRA_BANDS levels in one pass.  The once-extended array zF of the reference
+// is the view of ZF8 at offset (2,2) with leading dimension nx+8: the level-1 frame kernels below write into that view
+// (ld parameters), so zF is never materialised and never copied (r01: 8 B written + 8 B read + 8 B written per point).
+// ja..jb: rows of ZF8 (1-based) to write.
+__global__ void k_feb_center8(const float* __restrict__ src, int nx, int ny, double* P8, size_t src_stride, size_t dst_stride, int ja, int jb) {
+  const int n8 = nx + 8, m8 = ny + 8;
+  const float* s = src + blockIdx.y * src_stride;
+  double* d = P8 + blockIdx.y * dst_stride;
+  ja = max(ja, 1); jb = min(jb, m8);
+  if (jb < ja) return;
+  const size_t k0 = (size_t)(ja - 1) * n8, n = (size_t)(jb - ja + 1) * n8;
+  for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < n; kk += (size_t)gridDim.x * blockDim.x) {
+    const size_t k = k0 + kk;
+    const int j = (int)(k / n8) + 1, i = (int)(k % n8) + 1;
+    double v = 0.0;
+    if (i >= 5 && i <= n8 - 4 && j >= 5 && j <= m8 - 4) v = (double)s[(size_t)(i - 5) + (size_t)(j - 5) * nx];
+    d[k] = v;
+  }
+}
 // X array: east-west columns on rows 3..nyp4-2 (:148-165)
 __global__ void k_feb_x_ew(double* XP4, int nx, int ny, int k_ew) {
   const int nxp4 = nx + 4;
@@ -124,61 +144,64 @@ __global__ void k_feb_y_ew(double* YP4, int nx, int ny, int k_ew) {
   }
 }
 // Data array: east-west columns on rows 3..nyp4-2 (:245-270); grid.y = slab
-__global__ void k_feb_f_ew(const double* __restrict__ XP4, double* FP4, int nx, int ny, int k_ew, size_t stride) {
+// ldf: leading dimension of the field array (nxp4 for a dense array; larger when FP4 is a view into a bigger array)
+__global__ void k_feb_f_ew(const double* __restrict__ XP4, double* FP4, int nx, int ny, int k_ew, size_t stride, int ldf) {
   const int nxp4 = nx + 4;
   double* F = FP4 + blockIdx.y * stride;
   for (int jj = blockIdx.x * blockDim.x + threadIdx.x + 3; jj <= ny + 2; jj += gridDim.x * blockDim.x) {
     if (k_ew > -1) {
-      A2D(F, nxp4, 1, jj) = A2D(F, nxp4, nx - 1 - k_ew + 2, jj);
-      A2D(F, nxp4, 2, jj) = A2D(F, nxp4, nx - k_ew + 2, jj);
-      A2D(F, nxp4, nxp4, jj) = A2D(F, nxp4, 2 + k_ew + 2, jj);
-      A2D(F, nxp4, nxp4 - 1, jj) = A2D(F, nxp4, 1 + k_ew + 2, jj);
+      A2D(F, ldf, 1, jj) = A2D(F, ldf, nx - 1 - k_ew + 2, jj);
+      A2D(F, ldf, 2, jj) = A2D(F, ldf, nx - k_ew + 2, jj);
+      A2D(F, ldf, nxp4, jj) = A2D(F, ldf, 2 + k_ew + 2, jj);
+      A2D(F, ldf, nxp4 - 1, jj) = A2D(F, ldf, 1 + k_ew + 2, jj);
     } else {
       double y4, y5;
       d_extra_2_east(A2D(XP4, nxp4, nxp4 - 4, jj), A2D(XP4, nxp4, nxp4 - 3, jj), A2D(XP4, nxp4, nxp4 - 2, jj),
-                     A2D(XP4, nxp4, nxp4 - 1, jj), A2D(XP4, nxp4, nxp4, jj), A2D(F, nxp4, nxp4 - 4, jj),
-                     A2D(F, nxp4, nxp4 - 3, jj), A2D(F, nxp4, nxp4 - 2, jj), y4, y5);
-      A2D(F, nxp4, nxp4 - 1, jj) = y4;
-      A2D(F, nxp4, nxp4, jj) = y5;
+                     A2D(XP4, nxp4, nxp4 - 1, jj), A2D(XP4, nxp4, nxp4, jj), A2D(F, ldf, nxp4 - 4, jj),
+                     A2D(F, ldf, nxp4 - 3, jj), A2D(F, ldf, nxp4 - 2, jj), y4, y5);
+      A2D(F, ldf, nxp4 - 1, jj) = y4;
+      A2D(F, ldf, nxp4, jj) = y5;
       double y2, y1;
       d_extra_2_west(A2D(XP4, nxp4, 5, jj), A2D(XP4, nxp4, 4, jj), A2D(XP4, nxp4, 3, jj), A2D(XP4, nxp4, 2, jj),
-                     A2D(XP4, nxp4, 1, jj), A2D(F, nxp4, 5, jj), A2D(F, nxp4, 4, jj), A2D(F, nxp4, 3, jj), y2, y1);
-      A2D(F, nxp4, 2, jj) = y2;
-      A2D(F, nxp4, 1, jj) = y1;
+                     A2D(XP4, nxp4, 1, jj), A2D(F, ldf, 5, jj), A2D(F, ldf, 4, jj), A2D(F, ldf, 3, jj), y2, y1);
+      A2D(F, ldf, 2, jj) = y2;
+      A2D(F, ldf, 1, jj) = y1;
     }
   }
 }
 // Data array: default top (:288-294) and bottom (:297-303) per column; grid.y = slab
-__global__ void k_feb_f_tb(const double* __restrict__ YP4, double* FP4, int nxp4, int nyp4, int do_top, size_t stride) {
+__global__ void k_feb_f_tb(const double* __restrict__ YP4, double* FP4, int nxp4, int nyp4, int do_top, size_t stride, int ldf) {
   double* F = FP4 + blockIdx.y * stride;
   for (int ji = blockIdx.x * blockDim.x + threadIdx.x + 1; ji <= nxp4; ji += gridDim.x * blockDim.x) {
     if (do_top) {
       double y4, y5;
       d_extra_2_east(A2D(YP4, nxp4, ji, nyp4 - 4), A2D(YP4, nxp4, ji, nyp4 - 3), A2D(YP4, nxp4, ji, nyp4 - 2),
-                     A2D(YP4, nxp4, ji, nyp4 - 1), A2D(YP4, nxp4, ji, nyp4), A2D(F, nxp4, ji, nyp4 - 4),
-                     A2D(F, nxp4, ji, nyp4 - 3), A2D(F, nxp4, ji, nyp4 - 2), y4, y5);
-      A2D(F, nxp4, ji, nyp4 - 1) = y4;
-      A2D(F, nxp4, ji, nyp4) = y5;
+                     A2D(YP4, nxp4, ji, nyp4 - 1), A2D(YP4, nxp4, ji, nyp4), A2D(F, ldf, ji, nyp4 - 4),
+                     A2D(F, ldf, ji, nyp4 - 3), A2D(F, ldf, ji, nyp4 - 2), y4, y5);
+      A2D(F, ldf, ji, nyp4 - 1) = y4;
+      A2D(F, ldf, ji, nyp4) = y5;
     }
     double y2, y1;
     d_extra_2_west(A2D(YP4, nxp4, ji, 5), A2D(YP4, nxp4, ji, 4), A2D(YP4, nxp4, ji, 3), A2D(YP4, nxp4, ji, 2),
-                   A2D(YP4, nxp4, ji, 1), A2D(F, nxp4, ji, 5), A2D(F, nxp4, ji, 4), A2D(F, nxp4, ji, 3), y2, y1);
-    A2D(F, nxp4, ji, 2) = y2;
-    A2D(F, nxp4, ji, 1) = y1;
+                   A2D(YP4, nxp4, ji, 1), A2D(F, ldf, ji, 5), A2D(F, ldf, ji, 4), A2D(F, ldf, ji, 3), y2, y1);
+    A2D(F, ldf, ji, 2) = y2;
+    A2D(F, ldf, ji, 1) = y1;
   }
 }
 // ORCA north-fold section copies (:181-190 etc.): P(l0+k*ls, jl) = P(r0+k*rs, jr); RHS staged first
-__global__ void k_sectd_read(const double* P, int n1, int n, int r0, int rs, int jr, double* tmp, size_t stride, int ntmp) {
+__global__ void k_sectd_read(const double* P, int n1, int n, int r0, int rs, int jr, double* tmp, size_t stride, int ntmp, int ld = 0) {
   const double* Q = P + blockIdx.y * stride;
+  if (ld == 0) ld = n1;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     int ir = r0 + k * rs;
-    tmp[(size_t)blockIdx.y * ntmp + k] = (ir >= 1 && ir <= n1) ? A2D(Q, n1, ir, jr) : 0.0;
+    tmp[(size_t)blockIdx.y * ntmp + k] = (ir >= 1 && ir <= n1) ? A2D(Q, ld, ir, jr) : 0.0;
   }
 }
-__global__ void k_sectd_write(double* P, int n1, int n, int l0, int ls, int jl, const double* tmp, size_t stride, int ntmp) {
+__global__ void k_sectd_write(double* P, int n1, int n, int l0, int ls, int jl, const double* tmp, size_t stride, int ntmp, int ld = 0) {
   double* Q = P + blockIdx.y * stride;
+  if (ld == 0) ld = n1;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
-    A2D(Q, n1, l0 + k * ls, jl) = tmp[(size_t)blockIdx.y * ntmp + k];
+    A2D(Q, ld, l0 + k * ls, jl) = tmp[(size_t)blockIdx.y * ntmp + k];
 }
 
 // ---- SLOPES_AKIMA on the twice-extended arrays (:528-653); grid.y = slab -----------------------------
@@ -427,8 +450,10 @@ __global__ void __launch_bounds__(128, AK_EVAL_BLOCKS)
 k_akima_eval(const double* __restrict__ zX, const double* __restrict__ zY, const double* __restrict__ zFb,
              const double* __restrict__ sxb, const double* __restrict__ syb, const double* __restrict__ sxyb, int ni1, int nj1,
              const double* __restrict__ X2, const double* __restrict__ Y2, const int32_t* __restrict__ ixy, size_t nt, double x0,
-             double x1, double y0, double y1, float* Z2, size_t wstride, const double* __restrict__ x8, const double* __restrict__ y8) {
-  const double* ZF = zFb + blockIdx.y * wstride;
+             double x1, double y0, double y1, float* Z2, size_t wstride, const double* __restrict__ x8, const double* __restrict__ y8,
+             int ldf, size_t fstride) {
+  // zFb / ldf / fstride: the once-extended field -- a dense (ni1, nj1) array, or the view of ZF8 at offset (2,2) with ld ni1+4
+  const double* ZF = zFb + blockIdx.y * fstride;
   const double* sx = sxb + blockIdx.y * wstride;
   const double* sy = syb + blockIdx.y * wstride;
   const double* sxy = sxyb + blockIdx.y * wstride;
@@ -445,7 +470,7 @@ k_akima_eval(const double* __restrict__ zX, const double* __restrict__ zY, const
       double x = (x8 ? x8[ji + 2] : A2D(zX, ni1, ji + 1, jj)) - xa;
       double y = (y8 ? y8[jj + 2] : A2D(zY, ni1, ji, jj + 1)) - ya;
       double x2 = x * x, x3 = x2 * x, y2 = y * y, y3 = y2 * y, xy = x * y;
-      double b1 = A2D(ZF, ni1, ji, jj), b2 = A2D(ZF, ni1, ji + 1, jj), b3 = A2D(ZF, ni1, ji + 1, jj + 1), b4 = A2D(ZF, ni1, ji, jj + 1);
+      double b1 = A2D(ZF, ldf, ji, jj), b2 = A2D(ZF, ldf, ji + 1, jj), b3 = A2D(ZF, ldf, ji + 1, jj + 1), b4 = A2D(ZF, ldf, ji, jj + 1);
       double b5 = A2D(sx, ni1, ji, jj), b6 = A2D(sx, ni1, ji + 1, jj), b7 = A2D(sx, ni1, ji + 1, jj + 1), b8 = A2D(sx, ni1, ji, jj + 1);
       double b9 = A2D(sy, ni1, ji, jj), b10 = A2D(sy, ni1, ji + 1, jj), b11 = A2D(sy, ni1, ji + 1, jj + 1), b12 = A2D(sy, ni1, ji, jj + 1);
       double b13 = A2D(sxy, ni1, ji, jj), b14 = A2D(sxy, ni1, ji + 1, jj), b15 = A2D(sxy, ni1, ji + 1, jj + 1), b16 = A2D(sxy, ni1, ji, jj + 1);
@@ -771,20 +796,23 @@ static int feb_coords(sosie_ctx* ctx, int k_ew, const double* XX, const double* 
 }
 
 // field part of one FILL_EXTRA_BANDS level for `ns` slabs: F already holds zero + centre
+// ldf / fstride: leading dimension and slab stride of the field array (0: dense, nxp4 and nxp4*nyp4) -- the level-1 call
+// of the in-place build works on the view of ZF8 at offset (2,2)
 static int feb_field(sosie_ctx* ctx, int k_ew, const double* XP4, const double* YP4, double* FP4, int nx, int ny, int iorca, int ns,
-                     DBuf<double>& tmp) {
+                     DBuf<double>& tmp, int ldf = 0, size_t fstride = 0) {
   cudaStream_t st = ctx->stream;
   const int nxp4 = nx + 4, nyp4 = ny + 4;
-  size_t stride = (size_t)nxp4 * nyp4;
-  k_feb_f_ew<<<dim3(cdiv(ny, 128), ns), 128, 0, st>>>(XP4, FP4, nx, ny, k_ew, stride); KLAUNCH_CHECK();
+  if (ldf == 0) ldf = nxp4;
+  size_t stride = fstride ? fstride : (size_t)nxp4 * nyp4;
+  k_feb_f_ew<<<dim3(cdiv(ny, 128), ns), 128, 0, st>>>(XP4, FP4, nx, ny, k_ew, stride, ldf); KLAUNCH_CHECK();
   const bool fold = (iorca == 4 || iorca == 6);
   if (fold) {
     int ntmp = nxp4 + 8;
     CK(tmp.alloc((size_t)ntmp * ns));
     auto sect = [&](int l0, int ls, int n, int jl, int r0, int rs, int jr) -> int {
       if (n <= 0) return 0;
-      k_sectd_read<<<dim3(cdiv(n, 256), ns), 256, 0, st>>>(FP4, nxp4, n, r0, rs, jr, tmp.p, stride, ntmp); KLAUNCH_CHECK();
-      k_sectd_write<<<dim3(cdiv(n, 256), ns), 256, 0, st>>>(FP4, nxp4, n, l0, ls, jl, tmp.p, stride, ntmp); KLAUNCH_CHECK();
+      k_sectd_read<<<dim3(cdiv(n, 256), ns), 256, 0, st>>>(FP4, nxp4, n, r0, rs, jr, tmp.p, stride, ntmp, ldf); KLAUNCH_CHECK();
+      k_sectd_write<<<dim3(cdiv(n, 256), ns), 256, 0, st>>>(FP4, nxp4, n, l0, ls, jl, tmp.p, stride, ntmp, ldf); KLAUNCH_CHECK();
       return 0;
     };
     int rc = 0;
@@ -803,7 +831,7 @@ static int feb_field(sosie_ctx* ctx, int k_ew, const double* XP4, const double* 
     }
     if (rc) return rc;
   }
-  k_feb_f_tb<<<dim3(cdiv(nxp4, 128), ns), 128, 0, st>>>(YP4, FP4, nxp4, nyp4, fold ? 0 : 1, stride); KLAUNCH_CHECK();
+  k_feb_f_tb<<<dim3(cdiv(nxp4, 128), ns), 128, 0, st>>>(YP4, FP4, nxp4, nyp4, fold ? 0 : 1, stride, ldf); KLAUNCH_CHECK();
   return SOSIE_OK;
 }
 
@@ -903,12 +931,14 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
   const bool fused = ctx->ak_sep8 && ctx->ak_fused;
   const double* ax8 = ctx->ak_sep8 ? ctx->ak_ax8.p : nullptr;
   const double* ay8 = ctx->ak_sep8 ? ctx->ak_ax8.p + (ni1 + 4) : nullptr;
-  // slabs per batch: bound the f64 workspace (4*ne + ne8 doubles per slab, ne + ne8 when fused) to ~4 GB
-  size_t per = ((fused ? 1 : 4) * ne + ne8) * sizeof(double);
+  // slabs per batch: bound the f64 workspace (3*ne + ne8 doubles per slab, ne8 when fused) to ~4 GB
+  size_t per = ((fused ? 0 : 3) * ne + ne8) * sizeof(double);
   int nb = (int)std::max<size_t>(1, std::min<size_t>((size_t)nslab, (size_t)4e9 / per));
   if (nb > 32768) nb = 32768;
-  CK(ctx->ak_zF.alloc(ne * nb)); CK(ctx->ak_ZF8.alloc(ne8 * nb));
+  CK(ctx->ak_ZF8.alloc(ne8 * nb));
   if (!fused) { CK(ctx->ak_sx.alloc(ne * nb)); CK(ctx->ak_sy.alloc(ne * nb)); CK(ctx->ak_sxy.alloc(ne * nb)); }
+  const int n8 = ni1 + 4;
+  double* zFview = ctx->ak_ZF8.p + 2 + 2 * (size_t)n8;   // zF(i, j) == ZF8(i + 2, j + 2)
   DBuf<double> tmp;
   int kewp = -1;
   if (ctx->ak_kew > -1) kewp = ctx->ak_kew + 4;
@@ -929,9 +959,9 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
   for (int s0 = 0; s0 < nslab; s0 += nb) {
     int ns = std::min(nb, nslab - s0);
     prof_begin(ctx, SOSIE_T_AKIMA_PREP);
-    k_feb_center<float><<<dim3(grid_for(ctx, nfill, 256), ns), 256, 0, st>>>(dZ1 + (size_t)s0 * n1, nx1, ny1, ctx->ak_zF.p, n1, ne, fa, fb); KLAUNCH_CHECK();
-    if (int rc = feb_field(ctx, ctx->ak_kew, ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, nx1, ny1, ctx->ak_iorca, ns, tmp)) return rc;
-    k_feb_center<double><<<dim3(grid_for(ctx, nfill, 256), ns), 256, 0, st>>>(ctx->ak_zF.p, ni1, nj1, ctx->ak_ZF8.p, ne, ne8, fa8, fb8); KLAUNCH_CHECK();
+    // both FILL_EXTRA_BANDS levels in ONE array: zero + centre of ZF8, the level-1 frames into its (2,2) view, then level 2
+    k_feb_center8<<<dim3(grid_for(ctx, nfill, 256), ns), 256, 0, st>>>(dZ1 + (size_t)s0 * n1, nx1, ny1, ctx->ak_ZF8.p, n1, ne8, fa8, fb8); KLAUNCH_CHECK();
+    if (int rc = feb_field(ctx, ctx->ak_kew, ctx->ak_zX.p, ctx->ak_zY.p, zFview, nx1, ny1, ctx->ak_iorca, ns, tmp, n8, ne8)) return rc;
     if (int rc = feb_field(ctx, kewp, ctx->ak_ZX8.p, ctx->ak_ZY8.p, ctx->ak_ZF8.p, ni1, nj1, 0, ns, tmp)) return rc;
     if (fused) {
       prof_end(ctx, SOSIE_T_AKIMA_PREP);
@@ -967,9 +997,10 @@ int akima_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2) {
     }
     prof_end(ctx, SOSIE_T_AKIMA_PREP);
     prof_begin(ctx, SOSIE_T_AKIMA_EVAL);
-    k_akima_eval<<<dim3(grid_for(ctx, nt, 128), ns), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, ctx->ak_zF.p, ctx->ak_sx.p, ctx->ak_sy.p, ctx->ak_sxy.p,
+    k_akima_eval<<<dim3(grid_for(ctx, nt, 128), ns), 128, 0, st>>>(ctx->ak_zX.p, ctx->ak_zY.p, zFview, ctx->ak_sx.p, ctx->ak_sy.p, ctx->ak_sxy.p,
                                                                     ni1, nj1, ctx->ak_X2.p, ctx->ak_Y2.p, ctx->ak_ixy.p, nt, ctx->ak_range[0],
-                                                                    ctx->ak_range[1], ctx->ak_range[2], ctx->ak_range[3], dZ2 + (size_t)s0 * nt, ne, ax8, ay8); KLAUNCH_CHECK();
+                                                                    ctx->ak_range[1], ctx->ak_range[2], ctx->ak_range[3], dZ2 + (size_t)s0 * nt, ne, ax8, ay8,
+                                                                    n8, ne8); KLAUNCH_CHECK();
     prof_end(ctx, SOSIE_T_AKIMA_EVAL);
   }
   return SOSIE_OK;

@@ -923,8 +923,8 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
     // they could own a tile)
     prof_begin(ctx, SOSIE_T_APPLY);
     if (use_tma) {
-      static bool attr_set = false;
-      if (!attr_set) { CK(cudaFuncSetAttribute(k_apply_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES)); attr_set = true; }
+      // (function attributes are per device: a flag per context, not per process)
+      if (!ctx->attr_tma) { CK(cudaFuncSetAttribute(k_apply_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, TMA_SMEM_BYTES)); ctx->attr_tma = true; }
       k_apply_tma<<<grid, 256, TMA_SMEM_BYTES, ctx->stream>>>(tmap, ctx->d_pidx.p, ctx->d_pw.p, nt, v, dZ2, nslab, spc, po, tgm, ctx->d_boxes.p, own);
       KLAUNCH_CHECK();
     }

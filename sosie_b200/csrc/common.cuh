@@ -89,6 +89,7 @@ struct sosie_ctx {
   std::string err;
   int64_t launches = 0;
   int num_sms = SOSIE_NUM_SMS_B200;
+  bool attr_tma = false, attr_bdrown = false;   // opt-in shared-memory sizes set on this context's device
 
   // ---- bilinear state
   int k_ew = -1, l_reg_src = 0, i_orca_trg = 0, l_add_extra_j = 0;
@@ -182,7 +183,7 @@ struct sosie_ctx {
   bool ak_fused = false;             // sosie_akima_untiled_slopes(3): regular sources take the fused slopes + evaluation kernel
   DBuf<double> ak_ax8;               // the 1-D axes of the twice-extended grid: x8 (ni1+4), y8 (nj1+4)
   DBuf<uint8_t> ak_needed;           // (nx1+4,ny1+4): source points whose slopes some target reads
-  DBuf<double> ak_zF, ak_ZF8, ak_sx, ak_sy, ak_sxy;  // per-slab work arrays
+  DBuf<double> ak_ZF8, ak_sx, ak_sy, ak_sxy;  // per-slab work arrays
   DBuf<float> ak_stage1, ak_stage2;
   double ak_range[4] = {0, 0, 0, 0};
   DBuf<int32_t> ak_tiles;            // 32x8 tiles of the frame-extended slab that hold a needed point (k_slopes_tiled walks this list)

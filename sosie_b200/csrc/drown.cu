@@ -1036,8 +1036,8 @@ int bdrown_impl(sosie_ctx* ctx, int k_ew, int ni, int nj, int nslab, float* dX, 
   if (smem_need <= (size_t)227 * 1024 && (n + BDS_THREADS - 1) / BDS_THREADS <= BDS_MAXCPT && ni <= BDS_THREADS && n < 65536 && nb_inc <= 250 && !ctx->force_general_bdrown) {
     // the whole slab fits one SM's shared memory: one CTA per slab, every sweep on chip
     CK(ctx->dr_cnt.alloc(nslab));
-    static bool attr_set = false;
-    if (!attr_set) { CK(cudaFuncSetAttribute(k_bdrown_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); attr_set = true; }
+    // (function attributes are per device: a flag per context, not per process -- two contexts on two GPUs of one process)
+    if (!ctx->attr_bdrown) { CK(cudaFuncSetAttribute(k_bdrown_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024)); ctx->attr_bdrown = true; }
     int grid = nslab;   // one CTA per slab, dispatched as SMs free up: slabs differ in land fraction (work), a static stride left SMs idle
     prof_begin(ctx, SOSIE_T_BDROWN);
     k_bdrown_smem<<<grid, BDS_THREADS, smem_need, st>>>(g, dX, dmask, mask_per_slab, nslab, nb_inc, nb_smooth, pmin, pmax, pval_land, ctx->dr_cnt.p);
