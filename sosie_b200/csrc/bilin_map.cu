@@ -851,9 +851,11 @@ __device__ __forceinline__ void map_store(const MapOut& o, int iP, int jP, int m
 
 // ---------------------------------------------------------------------------------------------------
 // EASY search (src/mod_manip.f90:967-1069) fused with the MAPPING_BL body: one thread per target.
+// (__grid_constant__: the out-of-line rare paths take the geometry by reference; without it every thread copies the 280-byte
+// parameter struct to its stack first)
 template <bool SEP>
 __global__ void __launch_bounds__(128, MAP_MIN_BLOCKS)
-k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
+k_map_easy(const __grid_constant__ SrcGeom sg, const __grid_constant__ TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
            const double* __restrict__ vlat, int sorted_lon, int sorted_lat, int jlo, int jhi, int32_t* MT, double* AB,
            int16_t* IDP, float* DNP, int* err, size_t k0, size_t kcnt, int search_only, const DevPlan* __restrict__ plan) {
   const size_t nt = (size_t)tg.nx * tg.ny;
@@ -864,6 +866,14 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
     int m = mask ? mask[k] : 1;
     int iP = -1, jP = -1;
     double rlon = trg_lon(tg, ji_t, jj_t), rlat = trg_lat(tg, ji_t, jj_t);
+    // the coordinates of this thread's NEXT target head a ~1800-instruction dependent chain: ask for their lines now (-1 %)
+    if (!tg.is_1d) {
+      const size_t kn = k + (size_t)gridDim.x * blockDim.x;
+      if (kn < k0 + kcnt) {
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tg.X + kn));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(tg.Y + kn));
+      }
+    }
     double ux = 0.0, uy = 0.0, uz = 0.0, bpds = 0.0, bd = 0.0;
     bool have_u = false;
     if (m == 1 && jj_t >= jlo && jj_t <= jhi) {
@@ -890,7 +900,7 @@ k_map_easy(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, c
 
 // body only (after TWISTED): JI/JJ given
 __global__ void __launch_bounds__(128)
-k_map_body(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const int32_t* __restrict__ JI,
+k_map_body(const __grid_constant__ SrcGeom sg, const __grid_constant__ TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const int32_t* __restrict__ JI,
            const int32_t* __restrict__ JJ, int32_t* MT, double* AB, int16_t* IDP, float* DNP, int* err) {
   const size_t nt = (size_t)tg.nx * tg.ny;
   for (size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x; k < nt; k += (size_t)gridDim.x * blockDim.x) {
@@ -1174,7 +1184,7 @@ k_twisted_band(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ 
 
 // one pass of the chain: S_new[q] = f_q(S_old[q-1])   (:1336-1349, 1385-1391)
 __global__ void __launch_bounds__(128)
-k_twisted_chain(SrcGeom sg, TrgGeom tg, TwParams tp, const int64_t* __restrict__ order, int T,
+k_twisted_chain(const __grid_constant__ SrcGeom sg, const __grid_constant__ TrgGeom tg, const __grid_constant__ TwParams tp, const int64_t* __restrict__ order, int T,
                 const int2* __restrict__ band_pos, const int8_t* __restrict__ band_found,
                 const int2* __restrict__ S_old, int2* S_new, int8_t* found, int* changed, const int2* __restrict__ S_prev) {
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < T; q += gridDim.x * blockDim.x) {
