@@ -171,14 +171,14 @@ __device__ __forceinline__ bool box_is_tma(const int4& box) { return box.z > 0 &
 #endif
 #define GRP_STAGE 3072                                  // floats per pipeline stage: SD slabs x (GRP_STAGE / SD) floats of box
 #define GRP_CPT (GRP_STAGE / 4 / 256)                   // 16-byte chunks per thread and group at most (3)
-// The kernel is instantiated for groups of SD = 4, 2 and 1 slabs: a tile takes the deepest group its (padded) box allows --
-// 768, 1536 or 3072 floats per slab (the wide, short boxes next to the pole of a polar-stereographic target are the big ones)
+// The kernel is instantiated for groups of SD = 8, 4, 2 and 1 slabs: a tile takes the deepest group its (padded) box allows --
+// 384, 768, 1536 or 3072 floats per slab (the wide, short boxes next to the pole of a polar-stereographic target are the big ones)
 __host__ __device__ __forceinline__ int grp_cpr(const int4& box) { return ((box.x & 3) + box.z + 3) >> 2; }
 __host__ __device__ __forceinline__ int grp_pitch(const int4& box) { const int c = grp_cpr(box); return 4 * (c + ((c & 1) ? 0 : 1)); }
 __device__ __forceinline__ int grp_class(const int4& box) {   // slabs per group, 0: the box fits no instantiation
   if (box.z <= 0) return 0;
   const long long need = (long long)box.w * grp_pitch(box);
-  return need <= GRP_STAGE / 4 ? 4 : need <= GRP_STAGE / 2 ? 2 : need <= GRP_STAGE ? 1 : 0;
+  return need <= GRP_STAGE / 8 ? 8 : need <= GRP_STAGE / 4 ? 4 : need <= GRP_STAGE / 2 ? 2 : need <= GRP_STAGE ? 1 : 0;
 }
 __device__ __forceinline__ bool box_fits_grp(const int4& box) { return grp_class(box) != 0; }
 // which kernel of a batched apply takes a tile: 0 the 4-byte cp.async kernel (also direct gathers), 1 k_apply_grp,
@@ -194,7 +194,7 @@ __device__ __forceinline__ int tile_owner(const int4& box, int flags) {
 
 // one block per tile: bounding box (0-based i0, j0, w, h) of the tile's source cells; w == 0 -> not stageable.
 // counts[0..2]: tiles that fit the TMA box / the group-staged kernel / neither; counts[3]: tiles the group kernel does not
-// take, counts[4..6]: tiles of its instantiations with 4 / 2 / 1 slabs per group; lists: four compact tile lists of ntiles
+// take, counts[4..6]: tiles of its instantiations with 8 or 4 / 2 / 1 slabs per group; lists: four compact tile lists of ntiles
 // entries each (groups of 4, 2, 1, the rest), so that every kernel is launched over its own tiles only
 __global__ void __launch_bounds__(256)
 k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes, int* counts, int* lists) {
@@ -239,7 +239,7 @@ k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes, 
       }
       boxes[tile] = b;
       if (box_is_tma(b)) atomicAdd(&counts[0], 1);
-      const int gc = grp_class(b), li = gc == 4 ? 0 : gc == 2 ? 1 : gc == 1 ? 2 : 3;
+      const int gc = grp_class(b), li = gc >= 4 ? 0 : gc == 2 ? 1 : gc == 1 ? 2 : 3;
       if (gc) atomicAdd(&counts[1], 1);
       lists[(size_t)li * tgm.ntiles + atomicAdd(&counts[li == 3 ? 3 : 4 + li], 1)] = tile;
       if (!box_is_tma(b) && !box_fits_grp(b)) atomicAdd(&counts[2], 1);
@@ -419,6 +419,11 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
 }
+// the same under a predicate instead of a branch (a divergent branch around the copy costs a convergence barrier pair)
+__device__ __forceinline__ void cp_async16_if(bool on, float* smem_dst, const float* gsrc) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n" ::"r"(sa), "l"(gsrc), "r"((int)on));
+}
 
 // Batched slabs, group-staged (see GRP_* above).  Per tile and chunk of slabs: groups of GRP_SD slabs travel through
 // GRP_NSTG stages; per group a thread issues its (at most GRP_CPT, usually one) 16-byte copies, the block waits and
@@ -427,13 +432,20 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
 // set-up): the set-up is amortised over a long run of slabs (the host sizes the chunks for ~8 waves of blocks, not 32
 // slabs), its divisions go through multiply-high reciprocals, the kernel is specialised on the presence of post-ops, full
 // groups run without per-slab predicates, and the quotient by the weight sum is three instructions (div_by_rcp).
-template <int SD, bool FULL, bool POST>
+// the quotient outside the guarded range of the three-instruction form (zeros, denormals, huge values, Inf, NaN, or a weight sum
+// outside [0.5, 2]): rare, and kept out of line -- inlined, its FCHK / MUFU / fix-up call sequence was 2/3 of the kernel's code
+static __device__ __noinline__ float quot_general(float x, float wup, float rcp, bool fast) {
+  return fast ? div_by_rcp(x, wup, rcp) : __fdiv_rn(x, wup);
+}
+// SD slabs, PLANE floats apart, starting at b (a compile-time offset into the stage buffers once the caller's loops are unrolled:
+// the four corner loads are LDS [corner register + immediate])
+template <int SD, int PLANE, bool FULL, bool POST>
 __device__ __forceinline__ void grp_compute(const float* __restrict__ b, int left, int o1, int o2, int o3, int o4, const float4& w, float wup, float rcp,
                                             bool fast, bool masked, const PostOps& po, float*& outp, size_t nt) {
   float acc[SD];
 #pragma unroll
   for (int d = 0; d < SD; d++) {
-    const float* bd = b + d * (GRP_STAGE / SD);
+    const float* bd = b + d * PLANE;
     acc[d] = (FULL || d < left) ? __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(bd[o1], w.x), __fmul_rn(bd[o2], w.y)), __fmul_rn(bd[o3], w.z)), __fmul_rn(bd[o4], w.w)) : 1.0f;
   }
   // one range test for the group: every |acc| inside the guarded range of div_by_rcp.  The smallest magnitude through
@@ -443,15 +455,18 @@ __device__ __forceinline__ void grp_compute(const float* __restrict__ b, int lef
 #pragma unroll
   for (int d = 1; d < SD; d++) { lo = fminf(lo, fabsf(acc[d])); sum = __fadd_rn(sum, fabsf(acc[d])); }
   const bool all_fast = fast && lo >= 0x1p-90f && sum <= 0x1p90f;
+  // ONE branch per batch (not per slab): the general quotients of a batch that fails the test replace the accumulators
+  if (!all_fast) {
+#pragma unroll
+    for (int d = 0; d < SD; d++) acc[d] = quot_general(acc[d], wup, rcp, fast);
+  }
 #pragma unroll
   for (int d = 0; d < SD; d++) {
     if (FULL || d < left) {
-      float r;
+      float r = acc[d];
       if (all_fast) {
         const float q = __fmul_rn(acc[d], rcp);
         r = __fmaf_rn(__fmaf_rn(-q, wup, acc[d]), rcp, q);
-      } else {
-        r = fast ? div_by_rcp(acc[d], wup, rcp) : __fdiv_rn(acc[d], wup);
       }
       if (POST) {
         if (po.use_clamp) { r = fmaxf(r, po.vmin); r = fminf(r, po.vmax); }
@@ -508,35 +523,48 @@ __device__ __forceinline__ void grp_tile(float (*buf)[GRP_STAGE], const int4& bo
     gsrc[m] = Z1 + (size_t)(s0 + d) * src_stride + (size_t)(box.y + row) * v.nx + x0a + cc * 4;
   }
   float* outp = Z2 + (size_t)s0 * nt + k;
-  auto issue = [&](int g, bool full) {   // group g -> stage g % GRP_NSTG
-    float* sb = &buf[g % GRP_NSTG][0];
+  auto issue = [&](float* sb, int g, bool full) {   // group g -> the stage at sb
     const int left = full ? SD : s1 - (s0 + g * SD);   // slabs of this group that exist
 #pragma unroll
     for (int m = 0; m < GRP_CPT; m++) {
       if (m < ncp) {
-        if (sd_[m] < left) cp_async16(sb + soff[m], gsrc[m]);
+        cp_async16_if(sd_[m] < left, sb + soff[m], gsrc[m]);
         gsrc[m] += (size_t)SD * src_stride;
       }
     }
   };
 #pragma unroll
   for (int q = 0; q < GRP_NSTG - 1; q++) {
-    if (q < ngrp) issue(q, q < nfull);
+    if (q < ngrp) issue(&buf[q][0], q, q < nfull);
     cp_async_commit();
   }
-  int stage = 0;
-  for (int g = 0; g < ngrp; g++) {
-    cp_async_wait<GRP_NSTG - 2>();   // this thread's copies of group g have landed
-    __syncthreads();                 // ... everybody's have, and everybody is done reading the stage of group g-1
-    const int gn = g + GRP_NSTG - 1;
-    if (gn < ngrp) issue(gn, gn < nfull);   // refills the stage group g-1 used
-    cp_async_commit();
-    if (valid) {
-      const float* b = &buf[stage][0];
-      if (g < nfull) grp_compute<SD, true, POST>(b, SD, o1, o2, o3, o4, w, wup, rcp, fast, masked, po, outp, nt);
-      else grp_compute<SD, false, POST>(b, s1 - (s0 + g * SD), o1, o2, o3, o4, w, wup, rcp, fast, masked, po, outp, nt);
+  // a group of more than 4 slabs is interpolated 4 at a time (the accumulators of a batch live in registers)
+  constexpr int SC = SD > 4 ? 4 : SD, NH = SD / SC;
+  // GRP_NSTG groups per trip, so that every stage address below is a compile-time constant
+  int g = 0;
+  bool more = ngrp > 0;
+  while (more) {
+#pragma unroll
+    for (int st = 0; st < GRP_NSTG; st++, g++) {
+      if (g >= ngrp) { more = false; break; }   // (block-uniform)
+      cp_async_wait<GRP_NSTG - 2>();   // this thread's copies of group g have landed
+      __syncthreads();                 // ... everybody's have, and everybody is done reading the stage of group g-1
+      const int gn = g + GRP_NSTG - 1;
+      if (gn < ngrp) issue(&buf[(st + GRP_NSTG - 1) % GRP_NSTG][0], gn, gn < nfull);   // refills the stage group g-1 used
+      cp_async_commit();
+      if (valid) {
+        const float* b = &buf[st][0];
+        if (g < nfull) {
+#pragma unroll
+          for (int h = 0; h < NH; h++) grp_compute<SC, PLANE, true, POST>(b + h * SC * PLANE, SC, o1, o2, o3, o4, w, wup, rcp, fast, masked, po, outp, nt);
+        } else {
+          int left = s1 - (s0 + g * SD);
+#pragma unroll
+          for (int h = 0; h < NH; h++, left -= SC)
+            if (left > 0) grp_compute<SC, PLANE, false, POST>(b + h * SC * PLANE, left, o1, o2, o3, o4, w, wup, rcp, fast, masked, po, outp, nt);
+        }
+      }
     }
-    stage = stage + 1 == GRP_NSTG ? 0 : stage + 1;
   }
   __syncthreads();   // the next tile's prologue overwrites the stages
   cp_async_wait<0>();
@@ -587,8 +615,8 @@ __device__ __forceinline__ void direct_tile(int tile, const int4* __restrict__ p
 template <bool POST>
 __global__ void __launch_bounds__(256, 4)
 k_apply_grp(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, FastDiv dnx, const float* __restrict__ Z1,
-            float* __restrict__ Z2, int nslab, int slabs_per_chunk, PostOps po, TileGeom tgm, const int4* __restrict__ boxes, int own_flags,
-            const int* __restrict__ lists, int4 cnt) {
+            float* __restrict__ Z2, int nslab, int slabs_per_chunk, const __grid_constant__ PostOps po, TileGeom tgm, const int4* __restrict__ boxes,
+            int own_flags, const int* __restrict__ lists, int4 cnt) {
   __shared__ __align__(16) float buf[GRP_NSTG][GRP_STAGE];
   const int s0 = blockIdx.y * slabs_per_chunk;
   const int s1 = min(s0 + slabs_per_chunk, nslab);
@@ -605,7 +633,8 @@ k_apply_grp(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t
     const int4 box = boxes[tile];
     if (tile_owner(box, own_flags) == OWN_TMA) continue;   // block-uniform
     const int cls = grp_class(box);
-    if (cls == 4) grp_tile<4, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
+    if (cls == 8) grp_tile<8, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
+    else if (cls == 4) grp_tile<4, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
     else if (cls == 2) grp_tile<2, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
     else if (cls == 1) grp_tile<1, POST>(buf, box, tile, pidx, pw, nt, v, dnx, Z1, Z2, s0, s1, po, tgm);
     else direct_tile<POST>(tile, pidx, pw, nt, v, Z1, Z2, s0, s1, po, tgm);
