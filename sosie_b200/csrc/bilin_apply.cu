@@ -169,6 +169,9 @@ __device__ __forceinline__ bool box_is_tma(const int4& box) { return box.z > 0 &
 #ifndef GRP_NSTG
 #define GRP_NSTG 4
 #endif
+#ifndef GRP_MINB
+#define GRP_MINB 4                                      // resident blocks per SM the kernel is compiled for
+#endif
 #define GRP_STAGE 3072                                  // floats per pipeline stage: SD slabs x (GRP_STAGE / SD) floats of box
 #define GRP_CPT (GRP_STAGE / 4 / 256)                   // 16-byte chunks per thread and group at most (3)
 // The kernel is instantiated for groups of SD = 8, 4, 2 and 1 slabs: a tile takes the deepest group its (padded) box allows --
@@ -419,11 +422,7 @@ __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gsrc) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc));
 }
-// the same under a predicate instead of a branch (a divergent branch around the copy costs a convergence barrier pair)
-__device__ __forceinline__ void cp_async16_if(bool on, float* smem_dst, const float* gsrc) {
-  unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %2, 0;\n @p cp.async.cg.shared.global [%0], [%1], 16;\n}\n" ::"r"(sa), "l"(gsrc), "r"((int)on));
-}
+
 
 // Batched slabs, group-staged (see GRP_* above).  Per tile and chunk of slabs: groups of GRP_SD slabs travel through
 // GRP_NSTG stages; per group a thread issues its (at most GRP_CPT, usually one) 16-byte copies, the block waits and
@@ -528,7 +527,7 @@ __device__ __forceinline__ void grp_tile(float (*buf)[GRP_STAGE], const int4& bo
 #pragma unroll
     for (int m = 0; m < GRP_CPT; m++) {
       if (m < ncp) {
-        cp_async16_if(sd_[m] < left, sb + soff[m], gsrc[m]);
+        if (sd_[m] < left) cp_async16(sb + soff[m], gsrc[m]);
         gsrc[m] += (size_t)SD * src_stride;
       }
     }
@@ -613,7 +612,7 @@ __device__ __forceinline__ void direct_tile(int tile, const int4* __restrict__ p
 // the tail of the launch.  cnt = lengths of the four lists (4 / 2 / 1 slabs per group, direct), lists = k_tilebox's.
 // tile_list == nullptr (the TMA kernel also runs): every tile is visited and the owner test decides.
 template <bool POST>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, GRP_MINB)
 k_apply_grp(const int4* __restrict__ pidx, const float4* __restrict__ pw, size_t nt, SlabView v, FastDiv dnx, const float* __restrict__ Z1,
             float* __restrict__ Z2, int nslab, int slabs_per_chunk, const __grid_constant__ PostOps po, TileGeom tgm, const int4* __restrict__ boxes,
             int own_flags, const int* __restrict__ lists, int4 cnt) {
