@@ -410,11 +410,11 @@ __global__ void k_lat_table(const double* __restrict__ Yin, int ny, int nyw, dou
     lat[j] = (j < ny) ? Yin[j] : ((j == ny) ? 90.0 : 90.0 + dyp);
 }
 // ji_m = MINLOC(ABS(XX(:,ny)-MOD(zlon+180.,360.)))  (src/mod_manip.f90:1821-1826)
-__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r, double v0, double inv_d);
+__device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r, double v0, double inv_d, bool well_spaced);
 __global__ void k_jim_table(const double* __restrict__ lonrow, int nx, int sorted, int32_t* im) {
   for (int ji = blockIdx.x * blockDim.x + threadIdx.x; ji < nx; ji += gridDim.x * blockDim.x) {
     double zlon_m = fmod(lonrow[ji] + 180.0, 360.0);
-    if (sorted) { im[ji] = minloc_abs_sorted(lonrow, nx, zlon_m, 0.0, 0.0); continue; }
+    if (sorted) { im[ji] = minloc_abs_sorted(lonrow, nx, zlon_m, 0.0, 0.0, false); continue; }
     int best = 0;
     double bv = fabs(lonrow[0] - zlon_m);
     for (int i = 1; i < nx; i++) {
@@ -460,13 +460,18 @@ __device__ __forceinline__ int lower_bound_axis(const double* __restrict__ v, in
   }
   return lo;
 }
+// well_spaced: the axis is strictly increasing with steps >= 1e-9 and |v| <= 1e5 (is_sorted_host).  For |r| <= 1e6 every
+// |v - r| is then formed with an error below 2.4e-10, so entries further from r than the chosen neighbour of the bracket
+// are strictly further after rounding too: the walk back over equal distances (first minimum of MINLOC) cannot move, and
+// its dependent load is skipped.
 __device__ __forceinline__ int minloc_abs_sorted(const double* __restrict__ v, int n, double r, double v0 = 0.0,
-                                                 double inv_d = 0.0) {
+                                                 double inv_d = 0.0, bool well_spaced = false) {
   const int lo = lower_bound_axis(v, n, r, v0, inv_d);
   int best;
   if (lo == 0) best = 0;
   else if (lo == n) best = n - 1;
   else best = (fabs(v[lo - 1] - r) <= fabs(v[lo] - r)) ? lo - 1 : lo;
+  if (well_spaced && fabs(r) <= 1.0e6) return best + 1;
   double bv = fabs(v[best] - r);
   while (best > 0 && fabs(v[best - 1] - r) == bv) best--;
   return best + 1;
@@ -490,9 +495,13 @@ struct Best {
 #ifndef MAP_MIN_BLOCKS
 #define MAP_MIN_BLOCKS 8
 #endif
+// (out of line, and the winner comes back as ONE 64-bit word -- j in the high half, i in the low half; the caller forms the
+// dot product and the distance of that point with the very expressions of the loops below: a `Best&` argument, or a record
+// returned by value, lives on the kernel's stack)
 template <bool SEP>
-static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
-                                            int j2, Best& b, int ic, int jc) {
+static __device__ __noinline__ unsigned long long scan_window_exact_r(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1,
+                                                         int j2, int ic, int jc) {
+  Best b;
   // MINLOC = lexicographic minimum of (distance, column-major position).  The window centre (ic,jc) -- the
   // index-nearest point, almost always the winner or next to it -- is evaluated first, so that nearly every other
   // candidate is rejected by the dot-product margin without an acos; ties are still resolved by position, which
@@ -507,13 +516,13 @@ static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double 
     // cl*amax + c0 -- or cl*amin + c0 on the virtual row beyond the pole where cl < 0 -- IS that maximum).
     // Pass 0 is the centre alone (it seeds the running best); passes 1.. are the rows j1..j2.  One code copy of
     // the exact evaluation (acos) serves both: the kernel is instruction-cache bound.
-    double a[9];
+    // (the column terms are recomputed where they are used: this path is rare, and an array indexed by the survivor loop
+    // would live on the stack)
     double amax = -4.0, amin = 4.0;
-#pragma unroll
     for (int q = 0; q < 9; q++) {
       int ji = min(i1 + q, i2);
-      a[q] = ux * sg.clon[ji - 1] + uy * sg.slon[ji - 1];
-      amax = fmax(amax, a[q]); amin = fmin(amin, a[q]);
+      const double aq = ux * sg.clon[ji - 1] + uy * sg.slon[ji - 1];
+      amax = fmax(amax, aq); amin = fmin(amin, aq);
     }
     b.d = 1.0e300; b.pds = -4.0; b.i = 0; b.j = 0;
     const int nq = i2 - i1 + 1;
@@ -525,9 +534,10 @@ static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double 
       unsigned surv = 0;
       if (pass == 0) surv = 1u << (ic - i1);
       else if (!(((cl >= 0.0) ? cl * amax : cl * amin) + c0 < thr)) {
-#pragma unroll
-        for (int q = 0; q < 9; q++)
-          if (q < nq && !(cl * a[q] + c0 < thr)) surv |= 1u << q;
+        for (int q = 0; q < nq; q++) {
+          const double aq = ux * sg.clon[i1 + q - 1] + uy * sg.slon[i1 + q - 1];
+          if (!(cl * aq + c0 < thr)) surv |= 1u << q;
+        }
         if (jj == jc) surv &= ~(1u << (ic - i1));  // the centre is already in the running best
       }
       while (surv) {
@@ -541,7 +551,7 @@ static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double 
         if (d < b.d || (d == b.d && earlier)) { b.d = d; b.pds = zpds; b.i = ji; b.j = jj; }
       }
     }
-    return;
+    return ((unsigned long long)(unsigned)b.j << 32) | (unsigned)b.i;
   }
   b.d = 0.0; b.pds = -4.0; b.i = 0; b.j = 0;
   {
@@ -562,6 +572,23 @@ static __device__ __noinline__ void scan_window_exact(const SrcGeom& sg, double 
       if (d < b.d || (d == b.d && earlier)) { b.d = d; b.pds = zpds; b.i = ji; b.j = jj; }
     }
   }
+  return ((unsigned long long)(unsigned)b.j << 32) | (unsigned)b.i;
+}
+template <bool SEP>
+__device__ __forceinline__ void scan_window_exact(const SrcGeom& sg, double ux, double uy, double uz, int i1, int i2, int j1, int j2,
+                                                  Best& b, int ic, int jc) {
+  const unsigned long long r = scan_window_exact_r<SEP>(sg, ux, uy, uz, i1, i2, j1, j2, ic, jc);
+  b.i = (int)(unsigned)(r & 0xffffffffull); b.j = (int)(unsigned)(r >> 32);
+  if (b.i < 1 || b.j < 1) { b.pds = -4.0; b.d = 1.0e300; return; }   // (NaN coordinates: no candidate ever won)
+  if (SEP) {
+    const double cl = sg.clat[b.j - 1], sl = sg.slat[b.j - 1];
+    b.pds = ux * (sg.clon[b.i - 1] * cl) + uy * (sg.slon[b.i - 1] * cl) + uz * sl;
+  } else {
+    double vx, vy, vz;
+    src_vec(sg, b.i, b.j, vx, vy, vz);
+    b.pds = ux * vx + uy * vy + uz * vz;
+  }
+  b.d = G_ZR * pm_acos(fmin(b.pds, 1.0));
 }
 
 // The scan the kernel runs.  Regular source: the decision is taken on the dot products alone -- the candidate with the
@@ -877,8 +904,8 @@ k_map_easy(const __grid_constant__ SrcGeom sg, const __grid_constant__ TrgGeom t
     double ux = 0.0, uy = 0.0, uz = 0.0, bpds = 0.0, bd = 0.0;
     bool have_u = false;
     if (m == 1 && jj_t >= jlo && jj_t <= jhi) {
-      int ip = sorted_lon ? minloc_abs_sorted(vlon, sg.nx, rlon, sg.lon0, sg.inv_dlon) : minloc_abs_linear(vlon, sg.nx, rlon);
-      int jp = sorted_lat ? minloc_abs_sorted(vlat, sg.nyw, rlat, sg.lat0, sg.inv_dlat) : minloc_abs_linear(vlat, sg.nyw, rlat);
+      int ip = sorted_lon ? minloc_abs_sorted(vlon, sg.nx, rlon, sg.lon0, sg.inv_dlon, sorted_lon == 2) : minloc_abs_linear(vlon, sg.nx, rlon);
+      int jp = sorted_lat ? minloc_abs_sorted(vlat, sg.nyw, rlat, sg.lat0, sg.inv_dlat, sorted_lat == 2) : minloc_abs_linear(vlat, sg.nyw, rlat);
       int i1s = max(ip - 4, 1), i2s = min(ip + 4, sg.nx);
       int j1s = max(jp - 4, 1), j2s = min(jp + 4, sg.nyw);
       double cpt;
@@ -1408,9 +1435,15 @@ int bilin_prepare_src(sosie_ctx* ctx) {
   return SOSIE_OK;
 }
 
+// 0: not sorted; 1: non-decreasing; 2: increasing with every step >= 1e-9 and |v| <= 1e5 (minloc_abs_sorted's well_spaced)
 static int is_sorted_host(const std::vector<double>& v, int off, int n) {
-  for (int i = 1; i < n; i++) if (v[off + i] < v[off + i - 1]) return 0;
-  return 1;
+  bool spaced = true;
+  for (int i = 0; i < n; i++) {
+    if (i > 0 && v[off + i] < v[off + i - 1]) return 0;
+    if (i > 0 && !(v[off + i] - v[off + i - 1] >= 1.0e-9)) spaced = false;
+    if (!(std::fabs(v[off + i]) <= 1.0e5)) spaced = false;
+  }
+  return spaced ? 2 : 1;
 }
 
 // ---- FIND_NEAREST_POINT prelude (:888-947): regularity tests, latitude ranges, target row range.
