@@ -760,3 +760,42 @@ def test_akima_fused_kernel_paths(gpu, orc, case):
         assert np.array_equal(gpu.akima_get_ixy(), ixy)
     assert np.array_equal(res[3].view(np.uint32), Z2o.view(np.uint32)), f"fused differs at {(res[3] != Z2o).sum()} points"
     assert np.array_equal(res[0].view(np.uint32), Z2o.view(np.uint32))
+
+
+@pytest.mark.parametrize("kind", ["well_spaced", "tiny_steps", "far_offset"])
+def test_index_nearest_ties_on_sorted_axes(gpu, orc, kind):
+    """The EASY search starts from MINLOC(ABS(axis - coordinate)) per axis = the FIRST minimum.  On sorted axes the kernel
+    brackets the coordinate and, on axes whose steps are >= 1e-9 with |values| <= 1e5, skips the walk back over equal
+    distances (it cannot move there).  Targets exactly midway between two nodes, on nodes, and next to them must give the
+    oracle's indices on such an axis and on axes that do NOT qualify: steps of 1e-10 around some nodes (distances to
+    distinct nodes round to the same value for far-away coordinates) and an axis offset beyond 1e5."""
+    rng = np.random.default_rng(5)
+    nx, ny, kew = 64, 40, -1
+    lon = 10.0 + np.arange(nx) * 0.5
+    lat = -30.0 + np.arange(ny) * 0.5
+    if kind == "tiny_steps":
+        lon[20] = lon[19] + 1.0e-10; lon[41] = lon[40] + 3.0e-10
+        lat[11] = lat[10] + 1.0e-10
+    elif kind == "far_offset":
+        lon = lon + 2.0e5       # not geographic, but MINLOC does not care; MOD(.,360) happens later in the body
+    ii = rng.integers(1, nx - 1, 60)
+    jj = rng.integers(1, ny - 1, 60)
+    X, Y = [], []
+    for i, j in zip(ii, jj):
+        for fx in (0.0, 0.5, 0.25, 1.0e-11, -1.0e-11):
+            for fy in (0.0, 0.5, 0.75):
+                X.append(lon[i] + fx * (lon[i + 1] - lon[i]) if abs(fx) >= 1e-3 or fx == 0.0 else lon[i] + fx)
+                Y.append(lat[j] + fy * (lat[j + 1] - lat[j]))
+    n = len(X) // 30 * 30
+    Xt = np.array(X[:n]).reshape(-1, 30)
+    Yt = np.array(Y[:n]).reshape(-1, 30)
+    Z1 = (np.cos(3 * np.deg2rad(lon))[None, :] * np.sin(2 * np.deg2rad(lat))[:, None]).astype(np.float32)
+    gpu.l_first_call_interp_routine = True
+    Z2g = gpu.bilin_2d(kew, lon, lat, Z1, Xt, Yt, l_reg_src=True)
+    mg = gpu.bilin_get_map()
+    Z2o, mo = orc.bilin_2d(kew, lon, lat, Z1, Xt, Yt, l_reg_src=True)
+    for k in ("metrics", "ipb", "alphabeta", "dist_np"):
+        a, b = np.ascontiguousarray(mg[k]), np.ascontiguousarray(mo[k])
+        bad = np.argwhere(a.view(f"u{a.itemsize}") != b.view(f"u{b.itemsize}"))   # bit patterns: NaN == NaN
+        assert bad.size == 0, f"{kind}: {k} differs at {len(bad)} targets, first {bad[:5].tolist()}"
+    assert np.array_equal(Z2g.view(np.uint32), Z2o.view(np.uint32))
