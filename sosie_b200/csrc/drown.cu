@@ -654,6 +654,7 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
         float v[BDS_MAXCPT];
 #pragma unroll
         for (int m = 0; m < BDS_MAXCPT; m++) {
+          if (m * BDS_THREADS >= n_all) break;   // (block-uniform: the slots beyond the list cost nothing)
           const int q = tid + m * BDS_THREADS;
           if (q < n_all) {
             const int k = list[q];
@@ -675,6 +676,7 @@ k_bdrown_smem(BdGeom g, float* Xb, const int32_t* __restrict__ maskb, int mask_p
         __syncthreads();
 #pragma unroll
         for (int m = 0; m < BDS_MAXCPT; m++) {
+          if (m * BDS_THREADS >= n_all) break;
           const int q = tid + m * BDS_THREADS;
           if (q < n_all) X[list[q]] = v[m];
         }
