@@ -188,7 +188,7 @@ int sosie_bilin_2d_first(sosie_ctx* ctx, int32_t k_ew_per, int32_t nx1, int32_t 
                          const int32_t* mask_domain_trg, int32_t l_reg_src, int32_t i_orca_trg, int32_t nslab,
                          int32_t* metrics, double* alphabeta, int16_t* id_problem, float* dist_np);
 /* test hooks of the batched apply (results are identical whichever kernels run).  A batched apply splits the 32x8 target
- * tiles between up to three kernels by the shape of a tile's source box (csrc/bilin_apply.cu): k_apply_grp (groups of 4
+ * tiles between up to three kernels by the shape of a tile's source box (csrc/bilin_apply.cu): k_apply_grp (groups of 8 or 4
  * slabs staged with 16-byte cp.async, one block barrier per group: the default for boxes up to 768 padded cells),
  * k_apply_tma (3-D tensor map of the slab stack, one cp.async.bulk.tensor per tile and group; OFF by default -- switch on
  * with sosie_apply_tma(1) or SOSIE_APPLY_TMA=1 -- because that instruction traps under the gVisor nvproxy driver of the

@@ -198,7 +198,7 @@ __device__ __forceinline__ int tile_owner(const int4& box, int flags) {
 // one block per tile: bounding box (0-based i0, j0, w, h) of the tile's source cells; w == 0 -> not stageable.
 // counts[0..2]: tiles that fit the TMA box / the group-staged kernel / neither; counts[3]: tiles the group kernel does not
 // take, counts[4..6]: tiles of its instantiations with 8 or 4 / 2 / 1 slabs per group; lists: four compact tile lists of ntiles
-// entries each (groups of 4, 2, 1, the rest), so that every kernel is launched over its own tiles only
+// entries each (groups of 8 or 4, of 2, of 1, the rest), so that every kernel is launched over its own tiles only
 __global__ void __launch_bounds__(256)
 k_tilebox(const int4* __restrict__ pidx, SlabView v, TileGeom tgm, int4* boxes, int* counts, int* lists) {
   __shared__ int sh[4][8];
@@ -608,8 +608,8 @@ __device__ __forceinline__ void direct_tile(int tile, const int4* __restrict__ p
 }
 
 // The batched apply of a 16-byte aligned slab stack in ONE launch.  blockIdx.x walks the compact tile lists in the order
-// "direct" tiles, groups of 1, of 2, of 4 slabs: the slow tiles (huge or odd boxes) start first and the many cheap ones fill
-// the tail of the launch.  cnt = lengths of the four lists (4 / 2 / 1 slabs per group, direct), lists = k_tilebox's.
+// "direct" tiles, groups of 1, of 2, of 4 or 8 slabs: the slow tiles (huge or odd boxes) start first and the many cheap ones fill
+// the tail of the launch.  cnt = lengths of the four lists (8 or 4 / 2 / 1 slabs per group, direct), lists = k_tilebox's.
 // tile_list == nullptr (the TMA kernel also runs): every tile is visited and the owner test decides.
 template <bool POST>
 __global__ void __launch_bounds__(256, GRP_MINB)
@@ -968,7 +968,7 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
       int nchunk_g = std::max(1, std::min((nslab + 3) / 4, std::max((waves_blocks + nl - 1) / nl, (nslab + 127) / 128)));
       if (ctx->grp_spc > 0) nchunk_g = std::max(1, (nslab + ctx->grp_spc - 1) / ctx->grp_spc);    // tuning hook (SOSIE_GRP_SPC)
       int spc_g = (nslab + nchunk_g - 1) / nchunk_g;
-      spc_g = (spc_g + 3) / 4 * 4;
+      spc_g = (spc_g + 7) / 8 * 8;   // whole groups of 8 (and of 4, 2): only a block's last group can be incomplete
       const dim3 gg(nl, (nslab + spc_g - 1) / spc_g, 1);
       if (use_clamp || dmask_trg)
         k_apply_grp<true><<<gg, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, nt, v, dnx, dZ1, dZ2, nslab, spc_g, po, tgm, ctx->d_boxes.p, own, lst, cnt);

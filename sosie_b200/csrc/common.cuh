@@ -129,7 +129,7 @@ struct sosie_ctx {
   DBuf<int4> d_pidx;             // packed apply records
   DBuf<float4> d_pw;
   DBuf<int4> d_boxes;            // per-tile source bounding boxes of the staged apply
-  DBuf<int32_t> d_tilelist;      // four compact lists of ntiles entries: tiles of the group-staged kernel with 4 / 2 / 1 slabs per group, the rest
+  DBuf<int32_t> d_tilelist;      // four compact lists of ntiles entries: tiles of the group-staged kernel with 8 or 4 / 2 / 1 slabs per group, the rest
   DBuf<int32_t> d_tilecnt;
   int tiles_cls[4] = {0, 0, 0, 0};   // their lengths
   bool boxes_ready = false;

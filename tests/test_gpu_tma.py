@@ -1,5 +1,5 @@
 """The batched apply splits the target tiles between three kernels (csrc/bilin_apply.cu): the group-staged kernel (16-byte
-cp.async, 4 slabs per block barrier: the default), the 4-byte cp.async kernel (any alignment, odd boxes) and the TMA-staged
+cp.async, 8 / 4 / 2 / 1 slabs per block barrier depending on the tile's box: the default), the 4-byte cp.async kernel (any alignment, odd boxes) and the TMA-staged
 kernel (cp.async.bulk.tensor through a 3-D tensor map; off by default, see profiles/r02_tma_nvproxy.md).  Every combination
 must give the same bits as the oracle.  Also: the reciprocal-based correctly rounded division of these kernels against the
 IEEE division."""
@@ -30,7 +30,7 @@ def _variants(gpu, Z1):
 
 
 @pytest.mark.parametrize("name,scale,nslab", [("D", 0.25, 4), ("D", 0.25, 7), ("D", 0.125, 33), ("D", 0.5, 9), ("E", 0.02, 5), ("A", 0.5, 6),
-                                               ("D", 0.25, 2), ("D", 1.0, 5)])
+                                               ("D", 0.25, 2), ("D", 1.0, 5), ("D", 0.25, 19), ("D", 0.5, 16), ("E", 0.02, 24)])
 def test_batched_apply_kernels_agree_with_oracle(gpu, orc, name, scale, nslab):
     cfg = G.config(name, scale)
     assert cfg["nxs"] % 4 == 0               # 16-byte row pitch: the group-staged kernel is eligible
