@@ -14,7 +14,7 @@ for r in csv.reader(io.StringIO(raw)):
     if r and r[0] == "Line No":
         h = r; continue
     if h and keep and len(r) == len(h) and r[0].isdigit():
-        g = lambda k: r[h.index(k)]
+        g = lambda k: r[h.index(k)] if k in h else "0"   # (a kernel without shared memory has no such column)
         out.append((int(g("Instructions Executed") or 0), int(g("# Samples") or 0), r[0], r[1][:120], g("L1 Wavefronts Shared Excessive"), fn.split("(")[0]))
 tot = sum(o[0] for o in out) or 1; ts = sum(o[1] for o in out) or 1
 print(f"total warp-instructions {tot}, stall samples {ts}")
