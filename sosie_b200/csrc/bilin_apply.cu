@@ -24,15 +24,18 @@
 
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-k_pack(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ MT, const double* __restrict__ AB, int4* pidx,
-       float4* pw, size_t k0, size_t kcnt) {
+k_pack(SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ MT, const double* __restrict__ AB, const float* __restrict__ DNP,
+       int4* pidx, float4* pw, size_t k0, size_t kcnt) {
   const size_t nt = (size_t)tg.nx * tg.ny;
   for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < kcnt; kk += (size_t)gridDim.x * blockDim.x) {
     const size_t k = k0 + kk;
     int jj = (int)(k / tg.nx) + 1, ji = (int)(k % tg.nx) + 1;
     int4 id;
     float4 w;
-    pack_record(sg, k_ew, MT[k], MT[k + nt], MT[k + 2 * nt], AB[k], AB[k + nt], trg_lon(tg, ji, jj), trg_lat(tg, ji, jj), id, w);
+    const bool far = DNP[k] > PACK_FAR_KM;   // (false for NaN)
+    double lon_t = 0.0, lat_t = 0.0;
+    if (!far) { lon_t = trg_lon(tg, ji, jj); lat_t = trg_lat(tg, ji, jj); }
+    pack_record(sg, k_ew, MT[k], MT[k + nt], MT[k + 2 * nt], AB[k], AB[k + nt], lon_t, lat_t, id, w, far);
     pidx[k] = id;
     pw[k] = w;
   }
@@ -94,7 +97,7 @@ template <bool FUSE>
 __global__ void __launch_bounds__(256, FUSE ? APPLY1_FUSE_BLOCKS : 8)
 k_apply1(const int4* __restrict__ pidx, const float4* __restrict__ pw, SlabView v, const float* __restrict__ Z1, float* __restrict__ Z2,
          PostOps po, TileGeom tgm, SrcGeom sg, TrgGeom tg, int k_ew, const int32_t* __restrict__ MT, const double* __restrict__ AB,
-         int4* pidx_out, float4* pw_out) {
+         const float* __restrict__ DNP, int4* pidx_out, float4* pw_out) {
   const size_t nt = FUSE ? (size_t)tg.nx * tg.ny : 0;
   for (int tile = blockIdx.x; tile < tgm.ntiles; tile += gridDim.x) {
     const int ti = tile % tgm.tiles_x, tj = tile / tgm.tiles_x;
@@ -104,8 +107,10 @@ k_apply1(const int4* __restrict__ pidx, const float4* __restrict__ pw, SlabView 
     int4 id;
     float4 w;
     if (FUSE) {
-      pack_record(sg, k_ew, __ldcs(MT + k), __ldcs(MT + k + nt), __ldcs(MT + k + 2 * nt), __ldcs(AB + k), __ldcs(AB + k + nt),
-                  trg_lon(tg, i + 1, j + 1), trg_lat(tg, i + 1, j + 1), id, w);
+      const bool far = __ldcs(DNP + k) > PACK_FAR_KM;   // (false for NaN): no identical-point copy possible, coordinates not read
+      double lon_t = 0.0, lat_t = 0.0;
+      if (!far) { lon_t = trg_lon(tg, i + 1, j + 1); lat_t = trg_lat(tg, i + 1, j + 1); }
+      pack_record(sg, k_ew, __ldcs(MT + k), __ldcs(MT + k + nt), __ldcs(MT + k + 2 * nt), __ldcs(AB + k), __ldcs(AB + k + nt), lon_t, lat_t, id, w, far);
       if (pidx_out) {   // kept for the later calls (not on the very first apply of a mapping: see bilin_apply_impl)
         __stcs(pidx_out + k, id);
         __stcs(pw_out + k, w);
@@ -771,7 +776,7 @@ int bilin_pack_range(sosie_ctx* ctx, size_t k0, size_t kcnt) {
   if ((size_t)ctx->sg.nx * ctx->sg.nyw > 2147483647ULL) { ctx->err = "source slab too large for 32-bit offsets"; return SOSIE_ERR_ARG; }
   CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt));
   if (kcnt == 0) return SOSIE_OK;
-  k_pack<<<grid_for(ctx, kcnt, 256), 256, 0, ctx->stream>>>(ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p, ctx->d_ab.p, ctx->d_pidx.p, ctx->d_pw.p, k0, kcnt);
+  k_pack<<<grid_for(ctx, kcnt, 256), 256, 0, ctx->stream>>>(ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p, ctx->d_ab.p, ctx->d_dnp.p, ctx->d_pidx.p, ctx->d_pw.p, k0, kcnt);
   KLAUNCH_CHECK();
   return SOSIE_OK;
 }
@@ -990,13 +995,13 @@ int bilin_apply_impl(sosie_ctx* ctx, int nslab, const float* dZ1, float* dZ2, in
       const bool store = ctx->unpacked_applies >= 1 || ctx->always_store_records;
       if (store) { CK(ctx->d_pidx.alloc(nt)); CK(ctx->d_pw.alloc(nt)); }
       k_apply1<true><<<grid.x, 256, 0, ctx->stream>>>(nullptr, nullptr, v, dZ1, dZ2, po, tgm, ctx->sg, ctx->tg, ctx->k_ew, ctx->d_metrics.p,
-                                                      ctx->d_ab.p, store ? ctx->d_pidx.p : nullptr, store ? ctx->d_pw.p : nullptr);
+                                                      ctx->d_ab.p, ctx->d_dnp.p, store ? ctx->d_pidx.p : nullptr, store ? ctx->d_pw.p : nullptr);
       KLAUNCH_CHECK();
       if (store) { ctx->pack_ready = true; ctx->pack_gen++; ctx->boxes_ready = false; }
       else ctx->unpacked_applies++;
     } else {
       k_apply1<false><<<grid.x, 256, 0, ctx->stream>>>(ctx->d_pidx.p, ctx->d_pw.p, v, dZ1, dZ2, po, tgm, ctx->sg, ctx->tg, ctx->k_ew, nullptr,
-                                                       nullptr, nullptr, nullptr);   // nslab == 1 here
+                                                       nullptr, nullptr, nullptr, nullptr);   // nslab == 1 here
       KLAUNCH_CHECK();
     }
     prof_end(ctx, SOSIE_T_APPLY);

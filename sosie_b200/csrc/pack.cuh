@@ -9,15 +9,24 @@
 // (iP,jP,iqd,alpha,beta) -> int4 corner offsets in the working source slab (column-major, pole rows included) +
 // float4 REAL(4) weights exactly as INTERP_BL rounds them (src/mod_bilin_2d.f90:299-337); the identical-point copy
 // of the apply loop (:227-230) and INTERP_BL's error codes (:347-356) are encoded in the record.
+// far_from_nearest: the caller KNOWS the target is not the identical-point case and did not load (lon_t, lat_t) -- see
+// PACK_FAR_KM below.  false: the test of the apply loop is evaluated literally.
+//
+// PACK_FAR_KM: the mapping stores dist_np = DISTANCE(target, nearest source point) in km (REAL(4)).  The identical-point
+// copy needs both coordinate differences below 1e-5 degrees, i.e. the two points less than 1.6 m apart, for which DISTANCE
+// (unit vectors, ACOS) returns at most 0.0017 km; beyond 0.01 km the test cannot pass, and its 16 bytes of target
+// coordinates per target need not be read.  A mapping without distances (loaded from a file: dist_np zeroed) and targets
+// the body never reached (dist_np 0) take the literal test.
+#define PACK_FAR_KM 0.01f
 __device__ __forceinline__ void pack_record(const SrcGeom& sg, int k_ew, int iP_raw, int jP_raw, int iqd, double xa, double xb,
-                                            double lon_t, double lat_t, int4& id, float4& w) {
+                                            double lon_t, double lat_t, int4& id, float4& w, bool far_from_nearest = false) {
   const int nxi = sg.nx, nyi = sg.nyw;
   const double eps5 = (double)1.E-5f;
   int iP = max(iP_raw, 1), jP = max(jP_raw, 1);  // IMETRICS(:,:,1:2) = MAX(IMETRICS(:,:,1:2), 1)  (:217)
   w = make_float4(0.f, 0.f, 0.f, 0.f);
   // a stale mapping could hold iP/jP beyond the source: the reference would read out of bounds
   int iPc = min(iP, nxi), jPc = min(jP, nyi);
-  bool same = (fabs(d_degE_to_degWE(src_lon(sg, iPc, jPc)) - d_degE_to_degWE(lon_t)) < eps5) &&
+  bool same = !far_from_nearest && (fabs(d_degE_to_degWE(src_lon(sg, iPc, jPc)) - d_degE_to_degWE(lon_t)) < eps5) &&
               (fabs(src_lat(sg, iPc, jPc) - lat_t) < eps5);
   if (same) {
     id = make_int4(REC_COPY, (iPc - 1) + (jPc - 1) * nxi, 0, 0);

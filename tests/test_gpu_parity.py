@@ -511,7 +511,10 @@ def test_first_guess_quadrant_near_grid_lines(gpu, orc, kind):
         lat = 70.0 + np.arange(ny) * 0.4            # crosses the 89-degree limit of the shortcut
         lat = lat[lat < 89.9]
         ny = lat.size
-    offs = np.array([0.0, 1e-9, -1e-9, 5e-8, -5e-8, 0.99e-7, -0.99e-7, 1e-7, -1e-7, 1.01e-7, -1.01e-7, 3e-7, -3e-7, 1e-3, -1e-3])
+    offs = np.array([0.0, 1e-9, -1e-9, 5e-8, -5e-8, 0.99e-7, -0.99e-7, 1e-7, -1e-7, 1.01e-7, -1.01e-7, 3e-7, -3e-7, 1e-3, -1e-3,
+                     # around the identical-point tolerance of the apply loop (1e-5 degrees) and the distance beyond which the
+                     # apply kernels skip that test (0.01 km ~ 9e-5 degrees)
+                     0.9e-5, -0.9e-5, 1.1e-5, -1.1e-5, 5e-5, -5e-5, 8e-5, 1.0e-4, -2e-4])
     ii = rng.integers(1, nx - 1, 40)
     jj = rng.integers(1, ny - 1, 40)
     cell_x, cell_y = np.abs(lon[1] - lon[0]), np.abs(lat[1] - lat[0])
@@ -521,7 +524,7 @@ def test_first_guess_quadrant_near_grid_lines(gpu, orc, kind):
             for dy in np.concatenate([offs, [0.3 * cell_y, -0.3 * cell_y]]):
                 X.append(np.mod(lon[i] + dx, 360.0)); Y.append(min(max(lat[j] + dy, -89.99), 89.99))
     n = len(X)
-    ncol = 17 * 5
+    ncol = (offs.size + 2) * 5
     nrow = n // ncol
     Xt = np.array(X[:nrow * ncol]).reshape(nrow, ncol)
     Yt = np.array(Y[:nrow * ncol]).reshape(nrow, ncol)
