@@ -35,14 +35,20 @@ __device__ __forceinline__ void pack_record(const SrcGeom& sg, int k_ew, int iP_
   int jiPm1 = iP - 1, jiPp1 = iP + 1;
   if ((jiPm1 == 0) && (k_ew >= 0)) jiPm1 = nxi - k_ew;
   if ((jiPp1 == nxi + 1) && (k_ew >= 0)) jiPp1 = 1 + k_ew;
-  int i1 = 0, j1 = 0, i2 = 0, j2 = 0, i3 = 0, j3 = 0, i4 = 0, j4 = 0;  // Q19 (iqd outside 1..4 cannot occur after the fix-ups)
-  switch (iqd) {
-    case 1: i1 = iP; j1 = jP; i2 = jiPp1; j2 = jP; i3 = jiPp1; j3 = jP + 1; i4 = iP; j4 = jP + 1; break;
-    case 2: i1 = iP; j1 = jP; i2 = iP; j2 = jP - 1; i3 = jiPp1; j3 = jP - 1; i4 = jiPp1; j4 = jP; break;
-    case 3: i1 = iP; j1 = jP; i2 = jiPm1; j2 = jP; i3 = jiPm1; j3 = jP - 1; i4 = iP; j4 = jP - 1; break;
-    case 4: i1 = iP; j1 = jP; i2 = iP; j2 = jP + 1; i3 = jiPm1; j3 = jP + 1; i4 = jiPm1; j4 = jP; break;
-    default: break;
-  }
+  // The four corners of quadrant iqd (:299-327), counter-clockwise from (iP,jP):
+  //   1: (iP,jP) (iP+1,jP) (iP+1,jP+1) (iP,jP+1)      2: (iP,jP) (iP,jP-1) (iP+1,jP-1) (iP+1,jP)
+  //   3: (iP,jP) (iP-1,jP) (iP-1,jP-1) (iP,jP-1)      4: (iP,jP) (iP,jP+1) (iP-1,jP+1) (iP-1,jP)
+  // i.e. the opposite corner is (ix,jy) with ix east for 1, 2 / west for 3, 4 and jy north for 1, 4 / south for 2, 3; odd
+  // quadrants walk along i first, even ones along j first.  Selects instead of a four-way branch (the warps of the apply
+  // kernels mix quadrants).  iqd outside 1..4 (Q19: cannot occur after the fix-ups of MAPPING_BL) leaves all eight at 0.
+  const bool qok = (iqd >= 1) && (iqd <= 4);
+  const int ix = qok ? ((iqd <= 2) ? jiPp1 : jiPm1) : 0;
+  const int jy = qok ? ((iqd == 1 || iqd == 4) ? jP + 1 : jP - 1) : 0;
+  const bool odd = (iqd & 1) != 0;
+  const int i1 = qok ? iP : 0, j1 = qok ? jP : 0;
+  const int i2 = odd ? ix : i1, j2 = odd ? j1 : jy;
+  const int i3 = ix, j3 = jy;
+  const int i4 = odd ? i1 : ix, j4 = odd ? jy : j1;
   float w1 = (float)((1.0 - xa) * (1.0 - xb));
   float w2 = (float)(xa * (1.0 - xb));
   float w3 = (float)(xa * xb);
@@ -50,11 +56,12 @@ __device__ __forceinline__ void pack_record(const SrcGeom& sg, int k_ew, int iP_
   float wup = w1 + w2 + w3 + w4;
   float cst = 0.f;
   bool isc = true;
+  // INTERP_BL's index tests (:347-356), in its order; {i1..i4} = {i1, ix} and {j1..j4} = {j1, jy}
   if (wup == 0.f) cst = -9998.f;
-  else if ((i1 < 1) || (i2 < 1) || (i3 < 1) || (i4 < 1)) cst = -9997.f;
-  else if ((j1 < 1) || (j2 < 1) || (j3 < 1) || (j4 < 1)) cst = -9996.f;
-  else if ((j1 > nyi) || (j2 > nyi) || (j3 > nyi) || (j4 > nyi)) cst = -9995.f;
-  else if ((i1 > nxi) || (i2 > nxi) || (i3 > nxi) || (i4 > nxi)) cst = -9994.f;
+  else if (min(i1, ix) < 1) cst = -9997.f;
+  else if (min(j1, jy) < 1) cst = -9996.f;
+  else if (max(j1, jy) > nyi) cst = -9995.f;
+  else if (max(i1, ix) > nxi) cst = -9994.f;
   else isc = false;
   if (isc) { id = make_int4(REC_CONST, 0, 0, 0); w.x = cst; }
   else {
