@@ -884,12 +884,15 @@ template <bool SEP>
 __global__ void __launch_bounds__(128, MAP_MIN_BLOCKS)
 k_map_easy(const __grid_constant__ SrcGeom sg, const __grid_constant__ TrgGeom tg, int k_ew, const int32_t* __restrict__ mask, const double* __restrict__ vlon,
            const double* __restrict__ vlat, int sorted_lon, int sorted_lat, int jlo, int jhi, int32_t* MT, double* AB,
-           int16_t* IDP, float* DNP, int* err, size_t k0, size_t kcnt, int search_only, const DevPlan* __restrict__ plan) {
+           int16_t* IDP, float* DNP, int* err, size_t k0, size_t kcnt, int search_only, const DevPlan* __restrict__ plan, FastDiv dnx) {
   const size_t nt = (size_t)tg.nx * tg.ny;
+  const bool k32 = (k0 + kcnt) <= 0xffffffffull;   // the row / column split of k by a multiply-high (block-uniform)
   if (plan) { jlo = plan->jlo; jhi = plan->jhi; }   // the searched rows come from the device-side prelude (sosie_bilin_map_async)
   for (size_t kk = blockIdx.x * (size_t)blockDim.x + threadIdx.x; kk < kcnt; kk += (size_t)gridDim.x * blockDim.x) {
     const size_t k = k0 + kk;
-    int jj_t = (int)(k / tg.nx) + 1, ji_t = (int)(k % tg.nx) + 1;
+    int jj_t, ji_t;
+    if (k32) { const unsigned jq = fdiv((unsigned)k, dnx); jj_t = (int)jq + 1; ji_t = (int)((unsigned)k - jq * (unsigned)tg.nx) + 1; }
+    else { jj_t = (int)(k / tg.nx) + 1; ji_t = (int)(k % tg.nx) + 1; }
     int m = mask ? mask[k] : 1;
     int iP = -1, jP = -1;
     double rlon = trg_lon(tg, ji_t, jj_t), rlat = trg_lat(tg, ji_t, jj_t);
@@ -1624,11 +1627,11 @@ static int bilin_easy_rows_plan(sosie_ctx* ctx, int jlo, int jhi, size_t k0, siz
   if (sg.separable)
     k_map_easy<true><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->mask_is_ones ? nullptr : ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
                                                                  ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
-                                                                 ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt, ctx->search_only ? 1 : 0, plan);
+                                                                 ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt, ctx->search_only ? 1 : 0, plan, make_fastdiv((unsigned)tg.nx));
   else
     k_map_easy<false><<<grid_for(ctx, kcnt, 128, 16), 128, 0, st>>>(sg, tg, ctx->k_ew, ctx->mask_is_ones ? nullptr : ctx->t_mask.p, vax, vax + sg.nx, ctx->easy_sorted_lon,
                                                                   ctx->easy_sorted_lat, jlo, jhi, ctx->d_metrics.p, ctx->d_ab.p,
-                                                                  ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt, ctx->search_only ? 1 : 0, plan);
+                                                                  ctx->d_ipb.p, ctx->d_dnp.p, derr, k0, kcnt, ctx->search_only ? 1 : 0, plan, make_fastdiv((unsigned)tg.nx));
   KLAUNCH_CHECK();
   return SOSIE_OK;
 }
