@@ -622,23 +622,18 @@ __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double
   // row's parallel) falls off on both sides of the index-nearest row jc, so the rows are visited outwards from jc as well
   // and a side is abandoned at the first row the bound rejects (rows_unimodal); otherwise all rows j1..j2 are tested.
   // visit order: jc, jc+1, ..., j2 (or the first reject), then jc-1, ..., j1 (or the first reject)
-  const int nrows = j2 - j1 + 1;
-  int jj = rows_unimodal ? jc : j1, dir = 1;
-  for (int it = 0; it < nrows; it++) {
-    if (jj > j2) {                    // (upward side exhausted)
-      if (!rows_unimodal || dir < 0) break;
-      dir = -1; jj = jc - 1;
-    }
-    if (jj < j1) break;
-    const int jrow = jj;
-    jj += dir;
+  // two sides: upwards from jc (from j1 when the rows are not unimodal: then every row is tested and there is no second side),
+  // then downwards from jc - 1
+  for (int side = 0; side < 2; side++) {
+    if (side && !rows_unimodal) break;
+    const int jbeg = side ? jc - 1 : (rows_unimodal ? jc : j1), jend = side ? j1 : j2, jstep = side ? -1 : 1;
+  for (int jrow = jbeg; side ? (jrow >= jend) : (jrow <= jend); jrow += jstep) {
     const double cl = sg.clat[jrow - 1], sl = sg.slat[jrow - 1];
     const double c0 = uz * sl;
     const double thr = p1 - (PDS_MARGIN + 1.0e-14);
     if (fabs(cl) * acl + c0 < thr) {
       if (!rows_unimodal) continue;
-      if (dir > 0) { dir = -1; jj = jc - 1; continue; }
-      break;
+      break;   // this side is exhausted
     }
     auto cand = [&](int ji) -> bool {   // false: the cheap form rejects the column
       const double c = sg.clon[ji - 1], s = sg.slon[ji - 1];
@@ -656,6 +651,7 @@ __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double
       for (int ji = i1; ji <= i2; ji++)
         if (!(jrow == jc && ji == ic)) cand(ji);
     }
+  }
   }
   if (p2 >= p1 - PDS_MARGIN) { scan_window_exact<SEP>(sg, ux, uy, uz, i1, i2, j1, j2, b, ic, jc); return; }
   b.pds = p1; b.i = bi; b.j = bj;
