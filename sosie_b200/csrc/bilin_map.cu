@@ -621,37 +621,37 @@ __device__ __forceinline__ void scan_window(const SrcGeom& sg, double ux, double
   // rows: with a sorted latitude axis the row bound |clat_j|*acl + uz*slat_j (the cosine of the target's distance to the
   // row's parallel) falls off on both sides of the index-nearest row jc, so the rows are visited outwards from jc as well
   // and a side is abandoned at the first row the bound rejects (rows_unimodal); otherwise all rows j1..j2 are tested.
-  // visit order: jc, jc+1, ..., j2 (or the first reject), then jc-1, ..., j1 (or the first reject)
-  // two sides: upwards from jc (from j1 when the rows are not unimodal: then every row is tested and there is no second side),
-  // then downwards from jc - 1
+  // Visit order: jc, jc+1, ..., j2 (or the first reject), then jc-1, ..., j1 (or the first reject) -- two plain loops (a single
+  // loop with a direction variable spent a quarter of the scan's instructions on its own control flow).  Rows that are not
+  // unimodal: one side, j1..j2, every row tested.
   for (int side = 0; side < 2; side++) {
     if (side && !rows_unimodal) break;
     const int jbeg = side ? jc - 1 : (rows_unimodal ? jc : j1), jend = side ? j1 : j2, jstep = side ? -1 : 1;
-  for (int jrow = jbeg; side ? (jrow >= jend) : (jrow <= jend); jrow += jstep) {
-    const double cl = sg.clat[jrow - 1], sl = sg.slat[jrow - 1];
-    const double c0 = uz * sl;
-    const double thr = p1 - (PDS_MARGIN + 1.0e-14);
-    if (fabs(cl) * acl + c0 < thr) {
-      if (!rows_unimodal) continue;
-      break;   // this side is exhausted
+    for (int jrow = jbeg; side ? (jrow >= jend) : (jrow <= jend); jrow += jstep) {
+      const double cl = sg.clat[jrow - 1], sl = sg.slat[jrow - 1];
+      const double c0 = uz * sl;
+      const double thr = p1 - (PDS_MARGIN + 1.0e-14);
+      if (fabs(cl) * acl + c0 < thr) {
+        if (!rows_unimodal) continue;
+        break;   // this side is exhausted
+      }
+      auto cand = [&](int ji) -> bool {   // false: the cheap form rejects the column
+        const double c = sg.clon[ji - 1], s = sg.slon[ji - 1];
+        if (cl * (ux * c + uy * s) + c0 < thr) return false;
+        const double zpds = ux * (c * cl) + uy * (s * cl) + uz * sl;
+        if (zpds > p1) { p2 = p1; p1 = zpds; bi = ji; bj = jrow; }
+        else p2 = fmax(p2, zpds);
+        return true;
+      };
+      if (unimodal && cl >= 0.0) {
+        if (jrow != jc) { if (!cand(ic)) continue; }   // (on row jc the centre seeded p1)
+        for (int ji = ic + 1; ji <= i2; ji++) if (!cand(ji)) break;
+        for (int ji = ic - 1; ji >= i1; ji--) if (!cand(ji)) break;
+      } else {
+        for (int ji = i1; ji <= i2; ji++)
+          if (!(jrow == jc && ji == ic)) cand(ji);
+      }
     }
-    auto cand = [&](int ji) -> bool {   // false: the cheap form rejects the column
-      const double c = sg.clon[ji - 1], s = sg.slon[ji - 1];
-      if (cl * (ux * c + uy * s) + c0 < thr) return false;
-      const double zpds = ux * (c * cl) + uy * (s * cl) + uz * sl;
-      if (zpds > p1) { p2 = p1; p1 = zpds; bi = ji; bj = jrow; }
-      else p2 = fmax(p2, zpds);
-      return true;
-    };
-    if (unimodal && cl >= 0.0) {
-      if (jrow != jc) { if (!cand(ic)) continue; }   // (on row jc the centre seeded p1)
-      for (int ji = ic + 1; ji <= i2; ji++) if (!cand(ji)) break;
-      for (int ji = ic - 1; ji >= i1; ji--) if (!cand(ji)) break;
-    } else {
-      for (int ji = i1; ji <= i2; ji++)
-        if (!(jrow == jc && ji == ic)) cand(ji);
-    }
-  }
   }
   if (p2 >= p1 - PDS_MARGIN) { scan_window_exact<SEP>(sg, ux, uy, uz, i1, i2, j1, j2, b, ic, jc); return; }
   b.pds = p1; b.i = bi; b.j = bj;
