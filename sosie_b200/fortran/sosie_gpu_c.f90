@@ -253,6 +253,61 @@ MODULE SOSIE_GPU_C
          IMPORT :: C_PTR, C_INT
          TYPE(C_PTR), VALUE :: p
       END FUNCTION
+      ! ---- entries a maintainer needs beyond the four drop-in modules ----------------------------------------------------
+      INTEGER(C_INT) FUNCTION sosie_sync(ctx) BIND(C, name='sosie_sync')
+         !! waits for the context's stream; reports the deferred status of an asynchronous mapping
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: ctx
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_set_shard(ctx, j0, j1) BIND(C, name='sosie_bilin_set_shard')
+         !! this process owns target rows j0..j1 (1-based, inclusive; 0, 0 = all): one process per GPU (INTEGRATION.md 4b)
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: j0, j1
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_bilin_map_info(ctx, info) BIND(C, name='sosie_bilin_map_info')
+         !! what FIND_NEAREST_POINT / MAPPING_BL print: search kind, row range, counts of problem points (include/sosie_b200.h)
+         IMPORT :: C_PTR, C_INT
+         TYPE(C_PTR), VALUE :: ctx
+         INTEGER(C_INT)     :: info(*)
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_angle2(ctx, nperio, nx, ny, plamt, pphit, plamu, pphiu, plamv, pphiv, plamf, pphif, &
+         &                                 gcost, gsint, gcosu, gsinu, gcosv, gsinv, gcosf, gsinf) BIND(C, name='sosie_angle2')
+         !! ANGLE2 (mod_nemotools.f90:607-823) for corr_vect: the eight rotation arrays of the T / U / V / F points
+         IMPORT :: C_PTR, C_INT, C_DOUBLE
+         TYPE(C_PTR), VALUE    :: ctx
+         INTEGER(C_INT), VALUE :: nperio, nx, ny
+         REAL(C_DOUBLE), INTENT(in)  :: plamt(*), pphit(*), plamu(*), pphiu(*), plamv(*), pphiv(*), plamf(*), pphif(*)
+         REAL(C_DOUBLE), INTENT(out) :: gcost(*), gsint(*), gcosu(*), gsinu(*), gcosv(*), gsinv(*), gcosf(*), gsinf(*)
+      END FUNCTION
+      ! binary twin of P2D_MAPPING_AB / RD_MAPPING_AB (io_ezcdf.f90:2195-2304) for builds without NetCDF; path: a
+      ! NUL-terminated CHARACTER(KIND=C_CHAR) array (TRIM(cf)//C_NULL_CHAR); dist_np may be C_NULL_PTR
+      INTEGER(C_INT) FUNCTION sosie_mapping_write_bin(path, nx, ny, lon, lat, metrics, alphabeta, id_problem, dist_np, vflag) &
+         &           BIND(C, name='sosie_mapping_write_bin')
+         IMPORT :: C_PTR, C_INT, C_DOUBLE, C_SHORT, C_CHAR
+         CHARACTER(KIND=C_CHAR), INTENT(in) :: path(*)
+         INTEGER(C_INT), VALUE        :: nx, ny
+         REAL(C_DOUBLE), INTENT(in)   :: lon(*), lat(*), alphabeta(*)
+         INTEGER(C_INT), INTENT(in)   :: metrics(*)
+         INTEGER(C_SHORT), INTENT(in) :: id_problem(*)
+         TYPE(C_PTR), VALUE           :: dist_np
+         REAL(C_DOUBLE), VALUE        :: vflag
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_mapping_read_header_bin(path, nx, ny, has_dist_np) BIND(C, name='sosie_mapping_read_header_bin')
+         IMPORT :: C_INT, C_CHAR
+         CHARACTER(KIND=C_CHAR), INTENT(in) :: path(*)
+         INTEGER(C_INT), INTENT(out) :: nx, ny, has_dist_np
+      END FUNCTION
+      INTEGER(C_INT) FUNCTION sosie_mapping_read_bin(path, nx, ny, lon, lat, metrics, alphabeta, id_problem, dist_np) &
+         &           BIND(C, name='sosie_mapping_read_bin')
+         IMPORT :: C_PTR, C_INT, C_DOUBLE, C_SHORT, C_CHAR
+         CHARACTER(KIND=C_CHAR), INTENT(in) :: path(*)
+         INTEGER(C_INT), VALUE         :: nx, ny
+         TYPE(C_PTR), VALUE            :: lon, lat, dist_np      ! C_NULL_PTR: not wanted
+         INTEGER(C_INT), INTENT(out)   :: metrics(*)
+         REAL(C_DOUBLE), INTENT(out)   :: alphabeta(*)
+         INTEGER(C_SHORT), INTENT(out) :: id_problem(*)
+      END FUNCTION
    END INTERFACE
 
    !! Asynchronous mode of the drop-in modules (GPU_ASYNC_BEGIN / GPU_FLUSH below).  While it is on, the non-first calls of
