@@ -137,3 +137,52 @@ def test_every_fortran_interface_matches_a_header_prototype():
                 if not byval and kind != "ptr" and ctype not in ("any", kind):
                     problems.append(f"{cname} arg {pos + 1} '{a}': C element type {ctype}, Fortran {kind}")
     assert not problems, "\n".join(problems)
+
+
+def _f_calls(path):
+    """(name, number of actual arguments) of every sosie_* reference in a Fortran source (continuation lines joined)"""
+    text = open(path).read().split("\n")
+    joined, cur = [], ""
+    for ln in text:
+        ln = ln.split("!")[0].rstrip()
+        s = ln.strip()
+        if not s:
+            continue
+        if s.startswith("&"):
+            s = s[1:].strip()
+        cur = (cur + " " + s) if cur else s
+        if cur.endswith("&"):
+            cur = cur[:-1].rstrip()
+            continue
+        joined.append(cur); cur = ""
+    calls = []
+    for ln in joined:
+        if re.match(r"(?i)^\s*(INTEGER|TYPE|REAL)\b.*\bFUNCTION\b", ln) or re.match(r"(?i)^\s*END\b", ln):
+            continue
+        for m in re.finditer(r"\b(sosie_\w+)\s*\(", ln):
+            depth, j = 1, m.end()
+            while j < len(ln) and depth:
+                depth += ln[j] == "("
+                depth -= ln[j] == ")"
+                j += 1
+            inner = ln[m.end():j - 1]
+            calls.append((m.group(1), len([a for a in _split_args(inner) if a.strip()])))
+    return calls
+
+
+def test_drop_in_modules_call_the_interfaces_with_the_right_number_of_arguments():
+    ifs = _f_interfaces()
+    fdir = os.path.join(ROOT, "sosie_b200", "fortran")
+    seen, problems = 0, []
+    for fn in sorted(os.listdir(fdir)):
+        if not fn.endswith(".f90"):
+            continue
+        for name, nargs in _f_calls(os.path.join(fdir, fn)):
+            if name not in ifs:
+                problems.append(f"{fn}: {name} has no interface in sosie_gpu_c.f90")
+                continue
+            seen += 1
+            if nargs != len(ifs[name][1]):
+                problems.append(f"{fn}: {name} called with {nargs} arguments, its interface has {len(ifs[name][1])}")
+    assert seen >= 20, f"only {seen} calls found"
+    assert not problems, "\n".join(problems)
