@@ -154,6 +154,16 @@ __global__ void __launch_bounds__(1024) k_prelude_head(TrgGeom tg, const double*
     p->irreg_s = 0; p->irreg_t = 0; p->j_strt = 2147483647; p->j_stop = 0; p->err = 0; p->rtmp = 0.0;
   }
   __syncthreads();
+  // Early verdict for k_is_regular (which follows on the stream): ONE term |Xlon(i,2) - Xlon(i,1)| above the tolerance makes the
+  // row sum of L_IS_GRID_REGULAR (:1647-1652) exceed it -- a sum of non-negative terms is at least each of them, in any
+  // order -- so a curvilinear target is settled here from 1024 columns of two rows, and every block of k_is_regular leaves
+  // at its first look at the flag instead of summing a first wave of 592 rows (40 MB on the eNATL60-shaped target).
+  if (!tg.is_1d && tg.ny >= 2) {
+    const double tol = (double)1.E-12f;
+    int hit = 0;
+    for (int i = threadIdx.x; i < min(tg.nx, 1024); i += blockDim.x) hit |= (fabs(tg.X[(size_t)i + (size_t)tg.nx] - tg.X[i]) > tol);
+    if (__syncthreads_or(hit) && threadIdx.x == 0) atomicOr(&p->irreg_t, 1);
+  }
   if (!do_dlat) return;
   // ---- k_rtmp (same code: sign census, sequential sum only for mixed signs)
   __shared__ double sh[1024];
