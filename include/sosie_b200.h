@@ -71,7 +71,7 @@ int sosie_bilin_set_shard(sosie_ctx* ctx, int32_t j0, int32_t j1);
  * sosie_exchange_used: 1 when the last first call took the exchange path.                                          */
 typedef int (*sosie_allgather_fn)(void* user, const void* send, void* recv, size_t bytes_per_rank);
 int sosie_set_exchange(sosie_ctx* ctx, int32_t nranks, sosie_allgather_fn fn, void* user);
-int sosie_exchange_used(sosie_ctx* ctx);
+int sosie_exchange_used(sosie_ctx* ctx);   /* 0 no exchange, 1 callback (host or device), 2 peer memory */
 
 /* ---- bilinear: grids -> mapping -> apply -------------------------------------------------------
  * Replaces BILIN_2D / MAPPING_BL / INTERP_BL, src/mod_bilin_2d.f90:44-361,366-691, and the search
@@ -128,6 +128,17 @@ int sosie_bilin_map_async(sosie_ctx* ctx);
  * array (min / max / first occurrence in row order).  fn = NULL switches it off (every rank then reduces the whole array). */
 typedef int (*sosie_allgather_dev_fn)(void* user, const void* dsend, void* drecv, size_t bytes_per_rank, void* cuda_stream);
 int sosie_set_exchange_dev(sosie_ctx* ctx, int32_t nranks, sosie_allgather_dev_fn fn, void* user);
+/* The same exchange WITHOUT a collective call: one producer kernel and one consumer kernel over peer memory (NVLink P2P
+ * stores).  sosie_p2p_init allocates this rank's mailbox (slot_bytes per rank and parity; 0 = 2 MB, enough for 87 000 target
+ * columns) and returns its 64-byte CUDA IPC handle (ipc_handle_out, may be NULL) and its device address (mailbox_out, may be
+ * NULL).  The ranks swap the handles any way they like (MPI_Allgather, torch.distributed) and call sosie_p2p_connect with
+ * the nranks * 64 bytes -- or, for contexts of ONE process, with the nranks mailbox addresses.  From then on a sharded
+ * sosie_bilin_map[_async] on resident grids writes its prelude record straight into every rank's mailbox and merges the
+ * records once all have arrived; it takes precedence over sosie_set_exchange_dev.  Every rank must run the same number of
+ * mappings; a record that does not arrive within ~2 s is reported by the next synchronising entry (SOSIE_ERR_STATE).
+ * Where CUDA IPC is not available the calls fail with SOSIE_ERR_CUDA and the callback exchange remains.                   */
+int sosie_p2p_init(sosie_ctx* ctx, int32_t nranks, int32_t rank, size_t slot_bytes, void* ipc_handle_out, void** mailbox_out);
+int sosie_p2p_connect(sosie_ctx* ctx, const void* ipc_handles, void* const* mailboxes);
 /* copy the cached mapping to host arrays (what P2D_MAPPING_AB, src/io_ezcdf.f90:2195, writes).
  * Any pointer may be NULL.  mask_out receives mask_domain_trg as modified by the search (-1/-2).
  * A sharded context (sosie_bilin_set_shard) copies only its own target rows; the others are left untouched. */

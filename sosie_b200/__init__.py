@@ -47,7 +47,7 @@ EXPORTS = [
     "sosie_track_interp", "sosie_track_interp_dev", "sosie_set_exchange", "sosie_exchange_used", "sosie_find_nearest_point",
     "sosie_bilin_apply_enqueue", "sosie_akima_apply_enqueue", "sosie_bdrown_enqueue", "sosie_flush", "sosie_set_queue_depth",
     "sosie_queue_stats", "sosie_host_alloc", "sosie_host_free", "sosie_apply_tma", "sosie_apply_tile_classes", "sosie_selftest_div",
-    "sosie_bilin_map_async", "sosie_set_exchange_dev", "sosie_bilin_src_axes_hint",
+    "sosie_bilin_map_async", "sosie_set_exchange_dev", "sosie_bilin_src_axes_hint", "sosie_p2p_init", "sosie_p2p_connect",
 ]
 
 _lib = None
@@ -266,7 +266,8 @@ class Sosie:
         self._ck(self._lib.sosie_set_exchange(self._h, int(nranks), self._xchg_cb, None))
 
     def exchange_used(self):
-        return bool(self._lib.sosie_exchange_used(self._h))
+        """0: no exchange; 1: callback exchange (host or device); 2: peer-memory exchange"""
+        return int(self._lib.sosie_exchange_used(self._h))
 
     def bilin_set_grids(self, k_ew_per, X10, Y10, X20, Y20, mask_domain_trg=None, l_reg_src=False, i_orca_trg=0):
         X10, Y10, X20, Y20 = _f64(X10), _f64(Y10), _f64(X20), _f64(Y20)
@@ -336,6 +337,32 @@ class Sosie:
                 return 1
         self._xchg_dev_cb = self.ALLGATHER_DEV_FN(_cb)   # keep the trampoline alive
         self._ck(self._lib.sosie_set_exchange_dev(self._h, int(nranks), self._xchg_dev_cb, None))
+
+    def p2p_init(self, nranks, rank, slot_bytes=0):
+        """mailbox of the peer-memory prelude exchange (sosie_p2p_init): returns (64-byte CUDA IPC handle or None when IPC is
+        not available, device address of the mailbox)"""
+        h = (C.c_ubyte * 64)()
+        box = C.c_void_p()
+        lib = self._lib
+        lib.sosie_p2p_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]
+        rc = lib.sosie_p2p_init(self._h, int(nranks), int(rank), int(slot_bytes), h, C.byref(box))
+        if rc == 1 and box.value:      # SOSIE_ERR_CUDA from cudaIpcGetMemHandle: the mailbox exists, same-process peers can use it
+            return None, int(box.value)
+        self._ck(rc)
+        return bytes(h), int(box.value)
+
+    def p2p_connect(self, handles=None, mailboxes=None):
+        """sosie_p2p_connect: `handles` = the ranks' 64-byte IPC handles in rank order (processes), or `mailboxes` = their device
+        addresses (contexts of one process)"""
+        lib = self._lib
+        lib.sosie_p2p_connect.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+        if mailboxes is not None:
+            arr = (C.c_void_p * len(mailboxes))(*[int(m) for m in mailboxes])
+            self._ck(lib.sosie_p2p_connect(self._h, None, arr))
+        else:
+            blob = b"".join(handles)
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            self._ck(lib.sosie_p2p_connect(self._h, buf, None))
 
     def bilin_get_map(self):
         nx1, ny1, nx2, ny2 = self._shape

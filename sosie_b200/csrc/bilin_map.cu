@@ -295,6 +295,111 @@ __global__ void k_colpart_combine(int nx, int nchunk, const ColPart* __restrict_
     out[i] = r;
   }
 }
+// ---- the prelude exchange as ONE producer kernel and ONE consumer kernel over peer memory (no collective call) -----------
+// Every rank owns a mailbox (sosie_p2p_init) that its peers mapped through CUDA IPC (sosie_p2p_connect).  k_xchg_push is
+// k_colpart_combine whose output goes, with plain stores over NVLink, into slot [parity][my rank] of EVERY rank's mailbox;
+// the last block to finish raises flag [parity][my rank] = epoch on every rank (data first, system-scope fence, then the
+// flag).  k_xchg_merge is k_prelude_merge on the local mailbox once all nranks flags show the epoch.  Two parities: a
+// rank cannot be two exchanges ahead of a peer (its merge of exchange e+1 needs the peer's push of e+1, which the peer
+// issues after its own merge of e), so the slot it overwrites for e+2 has been consumed.  The consumer's wait is bounded
+// (P2P_SPIN_CYCLES): a peer that never arrives is an error at the next synchronising entry, not a hung GPU.
+#define P2P_SPIN_CYCLES 4000000000LL   // ~2 s at 1.9 GHz
+__host__ __device__ inline size_t p2p_flags_offset(int nranks, size_t slot) { return 2 * (size_t)nranks * slot; }
+__global__ void __launch_bounds__(128)
+k_xchg_push(int nx, int nchunk, const ColPart* __restrict__ part, const Prelude* p, int ja, int jb, unsigned char* const* __restrict__ peers,
+            int nranks, int rank, size_t slot, int par, unsigned epoch, unsigned* done) {
+  const size_t my = ((size_t)par * nranks + rank) * slot;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    XchgHead h;
+    h.j_a = ja; h.j_b = jb; h.irreg_t = p->irreg_t; h.nx = nx;
+    h.ymin_t = p->ymin_t; h.ymax_t = p->ymax_t; h.rmin_dlat = p->rmin_dlat; h.rtmp = p->rtmp;
+    for (int q = 0; q < nranks; q++) *reinterpret_cast<XchgHead*>(peers[q] + my) = h;
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    ColPart r;
+    r.emin = ~0ULL; r.emax = 0ULL; r.jmin = 0; r.jmax = 0;
+    for (int c = 0; c < nchunk; c++) {
+      const ColPart cp = part[(size_t)c * nx + i];
+      if (cp.jmin > 0 && cp.emin < r.emin) { r.emin = cp.emin; r.jmin = cp.jmin; }
+      if (cp.jmax > 0 && (cp.emax > r.emax || r.jmax == 0)) { r.emax = cp.emax; r.jmax = cp.jmax; }
+    }
+    for (int q = 0; q < nranks; q++) reinterpret_cast<ColPart*>(peers[q] + my + sizeof(XchgHead))[i] = r;
+  }
+  __threadfence_system();   // this thread's stores are visible to every GPU before the block reports
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(done, 1u);
+    if (t == gridDim.x - 1) {   // every block has reported: the record is complete on every rank
+      *done = 0;
+      __threadfence_system();
+      const size_t foff = p2p_flags_offset(nranks, slot) + ((size_t)par * nranks + rank) * sizeof(unsigned);
+      for (int q = 0; q < nranks; q++) *reinterpret_cast<volatile unsigned*>(peers[q] + foff) = epoch;
+      __threadfence_system();
+    }
+  }
+}
+__device__ __forceinline__ ColPart ldcg_colpart(const ColPart* q) {   // L2 only: the lines were written by other GPUs
+  ColPart c;
+  const unsigned long long* u = reinterpret_cast<const unsigned long long*>(q);
+  c.emin = __ldcg(u); c.emax = __ldcg(u + 1);
+  const unsigned long long jj = __ldcg(u + 2);
+  c.jmin = (int)(unsigned)(jj & 0xffffffffull); c.jmax = (int)(unsigned)(jj >> 32);
+  return c;
+}
+__global__ void __launch_bounds__(256)
+k_xchg_merge(int nranks, const unsigned char* __restrict__ box, size_t slot, int par, unsigned epoch, int nx, int ny, Prelude* p) {
+  __shared__ int order[256];
+  __shared__ int bad;
+  const unsigned char* all = box + (size_t)par * nranks * slot;
+  if (threadIdx.x == 0) {
+    bad = 0;
+    const volatile unsigned* flags = reinterpret_cast<const volatile unsigned*>(box + p2p_flags_offset(nranks, slot)) + (size_t)par * nranks;
+    const long long t0 = clock64();
+    for (int r = 0; r < nranks && !bad; r++)
+      while (flags[r] != epoch) {
+        if (clock64() - t0 > P2P_SPIN_CYCLES) { bad = 2; break; }
+        __nanosleep(200);
+      }
+    __threadfence_system();
+    if (bad) { if (blockIdx.x == 0) atomicOr(&p->err, 4); }
+    else {
+      for (int r = 0; r < nranks; r++) order[r] = r;
+      for (int a = 1; a < nranks; a++) {   // insertion sort by first row
+        const int v = order[a];
+        const int ja = __ldcg(&reinterpret_cast<const XchgHead*>(all + slot * (size_t)v)->j_a);
+        int b = a - 1;
+        while (b >= 0 && __ldcg(&reinterpret_cast<const XchgHead*>(all + slot * (size_t)order[b])->j_a) > ja) { order[b + 1] = order[b]; b--; }
+        order[b + 1] = v;
+      }
+      int expect = 1;
+      for (int q = 0; q < nranks; q++) {
+        const XchgHead* h = reinterpret_cast<const XchgHead*>(all + slot * (size_t)order[q]);
+        const int hja = __ldcg(&h->j_a), hjb = __ldcg(&h->j_b);
+        if (__ldcg(&h->nx) != nx || hja != expect || hjb < hja) bad = 1;
+        expect = hjb + 1;
+        if (blockIdx.x == 0) {
+          atomicMin(&p->ymin_t, __ldcg(&h->ymin_t)); atomicMax(&p->ymax_t, __ldcg(&h->ymax_t)); atomicMin(&p->rmin_dlat, __ldcg(&h->rmin_dlat));
+        }
+      }
+      if (expect != ny + 1) bad = 1;
+      if (bad && blockIdx.x == 0) atomicOr(&p->err, 2);
+    }
+  }
+  __syncthreads();
+  if (bad) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += gridDim.x * blockDim.x) {
+    unsigned long long emin = ~0ULL, emax = 0ULL;
+    int jmin = 0, jmax = 0;
+    for (int q = 0; q < nranks; q++) {
+      const ColPart cp = ldcg_colpart(reinterpret_cast<const ColPart*>(all + slot * (size_t)order[q] + sizeof(XchgHead)) + i);
+      if (cp.jmin > 0 && cp.emin < emin) { emin = cp.emin; jmin = cp.jmin; }
+      if (cp.jmax > 0 && (cp.emax > emax || jmax == 0)) { emax = cp.emax; jmax = cp.jmax; }
+    }
+    if (jmin > 0) atomicMin(&p->j_strt, jmin);
+    atomicMax(&p->j_stop, jmax);
+  }
+}
+
 // ---- the prelude's decisions ON THE DEVICE (regular source: the EASY search is known to run, only its row range depends
 // on the target) -- the host part prelude_finish() restated as a kernel, so that sosie_bilin_map_async needs no round trip
 struct DevPlan { int jlo, jhi, j_strt, j_stop, icr, err; };   // err 1: rows not covered (the reference loops out of bounds), 2: shards do not tile the grid
@@ -1875,8 +1980,22 @@ static int bilin_map_device_plan(sosie_ctx* ctx, bool async) {
   const bool sharded = ctx->shard_j0 >= 1;
   const size_t blob = sizeof(XchgHead) + sizeof(ColPart) * (size_t)tg.nx;
   const bool xchg = sharded && ctx->xchg_dev_fn && ctx->xchg_dev_nranks >= 2 && ctx->xchg_dev_nranks <= 256 && !tg.is_1d;
+  const bool xp2p = sharded && ctx->p2p_ready && ctx->p2p_nranks >= 2 && !tg.is_1d && blob <= ctx->p2p_slot;
   ctx->xchg_used = 0;
-  if (xchg) {
+  if (xp2p) {
+    // one producer + one consumer kernel over peer memory instead of combine + collective + merge
+    const int ja = ctx->shard_j0, jb = ctx->shard_j1;
+    const int nchunk = (jb - ja + 1 + JR_ROWS - 1) / JR_ROWS;
+    WS(ColPart, part, (size_t)tg.nx * nchunk);
+    const unsigned epoch = ++ctx->p2p_epoch;
+    const int par = (int)(epoch & 1u);
+    k_ypass<<<grid_for(ctx, (size_t)tg.nx * nchunk, 256), 256, 0, st>>>(tg, dp, do_dlat, part.p, ja, jb); KLAUNCH_CHECK();
+    k_xchg_push<<<cdiv(tg.nx, 128), 128, 0, st>>>(tg.nx, nchunk, part.p, dp, ja, jb, ctx->p2p_peers_dev, ctx->p2p_nranks, ctx->p2p_rank, ctx->p2p_slot,
+                                                  par, epoch, ctx->p2p_done); KLAUNCH_CHECK();
+    k_xchg_merge<<<std::max(1, std::min(64, cdiv(tg.nx, 256))), 256, 0, st>>>(ctx->p2p_nranks, ctx->p2p_box, ctx->p2p_slot, par, epoch, tg.nx, tg.ny, dp);
+    KLAUNCH_CHECK();
+    ctx->xchg_used = 2;
+  } else if (xchg) {
     const int ja = ctx->shard_j0, jb = ctx->shard_j1;
     const int nchunk = (jb - ja + 1 + JR_ROWS - 1) / JR_ROWS;
     WS(ColPart, part, (size_t)tg.nx * nchunk);
@@ -1921,7 +2040,8 @@ int bilin_map_check(sosie_ctx* ctx) {
   ctx->map_info[3] = 1; ctx->map_info[4] = (h.p.irreg_t == 0); ctx->map_info[5] = 0; ctx->map_info[6] = 0; ctx->map_info[7] = ctx->l_add_extra_j;
   const char* msg = nullptr;
   int code = SOSIE_ERR_REF_STOP;
-  if (h.plan.err & 2) { msg = "prelude exchange: the ranks' row shards do not tile the target grid"; code = SOSIE_ERR_ARG; }
+  if (h.plan.err & 4) { msg = "prelude exchange over peer memory: a rank's record did not arrive in time (did every rank call the mapping?)"; code = SOSIE_ERR_STATE; }
+  else if (h.plan.err & 2) { msg = "prelude exchange: the ranks' row shards do not tile the target grid"; code = SOSIE_ERR_ARG; }
   else if (h.plan.err & 1) msg = "FIND_NEAREST_POINT: target latitudes not covered by the source (the reference loops out of bounds)";
   else if (herr & 1) msg = "ERROR (L_InPoly of mod_poly.f90): we only expect positive longitudes!";
   else if (herr & 6) msg = "FIND_NEAREST: The nearest point was not found! (ji_s or jj_s = 0)";

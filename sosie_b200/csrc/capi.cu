@@ -15,6 +15,18 @@ int fill_i32_dev(sosie_ctx* ctx, int32_t* p, size_t n, int32_t v);
   if (cudaSetDevice(ctx->device) != cudaSuccess) { ctx->err = "cudaSetDevice failed"; return SOSIE_ERR_CUDA; } \
   if (ctx->q && queue_pending(ctx)) { if (int rcq__ = queue_flush(ctx)) return rcq__; }   /* a synchronous entry delivers the queued results first */
 
+// peer-memory prelude exchange: mailbox life cycle (entries below, kernels in bilin_map.cu)
+static void p2p_release(sosie_ctx* ctx) {
+  for (int r = 0; r < 256; r++)
+    if (ctx->p2p_opened[r]) { cudaIpcCloseMemHandle(ctx->p2p_opened[r]); ctx->p2p_opened[r] = nullptr; }
+  if (ctx->p2p_peers_dev) { cudaFree(ctx->p2p_peers_dev); ctx->p2p_peers_dev = nullptr; }
+  if (ctx->p2p_done) { cudaFree(ctx->p2p_done); ctx->p2p_done = nullptr; }
+  if (ctx->p2p_box) { cudaFree(ctx->p2p_box); ctx->p2p_box = nullptr; }
+  ctx->p2p_ready = false; ctx->p2p_nranks = 0; ctx->p2p_rank = -1; ctx->p2p_slot = 0; ctx->p2p_epoch = 0;
+}
+void p2p_destroy(sosie_ctx* ctx) { p2p_release(ctx); }
+
+
 extern "C" {
 
 const char* sosie_version(void) { return "sosie_b200 0.1 (sm_100a)"; }
@@ -44,6 +56,7 @@ int sosie_destroy(sosie_ctx* c) {
   cudaSetDevice(c->device);
   if (c->q) { queue_flush(c); queue_destroy(c); }
   cudaStreamSynchronize(c->stream);
+  p2p_destroy(c);
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
   return SOSIE_OK;
@@ -197,6 +210,62 @@ int sosie_set_exchange_dev(sosie_ctx* c, int32_t nranks, sosie_allgather_dev_fn 
   NEED(c);
   if (fn && (nranks < 1 || nranks > 256)) { ctx->err = "sosie_set_exchange_dev: nranks must be in 1..256"; return SOSIE_ERR_ARG; }
   ctx->xchg_dev_fn = fn; ctx->xchg_dev_user = user; ctx->xchg_dev_nranks = fn ? nranks : 0;
+  return SOSIE_OK;
+}
+
+// ---- prelude exchange over peer memory (see k_xchg_push / k_xchg_merge in bilin_map.cu) ------------------------------------
+int sosie_p2p_init(sosie_ctx* c, int32_t nranks, int32_t rank, size_t slot_bytes, void* ipc_handle_out, void** mailbox_out) {
+  NEED(c);
+  if (nranks < 2 || nranks > 256 || rank < 0 || rank >= nranks) { ctx->err = "sosie_p2p_init: nranks in 2..256, 0 <= rank < nranks"; return SOSIE_ERR_ARG; }
+  if (slot_bytes == 0) slot_bytes = (size_t)2 << 20;   // 2 MB: 64 B + 24 B per target column, 87 000 columns
+  slot_bytes = (slot_bytes + 255) / 256 * 256;
+  CK(cudaStreamSynchronize(ctx->stream));
+  p2p_release(ctx);
+  const size_t bytes = 2 * (size_t)nranks * slot_bytes + 2 * (size_t)nranks * sizeof(unsigned) + 256;
+  CK(cudaMalloc(&ctx->p2p_box, bytes));
+  CK(cudaMemset(ctx->p2p_box, 0, bytes));
+  CK(cudaMalloc(&ctx->p2p_done, sizeof(unsigned)));
+  CK(cudaMemset(ctx->p2p_done, 0, sizeof(unsigned)));
+  CK(cudaMalloc(&ctx->p2p_peers_dev, sizeof(unsigned char*) * (size_t)nranks));
+  ctx->p2p_nranks = nranks; ctx->p2p_rank = rank; ctx->p2p_slot = slot_bytes;
+  if (mailbox_out) *mailbox_out = ctx->p2p_box;
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, ctx->p2p_box) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->err = "sosie_p2p_init: cudaIpcGetMemHandle failed (CUDA IPC not available here); same-process peers can still connect by address";
+      memset(ipc_handle_out, 0, 64);
+      return SOSIE_ERR_CUDA;
+    }
+    memcpy(ipc_handle_out, &h, 64);
+  }
+  return SOSIE_OK;
+}
+
+int sosie_p2p_connect(sosie_ctx* c, const void* ipc_handles, void* const* mailboxes) {
+  NEED(c);
+  if (!ctx->p2p_box) { ctx->err = "sosie_p2p_connect: sosie_p2p_init first"; return SOSIE_ERR_STATE; }
+  if (!ipc_handles && !mailboxes) { ctx->err = "sosie_p2p_connect: IPC handles or mailbox addresses needed"; return SOSIE_ERR_ARG; }
+  const int n = ctx->p2p_nranks;
+  std::vector<unsigned char*> tab((size_t)n, nullptr);
+  for (int r = 0; r < n; r++) {
+    if (r == ctx->p2p_rank) { tab[r] = ctx->p2p_box; continue; }
+    if (mailboxes) { tab[r] = (unsigned char*)mailboxes[r]; continue; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, (const char*)ipc_handles + 64 * (size_t)r, 64);
+    void* q = nullptr;
+    if (cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ctx->err = "sosie_p2p_connect: cudaIpcOpenMemHandle failed (no peer access between the ranks' GPUs, or CUDA IPC not available)";
+      return SOSIE_ERR_CUDA;
+    }
+    ctx->p2p_opened[r] = q;
+    tab[r] = (unsigned char*)q;
+  }
+  for (int r = 0; r < n; r++) if (!tab[r]) { ctx->err = "sosie_p2p_connect: null mailbox address"; return SOSIE_ERR_ARG; }
+  CK(cudaMemcpy(ctx->p2p_peers_dev, tab.data(), sizeof(unsigned char*) * (size_t)n, cudaMemcpyHostToDevice));
+  ctx->p2p_ready = true;
   return SOSIE_OK;
 }
 

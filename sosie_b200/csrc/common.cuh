@@ -105,6 +105,16 @@ struct sosie_ctx {
   void* xchg_user = nullptr;
   int xchg_nranks = 0;
   int xchg_used = 0;            // 1: the last pipelined first call / device-planned mapping took the exchange path
+  // prelude exchange over PEER MEMORY (sosie_p2p_init / sosie_p2p_connect): every rank owns a mailbox its peers write their
+  // records into with plain stores over NVLink -- no collective launch; 2 = the last mapping took this path
+  unsigned char* p2p_box = nullptr;        // this rank's mailbox: [2 parities][nranks][p2p_slot] bytes, then [2][nranks] uint32 flags
+  size_t p2p_slot = 0;
+  int p2p_nranks = 0, p2p_rank = -1;
+  bool p2p_ready = false;
+  unsigned p2p_epoch = 0;
+  void* p2p_opened[256] = {nullptr};       // peers' mailboxes opened through CUDA IPC (closed in sosie_destroy)
+  unsigned char** p2p_peers_dev = nullptr; // device table of the nranks mailbox addresses (own included)
+  unsigned* p2p_done = nullptr;            // block counter of the push kernel
   int (*xchg_dev_fn)(void*, const void*, void*, size_t, void*) = nullptr;   // device-side all-gather (sosie_set_exchange_dev)
   void* xchg_dev_user = nullptr;
   int xchg_dev_nranks = 0;
@@ -332,6 +342,7 @@ int fetch_pair(sosie_ctx* ctx, const void* d1, void* h1, size_t b1, const void* 
 int bilin_materialize_mask(sosie_ctx* ctx);   // fills t_mask with 1 if it is still virtual
 int bilin_map_impl(sosie_ctx* ctx, bool async = false);
 int bilin_map_check(sosie_ctx* ctx);          // delivers the deferred status of sosie_bilin_map_async (one read-back)
+void p2p_destroy(sosie_ctx* ctx);            // capi.cu: frees the peer-memory mailbox, closes the IPC mappings
 int bilin_map_alloc(sosie_ctx* ctx);
 int bilin_map_prelude(sosie_ctx* ctx, MapPlan* pl, int xrow_a, int xrow_b, bool* need_full_x);
 // rows ja..jb (1-based) reduced here, the rest obtained from the other ranks; *undecided: fall back to the full prelude

@@ -802,3 +802,63 @@ def test_index_nearest_ties_on_sorted_axes(gpu, orc, kind):
         bad = np.argwhere(a.view(f"u{a.itemsize}") != b.view(f"u{b.itemsize}"))   # bit patterns: NaN == NaN
         assert bad.size == 0, f"{kind}: {k} differs at {len(bad)} targets, first {bad[:5].tolist()}"
     assert np.array_equal(Z2g.view(np.uint32), Z2o.view(np.uint32))
+
+
+def test_prelude_exchange_over_peer_memory(gpu, orc):
+    """sosie_p2p_init / sosie_p2p_connect: the prelude exchange of row-sharded mappings as one producer and one consumer kernel
+    over peer memory.  Three 'ranks' = three contexts of this process on their own streams, connected by mailbox address (the
+    multi-process form swaps CUDA IPC handles instead); every rank's mapping is enqueued before any is waited for, so the
+    consumers really wait for records that arrive later.  Three rounds (both mailbox parities), full-sphere source and a
+    source that stops short of the target's top rows: merged prelude and mapping rows equal the unsharded ones."""
+    import torch
+
+    import sosie_b200
+    from sosie_b200.shard import row_shard
+    cfg = G.config("E", 0.02)
+    lat_hi = G.regular_latlon(cfg["nxs"], cfg["nys"])[1]
+    world = 3
+    ctxs, streams = [], []
+    try:
+        for r in range(world):
+            c = sosie_b200.Sosie(0)
+            st = torch.cuda.Stream(device=0)
+            c.set_stream(st.cuda_stream)
+            ctxs.append(c); streams.append(st)
+        for src_lat, l_reg in [(cfg["src_lat"], True), (lat_hi[: int(0.74 * cfg["nys"])], False)]:
+            boxes = [c.p2p_init(world, r)[1] for r, c in enumerate(ctxs)]      # (a fresh mailbox: not connected yet)
+            gpu.bilin_set_shard(0, 0)
+            gpu.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], src_lat, cfg["trg_lon"], cfg["trg_lat"], l_reg_src=l_reg)
+            gpu.bilin_map()
+            ref = gpu.bilin_get_map()
+            shards = [row_shard(cfg["nyt"], r, world) for r in range(world)]
+            # warm-up without any exchange (every rank reduces the whole array): all work arrays exist before a consumer waits
+            for r, c in enumerate(ctxs):
+                c.bilin_set_shard(*shards[r])
+                c.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], src_lat, cfg["trg_lon"], cfg["trg_lat"], l_reg_src=l_reg)
+                c.bilin_map_async()
+                c.sync()
+                assert c.exchange_used() == 0
+            for c in ctxs:
+                c.p2p_connect(mailboxes=boxes)
+            for _ in range(3):
+                for r, c in enumerate(ctxs):
+                    c.bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], src_lat, cfg["trg_lon"], cfg["trg_lat"], l_reg_src=l_reg)
+                for c in reversed(ctxs):          # the last rank first: rank 0's consumer is enqueued last, the others wait for it
+                    c.bilin_map_async()
+                for r, c in enumerate(ctxs):
+                    c.sync()
+                    assert c.exchange_used() == 2
+                    j0, j1 = shards[r]
+                    m = c.bilin_get_map()
+                    assert np.array_equal(m["info"], ref["info"]), (m["info"], ref["info"])
+                    for k in ("metrics", "alphabeta"):
+                        assert np.array_equal(m[k][:, j0 - 1:j1], ref[k][:, j0 - 1:j1]), (k, r)
+                    assert np.array_equal(m["ipb"][j0 - 1:j1], ref["ipb"][j0 - 1:j1])
+            # a rank that never shows up: the others report it instead of hanging (bounded wait)
+        ctxs[0].bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"], l_reg_src=True)
+        ctxs[0].bilin_map_async()
+        with pytest.raises(sosie_b200.SosieError, match="did not arrive"):
+            ctxs[0].sync()
+    finally:
+        for c in ctxs:
+            c.close()
