@@ -937,6 +937,7 @@ def run_ours(args):
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
+    p2p_mode = "NCCL all-gather of the ranks' prelude records (device callback)"
     # shard target rows over the ranks
     from sosie_b200.shard import row_shard
     r0, r1 = row_shard(ny2, rank, world)
@@ -963,6 +964,36 @@ def run_ours(args):
         if not os.environ.get("SOSIE_BENCH_NO_EXCHANGE"):
             ctx.set_exchange(world, allgather)
             ctx.set_exchange_dev(world, allgather_dev)
+            # ... or, where the ranks' GPUs can map each other's memory (CUDA IPC + NVLink peer access), with no collective at
+            # all: each rank's record is stored into every rank's mailbox by the kernel that produces it (sosie_p2p_*).  All
+            # ranks take this path or none does (a consensus all-reduce after every step of the set-up).
+            if not os.environ.get("SOSIE_BENCH_NO_P2P"):
+                def agree(flag):
+                    t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int32)
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    return bool(t.item())
+                try:
+                    handle, _ = ctx.p2p_init(world, rank)
+                except sosie_b200.SosieError:
+                    handle = None
+                if agree(handle is not None):
+                    mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+                    allh = torch.empty(64 * world, dtype=torch.uint8, device=dev)
+                    dist.all_gather_into_tensor(allh, mine)
+                    hb = allh.cpu().numpy().tobytes()
+                    try:
+                        ctx.p2p_connect(handles=[hb[64 * q:64 * (q + 1)] for q in range(world)])
+                        connected = True
+                    except sosie_b200.SosieError as e:
+                        sys.stderr.write(f"[bench] rank {rank}: peer-memory exchange not available ({e}); NCCL all-gather instead\n")
+                        connected = False
+                    if agree(connected):
+                        p2p_mode = "peer memory (one producer + one consumer kernel, P2P stores over NVLink, no collective)"
+                    else:
+                        try:
+                            ctx.p2p_init(world, rank)      # a fresh, unconnected mailbox: the callback exchange is used
+                        except sosie_b200.SosieError:
+                            pass
     my_targets = (r1 - r0 + 1) * nx2
 
     ctx.bilin_src_axes_hint(cfg["src_lon"], cfg["src_lat"])   # host copy of the device-resident axes: no read-back in set_grids_dev
@@ -997,6 +1028,7 @@ def run_ours(args):
     e1.record()
     barrier()
     ctx.sync()      # delivers the status of the asynchronous mappings (raises if the reference would have STOPped)
+    dev_step_exchange = ctx.exchange_used()      # 2: the timed steps exchanged their preludes over peer memory
     elapsed_ms = e0.elapsed_time(e1)
     launches = (ctx.launches - l0) / max(1, args.steps)
     # per-kernel durations (CUDA events on the launching stream, inside the timed steps: last step's brackets;
@@ -1143,6 +1175,10 @@ def run_ours(args):
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "kernels": kernels,
             "host_vs_device_path_equal": same,
         }
+        if world > 1:
+            line["prelude_exchange"] = {"device_resident_step": p2p_mode if dev_step_exchange == 2 or "peer memory" not in p2p_mode
+                                        else p2p_mode + " [set up, but the timed mappings did not use it]",
+                                        "exchange_used": dev_step_exchange}
     # ---- records x levels sharded over the ranks (D: 1460 records, C: 372 slabs): every rank takes part
     sharded = None
     if not args.no_others:

@@ -10,3 +10,9 @@ print('N',d['n_gpus'],'value %.4e'%d['value'],'ms %.3f'%d['ms_per_step'],'e2e_ms
       'D',{k:round(v,3) for k,v in o.get('D',{}).get('sharded',{}).items() if isinstance(v,float)},
       'C',{k:round(v,3) for k,v in o.get('C',{}).get('sharded',{}).items() if isinstance(v,float)})
 PY
+python - <<PY
+import json
+t=open('gpurun_out/scale_r02_n$n.json').read(); d=json.loads(t[t.index('{"metric'):].split('\n')[0])
+print('prelude_exchange', d.get('prelude_exchange'))
+PY
+grep -h "peer-memory\|p2p\|IPC" gpurun_out/scale_r02_n$n.err | head -5
