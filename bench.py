@@ -1010,6 +1010,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    barrier()      # the ranks enter the first mapping together: a peer-memory consumer waits a bounded time for its peers' records
     for _ in range(args.warmup):
         step_dev()
     barrier()

@@ -135,7 +135,8 @@ int sosie_set_exchange_dev(sosie_ctx* ctx, int32_t nranks, sosie_allgather_dev_f
  * the nranks * 64 bytes -- or, for contexts of ONE process, with the nranks mailbox addresses.  From then on a sharded
  * sosie_bilin_map[_async] on resident grids writes its prelude record straight into every rank's mailbox and merges the
  * records once all have arrived; it takes precedence over sosie_set_exchange_dev.  Every rank must run the same number of
- * mappings; a record that does not arrive within ~2 s is reported by the next synchronising entry (SOSIE_ERR_STATE).
+ * mappings; a record that does not arrive within ~10 s (SOSIE_P2P_TIMEOUT_MS, read by sosie_p2p_init) is reported by the
+ * next synchronising entry (SOSIE_ERR_STATE).
  * Where CUDA IPC is not available the calls fail with SOSIE_ERR_CUDA and the callback exchange remains.                   */
 int sosie_p2p_init(sosie_ctx* ctx, int32_t nranks, int32_t rank, size_t slot_bytes, void* ipc_handle_out, void** mailbox_out);
 int sosie_p2p_connect(sosie_ctx* ctx, const void* ipc_handles, void* const* mailboxes);

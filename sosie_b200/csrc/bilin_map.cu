@@ -302,8 +302,8 @@ __global__ void k_colpart_combine(int nx, int nchunk, const ColPart* __restrict_
 // flag).  k_xchg_merge is k_prelude_merge on the local mailbox once all nranks flags show the epoch.  Two parities: a
 // rank cannot be two exchanges ahead of a peer (its merge of exchange e+1 needs the peer's push of e+1, which the peer
 // issues after its own merge of e), so the slot it overwrites for e+2 has been consumed.  The consumer's wait is bounded
-// (P2P_SPIN_CYCLES): a peer that never arrives is an error at the next synchronising entry, not a hung GPU.
-#define P2P_SPIN_CYCLES 4000000000LL   // ~2 s at 1.9 GHz
+// (ctx->p2p_spin_cycles: 10 s unless SOSIE_P2P_TIMEOUT_MS says otherwise): a peer that never arrives is an error at the next
+// synchronising entry, not a hung GPU.
 __host__ __device__ inline size_t p2p_flags_offset(int nranks, size_t slot) { return 2 * (size_t)nranks * slot; }
 __global__ void __launch_bounds__(128)
 k_xchg_push(int nx, int nchunk, const ColPart* __restrict__ part, const Prelude* p, int ja, int jb, unsigned char* const* __restrict__ peers,
@@ -347,7 +347,7 @@ __device__ __forceinline__ ColPart ldcg_colpart(const ColPart* q) {   // L2 only
   return c;
 }
 __global__ void __launch_bounds__(256)
-k_xchg_merge(int nranks, const unsigned char* __restrict__ box, size_t slot, int par, unsigned epoch, int nx, int ny, Prelude* p) {
+k_xchg_merge(int nranks, const unsigned char* __restrict__ box, size_t slot, int par, unsigned epoch, int nx, int ny, Prelude* p, long long spin_cycles) {
   __shared__ int order[256];
   __shared__ int bad;
   const unsigned char* all = box + (size_t)par * nranks * slot;
@@ -357,7 +357,7 @@ k_xchg_merge(int nranks, const unsigned char* __restrict__ box, size_t slot, int
     const long long t0 = clock64();
     for (int r = 0; r < nranks && !bad; r++)
       while (flags[r] != epoch) {
-        if (clock64() - t0 > P2P_SPIN_CYCLES) { bad = 2; break; }
+        if (clock64() - t0 > spin_cycles) { bad = 2; break; }
         __nanosleep(200);
       }
     __threadfence_system();
@@ -1992,7 +1992,8 @@ static int bilin_map_device_plan(sosie_ctx* ctx, bool async) {
     k_ypass<<<grid_for(ctx, (size_t)tg.nx * nchunk, 256), 256, 0, st>>>(tg, dp, do_dlat, part.p, ja, jb); KLAUNCH_CHECK();
     k_xchg_push<<<cdiv(tg.nx, 128), 128, 0, st>>>(tg.nx, nchunk, part.p, dp, ja, jb, ctx->p2p_peers_dev, ctx->p2p_nranks, ctx->p2p_rank, ctx->p2p_slot,
                                                   par, epoch, ctx->p2p_done); KLAUNCH_CHECK();
-    k_xchg_merge<<<std::max(1, std::min(64, cdiv(tg.nx, 256))), 256, 0, st>>>(ctx->p2p_nranks, ctx->p2p_box, ctx->p2p_slot, par, epoch, tg.nx, tg.ny, dp);
+    k_xchg_merge<<<std::max(1, std::min(64, cdiv(tg.nx, 256))), 256, 0, st>>>(ctx->p2p_nranks, ctx->p2p_box, ctx->p2p_slot, par, epoch, tg.nx, tg.ny, dp,
+                                                                              ctx->p2p_spin_cycles);
     KLAUNCH_CHECK();
     ctx->xchg_used = 2;
   } else if (xchg) {

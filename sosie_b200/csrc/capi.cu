@@ -228,6 +228,8 @@ int sosie_p2p_init(sosie_ctx* c, int32_t nranks, int32_t rank, size_t slot_bytes
   CK(cudaMemset(ctx->p2p_done, 0, sizeof(unsigned)));
   CK(cudaMalloc(&ctx->p2p_peers_dev, sizeof(unsigned char*) * (size_t)nranks));
   ctx->p2p_nranks = nranks; ctx->p2p_rank = rank; ctx->p2p_slot = slot_bytes;
+  ctx->p2p_spin_cycles = 20000000000LL;
+  if (const char* e = getenv("SOSIE_P2P_TIMEOUT_MS")) { const long long ms = atoll(e); if (ms >= 1 && ms <= 600000) ctx->p2p_spin_cycles = ms * 2000000LL; }
   if (mailbox_out) *mailbox_out = ctx->p2p_box;
   if (ipc_handle_out) {
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");

@@ -112,6 +112,7 @@ struct sosie_ctx {
   int p2p_nranks = 0, p2p_rank = -1;
   bool p2p_ready = false;
   unsigned p2p_epoch = 0;
+  long long p2p_spin_cycles = 20000000000LL;   // bound of the consumer's wait (~10 s; SOSIE_P2P_TIMEOUT_MS at sosie_p2p_init)
   void* p2p_opened[256] = {nullptr};       // peers' mailboxes opened through CUDA IPC (closed in sosie_destroy)
   unsigned char** p2p_peers_dev = nullptr; // device table of the nranks mailbox addresses (own included)
   unsigned* p2p_done = nullptr;            // block counter of the push kernel

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, against the CPU oracle on the same
 seeded inputs.  Bars (BASELINE.json north_star): mapping indices / ID_problem bit-exact, alpha/beta and
 fields bit-exact here (the requirement is 1e-12 / 1e-5 relative; FMA-off + pmath makes them equal)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -855,6 +857,13 @@ def test_prelude_exchange_over_peer_memory(gpu, orc):
                         assert np.array_equal(m[k][:, j0 - 1:j1], ref[k][:, j0 - 1:j1]), (k, r)
                     assert np.array_equal(m["ipb"][j0 - 1:j1], ref["ipb"][j0 - 1:j1])
             # a rank that never shows up: the others report it instead of hanging (bounded wait)
+        os.environ["SOSIE_P2P_TIMEOUT_MS"] = "300"
+        try:
+            boxes = [c.p2p_init(world, r)[1] for r, c in enumerate(ctxs)]
+        finally:
+            del os.environ["SOSIE_P2P_TIMEOUT_MS"]
+        for c in ctxs:
+            c.p2p_connect(mailboxes=boxes)
         ctxs[0].bilin_set_grids(cfg["ewper_src"], cfg["src_lon"], cfg["src_lat"], cfg["trg_lon"], cfg["trg_lat"], l_reg_src=True)
         ctxs[0].bilin_map_async()
         with pytest.raises(sosie_b200.SosieError, match="did not arrive"):
