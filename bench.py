@@ -1011,8 +1011,32 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     barrier()      # the ranks enter the first mapping together: a peer-memory consumer waits a bounded time for its peers' records
-    for _ in range(args.warmup):
-        step_dev()
+    warm_ok = True
+    if os.environ.get("SOSIE_BENCH_P2P_TEST_FAIL") and rank == world - 1:
+        time.sleep(1.0)      # test hook (with SOSIE_P2P_TIMEOUT_MS=200): the other ranks' consumers give up, the fallback below is taken
+    try:
+        for _ in range(args.warmup):
+            step_dev()
+        ctx.sync()
+    except sosie_b200.SosieError as e:
+        warm_ok = False
+        sys.stderr.write(f"[bench] rank {rank}: warm-up failed ({e})\n")
+    if world > 1 and "peer memory" in p2p_mode:
+        # a record that did not arrive in time (or any other failure of the peer-memory path) on ANY rank: every rank goes back
+        # to the NCCL callback exchange and warms up again
+        t = torch.tensor([1 if warm_ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if not bool(t.item()):
+            torch.cuda.synchronize()
+            ctx.p2p_init(world, rank)      # a fresh, unconnected mailbox switches the path off
+            p2p_mode = "NCCL all-gather of the ranks' prelude records (device callback) [the peer-memory exchange was set up but failed in the warm-up]"
+            barrier()
+            for _ in range(args.warmup):
+                step_dev()
+            ctx.sync()
+            warm_ok = True
+    if not warm_ok:
+        raise RuntimeError("warm-up failed")
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
