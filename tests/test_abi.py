@@ -94,3 +94,14 @@ def test_mapping_binary_twin_roundtrip(tmp_path):
     import pytest
     with pytest.raises(sosie_b200.SosieError):
         sosie_b200.mapping_read_bin(f)
+
+
+def test_header_is_plain_c(tmp_path):
+    """the drop-in boundary is a C ABI: include/sosie_b200.h compiles as C99 (what cgo / a Fortran interoperability checker /
+    any FFI generator would feed on) and as C++11, with warnings as errors"""
+    import subprocess
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "sosie_b200.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)])
+    subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Werror", "-I", inc, "-fsyntax-only", "-x", "c++", str(src)])
