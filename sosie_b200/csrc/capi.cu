@@ -250,6 +250,10 @@ int sosie_p2p_connect(sosie_ctx* c, const void* ipc_handles, void* const* mailbo
   if (!ctx->p2p_box) { ctx->err = "sosie_p2p_connect: sosie_p2p_init first"; return SOSIE_ERR_STATE; }
   if (!ipc_handles && !mailboxes) { ctx->err = "sosie_p2p_connect: IPC handles or mailbox addresses needed"; return SOSIE_ERR_ARG; }
   const int n = ctx->p2p_nranks;
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->p2p_ready = false;
+  for (int r = 0; r < 256; r++)      // a second connect replaces the first: its IPC mappings are closed, not leaked
+    if (ctx->p2p_opened[r]) { cudaIpcCloseMemHandle(ctx->p2p_opened[r]); ctx->p2p_opened[r] = nullptr; }
   std::vector<unsigned char*> tab((size_t)n, nullptr);
   for (int r = 0; r < n; r++) {
     if (r == ctx->p2p_rank) { tab[r] = ctx->p2p_box; continue; }
